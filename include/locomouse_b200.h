@@ -1,0 +1,165 @@
+/*
+ * locomouse_b200.h — C ABI of the B200-native LocoMouse per-frame detection path.
+ *
+ * This is the drop-in boundary for the hot loop of the reference program
+ * (reference main.cpp:54-82): every entry point below replaces one or more methods of the
+ * reference's `LocoMouse` / `LocoMouse_TM` / `LocoMouse_TM_DE` classes for a *batch* of frames:
+ *
+ *   lm_set_model        <- LocoMouse_Model(file)            LocoMouse_class.cpp:3095-3162, 2941-2990
+ *   lm_set_background   <- LocoMouse::loadBackground        LocoMouse_class.cpp:402-417
+ *   lm_set_calibration  <- LocoMouse::loadCalibration       LocoMouse_class.cpp:419-463
+ *   lm_detect_batch     <- readFrame + cropBoundingBox + detectTail + detectBottomCandidates +
+ *                          detectSideCandidates + matchBottomSideCandidates + storePreviousImage
+ *                          (LocoMouse_class.cpp:1273-1333, LocoMouse_TM.cpp:243-249,
+ *                           1408-1478, 2541-2767, 771-870, 1610-1905, 999-1267, 1508-1513)
+ *
+ * Plain pointers and sizes only; no C++ or torch types. All functions return LM_OK (0) or a
+ * negative lm_status; lm_last_error() gives the message. The host C++ mirror of the reference
+ * classes (locomouse_cpp_b200/host) turns non-zero codes into std::runtime_error /
+ * std::invalid_argument like reference main.cpp:94-101 expects.
+ *
+ * There is no CPU fallback: if no CUDA device is usable lm_create fails.
+ */
+#ifndef LOCOMOUSE_B200_H
+#define LOCOMOUSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LM_ABI_VERSION 1
+
+/* feature / view indices used in every [2] / [3] array below */
+enum { LM_PAW = 0, LM_SNOUT = 1, LM_TAIL = 2 };
+enum { LM_BOTTOM = 0, LM_SIDE = 1 };
+
+typedef enum {
+    LM_OK = 0,
+    LM_ERR_INVALID = -1,   /* bad argument / configuration  (reference: std::invalid_argument) */
+    LM_ERR_RUNTIME = -2,   /* CUDA failure, out of memory   (reference: std::runtime_error)    */
+    LM_ERR_ROI = -3,       /* a frame's bounding box leaves the padded canvas
+                              (reference: uncaught cv::Exception from Mat ROI, class.cpp:1433,1465) */
+    LM_ERR_OVERFLOW = -4,  /* a fixed-capacity list overflowed; see lm_results.flags           */
+    LM_ERR_STATE = -5      /* call order (model/background/calibration not set)                */
+} lm_status;
+
+/* per-frame flag bits in lm_results.flags */
+#define LM_FLAG_DET_OVERFLOW   0x1u  /* > det_cap positive pixels in one (feature, view)        */
+#define LM_FLAG_CAND_OVERFLOW  0x2u  /* > cand_cap candidates after NMS                         */
+#define LM_FLAG_MATCH_OVERFLOW 0x4u  /* > match_cap side matches for one feature                */
+
+/* One detector template = LocoMouse_Feature::w_b / w_s + rho (class.hpp:110-146).
+ * w is row-major float32, rows x cols; the correlation anchor is (cols/2, rows/2)
+ * as in cv::filter2D with anchor (-1,-1) (class.cpp:845,860,2575). */
+typedef struct {
+    const float *w;
+    int32_t rows, cols;
+    double rho;
+} lm_template;
+
+/* Everything the kernels need besides pixel data.  Field <- reference source:            */
+typedef struct {
+    int32_t vid_rows, vid_cols;  /* raw frame / background size      (class.cpp:494-500)   */
+    int32_t n_rows, n_cols;      /* calibrated image = CALIBRATION size (class.cpp:489-490)*/
+    int32_t bb_w;                /* BB_BOTTOM_MOUSE.width == BB_SIDE_MOUSE.width           */
+    int32_t bb_h_bottom;         /* BB_BOTTOM_MOUSE.height                                 */
+    int32_t bb_h_side;           /* BB_SIDE_MOUSE.height (TM: 150, TM_DE: side view height)*/
+    int32_t tail_w;              /* (int)(bb_w * tail_sub_bounding_box)  (class.cpp:711)   */
+    int32_t flip;                /* IMAGE_FLIP: side char 'L'            (class.cpp:465-484)*/
+    int32_t imadjust;            /* 1: LocoMouse_TM::readFrame imadjust(0,0.6,0,1)         */
+    int32_t conn;                /* conn_comp_connectivity 4|8           (class.hpp:53)    */
+    int32_t n_tail_points;       /* N_tail_points = 15                   (class.hpp:86)    */
+    double min_overlap;          /* side_bottom_min_overlap T            (class.hpp:56)    */
+    int32_t fma_mode;            /* 1: acc=fma(w,px,acc)   0: acc=acc+w*px (two roundings, the
+                                    OpenCV direct-path order)                   */
+    int32_t cand_cap;            /* capacity of every candidate list (default 64)          */
+    int32_t det_cap;             /* capacity of every positive-pixel list (default 8192)   */
+    int32_t match_cap;           /* capacity of the side-match pool per feature            */
+} lm_config;
+
+/* Candidate (Candidates.hpp:16-34): Point_<int> p; double s */
+typedef struct {
+    int32_t x, y;
+    double s;
+} lm_cand;
+
+/* Host result buffers, caller-allocated, struct-of-arrays, n = number of frames in the call.
+ * P22D (Candidates.hpp:63-105) for bottom candidate i of feature k in frame f is
+ *   CB = bottom[f][k][i];  its side list = match_y/match_s[f][k][o .. o+match_n[f][k][i])
+ *   with o = sum of match_n[f][k][0..i);  match_n == 0  <=>  the reference's sentinel
+ *   yt[0] = st[0] = -1 ("no side match", Candidates.cpp:40-45,148-156).
+ * number of P22D per frame/feature == n_bottom[f][k] (class.cpp:1154-1251). */
+typedef struct {
+    int64_t n_frames;
+    int32_t cand_cap, match_cap, n_tail_points;
+    int32_t *n_bottom;   /* [n][2]            CANDIDATES_BOTTOM_{PAW,SNOUT}[f].size()        */
+    int32_t *n_side;     /* [n][2]            CANDIDATES_SIDE_{PAW,SNOUT}[f].size()          */
+    lm_cand *bottom;     /* [n][2][cand_cap]                                                 */
+    lm_cand *side;       /* [n][2][cand_cap]                                                 */
+    int32_t *match_n;    /* [n][2][cand_cap]                                                 */
+    int32_t *match_y;    /* [n][2][match_cap]                                                */
+    double *match_s;     /* [n][2][match_cap]                                                */
+    int32_t *tail;       /* [n][3][n_tail_points]   TRACKS_TAIL[f] (x, y, z; -1 = missing)   */
+    uint32_t *flags;     /* [n]                                                              */
+} lm_results;
+
+typedef struct lm_ctx lm_ctx;
+
+/* lifetime ------------------------------------------------------------------------------- */
+int lm_abi_version(void);
+int lm_create(lm_ctx **out, int device);            /* binds a CUDA device, creates streams   */
+int lm_destroy(lm_ctx *ctx);
+const char *lm_last_error(const lm_ctx *ctx);       /* ctx may be NULL: last create error     */
+
+/* per-video state ------------------------------------------------------------------------ */
+int lm_configure(lm_ctx *ctx, const lm_config *cfg);
+/* t[view][feature]: t[LM_BOTTOM][LM_PAW] ... t[LM_SIDE][LM_TAIL] */
+int lm_set_model(lm_ctx *ctx, const lm_template t[2][3]);
+int lm_set_background(lm_ctx *ctx, const uint8_t *bkg);          /* vid_rows*vid_cols u8     */
+int lm_set_calibration(lm_ctx *ctx, const int32_t *ind_warp_mapping); /* n_rows*n_cols i32   */
+
+/* geometry the reference derives in initializeFeatureLoop (class.cpp:655-721), for callers
+ * that want to validate boxes themselves: pads[8] = spre_b.w, spre_b.h, spost_b.w, spost_b.h,
+ * spre_s.w, spre_s.h, spost_s.w, spost_s.h ; canvas[4] = PAD_PRE_COLS, PAD_PRE_ROWS,
+ * PAD_POST_COLS, PAD_POST_ROWS */
+int lm_get_geometry(const lm_ctx *ctx, int32_t pads[8], int32_t canvas[4]);
+
+/* frames --------------------------------------------------------------------------------- *
+ * Frames are raw 8-bit grayscale (channel 0 of the decoded video frame, class.cpp:1293),
+ * contiguous [n][vid_rows][vid_cols].
+ *  - frames            : n frames, host memory (pinned or pageable) or device memory,
+ *                        chosen by frames_on_device.
+ *  - prev_frame        : raw frame that precedes frames[0] in the video, same memory space;
+ *                        required when first_frame_index > 0 (it plays I_PREV_PAD,
+ *                        class.cpp:1469-1470,1510), ignored (may be NULL) otherwise.
+ *  - first_frame_index : CURRENT_FRAME of frames[0]; the velocity check is off for video
+ *                        frame 0 (class.cpp:1009).
+ *  - bb_x, bb_y_side, bb_y_bottom : BB_X_POS / BB_Y_SIDE_POS / BB_Y_BOTTOM_POS for these n
+ *                        frames (bottom-right box corners in calibrated-image coordinates,
+ *                        class.cpp:1411-1423,1457-1458), host memory.
+ * Results are written to the caller's host buffers when the call returns. */
+int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device,
+                    const uint8_t *prev_frame, int64_t n, int64_t first_frame_index,
+                    const uint32_t *bb_x, const uint32_t *bb_y_side, const uint32_t *bb_y_bottom,
+                    lm_results *out);
+
+/* measurement / debugging ---------------------------------------------------------------- */
+/* Device time (ms, CUDA events on the library's own stream) of the stages of the last
+ * lm_detect_batch call, summed over its sub-batches:
+ * ms[0]=min/max  ms[1]=preprocess+crop  ms[2]=correlation  ms[3]=tail  ms[4]=nms  ms[5]=pairing
+ * ms[6]=whole call on the device (first kernel to last D2H).  launches = kernels launched. */
+int lm_last_timing(const lm_ctx *ctx, float ms[7], int64_t *launches);
+
+/* Copies an intermediate of the LAST sub-batch back to the host for parity debugging.
+ * what: 0 = pre-processed bottom window (u8), 1 = side window (u8), 2 = bottom tail mask (u8 0/255,
+ * bb_h_bottom x tail_w), 3 = per-frame min/max (2 x int32). frame is relative to the last call.
+ * Returns the number of bytes written or a negative lm_status. */
+int64_t lm_debug_fetch(lm_ctx *ctx, int what, int64_t frame, void *dst, int64_t dst_bytes,
+                       int32_t dims[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOCOMOUSE_B200_H */

@@ -1,0 +1,75 @@
+/*
+ * lm_oracle.h — CPU oracle for the LocoMouse per-frame detection path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a CPU restatement of the reference algorithm
+ * (careylab/LocoMouse_cpp, file:line cited on every function in lm_oracle.cpp).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it; the
+ * product (locomouse_cpp_b200/) never does.
+ *
+ * PARITY PINNING: the reference ships no tests, golden vectors or fixtures, and cannot be built
+ * here (it needs the OpenCV C++ SDK, which is absent).  The oracle is therefore pinned against
+ * the only executable piece of the reference stack available in this image — OpenCV 4.13 through
+ * python `cv2` — primitive by primitive (tests/test_oracle_vs_cv2.py): filter2D, normalize,
+ * subtract, threshold, LUT, flip, connectedComponentsWithStats, moments; plus hand-derived
+ * known-answer tests for the reference's own loops (nmsMax, peakClustering, matchViews).  The
+ * reference's own control flow has no independent executable check: "parity unpinned" in the
+ * sense of SURVEY.md §8c for those loops.
+ */
+#ifndef LM_ORACLE_H
+#define LM_ORACLE_H
+
+#include "../include/locomouse_b200.h" /* shared POD types only: lm_config, lm_template, lm_results */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Full path for n consecutive frames (same argument meaning as lm_detect_batch, host memory only).
+ * n_threads >= 1 farms frames over std::thread (the reference itself is single threaded).
+ * stage_seconds[6] (optional) accumulates CPU seconds: preprocess, correlation, tail, nms bottom+side,
+ * pairing, total — summed over threads. */
+int lmo_detect(const lm_config *cfg, const lm_template t[2][3], const uint8_t *bkg,
+               const int32_t *calib, const uint8_t *frames, const uint8_t *prev_frame, int64_t n,
+               int64_t first_frame_index, const uint32_t *bb_x, const uint32_t *bb_y_side,
+               const uint32_t *bb_y_bottom, lm_results *out, int n_threads, double *stage_seconds);
+
+/* geometry of initializeFeatureLoop (class.cpp:655-721): same layout as lm_get_geometry */
+int lmo_geometry(const lm_config *cfg, const lm_template t[2][3], int32_t pads[8], int32_t canvas[4]);
+/* 0 if the frame's boxes are valid ROIs of the padded canvas, else -3 (LM_ERR_ROI) */
+int lmo_check_roi(const lm_config *cfg, const lm_template t[2][3], uint32_t bb_x, uint32_t bb_y_side,
+                  uint32_t bb_y_bottom);
+
+/* ---- stage-level entry points, for pinning against cv2 and for known-answer tests ---------- */
+/* readFrame (+imadjust if cfg->imadjust): raw frame -> calibrated image I [n_rows][n_cols];
+ * minmax[2] (optional) returns the min/max of sat(F-BKG). */
+int lmo_preprocess(const lm_config *cfg, const uint8_t *bkg, const int32_t *calib, const uint8_t *frame,
+                   uint8_t *I, int32_t *minmax);
+void lmo_imadjust_lut(double low_in, double high_in, double low_out, double high_out, uint8_t lut[256]);
+/* filter2D(ROI of zero-extended image, CV_32F, K, anchor(-1,-1), delta=-rho, BORDER_CONSTANT):
+ * scores for the w x h window whose top-left is (x0,y0) in image coordinates. */
+void lmo_correlate(const uint8_t *I, int32_t n_rows, int32_t n_cols, const lm_template *t, int32_t x0,
+                   int32_t y0, int32_t w, int32_t h, int32_t fma_mode, float *scores);
+/* nmsMax / peakClustering on a float score map; returns candidate count (uncapped), writes <= cap */
+int lmo_nms_max(const float *scores, int32_t rows, int32_t cols, int32_t box_w, int32_t box_h,
+                lm_cand *out, int32_t cap);
+int lmo_peak_clustering(const float *scores, int32_t rows, int32_t cols, int32_t box_w, int32_t box_h,
+                        lm_cand *out, int32_t cap);
+/* selectLargestRegion: binary u8 (nonzero = foreground) -> u8 0/255 */
+void lmo_largest_region(const uint8_t *bin, int32_t rows, int32_t cols, int32_t conn, uint8_t *out);
+/* detectLineCandidates after binarisation: tail tracks + masks from the two >0 maps */
+void lmo_tail_from_binary(const uint8_t *bin_bottom, int32_t rows_b, const uint8_t *bin_side,
+                          int32_t rows_s, int32_t cols, int32_t conn, int32_t n_points, int32_t *tracks,
+                          uint8_t *tail_mask);
+/* matchingWithVelocityConstraint on given candidate lists. I / Iprev are calibrated images
+ * (pre-processed, [n_rows][n_cols]); (x0,y0b,y0s) the unpadded crop origins in image coordinates.
+ * Returns 0; fills match_n[nb], match_y/match_s (concatenated), *n_match total. */
+int lmo_match_views(const lm_cand *cb, int32_t nb, const lm_cand *cs, int32_t ns, int32_t vel_check,
+                    int32_t tw_b, int32_t th_b, int32_t tw_s, int32_t th_s, double T, const uint8_t *I,
+                    const uint8_t *Iprev, int32_t n_rows, int32_t n_cols, int32_t x0, int32_t y0b,
+                    int32_t y0s, int32_t *match_n, int32_t *match_y, double *match_s, int32_t match_cap,
+                    int32_t *n_match);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,203 @@
+"""ctypes wrapper of the CPU oracle (oracle/liblm_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Nothing under locomouse_cpp_b200/ may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from locomouse_cpp_b200.types import (CAND_DTYPE, Config, Model, Results, lm_config, lm_results, lm_template)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liblm_oracle.so")
+_lib = None
+
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
+_u32p = C.POINTER(C.c_uint32)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with oracle/Makefile if the .so is missing or older than its sources."""
+    srcs = [os.path.join(_HERE, "lm_oracle.cpp"), os.path.join(_HERE, "lm_oracle.h"),
+            os.path.join(_HERE, "..", "include", "locomouse_b200.h")]
+    stale = force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs if os.path.exists(s))
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "-B", "liblm_oracle.so"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.lmo_detect.restype = C.c_int
+        L.lmo_detect.argtypes = [C.POINTER(lm_config), C.c_void_p, _u8p, _i32p, _u8p, _u8p, C.c_int64, C.c_int64,
+                                 _u32p, _u32p, _u32p, C.POINTER(lm_results), C.c_int, _f64p]
+        L.lmo_geometry.restype = C.c_int
+        L.lmo_geometry.argtypes = [C.POINTER(lm_config), C.c_void_p, _i32p, _i32p]
+        L.lmo_check_roi.restype = C.c_int
+        L.lmo_check_roi.argtypes = [C.POINTER(lm_config), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.lmo_preprocess.restype = C.c_int
+        L.lmo_preprocess.argtypes = [C.POINTER(lm_config), _u8p, _i32p, _u8p, _u8p, _i32p]
+        L.lmo_imadjust_lut.restype = None
+        L.lmo_imadjust_lut.argtypes = [C.c_double] * 4 + [_u8p]
+        L.lmo_correlate.restype = None
+        L.lmo_correlate.argtypes = [_u8p, C.c_int32, C.c_int32, C.POINTER(lm_template), C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_int32, C.c_int32, _f32p]
+        for fn in (L.lmo_nms_max, L.lmo_peak_clustering):
+            fn.restype = C.c_int
+            fn.argtypes = [_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
+        L.lmo_largest_region.restype = None
+        L.lmo_largest_region.argtypes = [_u8p, C.c_int32, C.c_int32, C.c_int32, _u8p]
+        L.lmo_tail_from_binary.restype = None
+        L.lmo_tail_from_binary.argtypes = [_u8p, C.c_int32, _u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                           _i32p, _u8p]
+        L.lmo_match_views.restype = C.c_int
+        L.lmo_match_views.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_double, _u8p, _u8p, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, _f64p,
+                                      C.c_int32, _i32p]
+        _lib = L
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a
+
+
+def detect(cfg: Config, model: Model, bkg, calib, frames, bb_x, bb_y_side, bb_y_bottom, prev_frame=None,
+           first_frame_index: int = 0, n_threads: int = 1, stage_seconds=None) -> Results:
+    """Oracle run of the whole path on host arrays; same argument meaning as Detector.detect_batch."""
+    frames = _u8(frames)
+    n = frames.shape[0]
+    bkg = _u8(bkg)
+    calib = np.ascontiguousarray(calib, dtype=np.int32)
+    bb_x = np.ascontiguousarray(bb_x, dtype=np.uint32)
+    bb_y_side = np.ascontiguousarray(bb_y_side, dtype=np.uint32)
+    bb_y_bottom = np.ascontiguousarray(bb_y_bottom, dtype=np.uint32)
+    prev = _u8(prev_frame) if prev_frame is not None else None
+    res = Results(n, cfg.cand_cap, cfg.match_cap, cfg.n_tail_points)
+    c = cfg.to_c()
+    t = model.to_c()
+    r = res.to_c()
+    st = np.zeros(6, np.float64)
+    rc = lib().lmo_detect(C.byref(c), C.cast(t, C.c_void_p), _p(bkg, _u8p), _p(calib, _i32p), _p(frames, _u8p),
+                          _p(prev, _u8p), n, first_frame_index, _p(bb_x, _u32p), _p(bb_y_side, _u32p),
+                          _p(bb_y_bottom, _u32p), C.byref(r), n_threads, _p(st, _f64p))
+    if stage_seconds is not None:
+        stage_seconds[:] = st
+    res.rc = rc
+    if rc not in (0, -4):
+        raise RuntimeError(f"oracle lmo_detect failed: {rc}")
+    return res
+
+
+def geometry(cfg: Config, model: Model):
+    pads = np.zeros(8, np.int32)
+    canvas = np.zeros(4, np.int32)
+    c, t = cfg.to_c(), model.to_c()
+    rc = lib().lmo_geometry(C.byref(c), C.cast(t, C.c_void_p), _p(pads, _i32p), _p(canvas, _i32p))
+    assert rc == 0
+    return pads, canvas
+
+
+def check_roi(cfg: Config, model: Model, bb_x, bb_y_side, bb_y_bottom) -> int:
+    c, t = cfg.to_c(), model.to_c()
+    return lib().lmo_check_roi(C.byref(c), C.cast(t, C.c_void_p), int(bb_x), int(bb_y_side), int(bb_y_bottom))
+
+
+def preprocess(cfg: Config, bkg, calib, frame):
+    bkg, frame = _u8(bkg), _u8(frame)
+    calib = np.ascontiguousarray(calib, dtype=np.int32)
+    out = np.zeros((cfg.n_rows, cfg.n_cols), np.uint8)
+    mm = np.zeros(2, np.int32)
+    c = cfg.to_c()
+    lib().lmo_preprocess(C.byref(c), _p(bkg, _u8p), _p(calib, _i32p), _p(frame, _u8p), _p(out, _u8p), _p(mm, _i32p))
+    return out, mm
+
+
+def imadjust_lut(low_in=0.0, high_in=0.6, low_out=0.0, high_out=1.0):
+    lut = np.zeros(256, np.uint8)
+    lib().lmo_imadjust_lut(low_in, high_in, low_out, high_out, _p(lut, _u8p))
+    return lut
+
+
+def correlate(I, w, rho, x0, y0, width, height, fma_mode=True):
+    I = _u8(I)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    t = lm_template(w.ctypes.data_as(_f32p), w.shape[0], w.shape[1], float(rho))
+    out = np.zeros((height, width), np.float32)
+    lib().lmo_correlate(_p(I, _u8p), I.shape[0], I.shape[1], C.byref(t), x0, y0, width, height, int(fma_mode),
+                        _p(out, _f32p))
+    return out
+
+
+def _nms(fn, scores, box_w, box_h, cap):
+    scores = np.ascontiguousarray(scores, dtype=np.float32)
+    out = np.zeros(cap, CAND_DTYPE)
+    n = fn(_p(scores, _f32p), scores.shape[0], scores.shape[1], box_w, box_h, out.ctypes.data, cap)
+    return [(int(c["x"]), int(c["y"]), float(c["s"])) for c in out[: min(n, cap)]], n
+
+
+def nms_max(scores, box_w, box_h, cap=4096):
+    return _nms(lib().lmo_nms_max, scores, box_w, box_h, cap)[0]
+
+
+def peak_clustering(scores, box_w, box_h, cap=4096):
+    return _nms(lib().lmo_peak_clustering, scores, box_w, box_h, cap)[0]
+
+
+def largest_region(binary, conn=8):
+    b = _u8(binary)
+    out = np.zeros_like(b)
+    lib().lmo_largest_region(_p(b, _u8p), b.shape[0], b.shape[1], conn, _p(out, _u8p))
+    return out
+
+
+def tail_from_binary(bin_bottom, bin_side, conn=8, n_points=15):
+    bb, bs = _u8(bin_bottom), _u8(bin_side)
+    assert bb.shape[1] == bs.shape[1]
+    tracks = np.zeros((3, n_points), np.int32)
+    mask = np.zeros_like(bb)
+    lib().lmo_tail_from_binary(_p(bb, _u8p), bb.shape[0], _p(bs, _u8p), bs.shape[0], bb.shape[1], conn, n_points,
+                               _p(tracks, _i32p), _p(mask, _u8p))
+    return tracks, mask
+
+
+def match_views(cb, cs, vel_check, tsize_b, tsize_s, T, I=None, Iprev=None, x0=0, y0b=0, y0s=0, match_cap=1024):
+    """cb / cs: lists of (x, y, s); tsize_* = (cols, rows) of the feature's templates."""
+    a = np.array([tuple(c) for c in cb], CAND_DTYPE) if len(cb) else np.zeros(0, CAND_DTYPE)
+    b = np.array([tuple(c) for c in cs], CAND_DTYPE) if len(cs) else np.zeros(0, CAND_DTYPE)
+    if I is None:
+        I = np.zeros((1, 1), np.uint8)
+    if Iprev is None:
+        Iprev = np.zeros_like(I)
+    I, Iprev = _u8(I), _u8(Iprev)
+    mn = np.zeros(max(len(cb), 1), np.int32)
+    my = np.full(match_cap, -1, np.int32)
+    ms = np.full(match_cap, -1.0, np.float64)
+    nm = np.zeros(1, np.int32)
+    lib().lmo_match_views(a.ctypes.data, len(cb), b.ctypes.data, len(cs), int(vel_check), tsize_b[0], tsize_b[1],
+                          tsize_s[0], tsize_s[1], float(T), _p(I, _u8p), _p(Iprev, _u8p), I.shape[0], I.shape[1],
+                          x0, y0b, y0s, _p(mn, _i32p), _p(my, _i32p), _p(ms, _f64p), match_cap, _p(nm, _i32p))
+    out, o = [], 0
+    for i in range(len(cb)):
+        m = int(mn[i])
+        out.append([(int(my[o + j]), float(ms[o + j])) for j in range(m)])
+        o += m
+    return out

@@ -1,0 +1,379 @@
+// k_corr.cu — template correlation (the dominant kernel; FP32-FMA bound).
+//
+// Replaces the six cv::filter2D calls of the reference hot loop (LocoMouse_class.cpp:845, 860,
+// 2575-2576) plus the score consumers that directly follow them: threshold(>0) of the tail scores
+// (2593-2594), `setTo(0, mask)` with mask = px <= 25 (782, 817, 849, 864) and the row-major scan
+// for positive detections (1638-1648, 1776-1786).
+//
+// Numerics contract (oracle/lm_oracle.cpp correlate_rows): every output pixel owns ONE
+// fp32 accumulator initialised to float(-rho) and visits the taps in row-major order; FMA mode
+// rounds once per tap (FFMA), the other mode twice (FMUL + FADD).  One thread owns a TY x TX patch
+// of outputs, so the per-output operation order is exactly the oracle's -> bit-exact scores.
+//
+// Mapping: a "task" is one TY x TX output patch; the tasks of one (view, template) box are numbered
+// row-major and dealt to CTAs 256 at a time, so every warp but the last of a box has 32 busy lanes.
+// The CTA stages the window rows it needs (u8 -> fp32, full box width + halo) in shared memory
+// once, next to the zero-padded template; the inner loop then issues only LDS.128 + FFMA:
+// TY*KW*TX FFMA per (TX+KW-1)/4 pixel LDS.128 and TY*KW/4 weight LDS.128 (broadcast).
+#include "lm_internal.h"
+
+namespace {
+
+constexpr int CORR_THREADS = 256;
+
+struct CorrJob {
+    int view, feat, is_tail;
+    int out_w, out_h;        // outputs computed: bb_w (or tail_w) x box_h
+    int ngx, ntasks;         // column groups, total tasks
+    int cta_begin, ncta;     // CTA range inside a frame's block of CTAs
+    int off_x, off_y;        // window column/row of tap (0,0) for output (0,0): halo - anchor
+    int kh, kwp4;            // template rows, smem row stride (floats)
+    int pitch;               // smem tile pitch (floats)
+    int ax, ay;
+    float init;
+    const float *w;          // device template, row stride kwp4? no: kwp (see LmTemplateDev)
+    int w_stride;
+};
+
+struct CorrParams {
+    CorrJob job[6];
+    int njobs;
+    int ctas_per_frame;
+    int B;
+    int det_cap;
+    int box_w[2];            // bb_w per view (index space of LmDet.idx)
+    int win_w[2], win_h[2], win_pitch[2];
+    int64_t win_stride[2];
+    const uint8_t *win[2];
+    uint8_t *tailbin[2];
+    int tail_pitch;
+    int64_t tailbin_stride[2];
+    LmDet *det;
+    int32_t *det_count;
+};
+
+template <int KW, int TX, int TY, bool FMA>
+__global__ void __launch_bounds__(CORR_THREADS, (KW <= 32) ? 2 : 1) k_corr(const __grid_constant__ CorrParams P) {
+    constexpr int NP = ((TX + KW - 1 + 3) / 4) * 4;  // pixel registers per tile row (multiple of 4)
+    constexpr int KW4 = ((KW + 3) / 4) * 4;
+    extern __shared__ __align__(16) float smem[];
+
+    const int f = blockIdx.x / P.ctas_per_frame;
+    const int c = blockIdx.x - f * P.ctas_per_frame;
+    int ji = 0;
+#pragma unroll
+    for (int q = 1; q < 6; ++q)
+        if (q < P.njobs && c >= P.job[q].cta_begin) ji = q;
+    const CorrJob &J = P.job[ji];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int first_task = (c - J.cta_begin) * CORR_THREADS;
+    const int ntask_cta = min(CORR_THREADS, J.ntasks - first_task);
+    const int rg_first = first_task / J.ngx;
+    const int rg_last = (first_task + ntask_cta - 1) / J.ngx;
+    const int tile_rows = (rg_last - rg_first + 1) * TY + J.kh - 1;
+    const int pitch = J.pitch;
+
+    float *wsm = smem;                       // [kh][KW4]
+    float *tile = smem + J.kh * KW4;         // [tile_rows][pitch]
+
+    // ---- stage template (zero padded to KW4) and window rows (u8 -> f32) -------------------------
+    for (int idx = tid; idx < J.kh * KW4; idx += CORR_THREADS) {
+        int j = idx / KW4, i = idx - j * KW4;
+        wsm[idx] = (i < J.w_stride) ? J.w[j * J.w_stride + i] : 0.f;
+    }
+    {
+        const int v = J.view;
+        const uint8_t *wbase = P.win[v] + (int64_t)f * P.win_stride[v];
+        const int win_w = P.win_w[v], win_h = P.win_h[v], wp = P.win_pitch[v];
+        const int row0 = rg_first * TY + J.off_y;
+        const int p4 = pitch >> 2;
+        for (int r = warp; r < tile_rows; r += CORR_THREADS / 32) {
+            const int wr = row0 + r;
+            const bool rok = (wr >= 0) && (wr < win_h);
+            const uint8_t *src = wbase + (int64_t)wr * wp;
+            float4 *dst = reinterpret_cast<float4 *>(tile + r * pitch);
+            for (int c4 = lane; c4 < p4; c4 += 32) {
+                const int wc = J.off_x + c4 * 4;
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rok) {
+                    if (((wc & 3) == 0) && wc >= 0 && wc + 4 <= wp) {
+                        // window rows are zero padded up to the pitch, so a full word is always valid
+                        uint32_t u = *reinterpret_cast<const uint32_t *>(src + wc);
+                        o.x = (float)(u & 0xff);
+                        o.y = (float)((u >> 8) & 0xff);
+                        o.z = (float)((u >> 16) & 0xff);
+                        o.w = (float)(u >> 24);
+                    } else {
+                        float t4[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            int cc = wc + q;
+                            t4[q] = (cc >= 0 && cc < win_w) ? (float)src[cc] : 0.f;
+                        }
+                        o = make_float4(t4[0], t4[1], t4[2], t4[3]);
+                    }
+                }
+                dst[c4] = o;
+            }
+        }
+    }
+    __syncthreads();
+    if (warp * 32 >= ntask_cta) return;  // idle warps of the last CTA of a box
+
+    const bool active = tid < ntask_cta;
+    const int task = first_task + (active ? tid : 0);
+    const int rg = task / J.ngx;
+    const int cg = task - rg * J.ngx;
+    const int rbase = (rg - rg_first) * TY;
+
+    float acc[TY][TX];
+#pragma unroll
+    for (int t = 0; t < TY; ++t)
+#pragma unroll
+        for (int k = 0; k < TX; ++k) acc[t][k] = J.init;
+
+    const float *prow = tile + rbase * pitch + cg * TX;
+    const int nr = J.kh + TY - 1;
+    const int kh = J.kh;
+    for (int r = 0; r < nr; ++r) {
+        float p[NP];
+        const float4 *src = reinterpret_cast<const float4 *>(prow + r * pitch);
+#pragma unroll
+        for (int q = 0; q < NP / 4; ++q) {
+            float4 v = src[q];
+            p[4 * q + 0] = v.x;
+            p[4 * q + 1] = v.y;
+            p[4 * q + 2] = v.z;
+            p[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int t = 0; t < TY; ++t) {
+            const int j = r - t;
+            if (j >= 0 && j < kh) {
+                const float4 *wr = reinterpret_cast<const float4 *>(wsm + j * KW4);
+                float wv[KW4];
+#pragma unroll
+                for (int q = 0; q < KW4 / 4; ++q) {
+                    float4 v = wr[q];
+                    wv[4 * q + 0] = v.x;
+                    wv[4 * q + 1] = v.y;
+                    wv[4 * q + 2] = v.z;
+                    wv[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int i = 0; i < KW; ++i) {
+#pragma unroll
+                    for (int k = 0; k < TX; ++k) {
+                        if (FMA)
+                            acc[t][k] = __fmaf_rn(wv[i], p[i + k], acc[t][k]);
+                        else
+                            acc[t][k] = __fadd_rn(acc[t][k], __fmul_rn(wv[i], p[i + k]));
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- epilogue ------------------------------------------------------------------------------------
+    const int x0 = cg * TX, y0 = rg * TY;
+    if (J.is_tail) {
+        if (!active) return;
+        uint8_t *tb = P.tailbin[J.view] + (int64_t)f * P.tailbin_stride[J.view];
+#pragma unroll
+        for (int t = 0; t < TY; ++t) {
+            const int y = y0 + t;
+            if (y >= J.out_h) continue;
+#pragma unroll
+            for (int k = 0; k < TX; ++k) {
+                const int x = x0 + k;
+                if (x < J.out_w) tb[(int64_t)y * P.tail_pitch + x] = acc[t][k] > 0.f ? 1 : 0;
+            }
+        }
+        return;
+    }
+    // paw / snout: positives that are not masked by (px <= 25); TAIL_MASK is applied by the NMS kernel
+    unsigned hit = 0;  // bit t*TX+k
+    int cnt = 0;
+    if (active) {
+#pragma unroll
+        for (int t = 0; t < TY; ++t) {
+            const int y = y0 + t;
+#pragma unroll
+            for (int k = 0; k < TX; ++k) {
+                const int x = x0 + k;
+                if (y < J.out_h && x < J.out_w && acc[t][k] > 0.f) {
+                    const float centre = tile[(rbase + t + J.ay) * pitch + x + J.ax];
+                    if (centre > 25.f) {
+                        hit |= 1u << (t * TX + k);
+                        ++cnt;
+                    }
+                }
+            }
+        }
+    }
+    static_assert(TX * TY <= 32, "hit mask is 32 bits");
+    const unsigned any = __ballot_sync(0xffffffffu, cnt > 0);
+    if (!any) return;
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int list = (f * 2 + J.feat) * 2 + J.view;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(&P.det_count[list], total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    int o = base + incl - cnt;
+    LmDet *out = P.det + (int64_t)list * P.det_cap;
+    const int bw = P.box_w[J.view];
+#pragma unroll
+    for (int t = 0; t < TY; ++t)
+#pragma unroll
+        for (int k = 0; k < TX; ++k)
+            if (hit & (1u << (t * TX + k))) {
+                if (o < P.det_cap) {
+                    LmDet d;
+                    d.idx = (uint32_t)((y0 + t) * bw + x0 + k);
+                    d.score = acc[t][k];
+                    out[o] = d;
+                }
+                ++o;
+            }
+}
+
+constexpr int kTX = 8, kTY = 4;
+const int kKwp[] = {8, 16, 24, 30, 32, 48, 60, 64};
+
+template <int KW>
+cudaError_t launch_kw(const CorrParams &P, size_t smem, bool fma, cudaStream_t s) {
+    auto kf = k_corr<KW, kTX, kTY, true>;
+    auto km = k_corr<KW, kTX, kTY, false>;
+    cudaError_t e;
+    if (fma) {
+        e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kf<<<P.B * P.ctas_per_frame, CORR_THREADS, smem, s>>>(P);
+    } else {
+        e = cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        km<<<P.B * P.ctas_per_frame, CORR_THREADS, smem, s>>>(P);
+    }
+    return cudaGetLastError();
+}
+
+size_t job_smem(const CorrJob &J) {
+    // worst case rows: a CTA's 256 tasks span at most ceil(255 / ngx) + 1 row groups
+    int rgs = (CORR_THREADS - 1) / J.ngx + 2;
+    int total_rg = (J.out_h + kTY - 1) / kTY;
+    if (rgs > total_rg) rgs = total_rg;
+    size_t rows = (size_t)rgs * kTY + J.kh - 1;
+    return ((size_t)J.kh * J.kwp4 + rows * J.pitch) * sizeof(float);
+}
+
+CorrJob make_job(const LmBatch &b, int view, int feat, int kwp) {
+    const LmTemplateDev &T = b.tmpl[view][feat];
+    const LmView &V = b.view[view];
+    CorrJob J{};
+    J.view = view;
+    J.feat = feat;
+    J.is_tail = (feat == LM_TAIL);
+    J.out_w = J.is_tail ? b.tail_w : V.box_w;
+    J.out_h = V.box_h;
+    J.ngx = (J.out_w + kTX - 1) / kTX;
+    int ngy = (J.out_h + kTY - 1) / kTY;
+    J.ntasks = J.ngx * ngy;
+    J.ncta = (J.ntasks + CORR_THREADS - 1) / CORR_THREADS;
+    J.off_x = V.halo_x - T.ax;
+    J.off_y = V.halo_y - T.ay;
+    J.kh = T.kh;
+    J.kwp4 = ((kwp + 3) / 4) * 4;
+    int np = ((kTX + kwp - 1 + 3) / 4) * 4;
+    J.pitch = (J.ngx - 1) * kTX + np;
+    J.ax = T.ax;
+    J.ay = T.ay;
+    J.init = T.init;
+    J.w = T.w;
+    J.w_stride = T.kwp;
+    return J;
+}
+
+}  // namespace
+
+int lm_corr_kwp(int kw) {
+    for (int v : kKwp)
+        if (v >= kw) return v;
+    return -1;
+}
+
+size_t lm_corr_smem_bytes(const LmBatch &b, int view, int feat) {
+    int kwp = lm_corr_kwp(b.tmpl[view][feat].kw);
+    if (kwp < 0) return (size_t)-1;
+    CorrJob J = make_job(b, view, feat, kwp);
+    return job_smem(J);
+}
+
+// One launch per distinct padded kernel width; all (view, template) boxes that share it ride in the
+// same grid so the tail of one box overlaps the head of the next.
+int lm_launch_corr(const LmBatch &b, cudaStream_t s) {
+    int launches = 0;
+    bool done[2][3] = {};
+    for (int v0 = 0; v0 < 2; ++v0)
+        for (int k0 = 0; k0 < 3; ++k0) {
+            if (done[v0][k0]) continue;
+            const int kwp = lm_corr_kwp(b.tmpl[v0][k0].kw);
+            CorrParams P{};
+            size_t smem = 0;
+            int cta = 0;
+            for (int v = 0; v < 2; ++v)
+                for (int k = 0; k < 3; ++k) {
+                    if (done[v][k] || lm_corr_kwp(b.tmpl[v][k].kw) != kwp) continue;
+                    if (k == LM_TAIL && b.tail_w <= 0) {
+                        done[v][k] = true;
+                        continue;
+                    }
+                    CorrJob J = make_job(b, v, k, kwp);
+                    J.cta_begin = cta;
+                    cta += J.ncta;
+                    size_t sm = job_smem(J);
+                    if (sm > smem) smem = sm;
+                    P.job[P.njobs++] = J;
+                    done[v][k] = true;
+                }
+            if (!P.njobs) continue;
+            P.ctas_per_frame = cta;
+            P.B = b.B;
+            P.det_cap = b.det_cap;
+            for (int v = 0; v < 2; ++v) {
+                P.box_w[v] = b.view[v].box_w;
+                P.win_w[v] = b.view[v].win_w;
+                P.win_h[v] = b.view[v].win_h;
+                P.win_pitch[v] = b.view[v].win_pitch;
+                P.win_stride[v] = b.view[v].win_stride;
+                P.win[v] = b.win[v];
+                P.tailbin[v] = b.tailbin[v];
+                P.tailbin_stride[v] = (int64_t)b.bb_h[v] * b.tail_pitch;
+            }
+            P.tail_pitch = b.tail_pitch;
+            P.det = b.det;
+            P.det_count = b.det_count;
+            cudaError_t e = cudaSuccess;
+            const bool fma = b.fma_mode != 0;
+            switch (kwp) {
+                case 8: e = launch_kw<8>(P, smem, fma, s); break;
+                case 16: e = launch_kw<16>(P, smem, fma, s); break;
+                case 24: e = launch_kw<24>(P, smem, fma, s); break;
+                case 30: e = launch_kw<30>(P, smem, fma, s); break;
+                case 32: e = launch_kw<32>(P, smem, fma, s); break;
+                case 48: e = launch_kw<48>(P, smem, fma, s); break;
+                case 60: e = launch_kw<60>(P, smem, fma, s); break;
+                case 64: e = launch_kw<64>(P, smem, fma, s); break;
+                default: e = cudaErrorInvalidValue;
+            }
+            if (e != cudaSuccess) return -1;
+            ++launches;
+        }
+    return launches;
+}

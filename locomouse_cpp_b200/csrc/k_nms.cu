@@ -1,0 +1,279 @@
+// k_nms.cu — candidate extraction from the positive-pixel lists: one CTA per (frame, feature).
+//
+//  k_nms_bottom = nmsMax          (LocoMouse_class.cpp:1610-1747) after detectPointCandidatesBottom's
+//                                  tail masking (783, 849)
+//  k_nms_side   = peakClustering  (LocoMouse_class.cpp:1749-1905), skipped when the feature's bottom
+//                                  list is empty (820, 828)
+//
+// Common front end: drop tail-masked pixels (bottom only), build 64-bit keys
+// (~score_bits << 32 | pixel index) and bitonic-sort them in shared memory: ascending key order ==
+// score descending, row-major index ascending == the oracle's total order.
+//
+// nmsMax's chain suppression (discarded detections keep suppressing, Q3) is equivalent to
+//   parent(j) = the best-ranked i < j whose box overlaps j's by more than 0.5, root = parent chain end
+// (j is discarded by the FIRST overlapping i met in rank order, discarded or not, and inherits that
+// i's root), so parents are found independently per detection and roots by pointer chasing.
+// peakClustering is truly greedy: maxima are confirmed one at a time in rank order, each confirmation
+// followed by a parallel sweep that clusters the still-free detections it overlaps.
+// Overlap predicate inter/(2wh - inter) > 0.5  <=>  3*(w-|dx|)*(h-|dy|) > 2*w*h (exact in integers).
+// Cluster sums are accumulated in double IN RANK ORDER by one thread per cluster, as the reference's
+// loops do (1731-1739, 1865-1869), because double addition is not associative.
+#include "lm_internal.h"
+
+namespace {
+
+constexpr int NMS_THREADS = 512;
+
+struct NmsSmem {
+    unsigned long long *key;  // [P]
+    short *x, *y;             // [P]
+    float *s;                 // [P]
+    int *link;                // [P]  parent / root / cluster id
+};
+
+__device__ __forceinline__ NmsSmem carve(unsigned char *base, int P) {
+    NmsSmem m;
+    m.key = reinterpret_cast<unsigned long long *>(base);
+    m.s = reinterpret_cast<float *>(m.key + P);
+    m.link = reinterpret_cast<int *>(m.s + P);
+    m.x = reinterpret_cast<short *>(m.link + P);
+    m.y = m.x + P;
+    return m;
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Loads, filters, sorts.  Returns the number of detections n (<= det_cap); sets *overflow.
+__device__ int load_and_sort(const LmBatch &b, int f, int feat, int view, NmsSmem &m, int P, int *s_n,
+                             bool *overflow) {
+    const int tid = threadIdx.x;
+    const int list = (f * 2 + feat) * 2 + view;
+    int cnt = b.det_count[list];
+    *overflow = cnt > b.det_cap;
+    if (cnt > b.det_cap) cnt = b.det_cap;
+    const LmDet *d = b.det + (int64_t)list * b.det_cap;
+    const int bw = b.bb_w;
+    const uint8_t *tm = (view == LM_BOTTOM && b.tail_w > 0)
+                            ? b.tailmask + (int64_t)f * b.bb_h[LM_BOTTOM] * b.tail_pitch
+                            : nullptr;
+    if (tid == 0) *s_n = 0;
+    for (int i = tid; i < P; i += NMS_THREADS) m.key[i] = ~0ull;
+    __syncthreads();
+    for (int i = tid; i < cnt; i += NMS_THREADS) {
+        LmDet e = d[i];
+        int y = e.idx / bw, x = e.idx - y * bw;
+        if (tm && x < b.tail_w && tm[y * b.tail_pitch + x]) continue;  // setTo(255, TAIL_MASK)
+        int o = atomicAdd(s_n, 1);
+        m.key[o] = ((unsigned long long)(~__float_as_uint(e.score)) << 32) | e.idx;
+    }
+    __syncthreads();
+    const int n = *s_n;
+    const int Q = next_pow2(n < 2 ? 2 : n);
+    for (int k = 2; k <= Q; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < Q; i += NMS_THREADS) {
+                int l = i ^ j;
+                if (l > i) {
+                    unsigned long long a = m.key[i], c = m.key[l];
+                    bool up = (i & k) == 0;
+                    if ((a > c) == up) {
+                        m.key[i] = c;
+                        m.key[l] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = tid; i < n; i += NMS_THREADS) {
+        unsigned long long k = m.key[i];
+        unsigned idx = (unsigned)(k & 0xffffffffu);
+        int y = idx / bw;
+        m.y[i] = (short)y;
+        m.x[i] = (short)(idx - y * bw);
+        m.s[i] = __uint_as_float(~(unsigned)(k >> 32));
+    }
+    __syncthreads();
+    return n;
+}
+
+__device__ __forceinline__ bool overlaps(int dx, int dy, int w, int h, int wh2) {
+    dx = dx < 0 ? -dx : dx;
+    dy = dy < 0 ? -dy : dy;
+    return dx < w && dy < h && 3 * (w - dx) * (h - dy) > wh2;
+}
+
+// One thread per cluster slot accumulates its members in rank order (double) and writes the candidate.
+template <bool HALF_EVEN>
+__device__ void write_candidates(const NmsSmem &m, int n, const int *slot_of_root, int ncand, int cap,
+                                 lm_cand *out, const int *root_rank) {
+    const int tid = threadIdx.x;
+    for (int k = tid; k < cap; k += NMS_THREADS) {
+        lm_cand c;
+        c.x = -1;
+        c.y = -1;
+        c.s = -1.0;
+        if (k < ncand) {
+            double wx = 0.0, wy = 0.0, ss = 0.0;
+            for (int i = 0; i < n; ++i) {
+                if (slot_of_root[m.link[i]] == k) {
+                    const double s = (double)m.s[i];
+                    wx = __dadd_rn(wx, __dmul_rn((double)m.x[i], s));
+                    wy = __dadd_rn(wy, __dmul_rn((double)m.y[i], s));
+                    ss = __dadd_rn(ss, s);
+                }
+            }
+            const double qx = __ddiv_rn(wx, ss), qy = __ddiv_rn(wy, ss);
+            if (HALF_EVEN) {
+                c.x = __double2int_rn(qx);
+                c.y = __double2int_rn(qy);
+            } else {
+                c.x = (int)round(qx);
+                c.y = (int)round(qy);
+            }
+            c.s = (double)m.s[root_rank[k]];
+        }
+        out[k] = c;
+    }
+}
+
+// ---- nmsMax ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NMS_THREADS) k_nms_bottom(const __grid_constant__ LmBatch b, int P) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    NmsSmem m = carve(raw, P);
+    int *slot = reinterpret_cast<int *>(m.y + P);      // [P] slot of a root rank
+    int *root_rank = slot + P;                          // [cand_cap]
+    __shared__ int s_n, s_nc;
+    const int f = blockIdx.x >> 1, feat = blockIdx.x & 1, tid = threadIdx.x;
+    bool overflow;
+    const int n = load_and_sort(b, f, feat, LM_BOTTOM, m, P, &s_n, &overflow);
+    const LmTemplateDev &T = b.tmpl[LM_BOTTOM][feat];
+    const int w = T.kw, h = T.kh, wh2 = 2 * w * h;
+    if (tid == 0) s_nc = 0;
+    // parent = first better-ranked overlapping detection
+    for (int j = tid; j < n; j += NMS_THREADS) {
+        const int xj = m.x[j], yj = m.y[j];
+        int par = j;
+        for (int i = 0; i < j; ++i)
+            if (overlaps(m.x[i] - xj, m.y[i] - yj, w, h, wh2)) {
+                par = i;
+                break;
+            }
+        m.link[j] = par;
+    }
+    __syncthreads();
+    // roots by pointer chasing (parents only point to better ranks, so chains end)
+    for (int j = tid; j < n; j += NMS_THREADS) {
+        int r = j;
+        while (m.link[r] != r) r = m.link[r];
+        slot[j] = r;  // temp: root of j
+    }
+    __syncthreads();
+    for (int j = tid; j < n; j += NMS_THREADS) m.link[j] = slot[j];
+    __syncthreads();
+    // candidate slots = roots in rank order (serial prefix by one warp is enough: n is small)
+    if (tid < 32) {
+        int base = 0;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            int j = j0 + tid;
+            bool is_root = j < n && m.link[j] == j;
+            unsigned bal = __ballot_sync(0xffffffffu, is_root);
+            if (is_root) {
+                int k = base + __popc(bal & ((1u << tid) - 1));
+                slot[j] = k;
+                if (k < b.cand_cap) root_rank[k] = j;
+            }
+            base += __popc(bal);
+        }
+        if (tid == 0) s_nc = base;
+    }
+    __syncthreads();
+    const int nc = s_nc;
+    const int ncw = nc < b.cand_cap ? nc : b.cand_cap;
+    write_candidates<true>(m, n, slot, ncw, b.cand_cap, b.bottom + (int64_t)(f * 2 + feat) * b.cand_cap, root_rank);
+    if (tid == 0) {
+        b.n_bottom[f * 2 + feat] = ncw;
+        unsigned fl = 0;
+        if (overflow) fl |= LM_FLAG_DET_OVERFLOW;
+        if (nc > b.cand_cap) fl |= LM_FLAG_CAND_OVERFLOW;
+        if (fl) atomicOr(&b.flags[f], fl);
+    }
+}
+
+// ---- peakClustering ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NMS_THREADS) k_nms_side(const __grid_constant__ LmBatch b, int P) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    NmsSmem m = carve(raw, P);
+    int *slot = reinterpret_cast<int *>(m.y + P);
+    int *root_rank = slot + P;
+    __shared__ int s_n;
+    const int f = blockIdx.x >> 1, feat = blockIdx.x & 1, tid = threadIdx.x;
+    lm_cand *out = b.side + (int64_t)(f * 2 + feat) * b.cand_cap;
+    if (b.n_bottom[f * 2 + feat] == 0) {  // Q6
+        for (int k = tid; k < b.cand_cap; k += NMS_THREADS) {
+            lm_cand c;
+            c.x = -1;
+            c.y = -1;
+            c.s = -1.0;
+            out[k] = c;
+        }
+        if (tid == 0) b.n_side[f * 2 + feat] = 0;
+        return;
+    }
+    bool overflow;
+    const int n = load_and_sort(b, f, feat, LM_SIDE, m, P, &s_n, &overflow);
+    const LmTemplateDev &T = b.tmpl[LM_SIDE][feat];
+    const int w = T.kw, h = T.kh, wh2 = 2 * w * h;
+    for (int j = tid; j < n; j += NMS_THREADS) m.link[j] = -1;  // -1 = free
+    __syncthreads();
+    int nc = 0;
+    for (int c = 0; c < n; ++c) {
+        if (m.link[c] >= 0) continue;  // already clustered (block-uniform: link only changes at barriers)
+        // c is the next maximum
+        const int xc = m.x[c], yc = m.y[c];
+        __syncthreads();  // everyone has read link[c] before it is written
+        if (tid == 0) {
+            m.link[c] = c;
+            slot[c] = nc;
+            if (nc < b.cand_cap) root_rank[nc] = c;
+        }
+        for (int j = c + 1 + tid; j < n; j += NMS_THREADS)
+            if (m.link[j] < 0 && overlaps(m.x[j] - xc, m.y[j] - yc, w, h, wh2)) m.link[j] = c;
+        ++nc;
+        __syncthreads();
+    }
+    const int ncw = nc < b.cand_cap ? nc : b.cand_cap;
+    write_candidates<false>(m, n, slot, ncw, b.cand_cap, out, root_rank);
+    if (tid == 0) {
+        b.n_side[f * 2 + feat] = ncw;
+        unsigned fl = 0;
+        if (overflow) fl |= LM_FLAG_DET_OVERFLOW;
+        if (nc > b.cand_cap) fl |= LM_FLAG_CAND_OVERFLOW;
+        if (fl) atomicOr(&b.flags[f], fl);
+    }
+}
+
+size_t nms_smem(int P, int cand_cap) {
+    // key 8 + s 4 + link 4 + x 2 + y 2 + slot 4 = 24 bytes per entry
+    return (size_t)P * 24 + (size_t)cand_cap * 4 + 16;
+}
+
+}  // namespace
+
+int lm_launch_nms(const LmBatch &b, cudaStream_t s) {
+    int P = 2;
+    while (P < b.det_cap) P <<= 1;
+    size_t smem = nms_smem(P, b.cand_cap);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_nms_bottom, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_nms_side, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_done = true;
+    }
+    k_nms_bottom<<<b.B * 2, NMS_THREADS, smem, s>>>(b, P);
+    k_nms_side<<<b.B * 2, NMS_THREADS, smem, s>>>(b, P);
+    return 2;
+}

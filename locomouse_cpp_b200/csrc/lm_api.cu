@@ -1,0 +1,610 @@
+// lm_api.cu — the C ABI of include/locomouse_b200.h: context, per-video state, the sub-batch
+// pipeline (H2D of sub-batch k+1 overlaps the kernels of sub-batch k; results return through pinned
+// staging), timing and debug fetches.  No CPU fallback: every entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lm_internal.h"
+
+namespace {
+std::string g_create_error;
+}
+
+struct lm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    lm_config cfg{};
+    bool configured = false, model_set = false, bkg_set = false, calib_set = false;
+    LmGeom geom{};
+    std::string err;
+
+    uint8_t *d_bkg = nullptr;
+    int32_t *d_calib = nullptr;
+    float *d_tmpl[2][3] = {};
+    int t_rows[2][3] = {}, t_cols[2][3] = {};
+    double t_rho[2][3] = {};
+
+    // sub-batch scratch
+    int Bcap = 0;
+    LmBatch bt{};                     // config-derived fields + scratch pointers
+    std::vector<void *> dev_allocs;   // everything cudaMalloc'ed for the scratch
+    uint8_t *d_stage[2] = {};         // staged raw frames (Bcap + 1 each) when frames come from the host
+    uint32_t *d_bb[2] = {};           // [3][Bcap] per slot
+    // result staging
+    struct ResOff {
+        size_t n_bottom, n_side, bottom, side, match_n, match_y, match_s, tail, flags, total;
+    } ro{};
+    uint8_t *d_res = nullptr;         // device results for one sub-batch
+    uint8_t *h_res[2] = {};           // pinned
+    cudaEvent_t ev_h2d[2] = {}, ev_done[2] = {};
+    cudaEvent_t ev_stage[2][8] = {};
+    float ms[7] = {};
+    int64_t launches = 0;
+    int last_B = 0;                   // size of the last sub-batch (for lm_debug_fetch)
+    int64_t last_s0 = 0;
+};
+
+namespace {
+
+int fail(lm_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c)
+        c->err = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(ctx, LM_ERR_RUNTIME, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                      \
+    } while (0)
+
+int ceil_half(int v) { return (int)std::ceil((double)v / 2.0); }
+
+// LocoMouse_Model ctor (class.cpp:3157-3161) + move-assignment quirk (3172-3173) +
+// initializeFeatureLoop (672-682)
+void make_geom(lm_ctx *c) {
+    LmGeom &g = c->geom;
+    int mbw = std::max(c->t_cols[0][0], c->t_cols[0][1]) - 1, mbh = std::max(c->t_rows[0][0], c->t_rows[0][1]) - 1;
+    int msw = std::max(c->t_cols[1][0], c->t_cols[1][1]) - 1, msh = std::max(c->t_rows[1][0], c->t_rows[1][1]) - 1;
+    g.spre_b_w = ceil_half(mbw);
+    g.spre_b_h = ceil_half(mbh);
+    g.spre_s_w = ceil_half(msw);
+    g.spre_s_h = ceil_half(msh);
+    g.spost_s_w = msw / 2;
+    g.spost_s_h = msh / 2;
+    g.spost_b_w = g.spre_b_w;
+    g.spost_b_h = g.spre_b_h;
+    g.pad_pre_rows = std::max(c->cfg.bb_h_side, std::max(g.spre_s_h, g.spre_b_h));
+    g.pad_post_rows = std::max(g.spost_b_h, g.spost_s_h);
+    g.pad_pre_cols = std::max(c->cfg.bb_w, std::max(g.spre_s_w, g.spre_b_w));
+    g.pad_post_cols = std::max(g.spost_b_w, g.spost_s_w);
+}
+
+// cropBoundingBox (class.cpp:1422-1423, 1457-1458) + the cv::Mat ROI assertion the reference relies on
+bool roi_ok(const lm_ctx *c, uint32_t bbx, uint32_t bbys, uint32_t bbyb) {
+    const LmGeom &g = c->geom;
+    const lm_config &k = c->cfg;
+    const int64_t cols = (int64_t)g.pad_pre_cols + k.n_cols + g.pad_post_cols;
+    const int64_t rows = (int64_t)g.pad_pre_rows + k.n_rows + g.pad_post_rows;
+    {
+        int64_t W = g.spre_b_w + k.bb_w + g.spost_b_w, H = g.spre_b_h + k.bb_h_bottom + g.spost_b_h;
+        int64_t x = (int32_t)(bbx + (uint32_t)g.pad_pre_cols - (uint32_t)(W - g.spost_b_w) + 1u);
+        int64_t y = (int32_t)(bbyb + (uint32_t)g.pad_pre_rows - (uint32_t)(H - g.spost_b_h) + 1u);
+        if (x < 0 || y < 0 || x + W > cols || y + H > rows) return false;
+    }
+    {
+        int64_t W = g.spre_s_w + k.bb_w + g.spost_s_w, H = g.spre_s_h + k.bb_h_side + g.spost_s_h;
+        int64_t x = (int32_t)(bbx + (uint32_t)g.pad_pre_cols - (uint32_t)(W - g.spost_s_w) + 1u);
+        int64_t y = (int32_t)(bbys + (uint32_t)g.pad_pre_rows - (uint32_t)(H - g.spost_s_h) + 1u);
+        if (x < 0 || y < 0 || x + W > cols || y + H > rows) return false;
+    }
+    return true;
+}
+
+void free_scratch(lm_ctx *c) {
+    for (void *p : c->dev_allocs) cudaFree(p);
+    c->dev_allocs.clear();
+    for (int s = 0; s < 2; ++s) {
+        if (c->h_res[s]) cudaFreeHost(c->h_res[s]);
+        c->h_res[s] = nullptr;
+        c->d_stage[s] = nullptr;
+        c->d_bb[s] = nullptr;
+    }
+    c->d_res = nullptr;
+    c->Bcap = 0;
+}
+
+template <typename T>
+int dalloc(lm_ctx *ctx, T **p, size_t count) {
+    void *q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 256)));
+    ctx->dev_allocs.push_back(q);
+    *p = reinterpret_cast<T *>(q);
+    return LM_OK;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// derive window geometry + allocate scratch for sub-batches of Bcap frames
+int prepare(lm_ctx *ctx) {
+    if (ctx->Bcap) return LM_OK;
+    const lm_config &k = ctx->cfg;
+    LmBatch &b = ctx->bt;
+    b = LmBatch{};
+    b.vid_rows = k.vid_rows;
+    b.vid_cols = k.vid_cols;
+    b.n_rows = k.n_rows;
+    b.n_cols = k.n_cols;
+    b.frame_bytes = (int64_t)k.vid_rows * k.vid_cols;
+    b.bb_w = k.bb_w;
+    b.bb_h[LM_BOTTOM] = k.bb_h_bottom;
+    b.bb_h[LM_SIDE] = k.bb_h_side;
+    b.tail_w = k.tail_w;
+    b.tail_pitch = std::max(4, (k.tail_w + 3) & ~3);
+    b.flip = k.flip;
+    b.imadjust = k.imadjust;
+    b.conn = k.conn;
+    b.n_tail_points = k.n_tail_points;
+    b.fma_mode = k.fma_mode;
+    b.cand_cap = k.cand_cap;
+    b.det_cap = k.det_cap;
+    b.match_cap = k.match_cap;
+    b.bkg = ctx->d_bkg;
+    b.calib = ctx->d_calib;
+    for (int f = 0; f < 2; ++f) b.ovlp[f] = (int)((double)ctx->t_cols[LM_BOTTOM][f] * (1 - k.min_overlap));
+    for (int v = 0; v < 2; ++v) {
+        LmView &V = b.view[v];
+        V.box_w = k.bb_w;
+        V.box_h = b.bb_h[v];
+        int hx = 0, hy = 0, px = 0, py = 0;
+        for (int f = 0; f < 3; ++f) {
+            LmTemplateDev &T = b.tmpl[v][f];
+            T.w = ctx->d_tmpl[v][f];
+            T.kh = ctx->t_rows[v][f];
+            T.kw = ctx->t_cols[v][f];
+            T.kwp = T.kw;
+            T.ax = T.kw / 2;
+            T.ay = T.kh / 2;
+            T.init = (float)(-ctx->t_rho[v][f]);
+            if (lm_corr_kwp(T.kw) < 0)
+                return fail(ctx, LM_ERR_INVALID, "template wider than %d columns is not supported", LM_MAX_KW);
+            hx = std::max(hx, T.ax);
+            hy = std::max(hy, T.ay);
+            px = std::max(px, T.kw - 1 - T.ax);
+            py = std::max(py, T.kh - 1 - T.ay);
+        }
+        V.halo_x = hx;
+        V.halo_y = hy;
+        V.win_w = V.box_w + hx + px;
+        V.win_h = V.box_h + hy + py;
+        V.win_pitch = (V.win_w + 15) & ~15;
+        V.win_stride = (int64_t)V.win_pitch * V.win_h;
+    }
+    int dev_smem = 0;
+    CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    for (int v = 0; v < 2; ++v)
+        for (int f = 0; f < 3; ++f) {
+            size_t need = lm_corr_smem_bytes(b, v, f);
+            if (need > (size_t)dev_smem)
+                return fail(ctx, LM_ERR_INVALID, "box %d px wide with a %dx%d template needs %zu B of shared memory",
+                            k.bb_w, ctx->t_rows[v][f], ctx->t_cols[v][f], need);
+        }
+
+    int Bcap = 256;
+    if (const char *e = getenv("LM_SUBBATCH")) Bcap = std::max(1, atoi(e));
+    const size_t B = (size_t)Bcap;
+    int rc;
+    if ((rc = dalloc(ctx, &b.minmax, (B + 1) * 2))) return rc;
+    if ((rc = dalloc(ctx, &b.lut, (B + 1) * 256))) return rc;
+    for (int v = 0; v < 2; ++v) {
+        if ((rc = dalloc(ctx, &b.win[v], B * b.view[v].win_stride))) return rc;
+        if ((rc = dalloc(ctx, &b.tailbin[v], B * b.bb_h[v] * b.tail_pitch))) return rc;
+    }
+    if ((rc = dalloc(ctx, &b.tailmask, B * b.bb_h[LM_BOTTOM] * b.tail_pitch))) return rc;
+    if ((rc = dalloc(ctx, &b.sidemask, B * b.bb_h[LM_SIDE] * b.tail_pitch))) return rc;
+    b.cc_stride = (int64_t)std::max(b.bb_h[0], b.bb_h[1]) * std::max(b.tail_w, 1);
+    if ((rc = dalloc(ctx, &b.cc, B * 3 * b.cc_stride))) return rc;
+    if ((rc = dalloc(ctx, &b.det, B * 4 * (size_t)k.det_cap))) return rc;
+    if ((rc = dalloc(ctx, &b.det_count, B * 4))) return rc;
+    for (int s = 0; s < 2; ++s)
+        if ((rc = dalloc(ctx, &ctx->d_bb[s], 3 * B))) return rc;
+    // results: one device block + two pinned host blocks, same sub-array order
+    lm_ctx::ResOff &o = ctx->ro;
+    size_t off = 0;
+    o.n_bottom = off; off = align256(off + B * 2 * 4);
+    o.n_side = off;   off = align256(off + B * 2 * 4);
+    o.bottom = off;   off = align256(off + B * 2 * k.cand_cap * sizeof(lm_cand));
+    o.side = off;     off = align256(off + B * 2 * k.cand_cap * sizeof(lm_cand));
+    o.match_n = off;  off = align256(off + B * 2 * k.cand_cap * 4);
+    o.match_y = off;  off = align256(off + B * 2 * k.match_cap * 4);
+    o.match_s = off;  off = align256(off + B * 2 * k.match_cap * 8);
+    o.tail = off;     off = align256(off + B * 3 * k.n_tail_points * 4);
+    o.flags = off;    off = align256(off + B * 4);
+    o.total = off;
+    if ((rc = dalloc(ctx, &ctx->d_res, o.total))) return rc;
+    for (int s = 0; s < 2; ++s) CK(cudaMallocHost((void **)&ctx->h_res[s], o.total));
+    b.n_bottom = (int32_t *)(ctx->d_res + o.n_bottom);
+    b.n_side = (int32_t *)(ctx->d_res + o.n_side);
+    b.bottom = (lm_cand *)(ctx->d_res + o.bottom);
+    b.side = (lm_cand *)(ctx->d_res + o.side);
+    b.match_n = (int32_t *)(ctx->d_res + o.match_n);
+    b.match_y = (int32_t *)(ctx->d_res + o.match_y);
+    b.match_s = (double *)(ctx->d_res + o.match_s);
+    b.tail = (int32_t *)(ctx->d_res + o.tail);
+    b.flags = (uint32_t *)(ctx->d_res + o.flags);
+    ctx->Bcap = Bcap;
+    return LM_OK;
+}
+
+int ensure_stage(lm_ctx *ctx) {
+    if (ctx->d_stage[0]) return LM_OK;
+    for (int s = 0; s < 2; ++s) {
+        int rc = dalloc(ctx, &ctx->d_stage[s], (size_t)(ctx->Bcap + 1) * ctx->bt.frame_bytes);
+        if (rc) return rc;
+    }
+    return LM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lm_abi_version(void) { return LM_ABI_VERSION; }
+
+const char *lm_last_error(const lm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int lm_create(lm_ctx **out, int device) {
+    lm_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, LM_ERR_INVALID, "lm_create: null output pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(nullptr, LM_ERR_RUNTIME, "no CUDA device: %s (this library has no CPU fallback)",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, LM_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, LM_ERR_RUNTIME, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10)
+        return fail(nullptr, LM_ERR_RUNTIME, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    ctx = new lm_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, LM_ERR_RUNTIME, "cudaStreamCreate failed");
+    }
+    for (int s = 0; s < 2; ++s) {
+        cudaEventCreateWithFlags(&ctx->ev_h2d[s], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_done[s], cudaEventDisableTiming);
+        for (int q = 0; q < 8; ++q) cudaEventCreate(&ctx->ev_stage[s][q]);
+    }
+    *out = ctx;
+    return LM_OK;
+}
+
+int lm_destroy(lm_ctx *ctx) {
+    if (!ctx) return LM_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_scratch(ctx);
+    cudaFree(ctx->d_bkg);
+    cudaFree(ctx->d_calib);
+    for (int v = 0; v < 2; ++v)
+        for (int f = 0; f < 3; ++f) cudaFree(ctx->d_tmpl[v][f]);
+    for (int s = 0; s < 2; ++s) {
+        cudaEventDestroy(ctx->ev_h2d[s]);
+        cudaEventDestroy(ctx->ev_done[s]);
+        for (int q = 0; q < 8; ++q) cudaEventDestroy(ctx->ev_stage[s][q]);
+    }
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+    return LM_OK;
+}
+
+int lm_configure(lm_ctx *ctx, const lm_config *cfg) {
+    if (!ctx) return LM_ERR_INVALID;
+    if (!cfg) return fail(ctx, LM_ERR_INVALID, "lm_configure: null config");
+    const lm_config &k = *cfg;
+    if (k.vid_rows <= 0 || k.vid_cols <= 0 || k.n_rows <= 0 || k.n_cols <= 0)
+        return fail(ctx, LM_ERR_INVALID, "image sizes must be positive");
+    if (k.bb_w <= 0 || k.bb_h_bottom <= 0 || k.bb_h_side <= 0) return fail(ctx, LM_ERR_INVALID, "box sizes must be positive");
+    if (k.tail_w < 0 || k.tail_w > k.bb_w) return fail(ctx, LM_ERR_INVALID, "tail_w must be in [0, bb_w]");
+    if (k.conn != 4 && k.conn != 8) return fail(ctx, LM_ERR_INVALID, "conn_comp_connectivity must be 4 or 8");
+    if (k.n_tail_points <= 0 || k.n_tail_points > 256) return fail(ctx, LM_ERR_INVALID, "n_tail_points out of range");
+    if (k.cand_cap <= 0 || k.cand_cap > 1024 || k.match_cap <= 0 || k.det_cap <= 0 || k.det_cap > 8192)
+        return fail(ctx, LM_ERR_INVALID, "capacities: 0 < cand_cap <= 1024, 0 < det_cap <= 8192, match_cap > 0");
+    if ((int64_t)k.bb_w * std::max(k.bb_h_bottom, k.bb_h_side) >= (1 << 21))
+        return fail(ctx, LM_ERR_INVALID, "box too large for the connected-component key packing");
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_scratch(ctx);
+    cudaFree(ctx->d_bkg);
+    cudaFree(ctx->d_calib);
+    ctx->d_bkg = nullptr;
+    ctx->d_calib = nullptr;
+    ctx->bkg_set = ctx->calib_set = false;
+    ctx->cfg = k;
+    ctx->configured = true;
+    return LM_OK;
+}
+
+int lm_set_model(lm_ctx *ctx, const lm_template t[2][3]) {
+    if (!ctx) return LM_ERR_INVALID;
+    if (!ctx->configured) return fail(ctx, LM_ERR_STATE, "lm_set_model before lm_configure");
+    if (!t) return fail(ctx, LM_ERR_INVALID, "null model");
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_scratch(ctx);
+    for (int v = 0; v < 2; ++v)
+        for (int f = 0; f < 3; ++f) {
+            const lm_template &T = t[v][f];
+            if (!T.w || T.rows <= 0 || T.cols <= 0) return fail(ctx, LM_ERR_INVALID, "template [%d][%d] is empty", v, f);
+            if (T.cols > LM_MAX_KW) return fail(ctx, LM_ERR_INVALID, "template [%d][%d] has %d columns (max %d)", v, f, T.cols, LM_MAX_KW);
+            cudaFree(ctx->d_tmpl[v][f]);
+            ctx->d_tmpl[v][f] = nullptr;
+            CK(cudaMalloc((void **)&ctx->d_tmpl[v][f], (size_t)T.rows * T.cols * sizeof(float)));
+            CK(cudaMemcpy(ctx->d_tmpl[v][f], T.w, (size_t)T.rows * T.cols * sizeof(float), cudaMemcpyHostToDevice));
+            ctx->t_rows[v][f] = T.rows;
+            ctx->t_cols[v][f] = T.cols;
+            ctx->t_rho[v][f] = T.rho;
+        }
+    ctx->model_set = true;
+    make_geom(ctx);
+    return LM_OK;
+}
+
+int lm_set_background(lm_ctx *ctx, const uint8_t *bkg) {
+    if (!ctx) return LM_ERR_INVALID;
+    if (!ctx->configured) return fail(ctx, LM_ERR_STATE, "lm_set_background before lm_configure");
+    if (!bkg) return fail(ctx, LM_ERR_INVALID, "null background");
+    cudaSetDevice(ctx->device);
+    const size_t n = (size_t)ctx->cfg.vid_rows * ctx->cfg.vid_cols;
+    if (!ctx->d_bkg) CK(cudaMalloc((void **)&ctx->d_bkg, n));
+    cudaDeviceSynchronize();
+    CK(cudaMemcpy(ctx->d_bkg, bkg, n, cudaMemcpyHostToDevice));
+    ctx->bt.bkg = ctx->d_bkg;
+    ctx->bkg_set = true;
+    return LM_OK;
+}
+
+int lm_set_calibration(lm_ctx *ctx, const int32_t *map) {
+    if (!ctx) return LM_ERR_INVALID;
+    if (!ctx->configured) return fail(ctx, LM_ERR_STATE, "lm_set_calibration before lm_configure");
+    if (!map) return fail(ctx, LM_ERR_INVALID, "null calibration map");
+    const size_t n = (size_t)ctx->cfg.n_rows * ctx->cfg.n_cols;
+    const int64_t lim = (int64_t)ctx->cfg.vid_rows * ctx->cfg.vid_cols;
+    // validateImageVideoSize (class.cpp:512-515): indices must address the raw frame
+    for (size_t i = 0; i < n; ++i)
+        if (map[i] < 0 || map[i] >= lim)
+            return fail(ctx, LM_ERR_RUNTIME, "Calibration mapping indices out of range (index %zu = %d, frame has %lld pixels)",
+                        i, map[i], (long long)lim);
+    cudaSetDevice(ctx->device);
+    if (!ctx->d_calib) CK(cudaMalloc((void **)&ctx->d_calib, n * sizeof(int32_t)));
+    cudaDeviceSynchronize();
+    CK(cudaMemcpy(ctx->d_calib, map, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    ctx->bt.calib = ctx->d_calib;
+    ctx->calib_set = true;
+    return LM_OK;
+}
+
+int lm_get_geometry(const lm_ctx *ctx, int32_t pads[8], int32_t canvas[4]) {
+    if (!ctx || !ctx->model_set) return LM_ERR_STATE;
+    const LmGeom &g = ctx->geom;
+    if (pads) {
+        int32_t p[8] = {g.spre_b_w, g.spre_b_h, g.spost_b_w, g.spost_b_h, g.spre_s_w, g.spre_s_h, g.spost_s_w, g.spost_s_h};
+        memcpy(pads, p, sizeof p);
+    }
+    if (canvas) {
+        int32_t c[4] = {g.pad_pre_cols, g.pad_pre_rows, g.pad_post_cols, g.pad_post_rows};
+        memcpy(canvas, c, sizeof c);
+    }
+    return LM_OK;
+}
+
+int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, const uint8_t *prev_frame, int64_t n,
+                    int64_t first_frame_index, const uint32_t *bb_x, const uint32_t *bb_y_side,
+                    const uint32_t *bb_y_bottom, lm_results *out) {
+    if (!ctx) return LM_ERR_INVALID;
+    if (!ctx->configured || !ctx->model_set || !ctx->bkg_set || !ctx->calib_set)
+        return fail(ctx, LM_ERR_STATE, "lm_detect_batch needs lm_configure, lm_set_model, lm_set_background and lm_set_calibration first");
+    if (n < 0 || first_frame_index < 0) return fail(ctx, LM_ERR_INVALID, "negative frame count or index");
+    if (n == 0) return LM_OK;
+    if (!frames || !bb_x || !bb_y_side || !bb_y_bottom || !out) return fail(ctx, LM_ERR_INVALID, "null argument");
+    if (first_frame_index > 0 && !prev_frame)
+        return fail(ctx, LM_ERR_INVALID, "prev_frame is required when first_frame_index > 0 (previous image of the velocity check)");
+    const lm_config &k = ctx->cfg;
+    if (out->n_frames < n || out->cand_cap != k.cand_cap || out->match_cap != k.match_cap ||
+        out->n_tail_points != k.n_tail_points)
+        return fail(ctx, LM_ERR_INVALID, "result buffers do not match the configuration");
+    for (int64_t f = 0; f < n; ++f)
+        if (!roi_ok(ctx, bb_x[f], bb_y_side[f], bb_y_bottom[f]))
+            return fail(ctx, LM_ERR_ROI, "frame %lld: bounding box (x=%u, y_side=%u, y_bottom=%u) leaves the padded image",
+                        (long long)(first_frame_index + f), bb_x[f], bb_y_side[f], bb_y_bottom[f]);
+    CK(cudaSetDevice(ctx->device));
+    int rc = prepare(ctx);
+    if (rc) return rc;
+    if (!frames_on_device && (rc = ensure_stage(ctx))) return rc;
+
+    const int Bcap = ctx->Bcap;
+    const int64_t fsz = ctx->bt.frame_bytes;
+    const int64_t nsub = (n + Bcap - 1) / Bcap;
+    const bool has_prev0 = first_frame_index > 0;
+    for (int q = 0; q < 7; ++q) ctx->ms[q] = 0.f;
+    ctx->launches = 0;
+    const lm_ctx::ResOff &o = ctx->ro;
+    cudaStream_t st = ctx->stream;
+
+    auto issue_h2d = [&](int64_t sub) -> int {
+        const int slot = (int)(sub & 1);
+        const int64_t s0 = sub * Bcap;
+        const int B = (int)std::min<int64_t>(Bcap, n - s0);
+        uint32_t *bb = ctx->d_bb[slot];
+        CK(cudaMemcpyAsync(bb, bb_x + s0, (size_t)B * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaMemcpyAsync(bb + Bcap, bb_y_side + s0, (size_t)B * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaMemcpyAsync(bb + 2 * Bcap, bb_y_bottom + s0, (size_t)B * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (!frames_on_device) {
+            uint8_t *stg = ctx->d_stage[slot];
+            if (s0 > 0)  // halo = last frame of the previous sub-batch, contiguous in the caller's array
+                CK(cudaMemcpyAsync(stg, frames + (s0 - 1) * fsz, (size_t)(B + 1) * fsz, cudaMemcpyHostToDevice, ctx->copy_stream));
+            else {
+                if (has_prev0) CK(cudaMemcpyAsync(stg, prev_frame, (size_t)fsz, cudaMemcpyHostToDevice, ctx->copy_stream));
+                CK(cudaMemcpyAsync(stg + fsz, frames, (size_t)B * fsz, cudaMemcpyHostToDevice, ctx->copy_stream));
+            }
+        }
+        CK(cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_stream));
+        return LM_OK;
+    };
+
+    int overflow = 0;
+    auto drain = [&](int64_t sub) -> int {  // wait for sub-batch `sub` and copy its results to the caller
+        const int slot = (int)(sub & 1);
+        const int64_t s0 = sub * Bcap;
+        const int B = (int)std::min<int64_t>(Bcap, n - s0);
+        CK(cudaEventSynchronize(ctx->ev_done[slot]));
+        const uint8_t *h = ctx->h_res[slot];
+        memcpy(out->n_bottom + s0 * 2, h + o.n_bottom, (size_t)B * 2 * 4);
+        memcpy(out->n_side + s0 * 2, h + o.n_side, (size_t)B * 2 * 4);
+        memcpy(out->bottom + s0 * 2 * k.cand_cap, h + o.bottom, (size_t)B * 2 * k.cand_cap * sizeof(lm_cand));
+        memcpy(out->side + s0 * 2 * k.cand_cap, h + o.side, (size_t)B * 2 * k.cand_cap * sizeof(lm_cand));
+        memcpy(out->match_n + s0 * 2 * k.cand_cap, h + o.match_n, (size_t)B * 2 * k.cand_cap * 4);
+        memcpy(out->match_y + s0 * 2 * k.match_cap, h + o.match_y, (size_t)B * 2 * k.match_cap * 4);
+        memcpy(out->match_s + s0 * 2 * k.match_cap, h + o.match_s, (size_t)B * 2 * k.match_cap * 8);
+        memcpy(out->tail + s0 * 3 * k.n_tail_points, h + o.tail, (size_t)B * 3 * k.n_tail_points * 4);
+        memcpy(out->flags + s0, h + o.flags, (size_t)B * 4);
+        for (int i = 0; i < B; ++i)
+            if (out->flags[s0 + i]) overflow = 1;
+        float t;
+        for (int q = 0; q < 6; ++q)
+            if (cudaEventElapsedTime(&t, ctx->ev_stage[slot][q], ctx->ev_stage[slot][q + 1]) == cudaSuccess) ctx->ms[q] += t;
+        if (cudaEventElapsedTime(&t, ctx->ev_stage[slot][0], ctx->ev_stage[slot][7]) == cudaSuccess) ctx->ms[6] += t;
+        return LM_OK;
+    };
+
+    if ((rc = issue_h2d(0))) return rc;
+    for (int64_t sub = 0; sub < nsub; ++sub) {
+        const int slot = (int)(sub & 1);
+        const int64_t s0 = sub * Bcap;
+        const int B = (int)std::min<int64_t>(Bcap, n - s0);
+        LmBatch b = ctx->bt;
+        b.B = B;
+        b.first_index = first_frame_index + s0;
+        if (frames_on_device) {
+            b.frames = frames + s0 * fsz;
+            b.prev = s0 > 0 ? frames + (s0 - 1) * fsz : (has_prev0 ? prev_frame : nullptr);
+        } else {
+            b.frames = ctx->d_stage[slot] + fsz;
+            b.prev = (s0 > 0 || has_prev0) ? ctx->d_stage[slot] : nullptr;
+        }
+        b.bb_x = ctx->d_bb[slot];
+        b.bb_y_side = ctx->d_bb[slot] + Bcap;
+        b.bb_y_bottom = ctx->d_bb[slot] + 2 * Bcap;
+        cudaEvent_t *ev = ctx->ev_stage[slot];
+        CK(cudaStreamWaitEvent(st, ctx->ev_h2d[slot], 0));
+        CK(cudaEventRecord(ev[0], st));
+        CK(cudaMemsetAsync(b.minmax, 0, (size_t)(B + 1) * 2 * 4, st));
+        CK(cudaMemsetAsync(b.det_count, 0, (size_t)B * 4 * 4, st));
+        CK(cudaMemsetAsync(b.flags, 0, (size_t)B * 4, st));
+        int nl;
+        if ((nl = lm_launch_minmax(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "minmax launch failed");
+        ctx->launches += nl;
+        CK(cudaEventRecord(ev[1], st));
+        if ((nl = lm_launch_prep(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "prep launch failed");
+        ctx->launches += nl;
+        CK(cudaEventRecord(ev[2], st));
+        if ((nl = lm_launch_corr(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "correlation launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ctx->launches += nl;
+        CK(cudaEventRecord(ev[3], st));
+        if ((nl = lm_launch_tail(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "tail launch failed");
+        ctx->launches += nl;
+        CK(cudaEventRecord(ev[4], st));
+        if ((nl = lm_launch_nms(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "nms launch failed");
+        ctx->launches += nl;
+        CK(cudaEventRecord(ev[5], st));
+        if ((nl = lm_launch_pair(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "pair launch failed");
+        ctx->launches += nl;
+        CK(cudaEventRecord(ev[6], st));
+        CK(cudaGetLastError());
+        // the next sub-batch's H2D may start as soon as the sub-batch that last used its slot is drained
+        if (sub + 1 < nsub) {
+            if (sub >= 1 && (rc = drain(sub - 1))) return rc;
+            if ((rc = issue_h2d(sub + 1))) return rc;
+        }
+        CK(cudaMemcpyAsync(ctx->h_res[slot], ctx->d_res, o.total, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ev[7], st));
+        CK(cudaEventRecord(ctx->ev_done[slot], st));
+        ctx->last_B = B;
+        ctx->last_s0 = s0;
+    }
+    if (nsub >= 2 && (rc = drain(nsub - 2))) return rc;
+    if ((rc = drain(nsub - 1))) return rc;
+    CK(cudaStreamSynchronize(st));
+    if (overflow) return fail(ctx, LM_ERR_OVERFLOW, "a fixed-capacity list overflowed (see lm_results.flags); raise det_cap / cand_cap / match_cap");
+    return LM_OK;
+}
+
+int lm_last_timing(const lm_ctx *ctx, float ms[7], int64_t *launches) {
+    if (!ctx) return LM_ERR_INVALID;
+    if (ms) memcpy(ms, ctx->ms, sizeof ctx->ms);
+    if (launches) *launches = ctx->launches;
+    return LM_OK;
+}
+
+int64_t lm_debug_fetch(lm_ctx *ctx, int what, int64_t frame, void *dst, int64_t dst_bytes, int32_t dims[4]) {
+    if (!ctx || !ctx->Bcap) return LM_ERR_STATE;
+    const int64_t i = frame - ctx->last_s0;
+    if (i < 0 || i >= ctx->last_B) return fail(ctx, LM_ERR_INVALID, "frame %lld is not in the last sub-batch", (long long)frame);
+    cudaSetDevice(ctx->device);
+    const LmBatch &b = ctx->bt;
+    const void *src = nullptr;
+    int64_t bytes = 0;
+    int32_t d[4] = {0, 0, 0, 0};
+    switch (what) {
+        case 0:
+        case 1: {
+            const LmView &V = b.view[what];
+            src = b.win[what] + i * V.win_stride;
+            bytes = V.win_stride;
+            d[0] = V.win_h; d[1] = V.win_pitch; d[2] = V.halo_y; d[3] = V.halo_x;
+            break;
+        }
+        case 2:
+            src = b.tailmask + i * b.bb_h[LM_BOTTOM] * b.tail_pitch;
+            bytes = (int64_t)b.bb_h[LM_BOTTOM] * b.tail_pitch;
+            d[0] = b.bb_h[LM_BOTTOM]; d[1] = b.tail_pitch; d[2] = b.tail_w;
+            break;
+        case 3:
+            src = b.minmax + (i + 1) * 2;
+            bytes = 8;
+            d[0] = 2;
+            break;
+        default:
+            return fail(ctx, LM_ERR_INVALID, "unknown debug item %d", what);
+    }
+    if (dims) memcpy(dims, d, sizeof d);
+    if (!dst || dst_bytes < bytes) return fail(ctx, LM_ERR_INVALID, "debug buffer too small (%lld needed)", (long long)bytes);
+    cudaError_t e = cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(ctx, LM_ERR_RUNTIME, "cudaMemcpy: %s", cudaGetErrorString(e));
+    return bytes;
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// lm_internal.h — shared declarations of the sm_100a kernels behind include/locomouse_b200.h.
+// Data layout in HBM for one sub-batch of B frames:
+//   raw frames      u8  [B(+1 halo)][vid_rows][vid_cols]     (caller's device memory or staging)
+//   minmax          i32 [B+1][2]            (255 - min, max) of sat(F - BKG); slot 0 = halo frame
+//   lut             u8  [B+1][256]          normalize ∘ imadjust per frame
+//   win[view]       u8  [B][win_h][win_pitch]   pre-processed crop + template halo, zero extended
+//   tailbin[view]   u8  [B][box_h][tail_pitch]  tail score > 0
+//   tailmask        u8  [B][bb_h_bottom][tail_pitch]  largest bottom region (TAIL_MASK) 0/1
+//   cc scratch      i32 [B][3][max_h * tail_w]  labels / area / key
+//   det lists       {u32 idx; f32 score} [B][2 feat][2 view][det_cap] + counts i32 [B][4]
+//   results         same struct-of-arrays as lm_results, for B frames
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/locomouse_b200.h"
+
+#define LM_MAX_KW 64  // widest template row the correlation kernel is instantiated for
+
+struct LmDet {
+    uint32_t idx;  // y * box_w + x in the unpadded crop
+    float score;
+};
+
+// geometry of one view's pre-processed window and of the three correlations run on it
+struct LmView {
+    int box_w, box_h;      // unpadded crop (bb_w x bb_h_*)
+    int halo_x, halo_y;    // window origin = crop origin - halo  (max anchor over the view's templates)
+    int win_w, win_h, win_pitch;
+    int64_t win_stride;    // bytes per frame
+};
+
+struct LmTemplateDev {
+    const float *w;  // device, row-major, row stride = kwp floats (zero padded), rows = kh
+    int kh, kw, kwp;
+    int ax, ay;      // anchor = (kw/2, kh/2)
+    float init;      // float(-rho)
+};
+
+struct LmGeom {
+    int spre_b_w, spre_b_h, spost_b_w, spost_b_h;
+    int spre_s_w, spre_s_h, spost_s_w, spost_s_h;
+    int pad_pre_cols, pad_pre_rows, pad_post_cols, pad_post_rows;
+};
+
+// everything a kernel needs to know about the current sub-batch
+struct LmBatch {
+    // inputs
+    const uint8_t *frames;      // frame i (0..B-1) at frames + i*frame_bytes
+    const uint8_t *prev;        // frame -1 (halo); may be null when first_index == 0
+    int64_t frame_bytes;
+    int B;
+    int64_t first_index;        // CURRENT_FRAME of frame 0 of this sub-batch
+    const uint8_t *bkg;
+    const int32_t *calib;
+    const uint32_t *bb_x, *bb_y_side, *bb_y_bottom;  // device, [B]
+    // config
+    int vid_rows, vid_cols, n_rows, n_cols;
+    int bb_w, bb_h[2], tail_w, tail_pitch;
+    int flip, imadjust, conn, n_tail_points, fma_mode;
+    int cand_cap, det_cap, match_cap;
+    int ovlp[2];                // (int)(w_bottom * (1 - T)) per feature (class.cpp:1047), host computed
+    LmView view[2];
+    LmTemplateDev tmpl[2][3];
+    // scratch
+    int32_t *minmax;            // [B+1][2]
+    uint8_t *lut;               // [B+1][256]
+    uint8_t *win[2];
+    uint8_t *tailbin[2];
+    uint8_t *tailmask;
+    uint8_t *sidemask;
+    int32_t *cc;                // [B][3][cc_stride]
+    int64_t cc_stride;
+    LmDet *det;                 // [B][2][2][det_cap]   index: ((f*2+feat)*2+view)
+    int32_t *det_count;         // [B][2][2]
+    // results (device mirrors of lm_results)
+    int32_t *n_bottom, *n_side;
+    lm_cand *bottom, *side;
+    int32_t *match_n, *match_y;
+    double *match_s;
+    int32_t *tail;
+    uint32_t *flags;
+};
+
+// launchers (each returns the number of kernels it launched)
+int lm_launch_minmax(const LmBatch &b, cudaStream_t s);
+int lm_launch_prep(const LmBatch &b, cudaStream_t s);
+int lm_launch_corr(const LmBatch &b, cudaStream_t s);
+int lm_launch_tail(const LmBatch &b, cudaStream_t s);
+int lm_launch_nms(const LmBatch &b, cudaStream_t s);
+int lm_launch_pair(const LmBatch &b, cudaStream_t s);
+
+// pick the padded kernel-row width the correlation kernel is instantiated for (>= kw), or -1
+int lm_corr_kwp(int kw);
+// dynamic shared memory the correlation kernel needs for a view/template (for capability checks)
+size_t lm_corr_smem_bytes(const LmBatch &b, int view, int feat);
+
+#define LM_CUDA_CHECK(x)                                                            \
+    do {                                                                            \
+        cudaError_t _e = (x);                                                       \
+        if (_e != cudaSuccess) return lm_fail_cuda(_e, #x, __FILE__, __LINE__);     \
+    } while (0)

@@ -149,7 +149,8 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device,
 /* Device time (ms, CUDA events on the library's own stream) of the stages of the last
  * lm_detect_batch call, summed over its sub-batches:
  * ms[0]=min/max  ms[1]=preprocess+crop  ms[2]=correlation  ms[3]=tail  ms[4]=nms  ms[5]=pairing
- * ms[6]=whole call on the device (first kernel to last D2H).  launches = kernels launched. */
+ * ms[6]=whole call on the device (event before the first copy/kernel to event after the last D2H,
+ * so host<->device copies and inter-sub-batch gaps are included).  launches = kernels launched. */
 int lm_last_timing(const lm_ctx *ctx, float ms[7], int64_t *launches);
 
 /* Copies an intermediate of the LAST sub-batch back to the host for parity debugging.

@@ -23,7 +23,8 @@ constexpr int CORR_THREADS = 256;
 
 struct CorrJob {
     int view, feat, is_tail;
-    int out_w, out_h;        // outputs computed: bb_w (or tail_w) x box_h
+    int x_begin;             // first output column of this strip (wide boxes are cut into column strips)
+    int out_w, out_h;        // outputs computed by this job: strip width x box_h
     int ngx, ntasks;         // column groups, total tasks
     int cta_begin, ncta;     // CTA range inside a frame's block of CTAs
     int off_x, off_y;        // window column/row of tap (0,0) for output (0,0): halo - anchor
@@ -35,8 +36,10 @@ struct CorrJob {
     int w_stride;
 };
 
+constexpr int MAX_JOBS = 24;
+
 struct CorrParams {
-    CorrJob job[6];
+    CorrJob job[MAX_JOBS];
     int njobs;
     int ctas_per_frame;
     int B;
@@ -61,9 +64,8 @@ __global__ void __launch_bounds__(CORR_THREADS, (KW <= 32) ? 2 : 1) k_corr(const
     const int f = blockIdx.x / P.ctas_per_frame;
     const int c = blockIdx.x - f * P.ctas_per_frame;
     int ji = 0;
-#pragma unroll
-    for (int q = 1; q < 6; ++q)
-        if (q < P.njobs && c >= P.job[q].cta_begin) ji = q;
+    for (int q = 1; q < P.njobs; ++q)
+        if (c >= P.job[q].cta_begin) ji = q;
     const CorrJob &J = P.job[ji];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(CORR_THREADS, (KW <= 32) ? 2 : 1) k_corr(const
 #pragma unroll
             for (int k = 0; k < TX; ++k) {
                 const int x = x0 + k;
-                if (x < J.out_w) tb[(int64_t)y * P.tail_pitch + x] = acc[t][k] > 0.f ? 1 : 0;
+                if (x < J.out_w) tb[(int64_t)y * P.tail_pitch + J.x_begin + x] = acc[t][k] > 0.f ? 1 : 0;
             }
         }
         return;
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(CORR_THREADS, (KW <= 32) ? 2 : 1) k_corr(const
             if (hit & (1u << (t * TX + k))) {
                 if (o < P.det_cap) {
                     LmDet d;
-                    d.idx = (uint32_t)((y0 + t) * bw + x0 + k);
+                    d.idx = (uint32_t)((y0 + t) * bw + J.x_begin + x0 + k);
                     d.score = acc[t][k];
                     out[o] = d;
                 }
@@ -273,20 +275,23 @@ size_t job_smem(const CorrJob &J) {
     return ((size_t)J.kh * J.kwp4 + rows * J.pitch) * sizeof(float);
 }
 
-CorrJob make_job(const LmBatch &b, int view, int feat, int kwp) {
+int full_out_w(const LmBatch &b, int view, int feat) { return feat == LM_TAIL ? b.tail_w : b.view[view].box_w; }
+
+CorrJob make_job(const LmBatch &b, int view, int feat, int kwp, int x_begin, int strip_w) {
     const LmTemplateDev &T = b.tmpl[view][feat];
     const LmView &V = b.view[view];
     CorrJob J{};
     J.view = view;
     J.feat = feat;
     J.is_tail = (feat == LM_TAIL);
-    J.out_w = J.is_tail ? b.tail_w : V.box_w;
+    J.x_begin = x_begin;
+    J.out_w = strip_w;
     J.out_h = V.box_h;
     J.ngx = (J.out_w + kTX - 1) / kTX;
     int ngy = (J.out_h + kTY - 1) / kTY;
     J.ntasks = J.ngx * ngy;
     J.ncta = (J.ntasks + CORR_THREADS - 1) / CORR_THREADS;
-    J.off_x = V.halo_x - T.ax;
+    J.off_x = V.halo_x - T.ax + x_begin;
     J.off_y = V.halo_y - T.ay;
     J.kh = T.kh;
     J.kwp4 = ((kwp + 3) / 4) * 4;
@@ -308,11 +313,29 @@ int lm_corr_kwp(int kw) {
     return -1;
 }
 
+// Column strips: the narrowest split of the box whose tile fits the shared-memory budget
+// (two CTAs per SM for kernel rows up to 32 taps, one CTA per SM beyond).
+static int strip_width(const LmBatch &b, int view, int feat, int kwp, size_t *smem_out) {
+    const size_t budget = (kwp <= 32) ? 110 * 1024 : 224 * 1024;
+    const int W = full_out_w(b, view, feat);
+    for (int ns = 1; ns <= W; ++ns) {
+        int sw = (((W + ns - 1) / ns + kTX - 1) / kTX) * kTX;
+        CorrJob J = make_job(b, view, feat, kwp, 0, sw);
+        size_t sm = job_smem(J);
+        if (sm <= budget || sw <= kTX) {
+            if (smem_out) *smem_out = sm;
+            return sw;
+        }
+    }
+    return kTX;
+}
+
 size_t lm_corr_smem_bytes(const LmBatch &b, int view, int feat) {
     int kwp = lm_corr_kwp(b.tmpl[view][feat].kw);
     if (kwp < 0) return (size_t)-1;
-    CorrJob J = make_job(b, view, feat, kwp);
-    return job_smem(J);
+    size_t sm = 0;
+    strip_width(b, view, feat, kwp, &sm);
+    return sm;
 }
 
 // One launch per distinct padded kernel width; all (view, template) boxes that share it ride in the
@@ -334,12 +357,17 @@ int lm_launch_corr(const LmBatch &b, cudaStream_t s) {
                         done[v][k] = true;
                         continue;
                     }
-                    CorrJob J = make_job(b, v, k, kwp);
-                    J.cta_begin = cta;
-                    cta += J.ncta;
-                    size_t sm = job_smem(J);
-                    if (sm > smem) smem = sm;
-                    P.job[P.njobs++] = J;
+                    const int W = full_out_w(b, v, k);
+                    const int sw = strip_width(b, v, k, kwp, nullptr);
+                    for (int xb = 0; xb < W; xb += sw) {
+                        if (P.njobs >= MAX_JOBS) return -1;
+                        CorrJob J = make_job(b, v, k, kwp, xb, (W - xb < sw) ? (W - xb) : sw);
+                        J.cta_begin = cta;
+                        cta += J.ncta;
+                        size_t sm = job_smem(J);
+                        if (sm > smem) smem = sm;
+                        P.job[P.njobs++] = J;
+                    }
                     done[v][k] = true;
                 }
             if (!P.njobs) continue;

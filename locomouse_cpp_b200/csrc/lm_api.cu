@@ -44,6 +44,7 @@ struct lm_ctx {
     uint8_t *h_res[2] = {};           // pinned
     cudaEvent_t ev_h2d[2] = {}, ev_done[2] = {};
     cudaEvent_t ev_stage[2][8] = {};
+    cudaEvent_t ev_call[2] = {};      // first kernel / last D2H of a whole lm_detect_batch call
     float ms[7] = {};
     int64_t launches = 0;
     int last_B = 0;                   // size of the last sub-batch (for lm_debug_fetch)
@@ -296,6 +297,7 @@ int lm_create(lm_ctx **out, int device) {
         cudaEventCreateWithFlags(&ctx->ev_h2d[s], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_done[s], cudaEventDisableTiming);
         for (int q = 0; q < 8; ++q) cudaEventCreate(&ctx->ev_stage[s][q]);
+        cudaEventCreate(&ctx->ev_call[s]);
     }
     *out = ctx;
     return LM_OK;
@@ -314,6 +316,7 @@ int lm_destroy(lm_ctx *ctx) {
         cudaEventDestroy(ctx->ev_h2d[s]);
         cudaEventDestroy(ctx->ev_done[s]);
         for (int q = 0; q < 8; ++q) cudaEventDestroy(ctx->ev_stage[s][q]);
+        cudaEventDestroy(ctx->ev_call[s]);
     }
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
@@ -496,10 +499,10 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, co
         float t;
         for (int q = 0; q < 6; ++q)
             if (cudaEventElapsedTime(&t, ctx->ev_stage[slot][q], ctx->ev_stage[slot][q + 1]) == cudaSuccess) ctx->ms[q] += t;
-        if (cudaEventElapsedTime(&t, ctx->ev_stage[slot][0], ctx->ev_stage[slot][7]) == cudaSuccess) ctx->ms[6] += t;
         return LM_OK;
     };
 
+    CK(cudaEventRecord(ctx->ev_call[0], st));
     if ((rc = issue_h2d(0))) return rc;
     for (int64_t sub = 0; sub < nsub; ++sub) {
         const int slot = (int)(sub & 1);
@@ -555,9 +558,14 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, co
         ctx->last_B = B;
         ctx->last_s0 = s0;
     }
+    CK(cudaEventRecord(ctx->ev_call[1], st));
     if (nsub >= 2 && (rc = drain(nsub - 2))) return rc;
     if ((rc = drain(nsub - 1))) return rc;
     CK(cudaStreamSynchronize(st));
+    {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ctx->ev_call[0], ctx->ev_call[1]) == cudaSuccess) ctx->ms[6] = t;
+    }
     if (overflow) return fail(ctx, LM_ERR_OVERFLOW, "a fixed-capacity list overflowed (see lm_results.flags); raise det_cap / cand_cap / match_cap");
     return LM_OK;
 }

@@ -1,0 +1,141 @@
+"""Frame-range sharding of the detection path across the GPUs of one box (one process per GPU).
+
+The hot path is per-frame except for a one-frame look-back (checkVelCriterion reads the previous
+image, LocoMouse_class.cpp:1256-1267, 1469-1470), so a video shards into contiguous frame ranges with
+a ONE-FRAME TEMPORAL HALO and no data-path collective.  The only communication is the
+final gather of the (compacted) candidate lists to rank 0, where the sequential host tracker
+(match2nd) runs.  torch.distributed is plumbing: backend "nccl" on the GPU box, "gloo" in CPU tests.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .types import CAND_DTYPE, Results
+
+
+def frame_range(n_frames: int, world: int, rank: int):
+    """Contiguous, balanced [f0, f1) for `rank`; the first n % world ranks get one extra frame."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    q, r = divmod(int(n_frames), world)
+    f0 = rank * q + min(rank, r)
+    return f0, f0 + q + (1 if rank < r else 0)
+
+
+@dataclass(frozen=True)
+class Shard:
+    video: int
+    f0: int
+    f1: int
+
+    @property
+    def needs_halo(self) -> bool:
+        """True when the frame before f0 must be supplied as prev_frame (video frame 0 has no look-back)."""
+        return self.f0 > 0
+
+
+def plan(n_videos: int, frames_per_video: int, world: int):
+    """Per-rank list of Shards.  Whole videos are dealt round-robin when there are at least as many
+    videos as ranks (no halo at all); otherwise every video is cut into `world` frame ranges."""
+    out = [[] for _ in range(world)]
+    if n_videos >= world:
+        for v in range(n_videos):
+            out[v % world].append(Shard(v, 0, frames_per_video))
+    else:
+        for v in range(n_videos):
+            for r in range(world):
+                f0, f1 = frame_range(frames_per_video, world, r)
+                if f1 > f0:
+                    out[r].append(Shard(v, f0, f1))
+    return out
+
+
+# ---- compact wire format for the gather ------------------------------------------------------------
+def pack(res: Results) -> np.ndarray:
+    """Results -> 1-D uint8 array holding only the live entries (counts + ragged lists)."""
+    n, cap = res.n, res.cand_cap
+    nb, ns = res.n_bottom[:n], res.n_side[:n]
+    sel_b = np.arange(cap)[None, None, :] < nb[:, :, None]
+    sel_s = np.arange(cap)[None, None, :] < ns[:, :, None]
+    mn = res.match_n[:n][sel_b]
+    per_list = np.where(sel_b, res.match_n[:n], 0).sum(axis=2).astype(np.int64)
+    sel_m = np.arange(res.match_cap)[None, None, :] < per_list[:, :, None]
+    head = np.array([n, cap, res.match_cap, res.n_tail_points], np.int64)
+    parts = [head, nb, ns, res.bottom[:n][sel_b], res.side[:n][sel_s], mn.astype(np.int32),
+             res.match_y[:n][sel_m], res.match_s[:n][sel_m], res.tail[:n], res.flags[:n]]
+    return np.concatenate([np.ascontiguousarray(p).view(np.uint8).reshape(-1) for p in parts])
+
+
+def unpack(buf: np.ndarray) -> Results:
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    o = 0
+
+    def take(dtype, count):
+        nonlocal o
+        nbytes = np.dtype(dtype).itemsize * count
+        a = buf[o:o + nbytes].view(dtype)
+        o += nbytes
+        return a
+
+    n, cap, mcap, ntp = map(int, take(np.int64, 4))
+    res = Results(n, cap, mcap, ntp)
+    res.bottom[:] = np.array((-1, -1, -1.0), CAND_DTYPE)
+    res.side[:] = np.array((-1, -1, -1.0), CAND_DTYPE)
+    res.match_y[:] = -1
+    res.match_s[:] = -1.0
+    if n == 0:
+        return res
+    res.n_bottom[:n] = take(np.int32, n * 2).reshape(n, 2)
+    res.n_side[:n] = take(np.int32, n * 2).reshape(n, 2)
+    sel_b = np.arange(cap)[None, None, :] < res.n_bottom[:n][:, :, None]
+    sel_s = np.arange(cap)[None, None, :] < res.n_side[:n][:, :, None]
+    res.bottom[:n][sel_b] = take(CAND_DTYPE, int(sel_b.sum()))
+    res.side[:n][sel_s] = take(CAND_DTYPE, int(sel_s.sum()))
+    mn = take(np.int32, int(sel_b.sum()))
+    res.match_n[:n][sel_b] = mn
+    per_list = res.match_n[:n].sum(axis=2).astype(np.int64)
+    sel_m = np.arange(mcap)[None, None, :] < per_list[:, :, None]
+    res.match_y[:n][sel_m] = take(np.int32, int(sel_m.sum()))
+    res.match_s[:n][sel_m] = take(np.float64, int(sel_m.sum()))
+    res.tail[:n] = take(np.int32, n * 3 * ntp).reshape(n, 3, ntp)
+    res.flags[:n] = take(np.uint32, n)
+    return res
+
+
+def concat(parts) -> Results:
+    """Concatenate per-shard Results in frame order."""
+    parts = list(parts)
+    n = sum(p.n for p in parts)
+    ref = parts[0]
+    out = Results(n, ref.cand_cap, ref.match_cap, ref.n_tail_points)
+    o = 0
+    for p in parts:
+        for name in Results.ARRAYS:
+            getattr(out, name)[o:o + p.n] = getattr(p, name)[:p.n]
+        o += p.n
+    return out
+
+
+def gather_to_rank0(res: Results, device=None):
+    """Gather every rank's Results on rank 0 (list in rank order; None elsewhere).  Variable-size
+    uint8 payloads: sizes travel with all_gather, payloads with gather (NCCL) / gather (gloo)."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    payload = torch.from_numpy(pack(res).copy())
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    size = torch.tensor([payload.numel()], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, size)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(sizes)
+    send = torch.zeros(mx, dtype=torch.uint8, device=dev)
+    send[: payload.numel()] = payload.to(dev)
+    recv = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+    dist.gather(send, recv, dst=0)
+    if rank != 0:
+        return None
+    return [unpack(r[:s].cpu().numpy()) for r, s in zip(recv, sizes)]

@@ -41,14 +41,27 @@ class SynthSpec:
     cand_cap: int = 64
     det_cap: int = 8192
     match_cap: int = 256
+    mouse_scale: float = 1.0    # size of the rendered mouse relative to the config-1 animal
+    tshapes: tuple | None = None  # optional ((rows, cols),)*3 per view: [[paw, snout, tail] bottom, [..] side]
 
     def scaled(self) -> "SynthSpec":
         s = self.scale
         if s == 1:
             return self
-        return SynthSpec(self.method, 1, self.n_rows * s, self.n_cols * s, self.side_h * s, self.bb_w * s,
-                         self.bb_h_side_tm * s, self.tsize * s, self.vid_pad, self.flip, self.warp, self.fma_mode,
-                         self.conn, self.cand_cap, self.det_cap, self.match_cap)
+        import dataclasses
+
+        return dataclasses.replace(self, scale=1, n_rows=self.n_rows * s, n_cols=self.n_cols * s,
+                                   side_h=self.side_h * s, bb_w=self.bb_w * s, bb_h_side_tm=self.bb_h_side_tm * s,
+                                   tsize=self.tsize * s, mouse_scale=self.mouse_scale * s)
+
+    def template_shape(self, view: int, feat: int):
+        if self.tshapes is not None:
+            return tuple(self.tshapes[view][feat])
+        t = self.scaled().tsize
+        return (t, t)
+
+    def max_tsize(self) -> int:
+        return max(max(self.template_shape(v, k)) for v in range(2) for k in range(3))
 
     def config(self) -> Config:
         s = self.scaled()
@@ -117,8 +130,9 @@ def make_model(spec: SynthSpec, seed: int = 7, rho=None) -> Model:
     w = [[None] * 3 for _ in range(2)]
     for v in (BOTTOM, SIDE):
         for k in (PAW, SNOUT, TAIL):
-            sigma = 2.0 * s.tsize / 30.0 if k != TAIL else 1.5 * s.tsize / 30.0
-            w[v][k] = _smooth_template(rng, s.tsize, s.tsize, max(1.0, sigma))
+            rows, cols = spec.template_shape(v, k)
+            sigma = 2.0 * min(rows, cols) / 30.0 if k != TAIL else 1.5 * min(rows, cols) / 30.0
+            w[v][k] = _smooth_template(rng, rows, cols, max(1.0, sigma))
     if rho is None:
         rho = [[0.0] * 3 for _ in range(2)]
     return Model(w=w, rho=[list(map(float, r)) for r in rho])
@@ -133,18 +147,18 @@ def _trajectory(spec: SynthSpec, n: int, seed: int, start_frame: int = 0, total:
     s = spec.scaled()
     total = total or (start_frame + n)
     rng = np.random.Generator(np.random.PCG64(seed + 17))
-    jitter = np.cumsum(rng.normal(0, 0.6 * s.scale if s.scale else 0.6, total))
+    jitter = np.cumsum(rng.normal(0, 0.6 * s.mouse_scale, total))
     jitter -= np.linspace(0, jitter[-1], total)
     t = np.arange(total) / max(total - 1, 1)
-    x_lo, x_hi = 0.09 * s.n_cols, s.n_cols - 1 - 12
+    x_lo, x_hi = 0.09 * s.n_cols, s.n_cols - 1 - 12 * s.mouse_scale
     nose = x_lo + (x_hi - x_lo) * t + jitter
-    raw = nose + 10.0
+    raw = nose + 10.0 * s.mouse_scale
     # moving average, window 5, as vecmovingaverage (LocoMouse_class.cpp:1559-1608)
     bbx = raw.copy()
     if total > 5:
         cs = np.convolve(raw, np.ones(5), mode="valid") / 5.0
         bbx[2:total - 2] = np.floor(cs)
-    bbx = np.clip(np.floor(bbx), s.tsize, s.n_cols - 1).astype(np.uint32)
+    bbx = np.clip(np.floor(bbx), spec.max_tsize(), s.n_cols - 1).astype(np.uint32)
     sl = slice(start_frame, start_frame + n)
     return nose[sl], bbx[sl]
 
@@ -155,7 +169,7 @@ def make_video(spec: SynthSpec, n: int, seed: int = 1000, device="cpu", bkg: np.
     uint32 numpy arrays).  Content: background + mouse model + N(0,3) noise, saturated to u8."""
     cfg = spec.config()
     s = spec.scaled()
-    sc = float(spec.scale)
+    sc = float(s.mouse_scale)
     if bkg is None:
         bkg = make_background(spec, seed)
     dev = torch.device(device)
@@ -221,6 +235,8 @@ def make_video(spec: SynthSpec, n: int, seed: int = 1000, device="cpu", bkg: np.
             else:
                 layer = layer * (Y < side_h).float()
             img = img + layer
+        if s.flip:  # the raw video shows the mouse mirrored; readFrame flips it back (class.cpp:1323)
+            img = img.flip(-1)
         gen.manual_seed(int(seed) * 1000003 + start_frame + c0)
         noise = torch.randn((B, H, W), generator=gen, device=dev, dtype=torch.float32) * 3.0
         img = img + bkg_t.view(1, H, W) + noise
@@ -261,32 +277,35 @@ def calibrate_rho(spec: SynthSpec, model: Model, bkg, calib, frames: np.ndarray,
         x0 = int(bb_x[f]) - cfg.bb_w + 1
         for v, (y_pos, h) in ((BOTTOM, (bb_y_bottom[f], cfg.bb_h_bottom)), (SIDE, (bb_y_side[f], cfg.bb_h_side))):
             y0 = int(y_pos) - h + 1
-            pad = spec.scaled().tsize
+            pad = spec.max_tsize()
             P = np.zeros((h + 2 * pad, cfg.bb_w + 2 * pad))
             ys, xs = np.arange(y0 - pad, y0 + h + pad), np.arange(x0 - pad, x0 + cfg.bb_w + pad)
             yv = (ys >= 0) & (ys < cfg.n_rows)
             xv = (xs >= 0) & (xs < cfg.n_cols)
             P[np.ix_(yv, xv)] = I[np.ix_(ys[yv], xs[xv])]
             crops[v].append(P)
+    from scipy.signal import fftconvolve
+
     for v in (BOTTOM, SIDE):
-        P = torch.from_numpy(np.stack(crops[v]))[:, None]
+        P = np.stack(crops[v])  # [n, h + 2 pad, w + 2 pad] float64
         h = cfg.bb_h_bottom if v == BOTTOM else cfg.bb_h_side
-        pad = spec.scaled().tsize
+        pad = spec.max_tsize()
+        centre = P[:, pad:pad + h, pad:pad + cfg.bb_w]
         for k in (PAW, SNOUT, TAIL):
-            w = torch.from_numpy(model.w[v][k].astype(np.float64))[None, None]
-            kh, kw = w.shape[-2:]
-            sc = torch.nn.functional.conv2d(P, w)  # valid correlation
+            w = model.w[v][k].astype(np.float64)
+            kh, kw = w.shape
+            # valid cross-correlation via FFT (flip the kernel); only used to pick rho
+            sc = np.stack([fftconvolve(P[i], w[::-1, ::-1], mode="valid") for i in range(P.shape[0])])
             oy, ox = pad - kh // 2, pad - kw // 2
-            sc = sc[:, 0, oy:oy + h, ox:ox + cfg.bb_w]
-            centre = P[:, 0, pad:pad + h, pad:pad + cfg.bb_w]
+            sc = sc[:, oy:oy + h, ox:ox + cfg.bb_w]
             if k == TAIL:
                 vals = sc[:, :, :cfg.tail_w].reshape(-1)
             else:
                 vals = sc[centre > 25]
-            if vals.numel() == 0:
+            if vals.size == 0:
                 rho[v][k] = 0.0
                 continue
-            q = torch.quantile(vals[: 4_000_000], 1.0 - target_frac[k]).item()
+            q = np.quantile(vals, 1.0 - target_frac[k])
             rho[v][k] = float(np.float32(q))
     return Model(w=model.w, rho=rho)
 

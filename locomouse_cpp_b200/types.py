@@ -186,10 +186,12 @@ class Results:
         return acc
 
 
-def diff_results(a: Results, b: Results, score_rtol: float = 0.0) -> list:
+def diff_results(a: Results, b: Results, score_rtol: float = 0.0, score_atol: float = 0.0) -> list:
     """Differences between two result sets.  Integer fields (counts, coordinates, pairings, tail,
-    flags) must be identical; scores are compared bit-exactly when score_rtol == 0 else within
-    score_rtol relative.  Returns a list of human-readable mismatch strings (empty = equal)."""
+    flags) must be identical; scores are compared bit-exactly when score_rtol == score_atol == 0, else
+    within |x - y| <= score_atol + score_rtol * |y|  (score_atol carries the tolerance relative to the
+    correlation magnitude: a detector score is a sum of O(rho) terms minus rho, so its error scales with
+    |rho|, not with the possibly tiny score).  Returns human-readable mismatch strings (empty = equal)."""
     out = []
     if a.n != b.n:
         return [f"n {a.n} != {b.n}"]
@@ -206,17 +208,17 @@ def diff_results(a: Results, b: Results, score_rtol: float = 0.0) -> list:
             if not np.array_equal(x[fld], y[fld]):
                 idx = tuple(np.argwhere(x[fld] != y[fld])[0])
                 out.append(f"{name}.{fld} differs first at {idx}: {x[fld][idx]} vs {y[fld][idx]}")
-        if not _scores_equal(x["s"], y["s"], score_rtol):
+        if not _scores_equal(x["s"], y["s"], score_rtol, score_atol):
             out.append(f"{name}.s differs (max rel {_max_rel(x['s'], y['s']):.3e})")
-    if not _scores_equal(a.match_s[:n], b.match_s[:n], score_rtol):
+    if not _scores_equal(a.match_s[:n], b.match_s[:n], score_rtol, score_atol):
         out.append(f"match_s differs (max rel {_max_rel(a.match_s[:n], b.match_s[:n]):.3e})")
     return out
 
 
-def _scores_equal(x, y, rtol):
-    if rtol == 0.0:
+def _scores_equal(x, y, rtol, atol=0.0):
+    if rtol == 0.0 and atol == 0.0:
         return np.array_equal(x.view(np.uint64), y.view(np.uint64)) or np.array_equal(x, y, equal_nan=True)
-    return bool(np.allclose(x, y, rtol=rtol, atol=0.0, equal_nan=True))
+    return bool(np.allclose(x, y, rtol=rtol, atol=atol, equal_nan=True))
 
 
 def _max_rel(x, y):

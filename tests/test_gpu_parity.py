@@ -76,7 +76,8 @@ def test_mul_add_mode_is_bitexact_and_close_to_fused(oracle):
     # same candidates whenever no score sits within rounding distance of a decision; compare scores loosely
     same = np.array_equal(fused.n_bottom, got.n_bottom) and np.array_equal(fused.n_side, got.n_side)
     if same:
-        assert diff_results(fused, got, score_rtol=SCORE_RTOL) == []
+        scale = float(np.abs(np.array(model.rho)).max())   # correlation magnitude: scores are sums of O(rho) minus rho
+        assert diff_results(fused, got, score_rtol=SCORE_RTOL, score_atol=SCORE_RTOL * scale) == []
 
 
 def test_mixed_template_shapes(oracle):

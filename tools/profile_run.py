@@ -1,0 +1,25 @@
+"""Small driver for ncu: N device-resident synthetic frames through lm_detect_batch, a few times."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from locomouse_cpp_b200 import synth  # noqa: E402
+from locomouse_cpp_b200.api import Detector  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--frames", type=int, default=512)
+ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--scale", type=int, default=1)
+args = ap.parse_args()
+spec = synth.SynthSpec(scale=args.scale) if args.scale == 1 else synth.SynthSpec(scale=args.scale, cand_cap=128, match_cap=512)
+cfg, model, bkg, calib, _, _, _, _ = synth.make_problem(spec, 8, seed=1000)
+frames, bx, bs, bb = synth.make_video(spec, args.frames, 1000, "cuda", bkg)
+torch.cuda.synchronize()
+det = Detector(cfg, model, bkg, calib)
+for _ in range(args.iters):
+    r = det.detect_batch(frames, bx, bs, bb, allow_overflow=True)
+    print(det.last_timing())
+print("flags", int((r.flags != 0).sum()), "n_bottom", r.n_bottom.mean(0), "n_side", r.n_side.mean(0))

@@ -156,7 +156,7 @@ int prepare(lm_ctx *ctx) {
     b.bb_h[LM_BOTTOM] = k.bb_h_bottom;
     b.bb_h[LM_SIDE] = k.bb_h_side;
     b.tail_w = k.tail_w;
-    b.tail_pitch = std::max(4, (k.tail_w + 3) & ~3);
+    b.tail_pitch = std::max(32, (k.tail_w + 31) & ~31);  // rows start 32-byte aligned (k_tail packs 32 px per word)
     b.flip = k.flip;
     b.imadjust = k.imadjust;
     b.conn = k.conn;
@@ -220,6 +220,7 @@ int prepare(lm_ctx *ctx) {
     if ((rc = dalloc(ctx, &b.sidemask, B * b.bb_h[LM_SIDE] * b.tail_pitch))) return rc;
     b.cc_stride = (int64_t)std::max(b.bb_h[0], b.bb_h[1]) * std::max(b.tail_w, 1);
     if ((rc = dalloc(ctx, &b.cc, B * 3 * b.cc_stride))) return rc;
+    if ((rc = dalloc(ctx, &b.cc_flag, B))) return rc;
     if ((rc = dalloc(ctx, &b.det, B * 4 * (size_t)k.det_cap))) return rc;
     if ((rc = dalloc(ctx, &b.det_count, B * 4))) return rc;
     for (int s = 0; s < 2; ++s)

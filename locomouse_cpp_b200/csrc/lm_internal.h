@@ -71,6 +71,7 @@ struct LmBatch {
     uint8_t *sidemask;
     int32_t *cc;                // [B][3][cc_stride]
     int64_t cc_stride;
+    int32_t *cc_flag;           // [B] 1 = frame exceeded the run capacity of k_tail and takes k_tail_slow
     LmDet *det;                 // [B][2][2][det_cap]   index: ((f*2+feat)*2+view)
     int32_t *det_count;         // [B][2][2]
     // results (device mirrors of lm_results)

@@ -133,6 +133,20 @@ def test_subbatch_split_and_device_frames_invariance(oracle, monkeypatch):
     assert small.checksum() == small_dev.checksum() == big.checksum() == pinned.checksum() == ref.checksum()
 
 
+def test_tail_slow_path_equals_fast_path(oracle, monkeypatch):
+    """k_tail labels runs in shared memory; frames with more runs than its capacity take the pixel-based
+    global-memory kernel.  Force that path (capacity 4) and compare with the oracle and the fast path."""
+    spec = synth.SynthSpec()
+    cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(spec, 5, seed=1009)
+    fr = frames.numpy()
+    ref = oracle.detect(cfg, model, bkg, calib, fr, bx, bs, bb, n_threads=5)
+    fast = _detector(cfg, model, bkg, calib).detect_batch(fr, bx, bs, bb)
+    monkeypatch.setenv("LM_TAIL_RUNCAP", "4")
+    slow = _detector(cfg, model, bkg, calib).detect_batch(fr, bx, bs, bb)
+    assert diff_results(fast, ref) == [] and diff_results(slow, ref) == []
+    assert (ref.tail[:, 0] >= 0).any()
+
+
 def test_repeatable(oracle):
     """Atomic-append order of detections must not leak into the results: 3 runs, identical bytes."""
     spec = synth.SynthSpec()

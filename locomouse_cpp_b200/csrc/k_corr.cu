@@ -55,6 +55,48 @@ struct CorrParams {
     int32_t *det_count;
 };
 
+
+// NT consecutive taps of one kernel row applied to one output row of the thread's patch (TX
+// accumulators), taps in increasing column order.  p[] holds the NP pixels those taps read, w points at
+// the first of the NT weights (16-byte aligned in shared memory).
+template <int NT, int TX, bool FMA, int NP>
+__device__ __forceinline__ void corr_taps(float (&acc)[TX], const float (&p)[NP], const float *__restrict__ w) {
+    constexpr int NT4 = ((NT + 3) / 4) * 4;
+    const float4 *wr = reinterpret_cast<const float4 *>(w);
+    float wv[NT4];
+#pragma unroll
+    for (int q = 0; q < NT4 / 4; ++q) {
+        float4 v = wr[q];
+        wv[4 * q + 0] = v.x;
+        wv[4 * q + 1] = v.y;
+        wv[4 * q + 2] = v.z;
+        wv[4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+#pragma unroll
+        for (int k = 0; k < TX; ++k) {
+            if (FMA)
+                acc[k] = __fmaf_rn(wv[i], p[i + k], acc[k]);
+            else
+                acc[k] = __fadd_rn(acc[k], __fmul_rn(wv[i], p[i + k]));
+        }
+    }
+}
+
+template <int NP>
+__device__ __forceinline__ void load_pixels(float (&p)[NP], const float *__restrict__ row) {
+    const float4 *src = reinterpret_cast<const float4 *>(row);
+#pragma unroll
+    for (int q = 0; q < NP / 4; ++q) {
+        float4 v = src[q];
+        p[4 * q + 0] = v.x;
+        p[4 * q + 1] = v.y;
+        p[4 * q + 2] = v.z;
+        p[4 * q + 3] = v.w;
+    }
+}
+
 template <int KW, int TX, int TY, bool FMA>
 __global__ void __launch_bounds__(CORR_THREADS, (KW <= 32) ? 2 : 1) k_corr(const __grid_constant__ CorrParams P) {
     constexpr int NP = ((TX + KW - 1 + 3) / 4) * 4;  // pixel registers per tile row (multiple of 4)
@@ -85,38 +127,53 @@ __global__ void __launch_bounds__(CORR_THREADS, (KW <= 32) ? 2 : 1) k_corr(const
         wsm[idx] = (i < J.w_stride) ? J.w[j * J.w_stride + i] : 0.f;
     }
     {
+        // Window rows -> fp32 tile.  All of a thread's global loads of a batch are issued before any is
+        // consumed (8 independent 32-bit loads in flight per thread), so the staging costs about one L2
+        // round trip per batch instead of one per word; bytes become floats with the 2^23 magic-number
+        // trick (PRMT + FADD, exact for 0..255) instead of the quarter-rate I2F pipe.
         const int v = J.view;
         const uint8_t *wbase = P.win[v] + (int64_t)f * P.win_stride[v];
         const int win_w = P.win_w[v], win_h = P.win_h[v], wp = P.win_pitch[v];
         const int row0 = rg_first * TY + J.off_y;
         const int p4 = pitch >> 2;
-        for (int r = warp; r < tile_rows; r += CORR_THREADS / 32) {
-            const int wr = row0 + r;
-            const bool rok = (wr >= 0) && (wr < win_h);
-            const uint8_t *src = wbase + (int64_t)wr * wp;
-            float4 *dst = reinterpret_cast<float4 *>(tile + r * pitch);
-            for (int c4 = lane; c4 < p4; c4 += 32) {
-                const int wc = J.off_x + c4 * 4;
-                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (rok) {
-                    if (((wc & 3) == 0) && wc >= 0 && wc + 4 <= wp) {
-                        // window rows are zero padded up to the pitch, so a full word is always valid
-                        uint32_t u = *reinterpret_cast<const uint32_t *>(src + wc);
-                        o.x = (float)(u & 0xff);
-                        o.y = (float)((u >> 8) & 0xff);
-                        o.z = (float)((u >> 16) & 0xff);
-                        o.w = (float)(u >> 24);
-                    } else {
-                        float t4[4];
+        const int nq = tile_rows * p4;
+        constexpr int SB = 8;
+        for (int base = 0; base < nq; base += CORR_THREADS * SB) {
+            uint32_t u[SB];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            int cc = wc + q;
-                            t4[q] = (cc >= 0 && cc < win_w) ? (float)src[cc] : 0.f;
+            for (int q = 0; q < SB; ++q) {
+                const int idx = base + q * CORR_THREADS + tid;
+                uint32_t w = 0u;
+                if (idx < nq) {
+                    const int r = idx / p4, c4 = idx - r * p4;
+                    const int wr = row0 + r, wc = J.off_x + c4 * 4;
+                    if (wr >= 0 && wr < win_h) {
+                        const uint8_t *src = wbase + (int64_t)wr * wp;
+                        if (((wc & 3) == 0) && wc >= 0 && wc + 4 <= wp) {
+                            // window rows are zero padded up to the pitch, so a full word is always valid
+                            w = __ldg(reinterpret_cast<const uint32_t *>(src + wc));
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int cc = wc + e;
+                                if (cc >= 0 && cc < win_w) w |= (uint32_t)__ldg(src + cc) << (8 * e);
+                            }
                         }
-                        o = make_float4(t4[0], t4[1], t4[2], t4[3]);
                     }
                 }
-                dst[c4] = o;
+                u[q] = w;
+            }
+#pragma unroll
+            for (int q = 0; q < SB; ++q) {
+                const int idx = base + q * CORR_THREADS + tid;
+                if (idx < nq) {
+                    float4 o;
+                    o.x = __uint_as_float(__byte_perm(u[q], 0x4B000000u, 0x7540)) - 8388608.f;
+                    o.y = __uint_as_float(__byte_perm(u[q], 0x4B000000u, 0x7541)) - 8388608.f;
+                    o.z = __uint_as_float(__byte_perm(u[q], 0x4B000000u, 0x7542)) - 8388608.f;
+                    o.w = __uint_as_float(__byte_perm(u[q], 0x4B000000u, 0x7543)) - 8388608.f;
+                    reinterpret_cast<float4 *>(tile)[idx] = o;
+                }
             }
         }
     }
@@ -136,45 +193,49 @@ __global__ void __launch_bounds__(CORR_THREADS, (KW <= 32) ? 2 : 1) k_corr(const
         for (int k = 0; k < TX; ++k) acc[t][k] = J.init;
 
     const float *prow = tile + rbase * pitch + cg * TX;
-    const int nr = J.kh + TY - 1;
     const int kh = J.kh;
-    for (int r = 0; r < nr; ++r) {
-        float p[NP];
-        const float4 *src = reinterpret_cast<const float4 *>(prow + r * pitch);
-#pragma unroll
-        for (int q = 0; q < NP / 4; ++q) {
-            float4 v = src[q];
-            p[4 * q + 0] = v.x;
-            p[4 * q + 1] = v.y;
-            p[4 * q + 2] = v.z;
-            p[4 * q + 3] = v.w;
-        }
+    const int nr = kh + TY - 1;
+    // Tile row r feeds output row t with kernel row j = r - t.  A kernel row is applied in two halves
+    // (taps [0,H0) then [H0,KW)): per accumulator the tap order is unchanged, but each half needs only
+    // ~TX+KW/2 pixel registers, which leaves room to double-buffer them: while one half is being
+    // multiplied the pixels of the next half (or of the next tile row) are already in flight, so the
+    // steady state never waits at a shared-memory load.  Rows 0..TY-2 and kh..kh+TY-2 touch only some of
+    // the TY output rows and run through the generic, branchy path.
+    constexpr int H0 = (KW >= 8) ? (((KW / 2) + 3) / 4) * 4 : KW;
+    constexpr int H1 = KW - H0;
+    constexpr int NP0 = ((TX + H0 - 1 + 3) / 4) * 4;
+    constexpr int NP1 = (H1 > 0) ? ((TX + H1 - 1 + 3) / 4) * 4 : 4;
+    static_assert(H0 + NP1 <= NP + 4 && NP0 <= NP, "half windows stay inside the staged row");
+    float pa[NP0], pb[NP1];
+    auto generic_row = [&](int r) {
+        load_pixels<NP0>(pa, prow + r * pitch);
+        if (H1 > 0) load_pixels<NP1>(pb, prow + r * pitch + H0);
 #pragma unroll
         for (int t = 0; t < TY; ++t) {
             const int j = r - t;
             if (j >= 0 && j < kh) {
-                const float4 *wr = reinterpret_cast<const float4 *>(wsm + j * KW4);
-                float wv[KW4];
-#pragma unroll
-                for (int q = 0; q < KW4 / 4; ++q) {
-                    float4 v = wr[q];
-                    wv[4 * q + 0] = v.x;
-                    wv[4 * q + 1] = v.y;
-                    wv[4 * q + 2] = v.z;
-                    wv[4 * q + 3] = v.w;
-                }
-#pragma unroll
-                for (int i = 0; i < KW; ++i) {
-#pragma unroll
-                    for (int k = 0; k < TX; ++k) {
-                        if (FMA)
-                            acc[t][k] = __fmaf_rn(wv[i], p[i + k], acc[t][k]);
-                        else
-                            acc[t][k] = __fadd_rn(acc[t][k], __fmul_rn(wv[i], p[i + k]));
-                    }
-                }
+                corr_taps<H0, TX, FMA, NP0>(acc[t], pa, wsm + j * KW4);
+                if (H1 > 0) corr_taps<(H1 > 0 ? H1 : 1), TX, FMA, NP1>(acc[t], pb, wsm + j * KW4 + H0);
             }
         }
+    };
+    if (kh >= TY) {
+        for (int r = 0; r < TY - 1; ++r) generic_row(r);
+        load_pixels<NP0>(pa, prow + (TY - 1) * pitch);
+        for (int r = TY - 1; r < kh; ++r) {
+            if (H1 > 0) load_pixels<NP1>(pb, prow + r * pitch + H0);
+#pragma unroll
+            for (int t = 0; t < TY; ++t) corr_taps<H0, TX, FMA, NP0>(acc[t], pa, wsm + (r - t) * KW4);
+            load_pixels<NP0>(pa, prow + (r + 1) * pitch);
+            if (H1 > 0) {
+#pragma unroll
+                for (int t = 0; t < TY; ++t)
+                    corr_taps<(H1 > 0 ? H1 : 1), TX, FMA, NP1>(acc[t], pb, wsm + (r - t) * KW4 + H0);
+            }
+        }
+        for (int r = kh; r < nr; ++r) generic_row(r);
+    } else {
+        for (int r = 0; r < nr; ++r) generic_row(r);
     }
 
     // ---- epilogue ------------------------------------------------------------------------------------

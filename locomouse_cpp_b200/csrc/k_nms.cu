@@ -141,13 +141,18 @@ __device__ void write_candidates(const NmsSmem &m, int n, const int *slot_of_roo
 }
 
 // ---- nmsMax ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NMS_THREADS) k_nms_bottom(const __grid_constant__ LmBatch b, int P) {
+__global__ void __launch_bounds__(NMS_THREADS) k_nms_bottom(const __grid_constant__ LmBatch b, int P, int lo, int hi) {
     extern __shared__ __align__(16) unsigned char raw[];
     NmsSmem m = carve(raw, P);
     int *slot = reinterpret_cast<int *>(m.y + P);      // [P] slot of a root rank
     int *root_rank = slot + P;                          // [cand_cap]
     __shared__ int s_n, s_nc;
     const int f = blockIdx.x >> 1, feat = blockIdx.x & 1, tid = threadIdx.x;
+    {   // size class of this list (the two launches partition the lists by raw count)
+        int c = b.det_count[(f * 2 + feat) * 2 + LM_BOTTOM];
+        c = c > b.det_cap ? b.det_cap : c;
+        if (c <= lo || c > hi) return;
+    }
     bool overflow;
     const int n = load_and_sort(b, f, feat, LM_BOTTOM, m, P, &s_n, &overflow);
     const LmTemplateDev &T = b.tmpl[LM_BOTTOM][feat];
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_bottom(const __grid_constan
 }
 
 // ---- peakClustering ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NMS_THREADS) k_nms_side(const __grid_constant__ LmBatch b, int P) {
+__global__ void __launch_bounds__(NMS_THREADS) k_nms_side(const __grid_constant__ LmBatch b, int P, int lo, int hi) {
     extern __shared__ __align__(16) unsigned char raw[];
     NmsSmem m = carve(raw, P);
     int *slot = reinterpret_cast<int *>(m.y + P);
@@ -212,6 +217,11 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_side(const __grid_constant_
     __shared__ int s_n;
     const int f = blockIdx.x >> 1, feat = blockIdx.x & 1, tid = threadIdx.x;
     lm_cand *out = b.side + (int64_t)(f * 2 + feat) * b.cand_cap;
+    {
+        int c = b.det_count[(f * 2 + feat) * 2 + LM_SIDE];
+        c = c > b.det_cap ? b.det_cap : c;
+        if (c <= lo || c > hi) return;
+    }
     if (b.n_bottom[f * 2 + feat] == 0) {  // Q6
         for (int k = tid; k < b.cand_cap; k += NMS_THREADS) {
             lm_cand c;
@@ -266,14 +276,28 @@ size_t nms_smem(int P, int cand_cap) {
 int lm_launch_nms(const LmBatch &b, cudaStream_t s) {
     int P = 2;
     while (P < b.det_cap) P <<= 1;
-    size_t smem = nms_smem(P, b.cand_cap);
+    // Two size classes: lists of up to SMALL positives run with a small shared-memory footprint (several
+    // CTAs per SM); the rare longer lists run in a second launch sized for det_cap (its other CTAs exit at once).
+    const int SMALL = 1024;
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(k_nms_bottom, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_nms_side, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr_done = true;
     }
-    k_nms_bottom<<<b.B * 2, NMS_THREADS, smem, s>>>(b, P);
-    k_nms_side<<<b.B * 2, NMS_THREADS, smem, s>>>(b, P);
-    return 2;
+    int launches = 0;
+    const int Ps = P < SMALL ? P : SMALL;
+    k_nms_bottom<<<b.B * 2, NMS_THREADS, nms_smem(Ps, b.cand_cap), s>>>(b, Ps, -1, Ps);
+    ++launches;
+    if (P > Ps) {
+        k_nms_bottom<<<b.B * 2, NMS_THREADS, nms_smem(P, b.cand_cap), s>>>(b, P, Ps, P);
+        ++launches;
+    }
+    k_nms_side<<<b.B * 2, NMS_THREADS, nms_smem(Ps, b.cand_cap), s>>>(b, Ps, -1, Ps);
+    ++launches;
+    if (P > Ps) {
+        k_nms_side<<<b.B * 2, NMS_THREADS, nms_smem(P, b.cand_cap), s>>>(b, P, Ps, P);
+        ++launches;
+    }
+    return launches;
 }

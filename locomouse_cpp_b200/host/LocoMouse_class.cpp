@@ -1,0 +1,564 @@
+// LocoMouse_class.cpp — host-side mirror of the reference's LocoMouse / LocoMouse_TM / LocoMouse_TM_DE
+// for the per-frame detection path; see LocoMouse_class.hpp.  All pixel work happens behind the C ABI
+// (include/locomouse_b200.h); nothing here computes scores, masks or candidates.
+#include "LocoMouse_class.hpp"
+
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+
+#include "lm_files.hpp"
+
+// =====================================================================================================
+// LocoMouse_ParseInputs (LocoMouse_ParseInputs.cpp:56-100)
+// =====================================================================================================
+LocoMouse_ParseInputs::LocoMouse_ParseInputs(int argc, char *argv[]) {
+    if (argc != 9)
+        // The reference falls back to sample files that are not shipped (LocoMouse_ParseInputs.cpp:62-84);
+        // here a wrong argument list is an input error.
+        throw std::invalid_argument(
+            "Invalid input list. The input should be: LocoMouse method config.yml video background model_file "
+            "calibration_file side_char output_folder.");
+    LM_CALL = argv[0];
+    METHOD = argv[1];
+    CONFIG_FILE = argv[2];
+    VIDEO_FILE = argv[3];
+    BKG_FILE = argv[4];
+    MODEL_FILE = argv[5];
+    CALIBRATION_FILE = argv[6];
+    FLIP_CHAR = argv[7];
+    OUTPUT_PATH = argv[8];
+    FILE_STEM = stripFileName(VIDEO_FILE);
+    const size_t slash = LM_CALL.find_last_of("/\\");
+    REF_PATH = slash == std::string::npos ? "./" : LM_CALL.substr(0, slash + 1);
+}
+
+std::string LocoMouse_ParseInputs::stripFileName(const std::string &s) {
+    const size_t slash = s.find_last_of("/\\");
+    std::string base = slash == std::string::npos ? s : s.substr(slash + 1);
+    const size_t dot = base.find_last_of('.');
+    return dot == std::string::npos ? base : base.substr(0, dot);
+}
+
+// =====================================================================================================
+// LocoMouse_Parameters: "key: value" scalars and "[a, b, c, d]" boxes (the subset of config.yml that the
+// detection path reads; range checks as LocoMouse_class.cpp:17-249 / LocoMouse_TM.cpp:57-112)
+// =====================================================================================================
+namespace {
+
+std::string trim(const std::string &s) {
+    size_t a = 0, b = s.size();
+    while (a < b && std::isspace((unsigned char)s[a])) ++a;
+    while (b > a && std::isspace((unsigned char)s[b - 1])) --b;
+    return s.substr(a, b - a);
+}
+
+std::vector<double> parse_list(const std::string &v, const std::string &key) {
+    std::string t = trim(v);
+    if (t.size() < 2 || t.front() != '[' || t.back() != ']') throw std::invalid_argument(key + " must be a [..] list.");
+    std::stringstream ss(t.substr(1, t.size() - 2));
+    std::vector<double> out;
+    std::string item;
+    while (std::getline(ss, item, ',')) out.push_back(std::stod(trim(item)));
+    return out;
+}
+
+cv::Rect parse_rect(const std::string &v, const std::string &key) {
+    std::vector<double> l = parse_list(v, key);
+    if (l.size() != 4) throw std::invalid_argument(key + " must have 4 entries: [x, y, width, height].");
+    return cv::Rect((int)l[0], (int)l[1], (int)l[2], (int)l[3]);
+}
+
+}  // namespace
+
+LocoMouse_Parameters::LocoMouse_Parameters(const std::string &config_file_name) {
+    std::ifstream in(config_file_name);
+    if (!in) throw std::invalid_argument("Could not open the configuration file: " + config_file_name);
+    std::string line;
+    while (std::getline(in, line)) {
+        const size_t hash = line.find('#');
+        if (hash != std::string::npos) line.erase(hash);
+        if (line.rfind("%YAML", 0) == 0 || line.rfind("---", 0) == 0) continue;
+        const size_t colon = line.find(':');
+        if (colon == std::string::npos) continue;
+        const std::string key = trim(line.substr(0, colon)), val = trim(line.substr(colon + 1));
+        if (val.empty()) continue;
+        try {
+            if (key == "conn_comp_connectivity") conn_comp_connectivity = std::stoi(val);
+            else if (key == "side_bottom_min_overlap") side_bottom_min_overlap = std::stod(val);
+            else if (key == "tail_sub_bounding_box") tail_sub_bounding_box = std::stod(val);
+            else if (key == "use_provided_bounding_box") use_provided_bb = std::stoi(val);
+            else if (key == "bounding_box_side") BB_USER_SIDE = parse_rect(val, key);
+            else if (key == "bounding_box_bottom") BB_USER_BOTTOM = parse_rect(val, key);
+            else if (key == "bb_width") bb_width = std::stoi(val);
+            else if (key == "bb_height_side") bb_height_side = std::stoi(val);
+            else if (key == "bounding_box_file") bounding_box_file = val;
+            else if (key == "device") device = std::stoi(val);
+            else if (key == "batch_frames") batch_frames = std::stoi(val);
+            else if (key == "fma_mode") fma_mode = std::stoi(val);
+            else if (key == "cand_cap") cand_cap = std::stoi(val);
+            else if (key == "det_cap") det_cap = std::stoi(val);
+            else if (key == "match_cap") match_cap = std::stoi(val);
+            // every other reference key belongs to pass 1 or to the host tracker and is ignored here
+        } catch (const std::invalid_argument &) {
+            throw;
+        } catch (const std::exception &) {
+            throw std::invalid_argument("Could not parse the value of " + key + " in " + config_file_name);
+        }
+    }
+    if (conn_comp_connectivity != 4 && conn_comp_connectivity != 8)
+        throw std::invalid_argument("conn_comp_connectivity must be either 4 or 8.");
+    if (!(side_bottom_min_overlap >= 0 && side_bottom_min_overlap <= 1))
+        throw std::invalid_argument("side_bottom_min_overlap must belong to [0, 1].");
+    if (!(tail_sub_bounding_box >= 0 && tail_sub_bounding_box <= 1))
+        throw std::invalid_argument("tail_sub_bounding_box must belong to [0, 1].");
+    if (bb_width <= 0 || bb_height_side <= 0) throw std::invalid_argument("bb_width and bb_height_side must be positive.");
+    if (batch_frames <= 0) throw std::invalid_argument("batch_frames must be positive.");
+}
+
+// =====================================================================================================
+// LocoMouse_Feature / LocoMouse_Model (LocoMouse_class.cpp:2941-2990, 3095-3162)
+// =====================================================================================================
+namespace {
+// Rect(-(round(w/2)/2), -(round(h/2)/2), round(w/2), round(h/2)) — LocoMouse_class.cpp:2954-2969
+cv::Rect half_box(cv::Size s) {
+    const int w = (int)std::lround(s.width / 2.0), h = (int)std::lround(s.height / 2.0);
+    return cv::Rect(-(w / 2), -(h / 2), w, h);
+}
+}  // namespace
+
+LocoMouse_Feature::LocoMouse_Feature(std::vector<float> w_b, cv::Size size_b, double rho_b, std::vector<float> w_s,
+                                     cv::Size size_s, double rho_s)
+    : W_B(std::move(w_b)), W_S(std::move(w_s)), SIZE_B(size_b), SIZE_S(size_s), RHO_B(rho_b), RHO_S(rho_s),
+      MATCH_BOX_B(half_box(size_b)), MATCH_BOX_S(half_box(size_s)) {}
+
+LocoMouse_Model::LocoMouse_Model(const std::string &model_file_name) {
+    lmfile::Reader r(model_file_name, "LMM1");
+    std::vector<float> w[6];
+    cv::Size sz[6];
+    double rho[6];
+    for (int k = 0; k < 6; ++k) {
+        const int rows = r.i32(), cols = r.i32();
+        rho[k] = r.f64();
+        if (rows <= 0 || cols <= 0 || rows > 4096 || cols > 4096) throw std::runtime_error("Model file holds an empty or oversized template.");
+        w[k].resize((size_t)rows * cols);
+        r.read(w[k].data(), w[k].size());
+        sz[k] = cv::Size(cols, rows);
+    }
+    paw = LocoMouse_Feature(w[0], sz[0], rho[0], w[3], sz[3], rho[3]);
+    snout = LocoMouse_Feature(w[1], sz[1], rho[1], w[4], sz[4], rho[4]);
+    tail = LocoMouse_Feature(w[2], sz[2], rho[2], w[5], sz[5], rho[5]);
+}
+
+// =====================================================================================================
+// LocoMouse
+// =====================================================================================================
+struct LocoMouse::Batch {
+    unsigned int first = 0, count = 0;
+    int cand_cap = 0, match_cap = 0, n_tail = 0;
+    std::vector<int32_t> n_bottom, n_side, match_n, match_y, tail;
+    std::vector<lm_cand> bottom, side;
+    std::vector<double> match_s;
+    std::vector<uint32_t> flags;
+    lm_results view() {
+        lm_results r{};
+        r.n_frames = count;
+        r.cand_cap = cand_cap;
+        r.match_cap = match_cap;
+        r.n_tail_points = n_tail;
+        r.n_bottom = n_bottom.data();
+        r.n_side = n_side.data();
+        r.bottom = bottom.data();
+        r.side = side.data();
+        r.match_n = match_n.data();
+        r.match_y = match_y.data();
+        r.match_s = match_s.data();
+        r.tail = tail.data();
+        r.flags = flags.data();
+        return r;
+    }
+};
+
+void LocoMouse::check(int rc) const {
+    if (rc == LM_OK) return;
+    const std::string msg = lm_last_error(CTX);
+    if (rc == LM_ERR_INVALID) throw std::invalid_argument(msg);
+    throw std::runtime_error(msg);  // LM_ERR_RUNTIME, LM_ERR_ROI, LM_ERR_OVERFLOW, LM_ERR_STATE
+}
+
+void LocoMouse::initializePaths(const LocoMouse_ParseInputs &INPUT) {
+    LM_CALL = INPUT.LM_CALL;
+    CONFIG_FILE = INPUT.CONFIG_FILE;
+    VIDEO_FILE = INPUT.VIDEO_FILE;
+    BKG_FILE = INPUT.BKG_FILE;
+    MODEL_FILE = INPUT.MODEL_FILE;
+    CALIBRATION_FILE = INPUT.CALIBRATION_FILE;
+    FLIP_CHAR = INPUT.FLIP_CHAR;
+    OUTPUT_PATH = INPUT.OUTPUT_PATH;
+    // output_<stem>.* next to the reference's output_<stem>.yml (LocoMouse_class.cpp:360)
+    output_file = OUTPUT_PATH + "/output_" + INPUT.FILE_STEM + ".lmo";
+}
+
+void LocoMouse::loadVideo() {
+    lmfile::Reader r(VIDEO_FILE, "LMV1");
+    const int n = r.i32();
+    VID_ROWS = r.i32();
+    VID_COLS = r.i32();
+    if (n <= 0 || VID_ROWS <= 0 || VID_COLS <= 0) throw std::runtime_error("Video file is empty: " + VIDEO_FILE);
+    N_FRAMES = (unsigned int)n;
+    VIDEO.resize((size_t)n * VID_ROWS * VID_COLS);
+    r.read(VIDEO.data(), VIDEO.size());
+}
+
+void LocoMouse::loadBackground() {
+    lmfile::Reader r(BKG_FILE, "LMI1");
+    const int rows = r.i32(), cols = r.i32();
+    if (rows <= 0 || cols <= 0) throw std::runtime_error("Background image is empty: " + BKG_FILE);
+    BKG.resize((size_t)rows * cols);
+    r.read(BKG.data(), BKG.size());
+    // size is checked against the video in validateImageVideoSize
+    if (rows != VID_ROWS || cols != VID_COLS) throw std::runtime_error("Background image and video frames must have the same size.");
+}
+
+void LocoMouse::loadCalibration() {
+    lmfile::Reader r(CALIBRATION_FILE, "LMC1");
+    const int rows = r.i32(), cols = r.i32();
+    if (rows <= 0 || cols <= 0) throw std::invalid_argument("ind_warp_mapping is empty or undefined.");
+    int32_t vb[8];
+    r.read(vb, 8);
+    BB_SIDE_VIEW = cv::Rect(vb[0], vb[1], vb[2], vb[3]);
+    BB_BOTTOM_VIEW = cv::Rect(vb[4], vb[5], vb[6], vb[7]);
+    N_ROWS = (unsigned int)rows;
+    N_COLS = (unsigned int)cols;
+    CALIBRATION.resize((size_t)rows * cols);
+    r.read(CALIBRATION.data(), CALIBRATION.size());
+}
+
+void LocoMouse::loadFlip() {
+    if (FLIP_CHAR.length() != 1 || (FLIP_CHAR[0] != 'L' && FLIP_CHAR[0] != 'R'))
+        throw std::invalid_argument("Mouse side option must be either \"L\" or \"R\".");
+    IMAGE_FLIP = FLIP_CHAR[0] == 'L';
+}
+
+// LocoMouse_class.cpp:486-540: the calibration map must address pixels of the video frame and the view boxes
+// must lie inside the calibrated image.
+void LocoMouse::validateImageVideoSize() {
+    const int64_t lim = (int64_t)VID_ROWS * VID_COLS;
+    for (int32_t v : CALIBRATION)
+        if (v < 0 || v >= lim) throw std::runtime_error("Calibration mapping indices do not match the video size.");
+    auto inside = [&](const cv::Rect &b) {
+        return b.x >= 0 && b.y >= 0 && b.width > 0 && b.height > 0 && b.x + b.width <= (int)N_COLS && b.y + b.height <= (int)N_ROWS;
+    };
+    if (!inside(BB_SIDE_VIEW) || !inside(BB_BOTTOM_VIEW)) throw std::runtime_error("view_boxes do not fit the calibrated image.");
+}
+
+LocoMouse::LocoMouse(LocoMouse_ParseInputs INPUTS) {
+    initializePaths(INPUTS);
+    LM_PARAMS = LocoMouse_Parameters(CONFIG_FILE);
+    loadVideo();
+    loadBackground();
+    loadCalibration();
+    validateImageVideoSize();
+    M = LocoMouse_Model(MODEL_FILE);
+    loadFlip();
+    // sized, not merely reserved (the reference indexes reserved vectors)
+    BB_X_POS.assign(N_FRAMES, 0);
+    BB_Y_SIDE_POS.assign(N_FRAMES, 0);
+    BB_Y_BOTTOM_POS.assign(N_FRAMES, 0);
+    const int rc = lm_create(&CTX, LM_PARAMS.device);
+    if (rc != LM_OK) throw std::runtime_error(std::string("lm_create: ") + lm_last_error(nullptr));
+}
+
+LocoMouse::~LocoMouse() { lm_destroy(CTX); }
+
+// ---- pass 1 (out of scope): positions come from the user box or from a pass-1 output file -------------
+namespace {
+void read_boxes(const std::string &file, unsigned int n_frames, std::vector<unsigned int> &x, std::vector<unsigned int> &ys,
+                std::vector<unsigned int> &yb) {
+    if (file.empty())
+        throw std::invalid_argument(
+            "The first pass (computeBoundingBox) is not part of this library: set use_provided_bounding_box or "
+            "bounding_box_file in the configuration.");
+    lmfile::Reader r(file, "LMB1");
+    const int n = r.i32();
+    if (n < 0 || (unsigned int)n != n_frames) throw std::runtime_error("bounding_box_file does not match the number of video frames.");
+    x.resize(n_frames);
+    ys.resize(n_frames);
+    yb.resize(n_frames);
+    r.read(x.data(), n_frames);
+    r.read(ys.data(), n_frames);
+    r.read(yb.data(), n_frames);
+}
+}  // namespace
+
+void LocoMouse::getBoundingBox() {
+    if (LM_PARAMS.use_provided_bb) {
+        // LocoMouse_class.cpp:545-567: bottom-right corner = origin + size, boxes re-anchored at (0, 0)
+        const unsigned int x = LM_PARAMS.BB_USER_BOTTOM.x + LM_PARAMS.BB_USER_BOTTOM.width;
+        const unsigned int ys = LM_PARAMS.BB_USER_SIDE.y + LM_PARAMS.BB_USER_SIDE.height;
+        const unsigned int yb = LM_PARAMS.BB_USER_BOTTOM.y + LM_PARAMS.BB_USER_BOTTOM.height;
+        std::fill(BB_X_POS.begin(), BB_X_POS.end(), x);
+        std::fill(BB_Y_SIDE_POS.begin(), BB_Y_SIDE_POS.end(), ys);
+        std::fill(BB_Y_BOTTOM_POS.begin(), BB_Y_BOTTOM_POS.end(), yb);
+        BB_BOTTOM_MOUSE = cv::Rect(0, 0, LM_PARAMS.BB_USER_BOTTOM.width, LM_PARAMS.BB_USER_BOTTOM.height);
+        BB_SIDE_MOUSE = cv::Rect(0, 0, LM_PARAMS.BB_USER_SIDE.width, LM_PARAMS.BB_USER_SIDE.height);
+    } else {
+        computeBoundingBox();
+    }
+}
+
+// Base method: positions and (via bounding_box_side / bounding_box_bottom widths and heights) sizes are
+// pass-1 outputs (LocoMouse_class.cpp:578-653 computes them from the whole video).
+void LocoMouse::computeBoundingBox() {
+    read_boxes(LM_PARAMS.bounding_box_file, N_FRAMES, BB_X_POS, BB_Y_SIDE_POS, BB_Y_BOTTOM_POS);
+    if (LM_PARAMS.BB_USER_BOTTOM.width <= 0 || LM_PARAMS.BB_USER_SIDE.width <= 0)
+        throw std::invalid_argument("bounding_box_side / bounding_box_bottom must give the box sizes for the default method.");
+    BB_BOTTOM_MOUSE = cv::Rect(0, 0, LM_PARAMS.BB_USER_BOTTOM.width, LM_PARAMS.BB_USER_BOTTOM.height);
+    BB_SIDE_MOUSE = cv::Rect(0, 0, LM_PARAMS.BB_USER_SIDE.width, LM_PARAMS.BB_USER_SIDE.height);
+}
+
+LocoMouse_TM::LocoMouse_TM(LocoMouse_ParseInputs INPUTS) : LocoMouse(INPUTS) { METHOD = 1; }
+
+// LocoMouse_TM.cpp:115-157: x from pass 1, bottom anchor = last image row, side anchor = row 164.
+void LocoMouse_TM::computeBoundingBox() {
+    std::vector<unsigned int> ys, yb;
+    read_boxes(LM_PARAMS.bounding_box_file, N_FRAMES, BB_X_POS, ys, yb);
+    std::fill(BB_Y_BOTTOM_POS.begin(), BB_Y_BOTTOM_POS.end(), N_ROWS - 1);
+    std::fill(BB_Y_SIDE_POS.begin(), BB_Y_SIDE_POS.end(), 165u - 1u);
+    BB_SIDE_MOUSE = cv::Rect(0, 0, LM_PARAMS.bb_width, LM_PARAMS.bb_height_side);
+    BB_BOTTOM_MOUSE = cv::Rect(0, 0, LM_PARAMS.bb_width, BB_BOTTOM_VIEW.height);
+}
+
+LocoMouse_TM_DE::LocoMouse_TM_DE(LocoMouse_ParseInputs INPUTS) : LocoMouse_TM(INPUTS) { METHOD = 2; }
+
+// LocoMouse_TM_DE.cpp:8-53: side anchor = last row of the side view, 400-wide boxes over the full view heights.
+void LocoMouse_TM_DE::computeBoundingBox() {
+    std::vector<unsigned int> ys, yb;
+    read_boxes(LM_PARAMS.bounding_box_file, N_FRAMES, BB_X_POS, ys, yb);
+    std::fill(BB_Y_BOTTOM_POS.begin(), BB_Y_BOTTOM_POS.end(), N_ROWS - 1);
+    std::fill(BB_Y_SIDE_POS.begin(), BB_Y_SIDE_POS.end(), (unsigned int)BB_SIDE_VIEW.height - 1u);
+    BB_SIDE_MOUSE = cv::Rect(0, 0, 400, BB_SIDE_VIEW.height);
+    BB_BOTTOM_MOUSE = cv::Rect(0, 0, 400, BB_BOTTOM_VIEW.height);
+}
+
+// ---- initializeFeatureLoop (LocoMouse_class.cpp:655-769): hand the per-video state to the device -------
+void LocoMouse::initializeFeatureLoop() {
+    if (BB_BOTTOM_MOUSE.width <= 0 || BB_BOTTOM_MOUSE.width != BB_SIDE_MOUSE.width)
+        throw std::invalid_argument("getBoundingBox() must run first and both views must share the box width.");
+    lm_config c{};
+    c.vid_rows = VID_ROWS;
+    c.vid_cols = VID_COLS;
+    c.n_rows = (int)N_ROWS;
+    c.n_cols = (int)N_COLS;
+    c.bb_w = BB_BOTTOM_MOUSE.width;
+    c.bb_h_bottom = BB_BOTTOM_MOUSE.height;
+    c.bb_h_side = BB_SIDE_MOUSE.height;
+    c.tail_w = (int)(unsigned int)((int)(double)(BB_BOTTOM_MOUSE.width) * LM_PARAMS.tail_sub_bounding_box);  // class.cpp:711
+    c.flip = IMAGE_FLIP ? 1 : 0;
+    c.imadjust = usesImadjust() ? 1 : 0;
+    c.conn = LM_PARAMS.conn_comp_connectivity;
+    c.n_tail_points = (int)LM_PARAMS.N_tail_points;
+    c.min_overlap = LM_PARAMS.side_bottom_min_overlap;
+    c.fma_mode = LM_PARAMS.fma_mode;
+    c.cand_cap = LM_PARAMS.cand_cap;
+    c.det_cap = LM_PARAMS.det_cap;
+    c.match_cap = LM_PARAMS.match_cap;
+    check(lm_configure(CTX, &c));
+    const LocoMouse_Feature *F[3] = {&M.paw, &M.snout, &M.tail};
+    lm_template t[2][3];
+    for (int k = 0; k < 3; ++k) {
+        t[LM_BOTTOM][k] = lm_template{F[k]->w_b().data(), F[k]->size_bottom().height, F[k]->size_bottom().width, F[k]->rho_b()};
+        t[LM_SIDE][k] = lm_template{F[k]->w_s().data(), F[k]->size_side().height, F[k]->size_side().width, F[k]->rho_s()};
+    }
+    check(lm_set_model(CTX, t));
+    check(lm_set_background(CTX, BKG.data()));
+    check(lm_set_calibration(CTX, CALIBRATION.data()));
+
+    CANDIDATES_BOTTOM_PAW.clear();
+    CANDIDATES_BOTTOM_SNOUT.clear();
+    CANDIDATES_SIDE_PAW.clear();
+    CANDIDATES_SIDE_SNOUT.clear();
+    CANDIDATES_MATCHED_VIEWS_PAW.clear();
+    CANDIDATES_MATCHED_VIEWS_SNOUT.clear();
+    TRACKS_TAIL.clear();
+    CANDIDATES_BOTTOM_PAW.reserve(N_FRAMES);
+    CANDIDATES_BOTTOM_SNOUT.reserve(N_FRAMES);
+    CANDIDATES_SIDE_PAW.reserve(N_FRAMES);
+    CANDIDATES_SIDE_SNOUT.reserve(N_FRAMES);
+    CANDIDATES_MATCHED_VIEWS_PAW.reserve(N_FRAMES);
+    CANDIDATES_MATCHED_VIEWS_SNOUT.reserve(N_FRAMES);
+    TRACKS_TAIL.reserve(N_FRAMES);
+    CURRENT_FRAME = -1;  // the reference rewinds the video here (class.cpp:762)
+    BATCH.reset();
+    LOOP_READY = true;
+}
+
+// One lm_detect_batch call for frames [first, first + batch_frames): this is the whole hot loop of
+// main.cpp:54-82 for those frames.
+void LocoMouse::runChunk(unsigned int first) {
+    const unsigned int n = std::min<unsigned int>((unsigned int)LM_PARAMS.batch_frames, N_FRAMES - first);
+    std::unique_ptr<Batch> b(new Batch());
+    b->first = first;
+    b->count = n;
+    b->cand_cap = LM_PARAMS.cand_cap;
+    b->match_cap = LM_PARAMS.match_cap;
+    b->n_tail = (int)LM_PARAMS.N_tail_points;
+    b->n_bottom.resize((size_t)n * 2);
+    b->n_side.resize((size_t)n * 2);
+    b->bottom.resize((size_t)n * 2 * b->cand_cap);
+    b->side.resize((size_t)n * 2 * b->cand_cap);
+    b->match_n.resize((size_t)n * 2 * b->cand_cap);
+    b->match_y.resize((size_t)n * 2 * b->match_cap);
+    b->match_s.resize((size_t)n * 2 * b->match_cap);
+    b->tail.resize((size_t)n * 3 * b->n_tail);
+    b->flags.resize(n);
+    lm_results r = b->view();
+    const size_t fsz = (size_t)VID_ROWS * VID_COLS;
+    const uint8_t *prev = first > 0 ? VIDEO.data() + (size_t)(first - 1) * fsz : nullptr;
+    check(lm_detect_batch(CTX, VIDEO.data() + (size_t)first * fsz, /*frames_on_device=*/0, prev, n, first, BB_X_POS.data() + first,
+                          BB_Y_SIDE_POS.data() + first, BB_Y_BOTTOM_POS.data() + first, &r));
+    BATCH = std::move(b);
+}
+
+const LocoMouse::Batch &LocoMouse::batchFor(int frame) const {
+    if (!BATCH || frame < (int)BATCH->first || frame >= (int)(BATCH->first + BATCH->count))
+        throw std::runtime_error("readFrame() must be called before the per-frame detection methods.");
+    return *BATCH;
+}
+
+// ---- the per-frame methods (same names and order as main.cpp:57-80) ---------------------------------
+void LocoMouse::readFrame() {
+    if (!LOOP_READY) throw std::runtime_error("initializeFeatureLoop() must be called before readFrame().");
+    if (CURRENT_FRAME + 1 >= (int)N_FRAMES) throw std::runtime_error("readFrame(): no more frames.");
+    ++CURRENT_FRAME;
+    if (!BATCH || CURRENT_FRAME >= (int)(BATCH->first + BATCH->count)) runChunk((unsigned int)CURRENT_FRAME);
+}
+
+void LocoMouse::cropBoundingBox() { batchFor(CURRENT_FRAME); }  // rect validity was checked by lm_detect_batch (LM_ERR_ROI)
+
+void LocoMouse::detectTail() {
+    const Batch &b = batchFor(CURRENT_FRAME);
+    const size_t i = (size_t)CURRENT_FRAME - b.first, len = (size_t)3 * b.n_tail;
+    TRACKS_TAIL.emplace_back(b.tail.begin() + i * len, b.tail.begin() + (i + 1) * len);
+}
+
+namespace {
+std::vector<Candidate> to_candidates(const lm_cand *c, int n) {
+    std::vector<Candidate> v;
+    v.reserve(n);
+    for (int i = 0; i < n; ++i) v.emplace_back(c[i].x, c[i].y, c[i].s);
+    return v;
+}
+}  // namespace
+
+void LocoMouse::detectBottomCandidates() {
+    const Batch &b = batchFor(CURRENT_FRAME);
+    const size_t i = (size_t)CURRENT_FRAME - b.first;
+    CANDIDATES_BOTTOM_PAW.push_back(to_candidates(&b.bottom[(i * 2 + LM_PAW) * b.cand_cap], b.n_bottom[i * 2 + LM_PAW]));
+    CANDIDATES_BOTTOM_SNOUT.push_back(to_candidates(&b.bottom[(i * 2 + LM_SNOUT) * b.cand_cap], b.n_bottom[i * 2 + LM_SNOUT]));
+}
+
+// computeUnaryCostsBottom / computePairwiseCostsBottom (LocoMouse_class.cpp:873-919) build the host tracker's
+// MyMat / MATSPARSE inputs from the candidate lists above; they belong to the tracker (out of scope)
+// and are left to the caller's existing implementation.
+void LocoMouse::computeUnaryCostsBottom() {}
+void LocoMouse::computePairwiseCostsBottom() {}
+
+void LocoMouse::detectSideCandidates() {
+    const Batch &b = batchFor(CURRENT_FRAME);
+    const size_t i = (size_t)CURRENT_FRAME - b.first;
+    CANDIDATES_SIDE_PAW.push_back(to_candidates(&b.side[(i * 2 + LM_PAW) * b.cand_cap], b.n_side[i * 2 + LM_PAW]));
+    CANDIDATES_SIDE_SNOUT.push_back(to_candidates(&b.side[(i * 2 + LM_SNOUT) * b.cand_cap], b.n_side[i * 2 + LM_SNOUT]));
+}
+
+// P22D records exactly as matchViews builds them (LocoMouse_class.cpp:1154-1251): P22D(Cb, Candidate(-1,-1,-1)) when a
+// bottom candidate has no accepted side match, else P22D(Cb, first) followed by add_side_candidate for the rest.
+void LocoMouse::matchBottomSideCandidates() {
+    const Batch &b = batchFor(CURRENT_FRAME);
+    const size_t i = (size_t)CURRENT_FRAME - b.first;
+    for (int feat = 0; feat < 2; ++feat) {
+        const std::vector<Candidate> &Cb = feat == LM_PAW ? CANDIDATES_BOTTOM_PAW.back() : CANDIDATES_BOTTOM_SNOUT.back();
+        const int32_t *mn = &b.match_n[(i * 2 + feat) * b.cand_cap];
+        const int32_t *my = &b.match_y[(i * 2 + feat) * b.match_cap];
+        const double *ms = &b.match_s[(i * 2 + feat) * b.match_cap];
+        std::vector<P22D> C;
+        C.reserve(Cb.size());
+        size_t o = 0;
+        for (size_t k = 0; k < Cb.size(); ++k) {
+            if (mn[k] == 0) {
+                C.push_back(P22D(Cb[k], Candidate(-1, -1, -1)));
+                continue;
+            }
+            C.push_back(P22D(Cb[k], Candidate(Cb[k].point().x, my[o], ms[o])));
+            for (int q = 1; q < mn[k]; ++q) C.back().add_side_candidate(my[o + q], ms[o + q]);
+            o += (size_t)mn[k];
+        }
+        (feat == LM_PAW ? CANDIDATES_MATCHED_VIEWS_PAW : CANDIDATES_MATCHED_VIEWS_SNOUT).push_back(std::move(C));
+    }
+}
+
+void LocoMouse::storePreviousImage() {}  // the device keeps the previous raw frame (halo) itself
+
+// The sequential tracker stays on the host unchanged (north_star); it is not part of this library.
+void LocoMouse::computeBottomTracks() {}
+void LocoMouse::computeSideTracks() {}
+
+// "LMO1": i32 n_frames, n_tail_points; per frame: 3*n_tail i32 tail track; then for paw, snout:
+//   i32 n_bottom, n_bottom x {i32 x, y; f64 s};  i32 n_side, n_side x {i32 x, y; f64 s};
+//   n_bottom x { i32 n_match, n_match x {i32 y; f64 s} }     (n_match = P22D::number_of_candidates())
+void LocoMouse::exportResults() {
+    lmfile::Writer w(output_file, "LMO1");
+    const size_t n = CANDIDATES_MATCHED_VIEWS_PAW.size();
+    w.i32((int32_t)n);
+    w.i32((int32_t)LM_PARAMS.N_tail_points);
+    auto put = [&](const std::vector<Candidate> &v) {
+        w.i32((int32_t)v.size());
+        for (const Candidate &c : v) {
+            w.i32(c.p.x);
+            w.i32(c.p.y);
+            w.f64(c.s);
+        }
+    };
+    for (size_t f = 0; f < n; ++f) {
+        w.write(TRACKS_TAIL[f].data(), TRACKS_TAIL[f].size());
+        for (int feat = 0; feat < 2; ++feat) {
+            put(feat == 0 ? CANDIDATES_BOTTOM_PAW[f] : CANDIDATES_BOTTOM_SNOUT[f]);
+            put(feat == 0 ? CANDIDATES_SIDE_PAW[f] : CANDIDATES_SIDE_SNOUT[f]);
+            const std::vector<P22D> &P = feat == 0 ? CANDIDATES_MATCHED_VIEWS_PAW[f] : CANDIDATES_MATCHED_VIEWS_SNOUT[f];
+            for (const P22D &p : P) {
+                const int m = p.number_of_candidates();
+                w.i32(m);
+                for (int q = 0; q < m; ++q) {
+                    w.i32(p.y_side_coord((uint)q));
+                    w.f64(p.score_side((uint)q));
+                }
+            }
+        }
+    }
+}
+
+// =====================================================================================================
+// LocoMouse_Initialize (LocoMouse_Methods.cpp:3-26)
+// =====================================================================================================
+std::unique_ptr<LocoMouse> LocoMouse_Initialize(LocoMouse_ParseInputs INPUT) {
+    std::unique_ptr<LocoMouse> L;
+    int mode = 0;
+    try {
+        mode = std::stoi(INPUT.METHOD);
+    } catch (const std::exception &) {
+        throw std::invalid_argument("method must be an integer: 0 (default), 1 (TM) or 2 (TM_DE).");
+    }
+    switch (mode) {
+        case 0: L.reset(new LocoMouse(INPUT)); break;
+        case 1: L.reset(new LocoMouse_TM(INPUT)); break;
+        case 2: L.reset(new LocoMouse_TM_DE(INPUT)); break;
+        default:
+            std::cout << "Unknown method option. Attempting to track with the default method." << std::endl;
+            L.reset(new LocoMouse(INPUT));
+    }
+    return L;
+}

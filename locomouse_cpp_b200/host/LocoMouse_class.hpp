@@ -1,0 +1,170 @@
+// LocoMouse_class.hpp — host-side C++ mirror of the reference's tracking-problem classes for the
+// per-frame detection path (LocoMouse_Core/LocoMouse_class.hpp:170-350, LocoMouse_TM.hpp:45-47,
+// LocoMouse_TM_DE.hpp:39-43).  Same class names, same public method names, same call sequence as
+// the reference's main.cpp:43-91, same result members (CANDIDATES_*, CANDIDATES_MATCHED_VIEWS_*,
+// TRACKS_TAIL, BB_*), same error convention (std::invalid_argument / std::runtime_error).
+//
+// What differs is WHERE the work happens: the per-frame methods do no pixel work.  The first
+// readFrame() of a chunk sends the chunk's raw frames through lm_detect_batch (include/locomouse_b200.h)
+// and the per-frame methods then move that frame's records from the batched result buffers into the
+// reference's per-frame vectors, so a driver written against the reference's interface runs
+// unmodified.  There is no CPU implementation behind these methods.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/locomouse_b200.h"
+#include "Candidates.hpp"
+#include "LocoMouse_ParseInputs.hpp"
+
+// LocoMouse_Parameters (class.hpp:48-100): the subset that reaches the detection path, plus the
+// inputs that replace the out-of-scope pass 1: per-frame box positions from a file.
+class LocoMouse_Parameters {
+public:
+    int conn_comp_connectivity = 8;
+    double side_bottom_min_overlap = 0.7;
+    double tail_sub_bounding_box = 0.6;
+    int use_provided_bb = 0;
+    cv::Rect BB_USER_SIDE, BB_USER_BOTTOM;
+    static constexpr unsigned int N_paws = 4, N_snout = 1, N_tail_points = 15;
+    // TM / TM_DE (LocoMouse_TM.cpp:57-112)
+    int bb_width = 400, bb_height_side = 150;
+    // B200 path
+    std::string bounding_box_file;  // pass-1 output (BB_X_POS, BB_Y_SIDE_POS, BB_Y_BOTTOM_POS), see lm_files.hpp
+    int device = 0;
+    int batch_frames = 4096;        // frames per lm_detect_batch call
+    int fma_mode = 1;
+    int cand_cap = 64, det_cap = 8192, match_cap = 256;
+
+    LocoMouse_Parameters() = default;
+    explicit LocoMouse_Parameters(const std::string &config_file_name);  // throws std::invalid_argument
+};
+
+// LocoMouse_Feature / LocoMouse_Model (class.hpp:110-167): templates, biases, sizes, match boxes.
+class LocoMouse_Feature {
+    std::vector<float> W_B, W_S;
+    cv::Size SIZE_B, SIZE_S;
+    double RHO_B = 0, RHO_S = 0;
+    cv::Rect MATCH_BOX_B, MATCH_BOX_S;
+
+public:
+    LocoMouse_Feature() = default;
+    LocoMouse_Feature(std::vector<float> w_b, cv::Size size_b, double rho_b, std::vector<float> w_s, cv::Size size_s,
+                      double rho_s);
+    const std::vector<float> &w_b() const { return W_B; }
+    const std::vector<float> &w_s() const { return W_S; }
+    double rho_b() const { return RHO_B; }
+    double rho_s() const { return RHO_S; }
+    cv::Size size_bottom() const { return SIZE_B; }
+    cv::Size size_side() const { return SIZE_S; }
+    cv::Rect match_box_bottom() const { return MATCH_BOX_B; }  // class.cpp:2954-2969
+    cv::Rect match_box_side() const { return MATCH_BOX_S; }
+};
+
+class LocoMouse_Model {
+public:
+    LocoMouse_Feature paw, snout, tail;
+    LocoMouse_Model() = default;
+    explicit LocoMouse_Model(const std::string &model_file_name);  // throws std::runtime_error
+};
+
+class LocoMouse {
+protected:
+    LocoMouse_Parameters LM_PARAMS;
+    std::string LM_CALL, CONFIG_FILE, VIDEO_FILE, BKG_FILE, MODEL_FILE, CALIBRATION_FILE, FLIP_CHAR, OUTPUT_PATH;
+    std::string output_file;
+
+    std::vector<uint8_t> VIDEO;       // raw 8-bit frames (channel 0), N_FRAMES x vid_rows x vid_cols
+    int VID_ROWS = 0, VID_COLS = 0;
+    std::vector<uint8_t> BKG;
+    std::vector<int32_t> CALIBRATION;  // ind_warp_mapping, N_ROWS x N_COLS
+    bool IMAGE_FLIP = false;
+
+    cv::Rect BB_SIDE_VIEW, BB_BOTTOM_VIEW;
+    cv::Rect BB_BOTTOM_MOUSE, BB_SIDE_MOUSE;
+    std::vector<unsigned int> BB_X_POS, BB_Y_SIDE_POS, BB_Y_BOTTOM_POS;
+
+    unsigned int N_FRAMES = 0, N_ROWS = 0, N_COLS = 0;
+    int CURRENT_FRAME = -1, METHOD = 0;
+
+    LocoMouse_Model M;
+
+    std::vector<std::vector<Candidate>> CANDIDATES_BOTTOM_PAW, CANDIDATES_BOTTOM_SNOUT;
+    std::vector<std::vector<Candidate>> CANDIDATES_SIDE_PAW, CANDIDATES_SIDE_SNOUT;
+    std::vector<std::vector<P22D>> CANDIDATES_MATCHED_VIEWS_PAW, CANDIDATES_MATCHED_VIEWS_SNOUT;
+    std::vector<std::vector<int32_t>> TRACKS_TAIL;  // per frame 3 x N_tail_points (x, y, z), -1 = missing
+
+    // ---- device side ------------------------------------------------------------------------------
+    lm_ctx *CTX = nullptr;
+    struct Batch;                      // result buffers of the chunk that contains CURRENT_FRAME
+    std::unique_ptr<Batch> BATCH;
+    bool LOOP_READY = false;
+
+    void initializePaths(const LocoMouse_ParseInputs &INPUT);
+    void loadVideo();
+    void loadBackground();
+    void loadCalibration();
+    void loadFlip();
+    void validateImageVideoSize();
+    void check(int rc) const;          // lm_status -> exception
+    void runChunk(unsigned int first_frame);
+    const Batch &batchFor(int frame) const;
+    virtual bool usesImadjust() const { return false; }  // LocoMouse_TM::readFrame applies imadjust(0, 0.6)
+
+public:
+    explicit LocoMouse(LocoMouse_ParseInputs INPUTS);
+    virtual ~LocoMouse();
+    LocoMouse(const LocoMouse &) = delete;
+    LocoMouse &operator=(const LocoMouse &) = delete;
+
+    virtual void readFrame();
+    virtual void getBoundingBox();
+    virtual void computeBoundingBox();
+    void initializeFeatureLoop();
+    void cropBoundingBox();
+    void detectTail();
+    void detectBottomCandidates();
+    void computeUnaryCostsBottom();
+    void computePairwiseCostsBottom();
+    void detectSideCandidates();
+    void matchBottomSideCandidates();
+    void storePreviousImage();
+    void computeBottomTracks();
+    void computeSideTracks();
+    void exportResults();
+
+    unsigned int N_frames() const { return N_FRAMES; }
+
+    // read access for the host stages that follow (cost builders, match2nd) and for tests
+    const std::vector<std::vector<Candidate>> &candidatesBottomPaw() const { return CANDIDATES_BOTTOM_PAW; }
+    const std::vector<std::vector<Candidate>> &candidatesBottomSnout() const { return CANDIDATES_BOTTOM_SNOUT; }
+    const std::vector<std::vector<Candidate>> &candidatesSidePaw() const { return CANDIDATES_SIDE_PAW; }
+    const std::vector<std::vector<Candidate>> &candidatesSideSnout() const { return CANDIDATES_SIDE_SNOUT; }
+    const std::vector<std::vector<P22D>> &candidatesMatchedViewsPaw() const { return CANDIDATES_MATCHED_VIEWS_PAW; }
+    const std::vector<std::vector<P22D>> &candidatesMatchedViewsSnout() const { return CANDIDATES_MATCHED_VIEWS_SNOUT; }
+    const std::vector<std::vector<int32_t>> &tracksTail() const { return TRACKS_TAIL; }
+};
+
+// LocoMouse_TM (LocoMouse_TM.hpp:45-47): imadjust in readFrame; box = bb_width x bb_height_side (side,
+// anchored at row 164) and bb_width x bottom-view height (LocoMouse_TM.cpp:142-155).
+class LocoMouse_TM : public LocoMouse {
+protected:
+    bool usesImadjust() const override { return true; }
+
+public:
+    explicit LocoMouse_TM(LocoMouse_ParseInputs INPUTS);
+    void computeBoundingBox() override;
+};
+
+// LocoMouse_TM_DE (LocoMouse_TM_DE.hpp:39-43): same readFrame; 400-wide boxes over the full view heights
+// (LocoMouse_TM_DE.cpp:38-51).
+class LocoMouse_TM_DE : public LocoMouse_TM {
+public:
+    explicit LocoMouse_TM_DE(LocoMouse_ParseInputs INPUTS);
+    void computeBoundingBox() override;
+};
+
+// LocoMouse_Methods.cpp:3-26
+std::unique_ptr<LocoMouse> LocoMouse_Initialize(LocoMouse_ParseInputs INPUT);

@@ -1,0 +1,158 @@
+"""Host-side C++ mirror of the reference classes (locomouse_cpp_b200/host).
+
+CPU part: the value types (Candidate / P22D) behave like Candidates/Candidates.cpp, the driver keeps
+main.cpp's error convention.  GPU part: the reference's main.cpp call sequence, run through the C++
+classes on files, yields exactly the oracle's candidates / P22D records / tail tracks.
+"""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "locomouse_cpp_b200", "host")
+
+
+@pytest.fixture(scope="module")
+def host_build():
+    p = subprocess.run(["make", "-C", HOST, "test_candidates"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    return HOST
+
+
+def _build_driver():
+    if not os.path.exists(os.path.join(ROOT, "locomouse_cpp_b200", "liblocomouse_b200.so")):
+        pytest.skip("CUDA library not built")
+    p = subprocess.run(["make", "-C", HOST], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    return os.path.join(HOST, "locomouse_b200")
+
+
+def test_value_types(host_build):
+    p = subprocess.run([os.path.join(host_build, "test_candidates")], capture_output=True, text=True)
+    assert p.returncode == 0 and p.stdout.strip().endswith("ok"), p.stdout + p.stderr
+
+
+def test_driver_error_convention(tmp_path):
+    """main.cpp:94-101: invalid inputs are reported and turned into EXIT_FAILURE, not a crash."""
+    exe = _build_driver()
+    p = subprocess.run([exe, "1", "only", "three"], capture_output=True, text=True)
+    assert p.returncode == 1 and "Invalid inputs" in p.stdout and "Total Elapsed time" in p.stdout
+    cfg = tmp_path / "config.yml"
+    cfg.write_text("conn_comp_connectivity: 5\n")
+    p = subprocess.run([exe, "1", str(cfg), "v", "b", "m", "c", "R", str(tmp_path)], capture_output=True, text=True)
+    assert p.returncode == 1 and "conn_comp_connectivity must be either 4 or 8" in p.stdout
+    cfg.write_text("conn_comp_connectivity: 8\n")
+    p = subprocess.run([exe, "1", str(cfg), str(tmp_path / "missing.lmv"), "b", "m", "c", "R", str(tmp_path)],
+                       capture_output=True, text=True)
+    assert p.returncode == 1 and "Runtime Error" in p.stdout and "Cannot open file" in p.stdout
+
+
+# ---------------------------------------------------------------------------------------------------
+def write_problem_files(d, cfg, model, bkg, calib, frames, bx, bs, bb, side_h, extra_cfg=""):
+    """The raw containers of locomouse_cpp_b200/host/lm_files.hpp."""
+    n, rows, cols = frames.shape
+    with open(d / "video.lmv", "wb") as f:
+        f.write(b"LMV1" + struct.pack("<iii", n, rows, cols))
+        f.write(np.ascontiguousarray(frames, np.uint8).tobytes())
+    with open(d / "bkg.lmi", "wb") as f:
+        f.write(b"LMI1" + struct.pack("<ii", *bkg.shape))
+        f.write(np.ascontiguousarray(bkg, np.uint8).tobytes())
+    with open(d / "model.lmm", "wb") as f:
+        f.write(b"LMM1")
+        for v in range(2):
+            for k in range(3):
+                w = np.ascontiguousarray(model.w[v][k], np.float32)
+                f.write(struct.pack("<iid", w.shape[0], w.shape[1], float(model.rho[v][k])))
+                f.write(w.tobytes())
+    with open(d / "calib.lmc", "wb") as f:
+        f.write(b"LMC1" + struct.pack("<ii", *calib.shape))
+        f.write(struct.pack("<8i", 0, 0, cfg.n_cols, side_h, 0, side_h, cfg.n_cols, cfg.n_rows - side_h))
+        f.write(np.ascontiguousarray(calib, np.int32).tobytes())
+    with open(d / "boxes.lmb", "wb") as f:
+        f.write(b"LMB1" + struct.pack("<i", n))
+        for a in (bx, bs, bb):
+            f.write(np.ascontiguousarray(a, np.uint32).tobytes())
+    (d / "config.yml").write_text(
+        "%YAML:1.0\n"
+        f"conn_comp_connectivity: {cfg.conn}\n"
+        f"side_bottom_min_overlap: {cfg.min_overlap!r}\n"
+        f"tail_sub_bounding_box: {cfg.tail_sub_bounding_box!r}\n"
+        f"bb_width: {cfg.bb_w}\nbb_height_side: {cfg.bb_h_side}\n"
+        f"bounding_box_file: {d / 'boxes.lmb'}\n"
+        f"fma_mode: {int(cfg.fma_mode)}\ncand_cap: {cfg.cand_cap}\ndet_cap: {cfg.det_cap}\nmatch_cap: {cfg.match_cap}\n"
+        + extra_cfg)
+
+
+def read_output(path):
+    """LMO1 (LocoMouse::exportResults) -> per frame dict."""
+    buf = open(path, "rb").read()
+    assert buf[:4] == b"LMO1"
+    off = 4
+    n, nt = struct.unpack_from("<ii", buf, off)
+    off += 8
+    frames = []
+    for _ in range(n):
+        tail = np.frombuffer(buf, "<i4", 3 * nt, off).reshape(3, nt)
+        off += 12 * nt
+        feats = []
+        for _feat in range(2):
+            lists = []
+            for _l in range(2):
+                (k,) = struct.unpack_from("<i", buf, off)
+                off += 4
+                c = []
+                for _i in range(k):
+                    x, y, s = struct.unpack_from("<iid", buf, off)
+                    off += 16
+                    c.append((x, y, s))
+                lists.append(c)
+            matches = []
+            for _i in range(len(lists[0])):
+                (m,) = struct.unpack_from("<i", buf, off)
+                off += 4
+                mm = []
+                for _q in range(m):
+                    y, s = struct.unpack_from("<id", buf, off)
+                    off += 12
+                    mm.append((y, s))
+                matches.append(mm)
+            feats.append((lists[0], lists[1], matches))
+        frames.append((tail, feats))
+    assert off == len(buf)
+    return frames
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,flip", [("TM", False), ("TM_DE", True)])
+def test_main_sequence_matches_oracle(tmp_path, oracle, method, flip):
+    from locomouse_cpp_b200 import synth
+
+    exe = _build_driver()
+    spec = synth.SynthSpec(method=method, flip=flip)
+    n = 7
+    cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(spec, n, seed=1000)
+    frames = frames.numpy()
+    ref = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=4)
+    # batch_frames 3 -> chunks of 3, 3, 1 frames: exercises the previous-frame halo between chunks
+    write_problem_files(tmp_path, cfg, model, bkg, calib, frames, bx, bs, bb, spec.side_h, extra_cfg="batch_frames: 3\n")
+    meth = {"base": "0", "TM": "1", "TM_DE": "2"}[method]
+    p = subprocess.run([exe, meth, str(tmp_path / "config.yml"), str(tmp_path / "video.lmv"), str(tmp_path / "bkg.lmi"),
+                        str(tmp_path / "model.lmm"), str(tmp_path / "calib.lmc"), "L" if flip else "R", str(tmp_path)],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    out = read_output(tmp_path / "output_video.lmo")
+    assert len(out) == n
+    total = 0
+    for f, (tail, feats) in enumerate(out):
+        assert np.array_equal(tail, ref.tail[f])
+        for feat in range(2):
+            cb, cs, matches = feats[feat]
+            assert cb == ref.candidates_bottom(f, feat)
+            assert cs == ref.candidates_side(f, feat)
+            want = ref.p22d(f, feat)
+            assert [m for m in matches] == [w[1] for w in want]
+            total += len(cb)
+    assert total > 0

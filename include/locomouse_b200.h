@@ -145,6 +145,16 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device,
                     const uint32_t *bb_x, const uint32_t *bb_y_side, const uint32_t *bb_y_bottom,
                     lm_results *out);
 
+/* tuning knobs that never change results ------------------------------------------------------ *
+ *  "screen"   1 (default): the six correlations run as an int8 tensor-core screen (tcgen05) followed by
+ *             an exact FP32 re-evaluation of the undecided outputs; 0: dense exact FP32 kernel only.
+ *             Both produce bit-identical results (the screen only discards outputs proven <= 0).
+ *  "subbatch" frames per internal sub-batch (default 256).
+ * lm_get_info: "screen_active" (1/0 after the first lm_detect_batch, -1 before), "subbatch",
+ *             "screen_eps_<view><feat>" / "screen_scale_<view><feat>" (error bound / weight quantum). */
+int lm_set_option(lm_ctx *ctx, const char *name, int64_t value);
+int lm_get_info(const lm_ctx *ctx, const char *name, double *value);
+
 /* measurement / debugging ---------------------------------------------------------------- */
 /* Device time (ms, CUDA events on the library's own stream) of the stages of the last
  * lm_detect_batch call, summed over its sub-batches:

@@ -25,7 +25,7 @@ _lib = None
 
 EXPORTS = ("lm_abi_version", "lm_create", "lm_destroy", "lm_last_error", "lm_configure", "lm_set_model",
            "lm_set_background", "lm_set_calibration", "lm_get_geometry", "lm_detect_batch", "lm_last_timing",
-           "lm_debug_fetch")
+           "lm_debug_fetch", "lm_set_option", "lm_get_info")
 
 
 class OverflowError_(RuntimeError):
@@ -63,6 +63,10 @@ def load_library():
     L.lm_detect_batch.argtypes = [vp, vp, i32, vp, i64, i64, vp, vp, vp, C.POINTER(lm_results)]
     L.lm_last_timing.restype = C.c_int
     L.lm_last_timing.argtypes = [vp, vp, vp]
+    L.lm_set_option.restype = C.c_int
+    L.lm_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.lm_get_info.restype = C.c_int
+    L.lm_get_info.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double)]
     L.lm_debug_fetch.restype = i64
     L.lm_debug_fetch.argtypes = [vp, i32, i64, vp, i64, vp]
     _lib = L
@@ -153,6 +157,17 @@ class Detector:
         self._check(rc, allow_overflow)
         res.rc = rc
         return res
+
+    def set_option(self, name: str, value: int):
+        """'screen' (0/1) or 'subbatch'; never changes results."""
+        self._check(self._L.lm_set_option(self._ctx, name.encode(), int(value)))
+
+    def info(self, name: str) -> float:
+        v = C.c_double(0.0)
+        rc = self._L.lm_get_info(self._ctx, name.encode(), C.byref(v))
+        if rc != 0:
+            raise ValueError(f"unknown info item {name!r}")
+        return float(v.value)
 
     def last_timing(self):
         ms = np.zeros(7, np.float32)

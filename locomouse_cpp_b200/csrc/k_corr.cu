@@ -16,6 +16,7 @@
 // once, next to the zero-padded template; the inner loop then issues only LDS.128 + FFMA:
 // TY*KW*TX FFMA per (TX+KW-1)/4 pixel LDS.128 and TY*KW/4 weight LDS.128 (broadcast).
 #include "lm_internal.h"
+#include "corr_common.cuh"
 
 namespace {
 
@@ -55,47 +56,6 @@ struct CorrParams {
     int32_t *det_count;
 };
 
-
-// NT consecutive taps of one kernel row applied to one output row of the thread's patch (TX
-// accumulators), taps in increasing column order.  p[] holds the NP pixels those taps read, w points at
-// the first of the NT weights (16-byte aligned in shared memory).
-template <int NT, int TX, bool FMA, int NP>
-__device__ __forceinline__ void corr_taps(float (&acc)[TX], const float (&p)[NP], const float *__restrict__ w) {
-    constexpr int NT4 = ((NT + 3) / 4) * 4;
-    const float4 *wr = reinterpret_cast<const float4 *>(w);
-    float wv[NT4];
-#pragma unroll
-    for (int q = 0; q < NT4 / 4; ++q) {
-        float4 v = wr[q];
-        wv[4 * q + 0] = v.x;
-        wv[4 * q + 1] = v.y;
-        wv[4 * q + 2] = v.z;
-        wv[4 * q + 3] = v.w;
-    }
-#pragma unroll
-    for (int i = 0; i < NT; ++i) {
-#pragma unroll
-        for (int k = 0; k < TX; ++k) {
-            if (FMA)
-                acc[k] = __fmaf_rn(wv[i], p[i + k], acc[k]);
-            else
-                acc[k] = __fadd_rn(acc[k], __fmul_rn(wv[i], p[i + k]));
-        }
-    }
-}
-
-template <int NP>
-__device__ __forceinline__ void load_pixels(float (&p)[NP], const float *__restrict__ row) {
-    const float4 *src = reinterpret_cast<const float4 *>(row);
-#pragma unroll
-    for (int q = 0; q < NP / 4; ++q) {
-        float4 v = src[q];
-        p[4 * q + 0] = v.x;
-        p[4 * q + 1] = v.y;
-        p[4 * q + 2] = v.z;
-        p[4 * q + 3] = v.w;
-    }
-}
 
 template <int KW, int TX, int TY, bool FMA>
 __global__ void __launch_bounds__(CORR_THREADS, (KW <= 32) ? 2 : 1) k_corr(const __grid_constant__ CorrParams P) {

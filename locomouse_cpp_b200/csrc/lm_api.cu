@@ -27,6 +27,10 @@ struct lm_ctx {
     uint8_t *d_bkg = nullptr;
     int32_t *d_calib = nullptr;
     float *d_tmpl[2][3] = {};
+    std::vector<float> h_tmpl[2][3];  // host copies (the screen's quantisation is derived from them)
+    int opt_screen = 1;               // tensor-core screen + sparse exact pass (0: dense exact kernel only)
+    int opt_subbatch = 256;
+    LmScreenHost scr_info[2][3] = {};
     int t_rows[2][3] = {}, t_cols[2][3] = {};
     double t_rho[2][3] = {};
 
@@ -206,14 +210,14 @@ int prepare(lm_ctx *ctx) {
                             k.bb_w, ctx->t_rows[v][f], ctx->t_cols[v][f], need);
         }
 
-    int Bcap = 256;
+    int Bcap = ctx->opt_subbatch;
     if (const char *e = getenv("LM_SUBBATCH")) Bcap = std::max(1, atoi(e));
     const size_t B = (size_t)Bcap;
     int rc;
     if ((rc = dalloc(ctx, &b.minmax, (B + 1) * 2))) return rc;
     if ((rc = dalloc(ctx, &b.lut, (B + 1) * 256))) return rc;
     for (int v = 0; v < 2; ++v) {
-        if ((rc = dalloc(ctx, &b.win[v], B * b.view[v].win_stride))) return rc;
+        if ((rc = dalloc(ctx, &b.win[v], B * b.view[v].win_stride + 512))) return rc;  // slack: k_corr_sparse reads whole words past a row end
         if ((rc = dalloc(ctx, &b.tailbin[v], B * b.bb_h[v] * b.tail_pitch))) return rc;
     }
     if ((rc = dalloc(ctx, &b.tailmask, B * b.bb_h[LM_BOTTOM] * b.tail_pitch))) return rc;
@@ -249,6 +253,45 @@ int prepare(lm_ctx *ctx) {
     b.match_s = (double *)(ctx->d_res + o.match_s);
     b.tail = (int32_t *)(ctx->d_res + o.tail);
     b.flags = (uint32_t *)(ctx->d_res + o.flags);
+    // ---- tensor-core screen (k_screen.cu): all six jobs must qualify, otherwise the dense kernel runs --------
+    b.scr = LmScreen{};
+    int want_screen = ctx->opt_screen;
+    if (const char *e = getenv("LM_SCREEN")) want_screen = atoi(e);
+    if (want_screen && k.bb_w <= 1024 && std::max(k.bb_h_bottom, k.bb_h_side) <= 512 && Bcap <= (1 << 17)) {
+        bool ok = true;
+        std::vector<int8_t> img[2][3];
+        for (int v = 0; v < 2 && ok; ++v)
+            for (int f = 0; f < 3 && ok; ++f) {
+                if (f == LM_TAIL && k.tail_w <= 0) continue;
+                const LmTemplateDev &T = b.tmpl[v][f];
+                ok = lm_screen_build(ctx->h_tmpl[v][f].data(), T.kh, T.kw, T.init, b.view[v].halo_x, b.view[v].halo_y, k.fma_mode,
+                                     &ctx->scr_info[v][f], &img[v][f]);
+            }
+        if (ok) {
+            if ((rc = dalloc(ctx, &b.scr.ntasks, 8))) return rc;
+            for (int v = 0; v < 2; ++v)
+                for (int f = 0; f < 3; ++f) {
+                    if (f == LM_TAIL && k.tail_w <= 0) continue;
+                    const LmScreenHost &H = ctx->scr_info[v][f];
+                    LmScreenJob &J = b.scr.job[v][f];
+                    int8_t *dimg = nullptr;
+                    if ((rc = dalloc(ctx, &dimg, img[v][f].size()))) return rc;
+                    CK(cudaMemcpy(dimg, img[v][f].data(), img[v][f].size(), cudaMemcpyHostToDevice));
+                    J.Bimg = dimg;
+                    J.kh = H.kh;
+                    J.ks = H.ks;
+                    J.dx = H.dx;
+                    J.dy = H.dy;
+                    J.rows = H.rows;
+                    J.t_lo = H.t_lo;
+                    J.t_hi = H.t_hi;
+                    const int ow = (f == LM_TAIL) ? k.tail_w : k.bb_w;
+                    J.task_cap = (int)std::min<size_t>((size_t)1 << 30, B * (size_t)((b.bb_h[v] + 3) / 4) * (size_t)((ow + 7) / 8));
+                    if ((rc = dalloc(ctx, &J.tasks, (size_t)J.task_cap))) return rc;
+                }
+            b.scr.enabled = 1;
+        }
+    }
     ctx->Bcap = Bcap;
     return LM_OK;
 }
@@ -368,6 +411,7 @@ int lm_set_model(lm_ctx *ctx, const lm_template t[2][3]) {
             ctx->d_tmpl[v][f] = nullptr;
             CK(cudaMalloc((void **)&ctx->d_tmpl[v][f], (size_t)T.rows * T.cols * sizeof(float)));
             CK(cudaMemcpy(ctx->d_tmpl[v][f], T.w, (size_t)T.rows * T.cols * sizeof(float), cudaMemcpyHostToDevice));
+            ctx->h_tmpl[v][f].assign(T.w, T.w + (size_t)T.rows * T.cols);
             ctx->t_rows[v][f] = T.rows;
             ctx->t_cols[v][f] = T.cols;
             ctx->t_rho[v][f] = T.rho;
@@ -535,7 +579,8 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, co
         if ((nl = lm_launch_prep(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "prep launch failed");
         ctx->launches += nl;
         CK(cudaEventRecord(ev[2], st));
-        if ((nl = lm_launch_corr(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "correlation launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        nl = b.scr.enabled ? lm_launch_screen(b, st) : lm_launch_corr(b, st);
+        if (nl < 0) return fail(ctx, LM_ERR_RUNTIME, "correlation launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         ctx->launches += nl;
         CK(cudaEventRecord(ev[3], st));
         if ((nl = lm_launch_tail(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "tail launch failed");
@@ -569,6 +614,45 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, co
     }
     if (overflow) return fail(ctx, LM_ERR_OVERFLOW, "a fixed-capacity list overflowed (see lm_results.flags); raise det_cap / cand_cap / match_cap");
     return LM_OK;
+}
+
+int lm_set_option(lm_ctx *ctx, const char *name, int64_t value) {
+    if (!ctx) return LM_ERR_INVALID;
+    if (!name) return fail(ctx, LM_ERR_INVALID, "lm_set_option: null name");
+    cudaSetDevice(ctx->device);
+    if (!strcmp(name, "screen")) {
+        if (value != 0 && value != 1) return fail(ctx, LM_ERR_INVALID, "option screen must be 0 or 1");
+        ctx->opt_screen = (int)value;
+    } else if (!strcmp(name, "subbatch")) {
+        if (value < 1 || value > 4096) return fail(ctx, LM_ERR_INVALID, "option subbatch must be in [1, 4096]");
+        ctx->opt_subbatch = (int)value;
+    } else {
+        return fail(ctx, LM_ERR_INVALID, "unknown option '%s'", name);
+    }
+    cudaDeviceSynchronize();
+    free_scratch(ctx);  // re-derived by the next lm_detect_batch
+    return LM_OK;
+}
+
+int lm_get_info(const lm_ctx *ctx, const char *name, double *value) {
+    if (!ctx || !name || !value) return LM_ERR_INVALID;
+    if (!strcmp(name, "screen_active")) {
+        *value = ctx->Bcap ? (double)ctx->bt.scr.enabled : -1.0;  // -1: not prepared yet
+        return LM_OK;
+    }
+    if (!strncmp(name, "screen_eps_", 11) || !strncmp(name, "screen_scale_", 13)) {
+        const bool eps = name[7] == 'e';
+        const char *q = name + (eps ? 11 : 13);
+        const int v = q[0] - '0', f = q[1] - '0';
+        if (v < 0 || v > 1 || f < 0 || f > 2 || q[2]) return LM_ERR_INVALID;
+        *value = eps ? ctx->scr_info[v][f].eps : ctx->scr_info[v][f].scale;
+        return LM_OK;
+    }
+    if (!strcmp(name, "subbatch")) {
+        *value = (double)ctx->Bcap;
+        return LM_OK;
+    }
+    return LM_ERR_INVALID;
 }
 
 int lm_last_timing(const lm_ctx *ctx, float ms[7], int64_t *launches) {

@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/locomouse_b200.h"
 
 #define LM_MAX_KW 64  // widest template row the correlation kernel is instantiated for
@@ -41,6 +43,23 @@ struct LmGeom {
     int spre_b_w, spre_b_h, spost_b_w, spost_b_h;
     int spre_s_w, spre_s_h, spost_s_w, spost_s_h;
     int pad_pre_cols, pad_pre_rows, pad_post_cols, pad_post_rows;
+};
+
+// Tensor-core screen (k_screen.cu): per (view, template) job, the int8 banded-Toeplitz B operand, the
+// integer decision thresholds and the list of 4x8 output patches the exact kernel must re-evaluate.
+struct LmScreenJob {
+    const int8_t *Bimg;   // device, [kh][2*ks chunks][64 rows][16 B]   (N = 64: 32 columns x {hi, lo} digit)
+    int kh, ks;           // kernel rows, K steps of 32 window bytes
+    int dx, dy;           // window column / row of tap (0,0) for output (0,0): halo - anchor
+    int rows;             // window rows staged per 128-row tile: 128 + kh - 1 + dy, rounded up to 8
+    long long t_lo, t_hi; // V <= t_lo: score provably <= 0;  V > t_hi: score provably > 0
+    uint32_t *tasks;      // device, [task_cap]: frame << 14 | patch_row << 7 | patch_col
+    int task_cap;
+};
+struct LmScreen {
+    int enabled;
+    LmScreenJob job[2][3];
+    int *ntasks;          // device, [6] = [view][feat]
 };
 
 // everything a kernel needs to know about the current sub-batch
@@ -72,6 +91,7 @@ struct LmBatch {
     int32_t *cc;                // [B][3][cc_stride]
     int64_t cc_stride;
     int32_t *cc_flag;           // [B] 1 = frame exceeded the run capacity of k_tail and takes k_tail_slow
+    LmScreen scr;
     LmDet *det;                 // [B][2][2][det_cap]   index: ((f*2+feat)*2+view)
     int32_t *det_count;         // [B][2][2]
     // results (device mirrors of lm_results)
@@ -90,6 +110,20 @@ int lm_launch_corr(const LmBatch &b, cudaStream_t s);
 int lm_launch_tail(const LmBatch &b, cudaStream_t s);
 int lm_launch_nms(const LmBatch &b, cudaStream_t s);
 int lm_launch_pair(const LmBatch &b, cudaStream_t s);
+
+// tensor-core screen + sparse exact re-evaluation (k_screen.cu); returns kernels launched or -1
+int lm_launch_screen(const LmBatch &b, cudaStream_t s);
+// Host-side preparation of one screen job from the fp32 template: quantisation to two int8 digits, the
+// Toeplitz operand image and the thresholds.  Returns false when the job cannot be screened (operand does
+// not fit in shared memory, non-finite weights); `img` receives kh * ks * 2048 bytes.
+struct LmScreenHost {
+    int kh, ks, dx, dy, rows;
+    long long t_lo, t_hi;
+    double scale, eps;
+};
+bool lm_screen_build(const float *w, int kh, int kw, float init, int halo_x, int halo_y, int fma_mode,
+                     LmScreenHost *out, std::vector<int8_t> *img);
+size_t lm_screen_smem_bytes(int kh, int ks, int rows, int stages);
 
 // pick the padded kernel-row width the correlation kernel is instantiated for (>= kw), or -1
 int lm_corr_kwp(int kw);

@@ -13,13 +13,16 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=512)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--scale", type=int, default=1)
+ap.add_argument("--screen", type=int, default=1)
 args = ap.parse_args()
 spec = synth.SynthSpec(scale=args.scale) if args.scale == 1 else synth.SynthSpec(scale=args.scale, cand_cap=128, match_cap=512)
 cfg, model, bkg, calib, _, _, _, _ = synth.make_problem(spec, 8, seed=1000)
 frames, bx, bs, bb = synth.make_video(spec, args.frames, 1000, "cuda", bkg)
 torch.cuda.synchronize()
 det = Detector(cfg, model, bkg, calib)
+det.set_option("screen", args.screen)
 for _ in range(args.iters):
     r = det.detect_batch(frames, bx, bs, bb, allow_overflow=True)
     print(det.last_timing())
+print("screen_active", det.info("screen_active"))
 print("flags", int((r.flags != 0).sum()), "n_bottom", r.n_bottom.mean(0), "n_side", r.n_side.mean(0))

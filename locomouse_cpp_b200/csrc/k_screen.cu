@@ -676,6 +676,7 @@ int lm_launch_screen(const LmBatch &b, cudaStream_t s) {
     int total_cta = P.job[P.njobs - 1].cta_begin + P.job[P.njobs - 1].ncta;
     k_screen<<<total_cta, SCR_THREADS, smem, s>>>(P);
     if (cudaGetLastError() != cudaSuccess) return -1;
+    if (b.ev_screen_done) cudaEventRecord(b.ev_screen_done, s);
     int launches = 1;
     // sparse exact pass: one launch per distinct padded kernel width (the jobs of other widths exit at once)
     bool done[6] = {};

@@ -49,6 +49,8 @@ struct lm_ctx {
     cudaEvent_t ev_h2d[2] = {}, ev_done[2] = {};
     cudaEvent_t ev_stage[2][8] = {};
     cudaEvent_t ev_call[2] = {};      // first kernel / last D2H of a whole lm_detect_batch call
+    cudaEvent_t ev_mid[2] = {};       // between k_screen and k_corr_sparse
+    float ms_screen = 0.f;            // k_screen alone, summed over the sub-batches of the last call
     float ms[7] = {};
     int64_t launches = 0;
     int last_B = 0;                   // size of the last sub-batch (for lm_debug_fetch)
@@ -342,6 +344,7 @@ int lm_create(lm_ctx **out, int device) {
         cudaEventCreateWithFlags(&ctx->ev_done[s], cudaEventDisableTiming);
         for (int q = 0; q < 8; ++q) cudaEventCreate(&ctx->ev_stage[s][q]);
         cudaEventCreate(&ctx->ev_call[s]);
+        cudaEventCreate(&ctx->ev_mid[s]);
     }
     *out = ctx;
     return LM_OK;
@@ -361,6 +364,7 @@ int lm_destroy(lm_ctx *ctx) {
         cudaEventDestroy(ctx->ev_done[s]);
         for (int q = 0; q < 8; ++q) cudaEventDestroy(ctx->ev_stage[s][q]);
         cudaEventDestroy(ctx->ev_call[s]);
+        cudaEventDestroy(ctx->ev_mid[s]);
     }
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
@@ -498,6 +502,7 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, co
     const int64_t nsub = (n + Bcap - 1) / Bcap;
     const bool has_prev0 = first_frame_index > 0;
     for (int q = 0; q < 7; ++q) ctx->ms[q] = 0.f;
+    ctx->ms_screen = 0.f;
     ctx->launches = 0;
     const lm_ctx::ResOff &o = ctx->ro;
     cudaStream_t st = ctx->stream;
@@ -544,6 +549,7 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, co
         float t;
         for (int q = 0; q < 6; ++q)
             if (cudaEventElapsedTime(&t, ctx->ev_stage[slot][q], ctx->ev_stage[slot][q + 1]) == cudaSuccess) ctx->ms[q] += t;
+        if (ctx->bt.scr.enabled && cudaEventElapsedTime(&t, ctx->ev_stage[slot][2], ctx->ev_mid[slot]) == cudaSuccess) ctx->ms_screen += t;
         return LM_OK;
     };
 
@@ -566,6 +572,7 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, co
         b.bb_x = ctx->d_bb[slot];
         b.bb_y_side = ctx->d_bb[slot] + Bcap;
         b.bb_y_bottom = ctx->d_bb[slot] + 2 * Bcap;
+        b.ev_screen_done = ctx->ev_mid[slot];
         cudaEvent_t *ev = ctx->ev_stage[slot];
         CK(cudaStreamWaitEvent(st, ctx->ev_h2d[slot], 0));
         CK(cudaEventRecord(ev[0], st));
@@ -646,6 +653,10 @@ int lm_get_info(const lm_ctx *ctx, const char *name, double *value) {
         const int v = q[0] - '0', f = q[1] - '0';
         if (v < 0 || v > 1 || f < 0 || f > 2 || q[2]) return LM_ERR_INVALID;
         *value = eps ? ctx->scr_info[v][f].eps : ctx->scr_info[v][f].scale;
+        return LM_OK;
+    }
+    if (!strcmp(name, "ms_screen")) {  // device time of k_screen alone in the last lm_detect_batch call
+        *value = (double)ctx->ms_screen;
         return LM_OK;
     }
     if (!strcmp(name, "subbatch")) {

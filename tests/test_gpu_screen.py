@@ -1,0 +1,110 @@
+"""The tensor-core screen (csrc/k_screen.cu) must never change a result: with the screen on (int8 tcgen05
+implicit GEMM + sparse exact re-evaluation) and off (dense exact FP32 kernel) every output byte is identical,
+and both equal the oracle.  Needs a B200:  pytest -m gpu.
+"""
+import numpy as np
+import pytest
+
+from locomouse_cpp_b200 import synth
+from locomouse_cpp_b200.types import Model, diff_results
+
+pytestmark = pytest.mark.gpu
+
+
+def _detector(cfg, model, bkg, calib, screen):
+    from locomouse_cpp_b200.api import Detector
+
+    d = Detector(cfg, model, bkg, calib, device=0)
+    d.set_option("screen", screen)
+    return d
+
+
+def _run_both(spec, n, seed, model_edit=None, **kw):
+    cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(spec, n, seed=seed)
+    if model_edit is not None:
+        model = model_edit(model)
+    frames = frames.numpy()
+    out = []
+    for screen in (1, 0):
+        det = _detector(cfg, model, bkg, calib, screen)
+        r = det.detect_batch(frames, bx, bs, bb, **kw)
+        out.append((r, det.info("screen_active")))
+        det.close()
+    return out, (cfg, model, bkg, calib, frames, bx, bs, bb)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(method="TM_DE", flip=True), dict(method="base", fma_mode=False),
+                                dict(warp=True, vid_pad=5, conn=4)])
+def test_screen_equals_dense_and_oracle(oracle, kw):
+    (on, on_active), (off, off_active) = _run_both(synth.SynthSpec(**kw), 6, 1000)[0]
+    assert on_active == 1.0 and off_active == 0.0
+    assert diff_results(on, off) == [] and on.checksum() == off.checksum()
+
+
+def test_screen_vs_oracle_mixed_template_shapes(oracle):
+    """Per-feature different template sizes: different anchors shift the Toeplitz band (dx, dy != 0), and the
+    sparse exact kernel runs one launch per padded kernel width."""
+    shapes = (((30, 30), (24, 28), (20, 16)), ((27, 30), (30, 22), (15, 17)))
+    spec = synth.SynthSpec(tshapes=shapes)
+    ((on, a1), (off, a0)), (cfg, model, bkg, calib, frames, bx, bs, bb) = _run_both(spec, 4, 1001)
+    assert a1 == 1.0
+    ref = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=8)
+    assert diff_results(on, ref) == [] and diff_results(off, ref) == []
+
+
+def test_screen_large_batch_property():
+    """Size-independent property at benchmark scale: 700 device-rendered frames (three sub-batches), screen on
+    and off give the same checksum of every result byte."""
+    import torch
+
+    spec = synth.SynthSpec()
+    cfg, model, bkg, calib, _, _, _, _ = synth.make_problem(spec, 8, seed=1000)
+    frames, bx, bs, bb = synth.make_video(spec, 700, 1234, "cuda", bkg)
+    torch.cuda.synchronize()
+    sums = []
+    for screen in (1, 0):
+        det = _detector(cfg, model, bkg, calib, screen)
+        r = det.detect_batch(frames, bx, bs, bb)
+        sums.append((r.checksum(), int(r.n_bottom.sum()), int(r.n_side.sum()), int(r.match_n.sum())))
+        det.close()
+    assert sums[0] == sums[1]
+    assert sums[0][1] > 1000
+
+
+def test_screen_dense_threshold_and_degenerate_templates(oracle):
+    """Stress the decision thresholds: (a) biases lowered so that a large share of all outputs is positive (many
+    survivors, overflow allowed), (b) an all-zero template with rho = 0 (every score is exactly -0.0 -> no
+    detection, quantisation scale degenerate), (c) rho exactly at a representable score level."""
+    def lower_rho(m):
+        return Model(w=m.w, rho=[[r * 0.25 for r in row] for row in m.rho])
+
+    ((on, a1), (off, _)), _ = _run_both(synth.SynthSpec(), 3, 1002, model_edit=lower_rho, allow_overflow=True)
+    assert a1 == 1.0
+    # overflowing lists keep an unspecified subset of detections; compare only frames without overflow
+    ok = (on.flags == 0) & (off.flags == 0)
+    assert np.array_equal(on.flags != 0, off.flags != 0)
+    for name in on.ARRAYS:
+        assert np.array_equal(getattr(on, name)[ok], getattr(off, name)[ok]), name
+
+    def zero_paw(m):
+        w = [[a.copy() for a in row] for row in m.w]
+        w[0][0][:] = 0.0
+        rho = [list(row) for row in m.rho]
+        rho[0][0] = 0.0
+        return Model(w=w, rho=rho)
+
+    ((on, a1), (off, _)), (cfg, model, bkg, calib, frames, bx, bs, bb) = _run_both(synth.SynthSpec(), 3, 1002, model_edit=zero_paw)
+    assert a1 == 1.0 and diff_results(on, off) == []
+    assert int(on.n_bottom[:, 0].sum()) == 0
+    ref = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=8)
+    assert diff_results(on, ref) == []
+
+
+def test_screen_falls_back_to_dense_for_large_templates(oracle):
+    """Templates whose Toeplitz operand does not fit in shared memory (here 40x40) run the dense exact kernel;
+    the option stays a no-op for results."""
+    shapes = (((40, 40), (40, 40), (40, 40)), ((40, 40), (40, 40), (40, 40)))
+    ((on, a1), (off, a0)), (cfg, model, bkg, calib, frames, bx, bs, bb) = _run_both(synth.SynthSpec(tshapes=shapes), 2, 1000)
+    assert a1 == 0.0 and a0 == 0.0
+    ref = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=8)
+    assert diff_results(on, ref) == []

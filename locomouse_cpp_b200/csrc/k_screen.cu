@@ -74,6 +74,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
     __trap();
 }
+// one elected lane of a converged warp (the compiler keeps values used under it in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{.reg .pred P; elect.sync _|P, 0xffffffff; selp.b32 %0, 1, 0, P;}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(const __grid_constant
             mbar_wait(d_empty(acc), accphase ^ 1u);
             mbar_wait(a_full(stage), phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t d = tmem + (uint32_t)acc * SCR_N;
                 uint64_t adesc = umma_desc(smem_u32(sA) + (uint32_t)stage * stage_bytes + (uint32_t)J.j.dy * 16u, panel_a);
                 uint64_t bdesc = bdesc0;

@@ -106,37 +106,50 @@ __device__ __forceinline__ bool overlaps(int dx, int dy, int w, int h, int wh2) 
     return dx < w && dy < h && 3 * (w - dx) * (h - dy) > wh2;
 }
 
-// One thread per cluster slot accumulates its members in rank order (double) and writes the candidate.
+// One WARP per cluster slot: the lanes scan the rank-ordered detections 32 at a time (ballot of the slot's members),
+// lane 0 accumulates the members of each ballot in rank order in double, as the reference's loops do (1731-1739,
+// 1865-1869; double addition is not associative, so the order is part of the result).  On entry link[i] holds the
+// root of detection i; it is first replaced by the root's candidate slot.
 template <bool HALF_EVEN>
 __device__ void write_candidates(const NmsSmem &m, int n, const int *slot_of_root, int ncand, int cap,
                                  lm_cand *out, const int *root_rank) {
-    const int tid = threadIdx.x;
-    for (int k = tid; k < cap; k += NMS_THREADS) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARPS = NMS_THREADS / 32;
+    for (int i = tid; i < n; i += NMS_THREADS) m.link[i] = slot_of_root[m.link[i]];
+    __syncthreads();
+    for (int k = warp; k < cap; k += NWARPS) {
         lm_cand c;
         c.x = -1;
         c.y = -1;
         c.s = -1.0;
         if (k < ncand) {
             double wx = 0.0, wy = 0.0, ss = 0.0;
-            for (int i = 0; i < n; ++i) {
-                if (slot_of_root[m.link[i]] == k) {
-                    const double s = (double)m.s[i];
-                    wx = __dadd_rn(wx, __dmul_rn((double)m.x[i], s));
-                    wy = __dadd_rn(wy, __dmul_rn((double)m.y[i], s));
-                    ss = __dadd_rn(ss, s);
+            for (int base = 0; base < n; base += 32) {
+                const int i = base + lane;
+                unsigned mask = __ballot_sync(0xffffffffu, i < n && m.link[i] == k);
+                if (lane == 0)
+                    while (mask) {
+                        const int q = base + __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const double s = (double)m.s[q];
+                        wx = __dadd_rn(wx, __dmul_rn((double)m.x[q], s));
+                        wy = __dadd_rn(wy, __dmul_rn((double)m.y[q], s));
+                        ss = __dadd_rn(ss, s);
+                    }
+            }
+            if (lane == 0) {
+                const double qx = __ddiv_rn(wx, ss), qy = __ddiv_rn(wy, ss);
+                if (HALF_EVEN) {
+                    c.x = __double2int_rn(qx);
+                    c.y = __double2int_rn(qy);
+                } else {
+                    c.x = (int)round(qx);
+                    c.y = (int)round(qy);
                 }
+                c.s = (double)m.s[root_rank[k]];
             }
-            const double qx = __ddiv_rn(wx, ss), qy = __ddiv_rn(wy, ss);
-            if (HALF_EVEN) {
-                c.x = __double2int_rn(qx);
-                c.y = __double2int_rn(qy);
-            } else {
-                c.x = (int)round(qx);
-                c.y = (int)round(qy);
-            }
-            c.s = (double)m.s[root_rank[k]];
         }
-        out[k] = c;
+        if (lane == 0) out[k] = c;
     }
 }
 

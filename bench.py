@@ -199,7 +199,8 @@ def main():
     stage = {k: 0.0 for k in Detector.STAGES}
     launches = 0
     ms_screen = 0.0
-    screen_on = det.info("screen_active") == 1.0
+    screen_mode = int(det.info("screen_active"))
+    screen_on = screen_mode >= 1
     t0 = time.perf_counter()
     for _ in range(args.steps):
         res = det.detect_batch(frames, bx, bs, bb)
@@ -254,11 +255,11 @@ def main():
         scr_ms_per_launch = ms_screen / (launches_per_step * args.steps)
         achieved = flop_per_launch / (scr_ms_per_launch * 1e-3) / 1e12
         tensor_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-        roofline = {"kernel": "k_screen", "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+        roofline = {"kernel": "k_screen2" if screen_mode == 2 else "k_screen", "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                     "frac": achieved / tensor_peak,
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                                     if "bf16_tflops_sustained" in peaks else "fallback 1590 TFLOP/s (of fallback)"),
-                    "traffic": traffic_of("k_screen"), "launch_ms": scr_ms_per_launch, "flop_per_launch": flop_per_launch,
+                    "traffic": traffic_of("k_screen2" if screen_mode == 2 else "k_screen"), "launch_ms": scr_ms_per_launch, "flop_per_launch": flop_per_launch,
                     "share_of_step": ms_screen / max(stage["total"], 1e-9),
                     "note": "algorithmic FLOPs = the exact correlation the screen decides (SURVEY 8d), not the int8 MMA work executed "
                             "(2 weight digits x 64/30 Toeplitz padding = 4.3x more MACs, run at the bf16-equivalent rate)",
@@ -288,7 +289,7 @@ def main():
             roofline["dense_exact_kernel"] = {"kernel": "k_corr", "bound": "fp32_fma", "achieved": dense_tflops, "peak": fp32_nominal,
                                               "frac": dense_tflops / fp32_nominal, "frames": m, "corr_ms": tm0["corr"],
                                               "frac_of_measured_ffma": (dense_tflops / ffma_measured["ffma_reg_tflops"]) if ffma_measured else None}
-            det.set_option("screen", 1)
+            det.set_option("screen", screen_mode)
             det.detect_batch(frames[:m], bx[:m], bs[:m], bb[:m])  # re-prepare scratch before the e2e leg
         except Exception as ex:  # pragma: no cover
             roofline["dense_exact_kernel"] = {"error": repr(ex)}

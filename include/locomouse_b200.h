@@ -146,11 +146,12 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device,
                     lm_results *out);
 
 /* tuning knobs that never change results ------------------------------------------------------ *
- *  "screen"   1 (default): the six correlations run as an int8 tensor-core screen (tcgen05) followed by
- *             an exact FP32 re-evaluation of the undecided outputs; 0: dense exact FP32 kernel only.
- *             Both produce bit-identical results (the screen only discards outputs proven <= 0).
+ *  "screen"   2 (default) / 1: the six correlations run as an int8 tensor-core screen (tcgen05; 2 = CTA pairs with
+ *             cta_group::2, 1 = one CTA per tile) followed by an exact FP32 re-evaluation of the undecided
+ *             outputs; 0: dense exact FP32 kernel only.  All three produce bit-identical results (the screen
+ *             only discards outputs proven <= 0).
  *  "subbatch" frames per internal sub-batch (default 256).
- * lm_get_info: "screen_active" (1/0 after the first lm_detect_batch, -1 before), "subbatch", "ms_screen"
+ * lm_get_info: "screen_active" (2/1/0 after the first lm_detect_batch, -1 before), "subbatch", "ms_screen"
  *             (device ms of the tensor-core kernel alone in the last call; ms[2] of lm_last_timing = screen + exact pass),
  *             "screen_eps_<view><feat>" / "screen_scale_<view><feat>" (error bound / weight quantum). */
 int lm_set_option(lm_ctx *ctx, const char *name, int64_t value);

@@ -27,6 +27,7 @@
 
 #include "lm_internal.h"
 #include "corr_common.cuh"
+#include "umma_common.cuh"
 
 namespace {
 
@@ -59,54 +60,6 @@ struct ScreenParams {
     int tail_pitch;
     int64_t tailbin_stride[2];
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// Bounded wait: a mis-programmed pipeline traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (int it = 0; it < (1 << 26); ++it) {
-        uint32_t ok;
-        asm volatile("{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p;}"
-                     : "=r"(ok)
-                     : "r"(bar), "r"(parity)
-                     : "memory");
-        if (ok) return;
-    }
-    __trap();
-}
-// one elected lane of a converged warp (the compiler keeps values used under it in uniform registers)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{.reg .pred P; elect.sync _|P, 0xffffffff; selp.b32 %0, 1, 0, P;}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// no-swizzle K-major shared-memory descriptor: rows linear at a 16-byte pitch (SBO = 128 B per 8 rows),
-// the two 16-byte K chunks of one instruction `lbo` bytes apart.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo) {
-    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) | ((uint64_t)(128u >> 4) << 32) |
-           ((uint64_t)1 << 46);
-}
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{.reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;}" ::"r"(tmem_d),
-                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
-        "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-}
 
 __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(const __grid_constant__ ScreenParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -529,16 +482,8 @@ size_t lm_screen_smem_bytes(int kh, int ks, int rows, int stages) {
     return (size_t)kh * 2 * ks * SCR_BJ + (size_t)stages * 2 * ks * rows * 16;
 }
 
-bool lm_screen_build(const float *w, int kh, int kw, float init, int halo_x, int halo_y, int fma_mode, LmScreenHost *out,
-                     std::vector<int8_t> *img) {
-    const int ax = kw / 2, ay = kh / 2;
-    const int dx = halo_x - ax, dy = halo_y - ay;
-    if (dx < 0 || dy < 0) return false;
-    const int kbytes = SCR_TILE_X - 1 + dx + kw;  // window bytes a tile row needs
-    const int ks = (kbytes + 31) / 32;
-    const int rows = (SCR_TILE_M + kh - 1 + dy + 7) & ~7;
-    if (lm_screen_smem_bytes(kh, ks, rows, SCR_STAGES) > 220 * 1024) return false;
-    const int ntaps = kh * kw;
+// 16-bit fixed-point weights (balanced int8 digits v = 256 * hi + lo) and the rigorous decision thresholds.
+static bool screen_quantize(const float *w, int ntaps, float init, std::vector<int> *vq, LmScreenHost *out) {
     double wmax = 0.0, wabs = 0.0;
     for (int i = 0; i < ntaps; ++i) {
         if (!std::isfinite(w[i])) return false;
@@ -546,14 +491,13 @@ bool lm_screen_build(const float *w, int kh, int kw, float init, int halo_x, int
         wabs += std::fabs((double)w[i]);
     }
     if (!std::isfinite(init)) return false;
-    // 16-bit fixed point, balanced int8 digits: v = 256 * hi + lo, hi, lo in [-128, 127]
     const double scale = wmax > 0.0 ? wmax / 32000.0 : 1.0;
-    std::vector<int> vq(ntaps);
+    vq->resize(ntaps);
     double eq = 0.0;
     for (int i = 0; i < ntaps; ++i) {
         long v = std::lround((double)w[i] / scale);
         v = std::max(-32000L, std::min(32000L, v));
-        vq[i] = (int)v;
+        (*vq)[i] = (int)v;
         eq += std::fabs((double)w[i] - scale * (double)v);
     }
     // |exact fp32 score - real-valued score| <= (2 taps + 2) u (|rho| + 255 sum|w|)   (covers FMA and mul+add orders)
@@ -562,18 +506,36 @@ bool lm_screen_build(const float *w, int kh, int kw, float init, int halo_x, int
     const double u = std::ldexp(1.0, -24);
     const double efp = (2.0 * ntaps + 2.0) * u * (std::fabs(rho_f) + 255.0 * wabs) * 1.01;
     const double eps = (255.0 * eq + efp) * (1.0 + 1e-9) + 1e-300;
-    (void)fma_mode;
     const double lo = std::floor((rho_f - eps) / scale) - 1.0, hi = std::ceil((rho_f + eps) / scale) + 1.0;
     const double lim = 4.0e18;
     out->t_lo = (long long)std::max(-lim, std::min(lim, lo));
     out->t_hi = (long long)std::max(-lim, std::min(lim, hi));
+    out->scale = scale;
+    out->eps = eps;
+    return true;
+}
+static inline void split_digits(int v, int *hi8, int *lo8) {
+    *lo8 = ((v + 128) & 255) - 128;
+    *hi8 = (v - *lo8) / 256;
+}
+
+bool lm_screen_build(const float *w, int kh, int kw, float init, int halo_x, int halo_y, int fma_mode, LmScreenHost *out,
+                     std::vector<int8_t> *img) {
+    (void)fma_mode;
+    const int ax = kw / 2, ay = kh / 2;
+    const int dx = halo_x - ax, dy = halo_y - ay;
+    if (dx < 0 || dy < 0) return false;
+    const int kbytes = SCR_TILE_X - 1 + dx + kw;  // window bytes a tile row needs
+    const int ks = (kbytes + 31) / 32;
+    const int rows = (SCR_TILE_M + kh - 1 + dy + 7) & ~7;
+    if (lm_screen_smem_bytes(kh, ks, rows, SCR_STAGES) > 220 * 1024) return false;
+    std::vector<int> vq;
+    if (!screen_quantize(w, kh * kw, init, &vq, out)) return false;
     out->kh = kh;
     out->ks = ks;
     out->dx = dx;
     out->dy = dy;
     out->rows = rows;
-    out->scale = scale;
-    out->eps = eps;
     // B image: [kh][2 ks chunks][64 rows][16 bytes]; row n < 32: hi digit of output column n, n >= 32: lo digit of
     // column n - 32; element k of the row = digit(v[j][k - c - dx]) inside the band, 0 outside.
     const int npanel = 2 * ks;
@@ -582,12 +544,42 @@ bool lm_screen_build(const float *w, int kh, int kw, float init, int halo_x, int
         for (int c = 0; c < SCR_TILE_X; ++c)
             for (int i = 0; i < kw; ++i) {
                 const int k = c + dx + i;
-                const int v = vq[j * kw + i];
-                const int lo8 = ((v + 128) & 255) - 128;
-                const int hi8 = (v - lo8) / 256;
+                int hi8, lo8;
+                split_digits(vq[j * kw + i], &hi8, &lo8);
                 const size_t base = (size_t)j * npanel * SCR_BJ + (size_t)(k >> 4) * SCR_BJ + (size_t)(k & 15);
                 (*img)[base + (size_t)c * 16] = (int8_t)hi8;
                 (*img)[base + (size_t)(c + 32) * 16] = (int8_t)lo8;
+            }
+    return true;
+}
+
+bool lm_screen_build2(const float *w, int kh, int kw, float init, int dx, int dy, int KH, int ks, int digits, LmScreenHost *out,
+                      std::vector<int8_t> *img) {
+    if (dx < 0 || dy < 0 || dy + kh > KH || SCR_TILE_X - 1 + dx + kw > 32 * ks) return false;
+    std::vector<int> vq;
+    if (!screen_quantize(w, kh * kw, init, &vq, out)) return false;
+    out->kh = KH;
+    out->ks = ks;
+    out->dx = dx;
+    out->dy = dy;
+    out->rows = (SCR_TILE_M + KH - 1 + 7) & ~7;
+    const int nhalf = digits < 0 ? 64 : 32;
+    const int npanel = 2 * ks;
+    const size_t chunk = (size_t)nhalf * 16;
+    img->assign((size_t)KH * npanel * chunk, 0);
+    for (int jj = 0; jj < kh; ++jj)
+        for (int c = 0; c < SCR_TILE_X; ++c)
+            for (int i = 0; i < kw; ++i) {
+                const int k = c + dx + i;
+                int hi8, lo8;
+                split_digits(vq[jj * kw + i], &hi8, &lo8);
+                const size_t base = (size_t)(jj + dy) * npanel * chunk + (size_t)(k >> 4) * chunk + (size_t)(k & 15);
+                if (digits < 0) {
+                    (*img)[base + (size_t)c * 16] = (int8_t)hi8;
+                    (*img)[base + (size_t)(c + 32) * 16] = (int8_t)lo8;
+                } else {
+                    (*img)[base + (size_t)c * 16] = (int8_t)(digits == 0 ? hi8 : lo8);
+                }
             }
     return true;
 }
@@ -679,9 +671,13 @@ int lm_launch_screen(const LmBatch &b, cudaStream_t s) {
         if (cudaFuncSetAttribute(k_screen, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) return -1;
         attr_done = true;
     }
-    int total_cta = P.job[P.njobs - 1].cta_begin + P.job[P.njobs - 1].ncta;
-    k_screen<<<total_cta, SCR_THREADS, smem, s>>>(P);
-    if (cudaGetLastError() != cudaSuccess) return -1;
+    if (b.scr.enabled == 2) {
+        if (lm_launch_screen2_kernel(b, s) < 0) return -1;
+    } else {
+        int total_cta = P.job[P.njobs - 1].cta_begin + P.job[P.njobs - 1].ncta;
+        k_screen<<<total_cta, SCR_THREADS, smem, s>>>(P);
+        if (cudaGetLastError() != cudaSuccess) return -1;
+    }
     if (b.ev_screen_done) cudaEventRecord(b.ev_screen_done, s);
     int launches = 1;
     // sparse exact pass: one launch per distinct padded kernel width (the jobs of other widths exit at once)

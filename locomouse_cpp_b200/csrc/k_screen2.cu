@@ -1,0 +1,373 @@
+// k_screen2.cu — the tensor-core screen of k_screen.cu on CTA PAIRS (tcgen05 cta_group::2).
+//
+// Why: an SS-operand tcgen05.mma with M = 128 is bound by operand streaming from shared memory (A is 4 kB per
+// instruction whatever N is), and a single CTA can only keep ONE template's Toeplitz operand
+// resident (120 kB), i.e. N = 64.  A CTA pair executes one M = 256 instruction: each CTA streams its own 128
+// window rows (its own y tile of the same frame / x tile) and only HALF of B, so N doubles at the same
+// per-SM operand traffic:
+//   paw + snout job : N = 128 = [paw hi | paw lo | snout hi | snout lo] x 32 columns; the paw images live in
+//                     CTA 0's shared memory, the snout images in CTA 1's.
+//   tail job        : N = 64  = [hi | lo] x 32 columns; hi digits in CTA 0, lo digits in CTA 1.
+// Everything else (exact int8 arithmetic, thresholds, 4x8 patch tasks for k_corr_sparse) is k_screen.cu's.
+//
+// Pair protocol: window-tile "full" and accumulator "empty" barriers live in the leader CTA (rank 0) and
+// collect arrivals from both CTAs (remote arrive through mapa); tcgen05.commit multicasts "tile free" and
+// "accumulator full" to the barrier at the same offset in both CTAs.  Only the leader issues MMAs.
+#include <algorithm>
+#include <cmath>
+
+#include "lm_internal.h"
+#include "umma_common.cuh"
+
+namespace {
+
+constexpr int S2_THREADS = 224;   // warps 0-3 epilogue, 4-5 loaders, 6 MMA issuer / TMEM owner
+constexpr int S2_TILE_M = 128;
+constexpr int S2_TILE_X = 32;
+constexpr int S2_STAGES = 4;
+constexpr int S2_TMEM_COLS = 256; // two accumulators of up to 128 columns
+
+struct Screen2JobDev {
+    LmScreen2Job j;
+    int out_w, out_h;
+    int nxt, nytp;            // x tiles, y-tile PAIRS
+    int pair_begin, npair;
+    int halo_x, halo_y;
+};
+
+struct Screen2Params {
+    Screen2JobDev job[4];
+    int njobs;
+    int B;
+    const uint8_t *win[2];
+    int win_h[2], win_pitch[2];
+    int64_t win_stride[2];
+    uint8_t *tailbin[2];
+    int tail_pitch;
+    int64_t tailbin_stride[2];
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_screen2(const __grid_constant__ Screen2Params P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[2 * S2_STAGES + 4];
+    __shared__ uint32_t tmem_base_s;
+
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    int ji = 0;
+    for (int q = 1; q < P.njobs; ++q)
+        if (pair >= P.job[q].pair_begin) ji = q;
+    const Screen2JobDev &J = P.job[ji];
+    const int prank = pair - J.pair_begin;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KH = J.j.KH, ks = J.j.ks, rows = J.j.rows, nhalf = J.j.nhalf;
+    const int npanel = 2 * ks;
+    const uint32_t panel_a = (uint32_t)rows * 16u;
+    const uint32_t stage_bytes = panel_a * npanel;
+    const uint32_t chunk_b = (uint32_t)nhalf * 16u;
+    const uint32_t b_bytes = (uint32_t)KH * npanel * chunk_b;
+    uint8_t *sB = smem;
+    uint8_t *sA = smem + b_bytes;
+    const int units_per_frame = J.nxt * J.nytp;
+    const int nunits = P.B * units_per_frame;
+    const int N = 2 * nhalf;  // UMMA N
+
+    const uint32_t bar0 = smem_u32(bars);
+    auto a_full = [&](int s) { return bar0 + 8u * s; };                       // leader's copy is used
+    auto a_empty = [&](int s) { return bar0 + 8u * (S2_STAGES + s); };        // local, multicast commit
+    auto d_full = [&](int a) { return bar0 + 8u * (2 * S2_STAGES + a); };     // local, multicast commit
+    auto d_empty = [&](int a) { return bar0 + 8u * (2 * S2_STAGES + 2 + a); };  // leader's copy is used
+
+    // ---- one-time setup ---------------------------------------------------------------------------------------
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(J.j.Bimg[rank]);
+        int4 *dst = reinterpret_cast<int4 *>(sB);
+        for (uint32_t i = tid; i < b_bytes / 16; i += S2_THREADS) dst[i] = __ldg(src + i);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < S2_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_full(s)), "r"(128));   // 64 loader threads x 2 CTAs
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_empty(s)), "r"(1));
+        }
+        for (int a = 0; a < 2; ++a) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(d_full(a)), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(d_empty(a)), "r"(256));  // 128 epilogue threads x 2 CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 6) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(S2_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers are initialised and both B halves are in place
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp >= 4 && warp < 6) {
+        // ================= loaders (both CTAs): this CTA's y tile of the unit ====================================
+        const int ll = tid - 128;
+        const int v = J.j.view;
+        const int win_h = P.win_h[v], pitch = P.win_pitch[v];
+        const int nchunks = rows * npanel;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int u = prank; u < nunits; u += J.npair) {
+            const int f = u / units_per_frame, rem = u - f * units_per_frame;
+            const int ytp = rem / J.nxt, xt = rem - ytp * J.nxt;
+            const int y0 = (2 * ytp + (int)rank) * S2_TILE_M, x0 = xt * S2_TILE_X;
+            const uint8_t *wbase = P.win[v] + (int64_t)f * P.win_stride[v];
+            mbar_wait(a_empty(stage), phase ^ 1u);
+            uint8_t *dstA = sA + (uint32_t)stage * stage_bytes;
+            constexpr int UNR = 5;
+            for (int base = 0; base < nchunks; base += 64 * UNR) {
+                int4 val[UNR];
+#pragma unroll
+                for (int q = 0; q < UNR; ++q) {
+                    const int idx = base + q * 64 + ll;
+                    int4 x = make_int4(0, 0, 0, 0);
+                    if (idx < nchunks) {
+                        const int r = idx / npanel, p = idx - r * npanel;
+                        const int wr = y0 + r, wc = x0 + 16 * p;
+                        if (wr < win_h && wc + 16 <= pitch) x = __ldg(reinterpret_cast<const int4 *>(wbase + (int64_t)wr * pitch + wc));
+                    }
+                    val[q] = x;
+                }
+#pragma unroll
+                for (int q = 0; q < UNR; ++q) {
+                    const int idx = base + q * 64 + ll;
+                    if (idx < nchunks) {
+                        const int r = idx / npanel, p = idx - r * npanel;
+                        *reinterpret_cast<int4 *>(dstA + (uint32_t)p * panel_a + (uint32_t)r * 16u) = val[q];
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_cluster(a_full(stage), 0);  // the leader's barrier counts both CTAs' loaders
+            if (++stage == S2_STAGES) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        }
+    } else if (warp == 6) {
+        // ================= MMA issuer (leader CTA only) =============================================================
+        if (rank == 0) {
+            // u8 x s8 -> s32, K-major operands, M = 256 across the pair, N = 2 * nhalf
+            const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            const uint64_t bdesc0 = umma_desc(smem_u32(sB), chunk_b);
+            const uint32_t a_step = (2u * panel_a) >> 4, b_step = (2u * chunk_b) >> 4;
+            const uint32_t b_row = ((uint32_t)npanel * chunk_b) >> 4;
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, accphase = 0;
+            for (int u = prank; u < nunits; u += J.npair) {
+                mbar_wait(d_empty(acc), accphase ^ 1u);
+                mbar_wait(a_full(stage), phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t d = tmem + (uint32_t)acc * 128u;
+                    uint64_t adesc = umma_desc(smem_u32(sA) + (uint32_t)stage * stage_bytes, panel_a);
+                    uint64_t bdesc = bdesc0;
+                    uint32_t accum = 0;
+                    for (int j = 0; j < KH; ++j) {
+                        uint64_t ad = adesc, bd = bdesc;
+                        for (int k = 0; k < ks; ++k) {
+                            umma_i8_2cta(d, ad, bd, idesc, accum);
+                            accum = 1;
+                            ad += a_step;
+                            bd += b_step;
+                        }
+                        adesc += 1;  // next kernel row: 16 bytes further down the same tile (in both CTAs)
+                        bdesc += b_row;
+                    }
+                    umma_commit_2cta(a_empty(stage));
+                    umma_commit_2cta(d_full(acc));
+                }
+                __syncwarp();
+                if (++stage == S2_STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    accphase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ================= epilogue (both CTAs): this CTA's 128 rows x N columns ===================================
+        const int v = J.j.view;
+        const int pitch = P.win_pitch[v];
+        int acc = 0;
+        uint32_t accphase = 0;
+        for (int u = prank; u < nunits; u += J.npair) {
+            const int f = u / units_per_frame, rem = u - f * units_per_frame;
+            const int ytp = rem / J.nxt, xt = rem - ytp * J.nxt;
+            const int y = (2 * ytp + (int)rank) * S2_TILE_M + tid, x0 = xt * S2_TILE_X;
+            mbar_wait(d_full(acc), accphase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)acc * 128u;
+            const bool rowok = y < J.out_h;
+            const int wvalid = J.out_w - x0;
+            const uint32_t colmask = wvalid >= 32 ? 0xffffffffu : (wvalid <= 0 ? 0u : ((1u << wvalid) - 1u));
+            uint32_t need_t[2] = {0u, 0u}, sign0 = 0u;
+            for (int t = 0; t < J.j.ntmpl; ++t) {
+                uint32_t hi[32], lo[32];
+                tmem_ld32(ta + (uint32_t)t * 64u, hi);
+                tmem_ld32(ta + (uint32_t)t * 64u + 32u, lo);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const long long t_lo = J.j.t_lo[t], t_hi = J.j.t_hi[t];
+                uint32_t need = 0, sign = 0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const long long V = (long long)(int)hi[c] * 256 + (long long)(int)lo[c];
+                    if (V > t_lo) need |= 1u << c;
+                    if (V > t_hi) sign |= 1u << c;
+                }
+                need_t[t] = rowok ? (need & colmask) : 0u;
+                if (t == 0) sign0 = sign;
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive_cluster(d_empty(acc), 0);  // the leader's barrier counts both CTAs' epilogues
+            if (++acc == 2) {
+                acc = 0;
+                accphase ^= 1u;
+            }
+            for (int t = 0; t < J.j.ntmpl; ++t) {
+                uint32_t need = need_t[t];
+                if (J.j.is_tail) {
+                    if (rowok) {
+                        uint8_t *tb = P.tailbin[v] + (int64_t)f * P.tailbin_stride[v] + (int64_t)y * P.tail_pitch + x0;
+                        uint32_t w[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const uint32_t nib = (sign0 >> (4 * q)) & 0xfu;
+                            w[q] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+                        }
+                        reinterpret_cast<uint4 *>(tb)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                        reinterpret_cast<uint4 *>(tb)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    }
+                    need &= ~sign0;
+                } else if (need) {
+                    const uint8_t *crow = P.win[v] + (int64_t)f * P.win_stride[v] + (int64_t)(y + J.halo_y) * pitch + x0 + J.halo_x;
+                    uint32_t m = need;
+                    while (m) {
+                        const int c = __ffs(m) - 1;
+                        m &= m - 1;
+                        if (__ldg(crow + c) <= 25) need &= ~(1u << c);
+                    }
+                }
+                uint32_t pf = ((need & 0xffu) ? 1u : 0u) | ((need & 0xff00u) ? 2u : 0u) | ((need & 0xff0000u) ? 4u : 0u) |
+                              ((need & 0xff000000u) ? 8u : 0u);
+                pf |= __shfl_xor_sync(0xffffffffu, pf, 1);
+                pf |= __shfl_xor_sync(0xffffffffu, pf, 2);
+                const int cnt = ((lane & 3) == 0) ? __popc(pf) : 0;
+                const uint32_t any = __ballot_sync(0xffffffffu, cnt > 0);
+                if (any) {
+                    int incl = cnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int w2 = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += w2;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    int base = 0;
+                    if (lane == 31) base = atomicAdd(J.j.ntasks[t], total);
+                    base = __shfl_sync(0xffffffffu, base, 31);
+                    int o = base + incl - cnt;
+                    if (cnt) {
+                        const uint32_t head = ((uint32_t)f << 14) | ((uint32_t)(y >> 2) << 7);
+                        uint32_t m = pf;
+                        while (m) {
+                            const int q = __ffs(m) - 1;
+                            m &= m - 1;
+                            if (o < J.j.task_cap[t]) J.j.tasks[t][o] = head | (uint32_t)((x0 >> 3) + q);
+                            ++o;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // ---- teardown: nobody may free TMEM (or exit, its barriers are remote targets) before the peer is done ----
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 6) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(S2_TMEM_COLS));
+    }
+}
+
+}  // namespace
+
+size_t lm_screen2_smem_bytes(int KH, int ks, int rows, int nhalf) {
+    return (size_t)KH * 2 * ks * nhalf * 16 + (size_t)S2_STAGES * 2 * ks * rows * 16;
+}
+
+// Launches k_screen2 for the four pair-level jobs; the caller has zeroed the task counters.
+int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s) {
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    const int npairs_total = n_sm / 2;
+    Screen2Params P{};
+    size_t smem = 0;
+    double work[4], total = 0.0;
+    for (int v = 0; v < 2; ++v)
+        for (int q = 0; q < 2; ++q) {
+            const LmScreen2Job &sj = b.scr.job2[v][q];
+            if (!sj.Bimg[0]) continue;  // no tail box
+            Screen2JobDev &J = P.job[P.njobs];
+            J.j = sj;
+            J.out_w = sj.is_tail ? b.tail_w : b.view[v].box_w;
+            J.out_h = b.view[v].box_h;
+            J.nxt = (J.out_w + S2_TILE_X - 1) / S2_TILE_X;
+            const int nyt = (J.out_h + S2_TILE_M - 1) / S2_TILE_M;
+            J.nytp = (nyt + 1) / 2;
+            J.halo_x = b.view[v].halo_x;
+            J.halo_y = b.view[v].halo_y;
+            // per-instruction cost ~ max(93, 42 + N/2) cycles (tools/umma_sw_probe.cu)
+            work[P.njobs] = (double)J.nxt * J.nytp * sj.KH * sj.ks * (sj.nhalf >= 64 ? 106.0 : 93.0);
+            total += work[P.njobs];
+            smem = std::max(smem, lm_screen2_smem_bytes(sj.KH, sj.ks, sj.rows, sj.nhalf));
+            ++P.njobs;
+        }
+    if (!P.njobs) return 0;
+    {
+        int left = npairs_total, pr = 0;
+        double wleft = total;
+        for (int q = 0; q < P.njobs; ++q) {
+            int n = (q == P.njobs - 1) ? left : (int)std::lround(left * work[q] / wleft);
+            n = std::max(1, std::min(n, left - (P.njobs - 1 - q)));
+            P.job[q].pair_begin = pr;
+            P.job[q].npair = n;
+            pr += n;
+            left -= n;
+            wleft -= work[q];
+        }
+    }
+    P.B = b.B;
+    for (int v = 0; v < 2; ++v) {
+        P.win[v] = b.win[v];
+        P.win_h[v] = b.view[v].win_h;
+        P.win_pitch[v] = b.view[v].win_pitch;
+        P.win_stride[v] = b.view[v].win_stride;
+        P.tailbin[v] = b.tailbin[v];
+        P.tailbin_stride[v] = (int64_t)b.bb_h[v] * b.tail_pitch;
+    }
+    P.tail_pitch = b.tail_pitch;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(k_screen2, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) return -1;
+        attr_done = true;
+    }
+    const int pairs = P.job[P.njobs - 1].pair_begin + P.job[P.njobs - 1].npair;
+    k_screen2<<<2 * pairs, S2_THREADS, smem, s>>>(P);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}

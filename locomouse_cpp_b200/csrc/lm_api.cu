@@ -28,7 +28,7 @@ struct lm_ctx {
     int32_t *d_calib = nullptr;
     float *d_tmpl[2][3] = {};
     std::vector<float> h_tmpl[2][3];  // host copies (the screen's quantisation is derived from them)
-    int opt_screen = 1;               // tensor-core screen + sparse exact pass (0: dense exact kernel only)
+    int opt_screen = 2;               // 0: dense exact kernel only, 1: tensor-core screen, one CTA per tile, 2: CTA pairs
     int opt_subbatch = 256;
     LmScreenHost scr_info[2][3] = {};
     int t_rows[2][3] = {}, t_cols[2][3] = {};
@@ -292,6 +292,73 @@ int prepare(lm_ctx *ctx) {
                     if ((rc = dalloc(ctx, &J.tasks, (size_t)J.task_cap))) return rc;
                 }
             b.scr.enabled = 1;
+            // ---- CTA-pair variant (k_screen2): per view a paw + snout job and a tail job in a common geometry ------
+            if (want_screen >= 2) {
+                bool ok2 = true;
+                std::vector<int8_t> img2[2][2][2];  // [view][job][cta rank]
+                int KHs[2][2], kss[2][2];
+                for (int v = 0; v < 2 && ok2; ++v) {
+                    auto dxy = [&](int f, int *dx, int *dy) {
+                        *dx = b.view[v].halo_x - b.tmpl[v][f].ax;
+                        *dy = b.view[v].halo_y - b.tmpl[v][f].ay;
+                    };
+                    for (int q = 0; q < 2 && ok2; ++q) {
+                        const int f0 = q == 0 ? LM_PAW : LM_TAIL, f1 = q == 0 ? LM_SNOUT : LM_TAIL;
+                        if (q == 1 && k.tail_w <= 0) continue;
+                        int KH = 0, ksx = 0;
+                        for (int f : {f0, f1}) {
+                            int dx, dy;
+                            dxy(f, &dx, &dy);
+                            KH = std::max(KH, dy + b.tmpl[v][f].kh);
+                            ksx = std::max(ksx, (31 + dx + b.tmpl[v][f].kw + 31) / 32);
+                        }
+                        const int rows = (128 + KH - 1 + 7) & ~7, nhalf = q == 0 ? 64 : 32;
+                        if (lm_screen2_smem_bytes(KH, ksx, rows, nhalf) > 220 * 1024) ok2 = false;
+                        KHs[v][q] = KH;
+                        kss[v][q] = ksx;
+                        for (int r = 0; r < 2 && ok2; ++r) {
+                            const int f = r == 0 ? f0 : f1;
+                            int dx, dy;
+                            dxy(f, &dx, &dy);
+                            LmScreenHost H{};
+                            ok2 = lm_screen_build2(ctx->h_tmpl[v][f].data(), b.tmpl[v][f].kh, b.tmpl[v][f].kw, b.tmpl[v][f].init, dx, dy, KH,
+                                                   ksx, q == 0 ? -1 : r, &H, &img2[v][q][r]);
+                            // same quantisation as the single-CTA build -> same thresholds
+                            if (ok2 && (H.t_lo != ctx->scr_info[v][f].t_lo || H.t_hi != ctx->scr_info[v][f].t_hi)) ok2 = false;
+                        }
+                    }
+                }
+                if (ok2) {
+                    for (int v = 0; v < 2; ++v)
+                        for (int q = 0; q < 2; ++q) {
+                            LmScreen2Job &J2 = b.scr.job2[v][q];
+                            J2 = LmScreen2Job{};
+                            if (q == 1 && k.tail_w <= 0) continue;
+                            for (int r = 0; r < 2; ++r) {
+                                int8_t *dimg = nullptr;
+                                if ((rc = dalloc(ctx, &dimg, img2[v][q][r].size()))) return rc;
+                                CK(cudaMemcpy(dimg, img2[v][q][r].data(), img2[v][q][r].size(), cudaMemcpyHostToDevice));
+                                J2.Bimg[r] = dimg;
+                            }
+                            J2.view = v;
+                            J2.is_tail = q;
+                            J2.ntmpl = q == 0 ? 2 : 1;
+                            J2.KH = KHs[v][q];
+                            J2.ks = kss[v][q];
+                            J2.rows = (128 + J2.KH - 1 + 7) & ~7;
+                            J2.nhalf = q == 0 ? 64 : 32;
+                            for (int t = 0; t < J2.ntmpl; ++t) {
+                                const int f = q == 0 ? t : LM_TAIL;
+                                J2.t_lo[t] = b.scr.job[v][f].t_lo;
+                                J2.t_hi[t] = b.scr.job[v][f].t_hi;
+                                J2.tasks[t] = b.scr.job[v][f].tasks;
+                                J2.task_cap[t] = b.scr.job[v][f].task_cap;
+                                J2.ntasks[t] = b.scr.ntasks + (v * 3 + f);
+                            }
+                        }
+                    b.scr.enabled = 2;
+                }
+            }
         }
     }
     ctx->Bcap = Bcap;
@@ -628,7 +695,7 @@ int lm_set_option(lm_ctx *ctx, const char *name, int64_t value) {
     if (!name) return fail(ctx, LM_ERR_INVALID, "lm_set_option: null name");
     cudaSetDevice(ctx->device);
     if (!strcmp(name, "screen")) {
-        if (value != 0 && value != 1) return fail(ctx, LM_ERR_INVALID, "option screen must be 0 or 1");
+        if (value < 0 || value > 2) return fail(ctx, LM_ERR_INVALID, "option screen must be 0, 1 or 2");
         ctx->opt_screen = (int)value;
     } else if (!strcmp(name, "subbatch")) {
         if (value < 1 || value > 4096) return fail(ctx, LM_ERR_INVALID, "option subbatch must be in [1, 4096]");

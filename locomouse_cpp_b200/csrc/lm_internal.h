@@ -56,9 +56,20 @@ struct LmScreenJob {
     uint32_t *tasks;      // device, [task_cap]: frame << 14 | patch_row << 7 | patch_col
     int task_cap;
 };
+// CTA-pair variant (k_screen2.cu): per view one paw+snout job (N = 128) and one tail job (N = 64).
+struct LmScreen2Job {
+    const int8_t *Bimg[2];  // device, per CTA rank: [KH][2*ks chunks][nhalf rows][16 B]
+    int view, is_tail, ntmpl;
+    int KH, ks, rows, nhalf;
+    long long t_lo[2], t_hi[2];   // per template decided by this job (paw, snout | tail)
+    uint32_t *tasks[2];
+    int task_cap[2];
+    int *ntasks[2];
+};
 struct LmScreen {
-    int enabled;
+    int enabled;          // 0: dense exact kernel, 1: k_screen (one CTA per tile), 2: k_screen2 (CTA pairs)
     LmScreenJob job[2][3];
+    LmScreen2Job job2[2][2];  // [view][0 = paw + snout, 1 = tail]
     int *ntasks;          // device, [6] = [view][feat]
 };
 
@@ -125,6 +136,13 @@ struct LmScreenHost {
 bool lm_screen_build(const float *w, int kh, int kw, float init, int halo_x, int halo_y, int fma_mode,
                      LmScreenHost *out, std::vector<int8_t> *img);
 size_t lm_screen_smem_bytes(int kh, int ks, int rows, int stages);
+// CTA-pair variant: image of one template in the common geometry of its job (KH kernel-row steps, ks K steps, the
+// template's own row offset dy folded in as leading zero rows).  digits: -1 = rows [0,32) hi + [32,64) lo,
+// 0 = hi only (32 rows), 1 = lo only (32 rows).  Thresholds / scale / eps as lm_screen_build.
+bool lm_screen_build2(const float *w, int kh, int kw, float init, int dx, int dy, int KH, int ks, int digits,
+                      LmScreenHost *out, std::vector<int8_t> *img);
+size_t lm_screen2_smem_bytes(int KH, int ks, int rows, int nhalf);
+int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s);
 
 // pick the padded kernel-row width the correlation kernel is instantiated for (>= kw), or -1
 int lm_corr_kwp(int kw);

@@ -25,7 +25,7 @@ def _run_both(spec, n, seed, model_edit=None, **kw):
         model = model_edit(model)
     frames = frames.numpy()
     out = []
-    for screen in (1, 0):
+    for screen in (2, 1, 0):
         det = _detector(cfg, model, bkg, calib, screen)
         r = det.detect_batch(frames, bx, bs, bb, **kw)
         out.append((r, det.info("screen_active")))
@@ -36,9 +36,10 @@ def _run_both(spec, n, seed, model_edit=None, **kw):
 @pytest.mark.parametrize("kw", [dict(), dict(method="TM_DE", flip=True), dict(method="base", fma_mode=False),
                                 dict(warp=True, vid_pad=5, conn=4)])
 def test_screen_equals_dense_and_oracle(oracle, kw):
-    (on, on_active), (off, off_active) = _run_both(synth.SynthSpec(**kw), 6, 1000)[0]
-    assert on_active == 1.0 and off_active == 0.0
+    (pair, pair_active), (on, on_active), (off, off_active) = _run_both(synth.SynthSpec(**kw), 6, 1000)[0]
+    assert pair_active == 2.0 and on_active == 1.0 and off_active == 0.0
     assert diff_results(on, off) == [] and on.checksum() == off.checksum()
+    assert diff_results(pair, off) == [] and pair.checksum() == off.checksum()
 
 
 def test_screen_vs_oracle_mixed_template_shapes(oracle):
@@ -46,10 +47,10 @@ def test_screen_vs_oracle_mixed_template_shapes(oracle):
     sparse exact kernel runs one launch per padded kernel width."""
     shapes = (((30, 30), (24, 28), (20, 16)), ((27, 30), (30, 22), (15, 17)))
     spec = synth.SynthSpec(tshapes=shapes)
-    ((on, a1), (off, a0)), (cfg, model, bkg, calib, frames, bx, bs, bb) = _run_both(spec, 4, 1001)
-    assert a1 == 1.0
+    ((pair, a2), (on, a1), (off, a0)), (cfg, model, bkg, calib, frames, bx, bs, bb) = _run_both(spec, 4, 1001)
+    assert a2 == 2.0 and a1 == 1.0
     ref = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=8)
-    assert diff_results(on, ref) == [] and diff_results(off, ref) == []
+    assert diff_results(pair, ref) == [] and diff_results(on, ref) == [] and diff_results(off, ref) == []
 
 
 def test_screen_large_batch_property():
@@ -62,12 +63,12 @@ def test_screen_large_batch_property():
     frames, bx, bs, bb = synth.make_video(spec, 700, 1234, "cuda", bkg)
     torch.cuda.synchronize()
     sums = []
-    for screen in (1, 0):
+    for screen in (2, 1, 0):
         det = _detector(cfg, model, bkg, calib, screen)
         r = det.detect_batch(frames, bx, bs, bb)
         sums.append((r.checksum(), int(r.n_bottom.sum()), int(r.n_side.sum()), int(r.match_n.sum())))
         det.close()
-    assert sums[0] == sums[1]
+    assert sums[0] == sums[2] and sums[1] == sums[2]
     assert sums[0][1] > 1000
 
 
@@ -78,13 +79,14 @@ def test_screen_dense_threshold_and_degenerate_templates(oracle):
     def lower_rho(m):
         return Model(w=m.w, rho=[[r * 0.25 for r in row] for row in m.rho])
 
-    ((on, a1), (off, _)), _ = _run_both(synth.SynthSpec(), 3, 1002, model_edit=lower_rho, allow_overflow=True)
-    assert a1 == 1.0
+    ((pair, a2), (on, a1), (off, _)), _ = _run_both(synth.SynthSpec(), 3, 1002, model_edit=lower_rho, allow_overflow=True)
+    assert a2 == 2.0 and a1 == 1.0
     # overflowing lists keep an unspecified subset of detections; compare only frames without overflow
-    ok = (on.flags == 0) & (off.flags == 0)
-    assert np.array_equal(on.flags != 0, off.flags != 0)
-    for name in on.ARRAYS:
-        assert np.array_equal(getattr(on, name)[ok], getattr(off, name)[ok]), name
+    for got in (pair, on):
+        ok = (got.flags == 0) & (off.flags == 0)
+        assert np.array_equal(got.flags != 0, off.flags != 0)
+        for name in got.ARRAYS:
+            assert np.array_equal(getattr(got, name)[ok], getattr(off, name)[ok]), name
 
     def zero_paw(m):
         w = [[a.copy() for a in row] for row in m.w]
@@ -93,18 +95,18 @@ def test_screen_dense_threshold_and_degenerate_templates(oracle):
         rho[0][0] = 0.0
         return Model(w=w, rho=rho)
 
-    ((on, a1), (off, _)), (cfg, model, bkg, calib, frames, bx, bs, bb) = _run_both(synth.SynthSpec(), 3, 1002, model_edit=zero_paw)
-    assert a1 == 1.0 and diff_results(on, off) == []
+    ((pair, a2), (on, a1), (off, _)), (cfg, model, bkg, calib, frames, bx, bs, bb) = _run_both(synth.SynthSpec(), 3, 1002, model_edit=zero_paw)
+    assert a2 == 2.0 and a1 == 1.0 and diff_results(on, off) == [] and diff_results(pair, off) == []
     assert int(on.n_bottom[:, 0].sum()) == 0
     ref = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=8)
-    assert diff_results(on, ref) == []
+    assert diff_results(pair, ref) == []
 
 
 def test_screen_falls_back_to_dense_for_large_templates(oracle):
     """Templates whose Toeplitz operand does not fit in shared memory (here 40x40) run the dense exact kernel;
     the option stays a no-op for results."""
     shapes = (((40, 40), (40, 40), (40, 40)), ((40, 40), (40, 40), (40, 40)))
-    ((on, a1), (off, a0)), (cfg, model, bkg, calib, frames, bx, bs, bb) = _run_both(synth.SynthSpec(tshapes=shapes), 2, 1000)
-    assert a1 == 0.0 and a0 == 0.0
+    ((pair, a2), (on, a1), (off, a0)), (cfg, model, bkg, calib, frames, bx, bs, bb) = _run_both(synth.SynthSpec(tshapes=shapes), 2, 1000)
+    assert a2 == 0.0 and a1 == 0.0 and a0 == 0.0
     ref = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=8)
-    assert diff_results(on, ref) == []
+    assert diff_results(pair, ref) == []

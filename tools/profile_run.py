@@ -13,7 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=512)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--scale", type=int, default=1)
-ap.add_argument("--screen", type=int, default=1)
+ap.add_argument("--screen", type=int, default=2)
 args = ap.parse_args()
 spec = synth.SynthSpec(scale=args.scale) if args.scale == 1 else synth.SynthSpec(scale=args.scale, cand_cap=128, match_cap=512)
 cfg, model, bkg, calib, _, _, _, _ = synth.make_problem(spec, 8, seed=1000)

@@ -171,16 +171,24 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_bottom(const __grid_constan
     const LmTemplateDev &T = b.tmpl[LM_BOTTOM][feat];
     const int w = T.kw, h = T.kh, wh2 = 2 * w * h;
     if (tid == 0) s_nc = 0;
-    // parent = first better-ranked overlapping detection
-    for (int j = tid; j < n; j += NMS_THREADS) {
-        const int xj = m.x[j], yj = m.y[j];
-        int par = j;
-        for (int i = 0; i < j; ++i)
-            if (overlaps(m.x[i] - xj, m.y[i] - yj, w, h, wh2)) {
-                par = i;
-                break;
+    // parent = first better-ranked overlapping detection.  One warp per detection j: the lanes test 32 better ranks at
+    // a time and the first set ballot bit is the parent, so the cost is ceil(parent_rank / 32) and evenly spread.
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int j = warp; j < n; j += NMS_THREADS / 32) {
+            const int xj = m.x[j], yj = m.y[j];
+            int par = j;
+            for (int base = 0; base < j; base += 32) {
+                const int i = base + lane;
+                const bool hit = i < j && overlaps(m.x[i] - xj, m.y[i] - yj, w, h, wh2);
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                if (bal) {
+                    par = base + __ffs(bal) - 1;
+                    break;
+                }
             }
-        m.link[j] = par;
+            if (lane == 0) m.link[j] = par;
+        }
     }
     __syncthreads();
     // roots by pointer chasing (parents only point to better ranks, so chains end)
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_side(const __grid_constant_
     NmsSmem m = carve(raw, P);
     int *slot = reinterpret_cast<int *>(m.y + P);
     int *root_rank = slot + P;
-    __shared__ int s_n;
+    __shared__ int s_n, s_next;
     const int f = blockIdx.x >> 1, feat = blockIdx.x & 1, tid = threadIdx.x;
     lm_cand *out = b.side + (int64_t)(f * 2 + feat) * b.cand_cap;
     {
@@ -252,13 +260,27 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_side(const __grid_constant_
     const int w = T.kw, h = T.kh, wh2 = 2 * w * h;
     for (int j = tid; j < n; j += NMS_THREADS) m.link[j] = -1;  // -1 = free
     __syncthreads();
-    int nc = 0;
-    for (int c = 0; c < n; ++c) {
-        if (m.link[c] >= 0) continue;  // already clustered (block-uniform: link only changes at barriers)
-        // c is the next maximum
+    // Greedy: the next maximum is the best-ranked detection that is still free; it is found with a block-wide
+    // atomicMin over 512 candidates at a time instead of a serial scan of the (mostly clustered) list.
+    const int INF = 0x7fffffff;
+    if (tid == 0) s_next = INF;
+    __syncthreads();
+    int nc = 0, c = -1;
+    for (;;) {
+        int found = INF;
+        for (int base = c + 1; base < n; base += NMS_THREADS) {
+            const int idx = base + tid;
+            if (idx < n && m.link[idx] < 0) atomicMin(&s_next, idx);
+            __syncthreads();
+            found = s_next;
+            __syncthreads();  // everyone has read s_next before the next chunk (or the reset below) touches it
+            if (found != INF) break;
+        }
+        if (found == INF) break;
+        c = found;
         const int xc = m.x[c], yc = m.y[c];
-        __syncthreads();  // everyone has read link[c] before it is written
         if (tid == 0) {
+            s_next = INF;
             m.link[c] = c;
             slot[c] = nc;
             if (nc < b.cand_cap) root_rank[nc] = c;

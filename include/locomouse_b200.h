@@ -151,6 +151,9 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device,
  *             outputs; 0: dense exact FP32 kernel only.  All three produce bit-identical results (the screen
  *             only discards outputs proven <= 0).
  *  "subbatch" frames per internal sub-batch (default 256).
+ *  "streams"  2 (default): consecutive sub-batches run on two streams with separate scratch, so the latency-bound
+ *             kernels of one overlap the tensor-core kernel of the next; 1: all kernels strictly serial (used when
+ *             timing a single kernel with events).
  * lm_get_info: "screen_active" (2/1/0 after the first lm_detect_batch, -1 before), "subbatch", "ms_screen"
  *             (device ms of the tensor-core kernel alone in the last call; ms[2] of lm_last_timing = screen + exact pass),
  *             "screen_eps_<view><feat>" / "screen_scale_<view><feat>" (error bound / weight quantum). */

@@ -18,7 +18,7 @@ std::string g_create_error;
 
 struct lm_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, stream1 = nullptr, copy_stream = nullptr;  // sub-batch k runs on stream (k & 1)
     lm_config cfg{};
     bool configured = false, model_set = false, bkg_set = false, calib_set = false;
     LmGeom geom{};
@@ -30,13 +30,15 @@ struct lm_ctx {
     std::vector<float> h_tmpl[2][3];  // host copies (the screen's quantisation is derived from them)
     int opt_screen = 2;               // 0: dense exact kernel only, 1: tensor-core screen, one CTA per tile, 2: CTA pairs
     int opt_subbatch = 256;
+    int opt_streams = 2;              // 2: consecutive sub-batches overlap on two streams, 1: strictly serial kernels
     LmScreenHost scr_info[2][3] = {};
     int t_rows[2][3] = {}, t_cols[2][3] = {};
     double t_rho[2][3] = {};
 
     // sub-batch scratch
     int Bcap = 0;
-    LmBatch bt{};                     // config-derived fields + scratch pointers
+    LmBatch bt{};                     // config-derived fields + scratch pointers (scratch set 0)
+    LmBatch bt1{};                    // the same with scratch set 1: consecutive sub-batches overlap on two streams
     std::vector<void *> dev_allocs;   // everything cudaMalloc'ed for the scratch
     uint8_t *d_stage[2] = {};         // staged raw frames (Bcap + 1 each) when frames come from the host
     uint32_t *d_bb[2] = {};           // [3][Bcap] per slot
@@ -44,7 +46,7 @@ struct lm_ctx {
     struct ResOff {
         size_t n_bottom, n_side, bottom, side, match_n, match_y, match_s, tail, flags, total;
     } ro{};
-    uint8_t *d_res = nullptr;         // device results for one sub-batch
+    uint8_t *d_res[2] = {};           // device results for one sub-batch, per scratch set
     uint8_t *h_res[2] = {};           // pinned
     cudaEvent_t ev_h2d[2] = {}, ev_done[2] = {};
     cudaEvent_t ev_stage[2][8] = {};
@@ -54,6 +56,7 @@ struct lm_ctx {
     float ms[7] = {};
     int64_t launches = 0;
     int last_B = 0;                   // size of the last sub-batch (for lm_debug_fetch)
+    int last_slot = 0;
     int64_t last_s0 = 0;
 };
 
@@ -132,7 +135,7 @@ void free_scratch(lm_ctx *c) {
         c->d_stage[s] = nullptr;
         c->d_bb[s] = nullptr;
     }
-    c->d_res = nullptr;
+    c->d_res[0] = c->d_res[1] = nullptr;
     c->Bcap = 0;
 }
 
@@ -244,17 +247,23 @@ int prepare(lm_ctx *ctx) {
     o.tail = off;     off = align256(off + B * 3 * k.n_tail_points * 4);
     o.flags = off;    off = align256(off + B * 4);
     o.total = off;
-    if ((rc = dalloc(ctx, &ctx->d_res, o.total))) return rc;
     for (int s = 0; s < 2; ++s) CK(cudaMallocHost((void **)&ctx->h_res[s], o.total));
-    b.n_bottom = (int32_t *)(ctx->d_res + o.n_bottom);
-    b.n_side = (int32_t *)(ctx->d_res + o.n_side);
-    b.bottom = (lm_cand *)(ctx->d_res + o.bottom);
-    b.side = (lm_cand *)(ctx->d_res + o.side);
-    b.match_n = (int32_t *)(ctx->d_res + o.match_n);
-    b.match_y = (int32_t *)(ctx->d_res + o.match_y);
-    b.match_s = (double *)(ctx->d_res + o.match_s);
-    b.tail = (int32_t *)(ctx->d_res + o.tail);
-    b.flags = (uint32_t *)(ctx->d_res + o.flags);
+    auto bind_results = [&](LmBatch &x, int set) -> int {
+        int rc2;
+        if ((rc2 = dalloc(ctx, &ctx->d_res[set], o.total))) return rc2;
+        uint8_t *r = ctx->d_res[set];
+        x.n_bottom = (int32_t *)(r + o.n_bottom);
+        x.n_side = (int32_t *)(r + o.n_side);
+        x.bottom = (lm_cand *)(r + o.bottom);
+        x.side = (lm_cand *)(r + o.side);
+        x.match_n = (int32_t *)(r + o.match_n);
+        x.match_y = (int32_t *)(r + o.match_y);
+        x.match_s = (double *)(r + o.match_s);
+        x.tail = (int32_t *)(r + o.tail);
+        x.flags = (uint32_t *)(r + o.flags);
+        return LM_OK;
+    };
+    if ((rc = bind_results(b, 0))) return rc;
     // ---- tensor-core screen (k_screen.cu): all six jobs must qualify, otherwise the dense kernel runs --------
     b.scr = LmScreen{};
     int want_screen = ctx->opt_screen;
@@ -361,6 +370,39 @@ int prepare(lm_ctx *ctx) {
             }
         }
     }
+    // ---- scratch set 1: same geometry and operands, its own mutable buffers ------------------------------------
+    {
+        LmBatch &c = ctx->bt1;
+        c = b;
+        if ((rc = dalloc(ctx, &c.minmax, (B + 1) * 2))) return rc;
+        if ((rc = dalloc(ctx, &c.lut, (B + 1) * 256))) return rc;
+        for (int v = 0; v < 2; ++v) {
+            if ((rc = dalloc(ctx, &c.win[v], B * b.view[v].win_stride + 512))) return rc;
+            if ((rc = dalloc(ctx, &c.tailbin[v], B * b.bb_h[v] * b.tail_pitch))) return rc;
+        }
+        if ((rc = dalloc(ctx, &c.tailmask, B * b.bb_h[LM_BOTTOM] * b.tail_pitch))) return rc;
+        if ((rc = dalloc(ctx, &c.sidemask, B * b.bb_h[LM_SIDE] * b.tail_pitch))) return rc;
+        if ((rc = dalloc(ctx, &c.cc, B * 3 * b.cc_stride))) return rc;
+        if ((rc = dalloc(ctx, &c.cc_flag, B))) return rc;
+        if ((rc = dalloc(ctx, &c.det, B * 4 * (size_t)k.det_cap))) return rc;
+        if ((rc = dalloc(ctx, &c.det_count, B * 4))) return rc;
+        if ((rc = bind_results(c, 1))) return rc;
+        if (b.scr.enabled) {
+            if ((rc = dalloc(ctx, &c.scr.ntasks, 8))) return rc;
+            for (int v = 0; v < 2; ++v)
+                for (int f = 0; f < 3; ++f)
+                    if (b.scr.job[v][f].tasks && (rc = dalloc(ctx, &c.scr.job[v][f].tasks, (size_t)b.scr.job[v][f].task_cap))) return rc;
+            for (int v = 0; v < 2; ++v)
+                for (int q = 0; q < 2; ++q) {
+                    LmScreen2Job &J2 = c.scr.job2[v][q];
+                    for (int t = 0; t < J2.ntmpl; ++t) {
+                        const int f = q == 0 ? t : LM_TAIL;
+                        J2.tasks[t] = c.scr.job[v][f].tasks;
+                        J2.ntasks[t] = c.scr.ntasks + (v * 3 + f);
+                    }
+                }
+        }
+    }
     ctx->Bcap = Bcap;
     return LM_OK;
 }
@@ -402,6 +444,7 @@ int lm_create(lm_ctx **out, int device) {
     ctx = new lm_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream1, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, LM_ERR_RUNTIME, "cudaStreamCreate failed");
@@ -434,6 +477,7 @@ int lm_destroy(lm_ctx *ctx) {
         cudaEventDestroy(ctx->ev_mid[s]);
     }
     cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->stream1);
     cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
     return LM_OK;
@@ -572,7 +616,7 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, co
     ctx->ms_screen = 0.f;
     ctx->launches = 0;
     const lm_ctx::ResOff &o = ctx->ro;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t streams[2] = {ctx->stream, ctx->opt_streams == 2 ? ctx->stream1 : ctx->stream};
 
     auto issue_h2d = [&](int64_t sub) -> int {
         const int slot = (int)(sub & 1);
@@ -620,13 +664,14 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, co
         return LM_OK;
     };
 
-    CK(cudaEventRecord(ctx->ev_call[0], st));
+    CK(cudaEventRecord(ctx->ev_call[0], streams[0]));
     if ((rc = issue_h2d(0))) return rc;
     for (int64_t sub = 0; sub < nsub; ++sub) {
         const int slot = (int)(sub & 1);
         const int64_t s0 = sub * Bcap;
         const int B = (int)std::min<int64_t>(Bcap, n - s0);
-        LmBatch b = ctx->bt;
+        cudaStream_t st = streams[slot];
+        LmBatch b = slot ? ctx->bt1 : ctx->bt;
         b.B = B;
         b.first_index = first_frame_index + s0;
         if (frames_on_device) {
@@ -672,16 +717,18 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, co
             if (sub >= 1 && (rc = drain(sub - 1))) return rc;
             if ((rc = issue_h2d(sub + 1))) return rc;
         }
-        CK(cudaMemcpyAsync(ctx->h_res[slot], ctx->d_res, o.total, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_res[slot], ctx->d_res[slot], o.total, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(ev[7], st));
         CK(cudaEventRecord(ctx->ev_done[slot], st));
         ctx->last_B = B;
         ctx->last_s0 = s0;
+        ctx->last_slot = slot;
     }
-    CK(cudaEventRecord(ctx->ev_call[1], st));
     if (nsub >= 2 && (rc = drain(nsub - 2))) return rc;
     if ((rc = drain(nsub - 1))) return rc;
-    CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(streams[1]));
+    CK(cudaEventRecord(ctx->ev_call[1], streams[0]));  // both streams are idle here: end of the whole call
+    CK(cudaStreamSynchronize(streams[0]));
     {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, ctx->ev_call[0], ctx->ev_call[1]) == cudaSuccess) ctx->ms[6] = t;
@@ -697,6 +744,9 @@ int lm_set_option(lm_ctx *ctx, const char *name, int64_t value) {
     if (!strcmp(name, "screen")) {
         if (value < 0 || value > 2) return fail(ctx, LM_ERR_INVALID, "option screen must be 0, 1 or 2");
         ctx->opt_screen = (int)value;
+    } else if (!strcmp(name, "streams")) {
+        if (value != 1 && value != 2) return fail(ctx, LM_ERR_INVALID, "option streams must be 1 or 2");
+        ctx->opt_streams = (int)value;
     } else if (!strcmp(name, "subbatch")) {
         if (value < 1 || value > 4096) return fail(ctx, LM_ERR_INVALID, "option subbatch must be in [1, 4096]");
         ctx->opt_subbatch = (int)value;
@@ -745,7 +795,7 @@ int64_t lm_debug_fetch(lm_ctx *ctx, int what, int64_t frame, void *dst, int64_t 
     const int64_t i = frame - ctx->last_s0;
     if (i < 0 || i >= ctx->last_B) return fail(ctx, LM_ERR_INVALID, "frame %lld is not in the last sub-batch", (long long)frame);
     cudaSetDevice(ctx->device);
-    const LmBatch &b = ctx->bt;
+    const LmBatch &b = ctx->last_slot ? ctx->bt1 : ctx->bt;
     const void *src = nullptr;
     int64_t bytes = 0;
     int32_t d[4] = {0, 0, 0, 0};

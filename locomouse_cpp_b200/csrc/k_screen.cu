@@ -519,6 +519,11 @@ static inline void split_digits(int v, int *hi8, int *lo8) {
     *hi8 = (v - *lo8) / 256;
 }
 
+bool lm_screen_quantize(const float *w, int kh, int kw, float init, LmScreenHost *out) {
+    std::vector<int> vq;
+    return screen_quantize(w, kh * kw, init, &vq, out);
+}
+
 bool lm_screen_build(const float *w, int kh, int kw, float init, int halo_x, int halo_y, int fma_mode, LmScreenHost *out,
                      std::vector<int8_t> *img) {
     (void)fma_mode;
@@ -637,7 +642,7 @@ int lm_launch_screen(const LmBatch &b, cudaStream_t s) {
         }
     if (!P.njobs) return 0;
     // CTAs are dealt to the jobs in proportion to their MMA work (one persistent CTA per SM)
-    {
+    if (b.scr.enabled == 1) {
         int left = n_sm, cta = 0;
         double wleft = total;
         for (int q = 0; q < P.njobs; ++q) {

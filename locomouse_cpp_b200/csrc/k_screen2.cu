@@ -24,7 +24,7 @@ namespace {
 constexpr int S2_THREADS = 224;   // warps 0-3 epilogue, 4-5 loaders, 6 MMA issuer / TMEM owner
 constexpr int S2_TILE_M = 128;
 constexpr int S2_TILE_X = 32;
-constexpr int S2_STAGES = 4;
+constexpr int S2_STAGES = 4;      // maximum ring depth; a job uses J.j.stages of them
 constexpr int S2_TMEM_COLS = 256; // two accumulators of up to 128 columns
 
 struct Screen2JobDev {
@@ -36,7 +36,7 @@ struct Screen2JobDev {
 };
 
 struct Screen2Params {
-    Screen2JobDev job[4];
+    Screen2JobDev job[6];
     int njobs;
     int B;
     const uint8_t *win[2];
@@ -60,7 +60,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
     const Screen2JobDev &J = P.job[ji];
     const int prank = pair - J.pair_begin;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int KH = J.j.KH, ks = J.j.ks, rows = J.j.rows, nhalf = J.j.nhalf;
+    const int KH = J.j.KH, ks = J.j.ks, rows = J.j.rows, nhalf = J.j.nhalf, nst = J.j.stages;
     const int npanel = 2 * ks;
     const uint32_t panel_a = (uint32_t)rows * 16u;
     const uint32_t stage_bytes = panel_a * npanel;
@@ -146,7 +146,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive_cluster(a_full(stage), 0);  // the leader's barrier counts both CTAs' loaders
-            if (++stage == S2_STAGES) {
+            if (++stage == nst) {
                 stage = 0;
                 phase ^= 1u;
             }
@@ -185,7 +185,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
                     umma_commit_2cta(d_full(acc));
                 }
                 __syncwarp();
-                if (++stage == S2_STAGES) {
+                if (++stage == nst) {
                     stage = 0;
                     phase ^= 1u;
                 }
@@ -302,8 +302,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
 
 }  // namespace
 
-size_t lm_screen2_smem_bytes(int KH, int ks, int rows, int nhalf) {
-    return (size_t)KH * 2 * ks * nhalf * 16 + (size_t)S2_STAGES * 2 * ks * rows * 16;
+size_t lm_screen2_smem_bytes(int KH, int ks, int rows, int nhalf, int stages) {
+    return (size_t)KH * 2 * ks * nhalf * 16 + (size_t)stages * 2 * ks * rows * 16;
 }
 
 // Launches k_screen2 for the four pair-level jobs; the caller has zeroed the task counters.
@@ -318,9 +318,9 @@ int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s) {
     const int npairs_total = n_sm / 2;
     Screen2Params P{};
     size_t smem = 0;
-    double work[4], total = 0.0;
+    double work[6], total = 0.0;
     for (int v = 0; v < 2; ++v)
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < 3; ++q) {
             const LmScreen2Job &sj = b.scr.job2[v][q];
             if (!sj.Bimg[0]) continue;  // no tail box
             Screen2JobDev &J = P.job[P.njobs];
@@ -335,7 +335,7 @@ int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s) {
             // per-instruction cost ~ max(93, 42 + N/2) cycles (tools/umma_sw_probe.cu)
             work[P.njobs] = (double)J.nxt * J.nytp * sj.KH * sj.ks * (sj.nhalf >= 64 ? 106.0 : 93.0);
             total += work[P.njobs];
-            smem = std::max(smem, lm_screen2_smem_bytes(sj.KH, sj.ks, sj.rows, sj.nhalf));
+            smem = std::max(smem, lm_screen2_smem_bytes(sj.KH, sj.ks, sj.rows, sj.nhalf, sj.stages));
             ++P.njobs;
         }
     if (!P.njobs) return 0;

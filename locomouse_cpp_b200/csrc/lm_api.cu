@@ -150,6 +150,150 @@ int dalloc(lm_ctx *ctx, T **p, size_t count) {
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// Builds everything the screen kernels need for the current model / geometry.  Mode 2 (CTA pairs, k_screen2) is
+// tried first when requested, then mode 1 (k_screen); if neither fits the dense kernel stays in charge.
+int prepare_screen(lm_ctx *ctx, LmBatch &b, int want, size_t B) {
+    b.scr = LmScreen{};
+    const lm_config &k = ctx->cfg;
+    const size_t smem_limit = 220 * 1024;
+    if (want <= 0 || k.bb_w > 1024 || std::max(k.bb_h_bottom, k.bb_h_side) > 512 || B > ((size_t)1 << 17)) return LM_OK;
+    const int nfeat = k.tail_w > 0 ? 3 : 2;
+    // 1. quantisation + thresholds of every template
+    for (int v = 0; v < 2; ++v)
+        for (int f = 0; f < nfeat; ++f) {
+            const LmTemplateDev &T = b.tmpl[v][f];
+            LmScreenHost &H = ctx->scr_info[v][f];
+            H = LmScreenHost{};
+            if (!lm_screen_quantize(ctx->h_tmpl[v][f].data(), T.kh, T.kw, T.init, &H)) return LM_OK;
+            H.dx = b.view[v].halo_x - T.ax;
+            H.dy = b.view[v].halo_y - T.ay;
+            if (H.dx < 0 || H.dy < 0) return LM_OK;
+        }
+    // 2a. CTA-pair jobs
+    struct Spec {
+        int f[2], ntmpl, is_tail, digit_split, KH, ks, rows, nhalf, stages;
+    };
+    Spec spec[2][3] = {};
+    std::vector<int8_t> img2[2][3][2];
+    bool have2 = want >= 2;
+    auto fit = [&](Spec &S, int v) {  // common geometry of the job's templates + the deepest ring that fits
+        S.KH = 0;
+        S.ks = 0;
+        for (int t = 0; t < S.ntmpl; ++t) {
+            const LmScreenHost &H = ctx->scr_info[v][S.f[t]];
+            S.KH = std::max(S.KH, H.dy + b.tmpl[v][S.f[t]].kh);
+            S.ks = std::max(S.ks, (31 + H.dx + b.tmpl[v][S.f[t]].kw + 31) / 32);
+        }
+        S.rows = (128 + S.KH - 1 + 7) & ~7;
+        S.nhalf = S.digit_split ? 32 : 64;
+        for (S.stages = 4; S.stages >= 2; --S.stages)
+            if (lm_screen2_smem_bytes(S.KH, S.ks, S.rows, S.nhalf, S.stages) <= smem_limit) return true;
+        return false;
+    };
+    for (int v = 0; v < 2 && have2; ++v) {
+        Spec ps{{LM_PAW, LM_SNOUT}, 2, 0, 0, 0, 0, 0, 0, 0};
+        if (fit(ps, v)) {
+            spec[v][0] = ps;
+        } else {  // one template per job, hi digits in CTA 0, lo digits in CTA 1
+            Spec p1{{LM_PAW, LM_PAW}, 1, 0, 1, 0, 0, 0, 0, 0}, s1{{LM_SNOUT, LM_SNOUT}, 1, 0, 1, 0, 0, 0, 0, 0};
+            if (!fit(p1, v) || !fit(s1, v)) have2 = false;
+            spec[v][0] = p1;
+            spec[v][2] = s1;
+        }
+        if (nfeat == 3) {
+            Spec tl{{LM_TAIL, LM_TAIL}, 1, 1, 1, 0, 0, 0, 0, 0};
+            if (!fit(tl, v)) have2 = false;
+            spec[v][1] = tl;
+        }
+        for (int q = 0; q < 3 && have2; ++q) {
+            const Spec &S = spec[v][q];
+            if (!S.ntmpl) continue;
+            for (int r = 0; r < 2 && have2; ++r) {
+                const int f = S.digit_split ? S.f[0] : S.f[r];
+                const LmScreenHost &H = ctx->scr_info[v][f];
+                LmScreenHost tmp{};
+                have2 = lm_screen_build2(ctx->h_tmpl[v][f].data(), b.tmpl[v][f].kh, b.tmpl[v][f].kw, b.tmpl[v][f].init, H.dx, H.dy, S.KH,
+                                         S.ks, S.digit_split ? r : -1, &tmp, &img2[v][q][r]);
+                if (have2 && (tmp.t_lo != H.t_lo || tmp.t_hi != H.t_hi)) have2 = false;
+            }
+        }
+    }
+    // 2b. single-CTA images
+    bool have1 = false;
+    std::vector<int8_t> img1[2][3];
+    if (!have2) {
+        have1 = true;
+        for (int v = 0; v < 2 && have1; ++v)
+            for (int f = 0; f < nfeat && have1; ++f) {
+                LmScreenHost tmp{};
+                const LmTemplateDev &T = b.tmpl[v][f];
+                have1 = lm_screen_build(ctx->h_tmpl[v][f].data(), T.kh, T.kw, T.init, b.view[v].halo_x, b.view[v].halo_y, k.fma_mode, &tmp,
+                                        &img1[v][f]);
+                if (have1) {
+                    ctx->scr_info[v][f].kh = tmp.kh;
+                    ctx->scr_info[v][f].ks = tmp.ks;
+                    ctx->scr_info[v][f].rows = tmp.rows;
+                }
+            }
+    }
+    if (!have1 && !have2) return LM_OK;
+    // 3. task lists + what k_corr_sparse needs, for both modes
+    int rc;
+    if ((rc = dalloc(ctx, &b.scr.ntasks, 8))) return rc;
+    for (int v = 0; v < 2; ++v)
+        for (int f = 0; f < nfeat; ++f) {
+            const LmScreenHost &H = ctx->scr_info[v][f];
+            LmScreenJob &J = b.scr.job[v][f];
+            J.kh = H.kh;
+            J.ks = H.ks;
+            J.dx = H.dx;
+            J.dy = H.dy;
+            J.rows = H.rows;
+            J.t_lo = H.t_lo;
+            J.t_hi = H.t_hi;
+            const int ow = (f == LM_TAIL) ? k.tail_w : k.bb_w;
+            J.task_cap = (int)std::min<size_t>((size_t)1 << 30, B * (size_t)((b.bb_h[v] + 3) / 4) * (size_t)((ow + 7) / 8));
+            if ((rc = dalloc(ctx, &J.tasks, (size_t)J.task_cap))) return rc;
+            if (have1) {
+                int8_t *dimg = nullptr;
+                if ((rc = dalloc(ctx, &dimg, img1[v][f].size()))) return rc;
+                CK(cudaMemcpy(dimg, img1[v][f].data(), img1[v][f].size(), cudaMemcpyHostToDevice));
+                J.Bimg = dimg;
+            }
+        }
+    if (have2)
+        for (int v = 0; v < 2; ++v)
+            for (int q = 0; q < 3; ++q) {
+                const Spec &S = spec[v][q];
+                if (!S.ntmpl) continue;
+                LmScreen2Job &J2 = b.scr.job2[v][q];
+                for (int r = 0; r < 2; ++r) {
+                    int8_t *dimg = nullptr;
+                    if ((rc = dalloc(ctx, &dimg, img2[v][q][r].size()))) return rc;
+                    CK(cudaMemcpy(dimg, img2[v][q][r].data(), img2[v][q][r].size(), cudaMemcpyHostToDevice));
+                    J2.Bimg[r] = dimg;
+                }
+                J2.view = v;
+                J2.is_tail = S.is_tail;
+                J2.ntmpl = S.ntmpl;
+                J2.KH = S.KH;
+                J2.ks = S.ks;
+                J2.rows = S.rows;
+                J2.nhalf = S.nhalf;
+                J2.stages = S.stages;
+                for (int t = 0; t < S.ntmpl; ++t) {
+                    const int f = S.f[t];
+                    J2.t_lo[t] = b.scr.job[v][f].t_lo;
+                    J2.t_hi[t] = b.scr.job[v][f].t_hi;
+                    J2.tasks[t] = b.scr.job[v][f].tasks;
+                    J2.task_cap[t] = b.scr.job[v][f].task_cap;
+                    J2.ntasks[t] = b.scr.ntasks + (v * 3 + f);
+                }
+            }
+    b.scr.enabled = have2 ? 2 : 1;
+    return LM_OK;
+}
+
 // derive window geometry + allocate scratch for sub-batches of Bcap frames
 int prepare(lm_ctx *ctx) {
     if (ctx->Bcap) return LM_OK;
@@ -264,111 +408,11 @@ int prepare(lm_ctx *ctx) {
         return LM_OK;
     };
     if ((rc = bind_results(b, 0))) return rc;
-    // ---- tensor-core screen (k_screen.cu): all six jobs must qualify, otherwise the dense kernel runs --------
-    b.scr = LmScreen{};
-    int want_screen = ctx->opt_screen;
-    if (const char *e = getenv("LM_SCREEN")) want_screen = atoi(e);
-    if (want_screen && k.bb_w <= 1024 && std::max(k.bb_h_bottom, k.bb_h_side) <= 512 && Bcap <= (1 << 17)) {
-        bool ok = true;
-        std::vector<int8_t> img[2][3];
-        for (int v = 0; v < 2 && ok; ++v)
-            for (int f = 0; f < 3 && ok; ++f) {
-                if (f == LM_TAIL && k.tail_w <= 0) continue;
-                const LmTemplateDev &T = b.tmpl[v][f];
-                ok = lm_screen_build(ctx->h_tmpl[v][f].data(), T.kh, T.kw, T.init, b.view[v].halo_x, b.view[v].halo_y, k.fma_mode,
-                                     &ctx->scr_info[v][f], &img[v][f]);
-            }
-        if (ok) {
-            if ((rc = dalloc(ctx, &b.scr.ntasks, 8))) return rc;
-            for (int v = 0; v < 2; ++v)
-                for (int f = 0; f < 3; ++f) {
-                    if (f == LM_TAIL && k.tail_w <= 0) continue;
-                    const LmScreenHost &H = ctx->scr_info[v][f];
-                    LmScreenJob &J = b.scr.job[v][f];
-                    int8_t *dimg = nullptr;
-                    if ((rc = dalloc(ctx, &dimg, img[v][f].size()))) return rc;
-                    CK(cudaMemcpy(dimg, img[v][f].data(), img[v][f].size(), cudaMemcpyHostToDevice));
-                    J.Bimg = dimg;
-                    J.kh = H.kh;
-                    J.ks = H.ks;
-                    J.dx = H.dx;
-                    J.dy = H.dy;
-                    J.rows = H.rows;
-                    J.t_lo = H.t_lo;
-                    J.t_hi = H.t_hi;
-                    const int ow = (f == LM_TAIL) ? k.tail_w : k.bb_w;
-                    J.task_cap = (int)std::min<size_t>((size_t)1 << 30, B * (size_t)((b.bb_h[v] + 3) / 4) * (size_t)((ow + 7) / 8));
-                    if ((rc = dalloc(ctx, &J.tasks, (size_t)J.task_cap))) return rc;
-                }
-            b.scr.enabled = 1;
-            // ---- CTA-pair variant (k_screen2): per view a paw + snout job and a tail job in a common geometry ------
-            if (want_screen >= 2) {
-                bool ok2 = true;
-                std::vector<int8_t> img2[2][2][2];  // [view][job][cta rank]
-                int KHs[2][2], kss[2][2];
-                for (int v = 0; v < 2 && ok2; ++v) {
-                    auto dxy = [&](int f, int *dx, int *dy) {
-                        *dx = b.view[v].halo_x - b.tmpl[v][f].ax;
-                        *dy = b.view[v].halo_y - b.tmpl[v][f].ay;
-                    };
-                    for (int q = 0; q < 2 && ok2; ++q) {
-                        const int f0 = q == 0 ? LM_PAW : LM_TAIL, f1 = q == 0 ? LM_SNOUT : LM_TAIL;
-                        if (q == 1 && k.tail_w <= 0) continue;
-                        int KH = 0, ksx = 0;
-                        for (int f : {f0, f1}) {
-                            int dx, dy;
-                            dxy(f, &dx, &dy);
-                            KH = std::max(KH, dy + b.tmpl[v][f].kh);
-                            ksx = std::max(ksx, (31 + dx + b.tmpl[v][f].kw + 31) / 32);
-                        }
-                        const int rows = (128 + KH - 1 + 7) & ~7, nhalf = q == 0 ? 64 : 32;
-                        if (lm_screen2_smem_bytes(KH, ksx, rows, nhalf) > 220 * 1024) ok2 = false;
-                        KHs[v][q] = KH;
-                        kss[v][q] = ksx;
-                        for (int r = 0; r < 2 && ok2; ++r) {
-                            const int f = r == 0 ? f0 : f1;
-                            int dx, dy;
-                            dxy(f, &dx, &dy);
-                            LmScreenHost H{};
-                            ok2 = lm_screen_build2(ctx->h_tmpl[v][f].data(), b.tmpl[v][f].kh, b.tmpl[v][f].kw, b.tmpl[v][f].init, dx, dy, KH,
-                                                   ksx, q == 0 ? -1 : r, &H, &img2[v][q][r]);
-                            // same quantisation as the single-CTA build -> same thresholds
-                            if (ok2 && (H.t_lo != ctx->scr_info[v][f].t_lo || H.t_hi != ctx->scr_info[v][f].t_hi)) ok2 = false;
-                        }
-                    }
-                }
-                if (ok2) {
-                    for (int v = 0; v < 2; ++v)
-                        for (int q = 0; q < 2; ++q) {
-                            LmScreen2Job &J2 = b.scr.job2[v][q];
-                            J2 = LmScreen2Job{};
-                            if (q == 1 && k.tail_w <= 0) continue;
-                            for (int r = 0; r < 2; ++r) {
-                                int8_t *dimg = nullptr;
-                                if ((rc = dalloc(ctx, &dimg, img2[v][q][r].size()))) return rc;
-                                CK(cudaMemcpy(dimg, img2[v][q][r].data(), img2[v][q][r].size(), cudaMemcpyHostToDevice));
-                                J2.Bimg[r] = dimg;
-                            }
-                            J2.view = v;
-                            J2.is_tail = q;
-                            J2.ntmpl = q == 0 ? 2 : 1;
-                            J2.KH = KHs[v][q];
-                            J2.ks = kss[v][q];
-                            J2.rows = (128 + J2.KH - 1 + 7) & ~7;
-                            J2.nhalf = q == 0 ? 64 : 32;
-                            for (int t = 0; t < J2.ntmpl; ++t) {
-                                const int f = q == 0 ? t : LM_TAIL;
-                                J2.t_lo[t] = b.scr.job[v][f].t_lo;
-                                J2.t_hi[t] = b.scr.job[v][f].t_hi;
-                                J2.tasks[t] = b.scr.job[v][f].tasks;
-                                J2.task_cap[t] = b.scr.job[v][f].task_cap;
-                                J2.ntasks[t] = b.scr.ntasks + (v * 3 + f);
-                            }
-                        }
-                    b.scr.enabled = 2;
-                }
-            }
-        }
+    // ---- tensor-core screen: operand images, thresholds, task lists (falls back to the dense kernel) ----------
+    {
+        int want_screen = ctx->opt_screen;
+        if (const char *e = getenv("LM_SCREEN")) want_screen = atoi(e);
+        if ((rc = prepare_screen(ctx, b, want_screen, B))) return rc;
     }
     // ---- scratch set 1: same geometry and operands, its own mutable buffers ------------------------------------
     {
@@ -393,10 +437,10 @@ int prepare(lm_ctx *ctx) {
                 for (int f = 0; f < 3; ++f)
                     if (b.scr.job[v][f].tasks && (rc = dalloc(ctx, &c.scr.job[v][f].tasks, (size_t)b.scr.job[v][f].task_cap))) return rc;
             for (int v = 0; v < 2; ++v)
-                for (int q = 0; q < 2; ++q) {
+                for (int q = 0; q < 3; ++q) {
                     LmScreen2Job &J2 = c.scr.job2[v][q];
                     for (int t = 0; t < J2.ntmpl; ++t) {
-                        const int f = q == 0 ? t : LM_TAIL;
+                        const int f = (int)(b.scr.job2[v][q].ntasks[t] - b.scr.ntasks) - v * 3;  // the template this slot decides
                         J2.tasks[t] = c.scr.job[v][f].tasks;
                         J2.ntasks[t] = c.scr.ntasks + (v * 3 + f);
                     }

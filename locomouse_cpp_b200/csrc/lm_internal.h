@@ -61,6 +61,7 @@ struct LmScreen2Job {
     const int8_t *Bimg[2];  // device, per CTA rank: [KH][2*ks chunks][nhalf rows][16 B]
     int view, is_tail, ntmpl;
     int KH, ks, rows, nhalf;
+    int stages;             // window-tile ring depth that fits next to the resident B operand (2..4)
     long long t_lo[2], t_hi[2];   // per template decided by this job (paw, snout | tail)
     uint32_t *tasks[2];
     int task_cap[2];
@@ -69,7 +70,7 @@ struct LmScreen2Job {
 struct LmScreen {
     int enabled;          // 0: dense exact kernel, 1: k_screen (one CTA per tile), 2: k_screen2 (CTA pairs)
     LmScreenJob job[2][3];
-    LmScreen2Job job2[2][2];  // [view][0 = paw + snout, 1 = tail]
+    LmScreen2Job job2[2][3];  // [view][0 = paw + snout (or paw alone), 1 = tail, 2 = snout alone]; unused: Bimg[0] == null
     int *ntasks;          // device, [6] = [view][feat]
 };
 
@@ -141,7 +142,9 @@ size_t lm_screen_smem_bytes(int kh, int ks, int rows, int stages);
 // 0 = hi only (32 rows), 1 = lo only (32 rows).  Thresholds / scale / eps as lm_screen_build.
 bool lm_screen_build2(const float *w, int kh, int kw, float init, int dx, int dy, int KH, int ks, int digits,
                       LmScreenHost *out, std::vector<int8_t> *img);
-size_t lm_screen2_smem_bytes(int KH, int ks, int rows, int nhalf);
+size_t lm_screen2_smem_bytes(int KH, int ks, int rows, int nhalf, int stages);
+// thresholds / scale / eps of one template (no image); false for non-finite weights
+bool lm_screen_quantize(const float *w, int kh, int kw, float init, LmScreenHost *out);
 int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s);
 
 // pick the padded kernel-row width the correlation kernel is instantiated for (>= kw), or -1

@@ -102,11 +102,27 @@ def test_screen_dense_threshold_and_degenerate_templates(oracle):
     assert diff_results(pair, ref) == []
 
 
-def test_screen_falls_back_to_dense_for_large_templates(oracle):
-    """Templates whose Toeplitz operand does not fit in shared memory (here 40x40) run the dense exact kernel;
-    the option stays a no-op for results."""
+def test_screen_large_templates_digit_split_and_dense_fallback(oracle):
+    """40x40 templates: one template's Toeplitz operand no longer fits next to another's, so the CTA-pair kernel
+    runs one template per job (hi digits in CTA 0, lo digits in CTA 1) while the single-CTA screen falls back to
+    the dense kernel.  64x64 templates fit neither: every mode runs the dense exact kernel.  Results never change."""
     shapes = (((40, 40), (40, 40), (40, 40)), ((40, 40), (40, 40), (40, 40)))
     ((pair, a2), (on, a1), (off, a0)), (cfg, model, bkg, calib, frames, bx, bs, bb) = _run_both(synth.SynthSpec(tshapes=shapes), 2, 1000)
+    assert a2 == 2.0 and a1 == 0.0 and a0 == 0.0
+    ref = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=8)
+    assert diff_results(pair, ref) == [] and diff_results(on, ref) == []
+    shapes = (((64, 64), (64, 64), (64, 64)), ((64, 64), (64, 64), (64, 64)))
+    ((pair, a2), (on, a1), (off, a0)), (cfg, model, bkg, calib, frames, bx, bs, bb) = _run_both(synth.SynthSpec(tshapes=shapes), 2, 1000)
     assert a2 == 0.0 and a1 == 0.0 and a0 == 0.0
+    assert diff_results(pair, off) == []
+
+
+def test_screen_config5_upsampled_60x60(oracle):
+    """SURVEY config 5 (800x3400 frames, 60x60 templates, boxes 800 x 470 / 300): the pair kernel runs three
+    digit-split jobs per view with a two-stage window ring and two y-tile pairs; bit-exact vs dense and oracle."""
+    spec = synth.SynthSpec(scale=2, det_cap=8192, cand_cap=128, match_cap=512)
+    ((pair, a2), (on, a1), (off, a0)), (cfg, model, bkg, calib, frames, bx, bs, bb) = _run_both(spec, 2, 1000, allow_overflow=True)
+    assert a2 == 2.0 and a0 == 0.0
+    assert diff_results(pair, off) == []
     ref = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=8)
     assert diff_results(pair, ref) == []

@@ -57,7 +57,7 @@ class ClockSampler(threading.Thread):
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
 
-    def __init__(self, index: int, period=0.1):
+    def __init__(self, index: int, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.power = [], set(), []

@@ -11,9 +11,14 @@
  * the only executable piece of the reference stack available in this image — OpenCV 4.13 through
  * python `cv2` — primitive by primitive (tests/test_oracle_vs_cv2.py): filter2D, normalize,
  * subtract, threshold, LUT, flip, connectedComponentsWithStats, moments; plus hand-derived
- * known-answer tests for the reference's own loops (nmsMax, peakClustering, matchViews).  The
- * reference's own control flow has no independent executable check: "parity unpinned" in the
- * sense of SURVEY.md §8c for those loops.
+ * known-answer tests for the reference's own loops (nmsMax, peakClustering, matchViews).
+ * nmsMax, peakClustering and the Candidate / P22D classes use OpenCV for value types only, so the
+ * reference's OWN source lines for them are compiled from /root/reference against a value-type shim
+ * (oracle/ref_shim, `make -C oracle ref` -> oracle/_ref/libref_nms.so) and the oracle is checked
+ * against that code bit for bit (tests/test_oracle_vs_reference.py, golden vectors in
+ * tests/golden/reference_nms.npz).  The remaining loops (matchViews, tail segmentation, readFrame)
+ * call OpenCV algorithms and have no independent executable check: "parity unpinned" in the sense of
+ * SURVEY.md §8c for those, pinned primitive by primitive against cv2.
  */
 #ifndef LM_ORACLE_H
 #define LM_ORACLE_H

@@ -1,0 +1,68 @@
+"""ctypes wrapper of oracle/_ref/libref_nms.so: the REFERENCE's own nmsMax / peakClustering / Candidate / P22D code
+(LocoMouse_class.cpp:1610-1905, Candidates/Candidates.cpp) compiled by `make -C oracle ref` against the value-type
+shim in oracle/ref_shim.  TEST INFRASTRUCTURE ONLY (tests/ and the golden-vector generator)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libref_nms.so")
+REF_ROOT = "/root/reference"
+CAND = np.dtype([("x", "<i4"), ("y", "<i4"), ("s", "<f8")])
+_lib = None
+
+
+def available(build: bool = True) -> bool:
+    """True when the library exists (it is built here, where /root/reference is mounted, and travels to the GPU box)."""
+    if not os.path.exists(LIB_PATH) and build and os.path.isdir(REF_ROOT):
+        subprocess.run(["make", "-C", _HERE, "ref"], capture_output=True)
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/libref_nms.so is missing and /root/reference is not mounted")
+        L = C.CDLL(LIB_PATH)
+        f32p = C.POINTER(C.c_float)
+        L.ref_nms_max.restype = C.c_int
+        L.ref_nms_max.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int]
+        L.ref_peak_clustering.restype = C.c_int
+        L.ref_peak_clustering.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int]
+        L.ref_p22d.restype = C.c_int
+        L.ref_p22d.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_default_candidate.restype = C.c_int
+        L.ref_default_candidate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _run(fn, scores, box_w, box_h, *extra, cap=4096):
+    s = np.ascontiguousarray(scores, np.float32)
+    out = np.zeros(cap, CAND)
+    n = fn(s.ctypes.data_as(C.POINTER(C.c_float)), s.shape[0], s.shape[1], box_w, box_h, *extra, out.ctypes.data, cap)
+    assert 0 <= n <= cap
+    return out[:n]
+
+
+def nms_max(scores, box_w, box_h, overlap=0.5):
+    return _run(lib().ref_nms_max, scores, box_w, box_h, C.c_double(overlap))
+
+
+def peak_clustering(scores, box_w, box_h, overlap=0.5, method=3):
+    return _run(lib().ref_peak_clustering, scores, box_w, box_h, method, C.c_double(overlap))
+
+
+def p22d(xb, yb, sb, side):
+    """side: list of (y, score).  Returns (number_of_candidates, [(y, s), ...]) of the reference's P22D."""
+    ys = np.array([y for y, _ in side], np.int32)
+    ss = np.array([s for _, s in side], np.float64)
+    oy = np.zeros(max(len(side), 1), np.int32)
+    os_ = np.zeros(max(len(side), 1), np.float64)
+    n = lib().ref_p22d(xb, yb, float(sb), len(side), ys.ctypes.data, ss.ctypes.data, oy.ctypes.data, os_.ctypes.data, len(oy))
+    return n, list(zip(oy[:n].tolist(), os_[:n].tolist()))

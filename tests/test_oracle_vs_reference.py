@@ -1,0 +1,88 @@
+"""Pins the oracle's nmsMax / peakClustering restatement (and the host C++ Candidate / P22D mirror's contract)
+against the REFERENCE'S OWN CODE: LocoMouse_class.cpp:1610-1905 and Candidates/Candidates.cpp compiled from
+/root/reference by `make -C oracle ref` (value-type shim only, oracle/ref_shim).  The committed golden file
+tests/golden/reference_nms.npz was produced by that library (tests/golden/make_reference_golden.py), so the pin
+also holds where the reference is not mounted; where the library exists, fresh random maps are compared too."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import reference_nms as ref
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_nms.npz")
+
+
+def _same(a, b):
+    """a: the oracle's list of (x, y, score); b: structured array from the reference.  Scores bit for bit."""
+    a = np.array(a, dtype=ref.CAND) if len(a) else np.zeros(0, ref.CAND)
+    b = np.asarray(b)
+    return len(a) == len(b) and np.array_equal(a["x"], b["x"]) and np.array_equal(a["y"], b["y"]) and np.array_equal(
+        np.ascontiguousarray(a["s"]).view(np.uint64), np.ascontiguousarray(b["s"]).view(np.uint64))
+
+
+def _cases():
+    z = np.load(GOLD)
+    names = sorted({k.rsplit("_", 1)[0] for k in z.files})
+    return z, names
+
+
+def test_oracle_matches_reference_golden(oracle):
+    z, names = _cases()
+    assert len(names) >= 10
+    total = 0
+    for n in names:
+        s, (bw, bh) = z[f"{n}_scores"], z[f"{n}_box"]
+        got_n = oracle.nms_max(s, int(bw), int(bh))
+        got_p = oracle.peak_clustering(s, int(bw), int(bh))
+        assert _same(got_n, z[f"{n}_nmsmax"]), f"nmsMax differs from the reference on {n}"
+        assert _same(got_p, z[f"{n}_peak"]), f"peakClustering differs from the reference on {n}"
+        total += len(got_n) + len(got_p)
+    assert total > 500
+    # the chain case separates the two suppression rules
+    assert len(z["chain_nmsmax"]) == 1 and len(z["chain_peak"]) == 2
+    # the half-way case separates the two rounding rules: x = 4.5 -> 4 (half-even) vs 5 (half-away)
+    assert z["halfway_nmsmax"]["x"].tolist() != z["halfway_peak"]["x"].tolist() or z["halfway_nmsmax"]["y"].tolist() != z[
+        "halfway_peak"]["y"].tolist()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libref_nms.so not built (reference not mounted)")
+def test_golden_file_is_what_the_reference_code_produces():
+    z, names = _cases()
+    for n in names:
+        s, (bw, bh) = z[f"{n}_scores"], z[f"{n}_box"]
+        assert _same(ref.nms_max(s, int(bw), int(bh)), z[f"{n}_nmsmax"])
+        assert _same(ref.peak_clustering(s, int(bw), int(bh)), z[f"{n}_peak"])
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libref_nms.so not built (reference not mounted)")
+def test_oracle_matches_reference_on_fresh_maps(oracle):
+    rng = np.random.Generator(np.random.PCG64(20261018))
+    for it in range(40):
+        rows, cols = int(rng.integers(8, 90)), int(rng.integers(8, 130))
+        bw, bh = int(rng.integers(2, 31)), int(rng.integers(2, 31))
+        s = rng.normal(0, 1, (rows, cols)).astype(np.float32)
+        yy, xx = np.mgrid[0:rows, 0:cols]
+        for _ in range(int(rng.integers(0, 5))):
+            cy, cx, sg = rng.uniform(0, rows), rng.uniform(0, cols), rng.uniform(1.5, 7)
+            s += (rng.uniform(1, 4) * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * sg * sg))).astype(np.float32)
+        s = (s - np.quantile(s, rng.uniform(0.5, 0.99))).astype(np.float32)
+        s += np.arange(s.size, dtype=np.float32).reshape(s.shape) * np.float32(1e-7)
+        if len(np.unique(s[s > 0])) != int((s > 0).sum()):
+            continue  # std::sort is unstable on ties; the oracle's total order is only defined without them
+        assert _same(oracle.nms_max(s, bw, bh), ref.nms_max(s, bw, bh)), f"nmsMax, map {it}"
+        assert _same(oracle.peak_clustering(s, bw, bh), ref.peak_clustering(s, bw, bh)), f"peakClustering, map {it}"
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libref_nms.so not built (reference not mounted)")
+def test_reference_p22d_contract():
+    """The record semantics the C ABI's match arrays encode (include/locomouse_b200.h) and the host mirror
+    (locomouse_cpp_b200/host/Candidates.cpp, test_candidates.cpp) reproduce, observed on the reference's own class."""
+    assert ref.p22d(10, 20, 0.9, []) == (0, [])                               # sentinel: no side match
+    assert ref.p22d(10, 20, 0.9, [(33, 0.25)]) == (1, [(33, 0.25)])
+    assert ref.p22d(10, 20, 0.9, [(33, 0.25), (44, 0.0)]) == (2, [(33, 0.25), (44, 0.0)])
+    n, _ = ref.p22d(1, 1, 1.0, [(9, -0.1)])                                    # negative first score keeps it "empty"
+    assert n == 0
+    x, y, s = (np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.float64))
+    code = ref.lib().ref_default_candidate(x.ctypes.data, y.ctypes.data, s.ctypes.data)
+    assert (int(x[0]), int(y[0]), float(s[0])) == (-1, -1, -1.0) and code == -1

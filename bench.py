@@ -164,6 +164,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    numa_bound = sharding.bind_to_gpu_numa_node(local) if world > 1 else False  # before any pinned allocation
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -348,7 +349,7 @@ def main():
             d2h = sum(getattr(r, a).nbytes for a in r.ARRAYS)
             e2e = {"value": world * n * args.steps / ew, "unit": UNIT,
                    "h2d_bytes_per_step": int(n * cfg.vid_rows * cfg.vid_cols + 3 * 4 * n), "d2h_bytes_per_step": int(d2h),
-                   "ms_per_step": ew / args.steps * 1e3,
+                   "ms_per_step": ew / args.steps * 1e3, "numa_bound": bool(numa_bound),
                    "note": "frames in pinned host memory, copied H2D inside the call (overlapped with compute per 256-frame "
                            "sub-batch); results copied D2H" + ("; candidate lists gathered to rank 0 over NCCL" if world > 1 else "")}
         except Exception as ex:  # pragma: no cover

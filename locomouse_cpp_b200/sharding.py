@@ -119,14 +119,29 @@ def concat(parts) -> Results:
 
 
 def gather_to_rank0(res: Results, device=None):
-    """Gather every rank's Results on rank 0 (list in rank order; None elsewhere).  Variable-size
-    uint8 payloads: sizes travel with all_gather, payloads with gather (NCCL) / gather (gloo)."""
+    """Gather every rank's Results on rank 0 (list in rank order; None elsewhere).
+
+    Equal frame counts on all ranks (the usual case): every rank's contiguous result buffer (Results.raw, fixed size)
+    moves with ONE collective and rank 0 adopts the received buffers as Results views -- no per-entry host work.
+    Ragged counts: compact payloads (pack / unpack), sizes exchanged first."""
     import torch
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(), dist.get_rank()
-    payload = torch.from_numpy(pack(res).copy())
     dev = torch.device(device) if device is not None else torch.device("cpu")
+    meta = torch.tensor([res.n, res.cand_cap, res.match_cap, res.n_tail_points], dtype=torch.int64, device=dev)
+    metas = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    metas = [tuple(int(v) for v in m.tolist()) for m in metas]
+    if all(m == metas[0] for m in metas):
+        send = torch.from_numpy(res.raw).to(dev, non_blocking=True)
+        recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+        dist.gather(send, recv, dst=0)
+        if rank != 0:
+            return None
+        n, cap, mcap, ntp = metas[0]
+        return [Results(n, cap, mcap, ntp, buffer=r.cpu().numpy()) for r in recv]
+    payload = torch.from_numpy(pack(res).copy())
     size = torch.tensor([payload.numel()], dtype=torch.int64, device=dev)
     sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(sizes, size)
@@ -139,3 +154,27 @@ def gather_to_rank0(res: Results, device=None):
     if rank != 0:
         return None
     return [unpack(r[:s].cpu().numpy()) for r, s in zip(recv, sizes)]
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> bool:
+    """Pin this process to the CPUs that are local to its GPU (NVML's CPU affinity) so that pinned host buffers are
+    first-touched on the GPU's own NUMA node: H2D copies of all ranks then scale instead of crossing the socket
+    interconnect.  Returns False (and changes nothing) when NVML or the affinity call is unavailable."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False

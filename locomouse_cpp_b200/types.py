@@ -124,21 +124,40 @@ class Model:
 class Results:
     """Host result buffers for n frames (struct-of-arrays, see lm_results in the header)."""
 
-    def __init__(self, n: int, cand_cap: int, match_cap: int, n_tail_points: int = 15):
+    def __init__(self, n: int, cand_cap: int, match_cap: int, n_tail_points: int = 15, buffer: np.ndarray | None = None):
+        """All arrays are views of ONE contiguous byte buffer (self.raw), so a whole result set moves with a single
+        copy / collective.  `buffer` adopts an existing buffer of exactly raw_nbytes(...) bytes (e.g. a gathered one)."""
         self.n = int(n)
         self.cand_cap = int(cand_cap)
         self.match_cap = int(match_cap)
         self.n_tail_points = int(n_tail_points)
-        n = max(self.n, 1)
-        self.n_bottom = np.zeros((n, 2), np.int32)
-        self.n_side = np.zeros((n, 2), np.int32)
-        self.bottom = np.zeros((n, 2, cand_cap), CAND_DTYPE)
-        self.side = np.zeros((n, 2, cand_cap), CAND_DTYPE)
-        self.match_n = np.zeros((n, 2, cand_cap), np.int32)
-        self.match_y = np.zeros((n, 2, match_cap), np.int32)
-        self.match_s = np.zeros((n, 2, match_cap), np.float64)
-        self.tail = np.zeros((n, 3, n_tail_points), np.int32)
-        self.flags = np.zeros((n,), np.uint32)
+        layout, total = self._layout(max(self.n, 1), self.cand_cap, self.match_cap, self.n_tail_points)
+        if buffer is None:
+            buffer = np.zeros(total, np.uint8)
+        else:
+            buffer = np.ascontiguousarray(buffer, dtype=np.uint8).reshape(-1)
+            if buffer.size != total:
+                raise ValueError(f"result buffer has {buffer.size} bytes, {total} expected")
+        self.raw = buffer
+        for name, (off, dtype, shape) in layout.items():
+            nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            setattr(self, name, buffer[off:off + nbytes].view(dtype).reshape(shape))
+
+    @staticmethod
+    def _layout(n, cand_cap, match_cap, n_tail_points):
+        spec = (("n_bottom", np.int32, (n, 2)), ("n_side", np.int32, (n, 2)), ("bottom", CAND_DTYPE, (n, 2, cand_cap)),
+                ("side", CAND_DTYPE, (n, 2, cand_cap)), ("match_n", np.int32, (n, 2, cand_cap)),
+                ("match_y", np.int32, (n, 2, match_cap)), ("match_s", np.float64, (n, 2, match_cap)),
+                ("tail", np.int32, (n, 3, n_tail_points)), ("flags", np.uint32, (n,)))
+        layout, off = {}, 0
+        for name, dtype, shape in spec:
+            layout[name] = (off, dtype, shape)
+            off += (int(np.prod(shape)) * np.dtype(dtype).itemsize + 15) & ~15
+        return layout, off
+
+    @staticmethod
+    def raw_nbytes(n, cand_cap, match_cap, n_tail_points=15) -> int:
+        return Results._layout(max(int(n), 1), cand_cap, match_cap, n_tail_points)[1]
 
     ARRAYS = ("n_bottom", "n_side", "bottom", "side", "match_n", "match_y", "match_s", "tail", "flags")
 

@@ -175,6 +175,13 @@ int lm_last_timing(const lm_ctx *ctx, float ms[7], int64_t *launches);
 int64_t lm_debug_fetch(lm_ctx *ctx, int what, int64_t frame, void *dst, int64_t dst_bytes,
                        int32_t dims[4]);
 
+/* Runs the candidate-extraction kernels of the configured geometry on a caller-supplied score map (host, float32,
+ * [bb_h of the view][bb_w]): view == LM_BOTTOM -> nmsMax (LocoMouse_class.cpp:1610-1747), view == LM_SIDE ->
+ * peakClustering (1749-1905); the suppression box is the template size of (view, feat), feat in {LM_PAW, LM_SNOUT};
+ * no tail mask.  out receives cand_cap records; returns the number of candidates or a negative lm_status.  Used to
+ * check the kernels directly against the reference's own code (tests/test_gpu_nms_reference.py). */
+int lm_debug_nms(lm_ctx *ctx, int view, int feat, const float *scores, lm_cand *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,7 @@ _lib = None
 
 EXPORTS = ("lm_abi_version", "lm_create", "lm_destroy", "lm_last_error", "lm_configure", "lm_set_model",
            "lm_set_background", "lm_set_calibration", "lm_get_geometry", "lm_detect_batch", "lm_last_timing",
-           "lm_debug_fetch", "lm_set_option", "lm_get_info")
+           "lm_debug_fetch", "lm_set_option", "lm_get_info", "lm_debug_nms")
 
 
 class OverflowError_(RuntimeError):
@@ -67,6 +67,8 @@ def load_library():
     L.lm_set_option.argtypes = [vp, C.c_char_p, i64]
     L.lm_get_info.restype = C.c_int
     L.lm_get_info.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double)]
+    L.lm_debug_nms.restype = C.c_int
+    L.lm_debug_nms.argtypes = [vp, i32, i32, vp, vp]
     L.lm_debug_fetch.restype = i64
     L.lm_debug_fetch.argtypes = [vp, i32, i64, vp, i64, vp]
     _lib = L
@@ -168,6 +170,20 @@ class Detector:
         if rc != 0:
             raise ValueError(f"unknown info item {name!r}")
         return float(v.value)
+
+    def debug_nms(self, view: int, feat: int, scores):
+        """nmsMax (view 0) / peakClustering (view 1) kernels on a given score map -> list of (x, y, score)."""
+        from .types import CAND_DTYPE
+
+        h = self.cfg.bb_h_bottom if view == 0 else self.cfg.bb_h_side
+        s = np.ascontiguousarray(scores, dtype=np.float32)
+        if s.shape != (h, self.cfg.bb_w):
+            raise ValueError(f"score map must be {(h, self.cfg.bb_w)}, got {s.shape}")
+        out = np.zeros(self.cfg.cand_cap, CAND_DTYPE)
+        n = self._L.lm_debug_nms(self._ctx, int(view), int(feat), s.ctypes.data, out.ctypes.data)
+        if n < 0:
+            self._check(n)
+        return out[:n]
 
     def last_timing(self):
         ms = np.zeros(7, np.float32)

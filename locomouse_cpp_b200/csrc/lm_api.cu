@@ -827,6 +827,53 @@ int lm_get_info(const lm_ctx *ctx, const char *name, double *value) {
     return LM_ERR_INVALID;
 }
 
+int lm_debug_nms(lm_ctx *ctx, int view, int feat, const float *scores, lm_cand *out) {
+    if (!ctx) return LM_ERR_INVALID;
+    if (!ctx->configured || !ctx->model_set) return fail(ctx, LM_ERR_STATE, "lm_debug_nms needs lm_configure and lm_set_model first");
+    if (view < 0 || view > 1 || feat < 0 || feat > 1 || !scores || !out) return fail(ctx, LM_ERR_INVALID, "lm_debug_nms: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    int rc = prepare(ctx);
+    if (rc) return rc;
+    LmBatch b = ctx->bt;
+    b.B = 1;
+    const lm_config &k = ctx->cfg;
+    const int bw = k.bb_w, bh = b.bb_h[view];
+    std::vector<LmDet> det;
+    for (int y = 0; y < bh; ++y)
+        for (int x = 0; x < bw; ++x) {
+            const float v = scores[(size_t)y * bw + x];
+            if (v > 0.f) det.push_back(LmDet{(uint32_t)(y * bw + x), v});
+        }
+    if ((int)det.size() > k.det_cap) return fail(ctx, LM_ERR_OVERFLOW, "lm_debug_nms: %zu positives exceed det_cap", det.size());
+    cudaStream_t st = ctx->stream;
+    CK(cudaStreamSynchronize(st));
+    const int list = (0 * 2 + feat) * 2 + view;
+    int32_t counts[4] = {0, 0, 0, 0};
+    counts[list] = (int32_t)det.size();
+    if (view == LM_SIDE) {
+        // peakClustering only runs for a feature whose bottom list is non-empty (class.cpp:820, 828): give it one detection
+        const int blist = (0 * 2 + feat) * 2 + LM_BOTTOM;
+        const LmDet one{0u, 1.0f};
+        counts[blist] = 1;
+        CK(cudaMemcpyAsync(b.det + (size_t)blist * k.det_cap, &one, sizeof one, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(b.det_count, counts, sizeof counts, cudaMemcpyHostToDevice, st));
+    if (!det.empty())
+        CK(cudaMemcpyAsync(b.det + (size_t)list * k.det_cap, det.data(), det.size() * sizeof(LmDet), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(b.tailmask, 0, (size_t)b.bb_h[LM_BOTTOM] * b.tail_pitch, st));
+    CK(cudaMemsetAsync(b.flags, 0, 4, st));
+    if (lm_launch_nms(b, st) < 0) return fail(ctx, LM_ERR_RUNTIME, "nms launch failed");
+    int32_t n = 0;
+    uint32_t flags = 0;
+    const lm_cand *src = (view == LM_BOTTOM ? b.bottom : b.side) + (size_t)feat * k.cand_cap;
+    CK(cudaMemcpyAsync(&n, (view == LM_BOTTOM ? b.n_bottom : b.n_side) + feat, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&flags, b.flags, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out, src, (size_t)k.cand_cap * sizeof(lm_cand), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (flags) return fail(ctx, LM_ERR_OVERFLOW, "lm_debug_nms: list overflow (flags %u)", flags);
+    return n;
+}
+
 int lm_last_timing(const lm_ctx *ctx, float ms[7], int64_t *launches) {
     if (!ctx) return LM_ERR_INVALID;
     if (ms) memcpy(ms, ctx->ms, sizeof ctx->ms);

@@ -299,6 +299,19 @@ def main():
                     "peak_source": f"nominal 148 SM x 128 FMA/clk x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 entry)",
                     "traffic": traffic_of("k_corr"), "launch_ms": corr_ms_per_launch, "flop_per_launch": flop_per_launch,
                     "share_of_step": stage["corr"] / max(stage["total"], 1e-9)}
+    # whole-path view of the north_star roofline ("the slower of HBM bytes at peak bandwidth and FMAs at peak"):
+    flop_frame = 2.0 * fma_frame
+    hbm_fps = float(peaks.get("hbm_gbs", 6650.0)) * 1e9 / (cfg.vid_rows * cfg.vid_cols)
+    fma_fps = fp32_nominal * 1e12 / flop_frame
+    tensor_fps = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))) * 1e12 / flop_frame
+    per_gpu = value / world
+    roofline["whole_path"] = {
+        "frames_per_s_per_gpu": per_gpu,
+        "bounds_frames_per_s": {"hbm": hbm_fps, "fp32_fma": fma_fps, "bf16_tensor": tensor_fps},
+        "frac_of_north_star_roofline": per_gpu / min(hbm_fps, fma_fps),
+        "frac_of_tensor_roofline": per_gpu / min(hbm_fps, tensor_fps),
+        "note": "north_star roofline = min(HBM bytes at measured bandwidth, correlation FMAs at the FP32 FMA peak); the path exceeds "
+                "it because the FMAs run as an exact int8 screen on the tensor cores"}
     roofline["peak_measured_ffma_microbench"] = (ffma_measured or {}).get("ffma_reg_tflops")
     roofline["hbm"] = {"kernel": "k_minmax", "achieved": (n * args.steps * 680000.0 / 1e9) / max(stage["minmax"] * 1e-3, 1e-12),
                        "peak": peaks.get("hbm_gbs"), "unit": "GB/s",

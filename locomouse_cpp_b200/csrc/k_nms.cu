@@ -314,11 +314,10 @@ int lm_launch_nms(const LmBatch &b, cudaStream_t s) {
     // Two size classes: lists of up to SMALL positives run with a small shared-memory footprint (several
     // CTAs per SM); the rare longer lists run in a second launch sized for det_cap (its other CTAs exit at once).
     const int SMALL = 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static LmDevOnce once;
+    if (once.first()) {
         cudaFuncSetAttribute(k_nms_bottom, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_nms_side, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        attr_done = true;
     }
     int launches = 0;
     const int Ps = P < SMALL ? P : SMALL;

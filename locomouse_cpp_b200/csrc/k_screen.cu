@@ -590,13 +590,7 @@ bool lm_screen_build2(const float *w, int kh, int kw, float init, int dx, int dy
 }
 
 int lm_launch_screen(const LmBatch &b, cudaStream_t s) {
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
-    }
+    const int n_sm = lm_sm_count();
     ScreenParams P{};
     SparseParams Q{};
     size_t smem = 0;
@@ -671,10 +665,9 @@ int lm_launch_screen(const LmBatch &b, cudaStream_t s) {
     Q.det_count = b.det_count;
 
     if (cudaMemsetAsync(b.scr.ntasks, 0, 6 * sizeof(int), s) != cudaSuccess) return -1;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static LmDevOnce once;
+    if (once.first()) {
         if (cudaFuncSetAttribute(k_screen, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) return -1;
-        attr_done = true;
     }
     if (b.scr.enabled == 2) {
         if (lm_launch_screen2_kernel(b, s) < 0) return -1;

@@ -308,13 +308,7 @@ size_t lm_screen2_smem_bytes(int KH, int ks, int rows, int nhalf, int stages) {
 
 // Launches k_screen2 for the four pair-level jobs; the caller has zeroed the task counters.
 int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s) {
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
-    }
+    const int n_sm = lm_sm_count();
     const int npairs_total = n_sm / 2;
     Screen2Params P{};
     size_t smem = 0;
@@ -362,10 +356,9 @@ int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s) {
         P.tailbin_stride[v] = (int64_t)b.bb_h[v] * b.tail_pitch;
     }
     P.tail_pitch = b.tail_pitch;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static LmDevOnce once;
+    if (once.first()) {
         if (cudaFuncSetAttribute(k_screen2, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) return -1;
-        attr_done = true;
     }
     const int pairs = P.job[P.njobs - 1].pair_begin + P.job[P.njobs - 1].npair;
     k_screen2<<<2 * pairs, S2_THREADS, smem, s>>>(P);

@@ -491,10 +491,9 @@ size_t tail_smem(const LmBatch &b) {
 int lm_launch_tail(const LmBatch &b, cudaStream_t s) {
     if (b.tail_w <= 0) return 0;
     const size_t smem = tail_smem(b);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static LmDevOnce once;
+    if (once.first()) {
         cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
     }
     int *need_slow = b.cc_flag;
     int runcap = RUNCAP;  // LM_TAIL_RUNCAP lowers the threshold (tests use it to exercise the slow path)

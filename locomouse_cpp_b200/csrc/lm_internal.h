@@ -152,6 +152,25 @@ int lm_corr_kwp(int kw);
 // dynamic shared memory the correlation kernel needs for a view/template (for capability checks)
 size_t lm_corr_smem_bytes(const LmBatch &b, int view, int feat);
 
+// Per-device one-time state of the launchers (function attributes are per device; a process may own several contexts).
+struct LmDevOnce {
+    bool done[64] = {};
+    bool first(void) {  // true exactly once per current device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+inline int lm_sm_count() {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+}
+
 #define LM_CUDA_CHECK(x)                                                            \
     do {                                                                            \
         cudaError_t _e = (x);                                                       \

@@ -160,6 +160,31 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device,
 int lm_set_option(lm_ctx *ctx, const char *name, int64_t value);
 int lm_get_info(const lm_ctx *ctx, const char *name, double *value);
 
+/* pass 1 -------------------------------------------------------------------------- *
+ * LocoMouse_TM_DE::computeBoundingBox / computeMouseBox_DE (LocoMouse_TM_DE.cpp:8-113): per frame, the base-class
+ * readFrame (no imadjust(0, 0.6)), imadjust_default on the side view (LocoMouse_class.cpp:3244-3311), zeroed border
+ * bands, threshold, column sums, firstLastOverT (LocoMouse_class.hpp:411-442) and
+ *     bb_x = min(side_w - 1, last * width_margin).
+ * The whole-video smoothing that follows (vecmovingaverage, LocoMouse_class.cpp:1559-1608) is sequential host work:
+ * lm_moving_average below.  Defaults = LocoMouse_TM_DE.hpp:27-29 and LocoMouse_TM_DE.cpp:68-71. */
+typedef struct {
+    int32_t side_x, side_y, side_w, side_h;   /* BB_SIDE_VIEW (calibration file view_boxes row 0)             */
+    int32_t zero_col_pre, zero_col_post;      /* columns [0, pre) and [post, n_cols) of the side view -> 0: 46, 760 */
+    int32_t zero_row_pre, zero_row_post;      /* rows    [0, pre) and [post, side_h) -> 0: 100, 149               */
+    double threshold;                         /* SIDE_THRESHOLD = 255 * 0.05                                        */
+    int32_t min_count;                        /* MIN_PIXEL_COUNT = 10 (column sum >= min_count)                     */
+    double width_margin;                      /* WIDTH_MARGIN = 1.1                                                 */
+} lm_bb_de_params;
+
+/* frames: n raw frames (host or device memory, as lm_detect_batch).  bb_x_raw[n] receives the per-frame, unsmoothed
+ * box position (double, may be -width_margin when no column qualifies); lims[n][2] (optional, may be NULL) the
+ * first / last qualifying columns (-1, -1 when none; the reference leaves last = 0 when exactly one column qualifies).
+ * Needs lm_configure, lm_set_background and lm_set_calibration; the model is not used. */
+int lm_bounding_box_tm_de(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, int64_t n,
+                          const lm_bb_de_params *p, double *bb_x_raw, int32_t *lims);
+/* vecmovingaverage (LocoMouse_class.cpp:1559-1608): central moving average, partial windows copied, (uint32_t) casts */
+int lm_moving_average(const double *v, int64_t n, int32_t window, uint32_t *out);
+
 /* measurement / debugging ---------------------------------------------------------------- */
 /* Device time (ms, CUDA events on the library's own stream) of the stages of the last
  * lm_detect_batch call, summed over its sub-batches:

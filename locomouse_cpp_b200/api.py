@@ -25,7 +25,7 @@ _lib = None
 
 EXPORTS = ("lm_abi_version", "lm_create", "lm_destroy", "lm_last_error", "lm_configure", "lm_set_model",
            "lm_set_background", "lm_set_calibration", "lm_get_geometry", "lm_detect_batch", "lm_last_timing",
-           "lm_debug_fetch", "lm_set_option", "lm_get_info", "lm_debug_nms")
+           "lm_debug_fetch", "lm_set_option", "lm_get_info", "lm_debug_nms", "lm_bounding_box_tm_de", "lm_moving_average")
 
 
 class OverflowError_(RuntimeError):
@@ -67,6 +67,10 @@ def load_library():
     L.lm_set_option.argtypes = [vp, C.c_char_p, i64]
     L.lm_get_info.restype = C.c_int
     L.lm_get_info.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double)]
+    L.lm_bounding_box_tm_de.restype = C.c_int
+    L.lm_bounding_box_tm_de.argtypes = [vp, vp, i32, i64, vp, vp, vp]
+    L.lm_moving_average.restype = C.c_int
+    L.lm_moving_average.argtypes = [vp, i64, i32, vp]
     L.lm_debug_nms.restype = C.c_int
     L.lm_debug_nms.argtypes = [vp, i32, i32, vp, vp]
     L.lm_debug_fetch.restype = i64
@@ -170,6 +174,21 @@ class Detector:
         if rc != 0:
             raise ValueError(f"unknown info item {name!r}")
         return float(v.value)
+
+    def bounding_box_tm_de(self, frames, params=None, window: int = 5):
+        """Pass 1 of LocoMouse_TM_DE (LocoMouse_TM_DE.cpp:8-113) for all frames: returns (BB_X_POS uint32[n] after the
+        moving average, raw bb_x float64[n], lims int32[n, 2])."""
+        from .types import bb_de_params
+
+        ptr, n, on_dev, keep = _frames_ptr(frames, self.cfg, self.device)
+        p = params if params is not None else bb_de_params(self.cfg)
+        raw = np.zeros(n, np.float64)
+        lims = np.zeros((n, 2), np.int32)
+        self._check(self._L.lm_bounding_box_tm_de(self._ctx, ptr, int(on_dev), n, C.addressof(p), raw.ctypes.data, lims.ctypes.data))
+        out = np.zeros(n, np.uint32)
+        if n:
+            self._check(self._L.lm_moving_average(raw.ctypes.data, n, int(window), out.ctypes.data))
+        return out, raw, lims
 
     def debug_nms(self, view: int, feat: int, scores):
         """nmsMax (view 0) / peakClustering (view 1) kernels on a given score map -> list of (x, y, score)."""

@@ -55,6 +55,15 @@ struct lm_ctx {
     float ms_screen = 0.f;            // k_screen alone, summed over the sub-batches of the last call
     float ms[7] = {};
     int64_t launches = 0;
+    // pass-1 scratch (lm_bounding_box_tm_de): independent of the model, allocated on first use
+    struct BBScratch {
+        int cap = 0;
+        int32_t *minmax = nullptr;
+        uint8_t *lut = nullptr, *pred = nullptr, *stage = nullptr;
+        uint32_t *hist = nullptr;
+        double *bbx = nullptr;
+        int32_t *lims = nullptr;
+    } bbs;
     int last_B = 0;                   // size of the last sub-batch (for lm_debug_fetch)
     int last_slot = 0;
     int64_t last_s0 = 0;
@@ -127,6 +136,14 @@ bool roi_ok(const lm_ctx *c, uint32_t bbx, uint32_t bbys, uint32_t bbyb) {
 }
 
 void free_scratch(lm_ctx *c) {
+    cudaFree(c->bbs.minmax);
+    cudaFree(c->bbs.lut);
+    cudaFree(c->bbs.pred);
+    cudaFree(c->bbs.stage);
+    cudaFree(c->bbs.hist);
+    cudaFree(c->bbs.bbx);
+    cudaFree(c->bbs.lims);
+    c->bbs = lm_ctx::BBScratch{};
     for (void *p : c->dev_allocs) cudaFree(p);
     c->dev_allocs.clear();
     for (int s = 0; s < 2; ++s) {
@@ -825,6 +842,91 @@ int lm_get_info(const lm_ctx *ctx, const char *name, double *value) {
         return LM_OK;
     }
     return LM_ERR_INVALID;
+}
+
+int lm_bounding_box_tm_de(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, int64_t n, const lm_bb_de_params *p,
+                          double *bb_x_raw, int32_t *lims) {
+    if (!ctx) return LM_ERR_INVALID;
+    if (!ctx->configured || !ctx->bkg_set || !ctx->calib_set)
+        return fail(ctx, LM_ERR_STATE, "lm_bounding_box_tm_de needs lm_configure, lm_set_background and lm_set_calibration first");
+    if (n < 0) return fail(ctx, LM_ERR_INVALID, "negative frame count");
+    if (n == 0) return LM_OK;
+    if (!frames || !p || !bb_x_raw) return fail(ctx, LM_ERR_INVALID, "null argument");
+    const lm_config &k = ctx->cfg;
+    if (p->side_x < 0 || p->side_y < 0 || p->side_w <= 0 || p->side_h <= 0 || p->side_x + p->side_w > k.n_cols ||
+        p->side_y + p->side_h > k.n_rows)
+        return fail(ctx, LM_ERR_INVALID, "side view box (%d, %d, %d x %d) leaves the calibrated image", p->side_x, p->side_y, p->side_w,
+                    p->side_h);
+    if ((int64_t)p->side_w * p->side_h >= (1 << 24))
+        return fail(ctx, LM_ERR_INVALID, "side view too large for the float histogram scan of imadjust_default");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t fsz = (int64_t)k.vid_rows * k.vid_cols;
+    lm_ctx::BBScratch &S = ctx->bbs;
+    const int cap = 256;
+    if (!S.cap) {
+        CK(cudaMalloc((void **)&S.minmax, (size_t)(cap + 1) * 2 * sizeof(int32_t)));
+        CK(cudaMalloc((void **)&S.lut, (size_t)(cap + 1) * 256));
+        CK(cudaMalloc((void **)&S.pred, (size_t)cap * 256));
+        CK(cudaMalloc((void **)&S.hist, (size_t)cap * 256 * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&S.bbx, (size_t)cap * sizeof(double)));
+        CK(cudaMalloc((void **)&S.lims, (size_t)cap * 2 * sizeof(int32_t)));
+        S.cap = cap;
+    }
+    if (!frames_on_device && !S.stage) CK(cudaMalloc((void **)&S.stage, (size_t)cap * fsz));
+    cudaStream_t st = ctx->stream;
+    std::vector<int32_t> hl((size_t)cap * 2);
+    for (int64_t s0 = 0; s0 < n; s0 += cap) {
+        const int B = (int)std::min<int64_t>(cap, n - s0);
+        LmBatch b{};
+        b.B = B;
+        b.frame_bytes = fsz;
+        b.prev = nullptr;
+        b.bkg = ctx->d_bkg;
+        b.calib = ctx->d_calib;
+        b.n_rows = k.n_rows;
+        b.n_cols = k.n_cols;
+        b.vid_rows = k.vid_rows;
+        b.vid_cols = k.vid_cols;
+        b.flip = k.flip;
+        b.imadjust = 0;  // LocoMouse::readFrame(I), not LocoMouse_TM::readFrame (LocoMouse_TM_DE.cpp:36)
+        b.minmax = S.minmax;
+        b.lut = S.lut;
+        if (frames_on_device) {
+            b.frames = frames + s0 * fsz;
+        } else {
+            CK(cudaMemcpyAsync(S.stage, frames + s0 * fsz, (size_t)B * fsz, cudaMemcpyHostToDevice, st));
+            b.frames = S.stage;
+        }
+        const int nl = lm_launch_bbox_tm_de(b, *p, S.hist, S.pred, S.bbx, S.lims, st);
+        if (nl < 0) return fail(ctx, LM_ERR_RUNTIME, "bounding-box launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        CK(cudaMemcpyAsync(bb_x_raw + s0, S.bbx, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hl.data(), S.lims, (size_t)B * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (lims) memcpy(lims + s0 * 2, hl.data(), (size_t)B * 2 * sizeof(int32_t));
+    }
+    return LM_OK;
+}
+
+// vecmovingaverage (LocoMouse_class.cpp:1559-1608).  (uint32_t)double of a negative value is undefined in C++; like
+// the reference built for x86-64 this converts through int64 and keeps the low 32 bits.
+int lm_moving_average(const double *v, int64_t n, int32_t window, uint32_t *out) {
+    if (!v || !out || n < 0 || window <= 0) return LM_ERR_INVALID;
+    auto u32 = [](double x) { return (uint32_t)(int64_t)x; };
+    if ((int64_t)window >= n) {
+        for (int64_t i = 0; i < n; ++i) out[i] = u32(v[i]);
+        return LM_OK;
+    }
+    const int half = window / 2;
+    double cur = 0;
+    for (int i = 0; i < half; ++i) out[i] = u32(v[i]);
+    for (int i = 0; i < window; ++i) cur += v[i];
+    out[half] = u32(std::floor(cur / window));
+    for (int64_t i = 0; i < n - window; ++i) {
+        cur = cur - v[i] + v[i + window];
+        out[half + 1 + i] = u32(std::floor(cur / window));
+    }
+    for (int64_t i = n - half - 1; i < n; ++i) out[i] = u32(v[i]);
+    return LM_OK;
 }
 
 int lm_debug_nms(lm_ctx *ctx, int view, int feat, const float *scores, lm_cand *out) {

@@ -123,6 +123,8 @@ int lm_launch_corr(const LmBatch &b, cudaStream_t s);
 int lm_launch_tail(const LmBatch &b, cudaStream_t s);
 int lm_launch_nms(const LmBatch &b, cudaStream_t s);
 int lm_launch_pair(const LmBatch &b, cudaStream_t s);
+int lm_launch_bbox_tm_de(const LmBatch &b, const lm_bb_de_params &p, uint32_t *hist, uint8_t *pred, double *bb_x, int32_t *lims,
+                         cudaStream_t s);
 
 // tensor-core screen + sparse exact re-evaluation (k_screen.cu); returns kernels launched or -1
 int lm_launch_screen(const LmBatch &b, cudaStream_t s);

@@ -57,6 +57,21 @@ class lm_results(C.Structure):
     ]
 
 
+class lm_bb_de_params(C.Structure):
+    _fields_ = [("side_x", C.c_int32), ("side_y", C.c_int32), ("side_w", C.c_int32), ("side_h", C.c_int32),
+                ("zero_col_pre", C.c_int32), ("zero_col_post", C.c_int32), ("zero_row_pre", C.c_int32), ("zero_row_post", C.c_int32),
+                ("threshold", C.c_double), ("min_count", C.c_int32), ("width_margin", C.c_double)]
+
+
+def bb_de_params(cfg, side_h: int = 165, **kw) -> lm_bb_de_params:
+    """LocoMouse_TM_DE defaults (LocoMouse_TM_DE.hpp:27-29, LocoMouse_TM_DE.cpp:68-71) for a side view that spans the
+    upper `side_h` rows of the calibrated image."""
+    d = dict(side_x=0, side_y=0, side_w=cfg.n_cols, side_h=side_h, zero_col_pre=46, zero_col_post=760, zero_row_pre=100,
+             zero_row_post=149, threshold=255 * 0.05, min_count=10, width_margin=1.1)
+    d.update(kw)
+    return lm_bb_de_params(**d)
+
+
 TemplateArray = (lm_template * 3) * 2  # t[view][feature]
 
 

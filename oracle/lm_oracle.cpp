@@ -723,6 +723,130 @@ void detect_frame(const lm_config &c, const lm_template t[2][3], const Geom &g, 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Pass 1, LocoMouse_TM_DE: LocoMouse_TM_DE.cpp:8-113.
+// ---------------------------------------------------------------------------------------------
+// imadjust_default (class.cpp:3244-3311): histogram -> first bin whose normalised cumulative count is > 0.01
+// (imin) / >= 0.99 (imax), all in float as in the reference; ranges = index / 255 (float); then the in-place
+// cv::MatExpr  Iout = (Iout - r0) / (r1 - r0)  which OpenCV evaluates as ONE convertTo(CV_8U, alpha, beta) with
+// alpha = 1 / (double)(r1 - r0) and beta = -(double)r0 * alpha (MatOp_AddEx::multiply), i.e. per pixel
+// saturate_cast<uchar>(fmaf(src, (float)alpha, (float)beta)) -- unless alpha == 1, where MatOp_AddEx::assign takes
+// the cv::add(src, -0) branch and the image is unchanged.  (Pinned against cv2.calcHist / cv2.convertScaleAbs.)
+void imadjust_default_lut(const uint32_t *hist, uint8_t *lut, int32_t *imin_imax) {
+    const float min_tol = 0.01f, max_tol = 0.99f;
+    float sum_histf = 0.f;
+    {
+        double acc = 0.0;  // cv::sum accumulates in double, the result is narrowed to float (class.cpp:3260-3261)
+        for (int i = 0; i < 256; ++i) acc += (double)(float)hist[i];
+        sum_histf = (float)acc;
+    }
+    float cumsum_step = 0.f;
+    int indices[2] = {0, 0}, imin = 0, imax = 0;
+    bool check_min = true, check_max = true;
+    for (int i = 0; i < 256; ++i) {
+        cumsum_step += (float)hist[i];
+        const float cn = cumsum_step / sum_histf;
+        if ((cn > min_tol) & check_min) {
+            indices[0] = i;
+            check_min = false;
+            imin = i;
+        }
+        if ((cn >= max_tol) & check_max) {
+            indices[1] = i;
+            check_max = false;
+            imax = i;
+        }
+        if (!(check_min || check_max)) break;
+    }
+    if (imin == imax) indices[1] = 256;
+    const float r0 = (float)indices[0] / 255.f, r1 = (float)indices[1] / 255.f;
+    const double s = (double)(r1 - r0);
+    const double alpha = 1.0 / s, beta = -(double)r0 * alpha;
+    if (imin_imax) {
+        imin_imax[0] = indices[0];
+        imin_imax[1] = indices[1];
+    }
+    if (std::fabs(alpha) == 1.0) {
+        for (int v = 0; v < 256; ++v) lut[v] = (uint8_t)v;
+        return;
+    }
+    const float a = (float)alpha, b = (float)beta;
+    for (int v = 0; v < 256; ++v) lut[v] = sat_u8_rint(__builtin_fmaf((float)v, a, b));
+}
+
+// firstLastOverT<int> (class.hpp:411-442): the first qualifying index goes to slot 0, every later one to slot 1;
+// with exactly one qualifying column slot 1 keeps its initial 0; none -> (-1, -1).
+void first_last_over_t(const float *p, uint32_t L, int th, int32_t *first_last) {
+    bool has_first = false;
+    first_last[0] = 0;
+    first_last[1] = 0;
+    int index = 0;
+    for (uint32_t i = 0; i < L; ++i)
+        if (p[i] >= (float)th) {
+            first_last[index] = (int32_t)i;
+            if (!has_first) {
+                index = 1;
+                has_first = true;
+            }
+        }
+    if (!has_first) first_last[0] = first_last[1] = -1;
+}
+
+// (uint32_t)double as x86-64 compilers evaluate it for the values that occur here (the conversion of a negative
+// double is undefined behaviour in C++; cvttsd2si to 64 bits, low 32 bits kept).
+inline uint32_t u32_from_double(double v) { return (uint32_t)(int64_t)v; }
+
+// vecmovingaverage (class.cpp:1559-1608)
+void vecmovingaverage(const double *v, int64_t n, int window, uint32_t *out) {
+    if ((int64_t)window >= n) {
+        for (int64_t i = 0; i < n; ++i) out[i] = u32_from_double(v[i]);
+        return;
+    }
+    double current_sum = 0;
+    const int half = window / 2;
+    for (int i = 0; i < half; ++i) out[i] = u32_from_double(v[i]);
+    for (int i = 0; i < window; ++i) current_sum += v[i];
+    out[half] = u32_from_double(std::floor(current_sum / window));
+    for (int64_t i = 0; i < n - window; ++i) {
+        current_sum = current_sum - v[i] + v[i + window];
+        out[half + 1 + i] = u32_from_double(std::floor(current_sum / window));
+    }
+    for (int64_t i = n - half - 1; i < n; ++i) out[i] = u32_from_double(v[i]);
+}
+
+// computeMouseBox_DE (LocoMouse_TM_DE.cpp:56-113) on the calibrated image of the BASE readFrame
+void bounding_box_tm_de_frame(const lm_config &c, const uint8_t *bkg, const int32_t *calib, const uint8_t *frame,
+                              const lm_bb_de_params &p, std::vector<uint8_t> &I, double *bb_x, int32_t *lims) {
+    lm_config base = c;
+    base.imadjust = 0;  // LocoMouse::readFrame(I), not LocoMouse_TM::readFrame (LocoMouse_TM_DE.cpp:36)
+    preprocess(base, bkg, calib, frame, I.data(), nullptr);
+    uint32_t hist[256] = {0};
+    for (int r = 0; r < p.side_h; ++r) {
+        const uint8_t *row = I.data() + (int64_t)(p.side_y + r) * c.n_cols + p.side_x;
+        for (int x = 0; x < p.side_w; ++x) ++hist[row[x]];
+    }
+    uint8_t lut[256];
+    imadjust_default_lut(hist, lut, nullptr);
+    std::vector<float> colsum(p.side_w, 0.f);
+    // colRange(0, pre) / colRange(post, N_COLS) / rowRange(0, pre) / rowRange(post, rows) set to zero (68-71),
+    // threshold(> SIDE_THRESHOLD -> 1) (75), reduce(SUM over rows, CV_32F) (91)
+    const int c0 = std::max(0, p.zero_col_pre), c1 = std::min(p.side_w, p.zero_col_post);
+    const int r0 = std::max(0, p.zero_row_pre), r1 = std::min(p.side_h, p.zero_row_post);
+    for (int r = r0; r < r1; ++r) {
+        const uint8_t *row = I.data() + (int64_t)(p.side_y + r) * c.n_cols + p.side_x;
+        for (int x = c0; x < c1; ++x)
+            if ((double)lut[row[x]] > p.threshold) colsum[x] += 1.f;
+    }
+    int32_t fl[2];
+    first_last_over_t(colsum.data(), (uint32_t)p.side_w, p.min_count, fl);
+    if (lims) {
+        lims[0] = fl[0];
+        lims[1] = fl[1];
+    }
+    *bb_x = std::min((double)(p.side_w - 1), (double)fl[1] * p.width_margin);
+}
+
 int validate(const lm_config *c, const lm_template t[2][3]) {
     if (!c || !t) return LM_ERR_INVALID;
     if (c->vid_rows <= 0 || c->vid_cols <= 0 || c->n_rows <= 0 || c->n_cols <= 0) return LM_ERR_INVALID;
@@ -739,6 +863,22 @@ int validate(const lm_config *c, const lm_template t[2][3]) {
 }  // namespace
 
 extern "C" {
+
+int lmo_bounding_box_tm_de(const lm_config *cfg, const uint8_t *bkg, const int32_t *calib, const uint8_t *frames, int64_t n,
+                           const lm_bb_de_params *p, double *bb_x, int32_t *lims) {
+    if (!cfg || !bkg || !calib || !frames || !p || !bb_x || n < 0) return LM_ERR_INVALID;
+    if (p->side_x < 0 || p->side_y < 0 || p->side_w <= 0 || p->side_h <= 0 || p->side_x + p->side_w > cfg->n_cols ||
+        p->side_y + p->side_h > cfg->n_rows)
+        return LM_ERR_INVALID;
+    std::vector<uint8_t> I((size_t)cfg->n_rows * cfg->n_cols);
+    const int64_t fsz = (int64_t)cfg->vid_rows * cfg->vid_cols;
+    for (int64_t f = 0; f < n; ++f)
+        bounding_box_tm_de_frame(*cfg, bkg, calib, frames + f * fsz, *p, I, bb_x + f, lims ? lims + 2 * f : nullptr);
+    return LM_OK;
+}
+void lmo_imadjust_default_lut(const uint32_t *hist, uint8_t *lut, int32_t *imin_imax) { imadjust_default_lut(hist, lut, imin_imax); }
+void lmo_first_last_over_t(const float *values, uint32_t L, int32_t th, int32_t *first_last) { first_last_over_t(values, L, th, first_last); }
+void lmo_vecmovingaverage(const double *v, int64_t n, int32_t window, uint32_t *out) { vecmovingaverage(v, n, window, out); }
 
 int lmo_geometry(const lm_config *cfg, const lm_template t[2][3], int32_t pads[8], int32_t canvas[4]) {
     if (validate(cfg, t)) return LM_ERR_INVALID;

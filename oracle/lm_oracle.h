@@ -74,6 +74,17 @@ int lmo_match_views(const lm_cand *cb, int32_t nb, const lm_cand *cs, int32_t ns
                     int32_t y0s, int32_t *match_n, int32_t *match_y, double *match_s, int32_t match_cap,
                     int32_t *n_match);
 
+/* ---- pass 1, LocoMouse_TM_DE -------------------------------------------------------- */
+/* computeMouseBox_DE per frame (LocoMouse_TM_DE.cpp:56-113 after the base readFrame): bb_x[n], lims[n][2] (optional) */
+int lmo_bounding_box_tm_de(const lm_config *cfg, const uint8_t *bkg, const int32_t *calib, const uint8_t *frames,
+                           int64_t n, const lm_bb_de_params *p, double *bb_x, int32_t *lims);
+/* imadjust_default's mapping for a given 256-bin histogram (LocoMouse_class.cpp:3244-3311): lut[256], {imin, imax} */
+void lmo_imadjust_default_lut(const uint32_t *hist, uint8_t *lut, int32_t *imin_imax);
+/* firstLastOverT<int> (LocoMouse_class.hpp:411-442) on float column sums */
+void lmo_first_last_over_t(const float *values, uint32_t L, int32_t th, int32_t *first_last);
+/* vecmovingaverage (LocoMouse_class.cpp:1559-1608) */
+void lmo_vecmovingaverage(const double *v, int64_t n, int32_t window, uint32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

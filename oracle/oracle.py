@@ -201,3 +201,47 @@ def match_views(cb, cs, vel_check, tsize_b, tsize_s, T, I=None, Iprev=None, x0=0
         out.append([(int(my[o + j]), float(ms[o + j])) for j in range(m)])
         o += m
     return out
+
+
+# ---- pass 1, LocoMouse_TM_DE ------------------------------------------------------------------------
+def bounding_box_tm_de(cfg: Config, bkg, calib, frames, params, window: int = 5):
+    """(BB_X_POS uint32[n], raw bb_x float64[n], lims int32[n, 2]) as LocoMouse_TM_DE::computeBoundingBox produces them."""
+    L = lib()
+    frames = _u8(frames)
+    n = frames.shape[0]
+    c = cfg.to_c()
+    raw = np.zeros(n, np.float64)
+    lims = np.zeros((n, 2), np.int32)
+    L.lmo_bounding_box_tm_de.restype = C.c_int
+    rc = L.lmo_bounding_box_tm_de(C.byref(c), _p(_u8(bkg), _u8p), _p(np.ascontiguousarray(calib, np.int32), _i32p), _p(frames, _u8p),
+                                  C.c_int64(n), C.byref(params), raw.ctypes.data_as(_f64p), lims.ctypes.data_as(_i32p))
+    if rc != 0:
+        raise ValueError(f"lmo_bounding_box_tm_de failed ({rc})")
+    out = np.zeros(n, np.uint32)
+    L.lmo_vecmovingaverage(raw.ctypes.data_as(_f64p), C.c_int64(n), C.c_int32(window), out.ctypes.data_as(_u32p))
+    return out, raw, lims
+
+
+def imadjust_default_lut(hist):
+    L = lib()
+    h = np.ascontiguousarray(hist, np.uint32)
+    lut = np.zeros(256, np.uint8)
+    mm = np.zeros(2, np.int32)
+    L.lmo_imadjust_default_lut(h.ctypes.data_as(_u32p), lut.ctypes.data_as(_u8p), mm.ctypes.data_as(_i32p))
+    return lut, (int(mm[0]), int(mm[1]))
+
+
+def first_last_over_t(values, th: int):
+    L = lib()
+    v = np.ascontiguousarray(values, np.float32)
+    fl = np.zeros(2, np.int32)
+    L.lmo_first_last_over_t(v.ctypes.data_as(_f32p), C.c_uint32(v.size), C.c_int32(th), fl.ctypes.data_as(_i32p))
+    return int(fl[0]), int(fl[1])
+
+
+def vecmovingaverage(v, window: int):
+    L = lib()
+    a = np.ascontiguousarray(v, np.float64)
+    out = np.zeros(a.size, np.uint32)
+    L.lmo_vecmovingaverage(a.ctypes.data_as(_f64p), C.c_int64(a.size), C.c_int32(window), out.ctypes.data_as(_u32p))
+    return out

@@ -333,6 +333,26 @@ def main():
         except Exception as ex:  # pragma: no cover
             roofline["dense_exact_kernel"] = {"error": repr(ex)}
 
+    # ---- pass 1 of LocoMouse_TM_DE on the same resident frames (HBM-bound; not part of `value`) --------
+    pass1 = None
+    if rank == 0:
+        try:
+            from locomouse_cpp_b200.types import bb_de_params
+
+            pp = bb_de_params(cfg, side_h=spec.side_h)
+            det.bounding_box_tm_de(frames, pp)
+            t1 = time.perf_counter()
+            reps = 2
+            for _ in range(reps):
+                det.bounding_box_tm_de(frames, pp)
+            dt1 = (time.perf_counter() - t1) / reps
+            pass1 = {"frames_per_s": n / dt1, "ms_per_10k_frames": dt1 * 1e3 * 10000 / n,
+                     "hbm_gbs_algorithmic": n * cfg.vid_rows * cfg.vid_cols / dt1 / 1e9,
+                     "note": "lm_bounding_box_tm_de (k_minmax + k_lut + k_bb_hist + k_bb_pred + k_bb_cols) + host moving average; "
+                             "algorithmic bytes = one read of every raw frame"}
+        except Exception as ex:  # pragma: no cover
+            pass1 = {"error": repr(ex)}
+
     # ---- e2e: host (pinned) buffers, H2D + D2H inside the timed region -------------------------------------
     e2e = None
     host = None
@@ -403,7 +423,7 @@ def main():
                            "note": "value/wall/device_event: two-stream overlapped pipeline; stage_ms_per_step_serial and the roofline "
                                    "launch times: the same steps with the library option streams=1 (kernels strictly serial)"},
                 "clocks": sampler.summary(), "gpu_launches": int(launches), "overflow_frames": overflow,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "pass1_tm_de": pass1}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

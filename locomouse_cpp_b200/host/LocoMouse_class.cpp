@@ -96,6 +96,7 @@ LocoMouse_Parameters::LocoMouse_Parameters(const std::string &config_file_name) 
             else if (key == "bounding_box_bottom") BB_USER_BOTTOM = parse_rect(val, key);
             else if (key == "bb_width") bb_width = std::stoi(val);
             else if (key == "bb_height_side") bb_height_side = std::stoi(val);
+            else if (key == "moving_average_window") moving_average_window = std::stoi(val);
             else if (key == "bounding_box_file") bounding_box_file = val;
             else if (key == "device") device = std::stoi(val);
             else if (key == "batch_frames") batch_frames = std::stoi(val);
@@ -118,6 +119,8 @@ LocoMouse_Parameters::LocoMouse_Parameters(const std::string &config_file_name) 
         throw std::invalid_argument("tail_sub_bounding_box must belong to [0, 1].");
     if (bb_width <= 0 || bb_height_side <= 0) throw std::invalid_argument("bb_width and bb_height_side must be positive.");
     if (batch_frames <= 0) throw std::invalid_argument("batch_frames must be positive.");
+    if (moving_average_window <= 0 || moving_average_window % 2 == 0)
+        throw std::invalid_argument("moving_average_window must be a positive odd integer.");
 }
 
 // =====================================================================================================
@@ -335,20 +338,40 @@ void LocoMouse_TM::computeBoundingBox() {
 
 LocoMouse_TM_DE::LocoMouse_TM_DE(LocoMouse_ParseInputs INPUTS) : LocoMouse_TM(INPUTS) { METHOD = 2; }
 
-// LocoMouse_TM_DE.cpp:8-53: side anchor = last row of the side view, 400-wide boxes over the full view heights.
+// LocoMouse_TM_DE.cpp:8-53: side anchor = last row of the side view, 400-wide boxes over the full view heights.  The
+// per-frame mouse position (computeMouseBox_DE, LocoMouse_TM_DE.cpp:56-113) runs on the device unless a pass-1 output
+// file is supplied; the moving average over the video follows on the host as in the reference.
 void LocoMouse_TM_DE::computeBoundingBox() {
-    std::vector<unsigned int> ys, yb;
-    read_boxes(LM_PARAMS.bounding_box_file, N_FRAMES, BB_X_POS, ys, yb);
-    std::fill(BB_Y_BOTTOM_POS.begin(), BB_Y_BOTTOM_POS.end(), N_ROWS - 1);
-    std::fill(BB_Y_SIDE_POS.begin(), BB_Y_SIDE_POS.end(), (unsigned int)BB_SIDE_VIEW.height - 1u);
     BB_SIDE_MOUSE = cv::Rect(0, 0, 400, BB_SIDE_VIEW.height);
     BB_BOTTOM_MOUSE = cv::Rect(0, 0, 400, BB_BOTTOM_VIEW.height);
+    if (!LM_PARAMS.bounding_box_file.empty()) {
+        std::vector<unsigned int> ys, yb;
+        read_boxes(LM_PARAMS.bounding_box_file, N_FRAMES, BB_X_POS, ys, yb);
+    } else {
+        configureDevice();
+        lm_bb_de_params p{};
+        p.side_x = BB_SIDE_VIEW.x;
+        p.side_y = BB_SIDE_VIEW.y;
+        p.side_w = BB_SIDE_VIEW.width;
+        p.side_h = BB_SIDE_VIEW.height;
+        p.zero_col_pre = 46;            // LocoMouse_TM_DE.cpp:68-71 ("hand-set like this for the TM")
+        p.zero_col_post = 760;
+        p.zero_row_pre = 100;
+        p.zero_row_post = 149;
+        p.threshold = 255 * 0.05;       // LocoMouse_TM_DE.hpp:27-29
+        p.min_count = 10;
+        p.width_margin = 1.1;
+        std::vector<double> bb_x(N_FRAMES);
+        check(lm_bounding_box_tm_de(CTX, VIDEO.data(), /*frames_on_device=*/0, N_FRAMES, &p, bb_x.data(), nullptr));
+        BB_X_POS.assign(N_FRAMES, 0);
+        if (lm_moving_average(bb_x.data(), N_FRAMES, LM_PARAMS.moving_average_window, BB_X_POS.data()) != LM_OK)
+            throw std::invalid_argument("moving_average_window is invalid.");
+    }
+    std::fill(BB_Y_BOTTOM_POS.begin(), BB_Y_BOTTOM_POS.end(), N_ROWS - 1);
+    std::fill(BB_Y_SIDE_POS.begin(), BB_Y_SIDE_POS.end(), (unsigned int)BB_SIDE_VIEW.height - 1u);
 }
 
-// ---- initializeFeatureLoop (LocoMouse_class.cpp:655-769): hand the per-video state to the device -------
-void LocoMouse::initializeFeatureLoop() {
-    if (BB_BOTTOM_MOUSE.width <= 0 || BB_BOTTOM_MOUSE.width != BB_SIDE_MOUSE.width)
-        throw std::invalid_argument("getBoundingBox() must run first and both views must share the box width.");
+void LocoMouse::configureDevice() {
     lm_config c{};
     c.vid_rows = VID_ROWS;
     c.vid_cols = VID_COLS;
@@ -368,6 +391,15 @@ void LocoMouse::initializeFeatureLoop() {
     c.det_cap = LM_PARAMS.det_cap;
     c.match_cap = LM_PARAMS.match_cap;
     check(lm_configure(CTX, &c));
+    check(lm_set_background(CTX, BKG.data()));
+    check(lm_set_calibration(CTX, CALIBRATION.data()));
+}
+
+// ---- initializeFeatureLoop (LocoMouse_class.cpp:655-769): hand the per-video state to the device -------
+void LocoMouse::initializeFeatureLoop() {
+    if (BB_BOTTOM_MOUSE.width <= 0 || BB_BOTTOM_MOUSE.width != BB_SIDE_MOUSE.width)
+        throw std::invalid_argument("getBoundingBox() must run first and both views must share the box width.");
+    configureDevice();
     const LocoMouse_Feature *F[3] = {&M.paw, &M.snout, &M.tail};
     lm_template t[2][3];
     for (int k = 0; k < 3; ++k) {
@@ -375,8 +407,6 @@ void LocoMouse::initializeFeatureLoop() {
         t[LM_SIDE][k] = lm_template{F[k]->w_s().data(), F[k]->size_side().height, F[k]->size_side().width, F[k]->rho_s()};
     }
     check(lm_set_model(CTX, t));
-    check(lm_set_background(CTX, BKG.data()));
-    check(lm_set_calibration(CTX, CALIBRATION.data()));
 
     CANDIDATES_BOTTOM_PAW.clear();
     CANDIDATES_BOTTOM_SNOUT.clear();

@@ -31,6 +31,7 @@ public:
     static constexpr unsigned int N_paws = 4, N_snout = 1, N_tail_points = 15;
     // TM / TM_DE (LocoMouse_TM.cpp:57-112)
     int bb_width = 400, bb_height_side = 150;
+    int moving_average_window = 5;
     // B200 path
     std::string bounding_box_file;  // pass-1 output (BB_X_POS, BB_Y_SIDE_POS, BB_Y_BOTTOM_POS), see lm_files.hpp
     int device = 0;
@@ -110,6 +111,7 @@ protected:
     void validateImageVideoSize();
     void check(int rc) const;          // lm_status -> exception
     void runChunk(unsigned int first_frame);
+    void configureDevice();            // lm_configure + background + calibration for the current box sizes
     const Batch &batchFor(int frame) const;
     virtual bool usesImadjust() const { return false; }  // LocoMouse_TM::readFrame applies imadjust(0, 0.6)
 

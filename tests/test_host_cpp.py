@@ -51,7 +51,7 @@ def test_driver_error_convention(tmp_path):
 
 
 # ---------------------------------------------------------------------------------------------------
-def write_problem_files(d, cfg, model, bkg, calib, frames, bx, bs, bb, side_h, extra_cfg=""):
+def write_problem_files(d, cfg, model, bkg, calib, frames, bx, bs, bb, side_h, extra_cfg="", with_boxes=True):
     """The raw containers of locomouse_cpp_b200/host/lm_files.hpp."""
     n, rows, cols = frames.shape
     with open(d / "video.lmv", "wb") as f:
@@ -81,7 +81,8 @@ def write_problem_files(d, cfg, model, bkg, calib, frames, bx, bs, bb, side_h, e
         f"side_bottom_min_overlap: {cfg.min_overlap!r}\n"
         f"tail_sub_bounding_box: {cfg.tail_sub_bounding_box!r}\n"
         f"bb_width: {cfg.bb_w}\nbb_height_side: {cfg.bb_h_side}\n"
-        f"bounding_box_file: {d / 'boxes.lmb'}\n"
+        + (f"bounding_box_file: {d / 'boxes.lmb'}\n" if with_boxes else "")
+        + 
         f"fma_mode: {int(cfg.fma_mode)}\ncand_cap: {cfg.cand_cap}\ndet_cap: {cfg.det_cap}\nmatch_cap: {cfg.match_cap}\n"
         + extra_cfg)
 
@@ -156,3 +157,33 @@ def test_main_sequence_matches_oracle(tmp_path, oracle, method, flip):
             assert [m for m in matches] == [w[1] for w in want]
             total += len(cb)
     assert total > 0
+
+
+@pytest.mark.gpu
+def test_tm_de_pass1_on_device_then_detection(tmp_path, oracle):
+    """LocoMouse_TM_DE with no pass-1 file: getBoundingBox() runs computeMouseBox_DE on the device
+    (lm_bounding_box_tm_de) + the host moving average; detection then uses those boxes.  Everything equals the oracle."""
+    from locomouse_cpp_b200 import synth
+    from locomouse_cpp_b200.types import bb_de_params
+
+    exe = _build_driver()
+    spec = synth.SynthSpec(method="TM_DE")
+    n = 8
+    cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(spec, n, seed=1000)
+    frames = frames.numpy()
+    want_bx, _, _ = oracle.bounding_box_tm_de(cfg, bkg, calib, frames, bb_de_params(cfg, side_h=spec.side_h), window=5)
+    ref = oracle.detect(cfg, model, bkg, calib, frames, want_bx, bs, bb, n_threads=4)
+    assert ref.rc == 0
+    write_problem_files(tmp_path, cfg, model, bkg, calib, frames, bx, bs, bb, spec.side_h, extra_cfg="batch_frames: 5\n",
+                        with_boxes=False)
+    p = subprocess.run([exe, "2", str(tmp_path / "config.yml"), str(tmp_path / "video.lmv"), str(tmp_path / "bkg.lmi"),
+                        str(tmp_path / "model.lmm"), str(tmp_path / "calib.lmc"), "R", str(tmp_path)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    out = read_output(tmp_path / "output_video.lmo")
+    assert len(out) == n
+    for f, (tail, feats) in enumerate(out):
+        assert np.array_equal(tail, ref.tail[f])
+        for feat in range(2):
+            cb, cs, matches = feats[feat]
+            assert cb == ref.candidates_bottom(f, feat) and cs == ref.candidates_side(f, feat)
+            assert matches == [w[1] for w in ref.p22d(f, feat)]

@@ -523,6 +523,12 @@ MatchBox match_box(int tw, int th) {
 //  (1069: Mat / double multiplies by the reciprocal); reductions of boolD (1144-1150); per bottom
 //  candidate the side candidates are visited in order; `colsum > 1 & vel_check` (1207, Q8).
 // ---------------------------------------------------------------------------------------------
+// Branch-coverage counters of the pairing stage (tests use them to prove that a parity input exercises the quirks):
+// 0 pairings with both lists non-empty, 1 all-equal boolD zeroed by normalize (Q7), 2 velocity comparisons (Q8),
+// 3 side candidates rejected by the velocity criterion, 4 accepted after a velocity comparison, 5 windows found moving,
+// 6 bottom candidates left without a side match, 7 side matches emitted.
+std::atomic<long long> g_cov[8];
+
 int match_views(const lm_cand *cb, int nb, const lm_cand *cs, int ns, int vel_check, int tw_b, int th_b,
                 int tw_s, int th_s, double T, const uint8_t *I, const uint8_t *Ip, int n_rows, int n_cols,
                 int x0, int y0b, int y0s, int32_t *match_n, int32_t *match_y, double *match_s, int match_cap,
@@ -549,6 +555,8 @@ int match_views(const lm_cand *cb, int nb, const lm_cand *cs, int ns, int vel_ch
                 double prod = (double)D * alpha;
                 wgt[(size_t)i * ns + j] = prod + 1.0;
             }
+        ++g_cov[0];
+        if (mx == mn && mx > 0) ++g_cov[1];
         // normalize(boolD, boolD, 0, 1, NORM_MINMAX): scale = 1/(max-min) or 0 when max == min
         for (size_t k = 0; k < (size_t)nb * ns; ++k) boolD[k] = (mx > mn) ? (boolD[k] ? 1 : 0) : 0;
         for (int i = 0; i < nb; ++i)
@@ -571,13 +579,17 @@ int match_views(const lm_cand *cb, int nb, const lm_cand *cs, int ns, int vel_ch
                         moving_b = check_vel(I, Ip, n_rows, n_cols, x0 + cb[i].x + mb.tlx, y0b + cb[i].y + mb.tly,
                                              mb.w, mb.h, tw_b * th_b, 0.02);
                         need_b = false;
+                        if (moving_b) ++g_cov[5];
                     }
                     if (need_t[j]) {
                         mov_t[j] = check_vel(I, Ip, n_rows, n_cols, x0 + cs[j].x + ms.tlx, y0s + cs[j].y + ms.tly,
                                              ms.w, ms.h, tw_s * th_s, 0.05);
                         need_t[j] = 0;
+                        if (mov_t[j]) ++g_cov[5];
                     }
                     match = (moving_b == (bool)mov_t[j]);
+                    ++g_cov[2];
+                    ++g_cov[match ? 4 : 3];
                 }
                 if (match) {
                     if (total < match_cap) {
@@ -591,6 +603,8 @@ int match_views(const lm_cand *cb, int nb, const lm_cand *cs, int ns, int vel_ch
             }
         }
         match_n[i] = cnt;
+        if (!cnt) ++g_cov[6];
+        g_cov[7] += cnt;
     }
     *n_match = total;
     return overflow;
@@ -879,6 +893,12 @@ int lmo_bounding_box_tm_de(const lm_config *cfg, const uint8_t *bkg, const int32
 void lmo_imadjust_default_lut(const uint32_t *hist, uint8_t *lut, int32_t *imin_imax) { imadjust_default_lut(hist, lut, imin_imax); }
 void lmo_first_last_over_t(const float *values, uint32_t L, int32_t th, int32_t *first_last) { first_last_over_t(values, L, th, first_last); }
 void lmo_vecmovingaverage(const double *v, int64_t n, int32_t window, uint32_t *out) { vecmovingaverage(v, n, window, out); }
+void lmo_coverage(int64_t out[8], int reset) {
+    for (int i = 0; i < 8; ++i) {
+        out[i] = g_cov[i].load();
+        if (reset) g_cov[i] = 0;
+    }
+}
 
 int lmo_geometry(const lm_config *cfg, const lm_template t[2][3], int32_t pads[8], int32_t canvas[4]) {
     if (validate(cfg, t)) return LM_ERR_INVALID;

@@ -82,6 +82,8 @@ int lmo_bounding_box_tm_de(const lm_config *cfg, const uint8_t *bkg, const int32
 void lmo_imadjust_default_lut(const uint32_t *hist, uint8_t *lut, int32_t *imin_imax);
 /* firstLastOverT<int> (LocoMouse_class.hpp:411-442) on float column sums */
 void lmo_first_last_over_t(const float *values, uint32_t L, int32_t th, int32_t *first_last);
+/* branch-coverage counters of the pairing stage since the last reset (see g_cov in lm_oracle.cpp) */
+void lmo_coverage(int64_t out[8], int reset);
 /* vecmovingaverage (LocoMouse_class.cpp:1559-1608) */
 void lmo_vecmovingaverage(const double *v, int64_t n, int32_t window, uint32_t *out);
 

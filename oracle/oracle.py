@@ -245,3 +245,15 @@ def vecmovingaverage(v, window: int):
     out = np.zeros(a.size, np.uint32)
     L.lmo_vecmovingaverage(a.ctypes.data_as(_f64p), C.c_int64(a.size), C.c_int32(window), out.ctypes.data_as(_u32p))
     return out
+
+
+COVERAGE_NAMES = ("pairings", "all_equal_boolD_zeroed", "velocity_comparisons", "velocity_rejections", "velocity_accepts",
+                  "moving_windows", "bottom_without_match", "side_matches")
+
+
+def coverage(reset: bool = False) -> dict:
+    """Branch-coverage counters of the oracle's pairing stage since the last reset."""
+    L = lib()
+    out = np.zeros(8, np.int64)
+    L.lmo_coverage(out.ctypes.data_as(C.POINTER(C.c_int64)), int(reset))
+    return dict(zip(COVERAGE_NAMES, map(int, out)))

@@ -30,28 +30,54 @@ struct BBoxDev {
     int32_t *lims;        // [B][2]
 };
 
-__device__ __forceinline__ int diff_at(const BBoxDev &P, const uint8_t *F, int row, int x) {
-    const int xs = P.flip ? (P.n_cols - 1 - x) : x;
-    const int idx = __ldg(P.calib + (int64_t)row * P.n_cols + xs);
-    const int d = (int)__ldg(F + idx) - (int)__ldg(P.bkg + idx);
-    return d < 0 ? 0 : d;
-}
-
 __global__ void __launch_bounds__(256) k_bb_hist(const __grid_constant__ BBoxDev P) {
-    __shared__ uint32_t sh[256];
+    // per-warp private histograms + warp-aggregated increments: a dark side view puts most pixels into a handful of
+    // bins, and 32 lanes hitting one shared-memory word would serialise
+    __shared__ uint32_t sh[8][256];
     __shared__ uint8_t lut[256];
-    const int f = blockIdx.y, tid = threadIdx.x;
-    sh[tid] = 0;
+    const int f = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 8 * 256; i += 256) (&sh[0][0])[i] = 0;
     lut[tid] = P.lut[(f + 1) * 256 + tid];
     __syncthreads();
     const uint8_t *F = P.frames + (int64_t)f * P.frame_bytes;
     const int npx = P.p.side_w * P.p.side_h;
-    for (int i = blockIdx.x * 256 + tid; i < npx; i += gridDim.x * 256) {
-        const int r = i / P.p.side_w, x = i - r * P.p.side_w;
-        atomicAdd(&sh[lut[diff_at(P, F, P.p.side_y + r, P.p.side_x + x)]], 1u);
+    // each lane takes UNR pixels per step, 32 * UNR consecutive pixels per warp; all calibration loads of a step are
+    // issued first, then all frame / background loads: the gather chain is latency-bound otherwise
+    constexpr int UNR = 8;
+    const int stride = gridDim.x * 256 * UNR;
+    for (int i0 = (blockIdx.x * 256 + warp * 32) * UNR; i0 < npx; i0 += stride) {
+        int idx[UNR], bin[UNR];
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+            const int i = i0 + q * 32 + lane;
+            idx[q] = -1;
+            if (i < npx) {
+                const int r = i / P.p.side_w, x = P.p.side_x + (i - r * P.p.side_w);
+                const int xs = P.flip ? (P.n_cols - 1 - x) : x;
+                idx[q] = __ldg(P.calib + (int64_t)(P.p.side_y + r) * P.n_cols + xs);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+            bin[q] = -1;
+            if (idx[q] >= 0) {
+                const int d = (int)__ldg(F + idx[q]) - (int)__ldg(P.bkg + idx[q]);
+                bin[q] = d < 0 ? 0 : d;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+            const int b = bin[q] >= 0 ? (int)lut[bin[q]] : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, b);
+            if (b >= 0 && lane == __ffs(peers) - 1) sh[warp][b] += __popc(peers);
+            __syncwarp();
+        }
     }
     __syncthreads();
-    if (sh[tid]) atomicAdd(&P.hist[f * 256 + tid], sh[tid]);
+    uint32_t tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += sh[w][tid];
+    if (tot) atomicAdd(&P.hist[f * 256 + tid], tot);
 }
 
 __global__ void __launch_bounds__(256) k_bb_pred(const __grid_constant__ BBoxDev P) {
@@ -119,8 +145,21 @@ __global__ void __launch_bounds__(256) k_bb_cols(const __grid_constant__ BBoxDev
     const int r0 = max(0, P.p.zero_row_pre), r1 = min(P.p.side_h, P.p.zero_row_post);
     for (int x = tid; x < P.p.side_w; x += 256) {
         int sum = 0;
-        if (x >= c0 && x < c1)
-            for (int r = r0; r < r1; ++r) sum += pred[diff_at(P, F, P.p.side_y + r, P.p.side_x + x)];
+        if (x >= c0 && x < c1) {
+            // rows in groups of 8 with the two dependent gathers (calibration index -> frame / background bytes) issued
+            // back to back: the column sum is latency-bound otherwise
+            const int xs = P.flip ? (P.n_cols - 1 - (P.p.side_x + x)) : (P.p.side_x + x);
+            for (int r = r0; r < r1; r += 8) {
+                int idx[8], d[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) idx[q] = (r + q < r1) ? __ldg(P.calib + (int64_t)(P.p.side_y + r + q) * P.n_cols + xs) : -1;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) d[q] = idx[q] >= 0 ? (int)__ldg(F + idx[q]) - (int)__ldg(P.bkg + idx[q]) : -1000;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (d[q] > -1000) sum += pred[d[q] < 0 ? 0 : d[q]];
+            }
+        }
         if (sum >= P.p.min_count) {  // firstLastOverT: p[i] >= th
             atomicMin(&s_first, x);
             atomicMax(&s_last, x);

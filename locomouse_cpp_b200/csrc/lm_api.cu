@@ -874,8 +874,16 @@ int lm_bounding_box_tm_de(lm_ctx *ctx, const uint8_t *frames, int frames_on_devi
     }
     if (!frames_on_device && !S.stage) CK(cudaMalloc((void **)&S.stage, (size_t)cap * fsz));
     cudaStream_t st = ctx->stream;
-    std::vector<int32_t> hl((size_t)cap * 2);
-    for (int64_t s0 = 0; s0 < n; s0 += cap) {
+    // results for the whole call stay on the device until the end: chunks run back to back without a host sync
+    double *d_bbx = nullptr;
+    int32_t *d_lims = nullptr;
+    CK(cudaMalloc((void **)&d_bbx, (size_t)n * sizeof(double)));
+    if (cudaMalloc((void **)&d_lims, (size_t)n * 2 * sizeof(int32_t)) != cudaSuccess) {
+        cudaFree(d_bbx);
+        return fail(ctx, LM_ERR_RUNTIME, "out of device memory");
+    }
+    int rc = LM_OK;
+    for (int64_t s0 = 0; s0 < n && rc == LM_OK; s0 += cap) {
         const int B = (int)std::min<int64_t>(cap, n - s0);
         LmBatch b{};
         b.B = B;
@@ -894,17 +902,23 @@ int lm_bounding_box_tm_de(lm_ctx *ctx, const uint8_t *frames, int frames_on_devi
         if (frames_on_device) {
             b.frames = frames + s0 * fsz;
         } else {
-            CK(cudaMemcpyAsync(S.stage, frames + s0 * fsz, (size_t)B * fsz, cudaMemcpyHostToDevice, st));
+            // the staging buffer is reused: stream order makes the copy wait for the previous chunk's kernels
+            if (cudaMemcpyAsync(S.stage, frames + s0 * fsz, (size_t)B * fsz, cudaMemcpyHostToDevice, st) != cudaSuccess)
+                rc = fail(ctx, LM_ERR_RUNTIME, "H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
             b.frames = S.stage;
         }
-        const int nl = lm_launch_bbox_tm_de(b, *p, S.hist, S.pred, S.bbx, S.lims, st);
-        if (nl < 0) return fail(ctx, LM_ERR_RUNTIME, "bounding-box launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        CK(cudaMemcpyAsync(bb_x_raw + s0, S.bbx, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(hl.data(), S.lims, (size_t)B * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (lims) memcpy(lims + s0 * 2, hl.data(), (size_t)B * 2 * sizeof(int32_t));
+        if (rc == LM_OK && lm_launch_bbox_tm_de(b, *p, S.hist, S.pred, d_bbx + s0, d_lims + s0 * 2, st) < 0)
+            rc = fail(ctx, LM_ERR_RUNTIME, "bounding-box launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    return LM_OK;
+    if (rc == LM_OK && cudaMemcpyAsync(bb_x_raw, d_bbx, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        rc = fail(ctx, LM_ERR_RUNTIME, "D2H copy failed");
+    if (rc == LM_OK && lims && cudaMemcpyAsync(lims, d_lims, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        rc = fail(ctx, LM_ERR_RUNTIME, "D2H copy failed");
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == LM_OK)
+        rc = fail(ctx, LM_ERR_RUNTIME, "pass 1 failed on the device: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_bbx);
+    cudaFree(d_lims);
+    return rc;
 }
 
 // vecmovingaverage (LocoMouse_class.cpp:1559-1608).  (uint32_t)double of a negative value is undefined in C++; like

@@ -383,7 +383,7 @@ def main():
             e2e = {"value": world * n * args.steps / ew, "unit": UNIT,
                    "h2d_bytes_per_step": int(n * cfg.vid_rows * cfg.vid_cols + 3 * 4 * n), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": ew / args.steps * 1e3, "numa_bound": bool(numa_bound),
-                   "note": "frames in pinned host memory, copied H2D inside the call (overlapped with compute per 256-frame "
+                   "note": f"frames in pinned host memory, copied H2D inside the call (overlapped with compute per {subb}-frame "
                            "sub-batch); results copied D2H" + ("; candidate lists gathered to rank 0 over NCCL" if world > 1 else "")}
         except Exception as ex:  # pragma: no cover
             e2e = {"value": None, "unit": UNIT, "error": repr(ex)}

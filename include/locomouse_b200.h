@@ -150,7 +150,7 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device,
  *             cta_group::2, 1 = one CTA per tile) followed by an exact FP32 re-evaluation of the undecided
  *             outputs; 0: dense exact FP32 kernel only.  All three produce bit-identical results (the screen
  *             only discards outputs proven <= 0).
- *  "subbatch" frames per internal sub-batch (default 256).
+ *  "subbatch" frames per internal sub-batch (default 512).
  *  "streams"  2 (default): consecutive sub-batches run on two streams with separate scratch, so the latency-bound
  *             kernels of one overlap the tensor-core kernel of the next; 1: all kernels strictly serial (used when
  *             timing a single kernel with events).

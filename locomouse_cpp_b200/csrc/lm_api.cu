@@ -29,7 +29,7 @@ struct lm_ctx {
     float *d_tmpl[2][3] = {};
     std::vector<float> h_tmpl[2][3];  // host copies (the screen's quantisation is derived from them)
     int opt_screen = 2;               // 0: dense exact kernel only, 1: tensor-core screen, one CTA per tile, 2: CTA pairs
-    int opt_subbatch = 256;
+    int opt_subbatch = 512;
     int opt_streams = 2;              // 2: consecutive sub-batches overlap on two streams, 1: strictly serial kernels
     LmScreenHost scr_info[2][3] = {};
     int t_rows[2][3] = {}, t_cols[2][3] = {};

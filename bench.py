@@ -116,7 +116,7 @@ def run_reference(args):
 
     spec = synth.SynthSpec()
     threads = host_threads()
-    per_step = max(threads * 4, 32)
+    per_step = max(threads * 32, 256)  # ~0.5 s of work per step on all host threads
     cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(spec, per_step, seed=1000)
     frames = frames.numpy()
     for _ in range(args.warmup):
@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_STEP, help="frames per step per GPU (default: the 10k config)")
-    ap.add_argument("--cpu-sample", type=int, default=256, help="frames of the workload timed on the CPU oracle (1 thread)")
+    ap.add_argument("--cpu-sample", type=int, default=640, help="frames of the workload timed on the CPU oracle (1 thread)")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

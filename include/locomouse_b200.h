@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LM_ABI_VERSION 1
+#define LM_ABI_VERSION 2  /* 2: lm_set_option, lm_get_info, lm_debug_nms, lm_bounding_box_tm_de, lm_moving_average */
 
 /* feature / view indices used in every [2] / [3] array below */
 enum { LM_PAW = 0, LM_SNOUT = 1, LM_TAIL = 2 };

@@ -12,7 +12,8 @@
  * python `cv2` — primitive by primitive (tests/test_oracle_vs_cv2.py): filter2D, normalize,
  * subtract, threshold, LUT, flip, connectedComponentsWithStats, moments; plus hand-derived
  * known-answer tests for the reference's own loops (nmsMax, peakClustering, matchViews).
- * nmsMax, peakClustering and the Candidate / P22D classes use OpenCV for value types only, so the
+ * nmsMax, peakClustering, vecmovingaverage, firstLastOverT, LocoMouse::imadjust and the Candidate / P22D
+ * classes use OpenCV for value types only (imadjust additionally cv::LUT), so the
  * reference's OWN source lines for them are compiled from /root/reference against a value-type shim
  * (oracle/ref_shim, `make -C oracle ref` -> oracle/_ref/libref_nms.so) and the oracle is checked
  * against that code bit for bit (tests/test_oracle_vs_reference.py, golden vectors in

@@ -6,7 +6,21 @@
 #include <algorithm>
 #include "Candidates.hpp"  // the reference's header, found through -I/root/reference/Candidates
 
-#include "_ref/ref_nms_body.inc"
+#include <cmath>
+#include <cstdint>
+#include <functional>
+#include <numeric>
+
+// stand-in for the class whose member LocoMouse::imadjust is compiled below (the real declaration,
+// LocoMouse_class.hpp:170-350, drags in VideoCapture / FileStorage members that the method never touches)
+class LocoMouse {
+public:
+    void imadjust(const cv::Mat &Iin, cv::Mat &Iout, double low_in, double high_in, double low_out, double high_out);
+};
+
+#include "_ref/ref_nms_body.inc"      // vecmovingaverage, nmsMax, peakClustering   (LocoMouse_class.cpp:1559-1905)
+#include "_ref/ref_hpp_body.inc"      // template firstLastOverT                     (LocoMouse_class.hpp:411-442)
+#include "_ref/ref_imadjust_body.inc" // LocoMouse::imadjust                         (LocoMouse_class.cpp:3204-3242)
 
 extern "C" {
 
@@ -46,6 +60,26 @@ int ref_p22d(int xb, int yb, double sb, int n_side, const int *ys, const double 
         out_s[i] = p.score_side((uint)i);
     }
     return n;
+}
+
+void ref_vecmovingaverage(const double *v, int n, int window, unsigned int *out) {
+    std::vector<double> a(v, v + n);
+    std::vector<unsigned int> o(n, 0u);
+    vecmovingaverage(a, o, window);
+    for (int i = 0; i < n; ++i) out[i] = o[i];
+}
+
+void ref_first_last_over_t(const float *values, unsigned int L, int th, int *first_last) {
+    cv::Mat m(1, (int)L, CV_32F, (void *)values, (size_t)L * sizeof(float));
+    firstLastOverT<int>(m, L, first_last, th);
+}
+
+void ref_imadjust_lut(double low_in, double high_in, double low_out, double high_out, unsigned char *lut) {
+    cv::Mat ramp(1, 256, CV_8U), out(1, 256, CV_8U);
+    for (int i = 0; i < 256; ++i) ramp.ptr<uchar>(0)[i] = (uchar)i;
+    LocoMouse L;
+    L.imadjust(ramp, out, low_in, high_in, low_out, high_out);
+    for (int i = 0; i < 256; ++i) lut[i] = out.ptr<uchar>(0)[i];
 }
 
 int ref_default_candidate(int *x, int *y, double *s) {

@@ -1,8 +1,10 @@
 // oracle/ref_shim/opencv2/core.hpp — TEST INFRASTRUCTURE ONLY.
 //
 // The reference (careylab/LocoMouse_cpp) cannot be built in this image: it needs the OpenCV C++ SDK.  Two
-// pieces of its detection path, however, use OpenCV only for VALUE TYPES: Candidates/Candidates.cpp and the
-// free functions nmsMax / peakClustering (LocoMouse_Core/LocoMouse_class.cpp:1610-1905).  This header supplies
+// pieces of its detection path, however, use OpenCV only for VALUE TYPES: Candidates/Candidates.cpp, the free
+// functions nmsMax / peakClustering / vecmovingaverage (LocoMouse_Core/LocoMouse_class.cpp:1559-1905), the
+// firstLastOverT template (LocoMouse_class.hpp:411-442) and LocoMouse::imadjust (3204-3242, which only fills a
+// 256-entry table and applies cv::LUT).  This header supplies
 // just those types (Point_, Size_, Rect_, a header-only Mat view, saturate_cast, CV_Assert and inert
 // FileStorage stubs) with OpenCV's documented semantics, so that oracle/Makefile can compile the reference's
 // OWN source lines, from where they lie under /root/reference, into oracle/_ref/libref_nms.so.  That library
@@ -12,6 +14,7 @@
 #include <cassert>
 #include <cmath>
 #include <cstddef>
+#include <cstdint>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -24,6 +27,8 @@ typedef unsigned char uchar;
     do {                                                                       \
         if (!(expr)) throw std::runtime_error("CV_Assert failed: " #expr);     \
     } while (0)
+#define CV_8U 0
+#define CV_8UC1 0
 #define CV_32F 5
 #define CV_32FC1 5
 
@@ -90,17 +95,51 @@ inline Rect_<T> operator&(const Rect_<T> &a, const Rect_<T> &b) {
 }
 typedef Rect_<int> Rect;
 
-// non-owning row-major view; only what nmsMax / peakClustering touch
+// row-major matrix header: a view on caller memory or an owned buffer; only what nmsMax / peakClustering /
+// firstLastOverT / imadjust touch (data, rows, cols, type(), ptr<T>())
 class Mat {
+    std::vector<uchar> own_;
+    int type_;
+
 public:
     uchar *data;
     int rows, cols;
     size_t step;
-    Mat() : data(nullptr), rows(0), cols(0), step(0) {}
-    Mat(int r, int c, int /*type*/, void *d, size_t step_bytes) : data((uchar *)d), rows(r), cols(c), step(step_bytes) {}
+    Mat() : type_(0), data(nullptr), rows(0), cols(0), step(0) {}
+    Mat(int r, int c, int type, void *d, size_t step_bytes) : type_(type), data((uchar *)d), rows(r), cols(c), step(step_bytes) {}
+    Mat(int r, int c, int type) : type_(type), rows(r), cols(c) {
+        const size_t esz = (type == 0) ? 1 : 4;  // CV_8U : CV_32F / CV_32S
+        step = (size_t)c * esz;
+        own_.assign((size_t)r * step, 0);
+        data = own_.data();
+    }
+    Mat(const Mat &o) : own_(o.own_), type_(o.type_), data(o.own_.empty() ? o.data : own_.data()), rows(o.rows), cols(o.cols), step(o.step) {}
+    Mat &operator=(const Mat &o) {
+        own_ = o.own_;
+        type_ = o.type_;
+        rows = o.rows;
+        cols = o.cols;
+        step = o.step;
+        data = o.own_.empty() ? o.data : own_.data();
+        return *this;
+    }
+    int type() const { return type_; }
     template <typename T>
     const T *ptr(int r) const { return (const T *)(data + (size_t)r * step); }
+    template <typename T>
+    T *ptr(int r) { return (T *)(data + (size_t)r * step); }
 };
+// cv::LUT for single-channel 8-bit data: dst(i) = lut(src(i))
+inline void LUT(const Mat &src, const Mat &lut, Mat &dst) {
+    Mat out(src.rows, src.cols, 0);
+    const uchar *t = lut.ptr<uchar>(0);
+    for (int r = 0; r < src.rows; ++r) {
+        const uchar *s = src.ptr<uchar>(r);
+        uchar *d = out.ptr<uchar>(r);
+        for (int c = 0; c < src.cols; ++c) d[c] = t[s[c]];
+    }
+    dst = out;
+}
 
 // inert persistence stubs: Candidates.cpp's YAML (de)serialisers must compile, they are never called
 class FileNode;

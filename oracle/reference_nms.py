@@ -36,6 +36,12 @@ def lib():
         L.ref_peak_clustering.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int]
         L.ref_p22d.restype = C.c_int
         L.ref_p22d.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_vecmovingaverage.restype = None
+        L.ref_vecmovingaverage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ref_first_last_over_t.restype = None
+        L.ref_first_last_over_t.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_void_p]
+        L.ref_imadjust_lut.restype = None
+        L.ref_imadjust_lut.argtypes = [C.c_double] * 4 + [C.c_void_p]
         L.ref_default_candidate.restype = C.c_int
         L.ref_default_candidate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
@@ -66,3 +72,26 @@ def p22d(xb, yb, sb, side):
     os_ = np.zeros(max(len(side), 1), np.float64)
     n = lib().ref_p22d(xb, yb, float(sb), len(side), ys.ctypes.data, ss.ctypes.data, oy.ctypes.data, os_.ctypes.data, len(oy))
     return n, list(zip(oy[:n].tolist(), os_[:n].tolist()))
+
+
+def vecmovingaverage(v, window: int):
+    """The reference's vecmovingaverage (LocoMouse_class.cpp:1559-1608)."""
+    a = np.ascontiguousarray(v, np.float64)
+    out = np.zeros(a.size, np.uint32)
+    lib().ref_vecmovingaverage(a.ctypes.data, a.size, int(window), out.ctypes.data)
+    return out
+
+
+def first_last_over_t(values, th: int):
+    """The reference's firstLastOverT<int> (LocoMouse_class.hpp:411-442)."""
+    a = np.ascontiguousarray(values, np.float32)
+    fl = np.zeros(2, np.int32)
+    lib().ref_first_last_over_t(a.ctypes.data, a.size, int(th), fl.ctypes.data)
+    return int(fl[0]), int(fl[1])
+
+
+def imadjust_lut(low_in=0.0, high_in=0.6, low_out=0.0, high_out=1.0):
+    """The 256-entry mapping the reference's LocoMouse::imadjust applies (LocoMouse_class.cpp:3204-3242)."""
+    lut = np.zeros(256, np.uint8)
+    lib().ref_imadjust_lut(float(low_in), float(high_in), float(low_out), float(high_out), lut.ctypes.data)
+    return lut

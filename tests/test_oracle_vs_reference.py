@@ -86,3 +86,23 @@ def test_reference_p22d_contract():
     x, y, s = (np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.float64))
     code = ref.lib().ref_default_candidate(x.ctypes.data, y.ctypes.data, s.ctypes.data)
     assert (int(x[0]), int(y[0]), float(s[0])) == (-1, -1, -1.0) and code == -1
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libref_nms.so not built (reference not mounted)")
+def test_oracle_helpers_match_reference_code(oracle):
+    """vecmovingaverage, firstLastOverT and LocoMouse::imadjust: the oracle vs the reference's own compiled lines."""
+    rng = np.random.Generator(np.random.PCG64(99))
+    for _ in range(60):
+        n, w = int(rng.integers(1, 80)), int(rng.choice([1, 3, 5, 7, 9, 11]))
+        v = rng.uniform(0, 1800, n)                      # non-negative: (uint32_t) of a negative double is UB in the reference
+        assert np.array_equal(oracle.vecmovingaverage(v, w), ref.vecmovingaverage(v, w))
+    for _ in range(60):
+        vals = rng.integers(0, 60, int(rng.integers(1, 300))).astype(np.float32)
+        th = int(rng.integers(0, 65))
+        assert oracle.first_last_over_t(vals, th) == ref.first_last_over_t(vals, th)
+    assert oracle.first_last_over_t([0, 7, 0], 7) == ref.first_last_over_t([0, 7, 0], 7) == (1, 0)
+    assert oracle.first_last_over_t([0, 0], 1) == ref.first_last_over_t([0, 0], 1) == (-1, -1)
+    for lo, hi, lo_o, hi_o in [(0.0, 0.6, 0.0, 1.0), (0.1, 0.9, 0.0, 1.0), (0.0, 1.0, 0.2, 0.8), (0.25, 0.5, 0.1, 1.0)]:
+        assert np.array_equal(oracle.imadjust_lut(lo, hi, lo_o, hi_o), ref.imadjust_lut(lo, hi, lo_o, hi_o))
+    # LocoMouse_TM::readFrame's imadjust(I, I, 0, 0.6, 0, 1) (LocoMouse_TM.cpp:247): 0, 2, 3, 5, 7, 8, 10, 12, ...
+    assert ref.imadjust_lut()[:8].tolist() == [0, 2, 3, 5, 7, 8, 10, 12] and ref.imadjust_lut()[153:].min() == 255

@@ -35,15 +35,31 @@ __global__ void __launch_bounds__(256) k_minmax(const __grid_constant__ LmBatch 
     const int64_t nvec = vec ? (n >> 4) : 0;
     const uint4 *F4 = reinterpret_cast<const uint4 *>(F);
     const uint4 *K4 = reinterpret_cast<const uint4 *>(K);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    // four independent 16-byte loads of the frame (and of the L2-resident background) in flight per thread: the pass is
+    // HBM-bound and a dependent one-load-per-iteration loop leaves the memory pipeline half empty
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        uint4 f[4], k[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) f[q] = __ldcs(F4 + i + q * stride);  // streamed once: do not keep in L2
+#pragma unroll
+        for (int q = 0; q < 4; ++q) k[q] = __ldg(K4 + i + q * stride);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t d0 = __vsubus4(f[q].x, k[q].x), d1 = __vsubus4(f[q].y, k[q].y), d2 = __vsubus4(f[q].z, k[q].z), d3 = __vsubus4(f[q].w, k[q].w);
+            mn = __vminu4(mn, __vminu4(__vminu4(d0, d1), __vminu4(d2, d3)));
+            mx = __vmaxu4(mx, __vmaxu4(__vmaxu4(d0, d1), __vmaxu4(d2, d3)));
+        }
+    }
+    for (; i < nvec; i += stride) {
         uint4 f = __ldg(F4 + i), k = __ldg(K4 + i);
         uint32_t d0 = __vsubus4(f.x, k.x), d1 = __vsubus4(f.y, k.y), d2 = __vsubus4(f.z, k.z), d3 = __vsubus4(f.w, k.w);
         mn = __vminu4(mn, __vminu4(__vminu4(d0, d1), __vminu4(d2, d3)));
         mx = __vmaxu4(mx, __vmaxu4(__vmaxu4(d0, d1), __vmaxu4(d2, d3)));
     }
-    for (int64_t i = (nvec << 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        int d = (int)F[i] - (int)K[i];
+    for (int64_t t = (nvec << 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        int d = (int)F[t] - (int)K[t];
         uint32_t u = d < 0 ? 0u : (uint32_t)d;
         mn = __vminu4(mn, u * 0x01010101u);
         mx = __vmaxu4(mx, u * 0x01010101u);

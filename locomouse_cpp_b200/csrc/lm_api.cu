@@ -645,9 +645,29 @@ int lm_get_geometry(const lm_ctx *ctx, int32_t pads[8], int32_t canvas[4]) {
     return LM_OK;
 }
 
+static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, const uint8_t *prev_frame, int64_t n,
+                             int64_t first_frame_index, const uint32_t *bb_x, const uint32_t *bb_y_side,
+                             const uint32_t *bb_y_bottom, lm_results *out);
+
 int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, const uint8_t *prev_frame, int64_t n,
                     int64_t first_frame_index, const uint32_t *bb_x, const uint32_t *bb_y_side,
                     const uint32_t *bb_y_bottom, lm_results *out) {
+    const int rc = detect_batch_impl(ctx, frames, frames_on_device, prev_frame, n, first_frame_index, bb_x, bb_y_side, bb_y_bottom, out);
+    if (ctx && rc != LM_OK && rc != LM_ERR_OVERFLOW) {
+        // a failure in the middle of the pipeline must not leave copies / kernels of this call in flight: the caller's
+        // buffers (and the next call's scratch) would still be in use
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->stream1);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, const uint8_t *prev_frame, int64_t n,
+                             int64_t first_frame_index, const uint32_t *bb_x, const uint32_t *bb_y_side,
+                             const uint32_t *bb_y_bottom, lm_results *out) {
     if (!ctx) return LM_ERR_INVALID;
     if (!ctx->configured || !ctx->model_set || !ctx->bkg_set || !ctx->calib_set)
         return fail(ctx, LM_ERR_STATE, "lm_detect_batch needs lm_configure, lm_set_model, lm_set_background and lm_set_calibration first");

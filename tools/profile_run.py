@@ -14,6 +14,7 @@ ap.add_argument("--frames", type=int, default=512)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--scale", type=int, default=1)
 ap.add_argument("--screen", type=int, default=2)
+ap.add_argument("--streams", type=int, default=2)
 args = ap.parse_args()
 spec = synth.SynthSpec(scale=args.scale) if args.scale == 1 else synth.SynthSpec(scale=args.scale, cand_cap=128, match_cap=512)
 cfg, model, bkg, calib, _, _, _, _ = synth.make_problem(spec, 8, seed=1000)
@@ -21,6 +22,7 @@ frames, bx, bs, bb = synth.make_video(spec, args.frames, 1000, "cuda", bkg)
 torch.cuda.synchronize()
 det = Detector(cfg, model, bkg, calib)
 det.set_option("screen", args.screen)
+det.set_option("streams", args.streams)
 for _ in range(args.iters):
     r = det.detect_batch(frames, bx, bs, bb, allow_overflow=True)
     print(det.last_timing())

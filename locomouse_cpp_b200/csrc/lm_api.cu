@@ -853,6 +853,13 @@ int lm_get_info(const lm_ctx *ctx, const char *name, double *value) {
         *value = eps ? ctx->scr_info[v][f].eps : ctx->scr_info[v][f].scale;
         return LM_OK;
     }
+    if (!strncmp(name, "stage_t_", 8) && name[8] >= '0' && name[8] <= '1' && name[9] == '_' && name[10] >= '0' && name[10] <= '7' && !name[11]) {
+        // device timeline of the last call: ms from the start of the call to stage event k of the LAST sub-batch that ran in slot s
+        float t = -1.f;
+        if (cudaEventElapsedTime(&t, ctx->ev_call[0], ctx->ev_stage[name[8] - '0'][name[10] - '0']) != cudaSuccess) t = -1.f;
+        *value = (double)t;
+        return LM_OK;
+    }
     if (!strcmp(name, "ms_screen")) {  // device time of k_screen alone in the last lm_detect_batch call
         *value = (double)ctx->ms_screen;
         return LM_OK;

@@ -1,5 +1,6 @@
-"""Development aid: run the CUDA path and the oracle on the same small synthetic problem and print
-where they differ, stage by stage.  (tests/ hold the real parity tests; this prints diagnostics.)"""
+"""Development aid (lives under tests/ because it uses the oracle): run the CUDA path and the oracle on the same small
+synthetic problem and print where they differ, stage by stage.  Not collected by pytest; run it directly:
+    python tests/dev_gpu_check.py --frames 8"""
 import argparse
 import os
 import sys

@@ -11,16 +11,51 @@
 #include <functional>
 #include <numeric>
 
-// stand-in for the class whose member LocoMouse::imadjust is compiled below (the real declaration,
-// LocoMouse_class.hpp:170-350, drags in VideoCapture / FileStorage members that the method never touches)
+#include <fstream>
+
+// Stand-ins for the declarations the compiled member functions need (the real ones, LocoMouse_class.hpp:110-350, drag in
+// VideoCapture / FileStorage / MyMat members that these methods never touch).  Only data the methods read is kept.
+struct LocoMouse_Parameters_Stub {
+    bool LM_DEBUG = false;
+};
+class LocoMouse_Feature {  // sizes + velocity-matching boxes; boxes by the formula of LocoMouse_class.cpp:2954-2969
+    cv::Size size_b, size_s;
+    cv::Rect match_rect_b, match_rect_s;
+
+public:
+    LocoMouse_Feature(int tw_b, int th_b, int tw_s, int th_s) : size_b(tw_b, th_b), size_s(tw_s, th_s) {
+        int new_b_w = round(((double)tw_b) / 2), new_b_h = round(((double)th_b) / 2);
+        int new_t_w = round(((double)tw_s) / 2), new_t_h = round(((double)th_s) / 2);
+        match_rect_b = cv::Rect(-(new_b_w / 2), -(new_b_h / 2), new_b_w, new_b_h);
+        match_rect_s = cv::Rect(-(new_t_w / 2), -(new_t_h / 2), new_t_w, new_t_h);
+    }
+    cv::Size size_bottom() const { return size_b; }
+    cv::Size size_side() const { return size_s; }
+    cv::Rect match_box_bottom() const { return match_rect_b; }
+    cv::Rect match_box_side() const { return match_rect_s; }
+};
 class LocoMouse {
 public:
+    LocoMouse_Parameters_Stub LM_PARAMS;
+    std::ofstream DEBUG_TEXT;
     void imadjust(const cv::Mat &Iin, cv::Mat &Iout, double low_in, double high_in, double low_out, double high_out);
+    std::vector<P22D> matchingWithVelocityConstraint(std::vector<Candidate> &Candidates_b, std::vector<Candidate> &Candidates_t,
+                                                     const cv::Mat &Ibbb, const cv::Mat &Itbb, const cv::Mat &Ibbb_prev,
+                                                     const cv::Mat &Itbbb_prev, const cv::Point_<int> padding_pre_bottom,
+                                                     const cv::Point_<int> padding_pre_side, bool vel_check, LocoMouse_Feature &F, double T,
+                                                     bool debug);
+    cv::Mat xDist(const std::vector<Candidate> &P1, const std::vector<Candidate> &P2);
+    std::vector<P22D> matchViews(const cv::Mat &boolD, const cv::Mat &D_side_weight, const std::vector<Candidate> &C_b,
+                                 const std::vector<Candidate> &C_t, bool vel_check, LocoMouse_Feature &F, const cv::Mat &Ibbb,
+                                 const cv::Mat &Itbb, const cv::Mat &Ibbb_prev, const cv::Mat &Itbb_prev,
+                                 const cv::Point_<int> padding_pre_bottom, const cv::Point_<int> padding_pre_side, bool debug);
+    bool checkVelCriterion(const cv::Mat &I, const cv::Mat &I_prev, const cv::Rect &im_box, int box_area, double alpha, double T);
 };
 
 #include "_ref/ref_nms_body.inc"      // vecmovingaverage, nmsMax, peakClustering   (LocoMouse_class.cpp:1559-1905)
 #include "_ref/ref_hpp_body.inc"      // template firstLastOverT                     (LocoMouse_class.hpp:411-442)
 #include "_ref/ref_imadjust_body.inc" // LocoMouse::imadjust                         (LocoMouse_class.cpp:3204-3242)
+#include "_ref/ref_pair_body.inc"     // matchingWithVelocityConstraint, xDist, matchViews, checkVelCriterion (1023-1267)
 
 extern "C" {
 
@@ -80,6 +115,69 @@ void ref_imadjust_lut(double low_in, double high_in, double low_out, double high
     LocoMouse L;
     L.imadjust(ramp, out, low_in, high_in, low_out, high_out);
     for (int i = 0; i < 256; ++i) lut[i] = out.ptr<uchar>(0)[i];
+}
+
+// matchingWithVelocityConstraint on padded crops (I_*_MOUSE_PAD of the current and the previous frame, row-major u8) with the
+// candidates in unpadded-crop coordinates, exactly the arguments matchBottomSideCandidates passes (class.cpp:999-1021).
+// Output: per bottom candidate number_of_candidates() and the stored (y, score) pairs, concatenated.
+int ref_match_views(const ref_cand *cb, int nb, const ref_cand *cs, int ns, int vel_check, int tw_b, int th_b, int tw_s, int th_s,
+                    double T, const unsigned char *Ibbb, const unsigned char *Ibbb_prev, int wb, int hb, const unsigned char *Itbb,
+                    const unsigned char *Itbb_prev, int ws, int hs, int pad_bx, int pad_by, int pad_sx, int pad_sy, int *match_n,
+                    int *match_y, double *match_s, int cap) {
+    std::vector<Candidate> B, S;
+    for (int i = 0; i < nb; ++i) B.push_back(Candidate(cb[i].x, cb[i].y, cb[i].s));
+    for (int i = 0; i < ns; ++i) S.push_back(Candidate(cs[i].x, cs[i].y, cs[i].s));
+    cv::Mat Ib(hb, wb, CV_8U, (void *)Ibbb, (size_t)wb), Ibp(hb, wb, CV_8U, (void *)Ibbb_prev, (size_t)wb);
+    cv::Mat It(hs, ws, CV_8U, (void *)Itbb, (size_t)ws), Itp(hs, ws, CV_8U, (void *)Itbb_prev, (size_t)ws);
+    LocoMouse_Feature F(tw_b, th_b, tw_s, th_s);
+    LocoMouse L;
+    std::vector<P22D> P;
+    try {
+        P = L.matchingWithVelocityConstraint(B, S, Ib, It, Ibp, Itp, cv::Point_<int>(pad_bx, pad_by), cv::Point_<int>(pad_sx, pad_sy),
+                                             vel_check != 0, F, T, false);
+    } catch (const std::exception &) {
+        return -1;  // the reference throws (CV_Assert / ROI): e.g. ovlp == 0 makes the weights NaN
+    }
+    int total = 0;
+    for (size_t i = 0; i < P.size(); ++i) {
+        const int n = P[i].number_of_candidates();
+        match_n[i] = n;
+        for (int k = 0; k < n; ++k, ++total)
+            if (total < cap) {
+                match_y[total] = P[i].y_side_coord((uint)k);
+                match_s[total] = P[i].score_side((uint)k);
+            }
+    }
+    return (int)P.size() * 100000 + total;
+}
+
+// The elementwise primitives of the shim that the pairing code calls, exposed so that tests/test_oracle_vs_cv2.py can pin
+// each of them against the real OpenCV (cv2): D <= ovlp, normalize(MINMAX), reduce(SUM) both ways, convertTo + the
+// alpha * A + beta expression, and checkVelCriterion's subtract / threshold / sum chain.
+void ref_shim_primitives(const int *D, int rows, int cols, int ovlp, unsigned char *bool_raw, unsigned char *bool_norm,
+                         float *colsum, float *rowsum, double *weight, const unsigned char *a, const unsigned char *b, int r2,
+                         int c2, double thr, double *count) {
+    cv::Mat Dm(rows, cols, CV_32SC1, (void *)D, (size_t)cols * 4);
+    cv::Mat boolD = Dm <= ovlp;
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) bool_raw[r * cols + c] = boolD.ptr<uchar>(r)[c];
+    cv::normalize(boolD, boolD, 0, 1, cv::NORM_MINMAX, -1);
+    cv::Mat cs, rs, W;
+    cv::reduce(boolD, cs, 0, cv::CV_REDUCE_SUM, CV_32FC1);
+    cv::reduce(boolD, rs, 1, cv::CV_REDUCE_SUM, CV_32FC1);
+    Dm.convertTo(W, CV_64FC1);
+    W = 1 - (W / (double)ovlp);
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) {
+            bool_norm[r * cols + c] = boolD.ptr<uchar>(r)[c];
+            weight[r * cols + c] = W.ptr<double>(r)[c];
+        }
+    for (int c = 0; c < cols; ++c) colsum[c] = cs.ptr<float>(0)[c];
+    for (int r = 0; r < rows; ++r) rowsum[r] = rs.ptr<float>(0)[r];
+    cv::Mat A(r2, c2, CV_8U, (void *)a, (size_t)c2), B(r2, c2, CV_8U, (void *)b, (size_t)c2), S;
+    cv::subtract(A, B, S, cv::noArray(), CV_8UC1);
+    cv::threshold(S, S, thr, 1, cv::THRESH_BINARY);
+    *count = cv::sum(S)(0);
 }
 
 int ref_default_candidate(int *x, int *y, double *s) {

@@ -5,17 +5,22 @@
 // functions nmsMax / peakClustering / vecmovingaverage (LocoMouse_Core/LocoMouse_class.cpp:1559-1905), the
 // firstLastOverT template (LocoMouse_class.hpp:411-442) and LocoMouse::imadjust (3204-3242, which only fills a
 // 256-entry table and applies cv::LUT).  This header supplies
-// just those types (Point_, Size_, Rect_, a header-only Mat view, saturate_cast, CV_Assert and inert
-// FileStorage stubs) with OpenCV's documented semantics, so that oracle/Makefile can compile the reference's
-// OWN source lines, from where they lie under /root/reference, into oracle/_ref/libref_nms.so.  That library
-// pins the oracle's restatement of those loops against the real reference code (tests/test_oracle_vs_reference.py).
-// No algorithm lives here.
+// just those types (Point_, Size_, Rect_, a header-only Mat with OpenCV's sharing semantics, saturate_cast,
+// CV_Assert, inert FileStorage stubs) plus the handful of ELEMENTWISE primitives the pairing code calls (compare,
+// normalize(MINMAX), convertTo, the alpha*A+beta expression, reduce(SUM), saturating subtract, threshold, sum, LUT),
+// each a few lines with OpenCV's documented semantics and each pinned against the real OpenCV (cv2) in
+// tests/test_oracle_vs_cv2.py.  With it oracle/Makefile compiles the reference's OWN source lines, from where they
+// lie under /root/reference, into oracle/_ref/libref_nms.so, which pins the oracle's restatement of those loops --
+// their control flow in particular -- against the real reference code (tests/test_oracle_vs_reference.py).
+// No reference algorithm (NMS, clustering, pairing, velocity criterion) lives here.
 #pragma once
 #include <cassert>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <iostream>
+#include <memory>
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <sys/types.h>
@@ -27,11 +32,6 @@ typedef unsigned char uchar;
     do {                                                                       \
         if (!(expr)) throw std::runtime_error("CV_Assert failed: " #expr);     \
     } while (0)
-#define CV_8U 0
-#define CV_8UC1 0
-#define CV_32F 5
-#define CV_32FC1 5
-
 namespace cv {
 
 // saturate_cast<int>(double) == cvRound: round half to even
@@ -95,10 +95,28 @@ inline Rect_<T> operator&(const Rect_<T> &a, const Rect_<T> &b) {
 }
 typedef Rect_<int> Rect;
 
-// row-major matrix header: a view on caller memory or an owned buffer; only what nmsMax / peakClustering /
-// firstLastOverT / imadjust touch (data, rows, cols, type(), ptr<T>())
+// Row-major single-channel matrix with OpenCV's sharing semantics (copies and ROIs alias the same buffer): what
+// nmsMax / peakClustering / firstLastOverT / imadjust / xDist / matchingWithVelocityConstraint / matchViews /
+// checkVelCriterion touch.  Depth codes as in OpenCV.
+#define CV_8U 0
+#define CV_8UC1 0
+#define CV_32S 4
+#define CV_32SC1 4
+#define CV_32F 5
+#define CV_32FC1 5
+#define CV_64F 6
+#define CV_64FC1 6
+enum { NORM_MINMAX = 32, THRESH_BINARY = 0, CV_REDUCE_SUM = 0 };
+
+class Mat;
+// the one lazy expression the path relies on: alpha * A + beta, folded like cv::MatOp_AddEx
+struct MatExpr {
+    const Mat *a;
+    double alpha, beta;
+};
+
 class Mat {
-    std::vector<uchar> own_;
+    std::shared_ptr<std::vector<uchar> > buf_;
     int type_;
 
 public:
@@ -108,30 +126,118 @@ public:
     Mat() : type_(0), data(nullptr), rows(0), cols(0), step(0) {}
     Mat(int r, int c, int type, void *d, size_t step_bytes) : type_(type), data((uchar *)d), rows(r), cols(c), step(step_bytes) {}
     Mat(int r, int c, int type) : type_(type), rows(r), cols(c) {
-        const size_t esz = (type == 0) ? 1 : 4;  // CV_8U : CV_32F / CV_32S
-        step = (size_t)c * esz;
-        own_.assign((size_t)r * step, 0);
-        data = own_.data();
+        step = (size_t)c * elemSize();
+        buf_.reset(new std::vector<uchar>((size_t)r * step + 1, 0));
+        data = buf_->data();
     }
-    Mat(const Mat &o) : own_(o.own_), type_(o.type_), data(o.own_.empty() ? o.data : own_.data()), rows(o.rows), cols(o.cols), step(o.step) {}
-    Mat &operator=(const Mat &o) {
-        own_ = o.own_;
-        type_ = o.type_;
-        rows = o.rows;
-        cols = o.cols;
-        step = o.step;
-        data = o.own_.empty() ? o.data : own_.data();
-        return *this;
-    }
+    static size_t elemSizeOf(int type) { return type == CV_8U ? 1 : (type == CV_64F ? 8 : 4); }
+    size_t elemSize() const { return elemSizeOf(type_); }
     int type() const { return type_; }
+    bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+    bool isContinuous() const { return rows <= 1 || step == (size_t)cols * elemSize(); }
+    Size_<int> size() const { return Size_<int>(cols, rows); }
     template <typename T>
     const T *ptr(int r) const { return (const T *)(data + (size_t)r * step); }
     template <typename T>
     T *ptr(int r) { return (T *)(data + (size_t)r * step); }
+    Mat operator()(const Rect_<int> &r) const {  // ROI view; out-of-range rectangles are an error as in OpenCV
+        if (r.x < 0 || r.y < 0 || r.width < 0 || r.height < 0 || r.x + r.width > cols || r.y + r.height > rows)
+            throw std::runtime_error("cv::Mat ROI out of range");
+        Mat m(*this);
+        m.data = data + (size_t)r.y * step + (size_t)r.x * elemSize();
+        m.rows = r.height;
+        m.cols = r.width;
+        return m;
+    }
+    // dst = saturate_cast<dst type>(src * alpha + beta); only the conversions the path uses
+    void convertTo(Mat &dst, int type, double alpha = 1.0, double beta = 0.0) const {
+        Mat out(rows, cols, type);
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < cols; ++c) {
+                double v = type_ == CV_8U ? (double)ptr<uchar>(r)[c] : type_ == CV_32S ? (double)ptr<int>(r)[c]
+                         : type_ == CV_32F ? (double)ptr<float>(r)[c] : ptr<double>(r)[c];
+                v = v * alpha + beta;
+                if (type == CV_64F) out.ptr<double>(r)[c] = v;
+                else if (type == CV_32F) out.ptr<float>(r)[c] = (float)v;
+                else if (type == CV_32S) out.ptr<int>(r)[c] = (int)std::lrint(v);
+                else { long q = std::lrint(v); out.ptr<uchar>(r)[c] = (uchar)(q < 0 ? 0 : (q > 255 ? 255 : q)); }
+            }
+        dst = out;
+    }
+    Mat &operator=(const MatExpr &e) {
+        Mat out;
+        e.a->convertTo(out, e.a->type(), e.alpha, e.beta);
+        *this = out;
+        return *this;
+    }
 };
+inline MatExpr operator/(const Mat &a, double s) { MatExpr e = {&a, 1.0 / s, 0.0}; return e; }
+inline MatExpr operator-(double c, const MatExpr &e) { MatExpr r = {e.a, -e.alpha, c - e.beta}; return r; }
+inline MatExpr operator-(int c, const MatExpr &e) { return (double)c - e; }
+// A <= s  ->  8-bit mask, 255 where true
+inline Mat operator<=(const Mat &a, double s) {
+    Mat out(a.rows, a.cols, CV_8U);
+    for (int r = 0; r < a.rows; ++r)
+        for (int c = 0; c < a.cols; ++c) out.ptr<uchar>(r)[c] = ((double)a.ptr<int>(r)[c] <= s) ? 255 : 0;
+    return out;
+}
+// cv::normalize(src, dst, alpha, beta, NORM_MINMAX, -1) on 8-bit data: scale = (beta - alpha) / (max - min), 0 when the
+// image is constant (so a constant image becomes all alpha: SURVEY Q7)
+inline void normalize(const Mat &src, Mat &dst, double alpha, double beta, int /*NORM_MINMAX*/, int /*dtype*/) {
+    double mn = 1e300, mx = -1e300;
+    for (int r = 0; r < src.rows; ++r)
+        for (int c = 0; c < src.cols; ++c) {
+            mn = std::min(mn, (double)src.ptr<uchar>(r)[c]);
+            mx = std::max(mx, (double)src.ptr<uchar>(r)[c]);
+        }
+    const double scale = (beta - alpha) * ((mx - mn) > 2.220446049250313e-16 ? 1.0 / (mx - mn) : 0.0);
+    const double shift = alpha - mn * scale;
+    Mat out;
+    src.convertTo(out, CV_8U, scale, shift);
+    dst = out;
+}
+// cv::reduce(src, dst, dim, CV_REDUCE_SUM, CV_32FC1) for 8-bit sources: dim 0 -> one row, dim 1 -> one column
+inline void reduce(const Mat &src, Mat &dst, int dim, int /*rtype*/, int /*dtype*/) {
+    Mat out(dim == 0 ? 1 : src.rows, dim == 0 ? src.cols : 1, CV_32F);
+    for (int r = 0; r < src.rows; ++r)
+        for (int c = 0; c < src.cols; ++c) {
+            if (dim == 0) out.ptr<float>(0)[c] += (float)src.ptr<uchar>(r)[c];
+            else out.ptr<float>(r)[0] += (float)src.ptr<uchar>(r)[c];
+        }
+    dst = out;
+}
+struct NoArray {};
+inline NoArray noArray() { return NoArray(); }
+inline void subtract(const Mat &a, const Mat &b, Mat &dst, const NoArray &, int /*CV_8UC1*/) {  // saturating 8-bit a - b
+    Mat out(a.rows, a.cols, CV_8U);
+    for (int r = 0; r < a.rows; ++r)
+        for (int c = 0; c < a.cols; ++c) {
+            const int d = (int)a.ptr<uchar>(r)[c] - (int)b.ptr<uchar>(r)[c];
+            out.ptr<uchar>(r)[c] = (uchar)(d < 0 ? 0 : d);
+        }
+    dst = out;
+}
+inline double threshold(const Mat &src, Mat &dst, double thresh, double maxval, int /*THRESH_BINARY*/) {
+    Mat out(src.rows, src.cols, CV_8U);
+    for (int r = 0; r < src.rows; ++r)
+        for (int c = 0; c < src.cols; ++c) out.ptr<uchar>(r)[c] = ((double)src.ptr<uchar>(r)[c] > thresh) ? (uchar)maxval : 0;
+    dst = out;
+    return thresh;
+}
+struct Scalar {
+    double v[4];
+    double operator()(int i) const { return v[i]; }
+    double operator[](int i) const { return v[i]; }
+};
+inline Scalar sum(const Mat &m) {
+    Scalar s = {{0, 0, 0, 0}};
+    for (int r = 0; r < m.rows; ++r)
+        for (int c = 0; c < m.cols; ++c) s.v[0] += (double)m.ptr<uchar>(r)[c];
+    return s;
+}
 // cv::LUT for single-channel 8-bit data: dst(i) = lut(src(i))
 inline void LUT(const Mat &src, const Mat &lut, Mat &dst) {
-    Mat out(src.rows, src.cols, 0);
+    Mat out(src.rows, src.cols, CV_8U);
     const uchar *t = lut.ptr<uchar>(0);
     for (int r = 0; r < src.rows; ++r) {
         const uchar *s = src.ptr<uchar>(r);
@@ -140,6 +246,8 @@ inline void LUT(const Mat &src, const Mat &lut, Mat &dst) {
     }
     dst = out;
 }
+template <typename T>
+inline Rect_<T> operator+(const Rect_<T> &r, const Point_<T> &p) { return Rect_<T>(r.x + p.x, r.y + p.y, r.width, r.height); }
 
 // inert persistence stubs: Candidates.cpp's YAML (de)serialisers must compile, they are never called
 class FileNode;

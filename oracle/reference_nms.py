@@ -95,3 +95,46 @@ def imadjust_lut(low_in=0.0, high_in=0.6, low_out=0.0, high_out=1.0):
     lut = np.zeros(256, np.uint8)
     lib().ref_imadjust_lut(float(low_in), float(high_in), float(low_out), float(high_out), lut.ctypes.data)
     return lut
+
+
+def match_views(cb, cs, vel_check, tsize_b, tsize_s, T, I, Iprev, x0, y0b, y0s, hb, hs, width, spre_b, spre_s, spost=None,
+                cap=4096):
+    """The reference's matchingWithVelocityConstraint / xDist / matchViews / checkVelCriterion (LocoMouse_class.cpp:1023-1267)
+    on the arguments matchBottomSideCandidates passes (999-1021): the PADDED crops of the current and the previous calibrated
+    image (cut here from the zero-extended canvas, class.cpp:672-697) and the pre-pads as offsets.
+    cb / cs: lists of (x, y, s) in unpadded-crop coordinates; tsize_* = (cols, rows); crops are `width` x hb / hs at
+    (x0, y0b) / (x0, y0s) of I; spre_* = (x, y) pre-pads.  Returns, per bottom candidate, the list of (y_side, score)."""
+    L = lib()
+    L.ref_match_views.restype = C.c_int
+    spost = spost or (spre_b, spre_s)
+    I, Iprev = np.ascontiguousarray(I, np.uint8), np.ascontiguousarray(Iprev, np.uint8)
+    big = 4 * max(width, hb, hs) + 64
+
+    def crop(img, y0, h, pre, post):
+        canvas = np.zeros((img.shape[0] + 2 * big, img.shape[1] + 2 * big), np.uint8)
+        canvas[big:big + img.shape[0], big:big + img.shape[1]] = img
+        return np.ascontiguousarray(canvas[big + y0 - pre[1]: big + y0 + h + post[1], big + x0 - pre[0]: big + x0 + width + post[0]])
+
+    a = np.array([tuple(c) for c in cb], CAND) if len(cb) else np.zeros(0, CAND)
+    b = np.array([tuple(c) for c in cs], CAND) if len(cs) else np.zeros(0, CAND)
+    Ib, Ibp = crop(I, y0b, hb, spre_b, spost[0]), crop(Iprev, y0b, hb, spre_b, spost[0])
+    It, Itp = crop(I, y0s, hs, spre_s, spost[1]), crop(Iprev, y0s, hs, spre_s, spost[1])
+    mn = np.zeros(max(len(cb), 1), np.int32)
+    my = np.zeros(cap, np.int32)
+    ms = np.zeros(cap, np.float64)
+    rc = L.ref_match_views(C.c_void_p(a.ctypes.data), len(cb), C.c_void_p(b.ctypes.data), len(cs), int(bool(vel_check)),
+                           int(tsize_b[0]), int(tsize_b[1]), int(tsize_s[0]), int(tsize_s[1]), C.c_double(T),
+                           C.c_void_p(Ib.ctypes.data), C.c_void_p(Ibp.ctypes.data), Ib.shape[1], Ib.shape[0],
+                           C.c_void_p(It.ctypes.data), C.c_void_p(Itp.ctypes.data), It.shape[1], It.shape[0],
+                           int(spre_b[0]), int(spre_b[1]), int(spre_s[0]), int(spre_s[1]),
+                           C.c_void_p(mn.ctypes.data), C.c_void_p(my.ctypes.data), C.c_void_p(ms.ctypes.data), cap)
+    if rc < 0:
+        raise RuntimeError("the reference's pairing code threw (CV_Assert / ROI out of range)")
+    n_p22d, total = divmod(rc, 100000)
+    assert n_p22d == len(cb) and total <= cap
+    out, o = [], 0
+    for i in range(len(cb)):
+        m = int(mn[i])
+        out.append([(int(my[o + j]), float(ms[o + j])) for j in range(m)])
+        o += m
+    return out

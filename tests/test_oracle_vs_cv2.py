@@ -245,3 +245,41 @@ def test_velocity_window_primitives():
     s = cv2.subtract(a, b)
     _, t = cv2.threshold(s, 25, 1, cv2.THRESH_BINARY)
     assert s.tolist() == [[26, 0, 25, 26]] and t.tolist() == [[1, 0, 0, 1]]
+
+
+def test_reference_shim_primitives_match_cv2():
+    """oracle/ref_shim/opencv2/core.hpp supplies the few elementwise OpenCV primitives that the reference's pairing code
+    (compiled from /root/reference into oracle/_ref/libref_nms.so) calls.  Each is checked here against the real OpenCV."""
+    import ctypes as C
+
+    from oracle import reference_nms as ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libref_nms.so not built (reference not mounted)")
+    L = ref.lib()
+    L.ref_shim_primitives.restype = None
+    rng = np.random.Generator(np.random.PCG64(2718))
+    for it in range(120):
+        rows, cols, ovlp = int(rng.integers(1, 9)), int(rng.integers(1, 9)), int(rng.integers(1, 20))
+        D = rng.integers(0, 30, (rows, cols)).astype(np.int32)
+        if it % 10 == 0:
+            D[:] = 0           # all true: normalize maps the constant matrix to zeros (SURVEY Q7)
+        if it % 10 == 1:
+            D[:] = 100         # all false
+        r2, c2 = int(rng.integers(1, 20)), int(rng.integers(1, 20))
+        a, b = rng.integers(0, 256, (r2, c2)).astype(np.uint8), rng.integers(0, 256, (r2, c2)).astype(np.uint8)
+        raw, norm = np.zeros((rows, cols), np.uint8), np.zeros((rows, cols), np.uint8)
+        cs, rs, w, cnt = np.zeros(cols, np.float32), np.zeros(rows, np.float32), np.zeros((rows, cols), np.float64), np.zeros(1, np.float64)
+        p = lambda x: C.c_void_p(x.ctypes.data)
+        L.ref_shim_primitives(p(D), rows, cols, ovlp, p(raw), p(norm), p(cs), p(rs), p(w), p(a), p(b), r2, c2, C.c_double(25.0), p(cnt))
+        want_raw = cv2.compare(D, np.full_like(D, ovlp), cv2.CMP_LE)
+        assert np.array_equal(raw, want_raw.reshape(rows, cols))
+        want_norm = cv2.normalize(want_raw, None, 0, 1, cv2.NORM_MINMAX, -1).reshape(rows, cols)
+        assert np.array_equal(norm, want_norm)
+        assert np.array_equal(cs, cv2.reduce(want_norm, 0, cv2.REDUCE_SUM, dtype=cv2.CV_32F).ravel())
+        assert np.array_equal(rs, cv2.reduce(want_norm, 1, cv2.REDUCE_SUM, dtype=cv2.CV_32F).ravel())
+        # 1 - D/ovlp is ONE convertTo(alpha = -(1/ovlp), beta = 1) in OpenCV (MatOp_AddEx); cv2 exposes no f64 convertTo, so the
+        # arithmetic form is stated here: one multiply and one add in double
+        assert np.array_equal(w, D.astype(np.float64) * (-(1.0 / ovlp)) + 1.0)
+        s = cv2.subtract(a, b)
+        _, t = cv2.threshold(s, 25.0, 1, cv2.THRESH_BINARY)
+        assert cnt[0] == cv2.sumElems(t)[0]

@@ -106,3 +106,95 @@ def test_oracle_helpers_match_reference_code(oracle):
         assert np.array_equal(oracle.imadjust_lut(lo, hi, lo_o, hi_o), ref.imadjust_lut(lo, hi, lo_o, hi_o))
     # LocoMouse_TM::readFrame's imadjust(I, I, 0, 0.6, 0, 1) (LocoMouse_TM.cpp:247): 0, 2, 3, 5, 7, 8, 10, 12, ...
     assert ref.imadjust_lut()[:8].tolist() == [0, 2, 3, 5, 7, 8, 10, 12] and ref.imadjust_lut()[153:].min() == 255
+
+
+# ---- pairing stage: matchingWithVelocityConstraint / xDist / matchViews / checkVelCriterion (class.cpp:1023-1267) ---------
+PAIR_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_pairing.npz")
+
+
+def _pair_cases():
+    z = np.load(PAIR_GOLD)
+    for i in range(len([k for k in z.files if k.endswith("_par")])):
+        k = f"c{i:02d}"
+        par = z[f"{k}_par"].tolist()
+        lst = lambda a: [(int(x), int(y), float(s)) for x, y, s in a]
+        want, o = [], 0
+        for n in z[f"{k}_n"].tolist():
+            want.append(list(zip(z[f"{k}_y"][o:o + n].tolist(), z[f"{k}_s"][o:o + n].tolist())))
+            o += n
+        yield dict(tsz=tuple(par[0:4]), org=tuple(par[4:7]), vel=par[7], T=float(z[f"{k}_T"]), I=z[f"{k}_img"][0], Ip=z[f"{k}_img"][1],
+                   cb=lst(z[f"{k}_cb"]), cs=lst(z[f"{k}_cs"]), want=want)
+
+
+def _same_pairs(a, b):
+    if len(a) != len(b):
+        return False
+    for p, q in zip(a, b):
+        if [y for y, _ in p] != [y for y, _ in q]:
+            return False
+        if not np.array_equal(np.array([s for _, s in p], np.float64).view(np.uint64), np.array([s for _, s in q], np.float64).view(np.uint64)):
+            return False
+    return True
+
+
+def test_oracle_pairing_matches_reference_golden(oracle):
+    """The oracle's pairing stage equals the reference's own compiled matchViews code, bit for bit (y, score x weight),
+    on the committed vectors; the vectors exercise the velocity criterion both ways and the all-true boolD quirk (Q7)."""
+    oracle.coverage(reset=True)
+    n = 0
+    for c in _pair_cases():
+        twb, thb, tws, ths = c["tsz"]
+        x0, y0b, y0s = c["org"]
+        got = oracle.match_views(c["cb"], c["cs"], c["vel"], (twb, thb), (tws, ths), c["T"], c["I"], c["Ip"], x0, y0b, y0s)
+        assert _same_pairs(got, c["want"]), f"pairing differs from the reference on case {n}"
+        n += 1
+    cov = oracle.coverage()
+    assert n >= 60 and cov["all_equal_boolD_zeroed"] >= 2 and cov["velocity_rejections"] >= 3 and cov["velocity_accepts"] >= 10
+    assert cov["moving_windows"] >= 5 and cov["side_matches"] >= 100 and cov["bottom_without_match"] >= 20
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libref_nms.so not built (reference not mounted)")
+def test_pairing_golden_is_what_the_reference_code_produces():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_pairing_golden", os.path.join(os.path.dirname(PAIR_GOLD), "make_reference_pairing_golden.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    for c, want in zip(g.cases(), _pair_cases()):
+        assert _same_pairs(g.run_reference(c), want["want"])
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libref_nms.so not built (reference not mounted)")
+def test_oracle_pairing_matches_reference_on_fresh_inputs(oracle):
+    rng = np.random.Generator(np.random.PCG64(31337))
+    nr, nc, W, hb, hs = 120, 200, 80, 50, 40
+    for it in range(200):
+        twb, thb, tws, ths = (int(v) for v in rng.integers(4, 31, 4))
+        x0, y0b, y0s = int(rng.integers(-5, nc - W + 5)), int(rng.integers(30, nr - hb + 5)), int(rng.integers(-3, 30))
+        I = rng.integers(0, 256, (nr, nc)).astype(np.uint8)
+        Ip = I.copy()
+        for _ in range(int(rng.integers(0, 12))):
+            y, x = int(rng.integers(0, nr - 20)), int(rng.integers(0, nc - 20))
+            Ip[y:y + 20, x:x + 20] = rng.integers(0, 60, (20, 20))
+            I[y:y + 20, x:x + 20] = rng.integers(70, 256, (20, 20))
+        nb, ns = int(rng.integers(0, 9)), int(rng.integers(0, 9))
+        cx = rng.integers(0, W, 3)
+        mk = lambda n_, h: [(int(np.clip(cx[rng.integers(0, 3)] + rng.integers(-12, 13), 0, W - 1)), int(rng.integers(0, h)),
+                             float(rng.uniform(0.01, 3))) for _ in range(n_)]
+        cb, cs = mk(nb, hb), mk(ns, hs)
+        T = float(rng.choice([0.7, 0.5, 0.9]))
+        if int(twb * (1 - T)) == 0:
+            T = 0.5
+        vel = int(rng.integers(0, 4) > 0)
+        a = oracle.match_views(cb, cs, vel, (twb, thb), (tws, ths), T, I, Ip, x0, y0b, y0s)
+        b = ref.match_views(cb, cs, vel, (twb, thb), (tws, ths), T, I, Ip, x0, y0b, y0s, hb, hs, W, (15, 15), (15, 15))
+        assert _same_pairs(a, b), f"pairing, input {it}"
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libref_nms.so not built (reference not mounted)")
+def test_reference_pairing_throws_when_overlap_is_zero():
+    """ovlp == 0 (T close to 1) divides by zero; the weights become NaN and Candidates.cpp's CV_Assert(S >= 0)
+    fires for a second side candidate.  The path is undefined there; the ABI rejects such a configuration."""
+    I = np.zeros((40, 60), np.uint8)
+    with pytest.raises(RuntimeError):
+        ref.match_views([(10, 5, 1.0), (30, 5, 1.0)], [(10, 4, 1.0), (10, 9, 1.0)], 0, (4, 4), (4, 4), 0.9, I, I, 0, 20, 0, 20, 20, 60,
+                        (15, 15), (15, 15))

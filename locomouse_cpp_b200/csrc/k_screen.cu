@@ -558,9 +558,9 @@ bool lm_screen_build(const float *w, int kh, int kw, float init, int halo_x, int
     return true;
 }
 
-bool lm_screen_build2(const float *w, int kh, int kw, float init, int dx, int dy, int KH, int ks, int digits, LmScreenHost *out,
-                      std::vector<int8_t> *img) {
-    if (dx < 0 || dy < 0 || dy + kh > KH || SCR_TILE_X - 1 + dx + kw > 32 * ks) return false;
+bool lm_screen_build_plane(const float *w, int kh, int kw, float init, int dx, int dy, int KH, int ks, int digit, int plane, int nplanes,
+                           LmScreenHost *out, std::vector<int8_t> *img) {
+    if (dx < 0 || dy < 0 || dy + kh > KH || SCR_TILE_X - 1 + dx + kw > 32 * ks || plane < 0 || plane >= nplanes) return false;
     std::vector<int> vq;
     if (!screen_quantize(w, kh * kw, init, &vq, out)) return false;
     out->kh = KH;
@@ -568,10 +568,9 @@ bool lm_screen_build2(const float *w, int kh, int kw, float init, int dx, int dy
     out->dx = dx;
     out->dy = dy;
     out->rows = (SCR_TILE_M + KH - 1 + 7) & ~7;
-    const int nhalf = digits < 0 ? 64 : 32;
     const int npanel = 2 * ks;
-    const size_t chunk = (size_t)nhalf * 16;
-    img->assign((size_t)KH * npanel * chunk, 0);
+    const size_t chunk = (size_t)nplanes * 32 * 16;
+    if (img->size() != (size_t)KH * npanel * chunk) return false;
     for (int jj = 0; jj < kh; ++jj)
         for (int c = 0; c < SCR_TILE_X; ++c)
             for (int i = 0; i < kw; ++i) {
@@ -579,12 +578,7 @@ bool lm_screen_build2(const float *w, int kh, int kw, float init, int dx, int dy
                 int hi8, lo8;
                 split_digits(vq[jj * kw + i], &hi8, &lo8);
                 const size_t base = (size_t)(jj + dy) * npanel * chunk + (size_t)(k >> 4) * chunk + (size_t)(k & 15);
-                if (digits < 0) {
-                    (*img)[base + (size_t)c * 16] = (int8_t)hi8;
-                    (*img)[base + (size_t)(c + 32) * 16] = (int8_t)lo8;
-                } else {
-                    (*img)[base + (size_t)c * 16] = (int8_t)(digits == 0 ? hi8 : lo8);
-                }
+                (*img)[base + (size_t)(plane * 32 + c) * 16] = (int8_t)(digit == 0 ? hi8 : lo8);
             }
     return true;
 }

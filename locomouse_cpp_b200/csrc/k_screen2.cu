@@ -5,9 +5,16 @@
 // resident (120 kB), i.e. N = 64.  A CTA pair executes one M = 256 instruction: each CTA streams its own 128
 // window rows (its own y tile of the same frame / x tile) and only HALF of B, so N doubles at the same
 // per-SM operand traffic:
-//   paw + snout job : N = 128 = [paw hi | paw lo | snout hi | snout lo] x 32 columns; the paw images live in
-//                     CTA 0's shared memory, the snout images in CTA 1's.
-//   tail job        : N = 64  = [hi | lo] x 32 columns; hi digits in CTA 0, lo digits in CTA 1.
+//   paw + snout + tail job : N = 192 = 32 columns x [paw hi | paw lo | tail hi || snout hi | snout lo | tail lo]; the first
+//                            three planes live in CTA 0's shared memory, the others in CTA 1's.  x tiles right of the tail
+//                            box issue the same operands with N = 128 (each CTA's first two planes).
+//   paw + snout job        : N = 128 (templates whose sizes differ too much to share kernel-row steps with the tail)
+//   one-template job       : N = 64  = [hi || lo]; hi digits in CTA 0, lo digits in CTA 1.
+// An instruction costs ~max(93, 42 + N/2) cycles whatever it computes (operand streaming), so wide N is what pays.
+// y tiles: either whole 256-row tile pairs per frame, or -- when that wastes more (side view: 150 of 256 rows) --
+// "stacked": the sub-batch's windows, contiguous in memory at the window pitch, are treated as one tall image and cut
+// into 256-row tile pairs (179-row windows: 84 % useful rows instead of 59 %); a tile may straddle two frames, each
+// accumulator row maps back to (frame, y) and rows in the inter-frame halo are dropped.
 // Everything else (exact int8 arithmetic, thresholds, 4x8 patch tasks for k_corr_sparse) is k_screen.cu's.
 //
 // Pair protocol: window-tile "full" and accumulator "empty" barriers live in the leader CTA (rank 0) and
@@ -25,12 +32,15 @@ constexpr int S2_THREADS = 224;   // warps 0-3 epilogue, 4-5 loaders, 6 MMA issu
 constexpr int S2_TILE_M = 128;
 constexpr int S2_TILE_X = 32;
 constexpr int S2_STAGES = 4;      // maximum ring depth; a job uses J.j.stages of them
-constexpr int S2_TMEM_COLS = 256; // two accumulators of up to 128 columns
+constexpr int S2_TMEM_COLS = 512; // two accumulators of up to 256 columns
+constexpr int S2_ACC_STRIDE = 256;
 
 struct Screen2JobDev {
     LmScreen2Job j;
-    int out_w, out_h;
-    int nxt, nytp;            // x tiles, y-tile PAIRS
+    int out_h, out_w[3];
+    int nxt;                  // x tiles
+    int ntp;                  // 256-row tile pairs over the whole sub-batch
+    int VH;                   // rows between consecutive frames in tile-row space (window height when stacked)
     int pair_begin, npair;
     int halo_x, halo_y;
 };
@@ -68,9 +78,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
     const uint32_t b_bytes = (uint32_t)KH * npanel * chunk_b;
     uint8_t *sB = smem;
     uint8_t *sA = smem + b_bytes;
-    const int units_per_frame = J.nxt * J.nytp;
-    const int nunits = P.B * units_per_frame;
-    const int N = 2 * nhalf;  // UMMA N
+    const int nunits = J.ntp * J.nxt;
+    const int VH = J.VH;
 
     const uint32_t bar0 = smem_u32(bars);
     auto a_full = [&](int s) { return bar0 + 8u * s; };                       // leader's copy is used
@@ -115,10 +124,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
         int stage = 0;
         uint32_t phase = 0;
         for (int u = prank; u < nunits; u += J.npair) {
-            const int f = u / units_per_frame, rem = u - f * units_per_frame;
-            const int ytp = rem / J.nxt, xt = rem - ytp * J.nxt;
-            const int y0 = (2 * ytp + (int)rank) * S2_TILE_M, x0 = xt * S2_TILE_X;
-            const uint8_t *wbase = P.win[v] + (int64_t)f * P.win_stride[v];
+            const int tp = u / J.nxt, xt = u - tp * J.nxt;
+            const int R0 = (2 * tp + (int)rank) * S2_TILE_M, x0 = xt * S2_TILE_X;  // first tile row in tile-row space
+            const int f0 = R0 / VH, yf0 = R0 - f0 * VH;
+            const uint8_t *wbase = P.win[v];
             mbar_wait(a_empty(stage), phase ^ 1u);
             uint8_t *dstA = sA + (uint32_t)stage * stage_bytes;
             constexpr int UNR = 5;
@@ -130,8 +139,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
                     int4 x = make_int4(0, 0, 0, 0);
                     if (idx < nchunks) {
                         const int r = idx / npanel, p = idx - r * npanel;
-                        const int wr = y0 + r, wc = x0 + 16 * p;
-                        if (wr < win_h && wc + 16 <= pitch) x = __ldg(reinterpret_cast<const int4 *>(wbase + (int64_t)wr * pitch + wc));
+                        int f = f0, wr = yf0 + r;   // a tile spans at most a few frames
+                        while (wr >= VH) {
+                            wr -= VH;
+                            ++f;
+                        }
+                        const int wc = x0 + 16 * p;
+                        if (f < P.B && wr < win_h && wc + 16 <= pitch)
+                            x = __ldg(reinterpret_cast<const int4 *>(wbase + (int64_t)f * P.win_stride[v] + (int64_t)wr * pitch + wc));
                     }
                     val[q] = x;
                 }
@@ -154,19 +169,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
     } else if (warp == 6) {
         // ================= MMA issuer (leader CTA only) =============================================================
         if (rank == 0) {
-            // u8 x s8 -> s32, K-major operands, M = 256 across the pair, N = 2 * nhalf
-            const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            // u8 x s8 -> s32, K-major operands, M = 256 across the pair; N = 2 * nhalf, or 2 * nhalf_narrow right of the tail box
+            const uint32_t idesc_base = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(256 >> 4) << 24);
+            const uint32_t idesc_wide = idesc_base | ((uint32_t)((2 * nhalf) >> 3) << 17);
+            const uint32_t idesc_narrow = idesc_base | ((uint32_t)((2 * J.j.nhalf_narrow) >> 3) << 17);
             const uint64_t bdesc0 = umma_desc(smem_u32(sB), chunk_b);
             const uint32_t a_step = (2u * panel_a) >> 4, b_step = (2u * chunk_b) >> 4;
             const uint32_t b_row = ((uint32_t)npanel * chunk_b) >> 4;
             int stage = 0, acc = 0;
             uint32_t phase = 0, accphase = 0;
             for (int u = prank; u < nunits; u += J.npair) {
+                const int xt = u % J.nxt;
+                const uint32_t idesc = (xt * S2_TILE_X >= J.j.narrow_x0) ? idesc_narrow : idesc_wide;
                 mbar_wait(d_empty(acc), accphase ^ 1u);
                 mbar_wait(a_full(stage), phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
-                    const uint32_t d = tmem + (uint32_t)acc * 128u;
+                    const uint32_t d = tmem + (uint32_t)acc * (uint32_t)S2_ACC_STRIDE;
                     uint64_t adesc = umma_desc(smem_u32(sA) + (uint32_t)stage * stage_bytes, panel_a);
                     uint64_t bdesc = bdesc0;
                     uint32_t accum = 0;
@@ -202,20 +221,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
         int acc = 0;
         uint32_t accphase = 0;
         for (int u = prank; u < nunits; u += J.npair) {
-            const int f = u / units_per_frame, rem = u - f * units_per_frame;
-            const int ytp = rem / J.nxt, xt = rem - ytp * J.nxt;
-            const int y = (2 * ytp + (int)rank) * S2_TILE_M + tid, x0 = xt * S2_TILE_X;
+            const int tp = u / J.nxt, xt = u - tp * J.nxt;
+            const int R = (2 * tp + (int)rank) * S2_TILE_M + tid, x0 = xt * S2_TILE_X;
+            const int f = R / VH, y = R - f * VH;   // VH % 4 == 0: the four rows of a patch share f and y >> 2
+            const int nar = x0 >= J.j.narrow_x0 ? 1 : 0;
+            const int nt = nar ? J.j.ntmpl_narrow : J.j.ntmpl;
             mbar_wait(d_full(acc), accphase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)acc * 128u;
-            const bool rowok = y < J.out_h;
-            const int wvalid = J.out_w - x0;
-            const uint32_t colmask = wvalid >= 32 ? 0xffffffffu : (wvalid <= 0 ? 0u : ((1u << wvalid) - 1u));
-            uint32_t need_t[2] = {0u, 0u}, sign0 = 0u;
-            for (int t = 0; t < J.j.ntmpl; ++t) {
+            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)acc * (uint32_t)S2_ACC_STRIDE;
+            const bool rowok = f < P.B && y < J.out_h;
+            uint32_t need_t[3] = {0u, 0u, 0u}, sign_t[3] = {0u, 0u, 0u};
+            for (int t = 0; t < nt; ++t) {
                 uint32_t hi[32], lo[32];
-                tmem_ld32(ta + (uint32_t)t * 64u, hi);
-                tmem_ld32(ta + (uint32_t)t * 64u + 32u, lo);
+                tmem_ld32(ta + (uint32_t)J.j.col_hi[nar][t], hi);
+                tmem_ld32(ta + (uint32_t)J.j.col_lo[nar][t], lo);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 const long long t_lo = J.j.t_lo[t], t_hi = J.j.t_hi[t];
                 uint32_t need = 0, sign = 0;
@@ -225,8 +244,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
                     if (V > t_lo) need |= 1u << c;
                     if (V > t_hi) sign |= 1u << c;
                 }
+                const int wvalid = J.out_w[t] - x0;
+                const uint32_t colmask = wvalid >= 32 ? 0xffffffffu : (wvalid <= 0 ? 0u : ((1u << wvalid) - 1u));
                 need_t[t] = rowok ? (need & colmask) : 0u;
-                if (t == 0) sign0 = sign;
+                sign_t[t] = sign;
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive_cluster(d_empty(acc), 0);  // the leader's barrier counts both CTAs' epilogues
@@ -234,10 +255,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
                 acc = 0;
                 accphase ^= 1u;
             }
-            for (int t = 0; t < J.j.ntmpl; ++t) {
+            for (int t = 0; t < nt; ++t) {
                 uint32_t need = need_t[t];
-                if (J.j.is_tail) {
+                if (J.j.feat[t] == LM_TAIL) {
+                    if (x0 >= J.out_w[t]) continue;  // warp-uniform: no tail columns in this x tile
                     if (rowok) {
+                        const uint32_t sign0 = sign_t[t];
                         uint8_t *tb = P.tailbin[v] + (int64_t)f * P.tailbin_stride[v] + (int64_t)y * P.tail_pitch + x0;
                         uint32_t w[8];
 #pragma unroll
@@ -248,7 +271,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
                         reinterpret_cast<uint4 *>(tb)[0] = make_uint4(w[0], w[1], w[2], w[3]);
                         reinterpret_cast<uint4 *>(tb)[1] = make_uint4(w[4], w[5], w[6], w[7]);
                     }
-                    need &= ~sign0;
+                    need &= ~sign_t[t];
                 } else if (need) {
                     const uint8_t *crow = P.win[v] + (int64_t)f * P.win_stride[v] + (int64_t)(y + J.halo_y) * pitch + x0 + J.halo_x;
                     uint32_t m = need;
@@ -306,28 +329,35 @@ size_t lm_screen2_smem_bytes(int KH, int ks, int rows, int nhalf, int stages) {
     return (size_t)KH * 2 * ks * nhalf * 16 + (size_t)stages * 2 * ks * rows * 16;
 }
 
-// Launches k_screen2 for the four pair-level jobs; the caller has zeroed the task counters.
+// Launches k_screen2 for the pair-level jobs; the caller has zeroed the task counters.
 int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s) {
     const int n_sm = lm_sm_count();
     const int npairs_total = n_sm / 2;
     Screen2Params P{};
     size_t smem = 0;
     double work[6], total = 0.0;
+    auto icost = [](int N) { return std::max(93.0, 42.0 + N / 2.0); };  // cycles per instruction (tools/umma_sw_probe.cu)
     for (int v = 0; v < 2; ++v)
         for (int q = 0; q < 3; ++q) {
             const LmScreen2Job &sj = b.scr.job2[v][q];
             if (!sj.Bimg[0]) continue;  // no tail box
             Screen2JobDev &J = P.job[P.njobs];
             J.j = sj;
-            J.out_w = sj.is_tail ? b.tail_w : b.view[v].box_w;
+            int ow = 0;
+            for (int t = 0; t < sj.ntmpl; ++t) {
+                J.out_w[t] = sj.feat[t] == LM_TAIL ? b.tail_w : b.view[v].box_w;
+                ow = std::max(ow, J.out_w[t]);
+            }
             J.out_h = b.view[v].box_h;
-            J.nxt = (J.out_w + S2_TILE_X - 1) / S2_TILE_X;
-            const int nyt = (J.out_h + S2_TILE_M - 1) / S2_TILE_M;
-            J.nytp = (nyt + 1) / 2;
+            J.nxt = (ow + S2_TILE_X - 1) / S2_TILE_X;
+            const int nytp = ((J.out_h + S2_TILE_M - 1) / S2_TILE_M + 1) / 2;
+            J.VH = sj.stacked ? b.view[v].win_h : 2 * S2_TILE_M * nytp;
+            J.ntp = (int)(((int64_t)b.B * J.VH + 2 * S2_TILE_M - 1) / (2 * S2_TILE_M));
             J.halo_x = b.view[v].halo_x;
             J.halo_y = b.view[v].halo_y;
-            // per-instruction cost ~ max(93, 42 + N/2) cycles (tools/umma_sw_probe.cu)
-            work[P.njobs] = (double)J.nxt * J.nytp * sj.KH * sj.ks * (sj.nhalf >= 64 ? 106.0 : 93.0);
+            int n_narrow = 0;
+            for (int xt = 0; xt < J.nxt; ++xt) n_narrow += (xt * S2_TILE_X >= sj.narrow_x0);
+            work[P.njobs] = (double)J.ntp * sj.KH * sj.ks * ((J.nxt - n_narrow) * icost(2 * sj.nhalf) + n_narrow * icost(2 * sj.nhalf_narrow));
             total += work[P.njobs];
             smem = std::max(smem, lm_screen2_smem_bytes(sj.KH, sj.ks, sj.rows, sj.nhalf, sj.stages));
             ++P.njobs;

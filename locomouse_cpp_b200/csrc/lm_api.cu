@@ -2,6 +2,7 @@
 // pipeline (H2D of sub-batch k+1 overlaps the kernels of sub-batch k; results return through pinned
 // staging), timing and debug fetches.  No CPU fallback: every entry point needs a CUDA device.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -30,6 +31,7 @@ struct lm_ctx {
     std::vector<float> h_tmpl[2][3];  // host copies (the screen's quantisation is derived from them)
     int opt_screen = 2;               // 0: dense exact kernel only, 1: tensor-core screen, one CTA per tile, 2: CTA pairs
     int opt_subbatch = 512;
+    int opt_screen_layout = 3;        // k_screen2 job layout: bit 0 = tail shares the paw + snout job (N = 192), bit 1 = stacked y tiles
     int opt_streams = 2;              // 2: consecutive sub-batches overlap on two streams, 1: strictly serial kernels
     LmScreenHost scr_info[2][3] = {};
     int t_rows[2][3] = {}, t_cols[2][3] = {};
@@ -186,10 +188,17 @@ int prepare_screen(lm_ctx *ctx, LmBatch &b, int want, size_t B) {
             H.dy = b.view[v].halo_y - T.ay;
             if (H.dx < 0 || H.dy < 0) return LM_OK;
         }
-    // 2a. CTA-pair jobs
+    // 2a. CTA-pair jobs.  A spec lists, per CTA rank, the planes (template slot, digit) of its B image.
     struct Spec {
-        int f[2], ntmpl, is_tail, digit_split, KH, ks, rows, nhalf, stages;
+        int ntmpl, f[3];
+        int nplanes;                 // planes per rank (nhalf = 32 * nplanes)
+        int pl_t[2][3], pl_d[2][3];  // [rank][plane]: template slot, digit (0 hi / 1 lo)
+        int narrow;                  // 1: the tail planes are last and x tiles right of the tail box skip them
+        int KH, ks, rows, stages;
     };
+    const Spec SPEC_PST{3, {LM_PAW, LM_SNOUT, LM_TAIL}, 3, {{0, 0, 2}, {1, 1, 2}}, {{0, 1, 0}, {0, 1, 1}}, 1, 0, 0, 0, 0};
+    const Spec SPEC_PS{2, {LM_PAW, LM_SNOUT, 0}, 2, {{0, 0, 0}, {1, 1, 0}}, {{0, 1, 0}, {0, 1, 0}}, 0, 0, 0, 0, 0};
+    auto single = [](int f) { return Spec{1, {f, 0, 0}, 1, {{0, 0, 0}, {0, 0, 0}}, {{0, 0, 0}, {1, 0, 0}}, 0, 0, 0, 0, 0}; };
     Spec spec[2][3] = {};
     std::vector<int8_t> img2[2][3][2];
     bool have2 = want >= 2;
@@ -202,36 +211,52 @@ int prepare_screen(lm_ctx *ctx, LmBatch &b, int want, size_t B) {
             S.ks = std::max(S.ks, (31 + H.dx + b.tmpl[v][S.f[t]].kw + 31) / 32);
         }
         S.rows = (128 + S.KH - 1 + 7) & ~7;
-        S.nhalf = S.digit_split ? 32 : 64;
         for (S.stages = 4; S.stages >= 2; --S.stages)
-            if (lm_screen2_smem_bytes(S.KH, S.ks, S.rows, S.nhalf, S.stages) <= smem_limit) return true;
+            if (lm_screen2_smem_bytes(S.KH, S.ks, S.rows, 32 * S.nplanes, S.stages) <= smem_limit) return true;
         return false;
     };
+    // issue cost of one tile in units of MMA cycles: KH * ks instructions of ~max(93, 42 + N/2) cycles (tools/umma_sw_probe.cu)
+    auto icost = [](int N) { return std::max(93.0, 42.0 + N / 2.0); };
+    const int nxt_box = (k.bb_w + 31) / 32, nxt_tail = (k.tail_w + 31) / 32;
     for (int v = 0; v < 2 && have2; ++v) {
-        Spec ps{{LM_PAW, LM_SNOUT}, 2, 0, 0, 0, 0, 0, 0, 0};
-        if (fit(ps, v)) {
-            spec[v][0] = ps;
-        } else {  // one template per job, hi digits in CTA 0, lo digits in CTA 1
-            Spec p1{{LM_PAW, LM_PAW}, 1, 0, 1, 0, 0, 0, 0, 0}, s1{{LM_SNOUT, LM_SNOUT}, 1, 0, 1, 0, 0, 0, 0, 0};
-            if (!fit(p1, v) || !fit(s1, v)) have2 = false;
-            spec[v][0] = p1;
-            spec[v][2] = s1;
+        Spec ps = SPEC_PS, pst = SPEC_PST, tl = single(LM_TAIL);
+        const bool ok_ps = fit(ps, v);
+        const bool ok_tl = nfeat == 3 && fit(tl, v);
+        bool merged = false;
+        if (nfeat == 3 && (ctx->opt_screen_layout & 1) && ok_ps && ok_tl && fit(pst, v)) {
+            const double sep = (double)nxt_box * ps.KH * ps.ks * icost(128) + (double)nxt_tail * tl.KH * tl.ks * icost(64);
+            const double mrg = (double)pst.KH * pst.ks * (nxt_tail * icost(192) + std::max(0, nxt_box - nxt_tail) * icost(128));
+            merged = mrg < sep;
         }
-        if (nfeat == 3) {
-            Spec tl{{LM_TAIL, LM_TAIL}, 1, 1, 1, 0, 0, 0, 0, 0};
-            if (!fit(tl, v)) have2 = false;
-            spec[v][1] = tl;
+        if (merged) {
+            spec[v][0] = pst;
+        } else {
+            if (ok_ps) {
+                spec[v][0] = ps;
+            } else {  // one template per job, hi digits in CTA 0, lo digits in CTA 1
+                Spec p1 = single(LM_PAW), s1 = single(LM_SNOUT);
+                if (!fit(p1, v) || !fit(s1, v)) have2 = false;
+                spec[v][0] = p1;
+                spec[v][2] = s1;
+            }
+            if (nfeat == 3) {
+                if (!ok_tl) have2 = false;
+                spec[v][1] = tl;
+            }
         }
         for (int q = 0; q < 3 && have2; ++q) {
             const Spec &S = spec[v][q];
             if (!S.ntmpl) continue;
             for (int r = 0; r < 2 && have2; ++r) {
-                const int f = S.digit_split ? S.f[0] : S.f[r];
-                const LmScreenHost &H = ctx->scr_info[v][f];
-                LmScreenHost tmp{};
-                have2 = lm_screen_build2(ctx->h_tmpl[v][f].data(), b.tmpl[v][f].kh, b.tmpl[v][f].kw, b.tmpl[v][f].init, H.dx, H.dy, S.KH,
-                                         S.ks, S.digit_split ? r : -1, &tmp, &img2[v][q][r]);
-                if (have2 && (tmp.t_lo != H.t_lo || tmp.t_hi != H.t_hi)) have2 = false;
+                img2[v][q][r].assign((size_t)S.KH * 2 * S.ks * S.nplanes * 512, 0);
+                for (int g = 0; g < S.nplanes && have2; ++g) {
+                    const int f = S.f[S.pl_t[r][g]];
+                    const LmScreenHost &H = ctx->scr_info[v][f];
+                    LmScreenHost tmp{};
+                    have2 = lm_screen_build_plane(ctx->h_tmpl[v][f].data(), b.tmpl[v][f].kh, b.tmpl[v][f].kw, b.tmpl[v][f].init, H.dx, H.dy,
+                                                  S.KH, S.ks, S.pl_d[r][g], g, S.nplanes, &tmp, &img2[v][q][r]);
+                    if (have2 && (tmp.t_lo != H.t_lo || tmp.t_hi != H.t_hi)) have2 = false;
+                }
             }
         }
     }
@@ -291,15 +316,30 @@ int prepare_screen(lm_ctx *ctx, LmBatch &b, int want, size_t B) {
                     J2.Bimg[r] = dimg;
                 }
                 J2.view = v;
-                J2.is_tail = S.is_tail;
                 J2.ntmpl = S.ntmpl;
                 J2.KH = S.KH;
                 J2.ks = S.ks;
                 J2.rows = S.rows;
-                J2.nhalf = S.nhalf;
+                J2.nhalf = 32 * S.nplanes;
                 J2.stages = S.stages;
+                // narrow instruction: without the trailing tail planes, for x tiles right of the tail box
+                J2.nhalf_narrow = S.narrow ? 32 * (S.nplanes - 1) : J2.nhalf;
+                J2.narrow_x0 = S.narrow ? ((k.tail_w + 31) / 32) * 32 : INT_MAX;
+                J2.ntmpl_narrow = S.narrow ? S.ntmpl - 1 : S.ntmpl;
+                for (int r = 0; r < 2; ++r)
+                    for (int g = 0; g < S.nplanes; ++g) {
+                        const int t = S.pl_t[r][g];
+                        (S.pl_d[r][g] ? J2.col_lo : J2.col_hi)[0][t] = r * J2.nhalf + 32 * g;
+                        (S.pl_d[r][g] ? J2.col_lo : J2.col_hi)[1][t] = r * J2.nhalf_narrow + 32 * g;
+                    }
+                // stacked y tiles when the window height wastes less of a 256-row tile pair than whole tiles per frame do
+                {
+                    const int nytp = ((b.bb_h[v] + 127) / 128 + 1) / 2;
+                    J2.stacked = (ctx->opt_screen_layout & 2) && (b.view[v].win_h % 4 == 0) && b.view[v].win_h < 256 * nytp;
+                }
                 for (int t = 0; t < S.ntmpl; ++t) {
                     const int f = S.f[t];
+                    J2.feat[t] = f;
                     J2.t_lo[t] = b.scr.job[v][f].t_lo;
                     J2.t_hi[t] = b.scr.job[v][f].t_hi;
                     J2.tasks[t] = b.scr.job[v][f].tasks;
@@ -362,7 +402,7 @@ int prepare(lm_ctx *ctx) {
         V.halo_x = hx;
         V.halo_y = hy;
         V.win_w = V.box_w + hx + px;
-        V.win_h = V.box_h + hy + py;
+        V.win_h = (V.box_h + hy + py + 3) & ~3;  // multiple of 4: stacked y tiles of k_screen2 keep 4-row patches inside one frame
         V.win_pitch = (V.win_w + 15) & ~15;
         V.win_stride = (int64_t)V.win_pitch * V.win_h;
     }
@@ -825,6 +865,9 @@ int lm_set_option(lm_ctx *ctx, const char *name, int64_t value) {
     if (!strcmp(name, "screen")) {
         if (value < 0 || value > 2) return fail(ctx, LM_ERR_INVALID, "option screen must be 0, 1 or 2");
         ctx->opt_screen = (int)value;
+    } else if (!strcmp(name, "screen_layout")) {
+        if (value < 0 || value > 3) return fail(ctx, LM_ERR_INVALID, "option screen_layout must be in [0, 3]");
+        ctx->opt_screen_layout = (int)value;
     } else if (!strcmp(name, "streams")) {
         if (value != 1 && value != 2) return fail(ctx, LM_ERR_INVALID, "option streams must be 1 or 2");
         ctx->opt_streams = (int)value;
@@ -858,6 +901,15 @@ int lm_get_info(const lm_ctx *ctx, const char *name, double *value) {
         float t = -1.f;
         if (cudaEventElapsedTime(&t, ctx->ev_call[0], ctx->ev_stage[name[8] - '0'][name[10] - '0']) != cudaSuccess) t = -1.f;
         *value = (double)t;
+        return LM_OK;
+    }
+    if (!strcmp(name, "screen2_merged") || !strcmp(name, "screen2_stacked")) {  // bit v: view v's pair job shares the tail / is stacked
+        int m = 0;
+        for (int v = 0; v < 2; ++v) {
+            const LmScreen2Job &J = ctx->bt.scr.job2[v][0];
+            if (ctx->Bcap && ctx->bt.scr.enabled == 2 && J.Bimg[0] && (name[8] == 'm' ? J.ntmpl == 3 : J.stacked)) m |= 1 << v;
+        }
+        *value = (double)m;
         return LM_OK;
     }
     if (!strcmp(name, "ms_screen")) {  // device time of k_screen alone in the last lm_detect_batch call

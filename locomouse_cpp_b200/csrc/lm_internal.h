@@ -56,21 +56,32 @@ struct LmScreenJob {
     uint32_t *tasks;      // device, [task_cap]: frame << 14 | patch_row << 7 | patch_col
     int task_cap;
 };
-// CTA-pair variant (k_screen2.cu): per view one paw+snout job (N = 128) and one tail job (N = 64).
+// CTA-pair variant (k_screen2.cu).  A job decides up to three templates of one view with one resident B operand per
+// CTA: B rows are 32-row "planes" (one weight digit of one template for the tile's 32 output columns); CTA rank r holds
+// nhalf / 32 planes, and plane g of rank r lands in accumulator columns 32 * (r * nhalf / 32 + g).
+//   paw + snout + tail (N = 192): rank 0 = [paw hi | paw lo | tail hi], rank 1 = [snout hi | snout lo | tail lo];
+//                                 x tiles right of the tail box use only the first nhalf_narrow = 64 rows (N = 128)
+//   paw + snout        (N = 128): rank 0 = [paw hi | paw lo], rank 1 = [snout hi | snout lo]
+//   one template       (N = 64) : rank 0 = [hi], rank 1 = [lo]   (tail alone, or templates too large to share)
 struct LmScreen2Job {
     const int8_t *Bimg[2];  // device, per CTA rank: [KH][2*ks chunks][nhalf rows][16 B]
-    int view, is_tail, ntmpl;
-    int KH, ks, rows, nhalf;
+    int view, ntmpl;
+    int feat[3];            // LM_PAW / LM_SNOUT / LM_TAIL of template slot t
+    int KH, ks, rows, nhalf, nhalf_narrow;
+    int narrow_x0;          // x tiles starting at or right of this column run the narrow instruction (INT_MAX: never)
+    int ntmpl_narrow;       // template slots decided by the narrow instruction (the leading ones)
+    int col_hi[2][3], col_lo[2][3];  // accumulator column of the hi / lo plane of slot t, [0] wide, [1] narrow
     int stages;             // window-tile ring depth that fits next to the resident B operand (2..4)
-    long long t_lo[2], t_hi[2];   // per template decided by this job (paw, snout | tail)
-    uint32_t *tasks[2];
-    int task_cap[2];
-    int *ntasks[2];
+    int stacked;            // 1: y tiles run over the frames of the sub-batch stacked at the window pitch
+    long long t_lo[3], t_hi[3];   // per template decided by this job
+    uint32_t *tasks[3];
+    int task_cap[3];
+    int *ntasks[3];
 };
 struct LmScreen {
     int enabled;          // 0: dense exact kernel, 1: k_screen (one CTA per tile), 2: k_screen2 (CTA pairs)
     LmScreenJob job[2][3];
-    LmScreen2Job job2[2][3];  // [view][0 = paw + snout (or paw alone), 1 = tail, 2 = snout alone]; unused: Bimg[0] == null
+    LmScreen2Job job2[2][3];  // [view][0 = paw + snout (+ tail) (or paw alone), 1 = tail, 2 = snout alone]; unused: Bimg[0] == null
     int *ntasks;          // device, [6] = [view][feat]
 };
 
@@ -139,11 +150,12 @@ struct LmScreenHost {
 bool lm_screen_build(const float *w, int kh, int kw, float init, int halo_x, int halo_y, int fma_mode,
                      LmScreenHost *out, std::vector<int8_t> *img);
 size_t lm_screen_smem_bytes(int kh, int ks, int rows, int stages);
-// CTA-pair variant: image of one template in the common geometry of its job (KH kernel-row steps, ks K steps, the
-// template's own row offset dy folded in as leading zero rows).  digits: -1 = rows [0,32) hi + [32,64) lo,
-// 0 = hi only (32 rows), 1 = lo only (32 rows).  Thresholds / scale / eps as lm_screen_build.
-bool lm_screen_build2(const float *w, int kh, int kw, float init, int dx, int dy, int KH, int ks, int digits,
-                      LmScreenHost *out, std::vector<int8_t> *img);
+// CTA-pair variant: writes ONE plane (32 rows: one weight digit, 0 = hi / 1 = lo, of one template) of a rank's B image
+// in the common geometry of its job (KH kernel-row steps, ks K steps, nplanes planes per rank; the template's own row
+// offset dy folded in as leading zero rows).  `img` must hold KH * 2 * ks * nplanes * 512 bytes, zero initialised.
+// Thresholds / scale / eps as lm_screen_build.
+bool lm_screen_build_plane(const float *w, int kh, int kw, float init, int dx, int dy, int KH, int ks, int digit, int plane,
+                           int nplanes, LmScreenHost *out, std::vector<int8_t> *img);
 size_t lm_screen2_smem_bytes(int KH, int ks, int rows, int nhalf, int stages);
 // thresholds / scale / eps of one template (no image); false for non-finite weights
 bool lm_screen_quantize(const float *w, int kh, int kw, float init, LmScreenHost *out);

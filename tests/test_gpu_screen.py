@@ -126,3 +126,28 @@ def test_screen_config5_upsampled_60x60(oracle):
     assert diff_results(pair, off) == []
     ref = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=8)
     assert diff_results(pair, ref) == []
+
+
+@pytest.mark.parametrize("kw,n,sub", [(dict(), 40, 16), (dict(method="TM_DE", flip=True), 9, 4),
+                                      (dict(tshapes=(((30, 30), (24, 28), (20, 16)), ((27, 30), (30, 22), (15, 17)))), 7, 3)])
+def test_screen2_job_layouts_are_equivalent(oracle, kw, n, sub):
+    """k_screen2's job layouts -- tail planes sharing the paw + snout operand (N = 192, N = 128 right of the tail box) and
+    y tiles stacked over the frames of a sub-batch (tiles straddle frames; ragged last tile) -- never change a result:
+    all four combinations equal the oracle bit for bit."""
+    from locomouse_cpp_b200.api import Detector
+
+    cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(synth.SynthSpec(**kw), n, seed=1003)
+    frames = frames.numpy()
+    ref = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=8)
+    seen = set()
+    for layout in (3, 2, 1, 0):
+        det = Detector(cfg, model, bkg, calib, device=0)
+        det.set_option("screen", 2)
+        det.set_option("screen_layout", layout)
+        det.set_option("subbatch", sub)
+        got = det.detect_batch(frames, bx, bs, bb)
+        assert det.info("screen_active") == 2.0
+        seen.add((det.info("screen2_merged"), det.info("screen2_stacked")))
+        det.close()
+        assert diff_results(got, ref) == [], f"layout {layout}"
+    assert (0.0, 0.0) in seen and len(seen) >= 3   # the layouts were really different

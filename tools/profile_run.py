@@ -15,6 +15,8 @@ ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--scale", type=int, default=1)
 ap.add_argument("--screen", type=int, default=2)
 ap.add_argument("--streams", type=int, default=2)
+ap.add_argument("--layout", type=int, default=3)
+ap.add_argument("--subbatch", type=int, default=0)
 args = ap.parse_args()
 spec = synth.SynthSpec(scale=args.scale) if args.scale == 1 else synth.SynthSpec(scale=args.scale, cand_cap=128, match_cap=512)
 cfg, model, bkg, calib, _, _, _, _ = synth.make_problem(spec, 8, seed=1000)
@@ -23,8 +25,11 @@ torch.cuda.synchronize()
 det = Detector(cfg, model, bkg, calib)
 det.set_option("screen", args.screen)
 det.set_option("streams", args.streams)
+det.set_option("screen_layout", args.layout)
+if args.subbatch:
+    det.set_option("subbatch", args.subbatch)
 for _ in range(args.iters):
     r = det.detect_batch(frames, bx, bs, bb, allow_overflow=True)
     print(det.last_timing())
-print("screen_active", det.info("screen_active"))
+print("screen_active", det.info("screen_active"), "merged", det.info("screen2_merged"), "stacked", det.info("screen2_stacked"), "ms_screen", det.info("ms_screen"), "checksum", r.checksum())
 print("flags", int((r.flags != 0).sum()), "n_bottom", r.n_bottom.mean(0), "n_side", r.n_side.mean(0))

@@ -49,11 +49,15 @@ struct lm_ctx {
         size_t n_bottom, n_side, bottom, side, match_n, match_y, match_s, tail, flags, total;
     } ro{};
     uint8_t *d_res[2] = {};           // device results for one sub-batch, per scratch set
-    uint8_t *h_res[2] = {};           // pinned
-    cudaEvent_t ev_h2d[2] = {}, ev_done[2] = {};
-    cudaEvent_t ev_stage[2][8] = {};
+    // Result staging and events are kept per "ring set" (sub-batch index mod NRES), scratch and streams per slot (index mod 2):
+    // the host queues sub-batches LOOKAHEAD ahead of the one it is copying out, so the device always has work of two
+    // sub-batches to overlap while the host copies results to the caller's arrays.
+    static constexpr int NRES = 4, LOOKAHEAD = 2;
+    uint8_t *h_res[NRES] = {};        // pinned
+    cudaEvent_t ev_h2d[2] = {}, ev_done[NRES] = {};
+    cudaEvent_t ev_stage[NRES][8] = {};
     cudaEvent_t ev_call[2] = {};      // first kernel / last D2H of a whole lm_detect_batch call
-    cudaEvent_t ev_mid[2] = {};       // between k_screen and k_corr_sparse
+    cudaEvent_t ev_mid[NRES] = {};    // between k_screen and k_corr_sparse
     float ms_screen = 0.f;            // k_screen alone, summed over the sub-batches of the last call
     float ms[7] = {};
     int64_t launches = 0;
@@ -148,9 +152,11 @@ void free_scratch(lm_ctx *c) {
     c->bbs = lm_ctx::BBScratch{};
     for (void *p : c->dev_allocs) cudaFree(p);
     c->dev_allocs.clear();
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < lm_ctx::NRES; ++s) {
         if (c->h_res[s]) cudaFreeHost(c->h_res[s]);
         c->h_res[s] = nullptr;
+    }
+    for (int s = 0; s < 2; ++s) {
         c->d_stage[s] = nullptr;
         c->d_bb[s] = nullptr;
     }
@@ -448,7 +454,7 @@ int prepare(lm_ctx *ctx) {
     o.tail = off;     off = align256(off + B * 3 * k.n_tail_points * 4);
     o.flags = off;    off = align256(off + B * 4);
     o.total = off;
-    for (int s = 0; s < 2; ++s) CK(cudaMallocHost((void **)&ctx->h_res[s], o.total));
+    for (int s = 0; s < lm_ctx::NRES; ++s) CK(cudaMallocHost((void **)&ctx->h_res[s], o.total));
     auto bind_results = [&](LmBatch &x, int set) -> int {
         int rc2;
         if ((rc2 = dalloc(ctx, &ctx->d_res[set], o.total))) return rc2;
@@ -552,9 +558,11 @@ int lm_create(lm_ctx **out, int device) {
     }
     for (int s = 0; s < 2; ++s) {
         cudaEventCreateWithFlags(&ctx->ev_h2d[s], cudaEventDisableTiming);
+        cudaEventCreate(&ctx->ev_call[s]);
+    }
+    for (int s = 0; s < lm_ctx::NRES; ++s) {
         cudaEventCreateWithFlags(&ctx->ev_done[s], cudaEventDisableTiming);
         for (int q = 0; q < 8; ++q) cudaEventCreate(&ctx->ev_stage[s][q]);
-        cudaEventCreate(&ctx->ev_call[s]);
         cudaEventCreate(&ctx->ev_mid[s]);
     }
     *out = ctx;
@@ -572,9 +580,11 @@ int lm_destroy(lm_ctx *ctx) {
         for (int f = 0; f < 3; ++f) cudaFree(ctx->d_tmpl[v][f]);
     for (int s = 0; s < 2; ++s) {
         cudaEventDestroy(ctx->ev_h2d[s]);
+        cudaEventDestroy(ctx->ev_call[s]);
+    }
+    for (int s = 0; s < lm_ctx::NRES; ++s) {
         cudaEventDestroy(ctx->ev_done[s]);
         for (int q = 0; q < 8; ++q) cudaEventDestroy(ctx->ev_stage[s][q]);
-        cudaEventDestroy(ctx->ev_call[s]);
         cudaEventDestroy(ctx->ev_mid[s]);
     }
     cudaStreamDestroy(ctx->stream);
@@ -744,6 +754,8 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
         const int64_t s0 = sub * Bcap;
         const int B = (int)std::min<int64_t>(Bcap, n - s0);
         uint32_t *bb = ctx->d_bb[slot];
+        // the staging slot (frames, boxes) is free once the sub-batch that last used it has finished on the device
+        if (sub >= 2) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[(sub - 2) % lm_ctx::NRES], 0));
         CK(cudaMemcpyAsync(bb, bb_x + s0, (size_t)B * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaMemcpyAsync(bb + Bcap, bb_y_side + s0, (size_t)B * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaMemcpyAsync(bb + 2 * Bcap, bb_y_bottom + s0, (size_t)B * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -762,7 +774,7 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
 
     int overflow = 0;
     auto drain = [&](int64_t sub) -> int {  // wait for sub-batch `sub` and copy its results to the caller
-        const int slot = (int)(sub & 1);
+        const int slot = (int)(sub % lm_ctx::NRES);
         const int64_t s0 = sub * Bcap;
         const int B = (int)std::min<int64_t>(Bcap, n - s0);
         CK(cudaEventSynchronize(ctx->ev_done[slot]));
@@ -786,9 +798,9 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
     };
 
     CK(cudaEventRecord(ctx->ev_call[0], streams[0]));
-    if ((rc = issue_h2d(0))) return rc;
-    for (int64_t sub = 0; sub < nsub; ++sub) {
-        const int slot = (int)(sub & 1);
+    auto issue_chain = [&](int64_t sub) -> int {  // every kernel of sub-batch `sub` + the D2H of its results
+        int rc = LM_OK;
+        const int slot = (int)(sub & 1), ring = (int)(sub % lm_ctx::NRES);
         const int64_t s0 = sub * Bcap;
         const int B = (int)std::min<int64_t>(Bcap, n - s0);
         cudaStream_t st = streams[slot];
@@ -805,8 +817,8 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
         b.bb_x = ctx->d_bb[slot];
         b.bb_y_side = ctx->d_bb[slot] + Bcap;
         b.bb_y_bottom = ctx->d_bb[slot] + 2 * Bcap;
-        b.ev_screen_done = ctx->ev_mid[slot];
-        cudaEvent_t *ev = ctx->ev_stage[slot];
+        b.ev_screen_done = ctx->ev_mid[ring];
+        cudaEvent_t *ev = ctx->ev_stage[ring];
         CK(cudaStreamWaitEvent(st, ctx->ev_h2d[slot], 0));
         CK(cudaEventRecord(ev[0], st));
         CK(cudaMemsetAsync(b.minmax, 0, (size_t)(B + 1) * 2 * 4, st));
@@ -833,20 +845,23 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
         ctx->launches += nl;
         CK(cudaEventRecord(ev[6], st));
         CK(cudaGetLastError());
-        // the next sub-batch's H2D may start as soon as the sub-batch that last used its slot is drained
-        if (sub + 1 < nsub) {
-            if (sub >= 1 && (rc = drain(sub - 1))) return rc;
-            if ((rc = issue_h2d(sub + 1))) return rc;
-        }
-        CK(cudaMemcpyAsync(ctx->h_res[slot], ctx->d_res[slot], o.total, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_res[ring], ctx->d_res[slot], o.total, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(ev[7], st));
-        CK(cudaEventRecord(ctx->ev_done[slot], st));
+        CK(cudaEventRecord(ctx->ev_done[ring], st));
         ctx->last_B = B;
         ctx->last_s0 = s0;
         ctx->last_slot = slot;
+        return rc;
+    };
+    // sub-batches are queued LOOKAHEAD ahead of the one being copied out; ring set (sub % NRES) was last drained at sub - NRES
+    int64_t issued = 0;
+    for (int64_t sub = 0; sub < nsub; ++sub) {
+        for (; issued < nsub && issued <= sub + lm_ctx::LOOKAHEAD; ++issued) {
+            if ((rc = issue_h2d(issued))) return rc;
+            if ((rc = issue_chain(issued))) return rc;
+        }
+        if ((rc = drain(sub))) return rc;
     }
-    if (nsub >= 2 && (rc = drain(nsub - 2))) return rc;
-    if ((rc = drain(nsub - 1))) return rc;
     CK(cudaStreamSynchronize(streams[1]));
     CK(cudaEventRecord(ctx->ev_call[1], streams[0]));  // both streams are idle here: end of the whole call
     CK(cudaStreamSynchronize(streams[0]));

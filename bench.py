@@ -194,7 +194,8 @@ def main():
     # ---- value: frames resident in HBM ------------------------------------------------------------------
     from locomouse_cpp_b200.types import Results
 
-    res = Results(n, cfg.cand_cap, cfg.match_cap, cfg.n_tail_points)  # caller-allocated result buffers, reused every step
+    # caller-allocated result buffers in page-locked memory, reused every step: the library copies device -> here directly
+    res = Results(n, cfg.cand_cap, cfg.match_cap, cfg.n_tail_points, pinned=True)
     for _ in range(args.warmup):
         det.detect_batch(frames, bx, bs, bb, results=res)
     sampler = ClockSampler(local)

@@ -23,13 +23,14 @@
 #ifndef LOCOMOUSE_B200_H
 #define LOCOMOUSE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define LM_ABI_VERSION 2  /* 2: lm_set_option, lm_get_info, lm_debug_nms, lm_bounding_box_tm_de, lm_moving_average */
+#define LM_ABI_VERSION 3  /* 2: lm_set_option, lm_get_info, lm_debug_nms, lm_bounding_box_tm_de, lm_moving_average; 3: lm_host_alloc / lm_host_free, options streams 1..4, screen_layout, screen_priority */
 
 /* feature / view indices used in every [2] / [3] array below */
 enum { LM_PAW = 0, LM_SNOUT = 1, LM_TAIL = 2 };
@@ -151,9 +152,12 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device,
  *             outputs; 0: dense exact FP32 kernel only.  All three produce bit-identical results (the screen
  *             only discards outputs proven <= 0).
  *  "subbatch" frames per internal sub-batch (default 512).
- *  "streams"  2 (default): consecutive sub-batches run on two streams with separate scratch, so the latency-bound
- *             kernels of one overlap the tensor-core kernel of the next; 1: all kernels strictly serial (used when
- *             timing a single kernel with events).
+ *  "streams"  n = 2 (default) .. 4: n consecutive sub-batches are in flight on n streams with separate scratch, so the
+ *             latency-bound kernels of one overlap the tensor-core kernel of the next; 1: all kernels strictly serial
+ *             (used when timing a single kernel with events).
+ *  "screen_layout"  bit 0: the tail template shares the paw + snout operand of the CTA-pair screen (N = 192),
+ *             bit 1: y tiles stacked over the frames of a sub-batch (default 3; never changes results).
+ *  "screen_priority"  1 (default): the tensor-core screen kernels run on a high-priority stream.
  * lm_get_info: "screen_active" (2/1/0 after the first lm_detect_batch, -1 before), "subbatch", "ms_screen"
  *             (device ms of the tensor-core kernel alone in the last call; ms[2] of lm_last_timing = screen + exact pass),
  *             "screen_eps_<view><feat>" / "screen_scale_<view><feat>" (error bound / weight quantum). */
@@ -184,6 +188,14 @@ int lm_bounding_box_tm_de(lm_ctx *ctx, const uint8_t *frames, int frames_on_devi
                           const lm_bb_de_params *p, double *bb_x_raw, int32_t *lims);
 /* vecmovingaverage (LocoMouse_class.cpp:1559-1608): central moving average, partial windows copied, (uint32_t) casts */
 int lm_moving_average(const double *v, int64_t n, int32_t window, uint32_t *out);
+
+/* Page-locked host memory for frames and result arrays (optional).  When EVERY array of the lm_results passed to
+ * lm_detect_batch lies in page-locked memory (from lm_host_alloc, cudaHostAlloc or cudaHostRegister), results are
+ * copied device -> caller directly; otherwise they go through the library's pinned staging and one host memcpy per
+ * sub-batch.  Frames in page-locked memory upload at full PCIe rate.  (The reference keeps results in std::vector
+ * members of LocoMouse, LocoMouse_class.hpp:188-236; a binding backs those with this memory or accepts the copy.) */
+int lm_host_alloc(void **ptr, size_t bytes);
+int lm_host_free(void *ptr);
 
 /* measurement / debugging ---------------------------------------------------------------- */
 /* Device time (ms, CUDA events on the library's own stream) of the stages of the last

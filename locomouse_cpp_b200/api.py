@@ -25,7 +25,8 @@ _lib = None
 
 EXPORTS = ("lm_abi_version", "lm_create", "lm_destroy", "lm_last_error", "lm_configure", "lm_set_model",
            "lm_set_background", "lm_set_calibration", "lm_get_geometry", "lm_detect_batch", "lm_last_timing",
-           "lm_debug_fetch", "lm_set_option", "lm_get_info", "lm_debug_nms", "lm_bounding_box_tm_de", "lm_moving_average")
+           "lm_debug_fetch", "lm_set_option", "lm_get_info", "lm_debug_nms", "lm_bounding_box_tm_de", "lm_moving_average",
+           "lm_host_alloc", "lm_host_free")
 
 
 class OverflowError_(RuntimeError):
@@ -156,7 +157,7 @@ class Detector:
         bb = np.ascontiguousarray(bb_y_bottom, dtype=np.uint32)
         if not (bx.size == bs.size == bb.size == n):
             raise ValueError("bounding-box arrays must have one entry per frame")
-        res = results if results is not None else Results(n, self.cfg.cand_cap, self.cfg.match_cap, self.cfg.n_tail_points)
+        res = results if results is not None else Results(n, self.cfg.cand_cap, self.cfg.match_cap, self.cfg.n_tail_points, pinned=True)
         r = res.to_c()
         rc = self._L.lm_detect_batch(self._ctx, ptr, int(on_dev), pptr, n, int(first_frame_index), bx.ctypes.data,
                                      bs.ctypes.data, bb.ctypes.data, C.byref(r))

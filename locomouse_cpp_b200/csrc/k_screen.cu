@@ -664,13 +664,22 @@ int lm_launch_screen(const LmBatch &b, cudaStream_t s) {
         if (cudaFuncSetAttribute(k_screen, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) return -1;
     }
     if (b.scr.enabled == 2) {
-        if (lm_launch_screen2_kernel(b, s) < 0) return -1;
+        // The screen owns whole SMs (its B operand fills shared memory), everything else is latency bound: on its own
+        // high-priority stream its CTAs take the SMs as soon as the previous sub-batch's screen leaves them.
+        const bool hi = b.screen_stream && b.ev_screen_go && b.ev_screen_done;
+        if (hi) {
+            if (cudaEventRecord(b.ev_screen_go, s) != cudaSuccess || cudaStreamWaitEvent(b.screen_stream, b.ev_screen_go, 0) != cudaSuccess) return -1;
+        }
+        if (lm_launch_screen2_kernel(b, hi ? b.screen_stream : s) < 0) return -1;
+        if (hi) {
+            if (cudaEventRecord(b.ev_screen_done, b.screen_stream) != cudaSuccess || cudaStreamWaitEvent(s, b.ev_screen_done, 0) != cudaSuccess) return -1;
+        }
     } else {
         int total_cta = P.job[P.njobs - 1].cta_begin + P.job[P.njobs - 1].ncta;
         k_screen<<<total_cta, SCR_THREADS, smem, s>>>(P);
         if (cudaGetLastError() != cudaSuccess) return -1;
     }
-    if (b.ev_screen_done) cudaEventRecord(b.ev_screen_done, s);
+    if (b.ev_screen_done && !(b.scr.enabled == 2 && b.screen_stream && b.ev_screen_go)) cudaEventRecord(b.ev_screen_done, s);
     int launches = 1;
     // sparse exact pass: one launch per distinct padded kernel width (the jobs of other widths exit at once)
     bool done[6] = {};

@@ -19,7 +19,10 @@ std::string g_create_error;
 
 struct lm_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, stream1 = nullptr, copy_stream = nullptr;  // sub-batch k runs on stream (k & 1)
+    static constexpr int NSLOT = 4;   // scratch sets / compute streams: sub-batch k runs in slot k % (option streams)
+    cudaStream_t stream = nullptr, stream_more[NSLOT - 1] = {}, copy_stream = nullptr;
+    cudaStream_t stream_hi = nullptr; // highest priority: the tensor-core screen kernels of all slots (option screen_priority)
+    int opt_screen_priority = 1;
     lm_config cfg{};
     bool configured = false, model_set = false, bkg_set = false, calib_set = false;
     LmGeom geom{};
@@ -32,7 +35,7 @@ struct lm_ctx {
     int opt_screen = 2;               // 0: dense exact kernel only, 1: tensor-core screen, one CTA per tile, 2: CTA pairs
     int opt_subbatch = 512;
     int opt_screen_layout = 3;        // k_screen2 job layout: bit 0 = tail shares the paw + snout job (N = 192), bit 1 = stacked y tiles
-    int opt_streams = 2;              // 2: consecutive sub-batches overlap on two streams, 1: strictly serial kernels
+    int opt_streams = 2;              // n > 1: n consecutive sub-batches in flight on n streams, 1: strictly serial kernels
     LmScreenHost scr_info[2][3] = {};
     int t_rows[2][3] = {}, t_cols[2][3] = {};
     double t_rho[2][3] = {};
@@ -40,26 +43,29 @@ struct lm_ctx {
     // sub-batch scratch
     int Bcap = 0;
     LmBatch bt{};                     // config-derived fields + scratch pointers (scratch set 0)
-    LmBatch bt1{};                    // the same with scratch set 1: consecutive sub-batches overlap on two streams
+    LmBatch bt_more[NSLOT - 1] = {};  // the same with scratch sets 1..: consecutive sub-batches overlap on their own streams
+    int nsets = 0;                    // scratch sets allocated by prepare()
     std::vector<void *> dev_allocs;   // everything cudaMalloc'ed for the scratch
     uint8_t *d_stage[2] = {};         // staged raw frames (Bcap + 1 each) when frames come from the host
-    uint32_t *d_bb[2] = {};           // [3][Bcap] per slot
+    uint32_t *d_bb[6] = {};           // [3][Bcap] per ring set
     // result staging
     struct ResOff {
         size_t n_bottom, n_side, bottom, side, match_n, match_y, match_s, tail, flags, total;
     } ro{};
-    uint8_t *d_res[2] = {};           // device results for one sub-batch, per scratch set
-    // Result staging and events are kept per "ring set" (sub-batch index mod NRES), scratch and streams per slot (index mod 2):
-    // the host queues sub-batches LOOKAHEAD ahead of the one it is copying out, so the device always has work of two
-    // sub-batches to overlap while the host copies results to the caller's arrays.
-    static constexpr int NRES = 4, LOOKAHEAD = 2;
+    uint8_t *d_res[NSLOT] = {};       // device results for one sub-batch, per scratch set
+    // Result staging, box arrays and events are kept per "ring set" (sub-batch index mod NRES), scratch and streams per slot
+    // (index mod the number of slots in use): the host queues as many sub-batches ahead of the one it is copying out as
+    // there are slots, so the device always has several sub-batches to overlap while the host copies results out.
+    static constexpr int NRES = 6;    // > the deepest lookahead (= number of slots in use)
     uint8_t *h_res[NRES] = {};        // pinned
-    cudaEvent_t ev_h2d[2] = {}, ev_done[NRES] = {};
+    cudaEvent_t ev_h2d[NRES] = {}, ev_done[NRES] = {};
     cudaEvent_t ev_stage[NRES][8] = {};
     cudaEvent_t ev_call[2] = {};      // first kernel / last D2H of a whole lm_detect_batch call
     cudaEvent_t ev_mid[NRES] = {};    // between k_screen and k_corr_sparse
+    cudaEvent_t ev_go[NRES] = {};     // before k_screen (hand-over to the high-priority stream)
     float ms_screen = 0.f;            // k_screen alone, summed over the sub-batches of the last call
     float ms[7] = {};
+    std::vector<float> timeline;     // [sub-batch][9]: ms from the start of the last call to its stage events 0..7 and to the end of the screen kernel
     int64_t launches = 0;
     // pass-1 scratch (lm_bounding_box_tm_de): independent of the model, allocated on first use
     struct BBScratch {
@@ -156,11 +162,10 @@ void free_scratch(lm_ctx *c) {
         if (c->h_res[s]) cudaFreeHost(c->h_res[s]);
         c->h_res[s] = nullptr;
     }
-    for (int s = 0; s < 2; ++s) {
-        c->d_stage[s] = nullptr;
-        c->d_bb[s] = nullptr;
-    }
-    c->d_res[0] = c->d_res[1] = nullptr;
+    for (int s = 0; s < 2; ++s) c->d_stage[s] = nullptr;
+    for (int s = 0; s < lm_ctx::NRES; ++s) c->d_bb[s] = nullptr;
+    for (int s = 0; s < lm_ctx::NSLOT; ++s) c->d_res[s] = nullptr;
+    c->nsets = 0;
     c->Bcap = 0;
 }
 
@@ -439,7 +444,7 @@ int prepare(lm_ctx *ctx) {
     if ((rc = dalloc(ctx, &b.cc_flag, B))) return rc;
     if ((rc = dalloc(ctx, &b.det, B * 4 * (size_t)k.det_cap))) return rc;
     if ((rc = dalloc(ctx, &b.det_count, B * 4))) return rc;
-    for (int s = 0; s < 2; ++s)
+    for (int s = 0; s < lm_ctx::NRES; ++s)
         if ((rc = dalloc(ctx, &ctx->d_bb[s], 3 * B))) return rc;
     // results: one device block + two pinned host blocks, same sub-array order
     lm_ctx::ResOff &o = ctx->ro;
@@ -477,9 +482,10 @@ int prepare(lm_ctx *ctx) {
         if (const char *e = getenv("LM_SCREEN")) want_screen = atoi(e);
         if ((rc = prepare_screen(ctx, b, want_screen, B))) return rc;
     }
-    // ---- scratch set 1: same geometry and operands, its own mutable buffers ------------------------------------
-    {
-        LmBatch &c = ctx->bt1;
+    // ---- scratch sets 1..: same geometry and operands, their own mutable buffers ---------------------------------
+    ctx->nsets = std::max(2, std::min(ctx->opt_streams, (int)lm_ctx::NSLOT));
+    for (int set = 1; set < ctx->nsets; ++set) {
+        LmBatch &c = ctx->bt_more[set - 1];
         c = b;
         if ((rc = dalloc(ctx, &c.minmax, (B + 1) * 2))) return rc;
         if ((rc = dalloc(ctx, &c.lut, (B + 1) * 256))) return rc;
@@ -493,7 +499,7 @@ int prepare(lm_ctx *ctx) {
         if ((rc = dalloc(ctx, &c.cc_flag, B))) return rc;
         if ((rc = dalloc(ctx, &c.det, B * 4 * (size_t)k.det_cap))) return rc;
         if ((rc = dalloc(ctx, &c.det_count, B * 4))) return rc;
-        if ((rc = bind_results(c, 1))) return rc;
+        if ((rc = bind_results(c, set))) return rc;
         if (b.scr.enabled) {
             if ((rc = dalloc(ctx, &c.scr.ntasks, 8))) return rc;
             for (int v = 0; v < 2; ++v)
@@ -550,20 +556,26 @@ int lm_create(lm_ctx **out, int device) {
                     prop.major, prop.minor);
     ctx = new lm_ctx();
     ctx->device = device;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream1, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    bool streams_ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+                      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int s = 0; s < lm_ctx::NSLOT - 1; ++s)
+        streams_ok = streams_ok && cudaStreamCreateWithFlags(&ctx->stream_more[s], cudaStreamNonBlocking) == cudaSuccess;
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi is the numerically lowest = highest priority
+        streams_ok = streams_ok && cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, hi) == cudaSuccess;
+    }
+    if (!streams_ok) {
         delete ctx;
         return fail(nullptr, LM_ERR_RUNTIME, "cudaStreamCreate failed");
     }
-    for (int s = 0; s < 2; ++s) {
-        cudaEventCreateWithFlags(&ctx->ev_h2d[s], cudaEventDisableTiming);
-        cudaEventCreate(&ctx->ev_call[s]);
-    }
+    for (int s = 0; s < 2; ++s) cudaEventCreate(&ctx->ev_call[s]);
     for (int s = 0; s < lm_ctx::NRES; ++s) {
+        cudaEventCreateWithFlags(&ctx->ev_h2d[s], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_done[s], cudaEventDisableTiming);
         for (int q = 0; q < 8; ++q) cudaEventCreate(&ctx->ev_stage[s][q]);
         cudaEventCreate(&ctx->ev_mid[s]);
+        cudaEventCreateWithFlags(&ctx->ev_go[s], cudaEventDisableTiming);
     }
     *out = ctx;
     return LM_OK;
@@ -578,17 +590,17 @@ int lm_destroy(lm_ctx *ctx) {
     cudaFree(ctx->d_calib);
     for (int v = 0; v < 2; ++v)
         for (int f = 0; f < 3; ++f) cudaFree(ctx->d_tmpl[v][f]);
-    for (int s = 0; s < 2; ++s) {
-        cudaEventDestroy(ctx->ev_h2d[s]);
-        cudaEventDestroy(ctx->ev_call[s]);
-    }
+    for (int s = 0; s < 2; ++s) cudaEventDestroy(ctx->ev_call[s]);
     for (int s = 0; s < lm_ctx::NRES; ++s) {
+        cudaEventDestroy(ctx->ev_h2d[s]);
         cudaEventDestroy(ctx->ev_done[s]);
         for (int q = 0; q < 8; ++q) cudaEventDestroy(ctx->ev_stage[s][q]);
         cudaEventDestroy(ctx->ev_mid[s]);
+        cudaEventDestroy(ctx->ev_go[s]);
     }
     cudaStreamDestroy(ctx->stream);
-    cudaStreamDestroy(ctx->stream1);
+    for (int s = 0; s < lm_ctx::NSLOT - 1; ++s) cudaStreamDestroy(ctx->stream_more[s]);
+    cudaStreamDestroy(ctx->stream_hi);
     cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
     return LM_OK;
@@ -709,7 +721,8 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, co
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamSynchronize(ctx->stream);
-        cudaStreamSynchronize(ctx->stream1);
+        for (int s = 0; s < lm_ctx::NSLOT - 1; ++s) cudaStreamSynchronize(ctx->stream_more[s]);
+        cudaStreamSynchronize(ctx->stream_hi);
         cudaGetLastError();
     }
     return rc;
@@ -746,21 +759,25 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
     for (int q = 0; q < 7; ++q) ctx->ms[q] = 0.f;
     ctx->ms_screen = 0.f;
     ctx->launches = 0;
+    ctx->timeline.assign((size_t)nsub * 9, -1.f);
     const lm_ctx::ResOff &o = ctx->ro;
-    cudaStream_t streams[2] = {ctx->stream, ctx->opt_streams == 2 ? ctx->stream1 : ctx->stream};
+    const int nslot = ctx->nsets;  // scratch sets in rotation; with option streams = 1 they share one stream (strictly serial kernels)
+    cudaStream_t streams[lm_ctx::NSLOT];
+    for (int q = 0; q < lm_ctx::NSLOT; ++q) streams[q] = (q == 0 || ctx->opt_streams == 1) ? ctx->stream : ctx->stream_more[q - 1];
+    const int lookahead = nslot;
 
     auto issue_h2d = [&](int64_t sub) -> int {
-        const int slot = (int)(sub & 1);
+        const int slot = (int)(sub & 1);   // frame staging slot
         const int64_t s0 = sub * Bcap;
         const int B = (int)std::min<int64_t>(Bcap, n - s0);
-        uint32_t *bb = ctx->d_bb[slot];
-        // the staging slot (frames, boxes) is free once the sub-batch that last used it has finished on the device
-        if (sub >= 2) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[(sub - 2) % lm_ctx::NRES], 0));
+        uint32_t *bb = ctx->d_bb[sub % lm_ctx::NRES];   // its last user (sub - NRES) has been drained
         CK(cudaMemcpyAsync(bb, bb_x + s0, (size_t)B * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaMemcpyAsync(bb + Bcap, bb_y_side + s0, (size_t)B * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaMemcpyAsync(bb + 2 * Bcap, bb_y_bottom + s0, (size_t)B * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
         if (!frames_on_device) {
             uint8_t *stg = ctx->d_stage[slot];
+            // the frame staging slot is free once the sub-batch that last used it has finished on the device
+            if (sub >= 2) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[(sub - 2) % lm_ctx::NRES], 0));
             if (s0 > 0)  // halo = last frame of the previous sub-batch, contiguous in the caller's array
                 CK(cudaMemcpyAsync(stg, frames + (s0 - 1) * fsz, (size_t)(B + 1) * fsz, cudaMemcpyHostToDevice, ctx->copy_stream));
             else {
@@ -768,10 +785,20 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
                 CK(cudaMemcpyAsync(stg + fsz, frames, (size_t)B * fsz, cudaMemcpyHostToDevice, ctx->copy_stream));
             }
         }
-        CK(cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_h2d[sub % lm_ctx::NRES], ctx->copy_stream));
         return LM_OK;
     };
 
+    // result arrays in page-locked memory receive the D2H copies directly (no staging, no host memcpy)
+    bool direct = true;
+    {
+        const void *arrs[9] = {out->n_bottom, out->n_side, out->bottom, out->side, out->match_n, out->match_y, out->match_s, out->tail, out->flags};
+        for (const void *a : arrs) {
+            cudaPointerAttributes at{};
+            if (cudaPointerGetAttributes(&at, a) != cudaSuccess || at.type != cudaMemoryTypeHost) direct = false;
+        }
+        cudaGetLastError();
+    }
     int overflow = 0;
     auto drain = [&](int64_t sub) -> int {  // wait for sub-batch `sub` and copy its results to the caller
         const int slot = (int)(sub % lm_ctx::NRES);
@@ -779,47 +806,57 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
         const int B = (int)std::min<int64_t>(Bcap, n - s0);
         CK(cudaEventSynchronize(ctx->ev_done[slot]));
         const uint8_t *h = ctx->h_res[slot];
-        memcpy(out->n_bottom + s0 * 2, h + o.n_bottom, (size_t)B * 2 * 4);
-        memcpy(out->n_side + s0 * 2, h + o.n_side, (size_t)B * 2 * 4);
-        memcpy(out->bottom + s0 * 2 * k.cand_cap, h + o.bottom, (size_t)B * 2 * k.cand_cap * sizeof(lm_cand));
-        memcpy(out->side + s0 * 2 * k.cand_cap, h + o.side, (size_t)B * 2 * k.cand_cap * sizeof(lm_cand));
-        memcpy(out->match_n + s0 * 2 * k.cand_cap, h + o.match_n, (size_t)B * 2 * k.cand_cap * 4);
-        memcpy(out->match_y + s0 * 2 * k.match_cap, h + o.match_y, (size_t)B * 2 * k.match_cap * 4);
-        memcpy(out->match_s + s0 * 2 * k.match_cap, h + o.match_s, (size_t)B * 2 * k.match_cap * 8);
-        memcpy(out->tail + s0 * 3 * k.n_tail_points, h + o.tail, (size_t)B * 3 * k.n_tail_points * 4);
-        memcpy(out->flags + s0, h + o.flags, (size_t)B * 4);
+        if (!direct) {
+            memcpy(out->n_bottom + s0 * 2, h + o.n_bottom, (size_t)B * 2 * 4);
+            memcpy(out->n_side + s0 * 2, h + o.n_side, (size_t)B * 2 * 4);
+            memcpy(out->bottom + s0 * 2 * k.cand_cap, h + o.bottom, (size_t)B * 2 * k.cand_cap * sizeof(lm_cand));
+            memcpy(out->side + s0 * 2 * k.cand_cap, h + o.side, (size_t)B * 2 * k.cand_cap * sizeof(lm_cand));
+            memcpy(out->match_n + s0 * 2 * k.cand_cap, h + o.match_n, (size_t)B * 2 * k.cand_cap * 4);
+            memcpy(out->match_y + s0 * 2 * k.match_cap, h + o.match_y, (size_t)B * 2 * k.match_cap * 4);
+            memcpy(out->match_s + s0 * 2 * k.match_cap, h + o.match_s, (size_t)B * 2 * k.match_cap * 8);
+            memcpy(out->tail + s0 * 3 * k.n_tail_points, h + o.tail, (size_t)B * 3 * k.n_tail_points * 4);
+            memcpy(out->flags + s0, h + o.flags, (size_t)B * 4);
+        }
         for (int i = 0; i < B; ++i)
             if (out->flags[s0 + i]) overflow = 1;
         float t;
         for (int q = 0; q < 6; ++q)
             if (cudaEventElapsedTime(&t, ctx->ev_stage[slot][q], ctx->ev_stage[slot][q + 1]) == cudaSuccess) ctx->ms[q] += t;
         if (ctx->bt.scr.enabled && cudaEventElapsedTime(&t, ctx->ev_stage[slot][2], ctx->ev_mid[slot]) == cudaSuccess) ctx->ms_screen += t;
+        for (int q = 0; q < 9; ++q) {
+            t = -1.f;
+            if (cudaEventElapsedTime(&t, ctx->ev_call[0], q < 8 ? ctx->ev_stage[slot][q] : ctx->ev_mid[slot]) != cudaSuccess) t = -1.f;
+            ctx->timeline[(size_t)sub * 9 + q] = t;
+        }
+        cudaGetLastError();
         return LM_OK;
     };
 
     CK(cudaEventRecord(ctx->ev_call[0], streams[0]));
     auto issue_chain = [&](int64_t sub) -> int {  // every kernel of sub-batch `sub` + the D2H of its results
         int rc = LM_OK;
-        const int slot = (int)(sub & 1), ring = (int)(sub % lm_ctx::NRES);
+        const int slot = (int)(sub % nslot), ring = (int)(sub % lm_ctx::NRES), stg = (int)(sub & 1);
         const int64_t s0 = sub * Bcap;
         const int B = (int)std::min<int64_t>(Bcap, n - s0);
         cudaStream_t st = streams[slot];
-        LmBatch b = slot ? ctx->bt1 : ctx->bt;
+        LmBatch b = slot ? ctx->bt_more[slot - 1] : ctx->bt;
         b.B = B;
         b.first_index = first_frame_index + s0;
         if (frames_on_device) {
             b.frames = frames + s0 * fsz;
             b.prev = s0 > 0 ? frames + (s0 - 1) * fsz : (has_prev0 ? prev_frame : nullptr);
         } else {
-            b.frames = ctx->d_stage[slot] + fsz;
-            b.prev = (s0 > 0 || has_prev0) ? ctx->d_stage[slot] : nullptr;
+            b.frames = ctx->d_stage[stg] + fsz;
+            b.prev = (s0 > 0 || has_prev0) ? ctx->d_stage[stg] : nullptr;
         }
-        b.bb_x = ctx->d_bb[slot];
-        b.bb_y_side = ctx->d_bb[slot] + Bcap;
-        b.bb_y_bottom = ctx->d_bb[slot] + 2 * Bcap;
+        b.bb_x = ctx->d_bb[ring];
+        b.bb_y_side = ctx->d_bb[ring] + Bcap;
+        b.bb_y_bottom = ctx->d_bb[ring] + 2 * Bcap;
         b.ev_screen_done = ctx->ev_mid[ring];
+        b.screen_stream = (ctx->opt_streams > 1 && ctx->opt_screen_priority) ? ctx->stream_hi : nullptr;
+        b.ev_screen_go = ctx->ev_go[ring];
         cudaEvent_t *ev = ctx->ev_stage[ring];
-        CK(cudaStreamWaitEvent(st, ctx->ev_h2d[slot], 0));
+        CK(cudaStreamWaitEvent(st, ctx->ev_h2d[ring], 0));
         CK(cudaEventRecord(ev[0], st));
         CK(cudaMemsetAsync(b.minmax, 0, (size_t)(B + 1) * 2 * 4, st));
         CK(cudaMemsetAsync(b.det_count, 0, (size_t)B * 4 * 4, st));
@@ -845,7 +882,21 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
         ctx->launches += nl;
         CK(cudaEventRecord(ev[6], st));
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(ctx->h_res[ring], ctx->d_res[slot], o.total, cudaMemcpyDeviceToHost, st));
+        if (direct) {
+            const uint8_t *d = ctx->d_res[slot];
+            const cudaMemcpyKind D2H = cudaMemcpyDeviceToHost;
+            CK(cudaMemcpyAsync(out->n_bottom + s0 * 2, d + o.n_bottom, (size_t)B * 2 * 4, D2H, st));
+            CK(cudaMemcpyAsync(out->n_side + s0 * 2, d + o.n_side, (size_t)B * 2 * 4, D2H, st));
+            CK(cudaMemcpyAsync(out->bottom + s0 * 2 * k.cand_cap, d + o.bottom, (size_t)B * 2 * k.cand_cap * sizeof(lm_cand), D2H, st));
+            CK(cudaMemcpyAsync(out->side + s0 * 2 * k.cand_cap, d + o.side, (size_t)B * 2 * k.cand_cap * sizeof(lm_cand), D2H, st));
+            CK(cudaMemcpyAsync(out->match_n + s0 * 2 * k.cand_cap, d + o.match_n, (size_t)B * 2 * k.cand_cap * 4, D2H, st));
+            CK(cudaMemcpyAsync(out->match_y + s0 * 2 * k.match_cap, d + o.match_y, (size_t)B * 2 * k.match_cap * 4, D2H, st));
+            CK(cudaMemcpyAsync(out->match_s + s0 * 2 * k.match_cap, d + o.match_s, (size_t)B * 2 * k.match_cap * 8, D2H, st));
+            CK(cudaMemcpyAsync(out->tail + s0 * 3 * k.n_tail_points, d + o.tail, (size_t)B * 3 * k.n_tail_points * 4, D2H, st));
+            CK(cudaMemcpyAsync(out->flags + s0, d + o.flags, (size_t)B * 4, D2H, st));
+        } else {
+            CK(cudaMemcpyAsync(ctx->h_res[ring], ctx->d_res[slot], o.total, cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaEventRecord(ev[7], st));
         CK(cudaEventRecord(ctx->ev_done[ring], st));
         ctx->last_B = B;
@@ -853,16 +904,16 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
         ctx->last_slot = slot;
         return rc;
     };
-    // sub-batches are queued LOOKAHEAD ahead of the one being copied out; ring set (sub % NRES) was last drained at sub - NRES
+    // sub-batches are queued `lookahead` ahead of the one being copied out; ring set (sub % NRES) was last drained at sub - NRES
     int64_t issued = 0;
     for (int64_t sub = 0; sub < nsub; ++sub) {
-        for (; issued < nsub && issued <= sub + lm_ctx::LOOKAHEAD; ++issued) {
+        for (; issued < nsub && issued <= sub + lookahead; ++issued) {
             if ((rc = issue_h2d(issued))) return rc;
             if ((rc = issue_chain(issued))) return rc;
         }
         if ((rc = drain(sub))) return rc;
     }
-    CK(cudaStreamSynchronize(streams[1]));
+    for (int q = 1; q < nslot; ++q) CK(cudaStreamSynchronize(streams[q]));
     CK(cudaEventRecord(ctx->ev_call[1], streams[0]));  // both streams are idle here: end of the whole call
     CK(cudaStreamSynchronize(streams[0]));
     {
@@ -883,8 +934,10 @@ int lm_set_option(lm_ctx *ctx, const char *name, int64_t value) {
     } else if (!strcmp(name, "screen_layout")) {
         if (value < 0 || value > 3) return fail(ctx, LM_ERR_INVALID, "option screen_layout must be in [0, 3]");
         ctx->opt_screen_layout = (int)value;
+    } else if (!strcmp(name, "screen_priority")) {
+        ctx->opt_screen_priority = value != 0;
     } else if (!strcmp(name, "streams")) {
-        if (value != 1 && value != 2) return fail(ctx, LM_ERR_INVALID, "option streams must be 1 or 2");
+        if (value < 1 || value > lm_ctx::NSLOT) return fail(ctx, LM_ERR_INVALID, "option streams must be in [1, %d]", (int)lm_ctx::NSLOT);
         ctx->opt_streams = (int)value;
     } else if (!strcmp(name, "subbatch")) {
         if (value < 1 || value > 4096) return fail(ctx, LM_ERR_INVALID, "option subbatch must be in [1, 4096]");
@@ -925,6 +978,12 @@ int lm_get_info(const lm_ctx *ctx, const char *name, double *value) {
             if (ctx->Bcap && ctx->bt.scr.enabled == 2 && J.Bimg[0] && (name[8] == 'm' ? J.ntmpl == 3 : J.stacked)) m |= 1 << v;
         }
         *value = (double)m;
+        return LM_OK;
+    }
+    if (!strncmp(name, "tl_", 3)) {  // tl_<sub>_<k>: device timeline of the last call (ms since its start), k = 0..7 stage events, 8 = screen end
+        int sub = -1, q = -1;
+        if (sscanf(name + 3, "%d_%d", &sub, &q) != 2 || sub < 0 || q < 0 || q > 8 || (size_t)sub * 9 + q >= ctx->timeline.size()) return LM_ERR_INVALID;
+        *value = (double)ctx->timeline[(size_t)sub * 9 + q];
         return LM_OK;
     }
     if (!strcmp(name, "ms_screen")) {  // device time of k_screen alone in the last lm_detect_batch call
@@ -1084,6 +1143,17 @@ int lm_debug_nms(lm_ctx *ctx, int view, int feat, const float *scores, lm_cand *
     return n;
 }
 
+int lm_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return LM_ERR_INVALID;
+    *ptr = nullptr;
+    return cudaHostAlloc(ptr, std::max<size_t>(bytes, 1), cudaHostAllocPortable) == cudaSuccess ? LM_OK : LM_ERR_RUNTIME;
+}
+
+int lm_host_free(void *ptr) {
+    if (!ptr) return LM_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? LM_OK : LM_ERR_RUNTIME;
+}
+
 int lm_last_timing(const lm_ctx *ctx, float ms[7], int64_t *launches) {
     if (!ctx) return LM_ERR_INVALID;
     if (ms) memcpy(ms, ctx->ms, sizeof ctx->ms);
@@ -1096,7 +1166,7 @@ int64_t lm_debug_fetch(lm_ctx *ctx, int what, int64_t frame, void *dst, int64_t 
     const int64_t i = frame - ctx->last_s0;
     if (i < 0 || i >= ctx->last_B) return fail(ctx, LM_ERR_INVALID, "frame %lld is not in the last sub-batch", (long long)frame);
     cudaSetDevice(ctx->device);
-    const LmBatch &b = ctx->last_slot ? ctx->bt1 : ctx->bt;
+    const LmBatch &b = ctx->last_slot ? ctx->bt_more[ctx->last_slot - 1] : ctx->bt;
     const void *src = nullptr;
     int64_t bytes = 0;
     int32_t d[4] = {0, 0, 0, 0};

@@ -116,6 +116,8 @@ struct LmBatch {
     int32_t *cc_flag;           // [B] 1 = frame exceeded the run capacity of k_tail and takes k_tail_slow
     LmScreen scr;
     cudaEvent_t ev_screen_done; // recorded by lm_launch_screen between k_screen and k_corr_sparse (may be null)
+    cudaStream_t screen_stream; // when set (with ev_screen_go and ev_screen_done): the screen kernel runs on this (high-priority) stream
+    cudaEvent_t ev_screen_go;
     LmDet *det;                 // [B][2][2][det_cap]   index: ((f*2+feat)*2+view)
     int32_t *det_count;         // [B][2][2]
     // results (device mirrors of lm_results)

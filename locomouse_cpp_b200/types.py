@@ -139,15 +139,24 @@ class Model:
 class Results:
     """Host result buffers for n frames (struct-of-arrays, see lm_results in the header)."""
 
-    def __init__(self, n: int, cand_cap: int, match_cap: int, n_tail_points: int = 15, buffer: np.ndarray | None = None):
+    def __init__(self, n: int, cand_cap: int, match_cap: int, n_tail_points: int = 15, buffer: np.ndarray | None = None,
+                 pinned: bool = False):
         """All arrays are views of ONE contiguous byte buffer (self.raw), so a whole result set moves with a single
-        copy / collective.  `buffer` adopts an existing buffer of exactly raw_nbytes(...) bytes (e.g. a gathered one)."""
+        copy / collective.  `buffer` adopts an existing buffer of exactly raw_nbytes(...) bytes (e.g. a gathered one).
+        pinned: allocate the buffer page-locked (needs a CUDA device), so lm_detect_batch copies results device -> here
+        directly instead of through its staging buffers."""
         self.n = int(n)
         self.cand_cap = int(cand_cap)
         self.match_cap = int(match_cap)
         self.n_tail_points = int(n_tail_points)
         layout, total = self._layout(max(self.n, 1), self.cand_cap, self.match_cap, self.n_tail_points)
-        if buffer is None:
+        self._pin = None
+        if buffer is None and pinned:
+            import torch
+
+            self._pin = torch.zeros(total, dtype=torch.uint8, pin_memory=True)   # keeps the page-locked allocation alive
+            buffer = self._pin.numpy()
+        elif buffer is None:
             buffer = np.zeros(total, np.uint8)
         else:
             buffer = np.ascontiguousarray(buffer, dtype=np.uint8).reshape(-1)

@@ -264,3 +264,25 @@ def test_large_resident_batch_properties(oracle):
                             first_frame_index=f)
         for name in Results.ARRAYS:
             assert np.array_equal(getattr(ref, name)[0], getattr(whole, name)[f]), (f, name)
+
+
+def test_pinned_and_pageable_result_buffers_agree():
+    """Results in page-locked memory are filled by direct D2H copies, pageable ones through the library's staging buffers
+    and a host memcpy; 2-, 3- and 4-slot pipelines and the screen's stream priority never change a byte."""
+    from locomouse_cpp_b200.api import Detector
+    from locomouse_cpp_b200.types import Results
+
+    cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(synth.SynthSpec(), 23, seed=1005)
+    frames = frames.numpy()
+    sums = set()
+    for streams, prio, pinned in ((2, 1, True), (2, 1, False), (3, 0, True), (4, 1, False), (1, 1, True)):
+        det = Detector(cfg, model, bkg, calib, device=0)
+        det.set_option("subbatch", 4)
+        det.set_option("streams", streams)
+        det.set_option("screen_priority", prio)
+        res = Results(len(frames), cfg.cand_cap, cfg.match_cap, cfg.n_tail_points, pinned=pinned)
+        for _ in range(2):
+            det.detect_batch(frames, bx, bs, bb, results=res)
+        sums.add(res.checksum())
+        det.close()
+    assert len(sums) == 1

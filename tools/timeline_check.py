@@ -1,4 +1,5 @@
-"""Device timeline of the two-stream pipeline: start/end of every stage of the last sub-batch in each slot."""
+"""Device timeline of the sub-batch pipeline: start / end of every stage of every sub-batch of one call (ms since the call began)."""
+import argparse
 import sys
 
 import torch
@@ -6,18 +7,30 @@ import torch
 sys.path.insert(0, '/root/repo')
 from locomouse_cpp_b200 import synth  # noqa: E402
 from locomouse_cpp_b200.api import Detector  # noqa: E402
+from locomouse_cpp_b200.types import Results  # noqa: E402
 
+ap = argparse.ArgumentParser()
+ap.add_argument("--frames", type=int, default=5120)
+ap.add_argument("--streams", type=int, nargs="+", default=[2, 1])
+ap.add_argument("--prio", type=int, default=1)
+args = ap.parse_args()
 spec = synth.SynthSpec()
 cfg, model, bkg, calib, _, _, _, _ = synth.make_problem(spec, 8, seed=1000)
-N = 2048
+N = args.frames
 frames, bx, bs, bb = synth.make_video(spec, N, 1000, "cuda", bkg)
 torch.cuda.synchronize()
 det = Detector(cfg, model, bkg, calib)
-names = ["start", "minmax_end", "prep_end", "corr_end", "tail_end", "nms_end", "pair_end", "d2h_end"]
-for streams in (2, 1):
+res = Results(N, cfg.cand_cap, cfg.match_cap, cfg.n_tail_points, pinned=True)
+names = ["start", "mm", "prep", "screen", "corr", "tail", "nms", "pair", "d2h"]
+for streams in args.streams:
     det.set_option("streams", streams)
+    det.set_option("screen_priority", args.prio)
     for _ in range(3):
-        det.detect_batch(frames, bx, bs, bb)
-    print(f"streams={streams} total {det.last_timing()[0]['total']:.3f} ms (4 sub-batches of 512; slot 0 ran #2, slot 1 ran #3)")
-    for slot in (0, 1):
-        print(f"  slot {slot}: " + "  ".join(f"{n}={det.info(f'stage_t_{slot}_{k}'):.3f}" for k, n in enumerate(names)))
+        det.detect_batch(frames, bx, bs, bb, results=res)
+    sub = int(det.info("subbatch"))
+    nsub = (N + sub - 1) // sub
+    print(f"streams={streams} prio={args.prio} total {det.last_timing()[0]['total']:.3f} ms, {nsub} sub-batches of {sub}")
+    for i in range(nsub):
+        t = [det.info(f"tl_{i}_{k}") for k in range(9)]
+        order = [t[0], t[1], t[2], t[8], t[3], t[4], t[5], t[6], t[7]]
+        print(f"  #{i:2d}: " + "  ".join(f"{n}={v:7.3f}" for n, v in zip(names, order)))

@@ -354,6 +354,41 @@ def main():
         except Exception as ex:  # pragma: no cover
             pass1 = {"error": repr(ex)}
 
+    # ---- the tracker's cost builders for the whole result set on the device (not part of `value`) -------
+    costs = None
+    if rank == 0:
+        try:
+            from locomouse_cpp_b200.types import location_priors, pairwise_params
+            from oracle import oracle as _orc  # checker + CPU timing beside it, on a bounded sample
+
+            rows = [(0.8, 0.25, 0.5, 0.4, 1.0, 0.0, 0.5), (0.8, 0.75, 0.5, 0.4, 1.0, 0.5, 1.0), (0.3, 0.25, 0.4, 0.0, 0.6, 0.0, 0.5),
+                    (0.3, 0.75, 0.35, 0.0, 0.6, 0.5, 1.0)]
+            pri = location_priors(rows)
+            pw = pairwise_params(cfg.bb_w, cfg.bb_h_bottom)
+            det.unary_costs(res, 0, cfg.bb_w, cfg.bb_h_bottom, pri)
+            offs, jc, ir, pr = det.pairwise_costs(res, 0, pw)
+            t1 = time.perf_counter()
+            for feat in range(2):
+                det.unary_costs(res, feat, cfg.bb_w, cfg.bb_h_bottom, pri)
+                det.pairwise_costs(res, feat, pw, cap=2 * len(ir) + 1024)
+            dt1 = time.perf_counter() - t1
+            m = min(n, 512)
+            t2 = time.perf_counter()
+            ok = True
+            for f in range(1, m):
+                a = res.candidates_bottom(f - 1, 0)
+                b_ = res.candidates_bottom(f, 0)
+                _, nc_, wjc, wir, wpr = _orc.pairwise_potential(a, b_, pw)
+                ok = ok and np.array_equal(ir[offs[f]:offs[f + 1]], wir) and np.array_equal(pr[offs[f]:offs[f + 1]].view(np.uint64), wpr.view(np.uint64))
+            dt2 = time.perf_counter() - t2
+            costs = {"frames_per_s": n / dt1, "ms_per_10k_frames": dt1 * 1e3 * 10000 / n, "stored_entries_paw": int(len(ir)),
+                     "bit_exact_on_sample": bool(ok), "cpu_port_frames_per_s_one_feature_pairwise_only": (m - 1) / dt2,
+                     "note": "lm_unary_costs + lm_pairwise_costs for both features, candidates uploaded from and matrices returned to "
+                             "pageable host memory inside the timed region (PCIe + allocation bound); CPU figure = oracle pairwisePotential "
+                             f"through ctypes on the first {m} frames, one feature"}
+        except Exception as ex:  # pragma: no cover
+            costs = {"error": repr(ex)}
+
     # ---- e2e: host (pinned) buffers, H2D + D2H inside the timed region -------------------------------------
     e2e = None
     host = None
@@ -424,7 +459,7 @@ def main():
                            "note": "value/wall/device_event: two-stream overlapped pipeline; stage_ms_per_step_serial and the roofline "
                                    "launch times: the same steps with the library option streams=1 (kernels strictly serial)"},
                 "clocks": sampler.summary(), "gpu_launches": int(launches), "overflow_frames": overflow,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "pass1_tm_de": pass1}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "pass1_tm_de": pass1, "cost_builders": costs}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

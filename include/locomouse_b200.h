@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LM_ABI_VERSION 3  /* 2: lm_set_option, lm_get_info, lm_debug_nms, lm_bounding_box_tm_de, lm_moving_average; 3: lm_host_alloc / lm_host_free, options streams 1..4, screen_layout, screen_priority */
+#define LM_ABI_VERSION 3  /* 2: lm_set_option, lm_get_info, lm_debug_nms, lm_bounding_box_tm_de, lm_moving_average; 3: lm_host_alloc / lm_host_free, lm_unary_costs / lm_pairwise_costs, options streams 1..4, screen_layout, screen_priority */
 
 /* feature / view indices used in every [2] / [3] array below */
 enum { LM_PAW = 0, LM_SNOUT = 1, LM_TAIL = 2 };
@@ -188,6 +188,38 @@ int lm_bounding_box_tm_de(lm_ctx *ctx, const uint8_t *frames, int frames_on_devi
                           const lm_bb_de_params *p, double *bb_x_raw, int32_t *lims);
 /* vecmovingaverage (LocoMouse_class.cpp:1559-1608): central moving average, partial windows copied, (uint32_t) casts */
 int lm_moving_average(const double *v, int64_t n, int32_t window, uint32_t *out);
+
+/* cost builders of the host tracker --------------------------------------------------------------- *
+ * LocoMouse::computeUnaryCostsBottom / unaryCostBox (LocoMouse_class.cpp:873-894, 1909-1952) and
+ * computePairwiseCostsBottom / pairwisePotential (896-919, 1954-2070) + MATSPARSE(const MyMat*) (MyMat.cpp:141-178), for
+ * ALL frames of a result set at once.  They feed match2nd, which stays on the host. */
+typedef struct {              /* LocoMouse_LocationPrior (LocoMouse_class.hpp:33-45, .cpp:3196-3202)                    */
+    double pos_x, pos_y;      /* POSITION, in box-normalised coordinates                                               */
+    double max_distance;      /* MAX_DISTANCE                                                                          */
+    double area_x, area_y, area_w, area_h; /* AREA = Rect_<double>(min_x, min_y, max_x - min_x, max_y - min_y)       */
+} lm_location_prior;
+typedef struct {
+    double grid_x, grid_y;    /* ONG_BR_corner (LocoMouse_class.cpp:733)                                               */
+    double grid_spacing;      /* occlusion_grid_spacing_pixels_bottom                                                  */
+    int32_t ong_w, ong_h;     /* ONG_size (731); Nong = ong_w * ong_h occlusion-grid nodes                             */
+    double max_displacement;  /* max_displacement_bottom                                                               */
+    double alpha_vel;         /* alpha_vel_bottom                                                                      */
+    double occluded_cost;     /* pairwise_occluded_cost                                                                */
+} lm_pairwise_params;
+
+/* UNARY_BOTTOM_{PAW,SNOUT}: for every frame f of `res` the MyMat unaryCostBox(CANDIDATES_BOTTOM_<feat>[f], BB, priors)
+ * returns (N_candidates x n_priors, column-major, zeros where the candidate lies outside the prior's area or too far).
+ * out[(f * n_priors + j) * cand_cap + i] = M(i, j); rows i >= n_bottom[f][feat] are 0.  bb_w / bb_h = BB_BOTTOM_MOUSE size. */
+int lm_unary_costs(lm_ctx *ctx, const lm_results *res, int64_t n, int32_t feat, int32_t bb_w, int32_t bb_h,
+                   const lm_location_prior *priors, int32_t n_priors, double *out);
+/* PAIRWISE_BOTTOM_{PAW,SNOUT}: for every frame f >= 1 the MATSPARSE (MATLAB-style CSC) of
+ * pairwisePotential(C[f-1], C[f], ...): (N_f + Nong) rows x (N_{f-1} + Nong) columns.
+ *   jc[f * (cand_cap + Nong + 1) + c], c = 0 .. ncols: column starts relative to offs[f] (frame 0: all zero, no matrix);
+ *   ir / pr [offs[f] + k]: row index / value of the k-th stored entry; entries equal to 0 are not stored, as in the
+ *   reference; offs has n + 1 entries, offs[n] = total number of stored entries.  cap = capacity of ir / pr in entries; LM_ERR_OVERFLOW (with
+ *   *total set to the required capacity) when it is too small. */
+int lm_pairwise_costs(lm_ctx *ctx, const lm_results *res, int64_t n, int32_t feat, const lm_pairwise_params *p,
+                      int64_t *offs, int32_t *jc, int32_t *ir, double *pr, int64_t cap, int64_t *total);
 
 /* Page-locked host memory for frames and result arrays (optional).  When EVERY array of the lm_results passed to
  * lm_detect_batch lies in page-locked memory (from lm_host_alloc, cudaHostAlloc or cudaHostRegister), results are

@@ -26,7 +26,7 @@ _lib = None
 EXPORTS = ("lm_abi_version", "lm_create", "lm_destroy", "lm_last_error", "lm_configure", "lm_set_model",
            "lm_set_background", "lm_set_calibration", "lm_get_geometry", "lm_detect_batch", "lm_last_timing",
            "lm_debug_fetch", "lm_set_option", "lm_get_info", "lm_debug_nms", "lm_bounding_box_tm_de", "lm_moving_average",
-           "lm_host_alloc", "lm_host_free")
+           "lm_host_alloc", "lm_host_free", "lm_unary_costs", "lm_pairwise_costs")
 
 
 class OverflowError_(RuntimeError):
@@ -190,6 +190,42 @@ class Detector:
         if n:
             self._check(self._L.lm_moving_average(raw.ctypes.data, n, int(window), out.ctypes.data))
         return out, raw, lims
+
+    # ---- cost builders of the host tracker ----------------------------------------------------------------
+    def unary_costs(self, res: Results, feat: int, bb_w: int, bb_h: int, priors):
+        """UNARY_BOTTOM_{PAW,SNOUT} for every frame of `res` (LocoMouse::unaryCostBox, LocoMouse_class.cpp:1909-1952):
+        float64 [n, n_priors, cand_cap]; [f, j, i] = MyMat(i, j) of frame f.  priors: types.location_priors(...)."""
+        out = np.zeros((res.n, len(priors), res.cand_cap), np.float64)
+        r = res.to_c()
+        self._L.lm_unary_costs.restype = C.c_int
+        self._check(self._L.lm_unary_costs(self._ctx, C.byref(r), C.c_int64(res.n), int(feat), int(bb_w), int(bb_h), priors, len(priors),
+                                           C.c_void_p(out.ctypes.data)))
+        return out
+
+    def pairwise_costs(self, res: Results, feat: int, params, cap: int | None = None):
+        """PAIRWISE_BOTTOM_{PAW,SNOUT} for every frame >= 1 of `res` (LocoMouse::pairwisePotential + MATSPARSE,
+        LocoMouse_class.cpp:1954-2070, MyMat.cpp:141-178) as packed CSC: (offs int64[n + 1], jc int32[n, cand_cap + Nong + 1],
+        ir int32[total], pr float64[total]); frame f's matrix has n_bottom[f] + Nong rows, n_bottom[f - 1] + Nong columns."""
+        nong = params.ong_w * params.ong_h
+        offs = np.zeros(res.n + 1, np.int64)
+        jc = np.zeros((max(res.n, 1), res.cand_cap + nong + 1), np.int32)
+        total = C.c_int64(0)
+        r = res.to_c()
+        self._L.lm_pairwise_costs.restype = C.c_int
+        if cap is None:   # generous first guess; the library reports the exact need on overflow
+            cap = int(res.n) * (2 * nong + 64) + 1024
+        for _ in range(2):
+            ir = np.zeros(max(cap, 1), np.int32)
+            pr = np.zeros(max(cap, 1), np.float64)
+            rc = self._L.lm_pairwise_costs(self._ctx, C.byref(r), C.c_int64(res.n), int(feat), C.byref(params), C.c_void_p(offs.ctypes.data),
+                                           C.c_void_p(jc.ctypes.data), C.c_void_p(ir.ctypes.data), C.c_void_p(pr.ctypes.data), C.c_int64(cap),
+                                           C.byref(total))
+            if rc == LM_ERR_OVERFLOW and total.value > cap:
+                cap = int(total.value)
+                continue
+            self._check(rc)
+            break
+        return offs, jc[:res.n], ir[:total.value].copy(), pr[:total.value].copy()
 
     def debug_nms(self, view: int, feat: int, scores):
         """nmsMax (view 0) / peakClustering (view 1) kernels on a given score map -> list of (x, y, score)."""

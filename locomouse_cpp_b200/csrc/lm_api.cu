@@ -1096,6 +1096,82 @@ int lm_moving_average(const double *v, int64_t n, int32_t window, uint32_t *out)
     return LM_OK;
 }
 
+// ---- cost builders of the host tracker: candidates up, cost matrices down -------------------------------
+namespace {
+struct DevBuf {  // scoped device allocation
+    void *p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 256)); }
+};
+}  // namespace
+
+int lm_unary_costs(lm_ctx *ctx, const lm_results *res, int64_t n, int32_t feat, int32_t bb_w, int32_t bb_h, const lm_location_prior *priors,
+                   int32_t n_priors, double *out) {
+    if (!ctx) return LM_ERR_INVALID;
+    if (!res || !priors || !out || n < 0 || n > res->n_frames || feat < 0 || feat > 1 || bb_w < 1 || bb_h < 1 || n_priors < 1 || res->cand_cap < 1)
+        return fail(ctx, LM_ERR_INVALID, "lm_unary_costs: bad argument");
+    if (n == 0) return LM_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t cap = (size_t)res->cand_cap;
+    DevBuf dc, dn, dp, dout;
+    CK(dc.alloc((size_t)n * 2 * cap * sizeof(lm_cand)));
+    CK(dn.alloc((size_t)n * 2 * 4));
+    CK(dp.alloc((size_t)n_priors * sizeof(lm_location_prior)));
+    CK(dout.alloc((size_t)n * n_priors * cap * 8));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(dc.p, res->bottom, (size_t)n * 2 * cap * sizeof(lm_cand), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dn.p, res->n_bottom, (size_t)n * 2 * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dp.p, priors, (size_t)n_priors * sizeof(lm_location_prior), cudaMemcpyHostToDevice, st));
+    if (lm_launch_unary((lm_cand *)dc.p, (int32_t *)dn.p, n, (int)cap, feat, bb_w, bb_h, (lm_location_prior *)dp.p, n_priors, (double *)dout.p, st) < 0)
+        return fail(ctx, LM_ERR_RUNTIME, "unary cost launch failed");
+    CK(cudaMemcpyAsync(out, dout.p, (size_t)n * n_priors * cap * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LM_OK;
+}
+
+int lm_pairwise_costs(lm_ctx *ctx, const lm_results *res, int64_t n, int32_t feat, const lm_pairwise_params *p, int64_t *offs, int32_t *jc,
+                      int32_t *ir, double *pr, int64_t cap, int64_t *total) {
+    if (!ctx) return LM_ERR_INVALID;
+    if (!res || !p || !offs || !jc || !total || n < 0 || n > res->n_frames || feat < 0 || feat > 1 || cap < 0 || (cap > 0 && (!ir || !pr)) ||
+        p->ong_w < 1 || p->ong_h < 1 || (int64_t)p->ong_w * p->ong_h > (1 << 20) || res->cand_cap < 1)
+        return fail(ctx, LM_ERR_INVALID, "lm_pairwise_costs: bad argument");
+    *total = 0;
+    offs[0] = 0;
+    if (n == 0) return LM_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t ccap = (size_t)res->cand_cap;
+    const size_t jc_stride = ccap + (size_t)p->ong_w * p->ong_h + 1;
+    DevBuf dc, dn, djc, dnnz, doffs, dir, dpr;
+    CK(dc.alloc((size_t)n * 2 * ccap * sizeof(lm_cand)));
+    CK(dn.alloc((size_t)n * 2 * 4));
+    CK(djc.alloc((size_t)n * jc_stride * 4));
+    CK(dnnz.alloc((size_t)n * 8));
+    CK(doffs.alloc((size_t)(n + 1) * 8));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(dc.p, res->bottom, (size_t)n * 2 * ccap * sizeof(lm_cand), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dn.p, res->n_bottom, (size_t)n * 2 * 4, cudaMemcpyHostToDevice, st));
+    if (lm_launch_pairwise((lm_cand *)dc.p, (int32_t *)dn.p, n, (int)ccap, feat, *p, (int32_t *)djc.p, (int64_t *)dnnz.p, (int64_t *)doffs.p,
+                           nullptr, nullptr, 0, 0, st) < 0)
+        return fail(ctx, LM_ERR_RUNTIME, "pairwise cost launch failed");
+    CK(cudaMemcpyAsync(offs, doffs.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(jc, djc.p, (size_t)n * jc_stride * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *total = offs[n];
+    if (*total > cap) return fail(ctx, LM_ERR_OVERFLOW, "lm_pairwise_costs: %lld stored entries, capacity %lld", (long long)*total, (long long)cap);
+    if (*total == 0) return LM_OK;
+    CK(dir.alloc((size_t)*total * 4));
+    CK(dpr.alloc((size_t)*total * 8));
+    if (lm_launch_pairwise((lm_cand *)dc.p, (int32_t *)dn.p, n, (int)ccap, feat, *p, (int32_t *)djc.p, (int64_t *)dnnz.p, (int64_t *)doffs.p,
+                           (int32_t *)dir.p, (double *)dpr.p, *total, 1, st) < 0)
+        return fail(ctx, LM_ERR_RUNTIME, "pairwise cost launch failed");
+    CK(cudaMemcpyAsync(ir, dir.p, (size_t)*total * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pr, dpr.p, (size_t)*total * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LM_OK;
+}
+
 int lm_debug_nms(lm_ctx *ctx, int view, int feat, const float *scores, lm_cand *out) {
     if (!ctx) return LM_ERR_INVALID;
     if (!ctx->configured || !ctx->model_set) return fail(ctx, LM_ERR_STATE, "lm_debug_nms needs lm_configure and lm_set_model first");

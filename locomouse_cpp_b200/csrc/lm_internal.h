@@ -139,6 +139,13 @@ int lm_launch_pair(const LmBatch &b, cudaStream_t s);
 int lm_launch_bbox_tm_de(const LmBatch &b, const lm_bb_de_params &p, uint32_t *hist, uint8_t *pred, double *bb_x, int32_t *lims,
                          cudaStream_t s);
 
+// cost builders (k_cost.cu); all pointers are device memory.  Pairwise: phase 0 = count + scan (fills jc, nnz, offs),
+// phase 1 = fill (ir, pr)
+int lm_launch_unary(const lm_cand *cand, const int32_t *ncand, int64_t n, int cand_cap, int feat, int bb_w, int bb_h,
+                    const lm_location_prior *pri, int np, double *out, cudaStream_t s);
+int lm_launch_pairwise(const lm_cand *cand, const int32_t *ncand, int64_t n, int cand_cap, int feat, const lm_pairwise_params &p,
+                       int32_t *jc, int64_t *nnz, int64_t *offs, int32_t *ir, double *pr, int64_t cap, int phase, cudaStream_t s);
+
 // tensor-core screen + sparse exact re-evaluation (k_screen.cu); returns kernels launched or -1
 int lm_launch_screen(const LmBatch &b, cudaStream_t s);
 // Host-side preparation of one screen job from the fp32 template: quantisation to two int8 digits, the

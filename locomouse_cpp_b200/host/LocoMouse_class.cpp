@@ -75,6 +75,11 @@ cv::Rect parse_rect(const std::string &v, const std::string &key) {
 
 }  // namespace
 
+LocoMouse_LocationPrior::LocoMouse_LocationPrior(double x, double y, double md, double minx, double maxx, double miny, double maxy)
+    : X(x), Y(y), MAX_DISTANCE(md), MIN_X(minx), MAX_X(maxx), MIN_Y(miny), MAX_Y(maxy) {
+    if (!(minx < maxx) || !(miny < maxy)) throw std::invalid_argument("location_prior: min must be below max.");  // CV_Assert, class.cpp:3197-3198
+}
+
 LocoMouse_Parameters::LocoMouse_Parameters(const std::string &config_file_name) {
     std::ifstream in(config_file_name);
     if (!in) throw std::invalid_argument("Could not open the configuration file: " + config_file_name);
@@ -104,6 +109,19 @@ LocoMouse_Parameters::LocoMouse_Parameters(const std::string &config_file_name) 
             else if (key == "cand_cap") cand_cap = std::stoi(val);
             else if (key == "det_cap") det_cap = std::stoi(val);
             else if (key == "match_cap") match_cap = std::stoi(val);
+            else if (key == "max_displacement_bottom") max_displacement_bottom = std::stoi(val);
+            else if (key == "occlusion_grid_spacing_pixels_bottom") occlusion_grid_spacing_pixels_bottom = std::stoi(val);
+            else if (key == "occlusion_grid_max_width") occlusion_grid_max_width = std::stod(val);
+            else if (key == "alpha_vel_bottom") alpha_vel_bottom = std::stod(val);
+            else if (key == "pairwise_occluded_cost") pairwise_occluded_cost = std::stod(val);
+            else if (key == "location_prior") {  // class.cpp:132-145: 5 x 7, rows 0-3 paws, row 4 snout (row-major flow list here)
+                const std::vector<double> W = parse_list(val, key);
+                if (W.size() != 35) throw std::invalid_argument("location_prior must be a 5x7 matrix. Was " + std::to_string(W.size()) + " values.");
+                for (unsigned int i = 0; i <= N_paws; ++i) {
+                    const double *q = W.data() + 7 * i;
+                    (i < N_paws ? PRIOR_PAW : PRIOR_SNOUT).push_back(LocoMouse_LocationPrior(q[0], q[1], q[2], q[3], q[4], q[5], q[6]));
+                }
+            }
             // every other reference key belongs to pass 1 or to the host tracker and is ignored here
         } catch (const std::invalid_argument &) {
             throw;
@@ -167,6 +185,13 @@ struct LocoMouse::Batch {
     std::vector<lm_cand> bottom, side;
     std::vector<double> match_s;
     std::vector<uint32_t> flags;
+    // cost builders (per feature): unary [count][n_priors][cand_cap]; pairwise packed CSC over count + 1 frames (frame 0 =
+    // last frame of the previous chunk, so that the first transition of this chunk is present)
+    bool has_costs = false;
+    int n_priors[2] = {0, 0}, nong = 0;
+    std::vector<double> unary[2], pw_pr[2];
+    std::vector<int64_t> pw_offs[2];
+    std::vector<int32_t> pw_jc[2], pw_ir[2];
     lm_results view() {
         lm_results r{};
         r.n_frames = count;
@@ -204,6 +229,7 @@ void LocoMouse::initializePaths(const LocoMouse_ParseInputs &INPUT) {
     OUTPUT_PATH = INPUT.OUTPUT_PATH;
     // output_<stem>.* next to the reference's output_<stem>.yml (LocoMouse_class.cpp:360)
     output_file = OUTPUT_PATH + "/output_" + INPUT.FILE_STEM + ".lmo";
+    costs_file = OUTPUT_PATH + "/costs_" + INPUT.FILE_STEM + ".lmo";
 }
 
 void LocoMouse::loadVideo() {
@@ -451,6 +477,60 @@ void LocoMouse::runChunk(unsigned int first) {
     const uint8_t *prev = first > 0 ? VIDEO.data() + (size_t)(first - 1) * fsz : nullptr;
     check(lm_detect_batch(CTX, VIDEO.data() + (size_t)first * fsz, /*frames_on_device=*/0, prev, n, first, BB_X_POS.data() + first,
                           BB_Y_SIDE_POS.data() + first, BB_Y_BOTTOM_POS.data() + first, &r));
+    if (!LM_PARAMS.PRIOR_PAW.empty() && !LM_PARAMS.PRIOR_SNOUT.empty()) {
+        // ---- cost builders for the whole chunk (class.cpp:873-919) --------------------------------------------------
+        // bottom candidates of [previous chunk's last frame | this chunk]: the halo gives the first pairwise transition
+        const size_t per = (size_t)2 * b->cand_cap;
+        std::vector<lm_cand> hb((size_t)(n + 1) * per);
+        std::vector<int32_t> hn((size_t)(n + 1) * 2, 0);
+        if (BATCH && first > 0) {
+            const size_t last = BATCH->count - 1;
+            std::copy(BATCH->bottom.begin() + last * per, BATCH->bottom.begin() + (last + 1) * per, hb.begin());
+            hn[0] = BATCH->n_bottom[last * 2];
+            hn[1] = BATCH->n_bottom[last * 2 + 1];
+        }
+        std::copy(b->bottom.begin(), b->bottom.end(), hb.begin() + per);
+        std::copy(b->n_bottom.begin(), b->n_bottom.end(), hn.begin() + 2);
+        lm_results h = r;
+        h.n_frames = n + 1;
+        h.bottom = hb.data();
+        h.n_bottom = hn.data();
+        lm_pairwise_params P{};
+        const int sp = LM_PARAMS.occlusion_grid_spacing_pixels_bottom;
+        P.ong_h = (int32_t)(unsigned int)(((BB_BOTTOM_MOUSE.height - sp) / sp) + 1);                                  // class.cpp:726
+        P.ong_w = (int32_t)(unsigned int)(((LM_PARAMS.occlusion_grid_max_width * BB_BOTTOM_MOUSE.width) - sp) / sp + 1);  // 727
+        P.grid_x = (double)(BB_BOTTOM_MOUSE.width - 1 - sp / 2);                                                        // 733
+        P.grid_y = (double)(BB_BOTTOM_MOUSE.height - 1 - sp / 2);
+        P.grid_spacing = (double)sp;
+        P.max_displacement = (double)LM_PARAMS.max_displacement_bottom;
+        P.alpha_vel = LM_PARAMS.alpha_vel_bottom;
+        P.occluded_cost = LM_PARAMS.pairwise_occluded_cost;
+        b->nong = P.ong_w * P.ong_h;
+        for (int feat = 0; feat < 2; ++feat) {
+            const std::vector<LocoMouse_LocationPrior> &pri = feat == LM_PAW ? LM_PARAMS.PRIOR_PAW : LM_PARAMS.PRIOR_SNOUT;
+            std::vector<lm_location_prior> pc;
+            for (const LocoMouse_LocationPrior &q : pri) pc.push_back(q.to_c());
+            b->n_priors[feat] = (int)pc.size();
+            b->unary[feat].assign((size_t)n * pc.size() * b->cand_cap, 0.0);
+            check(lm_unary_costs(CTX, &r, n, feat, BB_BOTTOM_MOUSE.width, BB_BOTTOM_MOUSE.height, pc.data(), (int32_t)pc.size(), b->unary[feat].data()));
+            b->pw_offs[feat].assign((size_t)n + 2, 0);
+            b->pw_jc[feat].assign((size_t)(n + 1) * (b->cand_cap + b->nong + 1), 0);
+            int64_t cap = (int64_t)(n + 1) * (2 * b->nong + 64), total = 0;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                b->pw_ir[feat].assign((size_t)cap, 0);
+                b->pw_pr[feat].assign((size_t)cap, 0.0);
+                const int rc = lm_pairwise_costs(CTX, &h, n + 1, feat, &P, b->pw_offs[feat].data(), b->pw_jc[feat].data(), b->pw_ir[feat].data(),
+                                                 b->pw_pr[feat].data(), cap, &total);
+                if (rc == LM_ERR_OVERFLOW && total > cap && attempt == 0) {
+                    cap = total;
+                    continue;
+                }
+                check(rc);
+                break;
+            }
+        }
+        b->has_costs = true;
+    }
     BATCH = std::move(b);
 }
 
@@ -492,11 +572,35 @@ void LocoMouse::detectBottomCandidates() {
     CANDIDATES_BOTTOM_SNOUT.push_back(to_candidates(&b.bottom[(i * 2 + LM_SNOUT) * b.cand_cap], b.n_bottom[i * 2 + LM_SNOUT]));
 }
 
-// computeUnaryCostsBottom / computePairwiseCostsBottom (LocoMouse_class.cpp:873-919) build the host tracker's
-// MyMat / MATSPARSE inputs from the candidate lists above; they belong to the tracker (out of scope)
-// and are left to the caller's existing implementation.
-void LocoMouse::computeUnaryCostsBottom() {}
-void LocoMouse::computePairwiseCostsBottom() {}
+// computeUnaryCostsBottom / computePairwiseCostsBottom (LocoMouse_class.cpp:873-919): the MyMat / MATSPARSE inputs of the
+// host tracker, built on the device for the whole chunk (lm_unary_costs / lm_pairwise_costs) and handed out per frame.
+// Without a location_prior in the configuration they are skipped (the reference refuses to start without one).
+void LocoMouse::computeUnaryCostsBottom() {
+    const Batch &b = batchFor(CURRENT_FRAME);
+    if (!b.has_costs) return;
+    const size_t i = (size_t)CURRENT_FRAME - b.first;
+    for (int feat = 0; feat < 2; ++feat) {
+        const int nc = b.n_bottom[i * 2 + feat], np = b.n_priors[feat];
+        MyMat M((unsigned int)nc, (unsigned int)np);
+        for (int j = 0; j < np; ++j)
+            std::copy_n(&b.unary[feat][(i * np + j) * b.cand_cap], nc, M.getValues() + (size_t)j * nc);
+        (feat == LM_PAW ? UNARY_BOTTOM_PAW : UNARY_BOTTOM_SNOUT).push_back(std::move(M));
+    }
+}
+
+void LocoMouse::computePairwiseCostsBottom() {
+    const Batch &b = batchFor(CURRENT_FRAME);
+    if (!b.has_costs || CURRENT_FRAME <= 0) return;  // class.cpp:901
+    const size_t i = (size_t)CURRENT_FRAME - b.first + 1;  // index in the halo-extended chunk
+    for (int feat = 0; feat < 2; ++feat) {
+        const std::vector<std::vector<Candidate>> &C = feat == LM_PAW ? CANDIDATES_BOTTOM_PAW : CANDIDATES_BOTTOM_SNOUT;
+        const int ni = (int)C.end()[-2].size(), nip1 = (int)C.end()[-1].size();
+        const int32_t *jc = &b.pw_jc[feat][i * (b.cand_cap + b.nong + 1)];
+        const int64_t o = b.pw_offs[feat][i];
+        (feat == LM_PAW ? PAIRWISE_BOTTOM_PAW : PAIRWISE_BOTTOM_SNOUT)
+            .push_back(MATSPARSE(nip1 + b.nong, ni + b.nong, jc, &b.pw_ir[feat][o], &b.pw_pr[feat][o]));
+    }
+}
 
 void LocoMouse::detectSideCandidates() {
     const Batch &b = batchFor(CURRENT_FRAME);
@@ -568,6 +672,25 @@ void LocoMouse::exportResults() {
                 }
             }
         }
+    }
+    if (!UNARY_BOTTOM_PAW.empty()) {  // the tracker's inputs, for tests and for a host match2nd: costs_<stem>.lmo
+        lmfile::Writer c(costs_file, "LMC1");
+        c.i32((int32_t)UNARY_BOTTOM_PAW.size());
+        for (size_t f = 0; f < UNARY_BOTTOM_PAW.size(); ++f)
+            for (int feat = 0; feat < 2; ++feat) {
+                const MyMat &U = feat == 0 ? UNARY_BOTTOM_PAW[f] : UNARY_BOTTOM_SNOUT[f];
+                c.i32(U.Nrows());
+                c.i32(U.Ncols());
+                c.write(U.getValues(), (size_t)U.Numel());
+                if (f == 0) continue;
+                const MATSPARSE &S = feat == 0 ? PAIRWISE_BOTTOM_PAW[f - 1] : PAIRWISE_BOTTOM_SNOUT[f - 1];
+                c.i32(S.Nrows());
+                c.i32(S.Ncols());
+                c.i32(S.nz());
+                c.write(S.getJc(), (size_t)S.Ncols() + 1);
+                c.write(S.getIr(), (size_t)S.nz());
+                c.write(S.getPr(), (size_t)S.nz());
+            }
     }
 }
 

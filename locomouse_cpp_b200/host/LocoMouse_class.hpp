@@ -18,11 +18,30 @@
 #include "../../include/locomouse_b200.h"
 #include "Candidates.hpp"
 #include "LocoMouse_ParseInputs.hpp"
+#include "MyMat.hpp"
 
 // LocoMouse_Parameters (class.hpp:48-100): the subset that reaches the detection path, plus the
 // inputs that replace the out-of-scope pass 1: per-frame box positions from a file.
+// LocoMouse_LocationPrior (class.hpp:33-45, ctor class.cpp:3196-3202)
+class LocoMouse_LocationPrior {
+    double X = 0, Y = 0, MAX_DISTANCE = 1, MIN_X = 0, MAX_X = 1, MIN_Y = 0, MAX_Y = 1;
+
+public:
+    LocoMouse_LocationPrior() = default;
+    LocoMouse_LocationPrior(double x, double y, double md, double minx, double maxx, double miny, double maxy);
+    double max_distance() const { return MAX_DISTANCE; }
+    lm_location_prior to_c() const { return lm_location_prior{X, Y, MAX_DISTANCE, MIN_X, MIN_Y, MAX_X - MIN_X, MAX_Y - MIN_Y}; }
+};
+
 class LocoMouse_Parameters {
 public:
+    // host-tracker cost builders (class.hpp:59-68, 88; class.cpp:132-145): used by computeUnaryCostsBottom / computePairwiseCostsBottom
+    int max_displacement_bottom = 15;
+    int occlusion_grid_spacing_pixels_bottom = 20;
+    double occlusion_grid_max_width = 0.75;
+    double alpha_vel_bottom = 1E-1;
+    double pairwise_occluded_cost = 1E-2;
+    std::vector<LocoMouse_LocationPrior> PRIOR_PAW, PRIOR_SNOUT;  // config key location_prior (5 x 7); empty: cost builders are skipped
     int conn_comp_connectivity = 8;
     double side_bottom_min_overlap = 0.7;
     double tail_sub_bounding_box = 0.6;
@@ -96,6 +115,9 @@ protected:
     std::vector<std::vector<Candidate>> CANDIDATES_SIDE_PAW, CANDIDATES_SIDE_SNOUT;
     std::vector<std::vector<P22D>> CANDIDATES_MATCHED_VIEWS_PAW, CANDIDATES_MATCHED_VIEWS_SNOUT;
     std::vector<std::vector<int32_t>> TRACKS_TAIL;  // per frame 3 x N_tail_points (x, y, z), -1 = missing
+    std::vector<MyMat> UNARY_BOTTOM_PAW, UNARY_BOTTOM_SNOUT;            // class.hpp: same names
+    std::vector<MATSPARSE> PAIRWISE_BOTTOM_PAW, PAIRWISE_BOTTOM_SNOUT;
+    std::string costs_file;
 
     // ---- device side ------------------------------------------------------------------------------
     lm_ctx *CTX = nullptr;
@@ -147,6 +169,10 @@ public:
     const std::vector<std::vector<P22D>> &candidatesMatchedViewsPaw() const { return CANDIDATES_MATCHED_VIEWS_PAW; }
     const std::vector<std::vector<P22D>> &candidatesMatchedViewsSnout() const { return CANDIDATES_MATCHED_VIEWS_SNOUT; }
     const std::vector<std::vector<int32_t>> &tracksTail() const { return TRACKS_TAIL; }
+    const std::vector<MyMat> &unaryBottomPaw() const { return UNARY_BOTTOM_PAW; }
+    const std::vector<MyMat> &unaryBottomSnout() const { return UNARY_BOTTOM_SNOUT; }
+    const std::vector<MATSPARSE> &pairwiseBottomPaw() const { return PAIRWISE_BOTTOM_PAW; }
+    const std::vector<MATSPARSE> &pairwiseBottomSnout() const { return PAIRWISE_BOTTOM_SNOUT; }
 };
 
 // LocoMouse_TM (LocoMouse_TM.hpp:45-47): imadjust in readFrame; box = bb_width x bb_height_side (side,

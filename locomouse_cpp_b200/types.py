@@ -72,6 +72,37 @@ def bb_de_params(cfg, side_h: int = 165, **kw) -> lm_bb_de_params:
     return lm_bb_de_params(**d)
 
 
+class lm_location_prior(C.Structure):
+    _fields_ = [("pos_x", C.c_double), ("pos_y", C.c_double), ("max_distance", C.c_double), ("area_x", C.c_double),
+                ("area_y", C.c_double), ("area_w", C.c_double), ("area_h", C.c_double)]
+
+
+class lm_pairwise_params(C.Structure):
+    _fields_ = [("grid_x", C.c_double), ("grid_y", C.c_double), ("grid_spacing", C.c_double), ("ong_w", C.c_int32),
+                ("ong_h", C.c_int32), ("max_displacement", C.c_double), ("alpha_vel", C.c_double), ("occluded_cost", C.c_double)]
+
+
+def location_priors(rows):
+    """rows: (x, y, max_distance, min_x, max_x, min_y, max_y) per prior -- the arguments of the reference's
+    LocoMouse_LocationPrior constructor (LocoMouse_class.cpp:3196-3202) -> ctypes array of lm_location_prior."""
+    arr = (lm_location_prior * len(rows))()
+    for k, (x, y, md, x0, x1, y0, y1) in enumerate(rows):
+        if not (x0 < x1 and y0 < y1):
+            raise ValueError("location prior: min must be below max (CV_Assert in the reference)")
+        arr[k] = lm_location_prior(x, y, md, x0, y0, x1 - x0, y1 - y0)
+    return arr
+
+
+def pairwise_params(bb_w: int, bb_h: int, spacing: int = 20, max_width: float = 0.75, max_displacement: float = 15,
+                    alpha_vel: float = 1e-1, occluded_cost: float = 1e-2) -> lm_pairwise_params:
+    """Occlusion grid and costs as LocoMouse::initializeFeatureLoop derives them (LocoMouse_class.cpp:723-733) from the
+    reference's default parameters (LocoMouse_class.hpp:59-68): integer divisions as there."""
+    ngrid_y = (bb_h - spacing) // spacing + 1
+    ngrid_x = int((max_width * bb_w - spacing) / spacing + 1)
+    return lm_pairwise_params(float(bb_w - 1 - spacing // 2), float(bb_h - 1 - spacing // 2), float(spacing), ngrid_x, ngrid_y,
+                              float(max_displacement), float(alpha_vel), float(occluded_cost))
+
+
 TemplateArray = (lm_template * 3) * 2  # t[view][feature]
 
 

@@ -955,6 +955,81 @@ void lmo_tail_from_binary(const uint8_t *bin_bottom, int32_t rows_b, const uint8
     tail_from_binary(bin_bottom, rows_b, bin_side, rows_s, cols, conn, n_points, tracks, tail_mask);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cost builders of the host tracker.
+// unaryCostBox — class.cpp:1909-1952: candidate normalised by the box size; inside the prior's area (cv::Point_::inside:
+// x <= px < x + w, same for y); val = sqrt(d.d) * (1 / sqrt(2)); stored (1 - val) * score when val <= max_distance.
+// ---------------------------------------------------------------------------------------------
+void lmo_unary_cost_box(const lm_cand *c, int32_t n, int32_t bb_w, int32_t bb_h, const lm_location_prior *priors,
+                        int32_t n_priors, double *out) {
+    for (int64_t k = 0; k < (int64_t)n * n_priors; ++k) out[k] = 0.0;  // MyMat(n, m) zero-fills (MyMat.cpp:50-63)
+    const double norm_fact = 1 / std::sqrt(2.0);
+    for (int i = 0; i < n; ++i) {
+        const double cx = (double)c[i].x / (double)bb_w, cy = (double)c[i].y / (double)bb_h;
+        for (int j = 0; j < n_priors; ++j) {
+            const lm_location_prior &P = priors[j];
+            if (P.area_x <= cx && cx < P.area_x + P.area_w && P.area_y <= cy && cy < P.area_y + P.area_h) {
+                const double dx = cx - P.pos_x, dy = cy - P.pos_y;
+                const double val = std::sqrt(dx * dx + dy * dy) * norm_fact;
+                if (val <= P.max_distance) out[(int64_t)j * n + i] = (1 - val) * c[i].s;  // column-major put (MyMat.cpp:65-69)
+            }
+        }
+    }
+}
+
+// pairwisePotential — class.cpp:1954-2070, literally on a dense D, then MATSPARSE(const MyMat*) — MyMat.cpp:141-178
+// (column by column, rows ascending, entries equal to 0 dropped).  Quirk kept: the "ONG -> X(i+1)" entries are written
+// inside the i == 0 iteration of the loop over frame i's candidates (2012-2024), so they are missing when Ci is empty.
+int lmo_pairwise_potential(const lm_cand *ci, int32_t ni, const lm_cand *cip1, int32_t nip1, const lm_pairwise_params *p,
+                           int32_t *jc, int32_t *ir, double *pr, int64_t cap, int32_t dims[3]) {
+    const int nong = p->ong_w * p->ong_h;
+    const int nrows = nip1 + nong, ncols = ni + nong;
+    std::vector<double> D((size_t)nrows * ncols, 0.0);
+    auto put = [&](int r, int c, double v) { D[(size_t)c * nrows + r] = v; };
+    auto clampi = [](int32_t v, int32_t lo, int32_t hi) { return v < lo ? lo : (v > hi ? hi : v); };  // matchToRange (class.hpp:364-374)
+    const double occ = p->occluded_cost * p->alpha_vel;
+    const int xa = p->ong_w - 1, ya = p->ong_h - 1;
+    for (int i = 0; i < ni; ++i) {
+        const int32_t xc = (int32_t)std::round((p->grid_x - (double)ci[i].x) / p->grid_spacing);
+        const int32_t yc = (int32_t)std::round((p->grid_y - (double)ci[i].y) / p->grid_spacing);
+        put(nip1 + (clampi(yc, 0, ya) * p->ong_w + clampi(xc, 0, xa)), i, occ);
+        for (int j = 0; j < nip1; ++j) {
+            if (i == 0) {
+                const int32_t x2 = (int32_t)std::round((p->grid_x - (double)cip1[j].x) / p->grid_spacing);
+                const int32_t y2 = (int32_t)std::round((p->grid_y - (double)cip1[j].y) / p->grid_spacing);
+                put(j, ni + (clampi(y2, 0, ya) * p->ong_w + clampi(x2, 0, xa)), occ);
+            }
+            const double dx = (double)cip1[j].x - (double)ci[i].x, dy = (double)cip1[j].y - (double)ci[i].y;
+            const double dist = std::sqrt(dx * dx + dy * dy);
+            if (dist < p->max_displacement) {
+                double inv = 1 - (dist / p->max_displacement);
+                inv = inv * p->alpha_vel;
+                put(j, i, inv);
+            }
+        }
+    }
+    for (int g = 0; g < nong; ++g) put(nip1 + g, ni + g, occ);
+    int64_t nz = 0;
+    jc[0] = 0;
+    for (int c = 0; c < ncols; ++c) {
+        for (int r = 0; r < nrows; ++r) {
+            const double v = D[(size_t)c * nrows + r];
+            if (v != 0) {
+                if (nz < cap) {
+                    ir[nz] = r;
+                    pr[nz] = v;
+                }
+                ++nz;
+            }
+        }
+        jc[c + 1] = (int32_t)nz;
+    }
+    dims[0] = nrows;
+    dims[1] = ncols;
+    dims[2] = (int32_t)nz;
+    return nz > cap ? 1 : 0;
+}
+
 int lmo_match_views(const lm_cand *cb, int32_t nb, const lm_cand *cs, int32_t ns, int32_t vel_check,
                     int32_t tw_b, int32_t th_b, int32_t tw_s, int32_t th_s, double T, const uint8_t *I,
                     const uint8_t *Iprev, int32_t n_rows, int32_t n_cols, int32_t x0, int32_t y0b, int32_t y0s,

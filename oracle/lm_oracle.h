@@ -83,6 +83,14 @@ int lmo_bounding_box_tm_de(const lm_config *cfg, const uint8_t *bkg, const int32
 void lmo_imadjust_default_lut(const uint32_t *hist, uint8_t *lut, int32_t *imin_imax);
 /* firstLastOverT<int> (LocoMouse_class.hpp:411-442) on float column sums */
 void lmo_first_last_over_t(const float *values, uint32_t L, int32_t th, int32_t *first_last);
+/* ---- cost builders ----------------------------------------------------------------- */
+/* unaryCostBox (LocoMouse_class.cpp:1909-1952): out = MyMat(n x n_priors), column-major */
+void lmo_unary_cost_box(const lm_cand *c, int32_t n, int32_t bb_w, int32_t bb_h, const lm_location_prior *priors,
+                        int32_t n_priors, double *out);
+/* pairwisePotential (1954-2070) followed by MATSPARSE(const MyMat*) (MyMat.cpp:141-178).  jc has ni + Nong + 1 entries,
+ * ir / pr up to cap; dims = {n_rows, n_cols, nnz}.  Returns 1 when cap is too small (nnz still reported). */
+int lmo_pairwise_potential(const lm_cand *ci, int32_t ni, const lm_cand *cip1, int32_t nip1, const lm_pairwise_params *p,
+                           int32_t *jc, int32_t *ir, double *pr, int64_t cap, int32_t dims[3]);
 /* branch-coverage counters of the pairing stage since the last reset (see g_cov in lm_oracle.cpp) */
 void lmo_coverage(int64_t out[8], int reset);
 /* vecmovingaverage (LocoMouse_class.cpp:1559-1608) */

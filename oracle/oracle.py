@@ -247,6 +247,35 @@ def vecmovingaverage(v, window: int):
     return out
 
 
+# ---- cost builders -----------------------------------------------------------------------------------
+def unary_cost_box(cands, bb_w, bb_h, priors):
+    """cands: list of (x, y, s); priors: ctypes array of lm_location_prior -> MyMat as an (n, n_priors) array."""
+    c = np.array([tuple(k) for k in cands], CAND_DTYPE) if len(cands) else np.zeros(0, CAND_DTYPE)
+    out = np.zeros((len(priors), max(len(c), 1)), np.float64)
+    L = lib()
+    L.lmo_unary_cost_box.restype = None
+    L.lmo_unary_cost_box(C.c_void_p(c.ctypes.data), len(c), int(bb_w), int(bb_h), priors, len(priors), C.c_void_p(out.ctypes.data))
+    return out.reshape(-1)[:len(priors) * len(c)].reshape(len(priors), len(c)).T.copy()
+
+
+def pairwise_potential(ci, cip1, params, cap=1 << 16):
+    """-> (n_rows, n_cols, jc, ir, pr) of the MATSPARSE pairwisePotential returns."""
+    a = np.array([tuple(k) for k in ci], CAND_DTYPE) if len(ci) else np.zeros(0, CAND_DTYPE)
+    b = np.array([tuple(k) for k in cip1], CAND_DTYPE) if len(cip1) else np.zeros(0, CAND_DTYPE)
+    nong = params.ong_w * params.ong_h
+    jc = np.zeros(len(a) + nong + 1, np.int32)
+    ir = np.zeros(cap, np.int32)
+    pr = np.zeros(cap, np.float64)
+    dims = np.zeros(3, np.int32)
+    L = lib()
+    L.lmo_pairwise_potential.restype = C.c_int
+    rc = L.lmo_pairwise_potential(C.c_void_p(a.ctypes.data), len(a), C.c_void_p(b.ctypes.data), len(b), C.byref(params),
+                                  C.c_void_p(jc.ctypes.data), C.c_void_p(ir.ctypes.data), C.c_void_p(pr.ctypes.data), C.c_int64(cap),
+                                  C.c_void_p(dims.ctypes.data))
+    assert rc == 0
+    return int(dims[0]), int(dims[1]), jc, ir[:dims[2]].copy(), pr[:dims[2]].copy()
+
+
 COVERAGE_NAMES = ("pairings", "all_equal_boolD_zeroed", "velocity_comparisons", "velocity_rejections", "velocity_accepts",
                   "moving_windows", "bottom_without_match", "side_matches")
 

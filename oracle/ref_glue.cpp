@@ -34,9 +34,28 @@ public:
     cv::Rect match_box_bottom() const { return match_rect_b; }
     cv::Rect match_box_side() const { return match_rect_s; }
 };
+// value type with the reference's interface (LocoMouse_class.hpp:33-45; ctor LocoMouse_class.cpp:3196-3202)
+class LocoMouse_LocationPrior {
+    cv::Point_<double> pos_;
+    double md_;
+    cv::Rect_<double> area_;
+
+public:
+    LocoMouse_LocationPrior(double x, double y, double md, double minx, double maxx, double miny, double maxy)
+        : pos_(x, y), md_(md), area_(minx, miny, maxx - minx, maxy - miny) {}
+    cv::Point_<double> position() const { return pos_; }
+    cv::Rect_<double> area() const { return area_; }
+    double max_distance() const { return md_; }
+};
+#include "MyMat.hpp"                      // the reference's own MyMat / MATSPARSE (MyMat/MyMat.hpp, compiled from MyMat.cpp)
+#include "_ref/ref_match_to_range.inc"    // template matchToRange (LocoMouse_class.hpp:364-374)
 class LocoMouse {
 public:
     LocoMouse_Parameters_Stub LM_PARAMS;
+    MyMat unaryCostBox(std::vector<Candidate> &p_candidates, cv::Rect &BB, std::vector<LocoMouse_LocationPrior> location_prior);
+    MATSPARSE pairwisePotential(std::vector<Candidate> &Ci, std::vector<Candidate> &Cip1, cv::Point_<double> &grid_mapping,
+                                double grid_spacing, std::vector<cv::Point_<double> > &ONGi, cv::Size ONG_size,
+                                double max_displacement_bottom, double alpha_vel_bottom, double pairwise_occluded_cost);
     std::ofstream DEBUG_TEXT;
     void imadjust(const cv::Mat &Iin, cv::Mat &Iout, double low_in, double high_in, double low_out, double high_out);
     std::vector<P22D> matchingWithVelocityConstraint(std::vector<Candidate> &Candidates_b, std::vector<Candidate> &Candidates_t,
@@ -55,6 +74,7 @@ public:
 #include "_ref/ref_nms_body.inc"      // vecmovingaverage, nmsMax, peakClustering   (LocoMouse_class.cpp:1559-1905)
 #include "_ref/ref_hpp_body.inc"      // template firstLastOverT                     (LocoMouse_class.hpp:411-442)
 #include "_ref/ref_imadjust_body.inc" // LocoMouse::imadjust                         (LocoMouse_class.cpp:3204-3242)
+#include "_ref/ref_cost_body.inc"     // unaryCostBox, pairwisePotential (LocoMouse_class.cpp:1909-2070)
 #include "_ref/ref_pair_body.inc"     // matchingWithVelocityConstraint, xDist, matchViews, checkVelCriterion (1023-1267)
 
 extern "C" {
@@ -149,6 +169,45 @@ int ref_match_views(const ref_cand *cb, int nb, const ref_cand *cs, int ns, int 
             }
     }
     return (int)P.size() * 100000 + total;
+}
+
+// unaryCostBox on a candidate list: out = the returned MyMat's column-major values (n x n_priors).
+// priors: n_priors x 7 doubles {x, y, max_distance, min_x, max_x, min_y, max_y} (the reference constructor's arguments).
+void ref_unary_cost_box(const ref_cand *c, int n, int bb_w, int bb_h, const double *priors, int n_priors, double *out) {
+    std::vector<Candidate> C;
+    for (int i = 0; i < n; ++i) C.push_back(Candidate(c[i].x, c[i].y, c[i].s));
+    std::vector<LocoMouse_LocationPrior> P;
+    for (int j = 0; j < n_priors; ++j) {
+        const double *q = priors + 7 * j;
+        P.push_back(LocoMouse_LocationPrior(q[0], q[1], q[2], q[3], q[4], q[5], q[6]));
+    }
+    cv::Rect BB(0, 0, bb_w, bb_h);
+    LocoMouse L;
+    MyMat M = L.unaryCostBox(C, BB, P);
+    for (int k = 0; k < M.Numel(); ++k) out[k] = M.getValues()[k];
+}
+
+// pairwisePotential -> the MATSPARSE it returns: jc[n_cols + 1], ir / pr [nnz]; dims = {n_rows, n_cols, nnz}.
+int ref_pairwise_potential(const ref_cand *ci, int ni, const ref_cand *cip1, int nip1, double grid_x, double grid_y, double spacing,
+                           int ong_w, int ong_h, double max_disp, double alpha_vel, double occluded_cost, int *jc, int *ir, double *pr,
+                           int cap, int *dims) {
+    std::vector<Candidate> A, B;
+    for (int i = 0; i < ni; ++i) A.push_back(Candidate(ci[i].x, ci[i].y, ci[i].s));
+    for (int i = 0; i < nip1; ++i) B.push_back(Candidate(cip1[i].x, cip1[i].y, cip1[i].s));
+    cv::Point_<double> gm(grid_x, grid_y);
+    std::vector<cv::Point_<double> > ONG((size_t)ong_w * ong_h);   // only its size is read (LocoMouse_class.cpp:1961)
+    LocoMouse L;
+    MATSPARSE S = L.pairwisePotential(A, B, gm, spacing, ONG, cv::Size(ong_w, ong_h), max_disp, alpha_vel, occluded_cost);
+    dims[0] = S.Nrows();
+    dims[1] = S.Ncols();
+    dims[2] = S.nz();
+    if (S.nz() > cap) return 1;
+    for (int c = 0; c <= S.Ncols(); ++c) jc[c] = S.getJc()[c];
+    for (int k = 0; k < S.nz(); ++k) {
+        ir[k] = S.getIr()[k];
+        pr[k] = S.getPr()[k];
+    }
+    return 0;
 }
 
 // The elementwise primitives of the shim that the pairing code calls, exposed so that tests/test_oracle_vs_cv2.py can pin

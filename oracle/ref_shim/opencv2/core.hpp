@@ -45,11 +45,15 @@ template <typename T>
 inline T saturate_cast(int v) { return (T)v; }
 
 template <typename T>
+class Rect_;
+template <typename T>
 class Point_ {
 public:
     T x, y;
     Point_() : x(0), y(0) {}
     Point_(T x_, T y_) : x(x_), y(y_) {}
+    T dot(const Point_ &p) const { return saturate_cast<T>(x * p.x + y * p.y); }   // cv::Point_::dot
+    bool inside(const Rect_<T> &r) const;                                            // cv::Rect_::contains: half-open
     template <typename U>
     operator Point_<U>() const { return Point_<U>(saturate_cast<U>(x), saturate_cast<U>(y)); }
     Point_ &operator+=(const Point_ &o) { x += o.x; y += o.y; return *this; }
@@ -57,6 +61,8 @@ public:
 };
 template <typename T>
 inline Point_<T> operator+(const Point_<T> &a, const Point_<T> &b) { return Point_<T>(a.x + b.x, a.y + b.y); }
+template <typename T>
+inline Point_<T> operator-(const Point_<T> &a, const Point_<T> &b) { return Point_<T>(saturate_cast<T>(a.x - b.x), saturate_cast<T>(a.y - b.y)); }
 template <typename T>
 inline Point_<T> operator*(const Point_<T> &a, double b) { return Point_<T>(saturate_cast<T>(a.x * b), saturate_cast<T>(a.y * b)); }
 template <typename T>
@@ -85,6 +91,8 @@ public:
     Rect_ &operator+=(const Point_<T> &p) { x += p.x; y += p.y; return *this; }
     Rect_ &operator-=(const Point_<T> &p) { x -= p.x; y -= p.y; return *this; }
 };
+template <typename T>
+inline bool Point_<T>::inside(const Rect_<T> &r) const { return r.x <= x && x < r.x + r.width && r.y <= y && y < r.y + r.height; }
 // intersection; empty -> Rect() (all zeros), as cv::Rect_::operator&=
 template <typename T>
 inline Rect_<T> operator&(const Rect_<T> &a, const Rect_<T> &b) {

@@ -138,3 +138,34 @@ def match_views(cb, cs, vel_check, tsize_b, tsize_s, T, I, Iprev, x0, y0b, y0s, 
         out.append([(int(my[o + j]), float(ms[o + j])) for j in range(m)])
         o += m
     return out
+
+
+def unary_cost_box(cands, bb_w, bb_h, prior_rows):
+    """The reference's LocoMouse::unaryCostBox (LocoMouse_class.cpp:1909-1952) returning its own MyMat.
+    prior_rows: (x, y, max_distance, min_x, max_x, min_y, max_y) per prior -> (n, n_priors) array."""
+    L = lib()
+    L.ref_unary_cost_box.restype = None
+    c = np.array([tuple(k) for k in cands], CAND) if len(cands) else np.zeros(0, CAND)
+    pr = np.ascontiguousarray(prior_rows, np.float64).reshape(-1, 7)
+    out = np.zeros(max(len(c) * len(pr), 1), np.float64)
+    L.ref_unary_cost_box(C.c_void_p(c.ctypes.data), len(c), int(bb_w), int(bb_h), C.c_void_p(pr.ctypes.data), len(pr), C.c_void_p(out.ctypes.data))
+    return out[:len(c) * len(pr)].reshape(len(pr), len(c)).T.copy()
+
+
+def pairwise_potential(ci, cip1, grid_x, grid_y, spacing, ong_w, ong_h, max_disp, alpha_vel, occluded_cost, cap=1 << 16):
+    """The reference's LocoMouse::pairwisePotential (LocoMouse_class.cpp:1954-2070) and its own MATSPARSE (MyMat.cpp:141-178)
+    -> (n_rows, n_cols, jc, ir, pr)."""
+    L = lib()
+    L.ref_pairwise_potential.restype = C.c_int
+    a = np.array([tuple(k) for k in ci], CAND) if len(ci) else np.zeros(0, CAND)
+    b = np.array([tuple(k) for k in cip1], CAND) if len(cip1) else np.zeros(0, CAND)
+    jc = np.zeros(len(a) + ong_w * ong_h + 1, np.int32)
+    ir = np.zeros(cap, np.int32)
+    pr = np.zeros(cap, np.float64)
+    dims = np.zeros(3, np.int32)
+    rc = L.ref_pairwise_potential(C.c_void_p(a.ctypes.data), len(a), C.c_void_p(b.ctypes.data), len(b), C.c_double(grid_x), C.c_double(grid_y),
+                                  C.c_double(spacing), int(ong_w), int(ong_h), C.c_double(max_disp), C.c_double(alpha_vel),
+                                  C.c_double(occluded_cost), C.c_void_p(jc.ctypes.data), C.c_void_p(ir.ctypes.data), C.c_void_p(pr.ctypes.data),
+                                  cap, C.c_void_p(dims.ctypes.data))
+    assert rc == 0
+    return int(dims[0]), int(dims[1]), jc, ir[:dims[2]].copy(), pr[:dims[2]].copy()

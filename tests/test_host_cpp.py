@@ -187,3 +187,58 @@ def test_tm_de_pass1_on_device_then_detection(tmp_path, oracle):
             cb, cs, matches = feats[feat]
             assert cb == ref.candidates_bottom(f, feat) and cs == ref.candidates_side(f, feat)
             assert matches == [w[1] for w in ref.p22d(f, feat)]
+
+
+@pytest.mark.gpu
+def test_main_sequence_builds_tracker_costs_on_device(tmp_path, oracle):
+    """With a location_prior in the configuration the main.cpp sequence's computeUnaryCostsBottom / computePairwiseCostsBottom
+    (LocoMouse_class.cpp:873-919) hand out, per frame, the MyMat / MATSPARSE that the device built for the whole chunk;
+    chunks of 3 frames exercise the one-frame halo of the pairwise transition.  Everything equals the oracle bit for bit."""
+    from locomouse_cpp_b200 import synth
+    from locomouse_cpp_b200.types import location_priors, pairwise_params
+
+    exe = _build_driver()
+    spec = synth.SynthSpec(method="TM")
+    n = 8
+    cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(spec, n, seed=1000)
+    frames = frames.numpy()
+    ref = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=4)
+    rows = [(0.8, 0.25, 0.5, 0.4, 1.0, 0.0, 0.5), (0.8, 0.75, 0.5, 0.4, 1.0, 0.5, 1.0), (0.3, 0.25, 0.4, 0.0, 0.6, 0.0, 0.5),
+            (0.3, 0.75, 0.35, 0.0, 0.6, 0.5, 1.0), (0.95, 0.5, 0.6, 0.5, 1.0, 0.0, 1.0)]
+    flat = ", ".join(repr(float(v)) for r in rows for v in r)
+    write_problem_files(tmp_path, cfg, model, bkg, calib, frames, bx, bs, bb, spec.side_h,
+                        extra_cfg=f"batch_frames: 3\nlocation_prior: [{flat}]\nmax_displacement_bottom: 40\n")
+    p = subprocess.run([exe, "1", str(tmp_path / "config.yml"), str(tmp_path / "video.lmv"), str(tmp_path / "bkg.lmi"),
+                        str(tmp_path / "model.lmm"), str(tmp_path / "calib.lmc"), "R", str(tmp_path)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    buf = (tmp_path / "costs_video.lmo").read_bytes()
+    assert buf[:4] == b"LMC1"
+    (nf,) = struct.unpack_from("<i", buf, 4)
+    assert nf == n
+    off = 8
+    pri = [location_priors(rows[:4]), location_priors(rows[4:])]
+    P = pairwise_params(cfg.bb_w, cfg.bb_h_bottom, max_displacement=40)
+    nnz = 0
+    for f in range(n):
+        for feat in range(2):
+            nr, nc = struct.unpack_from("<ii", buf, off)
+            off += 8
+            U = np.frombuffer(buf, np.float64, nr * nc, off).reshape(nc, nr).T
+            off += 8 * nr * nc
+            want = oracle.unary_cost_box(ref.candidates_bottom(f, feat), cfg.bb_w, cfg.bb_h_bottom, pri[feat])
+            assert U.shape == want.shape and np.array_equal(np.ascontiguousarray(U).view(np.uint64), want.view(np.uint64)), (f, feat)
+            if f == 0:
+                continue
+            sr, sc, nz = struct.unpack_from("<iii", buf, off)
+            off += 12
+            jc = np.frombuffer(buf, np.int32, sc + 1, off)
+            off += 4 * (sc + 1)
+            ir = np.frombuffer(buf, np.int32, nz, off)
+            off += 4 * nz
+            pr = np.frombuffer(buf, np.float64, nz, off)
+            off += 8 * nz
+            wr, wc, wjc, wir, wpr = oracle.pairwise_potential(ref.candidates_bottom(f - 1, feat), ref.candidates_bottom(f, feat), P)
+            assert (sr, sc) == (wr, wc) and np.array_equal(jc, wjc) and np.array_equal(ir, wir), (f, feat)
+            assert np.array_equal(pr.view(np.uint64), wpr.view(np.uint64)), (f, feat)
+            nnz += nz
+    assert off == len(buf) and nnz > n * P.ong_w * P.ong_h

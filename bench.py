@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES_PER_STEP, help="frames per step per GPU (default: the 10k config)")
     ap.add_argument("--cpu-sample", type=int, default=640, help="frames of the workload timed on the CPU oracle (1 thread)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="library option for the measured arm (lm_set_option), e.g. streams=3")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -189,6 +190,9 @@ def main():
     frames, bx, bs, bb = synth.make_video(spec, n, 1000 + rank, dev, bkg)
     torch.cuda.synchronize()
     det = Detector(cfg, model, bkg, calib, device=local)
+    for kv in args.opt:
+        det.set_option(kv.split('=')[0], int(kv.split('=')[1]))
+    n_streams = int(det.info("streams"))
     fma_frame = algorithmic_fma_per_frame(cfg, model)
 
     # ---- value: frames resident in HBM ------------------------------------------------------------------
@@ -242,7 +246,7 @@ def main():
     for k in stage:
         stage[k] *= args.steps / isteps   # normalised to the number of timed steps, as the fields below assume
     ms_screen *= args.steps / isteps
-    det.set_option("streams", 2)
+    det.set_option("streams", n_streams)
     det.detect_batch(frames[: min(n, 512)], bx[: min(n, 512)], bs[: min(n, 512)], bb[: min(n, 512)])
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------
@@ -456,7 +460,7 @@ def main():
                            "subbatch": subb},
                 "timing": {"wall_ms_per_step": wall / args.steps * 1e3, "device_event_ms_per_step": dev_ms / args.steps,
                            "stage_ms_per_step_serial": {k: v / args.steps for k, v in stage.items()},
-                           "note": "value/wall/device_event: two-stream overlapped pipeline; stage_ms_per_step_serial and the roofline "
+                           "streams": n_streams, "note": "value/wall/device_event: overlapped multi-stream pipeline; stage_ms_per_step_serial and the roofline "
                                    "launch times: the same steps with the library option streams=1 (kernels strictly serial)"},
                 "clocks": sampler.summary(), "gpu_launches": int(launches), "overflow_frames": overflow,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "pass1_tm_de": pass1, "cost_builders": costs}

@@ -152,9 +152,11 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device,
  *             outputs; 0: dense exact FP32 kernel only.  All three produce bit-identical results (the screen
  *             only discards outputs proven <= 0).
  *  "subbatch" frames per internal sub-batch (default 512).
- *  "streams"  n = 2 (default) .. 4: n consecutive sub-batches are in flight on n streams with separate scratch, so the
- *             latency-bound kernels of one overlap the tensor-core kernel of the next; 1: all kernels strictly serial
- *             (used when timing a single kernel with events).
+ *  "streams"  n = 2 .. 4 (default 4): n consecutive sub-batches are in flight on n streams with separate scratch (about
+ *             1 GB each at the default sub-batch), so the latency-bound kernels of some overlap the tensor-core kernel of
+ *             another; 1: all kernels strictly serial (used when timing a single kernel with events).
+ *  "screen_stages"  2 (default) .. 4: depth of the CTA-pair screen's window-tile ring; 2 leaves 27 kB of each SM's shared
+ *             memory to co-resident CTAs of the other sub-batches' small kernels.
  *  "screen_layout"  bit 0: the tail template shares the paw + snout operand of the CTA-pair screen (N = 192),
  *             bit 1: y tiles stacked over the frames of a sub-batch (default 3; never changes results).
  *  "screen_priority"  1 (default): the tensor-core screen kernels run on a high-priority stream.

@@ -311,27 +311,30 @@ size_t nms_smem(int P, int cand_cap) {
 int lm_launch_nms(const LmBatch &b, cudaStream_t s) {
     int P = 2;
     while (P < b.det_cap) P <<= 1;
-    // Two size classes: lists of up to SMALL positives run with a small shared-memory footprint (several
-    // CTAs per SM); the rare longer lists run in a second launch sized for det_cap (its other CTAs exit at once).
-    const int SMALL = 1024;
+    // Size classes: lists of up to SMALL (then MID) positives run with a small shared-memory footprint (several CTAs per
+    // SM, and room next to a resident k_screen2 CTA of the neighbouring sub-batch); the rare longer lists run in a launch
+    // sized for det_cap (the other CTAs of each launch exit at once).
+    int SMALL = 1024, MID = 2048;
+    if (const char *e = getenv("LM_NMS_SMALL")) SMALL = std::max(2, atoi(e));
     static LmDevOnce once;
     if (once.first()) {
         cudaFuncSetAttribute(k_nms_bottom, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_nms_side, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     }
     int launches = 0;
-    const int Ps = P < SMALL ? P : SMALL;
-    k_nms_bottom<<<b.B * 2, NMS_THREADS, nms_smem(Ps, b.cand_cap), s>>>(b, Ps, -1, Ps);
-    ++launches;
-    if (P > Ps) {
-        k_nms_bottom<<<b.B * 2, NMS_THREADS, nms_smem(P, b.cand_cap), s>>>(b, P, Ps, P);
-        ++launches;
-    }
-    k_nms_side<<<b.B * 2, NMS_THREADS, nms_smem(Ps, b.cand_cap), s>>>(b, Ps, -1, Ps);
-    ++launches;
-    if (P > Ps) {
-        k_nms_side<<<b.B * 2, NMS_THREADS, nms_smem(P, b.cand_cap), s>>>(b, P, Ps, P);
-        ++launches;
+    int cls[4], ncls = 0;
+    for (int c : {SMALL, MID, P})
+        if (ncls == 0 || (c > cls[ncls - 1] && cls[ncls - 1] < P)) cls[ncls++] = std::min(c, P);
+    for (int view = 0; view < 2; ++view) {
+        int lo = -1;
+        for (int q = 0; q < ncls; ++q) {
+            if (view == 0)
+                k_nms_bottom<<<b.B * 2, NMS_THREADS, nms_smem(cls[q], b.cand_cap), s>>>(b, cls[q], lo, cls[q]);
+            else
+                k_nms_side<<<b.B * 2, NMS_THREADS, nms_smem(cls[q], b.cand_cap), s>>>(b, cls[q], lo, cls[q]);
+            ++launches;
+            lo = cls[q];
+        }
     }
     return launches;
 }

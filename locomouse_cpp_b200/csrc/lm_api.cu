@@ -23,6 +23,7 @@ struct lm_ctx {
     cudaStream_t stream = nullptr, stream_more[NSLOT - 1] = {}, copy_stream = nullptr;
     cudaStream_t stream_hi = nullptr; // highest priority: the tensor-core screen kernels of all slots (option screen_priority)
     int opt_screen_priority = 1;
+    int opt_screen_stages = 2;        // deepest window-tile ring of k_screen2 (2..4): fewer stages leave shared memory for co-resident CTAs
     lm_config cfg{};
     bool configured = false, model_set = false, bkg_set = false, calib_set = false;
     LmGeom geom{};
@@ -35,7 +36,7 @@ struct lm_ctx {
     int opt_screen = 2;               // 0: dense exact kernel only, 1: tensor-core screen, one CTA per tile, 2: CTA pairs
     int opt_subbatch = 512;
     int opt_screen_layout = 3;        // k_screen2 job layout: bit 0 = tail shares the paw + snout job (N = 192), bit 1 = stacked y tiles
-    int opt_streams = 2;              // n > 1: n consecutive sub-batches in flight on n streams, 1: strictly serial kernels
+    int opt_streams = 4;              // n > 1: n consecutive sub-batches in flight on n streams, 1: strictly serial kernels
     LmScreenHost scr_info[2][3] = {};
     int t_rows[2][3] = {}, t_cols[2][3] = {};
     double t_rho[2][3] = {};
@@ -222,7 +223,7 @@ int prepare_screen(lm_ctx *ctx, LmBatch &b, int want, size_t B) {
             S.ks = std::max(S.ks, (31 + H.dx + b.tmpl[v][S.f[t]].kw + 31) / 32);
         }
         S.rows = (128 + S.KH - 1 + 7) & ~7;
-        for (S.stages = 4; S.stages >= 2; --S.stages)
+        for (S.stages = std::max(2, std::min(4, ctx->opt_screen_stages)); S.stages >= 2; --S.stages)
             if (lm_screen2_smem_bytes(S.KH, S.ks, S.rows, 32 * S.nplanes, S.stages) <= smem_limit) return true;
         return false;
     };
@@ -934,6 +935,9 @@ int lm_set_option(lm_ctx *ctx, const char *name, int64_t value) {
     } else if (!strcmp(name, "screen_layout")) {
         if (value < 0 || value > 3) return fail(ctx, LM_ERR_INVALID, "option screen_layout must be in [0, 3]");
         ctx->opt_screen_layout = (int)value;
+    } else if (!strcmp(name, "screen_stages")) {
+        if (value < 2 || value > 4) return fail(ctx, LM_ERR_INVALID, "option screen_stages must be in [2, 4]");
+        ctx->opt_screen_stages = (int)value;
     } else if (!strcmp(name, "screen_priority")) {
         ctx->opt_screen_priority = value != 0;
     } else if (!strcmp(name, "streams")) {
@@ -988,6 +992,10 @@ int lm_get_info(const lm_ctx *ctx, const char *name, double *value) {
     }
     if (!strcmp(name, "ms_screen")) {  // device time of k_screen alone in the last lm_detect_batch call
         *value = (double)ctx->ms_screen;
+        return LM_OK;
+    }
+    if (!strcmp(name, "streams")) {
+        *value = (double)ctx->opt_streams;
         return LM_OK;
     }
     if (!strcmp(name, "subbatch")) {

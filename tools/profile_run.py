@@ -17,6 +17,7 @@ ap.add_argument("--screen", type=int, default=2)
 ap.add_argument("--streams", type=int, default=2)
 ap.add_argument("--layout", type=int, default=3)
 ap.add_argument("--prio", type=int, default=1)
+ap.add_argument("--stages", type=int, default=4)
 ap.add_argument("--subbatch", type=int, default=0)
 args = ap.parse_args()
 spec = synth.SynthSpec(scale=args.scale) if args.scale == 1 else synth.SynthSpec(scale=args.scale, cand_cap=128, match_cap=512)
@@ -28,6 +29,7 @@ det.set_option("screen", args.screen)
 det.set_option("streams", args.streams)
 det.set_option("screen_layout", args.layout)
 det.set_option("screen_priority", args.prio)
+det.set_option("screen_stages", args.stages)
 if args.subbatch:
     det.set_option("subbatch", args.subbatch)
 for _ in range(args.iters):

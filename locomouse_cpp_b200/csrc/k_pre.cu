@@ -24,67 +24,114 @@ __device__ __forceinline__ const uint8_t *frame_ptr(const LmBatch &b, int i) {  
 
 // ---- k_minmax ------------------------------------------------------------------------------------
 // minmax[slot] = (255 - min, max) so that both reduce with atomicMax from a zero-initialised buffer.
-__global__ void __launch_bounds__(256) k_minmax(const __grid_constant__ LmBatch b, int slot0) {
-    const int slot = slot0 + blockIdx.y;  // slot 0 = halo frame (-1)
-    const uint8_t *F = frame_ptr(b, slot - 1);
-    if (!F) return;
+// The only pass over whole raw frames, hence HBM-bound.  A CTA owns an 8 kB pixel range (two 16-byte vectors per thread)
+// and walks MM_GROUP consecutive frames with the background vectors of that range held in registers, so the L2-resident
+// background costs 1/MM_GROUP of the frame traffic instead of doubling it; two frames' loads are in flight per thread
+// (streaming loads: a frame is read once).  Per-frame partials go warp -> shared memory, one barrier per CTA at the end.
+constexpr int MM_GROUP = 8;
+constexpr int MM_VEC = 2;
+
+// One 32-bit word = four pixels.  Bytes are widened to s16x2 lanes (even / odd bytes) and go through the DPX
+// instructions: d = max(f + (-k), 0) is one VIADDMNMX.S16x2.RELU, the running min / max one VIMNMX3.S16x2 each -- six
+// instructions per four pixels (the byte-SIMD intrinsics __vsubus4 / __vminu4 are emulated with dozens of instructions
+// on this architecture and made the pass ALU-bound at 40 % of the HBM rate).  nke / nko: the background's even / odd
+// bytes negated per 16-bit lane, prepared once per CTA.
+__device__ __forceinline__ void mm_word(uint32_t &mn, uint32_t &mx, uint32_t f, uint32_t nke, uint32_t nko) {
+    const uint32_t fe = f & 0x00ff00ffu, fo = (f >> 8) & 0x00ff00ffu;
+    const uint32_t de = __viaddmax_s16x2_relu(fe, nke, 0u), dd = __viaddmax_s16x2_relu(fo, nko, 0u);
+    mn = __vimin3_s16x2(mn, de, dd);
+    mx = __vimax3_s16x2(mx, de, dd);
+}
+struct NegBkg {
+    uint32_t e[4], o[4];
+};
+__device__ __forceinline__ NegBkg mm_neg(const uint4 &k) {
+    NegBkg r;
+    const uint32_t w[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        r.e[q] = __vneg2(w[q] & 0x00ff00ffu);
+        r.o[q] = __vneg2((w[q] >> 8) & 0x00ff00ffu);
+    }
+    return r;
+}
+__device__ __forceinline__ void mm_acc(uint32_t &mn, uint32_t &mx, const uint4 &f, const NegBkg &k) {
+    mm_word(mn, mx, f.x, k.e[0], k.o[0]);
+    mm_word(mn, mx, f.y, k.e[1], k.o[1]);
+    mm_word(mn, mx, f.z, k.e[2], k.o[2]);
+    mm_word(mn, mx, f.w, k.e[3], k.o[3]);
+}
+
+__global__ void __launch_bounds__(256, 6) k_minmax(const __grid_constant__ LmBatch b, int slot0, int nslots) {
+    __shared__ uint32_t slo[MM_GROUP][8], shi[MM_GROUP][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t n = b.frame_bytes;
     const uint8_t *K = b.bkg;
-    uint32_t mn = 0xffffffffu, mx = 0u;
-    const bool vec = ((reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(K)) & 15) == 0;
-    const int64_t nvec = vec ? (n >> 4) : 0;
-    const uint4 *F4 = reinterpret_cast<const uint4 *>(F);
-    const uint4 *K4 = reinterpret_cast<const uint4 *>(K);
-    // four independent 16-byte loads of the frame (and of the L2-resident background) in flight per thread: the pass is
-    // HBM-bound and a dependent one-load-per-iteration loop leaves the memory pipeline half empty
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < nvec; i += 4 * stride) {
-        uint4 f[4], k[4];
+    const int g0 = blockIdx.y * MM_GROUP;
+    const int ng = min(MM_GROUP, nslots - g0);
+    // all frames of a batch share alignment (contiguous, frame_bytes apart) unless frame_bytes is odd; checked per frame
+    const int64_t v0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * MM_VEC;  // first 16-byte vector of this thread
+    const int64_t nvec = n >> 4;
+    NegBkg k[MM_VEC];
+    const bool kvec = (reinterpret_cast<uintptr_t>(K) & 15) == 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) f[q] = __ldcs(F4 + i + q * stride);  // streamed once: do not keep in L2
+    for (int q = 0; q < MM_VEC; ++q)
+        k[q] = mm_neg((kvec && v0 + q < nvec) ? __ldg(reinterpret_cast<const uint4 *>(K) + v0 + q) : make_uint4(0, 0, 0, 0));
+    for (int g = 0; g < ng; ++g) {
+        const int slot = slot0 + g0 + g;  // slot 0 = halo frame (-1)
+        const uint8_t *F = frame_ptr(b, slot - 1);
+        uint32_t mn = 0x00ff00ffu, mx = 0u;  // s16x2 lanes
+        if (F) {
+            if (kvec && (reinterpret_cast<uintptr_t>(F) & 15) == 0) {
+                const uint4 *F4 = reinterpret_cast<const uint4 *>(F);
+                uint4 f[MM_VEC];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) k[q] = __ldg(K4 + i + q * stride);
+                for (int q = 0; q < MM_VEC; ++q) f[q] = (v0 + q < nvec) ? __ldcs(F4 + v0 + q) : make_uint4(0, 0, 0, 0);  // streamed once
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t d0 = __vsubus4(f[q].x, k[q].x), d1 = __vsubus4(f[q].y, k[q].y), d2 = __vsubus4(f[q].z, k[q].z), d3 = __vsubus4(f[q].w, k[q].w);
-            mn = __vminu4(mn, __vminu4(__vminu4(d0, d1), __vminu4(d2, d3)));
-            mx = __vmaxu4(mx, __vmaxu4(__vmaxu4(d0, d1), __vmaxu4(d2, d3)));
+                for (int q = 0; q < MM_VEC; ++q)
+                    if (v0 + q < nvec) mm_acc(mn, mx, f[q], k[q]);
+                // bytes after the last whole vector: the thread that owns the vector slot right after them
+                if (v0 <= nvec && nvec < v0 + MM_VEC)
+                    for (int64_t t = nvec << 4; t < n; ++t) {
+                        const int d = (int)F[t] - (int)K[t];
+                        const uint32_t u = d < 0 ? 0u : (uint32_t)d;
+                        mn = __vimin3_s16x2(mn, u * 0x00010001u, u * 0x00010001u);
+                        mx = __vimax3_s16x2(mx, u * 0x00010001u, u * 0x00010001u);
+                    }
+            } else {  // unaligned frames (odd frame size or caller pointer): bytewise over this thread's range
+                const int64_t t0 = v0 << 4, t1 = min(n, (v0 + MM_VEC) << 4);
+                for (int64_t t = t0; t < t1; ++t) {
+                    const int d = (int)F[t] - (int)K[t];
+                    const uint32_t u = d < 0 ? 0u : (uint32_t)d;
+                    mn = __vimin3_s16x2(mn, u * 0x00010001u, u * 0x00010001u);
+                    mx = __vimax3_s16x2(mx, u * 0x00010001u, u * 0x00010001u);
+                }
+            }
         }
-    }
-    for (; i < nvec; i += stride) {
-        uint4 f = __ldg(F4 + i), k = __ldg(K4 + i);
-        uint32_t d0 = __vsubus4(f.x, k.x), d1 = __vsubus4(f.y, k.y), d2 = __vsubus4(f.z, k.z), d3 = __vsubus4(f.w, k.w);
-        mn = __vminu4(mn, __vminu4(__vminu4(d0, d1), __vminu4(d2, d3)));
-        mx = __vmaxu4(mx, __vmaxu4(__vmaxu4(d0, d1), __vmaxu4(d2, d3)));
-    }
-    for (int64_t t = (nvec << 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
-        int d = (int)F[t] - (int)K[t];
-        uint32_t u = d < 0 ? 0u : (uint32_t)d;
-        mn = __vminu4(mn, u * 0x01010101u);
-        mx = __vmaxu4(mx, u * 0x01010101u);
-    }
-    uint32_t lo = min(min(mn & 0xff, (mn >> 8) & 0xff), min((mn >> 16) & 0xff, mn >> 24));
-    uint32_t hi = max(max(mx & 0xff, (mx >> 8) & 0xff), max((mx >> 16) & 0xff, mx >> 24));
+        uint32_t lo = min(mn & 0xffffu, mn >> 16);
+        uint32_t hi = max(mx & 0xffffu, mx >> 16);
 #pragma unroll
-    for (int d = 16; d; d >>= 1) {
-        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
-    }
-    __shared__ uint32_t slo[8], shi[8];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) {
-        slo[w] = lo;
-        shi[w] = hi;
+        for (int d = 16; d; d >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+        }
+        if (lane == 0) {
+            slo[g][w] = lo;
+            shi[g][w] = hi;
+        }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int q = 1; q < (int)(blockDim.x >> 5); ++q) {
-            lo = min(lo, slo[q]);
-            hi = max(hi, shi[q]);
+    if (threadIdx.x < ng) {
+        const int g = threadIdx.x, slot = slot0 + g0 + g;
+        if (frame_ptr(b, slot - 1)) {
+            uint32_t lo = slo[g][0], hi = shi[g][0];
+            for (int q = 1; q < 8; ++q) {
+                lo = min(lo, slo[g][q]);
+                hi = max(hi, shi[g][q]);
+            }
+            atomicMax(&b.minmax[slot * 2 + 0], (int)(255u - lo));
+            atomicMax(&b.minmax[slot * 2 + 1], (int)hi);
         }
-        atomicMax(&b.minmax[slot * 2 + 0], (int)(255u - lo));
-        atomicMax(&b.minmax[slot * 2 + 1], (int)hi);
     }
 }
 
@@ -159,11 +206,9 @@ int lm_launch_minmax(const LmBatch &b, cudaStream_t s) {
     const int slot0 = b.prev ? 0 : 1;
     const int nslots = b.B + 1 - slot0;
     if (nslots <= 0) return 0;
-    int64_t nvec = b.frame_bytes >> 4;
-    int bx = (int)((nvec + 256 * 8 - 1) / (256 * 8));
-    if (bx < 1) bx = 1;
-    if (bx > 64) bx = 64;
-    k_minmax<<<dim3(bx, nslots), 256, 0, s>>>(b, slot0);
+    const int64_t nvec = (b.frame_bytes >> 4) + 1;  // + 1: the slot that owns the bytes after the last whole vector
+    const int bx = (int)((nvec + 256 * MM_VEC - 1) / (256 * MM_VEC));
+    k_minmax<<<dim3(bx, (nslots + MM_GROUP - 1) / MM_GROUP), 256, 0, s>>>(b, slot0, nslots);
     k_lut<<<nslots, 256, 0, s>>>(b, slot0);
     return 2;
 }

@@ -858,10 +858,10 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
         b.ev_screen_go = ctx->ev_go[ring];
         cudaEvent_t *ev = ctx->ev_stage[ring];
         CK(cudaStreamWaitEvent(st, ctx->ev_h2d[ring], 0));
-        CK(cudaEventRecord(ev[0], st));
         CK(cudaMemsetAsync(b.minmax, 0, (size_t)(B + 1) * 2 * 4, st));
         CK(cudaMemsetAsync(b.det_count, 0, (size_t)B * 4 * 4, st));
         CK(cudaMemsetAsync(b.flags, 0, (size_t)B * 4, st));
+        CK(cudaEventRecord(ev[0], st));
         int nl;
         if ((nl = lm_launch_minmax(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "minmax launch failed");
         ctx->launches += nl;

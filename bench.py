@@ -374,7 +374,7 @@ def main():
             t1 = time.perf_counter()
             for feat in range(2):
                 det.unary_costs(res, feat, cfg.bb_w, cfg.bb_h_bottom, pri)
-                det.pairwise_costs(res, feat, pw, cap=2 * len(ir) + 1024)
+                det.pairwise_costs(res, feat, pw, cap=len(ir) + len(ir) // 8 + 1024)
             dt1 = time.perf_counter() - t1
             m = min(n, 512)
             t2 = time.perf_counter()

@@ -24,7 +24,8 @@
 namespace {
 
 constexpr int TAIL_THREADS = 256;
-constexpr int RUNCAP = 3072;
+constexpr int RUNCAP = 3072;               // largest run capacity the kernel's 16-bit run indices are used with
+constexpr int TAIL_RUNCAP_DEFAULT = 1536;
 
 struct TailSmem {
     uint32_t *bits;      // [rows][wpr] input bit image (row-major words)
@@ -300,17 +301,18 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ L
     S.bits = reinterpret_cast<uint32_t *>(p); p += (size_t)hmax * wpr * 4;
     S.obits = reinterpret_cast<uint32_t *>(p); p += (size_t)hmax * wpr * 4;
     S.rowfirst = reinterpret_cast<int *>(p); p += (size_t)(hmax + 1) * 4;
-    S.parent = reinterpret_cast<int *>(p); p += (size_t)RUNCAP * 4;
-    S.area = reinterpret_cast<int *>(p); p += (size_t)RUNCAP * 4;
-    S.key = reinterpret_cast<int *>(p); p += (size_t)RUNCAP * 4;
+    const size_t rcap = (size_t)((runcap > 1 ? runcap : 1) + 63) & ~(size_t)63;  // run arrays are sized for the launch's threshold
+    S.parent = reinterpret_cast<int *>(p); p += rcap * 4;
+    S.area = reinterpret_cast<int *>(p); p += rcap * 4;
+    S.key = reinterpret_cast<int *>(p); p += rcap * 4;
     S.colany = reinterpret_cast<int *>(p); p += (size_t)cols * 4;
     int *cnt_b = reinterpret_cast<int *>(p); p += (size_t)cols * 4;
     int *sum_b = reinterpret_cast<int *>(p); p += (size_t)cols * 4;
     int *cnt_s = reinterpret_cast<int *>(p); p += (size_t)cols * 4;
     int *sum_s = reinterpret_cast<int *>(p); p += (size_t)cols * 4;
-    S.rrow = reinterpret_cast<unsigned short *>(p); p += (size_t)RUNCAP * 2;
-    S.rx0 = reinterpret_cast<unsigned short *>(p); p += (size_t)RUNCAP * 2;
-    S.rx1 = reinterpret_cast<unsigned short *>(p); p += (size_t)RUNCAP * 2;
+    S.rrow = reinterpret_cast<unsigned short *>(p); p += rcap * 2;
+    S.rx0 = reinterpret_cast<unsigned short *>(p); p += rcap * 2;
+    S.rx1 = reinterpret_cast<unsigned short *>(p); p += rcap * 2;
     __shared__ int scratch[40];
     __shared__ unsigned long long s_best;
     __shared__ int s_first, s_last;
@@ -478,11 +480,12 @@ __global__ void __launch_bounds__(SLOW_THREADS) k_tail_slow(const __grid_constan
     write_tracks(b, f, s_first, s_last, cnt_b, sum_b, cnt_s, sum_s);
 }
 
-size_t tail_smem(const LmBatch &b) {
+size_t tail_smem(const LmBatch &b, int runcap) {
+    const size_t rcap = (size_t)((runcap > 1 ? runcap : 1) + 63) & ~(size_t)63;
     const int hmax = b.bb_h[0] > b.bb_h[1] ? b.bb_h[0] : b.bb_h[1];
     const int wpr = (b.tail_w + 31) >> 5;
-    size_t s = (size_t)hmax * wpr * 4 * 2 + (size_t)(hmax + 1) * 4 + (size_t)RUNCAP * 4 * 3 + (size_t)b.tail_w * 4 * 5 +
-               (size_t)RUNCAP * 2 * 3;
+    size_t s = (size_t)hmax * wpr * 4 * 2 + (size_t)(hmax + 1) * 4 + rcap * 4 * 3 + (size_t)b.tail_w * 4 * 5 +
+               rcap * 2 * 3;
     return (s + 15) & ~(size_t)15;
 }
 
@@ -490,17 +493,20 @@ size_t tail_smem(const LmBatch &b) {
 
 int lm_launch_tail(const LmBatch &b, cudaStream_t s) {
     if (b.tail_w <= 0) return 0;
-    const size_t smem = tail_smem(b);
     static LmDevOnce once;
     if (once.first()) {
         cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }
     int *need_slow = b.cc_flag;
-    int runcap = RUNCAP;  // LM_TAIL_RUNCAP lowers the threshold (tests use it to exercise the slow path)
+    // Run capacity of the shared-memory path; frames with more runs take k_tail_slow.  The default keeps the footprint
+    // below a quarter of an SM (4 CTAs per SM: one wave for a 512-frame sub-batch).  LM_TAIL_RUNCAP overrides it (tests
+    // lower it to exercise the slow path).
+    int runcap = TAIL_RUNCAP_DEFAULT;
     if (const char *e = getenv("LM_TAIL_RUNCAP")) {
         int v = atoi(e);
-        if (v >= 0 && v < RUNCAP) runcap = v;
+        if (v >= 0 && v <= RUNCAP) runcap = v;
     }
+    const size_t smem = tail_smem(b, runcap);
     k_tail<<<b.B, TAIL_THREADS, smem, s>>>(b, need_slow, runcap);
     k_tail_slow<<<b.B, SLOW_THREADS, (size_t)(5 * b.tail_w) * sizeof(int), s>>>(b, need_slow);
     return 2;

@@ -152,7 +152,7 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device,
  *             outputs; 0: dense exact FP32 kernel only.  All three produce bit-identical results (the screen
  *             only discards outputs proven <= 0).
  *  "subbatch" frames per internal sub-batch (default 512).
- *  "streams"  n = 2 .. 4 (default 4): n consecutive sub-batches are in flight on n streams with separate scratch (about
+ *  "streams"  n = 2 .. 8 (default 4): n consecutive sub-batches are in flight on n streams with separate scratch (about
  *             1 GB each at the default sub-batch), so the latency-bound kernels of some overlap the tensor-core kernel of
  *             another; 1: all kernels strictly serial (used when timing a single kernel with events).
  *  "screen_stages"  2 (default) .. 4: depth of the CTA-pair screen's window-tile ring; 2 leaves 27 kB of each SM's shared

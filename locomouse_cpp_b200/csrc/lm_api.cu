@@ -19,7 +19,7 @@ std::string g_create_error;
 
 struct lm_ctx {
     int device = 0;
-    static constexpr int NSLOT = 4;   // scratch sets / compute streams: sub-batch k runs in slot k % (option streams)
+    static constexpr int NSLOT = 8;   // scratch sets / compute streams: sub-batch k runs in slot k % (option streams)
     cudaStream_t stream = nullptr, stream_more[NSLOT - 1] = {}, copy_stream = nullptr;
     cudaStream_t stream_hi = nullptr; // highest priority: the tensor-core screen kernels of all slots (option screen_priority)
     int opt_screen_priority = 1;
@@ -48,7 +48,7 @@ struct lm_ctx {
     int nsets = 0;                    // scratch sets allocated by prepare()
     std::vector<void *> dev_allocs;   // everything cudaMalloc'ed for the scratch
     uint8_t *d_stage[2] = {};         // staged raw frames (Bcap + 1 each) when frames come from the host
-    uint32_t *d_bb[6] = {};           // [3][Bcap] per ring set
+    uint32_t *d_bb[10] = {};           // [3][Bcap] per ring set
     // result staging
     struct ResOff {
         size_t n_bottom, n_side, bottom, side, match_n, match_y, match_s, tail, flags, total;
@@ -57,7 +57,7 @@ struct lm_ctx {
     // Result staging, box arrays and events are kept per "ring set" (sub-batch index mod NRES), scratch and streams per slot
     // (index mod the number of slots in use): the host queues as many sub-batches ahead of the one it is copying out as
     // there are slots, so the device always has several sub-batches to overlap while the host copies results out.
-    static constexpr int NRES = 6;    // > the deepest lookahead (= number of slots in use)
+    static constexpr int NRES = 10;    // > the deepest lookahead (= number of slots in use)
     uint8_t *h_res[NRES] = {};        // pinned
     cudaEvent_t ev_h2d[NRES] = {}, ev_done[NRES] = {};
     cudaEvent_t ev_stage[NRES][8] = {};

@@ -110,11 +110,8 @@ __global__ void __launch_bounds__(256, 6) k_minmax(const __grid_constant__ LmBat
         }
         uint32_t lo = min(mn & 0xffffu, mn >> 16);
         uint32_t hi = max(mx & 0xffffu, mx >> 16);
-#pragma unroll
-        for (int d = 16; d; d >>= 1) {
-            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
-        }
+        lo = __reduce_min_sync(0xffffffffu, lo);   // REDUX: one instruction per warp reduction
+        hi = __reduce_max_sync(0xffffffffu, hi);
         if (lane == 0) {
             slo[g][w] = lo;
             shi[g][w] = hi;
@@ -165,37 +162,54 @@ __global__ void __launch_bounds__(256) k_lut(const __grid_constant__ LmBatch b, 
 }
 
 // ---- k_prep --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_prep(const __grid_constant__ LmBatch b) {
+// One CTA = PREP_ROWS window rows of one (frame, view); a thread owns one 4-pixel word column and walks the rows, so all
+// index arithmetic is 32-bit and incremental (the per-word division / 64-bit multiplies of a flat loop made the kernel
+// issue-bound at ~48 instructions per pixel).
+constexpr int PREP_ROWS = 16;
+
+__global__ void __launch_bounds__(128) k_prep(const __grid_constant__ LmBatch b) {
     const int f = blockIdx.y, v = blockIdx.z;
     const LmView &V = b.view[v];
     __shared__ uint8_t lut[256];
-    lut[threadIdx.x] = b.lut[(f + 1) * 256 + threadIdx.x];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = b.lut[(f + 1) * 256 + i];
     __syncthreads();
+    const int r0 = blockIdx.x * PREP_ROWS;
+    if (r0 >= V.win_h) return;
+    const int r1 = min(V.win_h, r0 + PREP_ROWS);
     const uint8_t *F = b.frames + (int64_t)f * b.frame_bytes;
+    const uint8_t *K = b.bkg;
     const int x0 = (int)b.bb_x[f] - b.bb_w + 1 - V.halo_x;
     const int ypos = (int)(v == LM_BOTTOM ? b.bb_y_bottom[f] : b.bb_y_side[f]);
     const int y0 = ypos - V.box_h + 1 - V.halo_y;
     uint8_t *W = b.win[v] + (int64_t)f * V.win_stride;
     const int words_per_row = V.win_pitch >> 2;
-    const int nwords = words_per_row * V.win_h;
-    for (int wi = blockIdx.x * blockDim.x + threadIdx.x; wi < nwords; wi += gridDim.x * blockDim.x) {
-        const int r = wi / words_per_row, c4 = (wi - r * words_per_row) << 2;
-        const int yy = y0 + r;
-        uint32_t out = 0;
-        if (yy >= 0 && yy < b.n_rows) {
+    const int n_cols = b.n_cols;
+    for (int w = threadIdx.x; w < words_per_row; w += blockDim.x) {
+        const int c4 = w << 2;
+        // image columns of this word's four pixels (after the optional mirror), -1 = outside the window or the image
+        int xs[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int c = c4 + q, xx = x0 + c;
-                if (c < V.win_w && xx >= 0 && xx < b.n_cols) {
-                    const int xs = b.flip ? (b.n_cols - 1 - xx) : xx;
-                    const int idx = __ldg(b.calib + (int64_t)yy * b.n_cols + xs);
-                    int d = (int)__ldg(F + idx) - (int)__ldg(b.bkg + idx);
-                    d = d < 0 ? 0 : d;
-                    out |= (uint32_t)lut[d] << (8 * q);
-                }
-            }
+        for (int q = 0; q < 4; ++q) {
+            const int c = c4 + q, xx = x0 + c;
+            xs[q] = (c < V.win_w && xx >= 0 && xx < n_cols) ? (b.flip ? n_cols - 1 - xx : xx) : -1;
         }
-        reinterpret_cast<uint32_t *>(W + (int64_t)r * V.win_pitch)[c4 >> 2] = out;
+        const bool any = xs[0] >= 0 || xs[1] >= 0 || xs[2] >= 0 || xs[3] >= 0;
+        for (int r = r0; r < r1; ++r) {
+            const int yy = y0 + r;
+            uint32_t out = 0;
+            if (any && yy >= 0 && yy < b.n_rows) {
+                const int32_t *crow = b.calib + (int64_t)yy * n_cols;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (xs[q] >= 0) {
+                        const int idx = __ldg(crow + xs[q]);
+                        int d = (int)__ldg(F + idx) - (int)__ldg(K + idx);
+                        d = d < 0 ? 0 : d;
+                        out |= (uint32_t)lut[d] << (8 * q);
+                    }
+            }
+            reinterpret_cast<uint32_t *>(W + (int64_t)r * V.win_pitch)[w] = out;
+        }
     }
 }
 
@@ -214,13 +228,9 @@ int lm_launch_minmax(const LmBatch &b, cudaStream_t s) {
 }
 
 int lm_launch_prep(const LmBatch &b, cudaStream_t s) {
-    int maxwords = 0;
-    for (int v = 0; v < 2; ++v) {
-        int w = (b.view[v].win_pitch >> 2) * b.view[v].win_h;
-        if (w > maxwords) maxwords = w;
-    }
-    int bx = (maxwords + 256 * 4 - 1) / (256 * 4);
-    if (bx < 1) bx = 1;
-    k_prep<<<dim3(bx, b.B, 2), 256, 0, s>>>(b);
+    int maxh = 0;
+    for (int v = 0; v < 2; ++v) maxh = b.view[v].win_h > maxh ? b.view[v].win_h : maxh;
+    const int bx = (maxh + PREP_ROWS - 1) / PREP_ROWS;
+    k_prep<<<dim3(bx < 1 ? 1 : bx, b.B, 2), 128, 0, s>>>(b);
     return 1;
 }

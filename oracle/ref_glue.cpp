@@ -17,6 +17,8 @@
 // VideoCapture / FileStorage / MyMat members that these methods never touch).  Only data the methods read is kept.
 struct LocoMouse_Parameters_Stub {
     bool LM_DEBUG = false;
+    unsigned int N_tail_points = 15;
+    int conn_comp_connectivity = 8;
 };
 class LocoMouse_Feature {  // sizes + velocity-matching boxes; boxes by the formula of LocoMouse_class.cpp:2954-2969
     cv::Size size_b, size_s;
@@ -33,6 +35,15 @@ public:
     cv::Size size_side() const { return size_s; }
     cv::Rect match_box_bottom() const { return match_rect_b; }
     cv::Rect match_box_side() const { return match_rect_s; }
+    // the tail code passes these to filter2D, whose outputs the harness injects (see ref_detect_line_candidates)
+    cv::Mat detector_bottom() const { return cv::Mat(); }
+    cv::Mat detector_side() const { return cv::Mat(); }
+    double rho_bottom() const { return 0.0; }
+    double rho_side() const { return 0.0; }
+};
+struct LocoMouse_Model_Stub {
+    LocoMouse_Feature tail;
+    LocoMouse_Model_Stub() : tail(30, 30, 30, 30) {}
 };
 // value type with the reference's interface (LocoMouse_class.hpp:33-45; ctor LocoMouse_class.cpp:3196-3202)
 class LocoMouse_LocationPrior {
@@ -52,6 +63,15 @@ public:
 class LocoMouse {
 public:
     LocoMouse_Parameters_Stub LM_PARAMS;
+    // tail stage (LocoMouse_class.hpp:188-236: same member names)
+    LocoMouse_Model_Stub M;
+    cv::Mat I_BOTTOM_MOUSE_PAD, I_SIDE_MOUSE_PAD, TAIL_MASK;
+    cv::Rect BB_BOTTOM_TAIL_PAD, BB_SIDE_TAIL_PAD, BB_UNPAD_TAIL_BOTTOM, BB_UNPAD_TAIL_SIDE;
+    std::vector<cv::Mat> TRACKS_TAIL;
+    void detectTail();
+    cv::Mat detectLineCandidates(const LocoMouse_Feature &F, const unsigned int N_line_points, cv::Mat &TAIL_MASK);
+    void selectLargestRegion(const cv::Mat &Iin, cv::Mat &Iout);
+    void exportDebugVariablesUnused();
     MyMat unaryCostBox(std::vector<Candidate> &p_candidates, cv::Rect &BB, std::vector<LocoMouse_LocationPrior> location_prior);
     MATSPARSE pairwisePotential(std::vector<Candidate> &Ci, std::vector<Candidate> &Cip1, cv::Point_<double> &grid_mapping,
                                 double grid_spacing, std::vector<cv::Point_<double> > &ONGi, cv::Size ONG_size,
@@ -74,6 +94,7 @@ public:
 #include "_ref/ref_nms_body.inc"      // vecmovingaverage, nmsMax, peakClustering   (LocoMouse_class.cpp:1559-1905)
 #include "_ref/ref_hpp_body.inc"      // template firstLastOverT                     (LocoMouse_class.hpp:411-442)
 #include "_ref/ref_imadjust_body.inc" // LocoMouse::imadjust                         (LocoMouse_class.cpp:3204-3242)
+#include "_ref/ref_tail_body.inc"     // detectTail, detectLineCandidates, selectLargestRegion (LocoMouse_class.cpp:2541-2767)
 #include "_ref/ref_cost_body.inc"     // unaryCostBox, pairwisePotential (LocoMouse_class.cpp:1909-2070)
 #include "_ref/ref_pair_body.inc"     // matchingWithVelocityConstraint, xDist, matchViews, checkVelCriterion (1023-1267)
 
@@ -169,6 +190,42 @@ int ref_match_views(const ref_cand *cb, int nb, const ref_cand *cs, int ns, int 
             }
     }
     return (int)P.size() * 100000 + total;
+}
+
+// detectTail on injected tail score maps (row-major f32, hb x tw and hs x tw: what the two filter2D calls of
+// detectLineCandidates return on the unpadded tail boxes).  cc: connectedComponentsWithStats of the REAL OpenCV (a ctypes
+// callback into cv2).  Outputs: TRACKS_TAIL.back() (3 x n_points int32) and TAIL_MASK (hb x tw, 0 / 255).
+static const float *g_maps[2];
+static int g_map_i = 0;
+static void next_map(float *dst, int rows, int cols) {
+    const float *src = g_maps[g_map_i++ & 1];
+    for (int i = 0; i < rows * cols; ++i) dst[i] = src[i];
+}
+int ref_detect_tail(const float *score_b, const float *score_s, int hb, int hs, int tw, int conn, int n_points, cv::shim_cc_fn cc,
+                    int *tracks, unsigned char *tail_mask) {
+    try {
+        LocoMouse L;
+        L.LM_PARAMS.N_tail_points = (unsigned int)n_points;
+        L.LM_PARAMS.conn_comp_connectivity = conn;
+        L.I_BOTTOM_MOUSE_PAD = cv::Mat(hb, tw, CV_8U);
+        L.I_SIDE_MOUSE_PAD = cv::Mat(hs, tw, CV_8U);
+        L.BB_BOTTOM_TAIL_PAD = L.BB_UNPAD_TAIL_BOTTOM = cv::Rect(0, 0, tw, hb);
+        L.BB_SIDE_TAIL_PAD = L.BB_UNPAD_TAIL_SIDE = cv::Rect(0, 0, tw, hs);
+        g_maps[0] = score_b;
+        g_maps[1] = score_s;
+        g_map_i = 0;
+        cv::shim_cc_callback() = cc;
+        cv::shim_filter_callback() = next_map;
+        L.detectTail();
+        const cv::Mat &T = L.TRACKS_TAIL.back();
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < n_points; ++c) tracks[r * n_points + c] = T.ptr<int>(r)[c];
+        for (int r = 0; r < hb; ++r)
+            for (int c = 0; c < tw; ++c) tail_mask[r * tw + c] = L.TAIL_MASK.ptr<unsigned char>(r)[c];
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
 }
 
 // unaryCostBox on a candidate list: out = the returned MyMat's column-major values (n x n_priors).

@@ -80,6 +80,8 @@ public:
     T area() const { return width * height; }
 };
 typedef Size_<int> Size;
+template <typename T>
+inline std::ostream &operator<<(std::ostream &o, const Size_<T> &s) { return o << "[" << s.width << " x " << s.height << "]"; }
 
 template <typename T>
 class Rect_ {
@@ -102,6 +104,8 @@ inline Rect_<T> operator&(const Rect_<T> &a, const Rect_<T> &b) {
     return Rect_<T>(x1, y1, w, h);
 }
 typedef Rect_<int> Rect;
+template <typename T>
+inline std::ostream &operator<<(std::ostream &o, const Rect_<T> &r) { return o << "[" << r.width << " x " << r.height << " from (" << r.x << ", " << r.y << ")]"; }
 
 // Row-major single-channel matrix with OpenCV's sharing semantics (copies and ROIs alias the same buffer): what
 // nmsMax / peakClustering / firstLastOverT / imadjust / xDist / matchingWithVelocityConstraint / matchViews /
@@ -114,7 +118,9 @@ typedef Rect_<int> Rect;
 #define CV_32FC1 5
 #define CV_64F 6
 #define CV_64FC1 6
-enum { NORM_MINMAX = 32, THRESH_BINARY = 0, CV_REDUCE_SUM = 0 };
+#define CV_16U 2
+#define CV_16UC1 2
+enum { NORM_MINMAX = 32, THRESH_BINARY = 0, CV_REDUCE_SUM = 0, CV_REDUCE_MAX = 2, CMP_EQ = 0, CC_STAT_AREA = 4, BORDER_CONSTANT = 0 };
 
 class Mat;
 // the one lazy expression the path relies on: alpha * A + beta, folded like cv::MatOp_AddEx
@@ -138,7 +144,7 @@ public:
         buf_.reset(new std::vector<uchar>((size_t)r * step + 1, 0));
         data = buf_->data();
     }
-    static size_t elemSizeOf(int type) { return type == CV_8U ? 1 : (type == CV_64F ? 8 : 4); }
+    static size_t elemSizeOf(int type) { return type == CV_8U ? 1 : (type == CV_16U ? 2 : (type == CV_64F ? 8 : 4)); }
     size_t elemSize() const { return elemSizeOf(type_); }
     int type() const { return type_; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
@@ -148,6 +154,23 @@ public:
     const T *ptr(int r) const { return (const T *)(data + (size_t)r * step); }
     template <typename T>
     T *ptr(int r) { return (T *)(data + (size_t)r * step); }
+    template <typename T>
+    T &at(int r, int c) { return ptr<T>(r)[c]; }
+    template <typename T>
+    const T &at(int r, int c) const { return ptr<T>(r)[c]; }
+    static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
+    static Mat zeros(Size_<int> sz, int type) { return Mat(sz.height, sz.width, type); }
+    static Mat ones(int r, int c, int type) {  // only the depths the path uses
+        Mat m(r, c, type);
+        for (int i = 0; i < r; ++i)
+            for (int j = 0; j < c; ++j) {
+                if (type == CV_32S) m.ptr<int>(i)[j] = 1;
+                else if (type == CV_8U) m.ptr<uchar>(i)[j] = 1;
+                else if (type == CV_32F) m.ptr<float>(i)[j] = 1.f;
+                else m.ptr<double>(i)[j] = 1.0;
+            }
+        return m;
+    }
     Mat operator()(const Rect_<int> &r) const {  // ROI view; out-of-range rectangles are an error as in OpenCV
         if (r.x < 0 || r.y < 0 || r.width < 0 || r.height < 0 || r.x + r.width > cols || r.y + r.height > rows)
             throw std::runtime_error("cv::Mat ROI out of range");
@@ -205,7 +228,18 @@ inline void normalize(const Mat &src, Mat &dst, double alpha, double beta, int /
     dst = out;
 }
 // cv::reduce(src, dst, dim, CV_REDUCE_SUM, CV_32FC1) for 8-bit sources: dim 0 -> one row, dim 1 -> one column
-inline void reduce(const Mat &src, Mat &dst, int dim, int /*rtype*/, int /*dtype*/) {
+inline void reduce(const Mat &src, Mat &dst, int dim, int rtype, int dtype = -1) {
+    if (rtype == CV_REDUCE_MAX) {  // 8-bit maximum, same depth (dtype -1): only dim 0 is used
+        Mat out(dim == 0 ? 1 : src.rows, dim == 0 ? src.cols : 1, CV_8U);
+        for (int r = 0; r < src.rows; ++r)
+            for (int c = 0; c < src.cols; ++c) {
+                uchar &o = dim == 0 ? out.ptr<uchar>(0)[c] : out.ptr<uchar>(r)[0];
+                o = std::max(o, src.ptr<uchar>(r)[c]);
+            }
+        dst = out;
+        return;
+    }
+    (void)dtype;
     Mat out(dim == 0 ? 1 : src.rows, dim == 0 ? src.cols : 1, CV_32F);
     for (int r = 0; r < src.rows; ++r)
         for (int c = 0; c < src.cols; ++c) {
@@ -226,12 +260,95 @@ inline void subtract(const Mat &a, const Mat &b, Mat &dst, const NoArray &, int 
     dst = out;
 }
 inline double threshold(const Mat &src, Mat &dst, double thresh, double maxval, int /*THRESH_BINARY*/) {
-    Mat out(src.rows, src.cols, CV_8U);
+    Mat out(src.rows, src.cols, src.type());  // same depth as the source: 8-bit or 32-bit float
     for (int r = 0; r < src.rows; ++r)
-        for (int c = 0; c < src.cols; ++c) out.ptr<uchar>(r)[c] = ((double)src.ptr<uchar>(r)[c] > thresh) ? (uchar)maxval : 0;
+        for (int c = 0; c < src.cols; ++c) {
+            if (src.type() == CV_32F) out.ptr<float>(r)[c] = (src.ptr<float>(r)[c] > (float)thresh) ? (float)maxval : 0.f;
+            else out.ptr<uchar>(r)[c] = ((double)src.ptr<uchar>(r)[c] > thresh) ? (uchar)maxval : 0;
+        }
     dst = out;
     return thresh;
 }
+// ---- additions for the tail code (detectLineCandidates / selectLargestRegion, LocoMouse_class.cpp:2558-2767) -----------
+inline Mat operator-(const Mat &a) {  // -Mat::ones(...): CV_32S only
+    Mat out(a.rows, a.cols, a.type());
+    for (int r = 0; r < a.rows; ++r)
+        for (int c = 0; c < a.cols; ++c) out.ptr<int>(r)[c] = -a.ptr<int>(r)[c];
+    return out;
+}
+inline Mat operator>(const Mat &a, double s) {  // CV_32F > s  ->  8-bit mask, 255 where true
+    Mat out(a.rows, a.cols, CV_8U);
+    for (int r = 0; r < a.rows; ++r)
+        for (int c = 0; c < a.cols; ++c) out.ptr<uchar>(r)[c] = ((double)a.ptr<float>(r)[c] > s) ? 255 : 0;
+    return out;
+}
+inline Mat operator&(const Mat &a, const Mat &b) {  // bitwise and of two 8-bit images
+    if (a.rows != b.rows || a.cols != b.cols) throw std::runtime_error("cv::bitwise_and: size mismatch");
+    Mat out(a.rows, a.cols, CV_8U);
+    for (int r = 0; r < a.rows; ++r)
+        for (int c = 0; c < a.cols; ++c) out.ptr<uchar>(r)[c] = a.ptr<uchar>(r)[c] & b.ptr<uchar>(r)[c];
+    return out;
+}
+inline Mat repeat(const Mat &src, int ny, int nx) {  // 8-bit
+    Mat out(src.rows * ny, src.cols * nx, CV_8U);
+    for (int r = 0; r < out.rows; ++r)
+        for (int c = 0; c < out.cols; ++c) out.ptr<uchar>(r)[c] = src.ptr<uchar>(r % src.rows)[c % src.cols];
+    return out;
+}
+inline void compare(const Mat &src, int value, Mat &dst, int /*CMP_EQ*/) {  // CV_16U labels == value -> 255 / 0
+    Mat out(src.rows, src.cols, CV_8U);
+    for (int r = 0; r < src.rows; ++r)
+        for (int c = 0; c < src.cols; ++c) out.ptr<uchar>(r)[c] = ((int)src.ptr<unsigned short>(r)[c] == value) ? 255 : 0;
+    dst = out;
+}
+struct Moments {
+    double m00, m10, m01;
+    Moments() : m00(0), m10(0), m01(0) {}
+};
+inline Moments moments(const Mat &img, bool binary) {  // raw spatial moments up to order 1 of an 8-bit image
+    Moments M;
+    for (int r = 0; r < img.rows; ++r)
+        for (int c = 0; c < img.cols; ++c) {
+            const double v = binary ? (img.ptr<uchar>(r)[c] != 0 ? 1.0 : 0.0) : (double)img.ptr<uchar>(r)[c];
+            M.m00 += v;
+            M.m10 += v * c;
+            M.m01 += v * r;
+        }
+    return M;
+}
+// cv::connectedComponentsWithStats and cv::filter2D are ALGORITHMS: the shim does not implement them.  The test harness
+// installs callbacks: the labelling runs in the REAL OpenCV (cv2, through ctypes), the filter outputs are injected.
+typedef int (*shim_cc_fn)(const uchar *img, int rows, int cols, int connectivity, unsigned short *labels, int *areas, int cap);
+typedef void (*shim_filter_fn)(float *dst, int rows, int cols);
+inline shim_cc_fn &shim_cc_callback() { static shim_cc_fn f = nullptr; return f; }
+inline shim_filter_fn &shim_filter_callback() { static shim_filter_fn f = nullptr; return f; }
+inline int connectedComponentsWithStats(const Mat &img, Mat &labels, Mat &stats, Mat & /*centroids*/, int connectivity, int /*CV_16U*/) {
+    if (!shim_cc_callback()) throw std::runtime_error("connectedComponentsWithStats: no callback installed");
+    std::vector<uchar> flat((size_t)img.rows * img.cols);
+    for (int r = 0; r < img.rows; ++r)
+        for (int c = 0; c < img.cols; ++c) flat[(size_t)r * img.cols + c] = img.ptr<uchar>(r)[c];
+    std::vector<unsigned short> lab(flat.size());
+    std::vector<int> areas(65536);
+    const int n = shim_cc_callback()(flat.data(), img.rows, img.cols, connectivity, lab.data(), areas.data(), (int)areas.size());
+    Mat L(img.rows, img.cols, CV_16U), S(n > 0 ? n : 1, 5, CV_32S);
+    for (int r = 0; r < img.rows; ++r)
+        for (int c = 0; c < img.cols; ++c) L.ptr<unsigned short>(r)[c] = lab[(size_t)r * img.cols + c];
+    for (int i = 0; i < n; ++i) S.ptr<int>(i)[CC_STAT_AREA] = areas[i];
+    labels = L;
+    stats = S;
+    return n;
+}
+inline void filter2D(const Mat &src, Mat &dst, int /*CV_32F*/, const Mat & /*kernel*/, Point_<int> /*anchor*/, double /*delta*/, int /*border*/) {
+    if (!shim_filter_callback()) throw std::runtime_error("filter2D: no callback installed");
+    Mat out(src.rows, src.cols, CV_32F);
+    std::vector<float> flat((size_t)src.rows * src.cols);
+    shim_filter_callback()(flat.data(), src.rows, src.cols);
+    for (int r = 0; r < src.rows; ++r)
+        for (int c = 0; c < src.cols; ++c) out.ptr<float>(r)[c] = flat[(size_t)r * src.cols + c];
+    dst = out;
+}
+
+inline std::ostream &operator<<(std::ostream &o, const Mat &m) { return o << "Mat(" << m.rows << " x " << m.cols << ")"; }  // debug prints only
 struct Scalar {
     double v[4];
     double operator()(int i) const { return v[i]; }

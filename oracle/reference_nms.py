@@ -169,3 +169,36 @@ def pairwise_potential(ci, cip1, grid_x, grid_y, spacing, ong_w, ong_h, max_disp
                                   cap, C.c_void_p(dims.ctypes.data))
     assert rc == 0
     return int(dims[0]), int(dims[1]), jc, ir[:dims[2]].copy(), pr[:dims[2]].copy()
+
+
+_CC_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ushort), C.POINTER(C.c_int), C.c_int)
+
+
+def detect_tail(score_bottom, score_side, conn=8, n_points=15):
+    """The reference's detectTail / detectLineCandidates / selectLargestRegion (LocoMouse_class.cpp:2541-2767) on given tail
+    score maps (what its two filter2D calls return on the unpadded tail boxes).  connectedComponentsWithStats runs in the
+    REAL OpenCV (cv2) through a callback.  Returns (tracks int32[3, n_points], tail_mask uint8[hb, tw] with 0 / 255)."""
+    import cv2
+
+    L = lib()
+    sb = np.ascontiguousarray(score_bottom, np.float32)
+    ss = np.ascontiguousarray(score_side, np.float32)
+    assert sb.shape[1] == ss.shape[1]
+
+    def cc(img, rows, cols, connectivity, labels, areas, cap):
+        a = np.ctypeslib.as_array(img, shape=(rows, cols))
+        n, lab, stats, _ = cv2.connectedComponentsWithStats(a, connectivity=connectivity, ltype=cv2.CV_16U)
+        assert n <= cap
+        np.ctypeslib.as_array(labels, shape=(rows, cols))[:] = lab
+        np.ctypeslib.as_array(areas, shape=(cap,))[:n] = stats[:, cv2.CC_STAT_AREA]
+        return int(n)
+
+    cb = _CC_FN(cc)
+    tracks = np.zeros((3, n_points), np.int32)
+    mask = np.zeros(sb.shape, np.uint8)
+    L.ref_detect_tail.restype = C.c_int
+    rc = L.ref_detect_tail(C.c_void_p(sb.ctypes.data), C.c_void_p(ss.ctypes.data), sb.shape[0], ss.shape[0], sb.shape[1], int(conn),
+                           int(n_points), cb, C.c_void_p(tracks.ctypes.data), C.c_void_p(mask.ctypes.data))
+    if rc != 0:
+        raise RuntimeError("the reference's tail code threw")
+    return tracks, mask

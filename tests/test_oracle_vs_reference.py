@@ -198,3 +198,48 @@ def test_reference_pairing_throws_when_overlap_is_zero():
     with pytest.raises(RuntimeError):
         ref.match_views([(10, 5, 1.0), (30, 5, 1.0)], [(10, 4, 1.0), (10, 9, 1.0)], 0, (4, 4), (4, 4), 0.9, I, I, 0, 20, 0, 20, 20, 60,
                         (15, 15), (15, 15))
+
+
+# ---- tail stage: detectTail / detectLineCandidates / selectLargestRegion (class.cpp:2541-2767) -----------------------------
+TAIL_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_tail.npz")
+
+
+def _tail_gen():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_tail_golden", os.path.join(os.path.dirname(TAIL_GOLD), "make_reference_tail_golden.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    return g
+
+
+def test_oracle_tail_matches_reference_golden(oracle):
+    """The oracle's tail segmentation (largest region, column extent, 15 segments, integer centroids, side z) equals the
+    reference's own compiled control flow running on the real OpenCV's connected components, on the committed vectors."""
+    z = np.load(TAIL_GOLD)
+    n = len([k for k in z.files if k.endswith("_conn")])
+    assert n >= 40
+    found = 0
+    for i in range(n):
+        sb, ss = z[f"c{i:02d}_sb"].astype(np.float32) / 4, z[f"c{i:02d}_ss"].astype(np.float32) / 4
+        t, m = oracle.tail_from_binary((sb > 0).astype(np.uint8), (ss > 0).astype(np.uint8), int(z[f"c{i:02d}_conn"]), 15)
+        assert np.array_equal(t, z[f"c{i:02d}_tracks"]), f"tail tracks differ from the reference on case {i}"
+        assert np.array_equal(np.packbits(m > 0), z[f"c{i:02d}_mask"]), f"TAIL_MASK differs from the reference on case {i}"
+        found += int((t[0] >= 0).sum())
+    assert found > 200
+    assert (z["c00_tracks"] == -1).all() and not z["c00_mask"].any()          # no foreground
+    assert z["c01_tracks"][0, 0] == 0 and z["c01_tracks"][1, 0] == 4 and (z["c01_tracks"][2] == -1).all()   # x == 0: no side z (Q13)
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libref_nms.so not built (reference not mounted)")
+def test_tail_golden_is_what_the_reference_code_produces_and_fresh_maps_agree(oracle):
+    pytest.importorskip("cv2")
+    g = _tail_gen()
+    z = np.load(TAIL_GOLD)
+    for i, c in enumerate(g.cases()):
+        t, m = ref.detect_tail(*g.maps(c), c["conn"], 15)
+        assert np.array_equal(t, z[f"c{i:02d}_tracks"]) and np.array_equal(np.packbits(m > 0), z[f"c{i:02d}_mask"])
+    for c in g.cases(seed=5, n=80):
+        sb, ss = g.maps(c)
+        t, m = ref.detect_tail(sb, ss, c["conn"], 15)
+        to, mo = oracle.tail_from_binary((sb > 0).astype(np.uint8), (ss > 0).astype(np.uint8), c["conn"], 15)
+        assert np.array_equal(t, to) and np.array_equal(m > 0, mo > 0)

@@ -23,9 +23,10 @@ struct LocoMouse_Parameters_Stub {
 class LocoMouse_Feature {  // sizes + velocity-matching boxes; boxes by the formula of LocoMouse_class.cpp:2954-2969
     cv::Size size_b, size_s;
     cv::Rect match_rect_b, match_rect_s;
+    int tag_;  // >= 0: detector_*() return 1 x 1 kernels holding tag (bottom) / tag + 2 (side), read by the injected filter2D
 
 public:
-    LocoMouse_Feature(int tw_b, int th_b, int tw_s, int th_s) : size_b(tw_b, th_b), size_s(tw_s, th_s) {
+    LocoMouse_Feature(int tw_b, int th_b, int tw_s, int th_s, int tag = -1) : size_b(tw_b, th_b), size_s(tw_s, th_s), tag_(tag) {
         int new_b_w = round(((double)tw_b) / 2), new_b_h = round(((double)th_b) / 2);
         int new_t_w = round(((double)tw_s) / 2), new_t_h = round(((double)th_s) / 2);
         match_rect_b = cv::Rect(-(new_b_w / 2), -(new_b_h / 2), new_b_w, new_b_h);
@@ -35,15 +36,21 @@ public:
     cv::Size size_side() const { return size_s; }
     cv::Rect match_box_bottom() const { return match_rect_b; }
     cv::Rect match_box_side() const { return match_rect_s; }
-    // the tail code passes these to filter2D, whose outputs the harness injects (see ref_detect_line_candidates)
-    cv::Mat detector_bottom() const { return cv::Mat(); }
-    cv::Mat detector_side() const { return cv::Mat(); }
+    // the detection code passes these to filter2D, whose outputs the harness injects
+    cv::Mat tagged(int id) const {
+        if (tag_ < 0) return cv::Mat();
+        cv::Mat k(1, 1, CV_32F);
+        k.ptr<float>(0)[0] = (float)id;
+        return k;
+    }
+    cv::Mat detector_bottom() const { return tagged(tag_); }
+    cv::Mat detector_side() const { return tagged(tag_ + 2); }
     double rho_bottom() const { return 0.0; }
     double rho_side() const { return 0.0; }
 };
 struct LocoMouse_Model_Stub {
-    LocoMouse_Feature tail;
-    LocoMouse_Model_Stub() : tail(30, 30, 30, 30) {}
+    LocoMouse_Feature paw, snout, tail;
+    LocoMouse_Model_Stub() : paw(30, 30, 30, 30, 0), snout(30, 30, 30, 30, 1), tail(30, 30, 30, 30) {}
 };
 // value type with the reference's interface (LocoMouse_class.hpp:33-45; ctor LocoMouse_class.cpp:3196-3202)
 class LocoMouse_LocationPrior {
@@ -66,6 +73,14 @@ public:
     // tail stage (LocoMouse_class.hpp:188-236: same member names)
     LocoMouse_Model_Stub M;
     cv::Mat I_BOTTOM_MOUSE_PAD, I_SIDE_MOUSE_PAD, TAIL_MASK;
+    // bottom / side candidate detection (same member names)
+    cv::Mat I_BOTTOM_MOUSE, I_SIDE_MOUSE;
+    cv::Rect BB_BOTTOM_TAIL, BB_UNPAD_MOUSE_BOTTOM, BB_UNPAD_MOUSE_SIDE;
+    std::vector<std::vector<Candidate> > CANDIDATES_BOTTOM_PAW, CANDIDATES_BOTTOM_SNOUT, CANDIDATES_SIDE_PAW, CANDIDATES_SIDE_SNOUT;
+    void detectBottomCandidates();
+    void detectSideCandidates();
+    std::vector<Candidate> detectPointCandidatesBottom(cv::Mat &I_VIEW_PAD, cv::Rect &BB_UNPAD, LocoMouse_Feature &M_FEAT, cv::Mat &I_bb_bottom_mask);
+    std::vector<Candidate> detectPointCandidatesSide(cv::Mat &I_VIEW_PAD, cv::Rect &BB_UNPAD, LocoMouse_Feature &M_FEAT, cv::Mat &I_bb_bottom_mask);
     cv::Rect BB_BOTTOM_TAIL_PAD, BB_SIDE_TAIL_PAD, BB_UNPAD_TAIL_BOTTOM, BB_UNPAD_TAIL_SIDE;
     std::vector<cv::Mat> TRACKS_TAIL;
     void detectTail();
@@ -94,6 +109,7 @@ public:
 #include "_ref/ref_nms_body.inc"      // vecmovingaverage, nmsMax, peakClustering   (LocoMouse_class.cpp:1559-1905)
 #include "_ref/ref_hpp_body.inc"      // template firstLastOverT                     (LocoMouse_class.hpp:411-442)
 #include "_ref/ref_imadjust_body.inc" // LocoMouse::imadjust                         (LocoMouse_class.cpp:3204-3242)
+#include "_ref/ref_detect_body.inc"   // detectBottomCandidates, detectSideCandidates, detectPointCandidates* (LocoMouse_class.cpp:771-870)
 #include "_ref/ref_tail_body.inc"     // detectTail, detectLineCandidates, selectLargestRegion (LocoMouse_class.cpp:2541-2767)
 #include "_ref/ref_cost_body.inc"     // unaryCostBox, pairwisePotential (LocoMouse_class.cpp:1909-2070)
 #include "_ref/ref_pair_body.inc"     // matchingWithVelocityConstraint, xDist, matchViews, checkVelCriterion (1023-1267)
@@ -197,7 +213,7 @@ int ref_match_views(const ref_cand *cb, int nb, const ref_cand *cs, int ns, int 
 // callback into cv2).  Outputs: TRACKS_TAIL.back() (3 x n_points int32) and TAIL_MASK (hb x tw, 0 / 255).
 static const float *g_maps[2];
 static int g_map_i = 0;
-static void next_map(float *dst, int rows, int cols) {
+static void next_map(float *dst, int rows, int cols, int /*id*/) {
     const float *src = g_maps[g_map_i++ & 1];
     for (int i = 0; i < rows * cols; ++i) dst[i] = src[i];
 }
@@ -222,6 +238,50 @@ int ref_detect_tail(const float *score_b, const float *score_s, int hb, int hs, 
             for (int c = 0; c < n_points; ++c) tracks[r * n_points + c] = T.ptr<int>(r)[c];
         for (int r = 0; r < hb; ++r)
             for (int c = 0; c < tw; ++c) tail_mask[r * tw + c] = L.TAIL_MASK.ptr<unsigned char>(r)[c];
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+
+// detectBottomCandidates + detectSideCandidates on one frame.  crops: the unpadded bottom / side crops (u8, hb x w, hs x w);
+// tail_mask: TAIL_MASK (hb x tail_w, 0 / 255); maps[4]: the filter2D outputs over the PADDED crops ((hb + pad_b) x (w + pad_b_x) ...)
+// for bottom paw, bottom snout, side paw, side snout, with the unpadded windows at unpad_b / unpad_s = {x, y};
+// tsz: template sizes {paw_b w, h, paw_s w, h, snout_b w, h, snout_s w, h}.  out: 4 lists of up to cap candidates, counts n[4].
+static const float *g_det_maps[4];
+static void det_map(float *dst, int rows, int cols, int id) {
+    const float *src = g_det_maps[id & 3];
+    for (int i = 0; i < rows * cols; ++i) dst[i] = src[i];
+}
+int ref_detect_candidates(const unsigned char *crop_b, const unsigned char *crop_s, int hb, int hs, int w, const unsigned char *tail_mask,
+                          int tail_w, const float *const *maps, const int *pad_b, const int *pad_s, const int *unpad_b, const int *unpad_s,
+                          const int *tsz, ref_cand *out, int cap, int *n) {
+    try {
+        LocoMouse L;
+        L.M.paw = LocoMouse_Feature(tsz[0], tsz[1], tsz[2], tsz[3], 0);
+        L.M.snout = LocoMouse_Feature(tsz[4], tsz[5], tsz[6], tsz[7], 1);
+        L.I_BOTTOM_MOUSE = cv::Mat(hb, w, CV_8U, (void *)crop_b, (size_t)w);
+        L.I_SIDE_MOUSE = cv::Mat(hs, w, CV_8U, (void *)crop_s, (size_t)w);
+        L.TAIL_MASK = cv::Mat(hb, tail_w, CV_8U, (void *)tail_mask, (size_t)tail_w);
+        L.BB_BOTTOM_TAIL = cv::Rect(0, 0, tail_w, hb);
+        L.I_BOTTOM_MOUSE_PAD = cv::Mat(pad_b[1], pad_b[0], CV_8U);   // only its size is read (by the injected filter2D)
+        L.I_SIDE_MOUSE_PAD = cv::Mat(pad_s[1], pad_s[0], CV_8U);
+        L.BB_UNPAD_MOUSE_BOTTOM = cv::Rect(unpad_b[0], unpad_b[1], w, hb);
+        L.BB_UNPAD_MOUSE_SIDE = cv::Rect(unpad_s[0], unpad_s[1], w, hs);
+        for (int k = 0; k < 4; ++k) g_det_maps[k] = maps[k];
+        cv::shim_filter_callback() = det_map;
+        L.detectBottomCandidates();
+        L.detectSideCandidates();
+        const std::vector<Candidate> *lists[4] = {&L.CANDIDATES_BOTTOM_PAW.back(), &L.CANDIDATES_BOTTOM_SNOUT.back(), &L.CANDIDATES_SIDE_PAW.back(),
+                                                  &L.CANDIDATES_SIDE_SNOUT.back()};
+        for (int k = 0; k < 4; ++k) {
+            n[k] = (int)lists[k]->size();
+            for (int i = 0; i < n[k] && i < cap; ++i) {
+                out[k * cap + i].x = (*lists[k])[i].point().x;
+                out[k * cap + i].y = (*lists[k])[i].point().y;
+                out[k * cap + i].s = (*lists[k])[i].score();
+            }
+        }
         return 0;
     } catch (const std::exception &) {
         return -1;

@@ -90,6 +90,7 @@ public:
     Rect_() : x(0), y(0), width(0), height(0) {}
     Rect_(T x_, T y_, T w, T h) : x(x_), y(y_), width(w), height(h) {}
     T area() const { return width * height; }
+    Size_<T> size() const { return Size_<T>(width, height); }
     Rect_ &operator+=(const Point_<T> &p) { x += p.x; y += p.y; return *this; }
     Rect_ &operator-=(const Point_<T> &p) { x -= p.x; y -= p.y; return *this; }
 };
@@ -120,7 +121,7 @@ inline std::ostream &operator<<(std::ostream &o, const Rect_<T> &r) { return o <
 #define CV_64FC1 6
 #define CV_16U 2
 #define CV_16UC1 2
-enum { NORM_MINMAX = 32, THRESH_BINARY = 0, CV_REDUCE_SUM = 0, CV_REDUCE_MAX = 2, CMP_EQ = 0, CC_STAT_AREA = 4, BORDER_CONSTANT = 0 };
+enum { NORM_MINMAX = 32, THRESH_BINARY = 0, THRESH_BINARY_INV = 1, CV_REDUCE_SUM = 0, CV_REDUCE_MAX = 2, CMP_EQ = 0, CC_STAT_AREA = 4, BORDER_CONSTANT = 0 };
 
 class Mat;
 // the one lazy expression the path relies on: alpha * A + beta, folded like cv::MatOp_AddEx
@@ -195,6 +196,16 @@ public:
             }
         dst = out;
     }
+    Mat &setTo(double v, const Mat &mask) {  // in place (ROI views write through to the parent), where mask != 0
+        if (mask.rows != rows || mask.cols != cols) throw std::runtime_error("cv::Mat::setTo: mask size mismatch");
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < cols; ++c)
+                if (mask.ptr<uchar>(r)[c]) {
+                    if (type_ == CV_32F) ptr<float>(r)[c] = (float)v;
+                    else ptr<uchar>(r)[c] = (uchar)v;
+                }
+        return *this;
+    }
     Mat &operator=(const MatExpr &e) {
         Mat out;
         e.a->convertTo(out, e.a->type(), e.alpha, e.beta);
@@ -259,12 +270,13 @@ inline void subtract(const Mat &a, const Mat &b, Mat &dst, const NoArray &, int 
         }
     dst = out;
 }
-inline double threshold(const Mat &src, Mat &dst, double thresh, double maxval, int /*THRESH_BINARY*/) {
+inline double threshold(const Mat &src, Mat &dst, double thresh, double maxval, int type) {  // THRESH_BINARY / THRESH_BINARY_INV
     Mat out(src.rows, src.cols, src.type());  // same depth as the source: 8-bit or 32-bit float
+    const bool inv = type == THRESH_BINARY_INV;
     for (int r = 0; r < src.rows; ++r)
         for (int c = 0; c < src.cols; ++c) {
-            if (src.type() == CV_32F) out.ptr<float>(r)[c] = (src.ptr<float>(r)[c] > (float)thresh) ? (float)maxval : 0.f;
-            else out.ptr<uchar>(r)[c] = ((double)src.ptr<uchar>(r)[c] > thresh) ? (uchar)maxval : 0;
+            if (src.type() == CV_32F) out.ptr<float>(r)[c] = ((src.ptr<float>(r)[c] > (float)thresh) != inv) ? (float)maxval : 0.f;
+            else out.ptr<uchar>(r)[c] = (((double)src.ptr<uchar>(r)[c] > thresh) != inv) ? (uchar)maxval : 0;
         }
     dst = out;
     return thresh;
@@ -319,7 +331,7 @@ inline Moments moments(const Mat &img, bool binary) {  // raw spatial moments up
 // cv::connectedComponentsWithStats and cv::filter2D are ALGORITHMS: the shim does not implement them.  The test harness
 // installs callbacks: the labelling runs in the REAL OpenCV (cv2, through ctypes), the filter outputs are injected.
 typedef int (*shim_cc_fn)(const uchar *img, int rows, int cols, int connectivity, unsigned short *labels, int *areas, int cap);
-typedef void (*shim_filter_fn)(float *dst, int rows, int cols);
+typedef void (*shim_filter_fn)(float *dst, int rows, int cols, int id);  // id: kernel(0, 0) of a tagged 1 x 1 kernel, else -1
 inline shim_cc_fn &shim_cc_callback() { static shim_cc_fn f = nullptr; return f; }
 inline shim_filter_fn &shim_filter_callback() { static shim_filter_fn f = nullptr; return f; }
 inline int connectedComponentsWithStats(const Mat &img, Mat &labels, Mat &stats, Mat & /*centroids*/, int connectivity, int /*CV_16U*/) {
@@ -338,11 +350,11 @@ inline int connectedComponentsWithStats(const Mat &img, Mat &labels, Mat &stats,
     stats = S;
     return n;
 }
-inline void filter2D(const Mat &src, Mat &dst, int /*CV_32F*/, const Mat & /*kernel*/, Point_<int> /*anchor*/, double /*delta*/, int /*border*/) {
+inline void filter2D(const Mat &src, Mat &dst, int /*CV_32F*/, const Mat &k, Point_<int> /*anchor*/, double /*delta*/, int /*border*/) {
     if (!shim_filter_callback()) throw std::runtime_error("filter2D: no callback installed");
     Mat out(src.rows, src.cols, CV_32F);
     std::vector<float> flat((size_t)src.rows * src.cols);
-    shim_filter_callback()(flat.data(), src.rows, src.cols);
+    shim_filter_callback()(flat.data(), src.rows, src.cols, k.empty() ? -1 : (int)k.ptr<float>(0)[0]);
     for (int r = 0; r < src.rows; ++r)
         for (int c = 0; c < src.cols; ++c) out.ptr<float>(r)[c] = flat[(size_t)r * src.cols + c];
     dst = out;

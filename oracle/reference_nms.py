@@ -202,3 +202,28 @@ def detect_tail(score_bottom, score_side, conn=8, n_points=15):
     if rc != 0:
         raise RuntimeError("the reference's tail code threw")
     return tracks, mask
+
+
+def detect_candidates(crop_b, crop_s, tail_mask, maps, pad_b, pad_s, unpad_b, unpad_s, tsz, cap=256):
+    """The reference's detectBottomCandidates + detectSideCandidates (+ detectPointCandidates*, nmsMax, peakClustering;
+    LocoMouse_class.cpp:771-870, 1610-1905) for one frame.  crop_b / crop_s: unpadded crops; tail_mask: TAIL_MASK (0 / 255);
+    maps: the four filter2D outputs over the padded crops [bottom paw, bottom snout, side paw, side snout] (injected);
+    pad_* = (cols, rows) of the padded crops, unpad_* = (x, y) of the unpadded window inside them;
+    tsz = (paw_b w, h, paw_s w, h, snout_b w, h, snout_s w, h).  Returns 4 lists of (x, y, score)."""
+    L = lib()
+    L.ref_detect_candidates.restype = C.c_int
+    cb, cs = np.ascontiguousarray(crop_b, np.uint8), np.ascontiguousarray(crop_s, np.uint8)
+    tm = np.ascontiguousarray(tail_mask, np.uint8)
+    ms = [np.ascontiguousarray(m, np.float32) for m in maps]
+    assert ms[0].shape == ms[1].shape == (pad_b[1], pad_b[0]) and ms[2].shape == ms[3].shape == (pad_s[1], pad_s[0])
+    ptrs = (C.c_void_p * 4)(*[m.ctypes.data for m in ms])
+    i4 = lambda v: (C.c_int * len(v))(*[int(x) for x in v])
+    out = np.zeros((4, cap), CAND)
+    n = np.zeros(4, np.int32)
+    rc = L.ref_detect_candidates(C.c_void_p(cb.ctypes.data), C.c_void_p(cs.ctypes.data), cb.shape[0], cs.shape[0], cb.shape[1],
+                                 C.c_void_p(tm.ctypes.data), tm.shape[1], ptrs, i4(pad_b), i4(pad_s), i4(unpad_b), i4(unpad_s), i4(tsz),
+                                 C.c_void_p(out.ctypes.data), cap, C.c_void_p(n.ctypes.data))
+    if rc != 0:
+        raise RuntimeError("the reference's candidate detection threw")
+    assert (n <= cap).all()
+    return [[(int(c["x"]), int(c["y"]), float(c["s"])) for c in out[k, :n[k]]] for k in range(4)]

@@ -243,3 +243,50 @@ def test_tail_golden_is_what_the_reference_code_produces_and_fresh_maps_agree(or
         t, m = ref.detect_tail(sb, ss, c["conn"], 15)
         to, mo = oracle.tail_from_binary((sb > 0).astype(np.uint8), (ss > 0).astype(np.uint8), c["conn"], 15)
         assert np.array_equal(t, to) and np.array_equal(m > 0, mo > 0)
+
+
+# ---- frame-level glue: detectBottomCandidates / detectSideCandidates (class.cpp:771-870) ------------------------------------
+FRAME_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_frame_candidates.npz")
+
+
+def _lists_equal(got, want):
+    want = np.asarray(want)
+    a = np.array(got, dtype=ref.CAND) if len(got) else np.zeros(0, ref.CAND)
+    return len(a) == len(want) and np.array_equal(a["x"], want["x"]) and np.array_equal(a["y"], want["y"]) and np.array_equal(
+        np.ascontiguousarray(a["s"]).view(np.uint64), np.ascontiguousarray(want["s"]).view(np.uint64))
+
+
+def test_oracle_frame_candidates_match_reference_golden(oracle):
+    """oracle.detect's four candidate lists per frame (masks at <= 25, TAIL_MASK over the tail box, unpadded window, nmsMax /
+    peakClustering, side detection skipped when the bottom list is empty) equal what the reference's own
+    detectBottomCandidates / detectSideCandidates code produced for the same frames (committed vectors)."""
+    import _frame_glue as G
+
+    z = np.load(FRAME_GOLD)
+    total = 0
+    for ci, kw in enumerate(G.CASES):
+        cfg, model, bkg, calib, frames, bx, bs, bb = G.case_problem(kw)
+        res = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=4)
+        for f in range(len(frames)):
+            got = [res.candidates_bottom(f, 0), res.candidates_bottom(f, 1), res.candidates_side(f, 0), res.candidates_side(f, 1)]
+            for k in range(4):
+                assert _lists_equal(got[k], z[f"c{ci}_f{f}_l{k}"]), f"case {kw}, frame {f}, list {k}"
+                total += len(got[k])
+            if kw.get("q6"):
+                assert got[0] == [] and got[2] == [] and len(got[3]) > 0   # Q6: side paw skipped, side snout still runs
+    assert total > 300
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libref_nms.so not built (reference not mounted)")
+def test_frame_golden_is_what_the_reference_code_produces(oracle):
+    pytest.importorskip("cv2")
+    import _frame_glue as G
+
+    z = np.load(FRAME_GOLD)
+    for ci, kw in enumerate(G.CASES[:2] + G.CASES[3:]):
+        ci = G.CASES.index(kw)
+        cfg, model, bkg, calib, frames, bx, bs, bb = G.case_problem(kw, n=2)
+        for f in range(2):
+            lists = G.reference_frame(oracle, cfg, model, bkg, calib, frames[f], bx[f], bs[f], bb[f])
+            for k in range(4):
+                assert _lists_equal(lists[k], z[f"c{ci}_f{f}_l{k}"])

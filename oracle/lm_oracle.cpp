@@ -8,13 +8,13 @@
  * reference — CMakeLists.txt:3 — whose documented semantics are restated here and pinned against
  * cv2 4.13 in tests/test_oracle_vs_cv2.py).
  *
- * Pin status (the reference ships no tests or golden vectors): nmsMax, peakClustering, the pairing stage,
- * the tail stage, the per-frame candidate glue, the cost builders, imadjust, vecmovingaverage, firstLastOverT and the
- * Candidate / P22D / MyMat / MATSPARSE value types are pinned against the REFERENCE'S OWN SOURCE LINES, compiled from
- * /root/reference by `make -C oracle ref` (oracle/ref_glue.cpp) -- tests/test_oracle_vs_reference.py,
- * tests/test_cost_builders.py and the committed vectors under tests/golden/ they produced.  readFrame (VideoCapture,
- * normalize, calibration gather) cannot be compiled here and is "parity unpinned" as a whole function: it is pinned
- * primitive by primitive against cv2.
+ * Pin status (the reference ships no tests or golden vectors): readFrame / correctImage, imadjust, the tail
+ * stage, the per-frame candidate glue, nmsMax, peakClustering, the pairing stage, the cost builders, vecmovingaverage,
+ * firstLastOverT and the Candidate / P22D / MyMat / MATSPARSE value types are pinned against the REFERENCE'S OWN SOURCE
+ * LINES, compiled from /root/reference by `make -C oracle ref` (oracle/ref_glue.cpp; OpenCV algorithms they call run in
+ * the real OpenCV through callbacks, filter2D outputs are injected) -- tests/test_oracle_vs_reference.py,
+ * tests/test_cost_builders.py and the committed vectors under tests/golden/ they produced.  The correlation itself
+ * (cv::filter2D) is pinned against cv2.filter2D directly (tests/test_oracle_vs_cv2.py).
  *
  * Build: g++ -O3 -std=c++17 -ffp-contract=off -fPIC -shared  (see oracle/Makefile).
  * -ffp-contract=off matters: the mul+add correlation mode must round twice.

@@ -65,6 +65,8 @@ public:
     cv::Rect_<double> area() const { return area_; }
     double max_distance() const { return md_; }
 };
+#include <sstream>
+#include "_ref/ref_stream_formatter.inc"   // class Stream_Formatter (LocoMouse_class.hpp:379-406)
 #include "MyMat.hpp"                      // the reference's own MyMat / MATSPARSE (MyMat/MyMat.hpp, compiled from MyMat.cpp)
 #include "_ref/ref_match_to_range.inc"    // template matchToRange (LocoMouse_class.hpp:364-374)
 class LocoMouse {
@@ -73,6 +75,13 @@ public:
     // tail stage (LocoMouse_class.hpp:188-236: same member names)
     LocoMouse_Model_Stub M;
     cv::Mat I_BOTTOM_MOUSE_PAD, I_SIDE_MOUSE_PAD, TAIL_MASK;
+    // readFrame / correctImage (same member names)
+    cv::VideoCapture V;
+    cv::Mat BKG, CALIBRATION;
+    bool IMAGE_FLIP = false;
+    int CURRENT_FRAME = -1;
+    void readFrame(cv::Mat &I);
+    void correctImage(cv::Mat &Iin, cv::Mat &Iout);
     // bottom / side candidate detection (same member names)
     cv::Mat I_BOTTOM_MOUSE, I_SIDE_MOUSE;
     cv::Rect BB_BOTTOM_TAIL, BB_UNPAD_MOUSE_BOTTOM, BB_UNPAD_MOUSE_SIDE;
@@ -109,6 +118,7 @@ public:
 #include "_ref/ref_nms_body.inc"      // vecmovingaverage, nmsMax, peakClustering   (LocoMouse_class.cpp:1559-1905)
 #include "_ref/ref_hpp_body.inc"      // template firstLastOverT                     (LocoMouse_class.hpp:411-442)
 #include "_ref/ref_imadjust_body.inc" // LocoMouse::imadjust                         (LocoMouse_class.cpp:3204-3242)
+#include "_ref/ref_read_body.inc"     // readFrame(cv::Mat&), correctImage (LocoMouse_class.cpp:1273-1406)
 #include "_ref/ref_detect_body.inc"   // detectBottomCandidates, detectSideCandidates, detectPointCandidates* (LocoMouse_class.cpp:771-870)
 #include "_ref/ref_tail_body.inc"     // detectTail, detectLineCandidates, selectLargestRegion (LocoMouse_class.cpp:2541-2767)
 #include "_ref/ref_cost_body.inc"     // unaryCostBox, pairwisePotential (LocoMouse_class.cpp:1909-2070)
@@ -239,6 +249,25 @@ int ref_detect_tail(const float *score_b, const float *score_s, int hb, int hs, 
         for (int r = 0; r < hb; ++r)
             for (int c = 0; c < tw; ++c) tail_mask[r * tw + c] = L.TAIL_MASK.ptr<unsigned char>(r)[c];
         return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+
+// readFrame(I) on an injected raw frame: background subtraction, normalisation and mirror run in the real OpenCV (callback),
+// correctImage (the calibration gather) is the reference's own loop.  out: n_rows x n_cols.
+int ref_read_frame(const unsigned char *frame, const unsigned char *bkg, int vr, int vc, const int *calib, int n_rows, int n_cols, int flip,
+                   cv::shim_u8_op_fn op, unsigned char *out) {
+    try {
+        LocoMouse L;
+        L.V.next = cv::Mat(vr, vc, CV_8U, (void *)frame, (size_t)vc);
+        L.BKG = cv::Mat(vr, vc, CV_8U, (void *)bkg, (size_t)vc);
+        L.CALIBRATION = cv::Mat(n_rows, n_cols, CV_32S, (void *)calib, (size_t)n_cols * 4);
+        L.IMAGE_FLIP = flip != 0;
+        cv::shim_u8_op_callback() = op;
+        cv::Mat I(n_rows, n_cols, CV_8U, (void *)out, (size_t)n_cols);
+        L.readFrame(I);
+        return L.CURRENT_FRAME;  // 0 after the first frame
     } catch (const std::exception &) {
         return -1;
     }

@@ -81,6 +81,8 @@ public:
 };
 typedef Size_<int> Size;
 template <typename T>
+inline bool operator==(const Size_<T> &a, const Size_<T> &b) { return a.width == b.width && a.height == b.height; }
+template <typename T>
 inline std::ostream &operator<<(std::ostream &o, const Size_<T> &s) { return o << "[" << s.width << " x " << s.height << "]"; }
 
 template <typename T>
@@ -155,6 +157,7 @@ public:
     const T *ptr(int r) const { return (const T *)(data + (size_t)r * step); }
     template <typename T>
     T *ptr(int r) { return (T *)(data + (size_t)r * step); }
+    Mat reshape(int /*cn*/, int /*rows*/) const { return *this; }  // the reference discards the result (class.cpp:1352)
     template <typename T>
     T &at(int r, int c) { return ptr<T>(r)[c]; }
     template <typename T>
@@ -225,7 +228,12 @@ inline Mat operator<=(const Mat &a, double s) {
 }
 // cv::normalize(src, dst, alpha, beta, NORM_MINMAX, -1) on 8-bit data: scale = (beta - alpha) / (max - min), 0 when the
 // image is constant (so a constant image becomes all alpha: SURVEY Q7)
+inline void shim_u8_op(int op, const Mat &src, Mat &dst);
 inline void normalize(const Mat &src, Mat &dst, double alpha, double beta, int /*NORM_MINMAX*/, int /*dtype*/) {
+    if (beta == 255) {  // readFrame's image normalisation: executed by the real OpenCV
+        shim_u8_op(0, src, dst);
+        return;
+    }
     double mn = 1e300, mx = -1e300;
     for (int r = 0; r < src.rows; ++r)
         for (int c = 0; c < src.cols; ++c) {
@@ -359,6 +367,53 @@ inline void filter2D(const Mat &src, Mat &dst, int /*CV_32F*/, const Mat &k, Poi
         for (int c = 0; c < src.cols; ++c) out.ptr<float>(r)[c] = flat[(size_t)r * src.cols + c];
     dst = out;
 }
+
+// ---- additions for readFrame / correctImage (LocoMouse_class.cpp:1273-1406) --------------------------------------------
+// normalize(F, F, 0, 255, NORM_MINMAX, CV_8UC1) on image data and flip are NOT implemented here: they run in the REAL
+// OpenCV through a callback (op 0 = cv2.normalize(src, None, 0, 255, NORM_MINMAX, CV_8U), op 1 = cv2.flip(src, 1)).
+typedef void (*shim_u8_op_fn)(int op, const uchar *src, uchar *dst, int rows, int cols);
+inline shim_u8_op_fn &shim_u8_op_callback() { static shim_u8_op_fn f = nullptr; return f; }
+inline void shim_u8_op(int op, const Mat &src, Mat &dst) {
+    if (!shim_u8_op_callback()) throw std::runtime_error("no callback installed for normalize / flip");
+    std::vector<uchar> in((size_t)src.rows * src.cols), out(in.size());
+    for (int r = 0; r < src.rows; ++r)
+        for (int c = 0; c < src.cols; ++c) in[(size_t)r * src.cols + c] = src.ptr<uchar>(r)[c];
+    shim_u8_op_callback()(op, in.data(), out.data(), src.rows, src.cols);
+    Mat o(src.rows, src.cols, CV_8U);
+    for (int r = 0; r < src.rows; ++r)
+        for (int c = 0; c < src.cols; ++c) o.ptr<uchar>(r)[c] = out[(size_t)r * src.cols + c];
+    dst = o;
+}
+inline void flip(const Mat &src, Mat &dst, int /*1: around the y axis*/) {
+    Mat tmp;
+    shim_u8_op(1, src, tmp);
+    // cv::flip(I, I, 1) works in place: the caller's buffer (a view of I_PAD in the reference) must receive the pixels
+    if (dst.data && dst.rows == src.rows && dst.cols == src.cols) {
+        for (int r = 0; r < tmp.rows; ++r)
+            for (int c = 0; c < tmp.cols; ++c) dst.ptr<uchar>(r)[c] = tmp.ptr<uchar>(r)[c];
+    } else {
+        dst = tmp;
+    }
+}
+inline void extractChannel(const Mat &src, Mat &dst, int /*0*/) { dst = src; }  // the injected frames are single-channel
+inline void subtract(const Mat &a, const Mat &b, Mat &dst) {  // saturating 8-bit a - b (3-argument form)
+    if (a.rows != b.rows || a.cols != b.cols) throw std::runtime_error("cv::subtract: size mismatch");
+    Mat out(a.rows, a.cols, CV_8U);
+    for (int r = 0; r < a.rows; ++r)
+        for (int c = 0; c < a.cols; ++c) {
+            const int d = (int)a.ptr<uchar>(r)[c] - (int)b.ptr<uchar>(r)[c];
+            out.ptr<uchar>(r)[c] = (uchar)(d < 0 ? 0 : d);
+        }
+    dst = out;
+}
+class VideoCapture {  // hands out the injected frame
+public:
+    Mat next;
+    VideoCapture &operator>>(Mat &f) {
+        f = next;
+        return *this;
+    }
+};
 
 inline std::ostream &operator<<(std::ostream &o, const Mat &m) { return o << "Mat(" << m.rows << " x " << m.cols << ")"; }  // debug prints only
 struct Scalar {

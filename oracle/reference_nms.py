@@ -227,3 +227,32 @@ def detect_candidates(crop_b, crop_s, tail_mask, maps, pad_b, pad_s, unpad_b, un
         raise RuntimeError("the reference's candidate detection threw")
     assert (n <= cap).all()
     return [[(int(c["x"]), int(c["y"]), float(c["s"])) for c in out[k, :n[k]]] for k in range(4)]
+
+
+_U8OP_FN = C.CFUNCTYPE(None, C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte), C.c_int, C.c_int)
+
+
+def read_frame(frame, bkg, calib, flip=False):
+    """The reference's LocoMouse::readFrame(cv::Mat&) + correctImage (LocoMouse_class.cpp:1273-1406) on an injected raw frame.
+    cv::normalize(F, F, 0, 255, NORM_MINMAX, CV_8UC1) and cv::flip run in the REAL OpenCV (cv2) through a callback;
+    cv::subtract is the shim's saturating loop; the calibration gather is the reference's own loop.
+    Returns the calibrated image (uint8 [n_rows, n_cols])."""
+    import cv2
+
+    L = lib()
+    fr, bk = np.ascontiguousarray(frame, np.uint8), np.ascontiguousarray(bkg, np.uint8)
+    cal = np.ascontiguousarray(calib, np.int32)
+
+    def op(code, src, dst, rows, cols):
+        a = np.ctypeslib.as_array(src, shape=(rows, cols))
+        r = cv2.normalize(a, None, 0, 255, cv2.NORM_MINMAX, cv2.CV_8U) if code == 0 else cv2.flip(a, 1)
+        np.ctypeslib.as_array(dst, shape=(rows, cols))[:] = r
+
+    cb = _U8OP_FN(op)
+    out = np.zeros(cal.shape, np.uint8)
+    L.ref_read_frame.restype = C.c_int
+    rc = L.ref_read_frame(C.c_void_p(fr.ctypes.data), C.c_void_p(bk.ctypes.data), fr.shape[0], fr.shape[1], C.c_void_p(cal.ctypes.data),
+                          cal.shape[0], cal.shape[1], int(bool(flip)), cb, C.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise RuntimeError("the reference's readFrame threw")
+    return out

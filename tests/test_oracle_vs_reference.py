@@ -290,3 +290,47 @@ def test_frame_golden_is_what_the_reference_code_produces(oracle):
             lists = G.reference_frame(oracle, cfg, model, bkg, calib, frames[f], bx[f], bs[f], bb[f])
             for k in range(4):
                 assert _lists_equal(lists[k], z[f"c{ci}_f{f}_l{k}"])
+
+
+# ---- readFrame / correctImage (class.cpp:1273-1406) + LocoMouse_TM::readFrame's imadjust -------------------------------------
+READ_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_readframe.npz")
+
+
+def _read_gen():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_readframe_golden", os.path.join(os.path.dirname(READ_GOLD), "make_reference_readframe_golden.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    return g
+
+
+def test_oracle_preprocess_matches_reference_readframe_golden(oracle):
+    """oracle.preprocess (background subtraction, per-frame min-max normalisation, calibration gather, mirror, imadjust) gives
+    the image the reference's own readFrame / correctImage code gave on the real OpenCV's normalize / flip (checksums)."""
+    import zlib
+
+    g = _read_gen()
+    z = np.load(READ_GOLD)
+    for ci, kw in enumerate(g.CASES):
+        cfg, bkg, calib, frames = g.frames_of(kw)
+        for f, fr in enumerate(frames):
+            img, _ = oracle.preprocess(cfg, bkg, calib, fr)
+            crc, total, mx = z[f"c{ci}_f{f}"].tolist()
+            assert (zlib.crc32(img.tobytes()), int(img.sum()), int(img.max())) == (crc, total, mx), f"case {kw}, frame {f}"
+        assert z[f"c{ci}_f0"][1] > 100000 and z[f"c{ci}_f3"][1] == 0   # a real image; the constant frame maps to zeros
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libref_nms.so not built (reference not mounted)")
+def test_readframe_golden_is_what_the_reference_code_produces(oracle):
+    pytest.importorskip("cv2")
+    import zlib
+
+    g = _read_gen()
+    z = np.load(READ_GOLD)
+    for ci, kw in enumerate(g.CASES):
+        cfg, bkg, calib, frames = g.frames_of(kw)
+        for f in (0, 3):
+            img = g.reference_image(cfg, bkg, calib, frames[f])
+            assert zlib.crc32(img.tobytes()) == int(z[f"c{ci}_f{f}"][0])
+            want, _ = oracle.preprocess(cfg, bkg, calib, frames[f])
+            assert np.array_equal(img, want)

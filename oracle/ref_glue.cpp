@@ -385,6 +385,40 @@ void ref_shim_primitives(const int *D, int rows, int cols, int ovlp, unsigned ch
     *count = cv::sum(S)(0);
 }
 
+// Second batch of shim primitives (used by the tail / candidate / readFrame code), exposed for tests/test_oracle_vs_cv2.py:
+// out8[0] = convertTo_u8(threshold(F, 0, 1, BINARY)), out8[1] = threshold(A, 25.5, 255, BINARY_INV), out8[2] = repeat(reduce(A, 0, MAX), rows, 1),
+// out8[3] = (F > 0) & A, out8[4] = compare(labels == value), out8[5] = subtract(A, B), out8[6] = A.setTo(7, B) (in place on a copy);
+// outf = F.setTo(0, B); mom = moments(A, binary = true) {m00, m10, m01}.
+void ref_shim_primitives2(const unsigned char *a, const unsigned char *b, const float *f, const unsigned short *labels, int value, int rows,
+                          int cols, unsigned char *out8, float *outf, double *mom) {
+    cv::Mat A(rows, cols, CV_8U, (void *)a, (size_t)cols), B(rows, cols, CV_8U, (void *)b, (size_t)cols);
+    cv::Mat F(rows, cols, CV_32F, (void *)f, (size_t)cols * 4), Lb(rows, cols, CV_16U, (void *)labels, (size_t)cols * 2);
+    cv::Mat t, r[7];
+    cv::threshold(F, t, 0, 1, cv::THRESH_BINARY);
+    t.convertTo(r[0], CV_8UC1);
+    cv::threshold(A, r[1], 25.5, 255, cv::THRESH_BINARY_INV);
+    cv::Mat mx;
+    cv::reduce(A, mx, 0, cv::CV_REDUCE_MAX);
+    r[2] = cv::repeat(mx, rows, 1);
+    r[3] = (F > 0) & A;
+    cv::compare(Lb, value, r[4], cv::CMP_EQ);
+    cv::subtract(A, B, r[5]);
+    A.convertTo(r[6], CV_8U);   // a copy
+    r[6].setTo(7, B);
+    cv::Mat Fc;
+    F.convertTo(Fc, CV_32F);
+    Fc.setTo(0, B);
+    for (int k = 0; k < 7; ++k)
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols; ++x) out8[((size_t)k * rows + y) * cols + x] = r[k].ptr<unsigned char>(y)[x];
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) outf[(size_t)y * cols + x] = Fc.ptr<float>(y)[x];
+    cv::Moments M = cv::moments(A, true);
+    mom[0] = M.m00;
+    mom[1] = M.m10;
+    mom[2] = M.m01;
+}
+
 int ref_default_candidate(int *x, int *y, double *s) {
     Candidate c;
     *x = c.point().x;

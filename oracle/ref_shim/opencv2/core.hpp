@@ -6,13 +6,16 @@
 // firstLastOverT template (LocoMouse_class.hpp:411-442) and LocoMouse::imadjust (3204-3242, which only fills a
 // 256-entry table and applies cv::LUT).  This header supplies
 // just those types (Point_, Size_, Rect_, a header-only Mat with OpenCV's sharing semantics, saturate_cast,
-// CV_Assert, inert FileStorage stubs) plus the handful of ELEMENTWISE primitives the pairing code calls (compare,
-// normalize(MINMAX), convertTo, the alpha*A+beta expression, reduce(SUM), saturating subtract, threshold, sum, LUT),
-// each a few lines with OpenCV's documented semantics and each pinned against the real OpenCV (cv2) in
-// tests/test_oracle_vs_cv2.py.  With it oracle/Makefile compiles the reference's OWN source lines, from where they
-// lie under /root/reference, into oracle/_ref/libref_nms.so, which pins the oracle's restatement of those loops --
-// their control flow in particular -- against the real reference code (tests/test_oracle_vs_reference.py).
-// No reference algorithm (NMS, clustering, pairing, velocity criterion) lives here.
+// CV_Assert, inert FileStorage stubs) plus the ELEMENTWISE primitives the compiled code calls (compare, normalize(MINMAX) of a
+// mask, convertTo, the alpha*A+beta expression, reduce(SUM / MAX), saturating subtract, threshold (binary / inverse), sum,
+// LUT, repeat, >, &, setTo, moments), each a few lines with OpenCV's documented semantics and each pinned against the real
+// OpenCV (cv2) in tests/test_oracle_vs_cv2.py (test_reference_shim_primitives_*).  OpenCV ALGORITHMS are not implemented
+// here: connectedComponentsWithStats, the image normalisation of readFrame and flip call back into the real OpenCV, and
+// filter2D hands out injected maps (the correlation is pinned against cv2.filter2D directly).  With it oracle/Makefile
+// compiles the reference's OWN source lines, from where they lie under /root/reference, into oracle/_ref/libref_nms.so,
+// which pins the oracle's restatement -- control flow in particular -- against the real reference code
+// (tests/test_oracle_vs_reference.py, tests/test_cost_builders.py).
+// No reference algorithm (NMS, clustering, pairing, velocity criterion, tail segmentation, cost builders) lives here.
 #pragma once
 #include <cassert>
 #include <cmath>

@@ -283,3 +283,44 @@ def test_reference_shim_primitives_match_cv2():
         s = cv2.subtract(a, b)
         _, t = cv2.threshold(s, 25.0, 1, cv2.THRESH_BINARY)
         assert cnt[0] == cv2.sumElems(t)[0]
+
+
+def test_reference_shim_primitives_batch2_match_cv2():
+    """The elementwise shim primitives behind the compiled tail / candidate / readFrame code, each against the real OpenCV."""
+    import ctypes as C
+
+    from oracle import reference_nms as ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libref_nms.so not built (reference not mounted)")
+    L = ref.lib()
+    L.ref_shim_primitives2.restype = None
+    rng = np.random.Generator(np.random.PCG64(31415))
+    for it in range(60):
+        rows, cols = int(rng.integers(1, 24)), int(rng.integers(1, 24))
+        a = rng.integers(0, 256, (rows, cols)).astype(np.uint8)
+        a[rng.random((rows, cols)) < 0.3] = rng.choice([0, 25, 26])
+        b = (rng.random((rows, cols)) < 0.4).astype(np.uint8) * int(rng.choice([1, 255]))
+        f = rng.normal(0, 1, (rows, cols)).astype(np.float32)
+        f[rng.random((rows, cols)) < 0.2] = 0.0
+        lab = rng.integers(0, 5, (rows, cols)).astype(np.uint16)
+        val = int(rng.integers(0, 5))
+        out8 = np.zeros((7, rows, cols), np.uint8)
+        outf = np.zeros((rows, cols), np.float32)
+        mom = np.zeros(3, np.float64)
+        p = lambda x: C.c_void_p(x.ctypes.data)
+        L.ref_shim_primitives2(p(a), p(b), p(f), p(lab), val, rows, cols, p(out8), p(outf), p(mom))
+        _, t = cv2.threshold(f, 0, 1, cv2.THRESH_BINARY)
+        assert np.array_equal(out8[0], t.astype(np.uint8))
+        assert np.array_equal(out8[1], cv2.threshold(a, 25.5, 255, cv2.THRESH_BINARY_INV)[1])
+        assert np.array_equal(out8[2], cv2.repeat(cv2.reduce(a, 0, cv2.REDUCE_MAX), rows, 1))
+        assert np.array_equal(out8[3], cv2.bitwise_and(cv2.compare(f, np.zeros_like(f), cv2.CMP_GT), a))
+        assert np.array_equal(out8[4], cv2.compare(lab, np.full_like(lab, val), cv2.CMP_EQ))
+        assert np.array_equal(out8[5], cv2.subtract(a, b))
+        want = a.copy()
+        want[b != 0] = 7                      # Mat::setTo(value, mask)
+        assert np.array_equal(out8[6], want)
+        wf = f.copy()
+        wf[b != 0] = 0
+        assert np.array_equal(outf, wf)
+        m = cv2.moments(a, True)
+        assert (mom[0], mom[1], mom[2]) == (m["m00"], m["m10"], m["m01"])

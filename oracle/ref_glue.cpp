@@ -75,6 +75,10 @@ public:
     // tail stage (LocoMouse_class.hpp:188-236: same member names)
     LocoMouse_Model_Stub M;
     cv::Mat I_BOTTOM_MOUSE_PAD, I_SIDE_MOUSE_PAD, TAIL_MASK;
+    // pass 1 (LocoMouse_TM_DE): imadjust_default + the members computeMouseBox_DE reads
+    void imadjust_default(const cv::Mat &Iin, cv::Mat &Iout);
+    unsigned int N_COLS = 0;
+    cv::Rect BB_SIDE_VIEW;
     // readFrame / correctImage (same member names)
     cv::VideoCapture V;
     cv::Mat BKG, CALIBRATION;
@@ -118,6 +122,15 @@ public:
 #include "_ref/ref_nms_body.inc"      // vecmovingaverage, nmsMax, peakClustering   (LocoMouse_class.cpp:1559-1905)
 #include "_ref/ref_hpp_body.inc"      // template firstLastOverT                     (LocoMouse_class.hpp:411-442)
 #include "_ref/ref_imadjust_body.inc" // LocoMouse::imadjust                         (LocoMouse_class.cpp:3204-3242)
+class LocoMouse_TM_DE : public LocoMouse {  // LocoMouse_TM_DE.hpp:27-29 defaults
+public:
+    int MIN_PIXEL_COUNT = 10;
+    double WIDTH_MARGIN = 1.1;
+    double SIDE_THRESHOLD = 255 * 0.05;
+    void computeMouseBox_DE(cv::Mat &I_SIDE, double &bb_x);
+};
+#include "_ref/ref_imadjust_default_body.inc"  // LocoMouse::imadjust_default (LocoMouse_class.cpp:3244-3311)
+#include "_ref/ref_box_de_body.inc"            // LocoMouse_TM_DE::computeMouseBox_DE (LocoMouse_TM_DE.cpp:56-113)
 #include "_ref/ref_read_body.inc"     // readFrame(cv::Mat&), correctImage (LocoMouse_class.cpp:1273-1406)
 #include "_ref/ref_detect_body.inc"   // detectBottomCandidates, detectSideCandidates, detectPointCandidates* (LocoMouse_class.cpp:771-870)
 #include "_ref/ref_tail_body.inc"     // detectTail, detectLineCandidates, selectLargestRegion (LocoMouse_class.cpp:2541-2767)
@@ -273,6 +286,27 @@ int ref_read_frame(const unsigned char *frame, const unsigned char *bkg, int vr,
     }
 }
 
+// computeMouseBox_DE on a calibrated side view (u8, side_h x n_cols, modified in place as the reference does): returns bb_x.
+// The scaled 8-bit conversion inside imadjust_default runs in the real OpenCV (callback).  adjusted (optional): the side view
+// after imadjust_default and the zeroed bands.
+int ref_mouse_box_de(unsigned char *side, int side_h, int n_cols, double threshold, int min_count, double margin, cv::shim_scale_fn scale,
+                     double *bb_x) {
+    try {
+        LocoMouse_TM_DE L;
+        L.N_COLS = (unsigned int)n_cols;
+        L.BB_SIDE_VIEW = cv::Rect(0, 0, n_cols, side_h);
+        L.SIDE_THRESHOLD = threshold;
+        L.MIN_PIXEL_COUNT = min_count;
+        L.WIDTH_MARGIN = margin;
+        cv::shim_scale_callback() = scale;
+        cv::Mat I(side_h, n_cols, CV_8U, (void *)side, (size_t)n_cols);
+        L.computeMouseBox_DE(I, *bb_x);
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+
 // detectBottomCandidates + detectSideCandidates on one frame.  crops: the unpadded bottom / side crops (u8, hb x w, hs x w);
 // tail_mask: TAIL_MASK (hb x tail_w, 0 / 255); maps[4]: the filter2D outputs over the PADDED crops ((hb + pad_b) x (w + pad_b_x) ...)
 // for bottom paw, bottom snout, side paw, side snout, with the unpadded windows at unpad_b / unpad_s = {x, y};
@@ -417,6 +451,23 @@ void ref_shim_primitives2(const unsigned char *a, const unsigned char *b, const 
     mom[0] = M.m00;
     mom[1] = M.m10;
     mom[2] = M.m01;
+}
+
+// calcHist (256 unit bins) + cv::sum of the float histogram, and colRange / rowRange / setTo views (pass-1 code), for the cv2 check
+void ref_shim_primitives3(const unsigned char *a, int rows, int cols, float *hist, double *total, unsigned char *banded) {
+    cv::Mat A(rows, cols, CV_8U, (void *)a, (size_t)cols), H;
+    const int nb = 256;
+    float range[] = {0, 256};
+    const float *hr = {range};
+    cv::calcHist(&A, 1, 0, cv::Mat(), H, 1, &nb, &hr);
+    for (int i = 0; i < 256; ++i) hist[i] = H.ptr<float>(0)[i];
+    *total = cv::sum(H)(0);
+    cv::Mat B;
+    A.copyTo(B);
+    B.colRange(0, cols / 4).setTo(0);
+    B.rowRange(rows / 2, rows).setTo(0);
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) banded[r * cols + c] = B.ptr<unsigned char>(r)[c];
 }
 
 int ref_default_candidate(int *x, int *y, double *s) {

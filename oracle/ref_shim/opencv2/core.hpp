@@ -160,6 +160,19 @@ public:
     const T *ptr(int r) const { return (const T *)(data + (size_t)r * step); }
     template <typename T>
     T *ptr(int r) { return (T *)(data + (size_t)r * step); }
+    Mat &assign_scaled_u8(const MatExpr &e);
+    Mat colRange(int a, int b) const { return (*this)(Rect_<int>(a, 0, b - a, rows)); }
+    Mat rowRange(int a, int b) const { return (*this)(Rect_<int>(0, a, cols, b - a)); }
+    Mat &setTo(double v) {  // in place, all elements (8-bit)
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < cols; ++c) ptr<uchar>(r)[c] = (uchar)v;
+        return *this;
+    }
+    void copyTo(Mat &dst) const {
+        Mat out;
+        convertTo(out, type_);
+        dst = out;
+    }
     Mat reshape(int /*cn*/, int /*rows*/) const { return *this; }  // the reference discards the result (class.cpp:1352)
     template <typename T>
     T &at(int r, int c) { return ptr<T>(r)[c]; }
@@ -213,6 +226,7 @@ public:
         return *this;
     }
     Mat &operator=(const MatExpr &e) {
+        if (e.a->type() == CV_8U) return assign_scaled_u8(e);  // 8-bit -> 8-bit with scale: executed by the real OpenCV
         Mat out;
         e.a->convertTo(out, e.a->type(), e.alpha, e.beta);
         *this = out;
@@ -220,6 +234,9 @@ public:
     }
 };
 inline MatExpr operator/(const Mat &a, double s) { MatExpr e = {&a, 1.0 / s, 0.0}; return e; }
+// (A - s) and (expr / s), folded like cv::MatOp_AddEx (matop.cpp: subtract -> beta -= s; divide -> multiply(e, 1. / s))
+inline MatExpr operator-(const Mat &a, double s) { MatExpr e = {&a, 1.0, -s}; return e; }
+inline MatExpr operator/(const MatExpr &x, double s) { MatExpr e = {x.a, x.alpha * (1.0 / s), x.beta * (1.0 / s)}; return e; }
 inline MatExpr operator-(double c, const MatExpr &e) { MatExpr r = {e.a, -e.alpha, c - e.beta}; return r; }
 inline MatExpr operator-(int c, const MatExpr &e) { return (double)c - e; }
 // A <= s  ->  8-bit mask, 255 where true
@@ -409,6 +426,41 @@ inline void subtract(const Mat &a, const Mat &b, Mat &dst) {  // saturating 8-bi
         }
     dst = out;
 }
+// 8-bit -> 8-bit Mat::convertTo(alpha, beta) (what `Iout = (Iout - r0) / (r1 - r0)` evaluates to): the real OpenCV's
+// cv2.convertScaleAbs through a callback (same float multiply-add + rounding kernels; every value here is >= -0.5, so the
+// absolute value changes nothing), except OpenCV's own shortcut: alpha == 1 and beta == 0 copies.
+typedef void (*shim_scale_fn)(const uchar *src, uchar *dst, int rows, int cols, double alpha, double beta);
+inline shim_scale_fn &shim_scale_callback() { static shim_scale_fn f = nullptr; return f; }
+inline Mat &Mat::assign_scaled_u8(const MatExpr &e) {
+    const Mat &a = *e.a;
+    std::vector<uchar> in((size_t)a.rows * a.cols), out(in.size());
+    for (int r = 0; r < a.rows; ++r)
+        for (int c = 0; c < a.cols; ++c) in[(size_t)r * a.cols + c] = a.ptr<uchar>(r)[c];
+    if (std::fabs(e.alpha - 1) < 2.220446049250313e-16 && std::fabs(e.beta) < 2.220446049250313e-16) {
+        out = in;
+    } else {
+        if (!shim_scale_callback()) throw std::runtime_error("no callback installed for the scaled 8-bit conversion");
+        shim_scale_callback()(in.data(), out.data(), a.rows, a.cols, e.alpha, e.beta);
+    }
+    // assignment to an existing Mat of the same size and type reuses its buffer (Mat::create is a no-op): ROI views stay views
+    const bool inplace = data && rows == a.rows && cols == a.cols && type_ == CV_8U;
+    if (!inplace) {
+        Mat o(a.rows, a.cols, CV_8U);
+        *this = o;
+    }
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) ptr<uchar>(r)[c] = out[(size_t)r * cols + c];
+    return *this;
+}
+// cv::calcHist for one 8-bit image, 256 unit bins on [0, 256): float counts in a 256 x 1 matrix
+inline void calcHist(const Mat *images, int /*nimages*/, const int * /*channels*/, const Mat & /*mask*/, Mat &hist, int /*dims*/,
+                     const int *histSize, const float ** /*ranges*/) {
+    Mat h(*histSize, 1, CV_32F);
+    for (int r = 0; r < images->rows; ++r)
+        for (int c = 0; c < images->cols; ++c) h.ptr<float>(images->ptr<uchar>(r)[c])[0] += 1.f;
+    hist = h;
+}
+
 class VideoCapture {  // hands out the injected frame
 public:
     Mat next;
@@ -424,10 +476,10 @@ struct Scalar {
     double operator()(int i) const { return v[i]; }
     double operator[](int i) const { return v[i]; }
 };
-inline Scalar sum(const Mat &m) {
+inline Scalar sum(const Mat &m) {  // double accumulation, as cv::sum
     Scalar s = {{0, 0, 0, 0}};
     for (int r = 0; r < m.rows; ++r)
-        for (int c = 0; c < m.cols; ++c) s.v[0] += (double)m.ptr<uchar>(r)[c];
+        for (int c = 0; c < m.cols; ++c) s.v[0] += m.type() == CV_32F ? (double)m.ptr<float>(r)[c] : (double)m.ptr<uchar>(r)[c];
     return s;
 }
 // cv::LUT for single-channel 8-bit data: dst(i) = lut(src(i))

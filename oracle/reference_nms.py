@@ -256,3 +256,29 @@ def read_frame(frame, bkg, calib, flip=False):
     if rc != 0:
         raise RuntimeError("the reference's readFrame threw")
     return out
+
+
+_SCALE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_double, C.c_double)
+
+
+def mouse_box_de(side_view, threshold=255 * 0.05, min_count=10, margin=1.1):
+    """The reference's LocoMouse_TM_DE::computeMouseBox_DE + LocoMouse::imadjust_default (LocoMouse_TM_DE.cpp:56-113,
+    LocoMouse_class.cpp:3244-3311) on a calibrated side view (its zeroed bands 46 / 760 / 100 / 149 are hard-coded there).
+    The scaled 8-bit conversion of imadjust_default runs in the real OpenCV (cv2.convertScaleAbs).  Returns bb_x (double)."""
+    import cv2
+
+    L = lib()
+    img = np.array(side_view, dtype=np.uint8, order="C", copy=True)   # modified in place by the reference
+
+    def scale(src, dst, rows, cols, alpha, beta):
+        a = np.ctypeslib.as_array(src, shape=(rows, cols))
+        np.ctypeslib.as_array(dst, shape=(rows, cols))[:] = cv2.convertScaleAbs(a, alpha=alpha, beta=beta)
+
+    cb = _SCALE_FN(scale)
+    bbx = C.c_double(0.0)
+    L.ref_mouse_box_de.restype = C.c_int
+    rc = L.ref_mouse_box_de(C.c_void_p(img.ctypes.data), img.shape[0], img.shape[1], C.c_double(threshold), int(min_count), C.c_double(margin),
+                            cb, C.byref(bbx))
+    if rc != 0:
+        raise RuntimeError("the reference's computeMouseBox_DE threw")
+    return float(bbx.value)

@@ -324,3 +324,27 @@ def test_reference_shim_primitives_batch2_match_cv2():
         assert np.array_equal(outf, wf)
         m = cv2.moments(a, True)
         assert (mom[0], mom[1], mom[2]) == (m["m00"], m["m10"], m["m01"])
+
+
+def test_reference_shim_primitives_batch3_match_cv2():
+    """calcHist / sum / colRange / rowRange / setTo of the shim (pass-1 code) against the real OpenCV."""
+    import ctypes as C
+
+    from oracle import reference_nms as ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libref_nms.so not built (reference not mounted)")
+    L = ref.lib()
+    L.ref_shim_primitives3.restype = None
+    rng = np.random.Generator(np.random.PCG64(1618))
+    for _ in range(20):
+        rows, cols = int(rng.integers(2, 40)), int(rng.integers(4, 60))
+        a = rng.integers(0, 256, (rows, cols)).astype(np.uint8)
+        hist, total, band = np.zeros(256, np.float32), np.zeros(1, np.float64), np.zeros((rows, cols), np.uint8)
+        p = lambda x: C.c_void_p(x.ctypes.data)
+        L.ref_shim_primitives3(p(a), rows, cols, p(hist), p(total), p(band))
+        want = cv2.calcHist([a], [0], None, [256], [0, 256]).ravel()
+        assert np.array_equal(hist, want) and total[0] == cv2.sumElems(want)[0]
+        w = a.copy()
+        w[:, :cols // 4] = 0
+        w[rows // 2:, :] = 0
+        assert np.array_equal(band, w)

@@ -334,3 +334,39 @@ def test_readframe_golden_is_what_the_reference_code_produces(oracle):
             assert zlib.crc32(img.tobytes()) == int(z[f"c{ci}_f{f}"][0])
             want, _ = oracle.preprocess(cfg, bkg, calib, frames[f])
             assert np.array_equal(img, want)
+
+
+# ---- pass 1, LocoMouse_TM_DE: computeMouseBox_DE + imadjust_default (TM_DE.cpp:56-113, class.cpp:3244-3311) ------------------
+PASS1_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_pass1.npz")
+
+
+def _pass1_gen():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_pass1_golden", os.path.join(os.path.dirname(PASS1_GOLD), "make_reference_pass1_golden.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    return g
+
+
+def test_oracle_pass1_matches_reference_golden(oracle):
+    """The oracle's pass 1 (per-frame bb_x of LocoMouse_TM_DE) equals what the reference's own readFrame -> imadjust_default ->
+    computeMouseBox_DE code produced, as exact doubles, incl. degenerate frames (-1.1 = no qualifying column x WIDTH_MARGIN)."""
+    from locomouse_cpp_b200.types import bb_de_params
+
+    g = _pass1_gen()
+    z = np.load(PASS1_GOLD)
+    for ci, kw in enumerate(g.CASES):
+        cfg, bkg, calib, frames = g.frames_of(kw)
+        _, raw, _ = oracle.bounding_box_tm_de(cfg, bkg, calib, frames, bb_de_params(cfg, side_h=g.SIDE_H), window=5)
+        assert np.array_equal(raw.view(np.uint64), z[f"c{ci}"].view(np.uint64)), f"case {kw}: {raw.tolist()} vs {z[f'c{ci}'].tolist()}"
+    assert len(set(z["c0"].tolist())) >= 3 and z["c0"][-1] == -1.1
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libref_nms.so not built (reference not mounted)")
+def test_pass1_golden_is_what_the_reference_code_produces():
+    pytest.importorskip("cv2")
+    g = _pass1_gen()
+    z = np.load(PASS1_GOLD)
+    cfg, bkg, calib, frames = g.frames_of(g.CASES[1])
+    got = [ref.mouse_box_de(ref.read_frame(fr, bkg, calib, cfg.flip)[:g.SIDE_H]) for fr in frames[[0, 3, 8]]]
+    assert got == z["c1"][[0, 3, 8]].tolist()

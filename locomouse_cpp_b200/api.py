@@ -29,6 +29,16 @@ EXPORTS = ("lm_abi_version", "lm_create", "lm_destroy", "lm_last_error", "lm_con
            "lm_host_alloc", "lm_host_free", "lm_unary_costs", "lm_pairwise_costs")
 
 
+def _pinned_zeros(shape, dtype):
+    """numpy array backed by page-locked memory (device -> host copies then run at the PCIe rate instead of through the
+    driver's pageable staging).  tensor.numpy() keeps its tensor alive through the array's base chain."""
+    import torch
+
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    t = torch.zeros(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+    return t.numpy()[:nbytes].view(dtype).reshape(shape)
+
+
 class OverflowError_(RuntimeError):
     """A fixed-capacity list overflowed (LM_ERR_OVERFLOW); results carry per-frame flags."""
 
@@ -195,7 +205,7 @@ class Detector:
     def unary_costs(self, res: Results, feat: int, bb_w: int, bb_h: int, priors):
         """UNARY_BOTTOM_{PAW,SNOUT} for every frame of `res` (LocoMouse::unaryCostBox, LocoMouse_class.cpp:1909-1952):
         float64 [n, n_priors, cand_cap]; [f, j, i] = MyMat(i, j) of frame f.  priors: types.location_priors(...)."""
-        out = np.zeros((res.n, len(priors), res.cand_cap), np.float64)
+        out = _pinned_zeros((res.n, len(priors), res.cand_cap), np.float64)
         r = res.to_c()
         self._L.lm_unary_costs.restype = C.c_int
         self._check(self._L.lm_unary_costs(self._ctx, C.byref(r), C.c_int64(res.n), int(feat), int(bb_w), int(bb_h), priors, len(priors),
@@ -208,15 +218,15 @@ class Detector:
         ir int32[total], pr float64[total]); frame f's matrix has n_bottom[f] + Nong rows, n_bottom[f - 1] + Nong columns."""
         nong = params.ong_w * params.ong_h
         offs = np.zeros(res.n + 1, np.int64)
-        jc = np.zeros((max(res.n, 1), res.cand_cap + nong + 1), np.int32)
+        jc = _pinned_zeros((max(res.n, 1), res.cand_cap + nong + 1), np.int32)
         total = C.c_int64(0)
         r = res.to_c()
         self._L.lm_pairwise_costs.restype = C.c_int
         if cap is None:   # generous first guess; the library reports the exact need on overflow
             cap = int(res.n) * (2 * nong + 64) + 1024
         for _ in range(2):
-            ir = np.zeros(max(cap, 1), np.int32)
-            pr = np.zeros(max(cap, 1), np.float64)
+            ir = _pinned_zeros((max(cap, 1),), np.int32)
+            pr = _pinned_zeros((max(cap, 1),), np.float64)
             rc = self._L.lm_pairwise_costs(self._ctx, C.byref(r), C.c_int64(res.n), int(feat), C.byref(params), C.c_void_p(offs.ctypes.data),
                                            C.c_void_p(jc.ctypes.data), C.c_void_p(ir.ctypes.data), C.c_void_p(pr.ctypes.data), C.c_int64(cap),
                                            C.byref(total))
@@ -225,7 +235,7 @@ class Detector:
                 continue
             self._check(rc)
             break
-        return offs, jc[:res.n], ir[:total.value].copy(), pr[:total.value].copy()
+        return offs, jc[:res.n], ir[:total.value], pr[:total.value]
 
     def debug_nms(self, view: int, feat: int, scores):
         """nmsMax (view 0) / peakClustering (view 1) kernels on a given score map -> list of (x, y, score)."""

@@ -1106,12 +1106,16 @@ int lm_moving_average(const double *v, int64_t n, int32_t window, uint32_t *out)
 
 // ---- cost builders of the host tracker: candidates up, cost matrices down -------------------------------
 namespace {
-struct DevBuf {  // scoped device allocation
+struct DevBuf {  // scoped, stream-ordered device allocation (the driver's pool makes repeated calls cheap)
     void *p = nullptr;
+    cudaStream_t st = nullptr;
+    explicit DevBuf(cudaStream_t s) : st(s) {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, st);
     }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 256)); }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, std::max<size_t>(bytes, 256), st); }
 };
 }  // namespace
 
@@ -1123,12 +1127,12 @@ int lm_unary_costs(lm_ctx *ctx, const lm_results *res, int64_t n, int32_t feat, 
     if (n == 0) return LM_OK;
     CK(cudaSetDevice(ctx->device));
     const size_t cap = (size_t)res->cand_cap;
-    DevBuf dc, dn, dp, dout;
+    cudaStream_t st = ctx->stream;
+    DevBuf dc(st), dn(st), dp(st), dout(st);
     CK(dc.alloc((size_t)n * 2 * cap * sizeof(lm_cand)));
     CK(dn.alloc((size_t)n * 2 * 4));
     CK(dp.alloc((size_t)n_priors * sizeof(lm_location_prior)));
     CK(dout.alloc((size_t)n * n_priors * cap * 8));
-    cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(dc.p, res->bottom, (size_t)n * 2 * cap * sizeof(lm_cand), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dn.p, res->n_bottom, (size_t)n * 2 * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dp.p, priors, (size_t)n_priors * sizeof(lm_location_prior), cudaMemcpyHostToDevice, st));
@@ -1151,13 +1155,13 @@ int lm_pairwise_costs(lm_ctx *ctx, const lm_results *res, int64_t n, int32_t fea
     CK(cudaSetDevice(ctx->device));
     const size_t ccap = (size_t)res->cand_cap;
     const size_t jc_stride = ccap + (size_t)p->ong_w * p->ong_h + 1;
-    DevBuf dc, dn, djc, dnnz, doffs, dir, dpr;
+    cudaStream_t st = ctx->stream;
+    DevBuf dc(st), dn(st), djc(st), dnnz(st), doffs(st), dir(st), dpr(st);
     CK(dc.alloc((size_t)n * 2 * ccap * sizeof(lm_cand)));
     CK(dn.alloc((size_t)n * 2 * 4));
     CK(djc.alloc((size_t)n * jc_stride * 4));
     CK(dnnz.alloc((size_t)n * 8));
     CK(doffs.alloc((size_t)(n + 1) * 8));
-    cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(dc.p, res->bottom, (size_t)n * 2 * ccap * sizeof(lm_cand), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dn.p, res->n_bottom, (size_t)n * 2 * 4, cudaMemcpyHostToDevice, st));
     if (lm_launch_pairwise((lm_cand *)dc.p, (int32_t *)dn.p, n, (int)ccap, feat, *p, (int32_t *)djc.p, (int64_t *)dnnz.p, (int64_t *)doffs.p,

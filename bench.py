@@ -387,8 +387,8 @@ def main():
             dt2 = time.perf_counter() - t2
             costs = {"frames_per_s": n / dt1, "ms_per_10k_frames": dt1 * 1e3 * 10000 / n, "stored_entries_paw": int(len(ir)),
                      "bit_exact_on_sample": bool(ok), "cpu_port_frames_per_s_one_feature_pairwise_only": (m - 1) / dt2,
-                     "note": "lm_unary_costs + lm_pairwise_costs for both features, candidates uploaded from and matrices returned to "
-                             "pageable host memory inside the timed region (PCIe + allocation bound); CPU figure = oracle pairwisePotential "
+                     "note": "lm_unary_costs + lm_pairwise_costs for both features, candidates uploaded from host memory, matrices returned to "
+                             "page-locked buffers allocated inside the timed region (transfer + allocation bound, not kernel bound); CPU figure = oracle pairwisePotential "
                              f"through ctypes on the first {m} frames, one feature"}
         except Exception as ex:  # pragma: no cover
             costs = {"error": repr(ex)}

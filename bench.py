@@ -371,10 +371,14 @@ def main():
             pw = pairwise_params(cfg.bb_w, cfg.bb_h_bottom)
             det.unary_costs(res, 0, cfg.bb_w, cfg.bb_h_bottom, pri)
             offs, jc, ir, pr = det.pairwise_costs(res, 0, pw)
+            def run_costs():
+                for feat in range(2):
+                    det.unary_costs(res, feat, cfg.bb_w, cfg.bb_h_bottom, pri)
+                    det.pairwise_costs(res, feat, pw, cap=len(ir) + len(ir) // 8 + 1024)
+
+            run_costs()   # warm-up: the page-locked output blocks return to torch's host allocator cache and are reused below
             t1 = time.perf_counter()
-            for feat in range(2):
-                det.unary_costs(res, feat, cfg.bb_w, cfg.bb_h_bottom, pri)
-                det.pairwise_costs(res, feat, pw, cap=len(ir) + len(ir) // 8 + 1024)
+            run_costs()
             dt1 = time.perf_counter() - t1
             m = min(n, 512)
             t2 = time.perf_counter()
@@ -388,7 +392,7 @@ def main():
             costs = {"frames_per_s": n / dt1, "ms_per_10k_frames": dt1 * 1e3 * 10000 / n, "stored_entries_paw": int(len(ir)),
                      "bit_exact_on_sample": bool(ok), "cpu_port_frames_per_s_one_feature_pairwise_only": (m - 1) / dt2,
                      "note": "lm_unary_costs + lm_pairwise_costs for both features, candidates uploaded from host memory, matrices returned to "
-                             "page-locked buffers allocated inside the timed region (transfer + allocation bound, not kernel bound); CPU figure = oracle pairwisePotential "
+                             "page-locked buffers (cached by torch's host allocator) inside the timed region (transfer bound, not kernel bound); CPU figure = oracle pairwisePotential "
                              f"through ctypes on the first {m} frames, one feature"}
         except Exception as ex:  # pragma: no cover
             costs = {"error": repr(ex)}

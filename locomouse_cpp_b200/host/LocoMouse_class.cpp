@@ -11,6 +11,7 @@
 #include <sstream>
 #include <stdexcept>
 
+#include "cv_yaml.hpp"
 #include "lm_files.hpp"
 
 // =====================================================================================================
@@ -114,7 +115,7 @@ LocoMouse_Parameters::LocoMouse_Parameters(const std::string &config_file_name) 
             else if (key == "occlusion_grid_max_width") occlusion_grid_max_width = std::stod(val);
             else if (key == "alpha_vel_bottom") alpha_vel_bottom = std::stod(val);
             else if (key == "pairwise_occluded_cost") pairwise_occluded_cost = std::stod(val);
-            else if (key == "location_prior") {  // class.cpp:132-145: 5 x 7, rows 0-3 paws, row 4 snout (row-major flow list here)
+            else if (key == "location_prior" && val.rfind("!!", 0) != 0) {  // 5 x 7 as a row-major flow list; the OpenCV matrix node is read below
                 const std::vector<double> W = parse_list(val, key);
                 if (W.size() != 35) throw std::invalid_argument("location_prior must be a 5x7 matrix. Was " + std::to_string(W.size()) + " values.");
                 for (unsigned int i = 0; i <= N_paws; ++i) {
@@ -127,6 +128,17 @@ LocoMouse_Parameters::LocoMouse_Parameters(const std::string &config_file_name) 
             throw;
         } catch (const std::exception &) {
             throw std::invalid_argument("Could not parse the value of " + key + " in " + config_file_name);
+        }
+    }
+    {   // location_prior written by OpenCV as a 5 x 7 matrix node (LocoMouse_class.cpp:132-145)
+        cvyaml::File y(config_file_name);
+        if (y.isOpened() && !y.mat("location_prior").empty() && PRIOR_PAW.empty()) {
+            const cvyaml::Matrix &W = y.mat("location_prior");
+            if (W.cols != 7 || W.rows != 5) throw std::invalid_argument("location_prior must be a 5x7 matrix. Was " + std::to_string(W.rows) + ".");
+            for (unsigned int i = 0; i <= N_paws; ++i) {
+                const double *q = W.data.data() + 7 * i;
+                (i < N_paws ? PRIOR_PAW : PRIOR_SNOUT).push_back(LocoMouse_LocationPrior(q[0], q[1], q[2], q[3], q[4], q[5], q[6]));
+            }
         }
     }
     if (conn_comp_connectivity != 4 && conn_comp_connectivity != 8)
@@ -158,6 +170,28 @@ LocoMouse_Feature::LocoMouse_Feature(std::vector<float> w_b, cv::Size size_b, do
       MATCH_BOX_B(half_box(size_b)), MATCH_BOX_S(half_box(size_s)) {}
 
 LocoMouse_Model::LocoMouse_Model(const std::string &model_file_name) {
+    {   // the reference's own format: OpenCV YAML with six matrices and six biases (LocoMouse_class.cpp:3095-3162)
+        cvyaml::File y(model_file_name);
+        if (y.isOpened()) {
+            std::vector<float> w[6];
+            cv::Size sz[6];
+            double rho[6];
+            const char *wn[6] = {"modelPaw_bottom", "modelSnout_bottom", "modelTail_bottom", "modelPaw_side", "modelSnout_side", "modelTail_side"};
+            const char *bn[6] = {"biasPaw_bottom", "biasSnout_bottom", "biasTail_bottom", "biasPaw_side", "biasSnout_side", "biasTail_side"};
+            for (int k = 0; k < 6; ++k) {
+                const cvyaml::Matrix &m = y.mat(wn[k]);
+                if (m.empty()) throw std::invalid_argument(std::string("Error: ") + wn[k] + " cannot be empty." + model_file_name);
+                w[k].resize(m.data.size());
+                for (size_t i = 0; i < m.data.size(); ++i) w[k][i] = (float)m.data[i];  // filter2D converts the kernel to CV_32F
+                sz[k] = cv::Size(m.cols, m.rows);
+                rho[k] = y.real(bn[k]);
+            }
+            paw = LocoMouse_Feature(w[0], sz[0], rho[0], w[3], sz[3], rho[3]);
+            snout = LocoMouse_Feature(w[1], sz[1], rho[1], w[4], sz[4], rho[4]);
+            tail = LocoMouse_Feature(w[2], sz[2], rho[2], w[5], sz[5], rho[5]);
+            return;
+        }
+    }
     lmfile::Reader r(model_file_name, "LMM1");
     std::vector<float> w[6];
     cv::Size sz[6];
@@ -254,6 +288,24 @@ void LocoMouse::loadBackground() {
 }
 
 void LocoMouse::loadCalibration() {
+    {   // the reference's own format: OpenCV YAML with ind_warp_mapping and view_boxes (LocoMouse_class.cpp:419-463)
+        cvyaml::File y(CALIBRATION_FILE);
+        if (y.isOpened()) {
+            const cvyaml::Matrix &c = y.mat("ind_warp_mapping"), &vb = y.mat("view_boxes");
+            if (c.empty()) throw std::invalid_argument("ind_warp_mapping is empty or undefined.");
+            if (vb.empty()) throw std::invalid_argument("view_boxes is empty or undefined.");
+            if (vb.rows != 2 || vb.cols != 4) throw std::invalid_argument("view_boxes sould be a 2x4 matrix.");
+            if (vb.dt != 'i') throw std::invalid_argument("Bounding boxes must be defined with integer pixel positions!");
+            if (!c.is_integer()) throw std::invalid_argument("ind_warp_mapping must hold integer pixel indices.");
+            BB_SIDE_VIEW = cv::Rect((int)vb.data[0], (int)vb.data[1], (int)vb.data[2], (int)vb.data[3]);
+            BB_BOTTOM_VIEW = cv::Rect((int)vb.data[4], (int)vb.data[5], (int)vb.data[6], (int)vb.data[7]);
+            N_ROWS = (unsigned int)c.rows;
+            N_COLS = (unsigned int)c.cols;
+            CALIBRATION.resize(c.data.size());
+            for (size_t i = 0; i < c.data.size(); ++i) CALIBRATION[i] = (int32_t)c.data[i];
+            return;
+        }
+    }
     lmfile::Reader r(CALIBRATION_FILE, "LMC1");
     const int rows = r.i32(), cols = r.i32();
     if (rows <= 0 || cols <= 0) throw std::invalid_argument("ind_warp_mapping is empty or undefined.");

@@ -242,3 +242,92 @@ def test_main_sequence_builds_tracker_costs_on_device(tmp_path, oracle):
             assert np.array_equal(pr.view(np.uint64), wpr.view(np.uint64)), (f, feat)
             nnz += nz
     assert off == len(buf) and nnz > n * P.ong_w * P.ong_h
+
+
+# ---- the reference's own on-disk formats (OpenCV YAML) ------------------------------------------------------
+def _write_opencv_yaml(path, items):
+    """Written by the REAL OpenCV (cv2.FileStorage), as the reference's users' files are."""
+    cv2 = pytest.importorskip("cv2")
+    fs = cv2.FileStorage(str(path), cv2.FILE_STORAGE_WRITE)
+    for k, v in items:
+        fs.write(k, v)
+    fs.release()
+
+
+def test_opencv_yaml_reader_reads_what_opencv_writes(tmp_path):
+    """host/cv_yaml.hpp against files written by cv2.FileStorage: matrices of every depth the reference uses (f64 templates,
+    i32 calibration map and view boxes, f32, u8), scalars, strings, infinities; missing nodes read as 0 / empty."""
+    p = subprocess.run(["make", "-C", HOST, "test_cv_yaml"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    rng = np.random.default_rng(1)
+    A = rng.normal(0, 1e-3, (30, 30))
+    A[0, :3] = [np.inf, -np.inf, 1.0]
+    B = rng.integers(0, 680000, (13, 17)).astype(np.int32)
+    Cm = rng.normal(0, 1, (2, 3)).astype(np.float32)
+    U = rng.integers(0, 256, (2, 5)).astype(np.uint8)
+    f = tmp_path / "m.yml"
+    _write_opencv_yaml(f, [("modelPaw_side", A), ("ind_warp_mapping", B), ("f", Cm), ("u", U), ("biasPaw_side", -1.2345678901234567),
+                           ("n", 7), ("name", "abc def")])
+    out = subprocess.run([os.path.join(HOST, "test_cv_yaml"), str(f), "modelPaw_side", "ind_warp_mapping", "f", "u", "biasPaw_side", "n",
+                          "name", "nothing"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-300:]
+    lines = out.stdout.strip().split("\n")
+    vals = lambda l: np.array([float(x) for x in l.split()[5:]])
+    assert lines[0].split()[1:5] == ["matrix", "30", "30", "d"] and np.array_equal(vals(lines[0]).reshape(30, 30), A)
+    assert lines[1].split()[1:5] == ["matrix", "13", "17", "i"] and np.array_equal(vals(lines[1]).reshape(13, 17), B)
+    assert lines[2].split()[4] == "f" and np.array_equal(vals(lines[2]).reshape(2, 3).astype(np.float32), Cm)
+    assert lines[3].split()[4] == "u" and np.array_equal(vals(lines[3]).reshape(2, 5), U)
+    assert lines[4].split()[:3] == ["biasPaw_side", "scalar", repr(-1.2345678901234567)]
+    assert lines[5].split()[:3] == ["n", "scalar", "7"] and lines[6].split()[1] == "string" and lines[6].endswith("[abc def]")
+    assert lines[7].split()[:3] == ["nothing", "missing", "0"]
+    out = subprocess.run([os.path.join(HOST, "test_cv_yaml"), str(tmp_path / "absent.yml"), "x"], capture_output=True, text=True)
+    assert out.returncode == 1 and "not-opened" in out.stdout
+
+
+@pytest.mark.gpu
+def test_main_sequence_with_opencv_yaml_model_calibration_and_config(tmp_path, oracle):
+    """The class mirror driven with the reference's own file formats for the model (six f64 matrices + biases), the calibration
+    (ind_warp_mapping, view_boxes) and the configuration (location_prior as a 5 x 7 matrix node), all written by the real OpenCV:
+    detection results and cost matrices equal the oracle."""
+    from locomouse_cpp_b200 import synth
+    from locomouse_cpp_b200.types import location_priors
+
+    exe = _build_driver()
+    spec = synth.SynthSpec(method="TM", warp=True)
+    n = 5
+    cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(spec, n, seed=1000)
+    frames = frames.numpy()
+    ref = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=4)
+    write_problem_files(tmp_path, cfg, model, bkg, calib, frames, bx, bs, bb, spec.side_h, extra_cfg="batch_frames: 4\n")
+    names = (("Paw", 0), ("Snout", 1), ("Tail", 2))
+    items = []
+    for view, vn in ((1, "side"), (0, "bottom")):
+        for fn, k in names:
+            items.append((f"model{fn}_{vn}", np.asarray(model.w[view][k], np.float64)))     # templates stored as doubles, as MATLAB exports them
+            items.append((f"bias{fn}_{vn}", float(model.rho[view][k])))
+    _write_opencv_yaml(tmp_path / "model.yml", items)
+    boxes = np.array([[0, 0, cfg.n_cols, spec.side_h], [0, spec.side_h, cfg.n_cols, cfg.n_rows - spec.side_h]], np.int32)
+    _write_opencv_yaml(tmp_path / "calibration.yml", [("ind_warp_mapping", np.ascontiguousarray(calib, np.int32)), ("view_boxes", boxes)])
+    rows = [(0.8, 0.25, 0.5, 0.4, 1.0, 0.0, 0.5), (0.8, 0.75, 0.5, 0.4, 1.0, 0.5, 1.0), (0.3, 0.25, 0.4, 0.0, 0.6, 0.0, 0.5),
+            (0.3, 0.75, 0.35, 0.0, 0.6, 0.5, 1.0), (0.95, 0.5, 0.6, 0.5, 1.0, 0.0, 1.0)]
+    # append the matrix node to the scalar configuration, as cv::FileStorage lays it out
+    _write_opencv_yaml(tmp_path / "prior.yml", [("location_prior", np.array(rows, np.float64))])
+    node = (tmp_path / "prior.yml").read_text().split("---\n", 1)[1]
+    (tmp_path / "config.yml").write_text((tmp_path / "config.yml").read_text() + node)
+    p = subprocess.run([exe, "1", str(tmp_path / "config.yml"), str(tmp_path / "video.lmv"), str(tmp_path / "bkg.lmi"),
+                        str(tmp_path / "model.yml"), str(tmp_path / "calibration.yml"), "R", str(tmp_path)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    out = read_output(tmp_path / "output_video.lmo")
+    assert len(out) == n
+    for f, (tail, feats) in enumerate(out):
+        assert np.array_equal(tail, ref.tail[f])
+        for feat in range(2):
+            cb, cs, matches = feats[feat]
+            assert cb == ref.candidates_bottom(f, feat) and cs == ref.candidates_side(f, feat)
+            assert [m for m in matches] == [w[1] for w in ref.p22d(f, feat)]
+    # the priors reached the cost builders: first frame's paw unary matrix
+    buf = (tmp_path / "costs_video.lmo").read_bytes()
+    nr, nc = struct.unpack_from("<ii", buf, 8)
+    U = np.frombuffer(buf, np.float64, nr * nc, 16).reshape(nc, nr).T
+    want = oracle.unary_cost_box(ref.candidates_bottom(0, 0), cfg.bb_w, cfg.bb_h_bottom, location_priors(rows[:4]))
+    assert np.array_equal(np.ascontiguousarray(U).view(np.uint64), want.view(np.uint64))

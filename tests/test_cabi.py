@@ -40,6 +40,8 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(types.lm_config) == 72
     assert ctypes.sizeof(types.lm_results) == 96
     assert types.CAND_DTYPE.itemsize == 16
+    assert ctypes.sizeof(types.lm_location_prior) == 56 and ctypes.sizeof(types.lm_pairwise_params) == 56
+    assert ctypes.sizeof(types.lm_bb_de_params) == 56
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -1023,7 +1023,7 @@ int lm_bounding_box_tm_de(lm_ctx *ctx, const uint8_t *frames, int frames_on_devi
     CK(cudaSetDevice(ctx->device));
     const int64_t fsz = (int64_t)k.vid_rows * k.vid_cols;
     lm_ctx::BBScratch &S = ctx->bbs;
-    const int cap = 256;
+    const int cap = 1024;  // frames per chunk: large enough that launch gaps do not matter, small scratch (1.3 MB)
     if (!S.cap) {
         CK(cudaMalloc((void **)&S.minmax, (size_t)(cap + 1) * 2 * sizeof(int32_t)));
         CK(cudaMalloc((void **)&S.lut, (size_t)(cap + 1) * 256));

@@ -22,7 +22,9 @@ struct lm_ctx {
     static constexpr int NSLOT = 8;   // scratch sets / compute streams: sub-batch k runs in slot k % (option streams)
     cudaStream_t stream = nullptr, stream_more[NSLOT - 1] = {}, copy_stream = nullptr;
     cudaStream_t stream_hi = nullptr; // highest priority: the tensor-core screen kernels of all slots (option screen_priority)
+    cudaStream_t stream_back[NSLOT] = {};  // medium priority, per slot: everything after k_prep (option back_priority)
     int opt_screen_priority = 1;
+    int opt_back_priority = 0;        // 1: a sub-batch's sparse / tail / NMS / pairing / D2H outrank the min-max / crop kernels of younger sub-batches
     int opt_screen_stages = 2;        // deepest window-tile ring of k_screen2 (2..4): fewer stages leave shared memory for co-resident CTAs
     lm_config cfg{};
     bool configured = false, model_set = false, bkg_set = false, calib_set = false;
@@ -565,6 +567,9 @@ int lm_create(lm_ctx **out, int device) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi is the numerically lowest = highest priority
         streams_ok = streams_ok && cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, hi) == cudaSuccess;
+        const int mid = hi < lo ? std::min(lo, hi + (lo - hi + 1) / 2) : lo;  // between the default (lo) and the screen's (hi)
+        for (int s = 0; s < lm_ctx::NSLOT; ++s)
+            streams_ok = streams_ok && cudaStreamCreateWithPriority(&ctx->stream_back[s], cudaStreamNonBlocking, mid) == cudaSuccess;
     }
     if (!streams_ok) {
         delete ctx;
@@ -602,6 +607,7 @@ int lm_destroy(lm_ctx *ctx) {
     cudaStreamDestroy(ctx->stream);
     for (int s = 0; s < lm_ctx::NSLOT - 1; ++s) cudaStreamDestroy(ctx->stream_more[s]);
     cudaStreamDestroy(ctx->stream_hi);
+    for (int s = 0; s < lm_ctx::NSLOT; ++s) cudaStreamDestroy(ctx->stream_back[s]);
     cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
     return LM_OK;
@@ -724,6 +730,7 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, co
         cudaStreamSynchronize(ctx->stream);
         for (int s = 0; s < lm_ctx::NSLOT - 1; ++s) cudaStreamSynchronize(ctx->stream_more[s]);
         cudaStreamSynchronize(ctx->stream_hi);
+        for (int s = 0; s < lm_ctx::NSLOT; ++s) cudaStreamSynchronize(ctx->stream_back[s]);
         cudaGetLastError();
     }
     return rc;
@@ -839,7 +846,9 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
         const int slot = (int)(sub % nslot), ring = (int)(sub % lm_ctx::NRES), stg = (int)(sub & 1);
         const int64_t s0 = sub * Bcap;
         const int B = (int)std::min<int64_t>(Bcap, n - s0);
-        cudaStream_t st = streams[slot];
+        cudaStream_t stf = streams[slot];   // front: min/max, LUT, crop
+        const bool split = ctx->opt_streams > 1 && ctx->opt_back_priority;
+        cudaStream_t st = split ? ctx->stream_back[slot] : stf;   // back: screen hand-over, sparse pass, tail, NMS, pairing, D2H
         LmBatch b = slot ? ctx->bt_more[slot - 1] : ctx->bt;
         b.B = B;
         b.first_index = first_frame_index + s0;
@@ -857,18 +866,21 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
         b.screen_stream = (ctx->opt_streams > 1 && ctx->opt_screen_priority) ? ctx->stream_hi : nullptr;
         b.ev_screen_go = ctx->ev_go[ring];
         cudaEvent_t *ev = ctx->ev_stage[ring];
-        CK(cudaStreamWaitEvent(st, ctx->ev_h2d[ring], 0));
-        CK(cudaMemsetAsync(b.minmax, 0, (size_t)(B + 1) * 2 * 4, st));
-        CK(cudaMemsetAsync(b.det_count, 0, (size_t)B * 4 * 4, st));
-        CK(cudaMemsetAsync(b.flags, 0, (size_t)B * 4, st));
-        CK(cudaEventRecord(ev[0], st));
+        CK(cudaStreamWaitEvent(stf, ctx->ev_h2d[ring], 0));
+        // with the back phase on its own stream the slot's scratch is no longer protected by stream order alone
+        if (split && sub >= nslot) CK(cudaStreamWaitEvent(stf, ctx->ev_done[(sub - nslot) % lm_ctx::NRES], 0));
+        CK(cudaMemsetAsync(b.minmax, 0, (size_t)(B + 1) * 2 * 4, stf));
+        CK(cudaMemsetAsync(b.det_count, 0, (size_t)B * 4 * 4, stf));
+        CK(cudaMemsetAsync(b.flags, 0, (size_t)B * 4, stf));
+        CK(cudaEventRecord(ev[0], stf));
         int nl;
-        if ((nl = lm_launch_minmax(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "minmax launch failed");
+        if ((nl = lm_launch_minmax(b, stf)) < 0) return fail(ctx, LM_ERR_RUNTIME, "minmax launch failed");
         ctx->launches += nl;
-        CK(cudaEventRecord(ev[1], st));
-        if ((nl = lm_launch_prep(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "prep launch failed");
+        CK(cudaEventRecord(ev[1], stf));
+        if ((nl = lm_launch_prep(b, stf)) < 0) return fail(ctx, LM_ERR_RUNTIME, "prep launch failed");
         ctx->launches += nl;
-        CK(cudaEventRecord(ev[2], st));
+        CK(cudaEventRecord(ev[2], stf));
+        if (split) CK(cudaStreamWaitEvent(st, ev[2], 0));
         nl = b.scr.enabled ? lm_launch_screen(b, st) : lm_launch_corr(b, st);
         if (nl < 0) return fail(ctx, LM_ERR_RUNTIME, "correlation launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         ctx->launches += nl;
@@ -915,6 +927,7 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
         if ((rc = drain(sub))) return rc;
     }
     for (int q = 1; q < nslot; ++q) CK(cudaStreamSynchronize(streams[q]));
+    for (int q = 0; q < nslot; ++q) CK(cudaStreamSynchronize(ctx->stream_back[q]));
     CK(cudaEventRecord(ctx->ev_call[1], streams[0]));  // both streams are idle here: end of the whole call
     CK(cudaStreamSynchronize(streams[0]));
     {
@@ -938,6 +951,8 @@ int lm_set_option(lm_ctx *ctx, const char *name, int64_t value) {
     } else if (!strcmp(name, "screen_stages")) {
         if (value < 2 || value > 4) return fail(ctx, LM_ERR_INVALID, "option screen_stages must be in [2, 4]");
         ctx->opt_screen_stages = (int)value;
+    } else if (!strcmp(name, "back_priority")) {
+        ctx->opt_back_priority = value != 0;
     } else if (!strcmp(name, "screen_priority")) {
         ctx->opt_screen_priority = value != 0;
     } else if (!strcmp(name, "streams")) {

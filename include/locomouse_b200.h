@@ -160,6 +160,8 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device,
  *  "screen_layout"  bit 0: the tail template shares the paw + snout operand of the CTA-pair screen (N = 192),
  *             bit 1: y tiles stacked over the frames of a sub-batch (default 3; never changes results).
  *  "screen_priority"  1 (default): the tensor-core screen kernels run on a high-priority stream.
+ *  "back_priority"  1: everything after the crop kernel of a sub-batch runs on a medium-priority stream of its slot (default 0;
+ *             measured neutral: the pipeline is bound by aggregate SM work, not by kernel ordering).
  * lm_get_info: "screen_active" (2/1/0 after the first lm_detect_batch, -1 before), "subbatch", "ms_screen"
  *             (device ms of the tensor-core kernel alone in the last call; ms[2] of lm_last_timing = screen + exact pass),
  *             "screen_eps_<view><feat>" / "screen_scale_<view><feat>" (error bound / weight quantum). */

@@ -151,3 +151,37 @@ def test_screen2_job_layouts_are_equivalent(oracle, kw, n, sub):
         det.close()
         assert diff_results(got, ref) == [], f"layout {layout}"
     assert (0.0, 0.0) in seen and len(seen) >= 3   # the layouts were really different
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_screen2_random_geometries_equal_oracle(oracle, seed):
+    """Random geometries for the CTA-pair screen's tiling: image / box sizes (boxes lower than one 128-row tile so that stacked
+    tiles span several frames, and taller than 256 rows so that a frame needs two tile pairs), tail boxes whose width is
+    not a multiple of the 32-column tile, template shapes that differ per feature and view, odd sub-batch sizes.  Every
+    result byte equals the oracle for the default layout and with merging / stacking off."""
+    from locomouse_cpp_b200.api import Detector
+
+    rng = np.random.Generator(np.random.PCG64(9000 + seed))
+    side_h = int(rng.choice([60, 96, 140, 165, 300]))
+    bottom_h = int(rng.choice([70, 120, 235, 280]))
+    bb_w = int(rng.choice([150, 250, 400, 430]))
+    n_cols = int(bb_w * rng.uniform(1.6, 3.0)) & ~3
+    tsh = lambda: (int(rng.integers(8, 31)), int(rng.integers(8, 31)))
+    shapes = tuple(tuple(tsh() for _ in range(3)) for _ in range(2))
+    method = str(rng.choice(["TM", "TM_DE"]))
+    spec = synth.SynthSpec(method=method, n_rows=side_h + bottom_h, n_cols=n_cols, side_h=side_h, bb_w=bb_w,
+                           bb_h_side_tm=max(40, side_h - 15), tshapes=shapes, mouse_scale=min(1.0, bb_w / 400, bottom_h / 235, side_h / 165),
+                           flip=bool(rng.integers(0, 2)), cand_cap=128, match_cap=1024)
+    n = int(rng.integers(5, 12))
+    cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(spec, n, seed=1000 + seed)
+    frames = frames.numpy()
+    ref = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=8)
+    for layout in (3, 0):
+        det = Detector(cfg, model, bkg, calib, device=0)
+        det.set_option("screen_layout", layout)
+        det.set_option("subbatch", int(rng.integers(2, 8)))
+        got = det.detect_batch(frames, bx, bs, bb, allow_overflow=True)
+        active = det.info("screen_active")
+        det.close()
+        assert active >= 1.0, "the screen should handle templates up to 30 x 30"
+        assert diff_results(got, ref) == [], f"seed {seed}, layout {layout}: side_h {side_h}, bottom_h {bottom_h}, bb_w {bb_w}, shapes {shapes}"

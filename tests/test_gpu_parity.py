@@ -286,3 +286,35 @@ def test_pinned_and_pageable_result_buffers_agree():
         sums.add(res.checksum())
         det.close()
     assert len(sums) == 1
+
+
+def test_results_in_lm_host_alloc_memory():
+    """lm_host_alloc / lm_host_free: result arrays carved from the library's page-locked allocation receive the same bytes
+    as ordinary numpy arrays."""
+    import ctypes as C
+
+    from locomouse_cpp_b200 import api
+    from locomouse_cpp_b200.api import Detector
+
+    cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(synth.SynthSpec(), 5, seed=1006)
+    frames = frames.numpy()
+    L = api.load_library()
+    nbytes = Results.raw_nbytes(len(frames), cfg.cand_cap, cfg.match_cap, cfg.n_tail_points)
+    p = C.c_void_p()
+    L.lm_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    L.lm_host_free.argtypes = [C.c_void_p]
+    assert L.lm_host_alloc(C.byref(p), nbytes) == 0 and p.value
+    try:
+        buf = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_ubyte)), shape=(nbytes,))
+        buf[:] = 0xAB
+        pinned = Results(len(frames), cfg.cand_cap, cfg.match_cap, cfg.n_tail_points, buffer=buf)
+        assert pinned.raw.ctypes.data == p.value          # adopted, not copied
+        det = Detector(cfg, model, bkg, calib, device=0)
+        det.detect_batch(frames, bx, bs, bb, results=pinned)
+        plain = det.detect_batch(frames, bx, bs, bb, results=Results(len(frames), cfg.cand_cap, cfg.match_cap, cfg.n_tail_points))
+        det.close()
+        assert diff_results(pinned, plain) == []
+        del pinned, buf
+    finally:
+        assert L.lm_host_free(p) == 0
+    assert L.lm_host_free(None) == 0

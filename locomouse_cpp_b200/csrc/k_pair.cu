@@ -53,9 +53,8 @@ __device__ bool check_vel(const LmBatch &b, int f, int view, int cx, int cy, con
         const int xx = x0 + bx, yy = y0 + by;
         int prev = 0;
         if (xx >= 0 && xx < b.n_cols && yy >= 0 && yy < b.n_rows) {
-            const int xs = b.flip ? (b.n_cols - 1 - xx) : xx;
-            const int idx = b.calib[(int64_t)yy * b.n_cols + xs];
-            int d = (int)Fp[idx] - (int)b.bkg[idx];
+            const int64_t at = (int64_t)yy * b.n_cols + xx;   // mirror folded into calib_flip / bkg_warp (k_fold_calib)
+            int d = (int)Fp[b.calib_flip[at]] - (int)b.bkg_warp[at];
             prev = lutp[d < 0 ? 0 : d];
         }
         int diff = cur - prev;
@@ -187,6 +186,8 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const __grid_constant_
 int lm_launch_pair(const LmBatch &b, cudaStream_t s) {
     const size_t per_warp = (size_t)b.cand_cap * (sizeof(double) + 6 * sizeof(int));
     const int units = b.B * 2;
+    static LmDevOnce once;  // cand_cap > 384 needs more than the default 48 kB of dynamic shared memory
+    if (once.first() && cudaFuncSetAttribute(k_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return -1;
     k_pair<<<(units + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, per_warp * PAIR_WARPS, s>>>(b);
-    return 1;
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

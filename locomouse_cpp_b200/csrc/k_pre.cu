@@ -162,53 +162,89 @@ __global__ void __launch_bounds__(256) k_lut(const __grid_constant__ LmBatch b, 
 }
 
 // ---- k_prep --------------------------------------------------------------------------------------
-// One CTA = PREP_ROWS window rows of one (frame, view); a thread owns one 4-pixel word column and walks the rows, so all
-// index arithmetic is 32-bit and incremental (the per-word division / 64-bit multiplies of a flat loop made the kernel
-// issue-bound at ~48 instructions per pixel).
-constexpr int PREP_ROWS = 16;
+// Per video, once (k_fold_calib): the calibration map with the optional mirror folded in, calib_flip[r][c] =
+// calib[r][flip ? n_cols - 1 - c : c], and the background seen through it, bkg_warp[r][c] = bkg[calib_flip[r][c]].  A window
+// pixel is then lut[max(F[calib_flip] - bkg_warp, 0)]: one gather (the frame) instead of three.
+// k_prep: one CTA = PREP_ROWS window rows of one (frame, view).  A thread owns one 4-pixel word column and walks the rows
+// (32-bit incremental indexing); words that lie wholly inside the image -- all but the box border -- take a path without
+// per-pixel predicates: four map loads, four frame bytes, the background word by two aligned loads + funnel shift.
+constexpr int PREP_ROWS = 64;
+constexpr int PREP_THREADS = 256;
 
-__global__ void __launch_bounds__(128) k_prep(const __grid_constant__ LmBatch b) {
+__global__ void __launch_bounds__(256) k_fold_calib(const int32_t *__restrict__ calib, const uint8_t *__restrict__ bkg, int n_rows, int n_cols,
+                                                    int flip, int32_t *__restrict__ calib_flip, uint8_t *__restrict__ bkg_warp) {
+    const int64_t n = (int64_t)n_rows * n_cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / n_cols), c = (int)(i - (int64_t)r * n_cols);
+        const int32_t src = calib[(int64_t)r * n_cols + (flip ? n_cols - 1 - c : c)];
+        calib_flip[i] = src;
+        bkg_warp[i] = bkg[src];
+    }
+}
+
+__global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ LmBatch b) {
     const int f = blockIdx.y, v = blockIdx.z;
     const LmView &V = b.view[v];
+    const int r0 = blockIdx.x * PREP_ROWS;
+    if (r0 >= V.win_h) return;
     __shared__ uint8_t lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = b.lut[(f + 1) * 256 + i];
     __syncthreads();
-    const int r0 = blockIdx.x * PREP_ROWS;
-    if (r0 >= V.win_h) return;
     const int r1 = min(V.win_h, r0 + PREP_ROWS);
-    const uint8_t *F = b.frames + (int64_t)f * b.frame_bytes;
-    const uint8_t *K = b.bkg;
+    const uint8_t *__restrict__ F = b.frames + (int64_t)f * b.frame_bytes;
+    const uint8_t *__restrict__ Kw = b.bkg_warp;
+    const int32_t *__restrict__ C2 = b.calib_flip;
     const int x0 = (int)b.bb_x[f] - b.bb_w + 1 - V.halo_x;
     const int ypos = (int)(v == LM_BOTTOM ? b.bb_y_bottom[f] : b.bb_y_side[f]);
     const int y0 = ypos - V.box_h + 1 - V.halo_y;
     uint8_t *W = b.win[v] + (int64_t)f * V.win_stride;
-    const int words_per_row = V.win_pitch >> 2;
-    const int n_cols = b.n_cols;
-    for (int w = threadIdx.x; w < words_per_row; w += blockDim.x) {
-        const int c4 = w << 2;
-        // image columns of this word's four pixels (after the optional mirror), -1 = outside the window or the image
-        int xs[4];
+    const int wpr = V.win_pitch >> 2, n_cols = b.n_cols, n_rows = b.n_rows;
+    // thread -> (row slot, word column); when a row has more words than the CTA has threads the words are looped over
+    const int nslot = wpr <= PREP_THREADS ? PREP_THREADS / wpr : 1;
+    const int slot = wpr <= PREP_THREADS ? (int)threadIdx.x / wpr : 0;
+    if (slot >= nslot) return;
+    for (int w = wpr <= PREP_THREADS ? (int)threadIdx.x - slot * wpr : (int)threadIdx.x; w < wpr; w += PREP_THREADS) {
+        const int c4 = w << 2, xx0 = x0 + c4;
+        // bit q: pixel q of the word is a window pixel that lies inside the image
+        unsigned vm = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int c = c4 + q, xx = x0 + c;
-            xs[q] = (c < V.win_w && xx >= 0 && xx < n_cols) ? (b.flip ? n_cols - 1 - xx : xx) : -1;
-        }
-        const bool any = xs[0] >= 0 || xs[1] >= 0 || xs[2] >= 0 || xs[3] >= 0;
-        for (int r = r0; r < r1; ++r) {
-            const int yy = y0 + r;
-            uint32_t out = 0;
-            if (any && yy >= 0 && yy < b.n_rows) {
-                const int32_t *crow = b.calib + (int64_t)yy * n_cols;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (xs[q] >= 0) {
-                        const int idx = __ldg(crow + xs[q]);
-                        int d = (int)__ldg(F + idx) - (int)__ldg(K + idx);
-                        d = d < 0 ? 0 : d;
-                        out |= (uint32_t)lut[d] << (8 * q);
-                    }
+        for (int q = 0; q < 4; ++q)
+            if (c4 + q < V.win_w && xx0 + q >= 0 && xx0 + q < n_cols) vm |= 1u << q;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(W + (int64_t)(r0 + slot) * V.win_pitch) + w;
+        const int dst_step = nslot * wpr;  // words
+        int yy = y0 + r0 + slot;
+        if (vm == 0xFu) {
+#pragma unroll 2
+            for (int r = r0 + slot; r < r1; r += nslot, yy += nslot, dst += dst_step) {
+                uint32_t out = 0;
+                if (yy >= 0 && yy < n_rows) {
+                    const int base = yy * n_cols + xx0;
+                    const int32_t *cp = C2 + base;
+                    const int i0 = __ldg(cp), i1 = __ldg(cp + 1), i2 = __ldg(cp + 2), i3 = __ldg(cp + 3);
+                    const uint32_t *kp = reinterpret_cast<const uint32_t *>(Kw + (base & ~3));  // bkg_warp is 4-byte aligned and padded
+                    const uint32_t kw4 = __funnelshift_r(__ldg(kp), __ldg(kp + 1), (base & 3) * 8);
+                    const int d0 = max((int)__ldg(F + i0) - (int)(kw4 & 0xffu), 0);
+                    const int d1 = max((int)__ldg(F + i1) - (int)((kw4 >> 8) & 0xffu), 0);
+                    const int d2 = max((int)__ldg(F + i2) - (int)((kw4 >> 16) & 0xffu), 0);
+                    const int d3 = max((int)__ldg(F + i3) - (int)(kw4 >> 24), 0);
+                    out = (uint32_t)lut[d0] | ((uint32_t)lut[d1] << 8) | ((uint32_t)lut[d2] << 16) | ((uint32_t)lut[d3] << 24);
+                }
+                *dst = out;
             }
-            reinterpret_cast<uint32_t *>(W + (int64_t)r * V.win_pitch)[w] = out;
+        } else {
+            for (int r = r0 + slot; r < r1; r += nslot, yy += nslot, dst += dst_step) {
+                uint32_t out = 0;
+                if (vm && yy >= 0 && yy < n_rows) {
+                    const int base = yy * n_cols + xx0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (vm & (1u << q)) {
+                            const int d = max((int)__ldg(F + __ldg(C2 + base + q)) - (int)__ldg(Kw + base + q), 0);
+                            out |= (uint32_t)lut[d] << (8 * q);
+                        }
+                }
+                *dst = out;
+            }
         }
     }
 }
@@ -231,6 +267,12 @@ int lm_launch_prep(const LmBatch &b, cudaStream_t s) {
     int maxh = 0;
     for (int v = 0; v < 2; ++v) maxh = b.view[v].win_h > maxh ? b.view[v].win_h : maxh;
     const int bx = (maxh + PREP_ROWS - 1) / PREP_ROWS;
-    k_prep<<<dim3(bx < 1 ? 1 : bx, b.B, 2), 128, 0, s>>>(b);
+    k_prep<<<dim3(bx < 1 ? 1 : bx, b.B, 2), PREP_THREADS, 0, s>>>(b);
     return 1;
+}
+
+int lm_launch_fold_calib(const int32_t *calib, const uint8_t *bkg, int n_rows, int n_cols, int flip, int32_t *calib_flip, uint8_t *bkg_warp,
+                         cudaStream_t s) {
+    k_fold_calib<<<lm_sm_count() * 4, 256, 0, s>>>(calib, bkg, n_rows, n_cols, flip, calib_flip, bkg_warp);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -20,7 +20,12 @@
 // Pair protocol: window-tile "full" and accumulator "empty" barriers live in the leader CTA (rank 0) and
 // collect arrivals from both CTAs (remote arrive through mapa); tcgen05.commit multicasts "tile free" and
 // "accumulator full" to the barrier at the same offset in both CTAs.  Only the leader issues MMAs.
+// Window tiles are moved by the TMA unit (cp.async.bulk.tensor, cta_group::2: each CTA's boxes land in its own
+// shared memory and their bytes are counted on the leader's "full" barrier), one elected producer thread per CTA.
+#include <cuda.h>
+
 #include <algorithm>
+#include <climits>
 #include <cmath>
 
 #include "lm_internal.h"
@@ -28,7 +33,8 @@
 
 namespace {
 
-constexpr int S2_THREADS = 224;   // warps 0-3 epilogue, 4-5 loaders, 6 MMA issuer / TMEM owner
+constexpr int S2_THREADS = 192;   // warps 0-3 epilogue, 4 TMA producer, 5 MMA issuer / TMEM owner
+constexpr int S2_WARP_TMA = 4, S2_WARP_MMA = 5;
 constexpr int S2_TILE_M = 128;
 constexpr int S2_TILE_X = 32;
 constexpr int S2_STAGES = 4;      // maximum ring depth; a job uses J.j.stages of them
@@ -43,9 +49,16 @@ struct Screen2JobDev {
     int VH;                   // rows between consecutive frames in tile-row space (window height when stacked)
     int pair_begin, npair;
     int halo_x, halo_y;
+    // 32-bit form of the thresholds on H = hi + (lo >> 8) (V = 256 H + (lo & 255)):  V > t_lo  =>  H >= q_need;
+    // H > q_sign  =>  V > t_hi.  Conservative by less than one hi-digit unit (256 of ~2e5 units between t_lo and t_hi).
+    int q_need[3], q_sign[3];
 };
 
 struct Screen2Params {
+    // Window tiles arrive by TMA: per job one tiled tensor map over the sub-batch's windows of its view, box = 16 bytes x
+    // `rows` window rows = one K panel of a tile.  Stacked jobs see the windows as one tall 2-D image (a tile may run on
+    // into the next frame), the others as [frame][row][byte] (rows past the window are zero-filled by the TMA unit).
+    CUtensorMap tmap[6];
     Screen2JobDev job[6];
     int njobs;
     int B;
@@ -95,7 +108,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
     }
     if (tid == 0) {
         for (int s = 0; s < S2_STAGES; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_full(s)), "r"(128));   // 64 loader threads x 2 CTAs
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_full(s)), "r"(2));     // one arrive.expect_tx per CTA; the TMA units add the bytes
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_empty(s)), "r"(1));
         }
         for (int a = 0; a < 2; ++a) {
@@ -104,7 +117,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 6) {
+    if (warp == S2_WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(S2_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     }
@@ -115,58 +128,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
 
-    if (warp >= 4 && warp < 6) {
-        // ================= loaders (both CTAs): this CTA's y tile of the unit ====================================
-        const int ll = tid - 128;
-        const int v = J.j.view;
-        const int win_h = P.win_h[v], pitch = P.win_pitch[v];
-        const int nchunks = rows * npanel;
+    if (warp == S2_WARP_TMA) {
+        // ================= TMA producer (both CTAs): this CTA's y tile of the unit ================================
+        const CUtensorMap *tm = &P.tmap[ji];
+        const bool stacked = J.j.stacked != 0;
         int stage = 0;
         uint32_t phase = 0;
         for (int u = prank; u < nunits; u += J.npair) {
             const int tp = u / J.nxt, xt = u - tp * J.nxt;
             const int R0 = (2 * tp + (int)rank) * S2_TILE_M, x0 = xt * S2_TILE_X;  // first tile row in tile-row space
-            const int f0 = R0 / VH, yf0 = R0 - f0 * VH;
-            const uint8_t *wbase = P.win[v];
             mbar_wait(a_empty(stage), phase ^ 1u);
-            uint8_t *dstA = sA + (uint32_t)stage * stage_bytes;
-            constexpr int UNR = 5;
-            for (int base = 0; base < nchunks; base += 64 * UNR) {
-                int4 val[UNR];
-#pragma unroll
-                for (int q = 0; q < UNR; ++q) {
-                    const int idx = base + q * 64 + ll;
-                    int4 x = make_int4(0, 0, 0, 0);
-                    if (idx < nchunks) {
-                        const int r = idx / npanel, p = idx - r * npanel;
-                        int f = f0, wr = yf0 + r;   // a tile spans at most a few frames
-                        while (wr >= VH) {
-                            wr -= VH;
-                            ++f;
-                        }
-                        const int wc = x0 + 16 * p;
-                        if (f < P.B && wr < win_h && wc + 16 <= pitch)
-                            x = __ldg(reinterpret_cast<const int4 *>(wbase + (int64_t)f * P.win_stride[v] + (int64_t)wr * pitch + wc));
-                    }
-                    val[q] = x;
-                }
-#pragma unroll
-                for (int q = 0; q < UNR; ++q) {
-                    const int idx = base + q * 64 + ll;
-                    if (idx < nchunks) {
-                        const int r = idx / npanel, p = idx - r * npanel;
-                        *reinterpret_cast<int4 *>(dstA + (uint32_t)p * panel_a + (uint32_t)r * 16u) = val[q];
-                    }
+            if (elect_one()) {
+                const uint32_t full = mapa_u32(a_full(stage), 0);  // the leader's barrier counts both CTAs' bytes
+                mbar_arrive_expect_tx_cluster(full, stage_bytes);
+                const uint32_t dst = smem_u32(sA) + (uint32_t)stage * stage_bytes;
+                if (stacked) {
+                    for (int p = 0; p < npanel; ++p) tma_load_2d_pair(dst + (uint32_t)p * panel_a, tm, full, x0 + 16 * p, R0);
+                } else {
+                    const int f0 = R0 / VH, yf0 = R0 - f0 * VH;
+                    for (int p = 0; p < npanel; ++p) tma_load_3d_pair(dst + (uint32_t)p * panel_a, tm, full, x0 + 16 * p, yf0, f0);
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive_cluster(a_full(stage), 0);  // the leader's barrier counts both CTAs' loaders
+            __syncwarp();
             if (++stage == nst) {
                 stage = 0;
                 phase ^= 1u;
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == S2_WARP_MMA) {
         // ================= MMA issuer (leader CTA only) =============================================================
         if (rank == 0) {
             // u8 x s8 -> s32, K-major operands, M = 256 across the pair; N = 2 * nhalf, or 2 * nhalf_narrow right of the tail box
@@ -236,13 +225,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
                 tmem_ld32(ta + (uint32_t)J.j.col_hi[nar][t], hi);
                 tmem_ld32(ta + (uint32_t)J.j.col_lo[nar][t], lo);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const long long t_lo = J.j.t_lo[t], t_hi = J.j.t_hi[t];
+                const int q_need = J.q_need[t], q_sign = J.q_sign[t];
                 uint32_t need = 0, sign = 0;
+                if (J.j.feat[t] == LM_TAIL) {  // warp-uniform: only the tail consumes the "provably positive" map
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const long long V = (long long)(int)hi[c] * 256 + (long long)(int)lo[c];
-                    if (V > t_lo) need |= 1u << c;
-                    if (V > t_hi) sign |= 1u << c;
+                    for (int c = 0; c < 32; ++c) {
+                        const int H = (int)hi[c] + ((int)lo[c] >> 8);
+                        if (H >= q_need) need |= 1u << c;
+                        if (H > q_sign) sign |= 1u << c;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int H = (int)hi[c] + ((int)lo[c] >> 8);
+                        if (H >= q_need) need |= 1u << c;
+                    }
                 }
                 const int wvalid = J.out_w[t] - x0;
                 const uint32_t colmask = wvalid >= 32 ? 0xffffffffu : (wvalid <= 0 ? 0u : ((1u << wvalid) - 1u));
@@ -317,7 +314,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     cluster_sync_all();
-    if (warp == 6) {
+    if (warp == S2_WARP_MMA) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(S2_TMEM_COLS));
     }
@@ -327,6 +324,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
 
 size_t lm_screen2_smem_bytes(int KH, int ks, int rows, int nhalf, int stages) {
     return (size_t)KH * 2 * ks * nhalf * 16 + (size_t)stages * 2 * ks * rows * 16;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// One K panel of a window tile = a box of 16 bytes x `rows` rows; out-of-range rows / columns / frames read as zero.
+static bool encode_window_map(CUtensorMap *tm, const uint8_t *win, int pitch, int win_h, int64_t win_stride, int frames, int rows, bool stacked) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || rows > 256 || (pitch & 15) || (win_stride & 15)) return false;
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (stacked) {  // frames are win_h rows apart (win_stride == pitch * win_h): one tall image
+        const cuuint64_t dim[2] = {(cuuint64_t)pitch, (cuuint64_t)win_h * (cuuint64_t)frames};
+        const cuuint64_t str[1] = {(cuuint64_t)pitch};
+        const cuuint32_t box[2] = {16, (cuuint32_t)rows};
+        return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(win), dim, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    const cuuint64_t dim[3] = {(cuuint64_t)pitch, (cuuint64_t)win_h, (cuuint64_t)frames};
+    const cuuint64_t str[2] = {(cuuint64_t)pitch, (cuuint64_t)win_stride};
+    const cuuint32_t box[3] = {16, (cuuint32_t)rows, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(win), dim, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Launches k_screen2 for the pair-level jobs; the caller has zeroed the task counters.
@@ -355,11 +384,20 @@ int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s) {
             J.ntp = (int)(((int64_t)b.B * J.VH + 2 * S2_TILE_M - 1) / (2 * S2_TILE_M));
             J.halo_x = b.view[v].halo_x;
             J.halo_y = b.view[v].halo_y;
+            for (int t = 0; t < sj.ntmpl; ++t) {
+                auto fdiv256 = [](long long x) { return x >= 0 ? x / 256 : -((-x + 255) / 256); };  // floor
+                auto clampi = [](long long x) { return (int)std::max<long long>(INT_MIN + 1LL, std::min<long long>(INT_MAX - 1LL, x)); };
+                J.q_need[t] = clampi(fdiv256(sj.t_lo[t]));
+                J.q_sign[t] = clampi(fdiv256(sj.t_hi[t]));
+            }
             int n_narrow = 0;
             for (int xt = 0; xt < J.nxt; ++xt) n_narrow += (xt * S2_TILE_X >= sj.narrow_x0);
             work[P.njobs] = (double)J.ntp * sj.KH * sj.ks * ((J.nxt - n_narrow) * icost(2 * sj.nhalf) + n_narrow * icost(2 * sj.nhalf_narrow));
             total += work[P.njobs];
             smem = std::max(smem, lm_screen2_smem_bytes(sj.KH, sj.ks, sj.rows, sj.nhalf, sj.stages));
+            if (sj.stacked && b.view[v].win_stride != (int64_t)b.view[v].win_pitch * b.view[v].win_h) return -1;
+            if (!encode_window_map(&P.tmap[P.njobs], b.win[v], b.view[v].win_pitch, b.view[v].win_h, b.view[v].win_stride, b.B, sj.rows, sj.stacked != 0))
+                return -1;
             ++P.njobs;
         }
     if (!P.njobs) return 0;
@@ -386,6 +424,7 @@ int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s) {
         P.tailbin_stride[v] = (int64_t)b.bb_h[v] * b.tail_pitch;
     }
     P.tail_pitch = b.tail_pitch;
+    static_assert(sizeof(Screen2Params) <= 4000, "kernel parameter space");
     static LmDevOnce once;
     if (once.first()) {
         if (cudaFuncSetAttribute(k_screen2, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) return -1;

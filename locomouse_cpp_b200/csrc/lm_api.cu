@@ -33,6 +33,9 @@ struct lm_ctx {
 
     uint8_t *d_bkg = nullptr;
     int32_t *d_calib = nullptr;
+    int32_t *d_calib_flip = nullptr;  // calibration with the mirror folded in + the background seen through it (k_fold_calib):
+    uint8_t *d_bkg_warp = nullptr;    // scratch of prepare(), rebuilt when the background / calibration change (fold_dirty)
+    bool fold_dirty = true;
     float *d_tmpl[2][3] = {};
     std::vector<float> h_tmpl[2][3];  // host copies (the screen's quantisation is derived from them)
     int opt_screen = 2;               // 0: dense exact kernel only, 1: tensor-core screen, one CTA per tile, 2: CTA pairs
@@ -166,6 +169,9 @@ void free_scratch(lm_ctx *c) {
         c->h_res[s] = nullptr;
     }
     for (int s = 0; s < 2; ++s) c->d_stage[s] = nullptr;
+    c->d_calib_flip = nullptr;
+    c->d_bkg_warp = nullptr;
+    c->fold_dirty = true;
     for (int s = 0; s < lm_ctx::NRES; ++s) c->d_bb[s] = nullptr;
     for (int s = 0; s < lm_ctx::NSLOT; ++s) c->d_res[s] = nullptr;
     c->nsets = 0;
@@ -434,6 +440,11 @@ int prepare(lm_ctx *ctx) {
     if (const char *e = getenv("LM_SUBBATCH")) Bcap = std::max(1, atoi(e));
     const size_t B = (size_t)Bcap;
     int rc;
+    if ((rc = dalloc(ctx, &ctx->d_calib_flip, (size_t)k.n_rows * k.n_cols))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_bkg_warp, (size_t)k.n_rows * k.n_cols + 16))) return rc;  // + padding: word loads past the last pixel
+    b.calib_flip = ctx->d_calib_flip;
+    b.bkg_warp = ctx->d_bkg_warp;
+    ctx->fold_dirty = true;
     if ((rc = dalloc(ctx, &b.minmax, (B + 1) * 2))) return rc;
     if ((rc = dalloc(ctx, &b.lut, (B + 1) * 256))) return rc;
     for (int v = 0; v < 2; ++v) {
@@ -677,6 +688,7 @@ int lm_set_background(lm_ctx *ctx, const uint8_t *bkg) {
     CK(cudaMemcpy(ctx->d_bkg, bkg, n, cudaMemcpyHostToDevice));
     ctx->bt.bkg = ctx->d_bkg;
     ctx->bkg_set = true;
+    ctx->fold_dirty = true;
     return LM_OK;
 }
 
@@ -697,6 +709,7 @@ int lm_set_calibration(lm_ctx *ctx, const int32_t *map) {
     CK(cudaMemcpy(ctx->d_calib, map, n * sizeof(int32_t), cudaMemcpyHostToDevice));
     ctx->bt.calib = ctx->d_calib;
     ctx->calib_set = true;
+    ctx->fold_dirty = true;
     return LM_OK;
 }
 
@@ -759,6 +772,12 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
     int rc = prepare(ctx);
     if (rc) return rc;
     if (!frames_on_device && (rc = ensure_stage(ctx))) return rc;
+    if (ctx->fold_dirty) {  // per-video constants of k_prep / k_pair; every stream of the previous call has been drained
+        if (lm_launch_fold_calib(ctx->d_calib, ctx->d_bkg, k.n_rows, k.n_cols, k.flip, ctx->d_calib_flip, ctx->d_bkg_warp, ctx->stream) < 0)
+            return fail(ctx, LM_ERR_RUNTIME, "calibration fold launch failed");
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->fold_dirty = false;
+    }
 
     const int Bcap = ctx->Bcap;
     const int64_t fsz = ctx->bt.frame_bytes;

@@ -95,6 +95,8 @@ struct LmBatch {
     int64_t first_index;        // CURRENT_FRAME of frame 0 of this sub-batch
     const uint8_t *bkg;
     const int32_t *calib;
+    const int32_t *calib_flip;  // [n_rows][n_cols] calib with the mirror folded in (k_fold_calib); detection path only
+    const uint8_t *bkg_warp;    // [n_rows][n_cols] bkg[calib_flip], 4-byte aligned, >= 8 bytes of padding behind it
     const uint32_t *bb_x, *bb_y_side, *bb_y_bottom;  // device, [B]
     // config
     int vid_rows, vid_cols, n_rows, n_cols;
@@ -132,6 +134,8 @@ struct LmBatch {
 // launchers (each returns the number of kernels it launched)
 int lm_launch_minmax(const LmBatch &b, cudaStream_t s);
 int lm_launch_prep(const LmBatch &b, cudaStream_t s);
+int lm_launch_fold_calib(const int32_t *calib, const uint8_t *bkg, int n_rows, int n_cols, int flip, int32_t *calib_flip, uint8_t *bkg_warp,
+                         cudaStream_t s);
 int lm_launch_corr(const LmBatch &b, cudaStream_t s);
 int lm_launch_tail(const LmBatch &b, cudaStream_t s);
 int lm_launch_nms(const LmBatch &b, cudaStream_t s);

@@ -80,3 +80,27 @@ __device__ __forceinline__ void umma_i8_2cta(uint32_t tmem_d, uint64_t adesc, ui
                  "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
                  : "memory");
 }
+
+// ---- TMA (cp.async.bulk.tensor) into a CTA pair's window ring ------------------------------------------------
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+// one arrival + `bytes` expected transaction bytes on a barrier given by its shared::cluster address (may be the peer's)
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t bar_cluster, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster), "r"(bytes) : "memory");
+}
+// 2-D / 3-D tiled loads executed by either CTA of a pair: the box lands in THIS CTA's shared memory, the transaction bytes
+// are counted on the barrier at `bar_cluster` (the leader's), as a cta_group::2 MMA needs both halves before it may issue.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void *tmap, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(bar_cluster)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const void *tmap, uint32_t bar_cluster, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster)
+                 : "memory");
+}

@@ -115,6 +115,10 @@ LocoMouse_Parameters::LocoMouse_Parameters(const std::string &config_file_name) 
             else if (key == "occlusion_grid_max_width") occlusion_grid_max_width = std::stod(val);
             else if (key == "alpha_vel_bottom") alpha_vel_bottom = std::stod(val);
             else if (key == "pairwise_occluded_cost") pairwise_occluded_cost = std::stod(val);
+            else if (key == "max_displacement_side") max_displacement_side = std::stoi(val);
+            else if (key == "occlusion_grid_spacing_pixels_side") occlusion_grid_spacing_pixels_side = std::stoi(val);
+            else if (key == "alpha_vel_side") alpha_vel_side = std::stod(val);
+            else if (key == "tracker_threads") tracker_threads = std::stoi(val);
             else if (key == "location_prior" && val.rfind("!!", 0) != 0) {  // 5 x 7 as a row-major flow list; the OpenCV matrix node is read below
                 const std::vector<double> W = parse_list(val, key);
                 if (W.size() != 35) throw std::invalid_argument("location_prior must be a 5x7 matrix. Was " + std::to_string(W.size()) + " values.");
@@ -149,6 +153,10 @@ LocoMouse_Parameters::LocoMouse_Parameters(const std::string &config_file_name) 
         throw std::invalid_argument("tail_sub_bounding_box must belong to [0, 1].");
     if (bb_width <= 0 || bb_height_side <= 0) throw std::invalid_argument("bb_width and bb_height_side must be positive.");
     if (batch_frames <= 0) throw std::invalid_argument("batch_frames must be positive.");
+    if (max_displacement_side < 0) throw std::invalid_argument("max_displacement_side must be non-negative. Was " + std::to_string(max_displacement_side) + ".");
+    if (occlusion_grid_spacing_pixels_side <= 0 || occlusion_grid_spacing_pixels_bottom <= 0)
+        throw std::invalid_argument("occlusion_grid_spacing_pixels_side / _bottom must be positive.");
+    if (alpha_vel_side < 0) throw std::invalid_argument("alpha_vel_side must be non-negative. Was " + std::to_string(alpha_vel_side) + ".");
     if (moving_average_window <= 0 || moving_average_window % 2 == 0)
         throw std::invalid_argument("moving_average_window must be a positive odd integer.");
 }
@@ -264,6 +272,7 @@ void LocoMouse::initializePaths(const LocoMouse_ParseInputs &INPUT) {
     // output_<stem>.* next to the reference's output_<stem>.yml (LocoMouse_class.cpp:360)
     output_file = OUTPUT_PATH + "/output_" + INPUT.FILE_STEM + ".lmo";
     costs_file = OUTPUT_PATH + "/costs_" + INPUT.FILE_STEM + ".lmo";
+    tracks_file = OUTPUT_PATH + "/output_" + INPUT.FILE_STEM + ".yml";  // the reference's own output file (class.cpp:360)
 }
 
 void LocoMouse::loadVideo() {
@@ -500,6 +509,25 @@ void LocoMouse::initializeFeatureLoop() {
     CANDIDATES_MATCHED_VIEWS_PAW.reserve(N_FRAMES);
     CANDIDATES_MATCHED_VIEWS_SNOUT.reserve(N_FRAMES);
     TRACKS_TAIL.reserve(N_FRAMES);
+    {   // occlusion grids (class.cpp:726-759); integer / double arithmetic as written there
+        const int sp = LM_PARAMS.occlusion_grid_spacing_pixels_bottom, sps = LM_PARAMS.occlusion_grid_spacing_pixels_side;
+        const unsigned int ngrid_y = (unsigned int)(((BB_BOTTOM_MOUSE.height - sp) / sp) + 1);
+        const unsigned int ngrid_x = (unsigned int)(((LM_PARAMS.occlusion_grid_max_width * BB_BOTTOM_MOUSE.width) - sp) / sp + 1);
+        ONG_size = cv::Size((int)ngrid_x, (int)ngrid_y);
+        ONG_BR_corner = cv::Point_<double>(BB_BOTTOM_MOUSE.width - 1 - sp / 2, BB_BOTTOM_MOUSE.height - 1 - sp / 2);
+        ONG.assign((size_t)ngrid_x * ngrid_y, cv::Point_<double>(0, 0));
+        for (unsigned int j = 0; j < ngrid_y; ++j)
+            for (unsigned int i = 0; i < ngrid_x; ++i)
+                ONG[(size_t)j * ngrid_x + i] = cv::Point_<double>(ONG_BR_corner.x - (double)(i * (unsigned int)sp), ONG_BR_corner.y - (double)(j * (unsigned int)sp));
+        const unsigned int nong_side = (unsigned int)(((BB_SIDE_MOUSE.height - sps) / sps) + 1);
+        ONG_SIDE_LOWEST_POINT = (unsigned int)(BB_SIDE_MOUSE.height - 1 - sps / 2);
+        ONG_SIDE.clear();
+        for (unsigned int i = 0; i < nong_side; ++i) ONG_SIDE.push_back(ONG_SIDE_LOWEST_POINT - i * (unsigned int)sps);
+    }
+    UNARY_BOTTOM_PAW.clear();
+    UNARY_BOTTOM_SNOUT.clear();
+    PAIRWISE_BOTTOM_PAW.clear();
+    PAIRWISE_BOTTOM_SNOUT.clear();
     CURRENT_FRAME = -1;  // the reference rewinds the video here (class.cpp:762)
     BATCH.reset();
     LOOP_READY = true;
@@ -689,14 +717,13 @@ void LocoMouse::matchBottomSideCandidates() {
 
 void LocoMouse::storePreviousImage() {}  // the device keeps the previous raw frame (halo) itself
 
-// The sequential tracker stays on the host unchanged (north_star); it is not part of this library.
-void LocoMouse::computeBottomTracks() {}
-void LocoMouse::computeSideTracks() {}
+// computeBottomTracks / computeSideTracks / exportPointTracks / exportLineTracks: LocoMouse_tracks.cpp
 
 // "LMO1": i32 n_frames, n_tail_points; per frame: 3*n_tail i32 tail track; then for paw, snout:
 //   i32 n_bottom, n_bottom x {i32 x, y; f64 s};  i32 n_side, n_side x {i32 x, y; f64 s};
 //   n_bottom x { i32 n_match, n_match x {i32 y; f64 s} }     (n_match = P22D::number_of_candidates())
 void LocoMouse::exportResults() {
+    exportTracks();  // output_<stem>.yml, the reference's output (LocoMouse_tracks.cpp); skipped when the tracker did not run
     lmfile::Writer w(output_file, "LMO1");
     const size_t n = CANDIDATES_MATCHED_VIEWS_PAW.size();
     w.i32((int32_t)n);

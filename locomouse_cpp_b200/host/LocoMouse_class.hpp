@@ -41,6 +41,11 @@ public:
     double occlusion_grid_max_width = 0.75;
     double alpha_vel_bottom = 1E-1;
     double pairwise_occluded_cost = 1E-2;
+    // side-view tracker (class.hpp:60-61, 67): bestSideViewMatch / pairwisePotential_SideView
+    int max_displacement_side = 15;
+    int occlusion_grid_spacing_pixels_side = 20;
+    double alpha_vel_side = 100;
+    int tracker_threads = 0;          // host threads for the independent match2nd problems (0: one per hardware thread)
     std::vector<LocoMouse_LocationPrior> PRIOR_PAW, PRIOR_SNOUT;  // config key location_prior (5 x 7); empty: cost builders are skipped
     int conn_comp_connectivity = 8;
     double side_bottom_min_overlap = 0.7;
@@ -90,6 +95,11 @@ public:
     explicit LocoMouse_Model(const std::string &model_file_name);  // throws std::runtime_error
 };
 
+namespace cvyaml {
+class Writer;
+}
+using cvyaml_writer = cvyaml::Writer;
+
 class LocoMouse {
 protected:
     LocoMouse_Parameters LM_PARAMS;
@@ -117,7 +127,15 @@ protected:
     std::vector<std::vector<int32_t>> TRACKS_TAIL;  // per frame 3 x N_tail_points (x, y, z), -1 = missing
     std::vector<MyMat> UNARY_BOTTOM_PAW, UNARY_BOTTOM_SNOUT;            // class.hpp: same names
     std::vector<MATSPARSE> PAIRWISE_BOTTOM_PAW, PAIRWISE_BOTTOM_SNOUT;
-    std::string costs_file;
+    std::string costs_file, tracks_file;
+    // occlusion grids (class.hpp:238-246; filled by initializeFeatureLoop, class.cpp:726-759) and the tracker's results
+    std::vector<cv::Point_<double>> ONG;
+    cv::Size ONG_size;
+    cv::Point_<double> ONG_BR_corner;
+    std::vector<unsigned int> ONG_SIDE;
+    unsigned int ONG_SIDE_LOWEST_POINT = 0;
+    cv::Mat TRACK_INDEX_PAW_BOTTOM, TRACK_INDEX_SNOUT_BOTTOM, TRACK_INDEX_PAW_SIDE, TRACK_INDEX_SNOUT_SIDE;  // points x frames labels
+    std::vector<cv::Mat> EXPORTED;    // the matrices exportResults wrote, in file order (tests)
 
     // ---- device side ------------------------------------------------------------------------------
     lm_ctx *CTX = nullptr;
@@ -136,6 +154,13 @@ protected:
     void configureDevice();            // lm_configure + background + calibration for the current box sizes
     const Batch &batchFor(int frame) const;
     virtual bool usesImadjust() const { return false; }  // LocoMouse_TM::readFrame applies imadjust(0, 0.6)
+    // class.cpp:2221-2346, 2385-2482
+    cv::Mat bestSideViewMatch(const cv::Mat &T, const std::vector<std::vector<P22D>> &candidates_bottom_side_matched,
+                              const std::vector<unsigned int> &ONG_side, unsigned int lowest_point, unsigned int N_features);
+    void exportPointTracks(cvyaml_writer &out, const cv::Mat &T_bottom, const cv::Mat &T_side,
+                           const std::vector<std::vector<P22D>> &candidates_bottom_side_matched, const std::string &feature_name, unsigned int N_features);
+    void exportTracks();
+    void exportLineTracks(cvyaml_writer &out, const std::vector<std::vector<int32_t>> &Tracks, const std::string &track_name, int N_line_points);
 
 public:
     explicit LocoMouse(LocoMouse_ParseInputs INPUTS);
@@ -173,6 +198,14 @@ public:
     const std::vector<MyMat> &unaryBottomSnout() const { return UNARY_BOTTOM_SNOUT; }
     const std::vector<MATSPARSE> &pairwiseBottomPaw() const { return PAIRWISE_BOTTOM_PAW; }
     const std::vector<MATSPARSE> &pairwiseBottomSnout() const { return PAIRWISE_BOTTOM_SNOUT; }
+    const cv::Mat &trackIndexPawBottom() const { return TRACK_INDEX_PAW_BOTTOM; }
+    const cv::Mat &trackIndexSnoutBottom() const { return TRACK_INDEX_SNOUT_BOTTOM; }
+    const cv::Mat &trackIndexPawSide() const { return TRACK_INDEX_PAW_SIDE; }
+    const cv::Mat &trackIndexSnoutSide() const { return TRACK_INDEX_SNOUT_SIDE; }
+    // LocoMouse_class.cpp:2073-2150 (see lm_track::side_view_transitions)
+    static MATSPARSE pairwisePotential_SideView(const std::vector<unsigned int> &Zi, const std::vector<unsigned int> &Zip1, double grid_mapping,
+                                                double grid_spacing, const std::vector<unsigned int> &ONGi, unsigned int Nong,
+                                                double max_displacement_bottom, double alpha_vel_bottom, double pairwise_occluded_cost);
 };
 
 // LocoMouse_TM (LocoMouse_TM.hpp:45-47): imadjust in readFrame; box = bb_width x bb_height_side (side,

@@ -34,6 +34,20 @@ class MATSPARSE {
 
 public:
     MATSPARSE() = default;
+    // MATSPARSE(const MyMat*) (MyMat.cpp:141-178): column by column, entries equal to 0 are not stored
+    explicit MATSPARSE(const MyMat *M) : n_rows(M->Nrows()), n_cols(M->Ncols()) {
+        Jc.push_back(0);
+        for (int j = 0; j < n_cols; ++j) {
+            for (int i = 0; i < n_rows; ++i) {
+                const double v = M->get((unsigned int)i, (unsigned int)j);
+                if (v != 0) {
+                    Ir.push_back(i);
+                    Pr.push_back(v);
+                }
+            }
+            Jc.push_back((int)Ir.size());
+        }
+    }
     MATSPARSE(int rows, int cols, const int *jc, const int *ir, const double *pr)
         : Ir(ir, ir + jc[cols]), Jc(jc, jc + cols + 1), Pr(pr, pr + jc[cols]), n_rows(rows), n_cols(cols) {}
     const int *getIr() const { return Ir.data(); }

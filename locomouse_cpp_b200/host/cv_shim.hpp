@@ -9,6 +9,10 @@
 #include <opencv2/core.hpp>
 #else
 #include <ostream>
+#include <vector>
+#ifndef CV_32SC1
+#define CV_32SC1 4
+#endif
 namespace cv {
 template <typename T>
 struct Point_ {
@@ -32,6 +36,30 @@ struct Rect_ {
     Rect_(T x_, T y_, T w, T h) : x(x_), y(y_), width(w), height(h) {}
     Rect_ operator+(const Point_<T> &p) const { return Rect_(x + p.x, y + p.y, width, height); }
     T area() const { return width * height; }
+};
+// The only cv::Mat the host stages that follow detection exchange: 32-bit signed label / track matrices (match2nd's
+// result, TRACK_INDEX_*, the exported N_FRAMES x 3 tracks).  Owning, continuous, row-major.
+class Mat {
+    std::vector<int> v_;
+
+public:
+    int rows = 0, cols = 0;
+    Mat() = default;
+    Mat(int r, int c, int /*type: CV_32SC1*/, int fill = 0) : v_((size_t)(r > 0 ? r : 0) * (size_t)(c > 0 ? c : 0), fill), rows(r), cols(c) {}
+    static Mat zeros(int r, int c, int type) { return Mat(r, c, type, 0); }
+    static Mat ones(int r, int c, int type) { return Mat(r, c, type, 1); }
+    bool empty() const { return v_.empty(); }
+    bool isContinuous() const { return true; }
+    int type() const { return CV_32SC1; }
+    template <typename T>
+    T *ptr(int r = 0) { return reinterpret_cast<T *>(v_.data() + (size_t)r * cols); }
+    template <typename T>
+    const T *ptr(int r = 0) const { return reinterpret_cast<const T *>(v_.data() + (size_t)r * cols); }
+    template <typename T>
+    T &at(int r, int c) { return ptr<T>(r)[c]; }
+    template <typename T>
+    const T &at(int r, int c) const { return ptr<T>(r)[c]; }
+    void copyTo(Mat &dst) const { dst = *this; }
 };
 using Point = Point_<int>;
 using Size = Size_<int>;

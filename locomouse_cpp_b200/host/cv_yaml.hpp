@@ -10,6 +10,7 @@
 // OpenCV (cv2.FileStorage) are what tests/test_host_cpp.py feeds this reader.  Host-side I/O only.
 #pragma once
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <limits>
@@ -132,6 +133,50 @@ public:
         static const Matrix none;
         auto it = mats_.find(key);
         return it == mats_.end() ? none : it->second;
+    }
+};
+
+
+// Writer for the reference's output file (cv::FileStorage WRITE, LocoMouse_class.cpp:360, 2385-2482): top-level
+// 32-bit integer matrices as `name: !!opencv-matrix` nodes.  The flow sequence is wrapped exactly as OpenCV's YAML
+// emitter wraps it (an item moves to a new line, indented by 7, when the line would pass column 71), so files are
+// byte-identical to what cv2.FileStorage writes for the same matrices (tests/test_host_tracks.py).
+class Writer {
+    std::FILE *f_ = nullptr;  // C stdio: this header is also built into a dlopen()ed test library
+    bool ok_ = true;
+    void put(const std::string &t) { ok_ = ok_ && std::fwrite(t.data(), 1, t.size(), f_) == t.size(); }
+
+public:
+    explicit Writer(const std::string &name) : f_(std::fopen(name.c_str(), "wb")) {
+        if (!f_) throw std::runtime_error("Could not open the output file: " + name);
+        put("%YAML:1.0\n---\n");
+    }
+    Writer(const Writer &) = delete;
+    Writer &operator=(const Writer &) = delete;
+    ~Writer() {
+        if (f_) std::fclose(f_);
+    }
+    void write(const std::string &name, int rows, int cols, const int *data) {
+        put(name + ": !!opencv-matrix\n   rows: " + std::to_string(rows) + "\n   cols: " + std::to_string(cols) + "\n   dt: i\n");
+        std::string line = "   data: [";
+        bool first = true;
+        for (long i = 0; i < (long)rows * cols; ++i) {
+            const std::string item = std::to_string(data[i]);
+            if (!first) line += ',';
+            if (line.size() + item.size() > 71 && line.size() > 7) {
+                put(line + "\n");
+                line.assign(7, ' ');
+            } else {
+                line += ' ';
+            }
+            line += item;
+            first = false;
+        }
+        put(line + " ]\n");
+    }
+    bool good() {
+        ok_ = ok_ && std::fflush(f_) == 0;
+        return ok_;
     }
 };
 

@@ -104,6 +104,9 @@ public:
     MATSPARSE pairwisePotential(std::vector<Candidate> &Ci, std::vector<Candidate> &Cip1, cv::Point_<double> &grid_mapping,
                                 double grid_spacing, std::vector<cv::Point_<double> > &ONGi, cv::Size ONG_size,
                                 double max_displacement_bottom, double alpha_vel_bottom, double pairwise_occluded_cost);
+    MATSPARSE pairwisePotential_SideView(const std::vector<uint> &Zi, const std::vector<uint> &Zip1, double grid_mapping, double grid_spacing,
+                                         const std::vector<uint> &ONGi, const unsigned int Nong, const double max_displacement_bottom,
+                                         const double alpha_vel_bottom, const double pairwise_occluded_cost);
     std::ofstream DEBUG_TEXT;
     void imadjust(const cv::Mat &Iin, cv::Mat &Iout, double low_in, double high_in, double low_out, double high_out);
     std::vector<P22D> matchingWithVelocityConstraint(std::vector<Candidate> &Candidates_b, std::vector<Candidate> &Candidates_t,
@@ -136,6 +139,7 @@ public:
 #include "_ref/ref_tail_body.inc"     // detectTail, detectLineCandidates, selectLargestRegion (LocoMouse_class.cpp:2541-2767)
 #include "_ref/ref_cost_body.inc"     // unaryCostBox, pairwisePotential (LocoMouse_class.cpp:1909-2070)
 #include "_ref/ref_pair_body.inc"     // matchingWithVelocityConstraint, xDist, matchViews, checkVelCriterion (1023-1267)
+#include "_ref/ref_side_cost_body.inc" // pairwisePotential_SideView (LocoMouse_class.cpp:2073-2150)
 
 extern "C" {
 
@@ -378,6 +382,24 @@ int ref_pairwise_potential(const ref_cand *ci, int ni, const ref_cand *cip1, int
     std::vector<cv::Point_<double> > ONG((size_t)ong_w * ong_h);   // only its size is read (LocoMouse_class.cpp:1961)
     LocoMouse L;
     MATSPARSE S = L.pairwisePotential(A, B, gm, spacing, ONG, cv::Size(ong_w, ong_h), max_disp, alpha_vel, occluded_cost);
+    dims[0] = S.Nrows();
+    dims[1] = S.Ncols();
+    dims[2] = S.nz();
+    if (S.nz() > cap) return 1;
+    for (int c = 0; c <= S.Ncols(); ++c) jc[c] = S.getJc()[c];
+    for (int k = 0; k < S.nz(); ++k) {
+        ir[k] = S.getIr()[k];
+        pr[k] = S.getPr()[k];
+    }
+    return 0;
+}
+
+// pairwisePotential_SideView -> the MATSPARSE it returns (side-view tracker transitions of bestSideViewMatch)
+int ref_pairwise_potential_side(const unsigned int *zi, int ni, const unsigned int *zip1, int nip1, double grid_mapping, double spacing, int nong,
+                                double max_disp, double alpha_vel, double occluded_cost, int *jc, int *ir, double *pr, int cap, int *dims) {
+    std::vector<uint> A(zi, zi + ni), B(zip1, zip1 + nip1), ONG((size_t)nong);
+    LocoMouse L;
+    MATSPARSE S = L.pairwisePotential_SideView(A, B, grid_mapping, spacing, ONG, (unsigned int)nong, max_disp, alpha_vel, occluded_cost);
     dims[0] = S.Nrows();
     dims[1] = S.Ncols();
     dims[2] = S.nz();

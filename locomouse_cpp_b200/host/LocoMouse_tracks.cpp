@@ -4,6 +4,7 @@
 // north_star keeps the sequential track assignment on the host; what differs from the reference is only that the
 // tracker (match2nd.cpp here) is re-entrant, so the independent problems -- the paw permutations and the snout; the
 // side-view tracks of every feature -- are solved on several host threads at once.
+#include <iostream>
 #include <stdexcept>
 
 #include "LocoMouse_class.hpp"
@@ -25,6 +26,12 @@ MATSPARSE LocoMouse::pairwisePotential_SideView(const std::vector<unsigned int> 
 }
 
 void LocoMouse::computeBottomTracks() {
+    if (LM_PARAMS.PRIOR_PAW.empty() || LM_PARAMS.PRIOR_SNOUT.empty()) {
+        // The reference refuses to start without a location_prior (class.cpp:132-145); this mirror also serves callers
+        // that only want the per-frame detections (candidate files), so it says so and leaves the tracks empty.
+        std::cout << "location_prior is not set: the tracker's cost matrices were not built, tracks are not computed." << std::endl;
+        return;
+    }
     if (UNARY_BOTTOM_PAW.size() != N_FRAMES || UNARY_BOTTOM_SNOUT.size() != N_FRAMES || PAIRWISE_BOTTOM_PAW.size() + 1 != N_FRAMES)
         throw std::runtime_error(
             "computeBottomTracks(): the unary / pairwise costs of every frame are needed (set location_prior in the configuration and run "
@@ -69,6 +76,7 @@ void LocoMouse::computeBottomTracks() {
 }
 
 void LocoMouse::computeSideTracks() {
+    if (LM_PARAMS.PRIOR_PAW.empty() || LM_PARAMS.PRIOR_SNOUT.empty()) return;  // see computeBottomTracks
     if (TRACK_INDEX_PAW_BOTTOM.empty() || TRACK_INDEX_SNOUT_BOTTOM.empty()) throw std::runtime_error("computeSideTracks(): computeBottomTracks() must run first.");
     TRACK_INDEX_PAW_SIDE = bestSideViewMatch(TRACK_INDEX_PAW_BOTTOM, CANDIDATES_MATCHED_VIEWS_PAW, ONG_SIDE, ONG_SIDE_LOWEST_POINT, LM_PARAMS.N_paws);
     TRACK_INDEX_SNOUT_SIDE = bestSideViewMatch(TRACK_INDEX_SNOUT_BOTTOM, CANDIDATES_MATCHED_VIEWS_SNOUT, ONG_SIDE, ONG_SIDE_LOWEST_POINT, LM_PARAMS.N_snout);

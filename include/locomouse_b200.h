@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LM_ABI_VERSION 3  /* 2: lm_set_option, lm_get_info, lm_debug_nms, lm_bounding_box_tm_de, lm_moving_average; 3: lm_host_alloc / lm_host_free, lm_unary_costs / lm_pairwise_costs, options streams 1..4, screen_layout, screen_priority */
+#define LM_ABI_VERSION 4  /* 4: lm_bounding_box_base, lm_mouse_box_size; 2: lm_set_option, lm_get_info, lm_debug_nms, lm_bounding_box_tm_de, lm_moving_average; 3: lm_host_alloc / lm_host_free, lm_unary_costs / lm_pairwise_costs, options streams 1..4, screen_layout, screen_priority */
 
 /* feature / view indices used in every [2] / [3] array below */
 enum { LM_PAW = 0, LM_SNOUT = 1, LM_TAIL = 2 };
@@ -192,6 +192,34 @@ int lm_bounding_box_tm_de(lm_ctx *ctx, const uint8_t *frames, int frames_on_devi
                           const lm_bb_de_params *p, double *bb_x_raw, int32_t *lims);
 /* vecmovingaverage (LocoMouse_class.cpp:1559-1608): central moving average, partial windows copied, (uint32_t) casts */
 int lm_moving_average(const double *v, int64_t n, int32_t window, uint32_t *out);
+
+/* Pass 1 of the base class: LocoMouse::computeBoundingBox / computeMouseBox / largestBWAreaObject
+ * (LocoMouse_class.cpp:579-653, 921-997): per frame, the base-class readFrame; medianBlur(median_filter_size) of the
+ * zero-padded image; threshold(> 2.55 -> 1); the largest connected component of the side view and of the bottom view;
+ * column sums (Row_*) and row sums (Col_*) of those 0 / 255 images as CV_32S; firstLastOverT on each; and from the four
+ * (first, last) pairs the six per-frame numbers
+ *     box[f] = { bb_x, bb_y_bottom (+ BB_BOTTOM_VIEW.y), bb_y_side, bb_width, bb_height_bottom, bb_height_side }.
+ * The whole-video post-processing (computeMouseBoxSize, vecmovingaverage) is sequential host work: lm_mouse_box_size,
+ * lm_moving_average.
+ * sums_as_float = 1 is the reference: firstLastOverT reads its argument through a float pointer (LocoMouse_class.hpp:417)
+ * although these sums are 32-bit integers, so a sum s is compared as the float with s's bit pattern (a denormal): with
+ * min_pixel_visible >= 1 no entry ever qualifies and every limit is -1; with 0 every entry does.  sums_as_float = 0 compares
+ * the integer sums themselves (what the code evidently intends; LocoMouse_TM_DE reduces to CV_32F and is not affected). */
+typedef struct {
+    int32_t side_x, side_y, side_w, side_h;         /* BB_SIDE_VIEW   (calibration file view_boxes row 0)               */
+    int32_t bottom_x, bottom_y, bottom_w, bottom_h; /* BB_BOTTOM_VIEW (row 1)                                            */
+    int32_t median_filter_size;                     /* odd; LocoMouse_class.hpp:54: 11                                   */
+    int32_t min_pixel_visible;                      /* LocoMouse_class.hpp:55: 1                                         */
+    int32_t sums_as_float;                          /* 1: as the reference (see above), 0: integer sums                   */
+    int32_t reserved;
+} lm_bb_base_params;
+/* box: [n][6] doubles; lims (optional, may be NULL): [n][4][2] = (first, last) of Row_side, Row_bottom, Col_side, Col_bottom.
+ * Needs lm_configure (its conn_comp_connectivity is used), lm_set_background and lm_set_calibration. */
+int lm_bounding_box_base(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, int64_t n, const lm_bb_base_params *p,
+                         double *box, int32_t *lims);
+/* computeMouseBoxSize (LocoMouse_class.cpp:1481-1506) with medianvec / stdvec (1515-1556): size[3] = final width, bottom
+ * height, side height = min(median + 3 std, max) per series.  The three arrays are sorted in place, as the reference's are. */
+int lm_mouse_box_size(double *bb_w, double *bb_hb, double *bb_hs, int64_t n, int32_t size[3]);
 
 /* cost builders of the host tracker --------------------------------------------------------------- *
  * LocoMouse::computeUnaryCostsBottom / unaryCostBox (LocoMouse_class.cpp:873-894, 1909-1952) and

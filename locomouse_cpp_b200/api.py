@@ -26,7 +26,7 @@ _lib = None
 EXPORTS = ("lm_abi_version", "lm_create", "lm_destroy", "lm_last_error", "lm_configure", "lm_set_model",
            "lm_set_background", "lm_set_calibration", "lm_get_geometry", "lm_detect_batch", "lm_last_timing",
            "lm_debug_fetch", "lm_set_option", "lm_get_info", "lm_debug_nms", "lm_bounding_box_tm_de", "lm_moving_average",
-           "lm_host_alloc", "lm_host_free", "lm_unary_costs", "lm_pairwise_costs")
+           "lm_host_alloc", "lm_host_free", "lm_unary_costs", "lm_pairwise_costs", "lm_bounding_box_base", "lm_mouse_box_size")
 
 
 def _pinned_zeros(shape, dtype):
@@ -86,6 +86,18 @@ def load_library():
     L.lm_debug_nms.argtypes = [vp, i32, i32, vp, vp]
     L.lm_debug_fetch.restype = i64
     L.lm_debug_fetch.argtypes = [vp, i32, i64, vp, i64, vp]
+    L.lm_unary_costs.restype = C.c_int
+    L.lm_unary_costs.argtypes = [vp, C.POINTER(lm_results), i64, i32, i32, i32, vp, i32, vp]
+    L.lm_pairwise_costs.restype = C.c_int
+    L.lm_pairwise_costs.argtypes = [vp, C.POINTER(lm_results), i64, i32, vp, vp, vp, vp, vp, i64, vp]
+    L.lm_bounding_box_base.restype = C.c_int
+    L.lm_bounding_box_base.argtypes = [vp, vp, i32, i64, vp, vp, vp]
+    L.lm_mouse_box_size.restype = C.c_int
+    L.lm_mouse_box_size.argtypes = [vp, vp, vp, i64, vp]
+    L.lm_host_alloc.restype = C.c_int
+    L.lm_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.lm_host_free.restype = C.c_int
+    L.lm_host_free.argtypes = [vp]
     _lib = L
     return L
 
@@ -200,6 +212,25 @@ class Detector:
         if n:
             self._check(self._L.lm_moving_average(raw.ctypes.data, n, int(window), out.ctypes.data))
         return out, raw, lims
+
+    def bounding_box_base(self, frames, params=None):
+        """Pass 1 of the base class, per frame (LocoMouse::computeMouseBox after the base readFrame, LocoMouse_class.cpp:579-631,
+        921-997): (box float64[n, 6] = bb_x, bb_y_bottom, bb_y_side, width, height_bottom, height_side; lims int32[n, 4, 2])."""
+        from .types import bb_base_params
+
+        ptr, n, on_dev, keep = _frames_ptr(frames, self.cfg, self.device)
+        p = params if params is not None else bb_base_params(self.cfg)
+        box = np.zeros((n, 6), np.float64)
+        lims = np.zeros((n, 4, 2), np.int32)
+        self._check(self._L.lm_bounding_box_base(self._ctx, ptr, int(on_dev), n, C.addressof(p), box.ctypes.data, lims.ctypes.data))
+        return box, lims
+
+    def mouse_box_size(self, w, hb, hs):
+        """computeMouseBoxSize (LocoMouse_class.cpp:1481-1506) -> (width, bottom height, side height)."""
+        a, b, c = (np.array(v, np.float64, copy=True) for v in (w, hb, hs))
+        size = np.zeros(3, np.int32)
+        self._check(self._L.lm_mouse_box_size(a.ctypes.data, b.ctypes.data, c.ctypes.data, a.size, size.ctypes.data))
+        return tuple(int(v) for v in size)
 
     # ---- cost builders of the host tracker (SURVEY 8f-2) ----------------------------------------------------------------
     def unary_costs(self, res: Results, feat: int, bb_w: int, bb_h: int, priors):

@@ -8,13 +8,28 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "lm_internal.h"
 
 namespace {
-std::string g_create_error;
+std::string g_create_error;     // last lm_create failure (lm_last_error(NULL)); guarded by g_mutex
+std::mutex g_mutex;
+
+// Every entry point runs on its context's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
 }
 
 struct lm_ctx {
@@ -97,8 +112,10 @@ int fail(lm_ctx *c, int code, const char *fmt, ...) {
     va_end(ap);
     if (c)
         c->err = buf;
-    else
+    else {
+        std::lock_guard<std::mutex> lock(g_mutex);
         g_create_error = buf;
+    }
     return code;
 }
 
@@ -549,7 +566,13 @@ extern "C" {
 
 int lm_abi_version(void) { return LM_ABI_VERSION; }
 
-const char *lm_last_error(const lm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+const char *lm_last_error(const lm_ctx *ctx) {
+    if (ctx) return ctx->err.c_str();
+    static thread_local std::string copy;  // the global may be rewritten by a concurrent lm_create
+    std::lock_guard<std::mutex> lock(g_mutex);
+    copy = g_create_error;
+    return copy.c_str();
+}
 
 int lm_create(lm_ctx **out, int device) {
     lm_ctx *ctx = nullptr;
@@ -561,6 +584,7 @@ int lm_create(lm_ctx **out, int device) {
         return fail(nullptr, LM_ERR_RUNTIME, "no CUDA device: %s (this library has no CPU fallback)",
                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     if (device < 0 || device >= n) return fail(nullptr, LM_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+    DeviceGuard guard(device);
     e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail(nullptr, LM_ERR_RUNTIME, "cudaSetDevice: %s", cudaGetErrorString(e));
     cudaDeviceProp prop;
@@ -600,7 +624,7 @@ int lm_create(lm_ctx **out, int device) {
 
 int lm_destroy(lm_ctx *ctx) {
     if (!ctx) return LM_OK;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     cudaDeviceSynchronize();
     free_scratch(ctx);
     cudaFree(ctx->d_bkg);
@@ -638,7 +662,7 @@ int lm_configure(lm_ctx *ctx, const lm_config *cfg) {
         return fail(ctx, LM_ERR_INVALID, "capacities: 0 < cand_cap <= 1024, 0 < det_cap <= 8192, match_cap > 0");
     if ((int64_t)k.bb_w * std::max(k.bb_h_bottom, k.bb_h_side) >= (1 << 21))
         return fail(ctx, LM_ERR_INVALID, "box too large for the connected-component key packing");
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     cudaDeviceSynchronize();
     free_scratch(ctx);
     cudaFree(ctx->d_bkg);
@@ -648,6 +672,7 @@ int lm_configure(lm_ctx *ctx, const lm_config *cfg) {
     ctx->bkg_set = ctx->calib_set = false;
     ctx->cfg = k;
     ctx->configured = true;
+    if (ctx->model_set) make_geom(ctx);  // pads / canvas depend on the box sizes: a new configuration keeps the model
     return LM_OK;
 }
 
@@ -655,9 +680,10 @@ int lm_set_model(lm_ctx *ctx, const lm_template t[2][3]) {
     if (!ctx) return LM_ERR_INVALID;
     if (!ctx->configured) return fail(ctx, LM_ERR_STATE, "lm_set_model before lm_configure");
     if (!t) return fail(ctx, LM_ERR_INVALID, "null model");
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     cudaDeviceSynchronize();
     free_scratch(ctx);
+    ctx->model_set = false;  // a failure below must not leave a half-updated model in use
     for (int v = 0; v < 2; ++v)
         for (int f = 0; f < 3; ++f) {
             const lm_template &T = t[v][f];
@@ -681,7 +707,7 @@ int lm_set_background(lm_ctx *ctx, const uint8_t *bkg) {
     if (!ctx) return LM_ERR_INVALID;
     if (!ctx->configured) return fail(ctx, LM_ERR_STATE, "lm_set_background before lm_configure");
     if (!bkg) return fail(ctx, LM_ERR_INVALID, "null background");
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     const size_t n = (size_t)ctx->cfg.vid_rows * ctx->cfg.vid_cols;
     if (!ctx->d_bkg) CK(cudaMalloc((void **)&ctx->d_bkg, n));
     cudaDeviceSynchronize();
@@ -703,7 +729,7 @@ int lm_set_calibration(lm_ctx *ctx, const int32_t *map) {
         if (map[i] < 0 || map[i] >= lim)
             return fail(ctx, LM_ERR_RUNTIME, "Calibration mapping indices out of range (index %zu = %d, frame has %lld pixels)",
                         i, map[i], (long long)lim);
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     if (!ctx->d_calib) CK(cudaMalloc((void **)&ctx->d_calib, n * sizeof(int32_t)));
     cudaDeviceSynchronize();
     CK(cudaMemcpy(ctx->d_calib, map, n * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -734,6 +760,8 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
 int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, const uint8_t *prev_frame, int64_t n,
                     int64_t first_frame_index, const uint32_t *bb_x, const uint32_t *bb_y_side,
                     const uint32_t *bb_y_bottom, lm_results *out) {
+    if (!ctx) return LM_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
     const int rc = detect_batch_impl(ctx, frames, frames_on_device, prev_frame, n, first_frame_index, bb_x, bb_y_side, bb_y_bottom, out);
     if (ctx && rc != LM_OK && rc != LM_ERR_OVERFLOW) {
         // a failure in the middle of the pipeline must not leave copies / kernels of this call in flight: the caller's
@@ -764,14 +792,19 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
     if (out->n_frames < n || out->cand_cap != k.cand_cap || out->match_cap != k.match_cap ||
         out->n_tail_points != k.n_tail_points)
         return fail(ctx, LM_ERR_INVALID, "result buffers do not match the configuration");
+    if (!out->n_bottom || !out->n_side || !out->bottom || !out->side || !out->match_n || !out->match_y || !out->match_s || !out->tail || !out->flags)
+        return fail(ctx, LM_ERR_INVALID, "every array of lm_results must be allocated");
     for (int64_t f = 0; f < n; ++f)
         if (!roi_ok(ctx, bb_x[f], bb_y_side[f], bb_y_bottom[f]))
             return fail(ctx, LM_ERR_ROI, "frame %lld: bounding box (x=%u, y_side=%u, y_bottom=%u) leaves the padded image",
                         (long long)(first_frame_index + f), bb_x[f], bb_y_side[f], bb_y_bottom[f]);
     CK(cudaSetDevice(ctx->device));
     int rc = prepare(ctx);
-    if (rc) return rc;
-    if (!frames_on_device && (rc = ensure_stage(ctx))) return rc;
+    if (rc == LM_OK && !frames_on_device) rc = ensure_stage(ctx);
+    if (rc) {  // a half-built scratch set (device or pinned memory ran out) is released, not leaked
+        free_scratch(ctx);
+        return rc;
+    }
     if (ctx->fold_dirty) {  // per-video constants of k_prep / k_pair; every stream of the previous call has been drained
         if (lm_launch_fold_calib(ctx->d_calib, ctx->d_bkg, k.n_rows, k.n_cols, k.flip, ctx->d_calib_flip, ctx->d_bkg_warp, ctx->stream) < 0)
             return fail(ctx, LM_ERR_RUNTIME, "calibration fold launch failed");
@@ -960,7 +993,7 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
 int lm_set_option(lm_ctx *ctx, const char *name, int64_t value) {
     if (!ctx) return LM_ERR_INVALID;
     if (!name) return fail(ctx, LM_ERR_INVALID, "lm_set_option: null name");
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     if (!strcmp(name, "screen")) {
         if (value < 0 || value > 2) return fail(ctx, LM_ERR_INVALID, "option screen must be 0, 1 or 2");
         ctx->opt_screen = (int)value;
@@ -1039,6 +1072,21 @@ int lm_get_info(const lm_ctx *ctx, const char *name, double *value) {
     return LM_ERR_INVALID;
 }
 
+// ---- cost builders of the host tracker (SURVEY 8f-2): candidates up, cost matrices down -------------------------------
+namespace {
+struct DevBuf {  // scoped, stream-ordered device allocation (the driver's pool makes repeated calls cheap)
+    void *p = nullptr;
+    cudaStream_t st = nullptr;
+    explicit DevBuf(cudaStream_t s) : st(s) {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() {
+        if (p) cudaFreeAsync(p, st);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, std::max<size_t>(bytes, 256), st); }
+};
+}  // namespace
+
 int lm_bounding_box_tm_de(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, int64_t n, const lm_bb_de_params *p,
                           double *bb_x_raw, int32_t *lims) {
     if (!ctx) return LM_ERR_INVALID;
@@ -1054,7 +1102,7 @@ int lm_bounding_box_tm_de(lm_ctx *ctx, const uint8_t *frames, int frames_on_devi
                     p->side_h);
     if ((int64_t)p->side_w * p->side_h >= (1 << 24))
         return fail(ctx, LM_ERR_INVALID, "side view too large for the float histogram scan of imadjust_default");
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     const int64_t fsz = (int64_t)k.vid_rows * k.vid_cols;
     lm_ctx::BBScratch &S = ctx->bbs;
     const int cap = 1024;  // frames per chunk: large enough that launch gaps do not matter, small scratch (1.3 MB)
@@ -1116,6 +1164,111 @@ int lm_bounding_box_tm_de(lm_ctx *ctx, const uint8_t *frames, int frames_on_devi
     return rc;
 }
 
+// Pass 1 of the base class, per frame (LocoMouse_class.cpp:579-631, 921-997); see include/locomouse_b200.h.
+int lm_bounding_box_base(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, int64_t n, const lm_bb_base_params *p, double *box,
+                         int32_t *lims) {
+    if (!ctx) return LM_ERR_INVALID;
+    if (!ctx->configured || !ctx->bkg_set || !ctx->calib_set)
+        return fail(ctx, LM_ERR_STATE, "lm_bounding_box_base needs lm_configure, lm_set_background and lm_set_calibration first");
+    if (n < 0) return fail(ctx, LM_ERR_INVALID, "negative frame count");
+    if (n == 0) return LM_OK;
+    if (!frames || !p || !box) return fail(ctx, LM_ERR_INVALID, "null argument");
+    const lm_config &k = ctx->cfg;
+    auto inside = [&](int x, int y, int w, int h) { return x >= 0 && y >= 0 && w > 0 && h > 0 && x + w <= k.n_cols && y + h <= k.n_rows; };
+    if (!inside(p->side_x, p->side_y, p->side_w, p->side_h) || !inside(p->bottom_x, p->bottom_y, p->bottom_w, p->bottom_h))
+        return fail(ctx, LM_ERR_INVALID, "view boxes must lie inside the calibrated image");
+    if (p->median_filter_size < 1 || !(p->median_filter_size & 1) || p->median_filter_size > 31)
+        return fail(ctx, LM_ERR_INVALID, "median_filter_size must be odd and at most 31. Was %d.", p->median_filter_size);
+    if (p->min_pixel_visible < 0) return fail(ctx, LM_ERR_INVALID, "min_pixel_visible must be non-negative. Was %d.", p->min_pixel_visible);
+    if ((int64_t)p->side_w * p->side_h >= (1 << 21) || (int64_t)p->bottom_w * p->bottom_h >= (1 << 21) || p->side_w > 65535 || p->bottom_w > 65535)
+        return fail(ctx, LM_ERR_INVALID, "view too large for the connected-component key packing");
+    DeviceGuard guard(ctx->device);
+    const int64_t fsz = (int64_t)k.vid_rows * k.vid_cols;
+    const int cap = 256;  // frames per chunk: two bit images of the whole calibrated image per frame
+    cudaStream_t st = ctx->stream;
+    DevBuf d_minmax(st), d_lut(st), d_bits(st), d_major(st), d_cc(st), d_vmap(st), d_vmask(st), d_slow(st), d_lims(st), d_stage(st);
+    const size_t slow = lm_bbox_base_slow_ints(*p);
+    CK(d_minmax.alloc((size_t)(cap + 1) * 2 * sizeof(int32_t)));
+    CK(d_lut.alloc((size_t)(cap + 1) * 256));
+    CK(d_bits.alloc(lm_bbox_base_bits_bytes(k.n_rows, k.n_cols, cap)));
+    CK(d_major.alloc(lm_bbox_base_bits_bytes(k.n_rows, k.n_cols, cap)));
+    CK(d_cc.alloc((size_t)LM_BBOX_SLOW_SLOTS * 3 * slow * sizeof(int32_t)));
+    CK(d_vmap.alloc((size_t)LM_BBOX_SLOW_SLOTS * slow));
+    CK(d_vmask.alloc((size_t)LM_BBOX_SLOW_SLOTS * slow));
+    CK(d_slow.alloc((size_t)cap * 2 * sizeof(int)));
+    CK(d_lims.alloc((size_t)n * 8 * sizeof(int32_t)));
+    if (!frames_on_device) CK(d_stage.alloc((size_t)cap * fsz));
+    for (int64_t s0 = 0; s0 < n; s0 += cap) {
+        const int B = (int)std::min<int64_t>(cap, n - s0);
+        LmBatch b{};
+        b.B = B;
+        b.frame_bytes = fsz;
+        b.prev = nullptr;
+        b.bkg = ctx->d_bkg;
+        b.calib = ctx->d_calib;
+        b.n_rows = k.n_rows;
+        b.n_cols = k.n_cols;
+        b.vid_rows = k.vid_rows;
+        b.vid_cols = k.vid_cols;
+        b.flip = k.flip;
+        b.conn = k.conn;
+        b.imadjust = 0;  // LocoMouse::readFrame(I_center), class.cpp:622
+        b.minmax = (int32_t *)d_minmax.p;
+        b.lut = (uint8_t *)d_lut.p;
+        if (frames_on_device) {
+            b.frames = frames + s0 * fsz;
+        } else {
+            CK(cudaMemcpyAsync(d_stage.p, frames + s0 * fsz, (size_t)B * fsz, cudaMemcpyHostToDevice, st));
+            b.frames = (const uint8_t *)d_stage.p;
+        }
+        if (lm_launch_bbox_base(b, *p, (uint32_t *)d_bits.p, (uint32_t *)d_major.p, (int32_t *)d_cc.p, (uint8_t *)d_vmap.p, (uint8_t *)d_vmask.p,
+                                (int *)d_slow.p, (int32_t *)d_lims.p + s0 * 8, st) < 0)
+            return fail(ctx, LM_ERR_RUNTIME, "bounding-box launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    std::vector<int32_t> h_lims((size_t)n * 8);
+    CK(cudaMemcpyAsync(h_lims.data(), d_lims.p, h_lims.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int64_t f = 0; f < n; ++f) {  // computeMouseBox's last lines (class.cpp:981-993) + the caller's offset (628)
+        const int32_t *rs = &h_lims[(size_t)f * 8], *rb = rs + 2, *cs = rs + 4, *cb = rs + 6;
+        double *o = box + f * 6;
+        o[0] = rb[1] > rs[1] ? (double)rb[1] : (double)rs[1];
+        o[1] = (double)cb[1] + (double)p->bottom_y;
+        o[2] = (double)cs[1];
+        const unsigned int wt = (unsigned int)(rs[1] - rs[0]), wb = (unsigned int)(rb[1] - rb[0]);
+        o[3] = wt > wb ? (double)wt : (double)wb;
+        o[4] = (double)(cb[1] - cb[0]);
+        o[5] = (double)(cs[1] - cs[0]);
+    }
+    if (lims) memcpy(lims, h_lims.data(), h_lims.size() * sizeof(int32_t));
+    return LM_OK;
+}
+
+// computeMouseBoxSize (LocoMouse_class.cpp:1481-1506): per series min(median + 3 std, max).  medianvec sorts the series
+// and, for an odd count, returns the element below the middle; stdvec is the sample standard deviation (1515-1556).
+int lm_mouse_box_size(double *bb_w, double *bb_hb, double *bb_hs, int64_t n, int32_t size[3]) {
+    if (!bb_w || !bb_hb || !bb_hs || !size || n < 1) return LM_ERR_INVALID;
+    double *series[3] = {bb_w, bb_hb, bb_hs};
+    for (int q = 0; q < 3; ++q) {
+        double *v = series[q];
+        double med = v[0], sd = 0.0;
+        if (n > 1) {
+            std::sort(v, v + n);
+            const int64_t half = n / 2;
+            med = (n % 2 == 0) ? (v[half - 1] + v[half]) / 2 : v[half - 1];
+            double sum = 0.0;
+            for (int64_t i = 0; i < n; ++i) sum += v[i];
+            const double mean = sum / (double)n;
+            double sq = 0.0;
+            for (int64_t i = 0; i < n; ++i) sq += (v[i] - mean) * (v[i] - mean);
+            sd = std::sqrt(sq / (double)(n - 1));
+        }
+        const uint32_t m3 = (uint32_t)(int64_t)(med + 3 * sd);
+        const double last = v[n - 1];
+        size[q] = (int32_t)(uint32_t)(int64_t)((double)m3 < last ? (double)m3 : last);
+    }
+    return LM_OK;
+}
+
 // vecmovingaverage (LocoMouse_class.cpp:1559-1608).  (uint32_t)double of a negative value is undefined in C++; like
 // the reference built for x86-64 this converts through int64 and keeps the low 32 bits.
 int lm_moving_average(const double *v, int64_t n, int32_t window, uint32_t *out) {
@@ -1138,28 +1291,13 @@ int lm_moving_average(const double *v, int64_t n, int32_t window, uint32_t *out)
     return LM_OK;
 }
 
-// ---- cost builders of the host tracker (SURVEY 8f-2): candidates up, cost matrices down -------------------------------
-namespace {
-struct DevBuf {  // scoped, stream-ordered device allocation (the driver's pool makes repeated calls cheap)
-    void *p = nullptr;
-    cudaStream_t st = nullptr;
-    explicit DevBuf(cudaStream_t s) : st(s) {}
-    DevBuf(const DevBuf &) = delete;
-    DevBuf &operator=(const DevBuf &) = delete;
-    ~DevBuf() {
-        if (p) cudaFreeAsync(p, st);
-    }
-    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, std::max<size_t>(bytes, 256), st); }
-};
-}  // namespace
-
 int lm_unary_costs(lm_ctx *ctx, const lm_results *res, int64_t n, int32_t feat, int32_t bb_w, int32_t bb_h, const lm_location_prior *priors,
                    int32_t n_priors, double *out) {
     if (!ctx) return LM_ERR_INVALID;
     if (!res || !priors || !out || n < 0 || n > res->n_frames || feat < 0 || feat > 1 || bb_w < 1 || bb_h < 1 || n_priors < 1 || res->cand_cap < 1)
         return fail(ctx, LM_ERR_INVALID, "lm_unary_costs: bad argument");
     if (n == 0) return LM_OK;
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     const size_t cap = (size_t)res->cand_cap;
     cudaStream_t st = ctx->stream;
     DevBuf dc(st), dn(st), dp(st), dout(st);
@@ -1186,7 +1324,7 @@ int lm_pairwise_costs(lm_ctx *ctx, const lm_results *res, int64_t n, int32_t fea
     *total = 0;
     offs[0] = 0;
     if (n == 0) return LM_OK;
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     const size_t ccap = (size_t)res->cand_cap;
     const size_t jc_stride = ccap + (size_t)p->ong_w * p->ong_h + 1;
     cudaStream_t st = ctx->stream;
@@ -1222,9 +1360,12 @@ int lm_debug_nms(lm_ctx *ctx, int view, int feat, const float *scores, lm_cand *
     if (!ctx) return LM_ERR_INVALID;
     if (!ctx->configured || !ctx->model_set) return fail(ctx, LM_ERR_STATE, "lm_debug_nms needs lm_configure and lm_set_model first");
     if (view < 0 || view > 1 || feat < 0 || feat > 1 || !scores || !out) return fail(ctx, LM_ERR_INVALID, "lm_debug_nms: bad argument");
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     int rc = prepare(ctx);
-    if (rc) return rc;
+    if (rc) {
+        free_scratch(ctx);
+        return rc;
+    }
     LmBatch b = ctx->bt;
     b.B = 1;
     const lm_config &k = ctx->cfg;
@@ -1287,7 +1428,7 @@ int64_t lm_debug_fetch(lm_ctx *ctx, int what, int64_t frame, void *dst, int64_t 
     if (!ctx || !ctx->Bcap) return LM_ERR_STATE;
     const int64_t i = frame - ctx->last_s0;
     if (i < 0 || i >= ctx->last_B) return fail(ctx, LM_ERR_INVALID, "frame %lld is not in the last sub-batch", (long long)frame);
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     const LmBatch &b = ctx->last_slot ? ctx->bt_more[ctx->last_slot - 1] : ctx->bt;
     const void *src = nullptr;
     int64_t bytes = 0;

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <vector>
 
 #include "../../include/locomouse_b200.h"
@@ -143,6 +144,13 @@ int lm_launch_pair(const LmBatch &b, cudaStream_t s);
 int lm_launch_bbox_tm_de(const LmBatch &b, const lm_bb_de_params &p, uint32_t *hist, uint8_t *pred, double *bb_x, int32_t *lims,
                          cudaStream_t s);
 
+// pass 1 of the base class (k_bbox_base.cu)
+size_t lm_bbox_base_bits_bytes(int n_rows, int n_cols, int B);
+size_t lm_bbox_base_slow_ints(const lm_bb_base_params &p);
+constexpr int LM_BBOX_SLOW_SLOTS = 8;
+int lm_launch_bbox_base(const LmBatch &b, const lm_bb_base_params &p, uint32_t *bits, uint32_t *major, int32_t *cc, uint8_t *vmap, uint8_t *vmask,
+                        int *need_slow, int32_t *lims, cudaStream_t s);
+
 // cost builders (k_cost.cu); all pointers are device memory.  Pairwise: phase 0 = count + scan (fills jc, nnz, offs),
 // phase 1 = fill (ir, pr)
 int lm_launch_unary(const lm_cand *cand, const int32_t *ncand, int64_t n, int cand_cap, int feat, int bb_w, int bb_h,
@@ -181,14 +189,12 @@ size_t lm_corr_smem_bytes(const LmBatch &b, int view, int feat);
 
 // Per-device one-time state of the launchers (function attributes are per device; a process may own several contexts).
 struct LmDevOnce {
-    bool done[64] = {};
-    bool first(void) {  // true exactly once per current device
+    std::atomic<bool> done[64] = {};
+    bool first(void) {  // true exactly once per current device, also when several host threads launch at once
         int dev = 0;
         cudaGetDevice(&dev);
         dev &= 63;
-        if (done[dev]) return false;
-        done[dev] = true;
-        return true;
+        return !done[dev].exchange(true);
     }
 };
 inline int lm_sm_count() {

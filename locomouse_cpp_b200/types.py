@@ -72,6 +72,21 @@ def bb_de_params(cfg, side_h: int = 165, **kw) -> lm_bb_de_params:
     return lm_bb_de_params(**d)
 
 
+class lm_bb_base_params(C.Structure):
+    _fields_ = [("side_x", C.c_int32), ("side_y", C.c_int32), ("side_w", C.c_int32), ("side_h", C.c_int32),
+                ("bottom_x", C.c_int32), ("bottom_y", C.c_int32), ("bottom_w", C.c_int32), ("bottom_h", C.c_int32),
+                ("median_filter_size", C.c_int32), ("min_pixel_visible", C.c_int32), ("sums_as_float", C.c_int32), ("reserved", C.c_int32)]
+
+
+def bb_base_params(cfg, side_h: int = 165, **kw) -> lm_bb_base_params:
+    """Base-class pass-1 defaults (LocoMouse_class.hpp:54-55) for views that split the calibrated image at row `side_h`;
+    sums_as_float = 1 is the reference's behaviour (see include/locomouse_b200.h)."""
+    d = dict(side_x=0, side_y=0, side_w=cfg.n_cols, side_h=side_h, bottom_x=0, bottom_y=side_h, bottom_w=cfg.n_cols,
+             bottom_h=cfg.n_rows - side_h, median_filter_size=11, min_pixel_visible=1, sums_as_float=1, reserved=0)
+    d.update(kw)
+    return lm_bb_base_params(**d)
+
+
 class lm_location_prior(C.Structure):
     _fields_ = [("pos_x", C.c_double), ("pos_y", C.c_double), ("max_distance", C.c_double), ("area_x", C.c_double),
                 ("area_y", C.c_double), ("area_w", C.c_double), ("area_h", C.c_double)]

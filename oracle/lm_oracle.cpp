@@ -869,6 +869,107 @@ void bounding_box_tm_de_frame(const lm_config &c, const uint8_t *bkg, const int3
     *bb_x = std::min((double)(p.side_w - 1), (double)fl[1] * p.width_margin);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pass 1 of the base class — computeMouseBox (class.cpp:921-997) on the image the base readFrame produced.
+//  * medianBlur(I_median, I_median, k) runs on the image padded by k/2 zeros (class.cpp:584-601); the padding stays zero
+//    from frame to frame (a padding pixel's window holds at most k*(k-1)/2 image pixels, fewer than half), so the result
+//    inside the image is the median over a zero-extended k x k window.
+//  * threshold(I, I, 2.55, 1, THRESH_BINARY): 1 where the median is >= 3.
+//  * largestBWAreaObject on each view: largest component, ties -> lowest OpenCV label (as selectLargestRegion), 0 / 255.
+//  * reduce(SUM, CV_32S) along both axes, firstLastOverT<int>.  firstLastOverT reads through `const float *`
+//    (class.hpp:417): with sums_as_float the int32 bit patterns are compared as floats, exactly what the reference does.
+// ---------------------------------------------------------------------------------------------
+void first_last_i32(const int32_t *sums, uint32_t L, int th, bool as_float, int32_t *fl) {
+    std::vector<float> v(L);
+    for (uint32_t i = 0; i < L; ++i) {
+        if (as_float)
+            std::memcpy(&v[i], &sums[i], 4);
+        else
+            v[i] = (float)sums[i];
+    }
+    first_last_over_t(v.data(), L, th, fl);
+}
+
+void mouse_box_base(const uint8_t *I, int n_rows, int n_cols, int conn, const lm_bb_base_params &p, double *box, int32_t *lims) {
+    const int k = p.median_filter_size, h = k / 2, need = (k * k + 1) / 2;
+    // median >= 3  <=>  at least (k*k+1)/2 of the k*k window values (zeros outside the image) are >= 3
+    std::vector<uint8_t> bin((size_t)n_rows * n_cols);
+    std::vector<int32_t> integral((size_t)(n_rows + 1) * (n_cols + 1), 0);
+    for (int r = 0; r < n_rows; ++r)
+        for (int c = 0; c < n_cols; ++c)
+            integral[(size_t)(r + 1) * (n_cols + 1) + c + 1] = (I[(size_t)r * n_cols + c] >= 3) + integral[(size_t)r * (n_cols + 1) + c + 1] +
+                                                                integral[(size_t)(r + 1) * (n_cols + 1) + c] - integral[(size_t)r * (n_cols + 1) + c];
+    for (int r = 0; r < n_rows; ++r) {
+        const int r0 = std::max(0, r - h), r1 = std::min(n_rows, r + h + 1);
+        for (int c = 0; c < n_cols; ++c) {
+            const int c0 = std::max(0, c - h), c1 = std::min(n_cols, c + h + 1);
+            const int cnt = integral[(size_t)r1 * (n_cols + 1) + c1] - integral[(size_t)r0 * (n_cols + 1) + c1] -
+                            integral[(size_t)r1 * (n_cols + 1) + c0] + integral[(size_t)r0 * (n_cols + 1) + c0];
+            bin[(size_t)r * n_cols + c] = cnt >= need ? 1 : 0;
+        }
+    }
+    int32_t fl[4][2];
+    const int vx[2] = {p.side_x, p.bottom_x}, vy[2] = {p.side_y, p.bottom_y}, vw[2] = {p.side_w, p.bottom_w}, vh[2] = {p.side_h, p.bottom_h};
+    for (int v = 0; v < 2; ++v) {
+        std::vector<uint8_t> view((size_t)vw[v] * vh[v]), big(view.size());
+        for (int r = 0; r < vh[v]; ++r)
+            for (int c = 0; c < vw[v]; ++c) view[(size_t)r * vw[v] + c] = bin[(size_t)(vy[v] + r) * n_cols + vx[v] + c];
+        largest_region(view.data(), vh[v], vw[v], conn, big.data());
+        std::vector<int32_t> row(vw[v], 0), col(vh[v], 0);
+        for (int r = 0; r < vh[v]; ++r)
+            for (int c = 0; c < vw[v]; ++c) {
+                row[c] += big[(size_t)r * vw[v] + c];
+                col[r] += big[(size_t)r * vw[v] + c];
+            }
+        // firstLastOverT(Row_*, I.cols, ...) scans N_COLS entries of a vector that has view-width entries: identical when the
+        // view spans the image width (the reference's calibration files); a narrower view is scanned over its own width
+        first_last_i32(row.data(), (uint32_t)std::min(n_cols, vw[v]), p.min_pixel_visible, p.sums_as_float != 0, fl[v]);
+        first_last_i32(col.data(), (uint32_t)vh[v], p.min_pixel_visible, p.sums_as_float != 0, fl[2 + v]);
+    }
+    const int32_t *rs = fl[0], *rb = fl[1], *cs = fl[2], *cb = fl[3];
+    box[0] = rb[1] > rs[1] ? (double)rb[1] : (double)rs[1];
+    box[1] = (double)cb[1] + (double)p.bottom_y;  // class.cpp:628: made absolute by the caller
+    box[2] = (double)cs[1];
+    const unsigned int wt = (unsigned int)(rs[1] - rs[0]), wb = (unsigned int)(rb[1] - rb[0]);
+    box[3] = wt > wb ? (double)wt : (double)wb;
+    box[4] = (double)(cb[1] - cb[0]);
+    box[5] = (double)(cs[1] - cs[0]);
+    if (lims) std::memcpy(lims, fl, sizeof fl);
+}
+
+// medianvec / stdvec / computeMouseBoxSize (class.cpp:1481-1556).  medianvec sorts its argument; for an odd count it
+// returns the element BELOW the middle (v[N/2 - 1]), as written there.  stdvec runs on the sorted data.
+double medianvec(std::vector<double> &v) {
+    const int N = (int)v.size();
+    if (N == 1) return v[0];
+    std::sort(v.begin(), v.end());
+    const int half = N / 2;
+    return N % 2 == 0 ? (v[half - 1] + v[half]) / 2 : v[half - 1];
+}
+double stdvec(const std::vector<double> &v) {
+    const int N = (int)v.size();
+    if (N == 1) return 0.0;
+    double sum = 0.0;
+    for (double x : v) sum += x;               // std::accumulate, left to right
+    const double mean = sum / N;
+    double sq = 0.0;
+    for (double x : v) sq += (x - mean) * (x - mean);  // std::inner_product of the differences with themselves
+    return std::sqrt(sq / (N - 1));
+}
+void mouse_box_size(double *w, double *hb, double *hs, int64_t n, int32_t size[3]) {
+    double *series[3] = {w, hb, hs};
+    for (int q = 0; q < 3; ++q) {
+        std::vector<double> v(series[q], series[q] + n);
+        const double med = medianvec(v);
+        const double sd = stdvec(v);
+        const uint32_t m3 = u32_from_double(med + 3 * sd);
+        // `uint32_t final = (m3 < v[N-1]) ? m3 : v[N-1]`: the comparison and the conditional's value are double
+        const double last = v[(size_t)n - 1];
+        size[q] = (int32_t)u32_from_double((double)m3 < last ? (double)m3 : last);
+        std::copy(v.begin(), v.end(), series[q]);
+    }
+}
+
 int validate(const lm_config *c, const lm_template t[2][3]) {
     if (!c || !t) return LM_ERR_INVALID;
     if (c->vid_rows <= 0 || c->vid_cols <= 0 || c->n_rows <= 0 || c->n_cols <= 0) return LM_ERR_INVALID;
@@ -898,6 +999,31 @@ int lmo_bounding_box_tm_de(const lm_config *cfg, const uint8_t *bkg, const int32
         bounding_box_tm_de_frame(*cfg, bkg, calib, frames + f * fsz, *p, I, bb_x + f, lims ? lims + 2 * f : nullptr);
     return LM_OK;
 }
+static bool base_params_ok(const lm_bb_base_params *p, int n_rows, int n_cols) {
+    return p && p->median_filter_size >= 1 && (p->median_filter_size & 1) && p->median_filter_size <= 255 && p->min_pixel_visible >= 0 &&
+           p->side_x >= 0 && p->side_y >= 0 && p->side_w > 0 && p->side_h > 0 && p->side_x + p->side_w <= n_cols && p->side_y + p->side_h <= n_rows &&
+           p->bottom_x >= 0 && p->bottom_y >= 0 && p->bottom_w > 0 && p->bottom_h > 0 && p->bottom_x + p->bottom_w <= n_cols &&
+           p->bottom_y + p->bottom_h <= n_rows;
+}
+int lmo_mouse_box_base(const uint8_t *I, int32_t n_rows, int32_t n_cols, int32_t conn, const lm_bb_base_params *p, double *box, int32_t *lims) {
+    if (!I || !box || !base_params_ok(p, n_rows, n_cols) || (conn != 4 && conn != 8)) return LM_ERR_INVALID;
+    mouse_box_base(I, n_rows, n_cols, conn, *p, box, lims);
+    return LM_OK;
+}
+int lmo_bounding_box_base(const lm_config *cfg, const uint8_t *bkg, const int32_t *calib, const uint8_t *frames, int64_t n,
+                          const lm_bb_base_params *p, double *box, int32_t *lims) {
+    if (!cfg || !bkg || !calib || !frames || !box || n < 0 || !base_params_ok(p, cfg->n_rows, cfg->n_cols)) return LM_ERR_INVALID;
+    lm_config base = *cfg;
+    base.imadjust = 0;  // LocoMouse::readFrame(I_center), class.cpp:622
+    std::vector<uint8_t> I((size_t)cfg->n_rows * cfg->n_cols);
+    const int64_t fsz = (int64_t)cfg->vid_rows * cfg->vid_cols;
+    for (int64_t f = 0; f < n; ++f) {
+        preprocess(base, bkg, calib, frames + f * fsz, I.data(), nullptr);
+        mouse_box_base(I.data(), cfg->n_rows, cfg->n_cols, cfg->conn, *p, box + f * 6, lims ? lims + f * 8 : nullptr);
+    }
+    return LM_OK;
+}
+void lmo_mouse_box_size(double *w, double *hb, double *hs, int64_t n, int32_t size[3]) { mouse_box_size(w, hb, hs, n, size); }
 void lmo_imadjust_default_lut(const uint32_t *hist, uint8_t *lut, int32_t *imin_imax) { imadjust_default_lut(hist, lut, imin_imax); }
 void lmo_first_last_over_t(const float *values, uint32_t L, int32_t th, int32_t *first_last) { first_last_over_t(values, L, th, first_last); }
 void lmo_vecmovingaverage(const double *v, int64_t n, int32_t window, uint32_t *out) { vecmovingaverage(v, n, window, out); }

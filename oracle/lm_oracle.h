@@ -83,6 +83,13 @@ int lmo_bounding_box_tm_de(const lm_config *cfg, const uint8_t *bkg, const int32
 void lmo_imadjust_default_lut(const uint32_t *hist, uint8_t *lut, int32_t *imin_imax);
 /* firstLastOverT<int> (LocoMouse_class.hpp:411-442) on float column sums */
 void lmo_first_last_over_t(const float *values, uint32_t L, int32_t th, int32_t *first_last);
+/* ---- pass 1, base class: computeMouseBox (LocoMouse_class.cpp:921-997) after the base readFrame ---- */
+int lmo_bounding_box_base(const lm_config *cfg, const uint8_t *bkg, const int32_t *calib, const uint8_t *frames, int64_t n,
+                          const lm_bb_base_params *p, double *box, int32_t *lims);
+/* the same from an already pre-processed image I [n_rows][n_cols] (what the reference-compiled checker is fed) */
+int lmo_mouse_box_base(const uint8_t *I, int32_t n_rows, int32_t n_cols, int32_t conn, const lm_bb_base_params *p, double *box, int32_t *lims);
+/* computeMouseBoxSize + medianvec + stdvec (LocoMouse_class.cpp:1481-1556); sorts the inputs like the reference */
+void lmo_mouse_box_size(double *w, double *hb, double *hs, int64_t n, int32_t size[3]);
 /* ---- cost builders ----------------------------------------------------------------- */
 /* unaryCostBox (LocoMouse_class.cpp:1909-1952): out = MyMat(n x n_priors), column-major */
 void lmo_unary_cost_box(const lm_cand *c, int32_t n, int32_t bb_w, int32_t bb_h, const lm_location_prior *priors,

@@ -222,6 +222,46 @@ def bounding_box_tm_de(cfg: Config, bkg, calib, frames, params, window: int = 5)
     return out, raw, lims
 
 
+def bounding_box_base(cfg: Config, bkg, calib, frames, params):
+    """Per-frame output of LocoMouse::computeMouseBox after the base readFrame (LocoMouse_class.cpp:579-631, 921-997):
+    (box float64[n, 6], lims int32[n, 4, 2])."""
+    L = lib()
+    frames = _u8(frames)
+    n = frames.shape[0]
+    c = cfg.to_c()
+    box = np.zeros((n, 6), np.float64)
+    lims = np.zeros((n, 4, 2), np.int32)
+    L.lmo_bounding_box_base.restype = C.c_int
+    rc = L.lmo_bounding_box_base(C.byref(c), _p(_u8(bkg), _u8p), _p(np.ascontiguousarray(calib, np.int32), _i32p), _p(frames, _u8p),
+                                 C.c_int64(n), C.byref(params), box.ctypes.data_as(_f64p), lims.ctypes.data_as(_i32p))
+    if rc != 0:
+        raise ValueError(f"lmo_bounding_box_base failed ({rc})")
+    return box, lims
+
+
+def mouse_box_base(image, conn, params):
+    """computeMouseBox on an already pre-processed calibrated image -> (box float64[6], lims int32[4, 2])."""
+    L = lib()
+    I = _u8(image)
+    box = np.zeros(6, np.float64)
+    lims = np.zeros((4, 2), np.int32)
+    L.lmo_mouse_box_base.restype = C.c_int
+    rc = L.lmo_mouse_box_base(_p(I, _u8p), I.shape[0], I.shape[1], int(conn), C.byref(params), box.ctypes.data_as(_f64p), lims.ctypes.data_as(_i32p))
+    if rc != 0:
+        raise ValueError(f"lmo_mouse_box_base failed ({rc})")
+    return box, lims
+
+
+def mouse_box_size(w, hb, hs):
+    """computeMouseBoxSize (LocoMouse_class.cpp:1481-1506) -> (final_w, final_hb, final_hs)."""
+    L = lib()
+    a, b, c = (np.array(v, np.float64, copy=True) for v in (w, hb, hs))
+    size = np.zeros(3, np.int32)
+    L.lmo_mouse_box_size.restype = None
+    L.lmo_mouse_box_size(a.ctypes.data_as(_f64p), b.ctypes.data_as(_f64p), c.ctypes.data_as(_f64p), C.c_int64(a.size), size.ctypes.data_as(_i32p))
+    return tuple(int(v) for v in size)
+
+
 def imadjust_default_lut(hist):
     L = lib()
     h = np.ascontiguousarray(hist, np.uint32)

@@ -19,7 +19,12 @@ struct LocoMouse_Parameters_Stub {
     bool LM_DEBUG = false;
     unsigned int N_tail_points = 15;
     int conn_comp_connectivity = 8;
+    int median_filter_size = 11;   // LocoMouse_class.hpp:54-55
+    int min_pixel_visible = 1;
 };
+typedef LocoMouse_Parameters_Stub LocoMouse_Parameters;  // computeMouseBox takes `const LocoMouse_Parameters &`
+double medianvec(std::vector<double> &v, const int N);    // LocoMouse_class.hpp:356-358
+double stdvec(std::vector<double> &v, int N);
 class LocoMouse_Feature {  // sizes + velocity-matching boxes; boxes by the formula of LocoMouse_class.cpp:2954-2969
     cv::Size size_b, size_s;
     cv::Rect match_rect_b, match_rect_s;
@@ -104,6 +109,13 @@ public:
     MATSPARSE pairwisePotential(std::vector<Candidate> &Ci, std::vector<Candidate> &Cip1, cv::Point_<double> &grid_mapping,
                                 double grid_spacing, std::vector<cv::Point_<double> > &ONGi, cv::Size ONG_size,
                                 double max_displacement_bottom, double alpha_vel_bottom, double pairwise_occluded_cost);
+    // pass 1 of the base class (same member names)
+    cv::Mat I_PAD, I_PREV_PAD;
+    void largestBWAreaObject(cv::Mat &Iin, cv::Mat &Iout);
+    void computeMouseBox(cv::Mat &I_median, cv::Mat &I, cv::Mat &I_side_view, cv::Mat &I_bottom_view, double &bb_x, double &bb_y_bottom,
+                         double &bb_y_side, double &bb_width, double &bb_height_bottom, double &bb_height_side, const LocoMouse_Parameters &LM_PARAMS);
+    void computeMouseBoxSize(std::vector<double> &bb_w, std::vector<double> &bb_hb, std::vector<double> &bb_ht, cv::Rect &BB_side, cv::Rect &BB_bottom);
+    void storePreviousImage();
     MATSPARSE pairwisePotential_SideView(const std::vector<uint> &Zi, const std::vector<uint> &Zip1, double grid_mapping, double grid_spacing,
                                          const std::vector<uint> &ONGi, const unsigned int Nong, const double max_displacement_bottom,
                                          const double alpha_vel_bottom, const double pairwise_occluded_cost);
@@ -140,6 +152,8 @@ public:
 #include "_ref/ref_cost_body.inc"     // unaryCostBox, pairwisePotential (LocoMouse_class.cpp:1909-2070)
 #include "_ref/ref_pair_body.inc"     // matchingWithVelocityConstraint, xDist, matchViews, checkVelCriterion (1023-1267)
 #include "_ref/ref_side_cost_body.inc" // pairwisePotential_SideView (LocoMouse_class.cpp:2073-2150)
+#include "_ref/ref_box_base_body.inc"  // largestBWAreaObject, computeMouseBox (LocoMouse_class.cpp:921-997)
+#include "_ref/ref_box_size_body.inc"  // computeMouseBoxSize, storePreviousImage, medianvec, stdvec (LocoMouse_class.cpp:1481-1556)
 
 extern "C" {
 
@@ -410,6 +424,49 @@ int ref_pairwise_potential_side(const unsigned int *zi, int ni, const unsigned i
         pr[k] = S.getPr()[k];
     }
     return 0;
+}
+
+// computeMouseBox for a SEQUENCE of frames, set up as computeBoundingBox does (LocoMouse_class.cpp:579-631): one padded
+// I_median kept across the frames, readFrame's output (here: the injected calibrated images) written into its centre, the
+// two views bound to it; bb_y_bottom made absolute.  medianBlur and connectedComponentsWithStats run in the real OpenCV.
+int ref_compute_mouse_box(const unsigned char *images, int n, int n_rows, int n_cols, const int *side, const int *bottom, int median_size,
+                          int min_pixel_visible, int conn, cv::shim_median_fn med, cv::shim_cc_fn cc, double *box) {
+    try {
+        LocoMouse L;
+        L.LM_PARAMS.median_filter_size = median_size;
+        L.LM_PARAMS.min_pixel_visible = min_pixel_visible;
+        L.LM_PARAMS.conn_comp_connectivity = conn;
+        cv::shim_median_callback() = med;
+        cv::shim_cc_callback() = cc;
+        const int off = median_size / 2, pad = off * 2;
+        cv::Mat I_median = cv::Mat::zeros(n_rows + pad, n_cols + pad, CV_8UC1);
+        cv::Mat I_center = I_median(cv::Rect(off, off, n_cols, n_rows));
+        for (int f = 0; f < n; ++f) {
+            cv::Mat I_bottom_view = I_center(cv::Rect(bottom[0], bottom[1], bottom[2], bottom[3]));
+            cv::Mat I_side_view = I_center(cv::Rect(side[0], side[1], side[2], side[3]));
+            for (int r = 0; r < n_rows; ++r) std::memcpy(I_center.ptr<unsigned char>(r), images + ((size_t)f * n_rows + r) * n_cols, (size_t)n_cols);
+            double *o = box + (size_t)f * 6;
+            L.computeMouseBox(I_median, I_center, I_side_view, I_bottom_view, o[0], o[1], o[2], o[3], o[4], o[5], L.LM_PARAMS);
+            o[1] += bottom[1];
+        }
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+// computeMouseBoxSize: size = {BB_bottom.width, BB_bottom.height, BB_side.height}; the three series are sorted in place
+int ref_mouse_box_size(double *w, double *hb, double *hs, int n, int *size) {
+    std::vector<double> a(w, w + n), b(hb, hb + n), c(hs, hs + n);
+    cv::Rect side, bottom;
+    LocoMouse L;
+    L.computeMouseBoxSize(a, b, c, side, bottom);
+    size[0] = bottom.width;
+    size[1] = bottom.height;
+    size[2] = side.height;
+    std::copy(a.begin(), a.end(), w);
+    std::copy(b.begin(), b.end(), hb);
+    std::copy(c.begin(), c.end(), hs);
+    return side.width == bottom.width ? 0 : 1;
 }
 
 // The elementwise primitives of the shim that the pairing code calls, exposed so that tests/test_oracle_vs_cv2.py can pin

@@ -19,6 +19,7 @@
 #pragma once
 #include <cassert>
 #include <cmath>
+#include <cstring>
 #include <cstddef>
 #include <cstdint>
 #include <iostream>
@@ -278,7 +279,16 @@ inline void reduce(const Mat &src, Mat &dst, int dim, int rtype, int dtype = -1)
         dst = out;
         return;
     }
-    (void)dtype;
+    if (dtype == CV_32SC1) {  // 8-bit -> 32-bit signed sums (computeMouseBox, LocoMouse_class.cpp:964-968; pinned vs cv2.reduce)
+        Mat out(dim == 0 ? 1 : src.rows, dim == 0 ? src.cols : 1, CV_32S);
+        for (int r = 0; r < src.rows; ++r)
+            for (int c = 0; c < src.cols; ++c) {
+                if (dim == 0) out.ptr<int>(0)[c] += (int)src.ptr<uchar>(r)[c];
+                else out.ptr<int>(r)[0] += (int)src.ptr<uchar>(r)[c];
+            }
+        dst = out;
+        return;
+    }
     Mat out(dim == 0 ? 1 : src.rows, dim == 0 ? src.cols : 1, CV_32F);
     for (int r = 0; r < src.rows; ++r)
         for (int c = 0; c < src.cols; ++c) {
@@ -299,6 +309,9 @@ inline void subtract(const Mat &a, const Mat &b, Mat &dst, const NoArray &, int 
     dst = out;
 }
 inline double threshold(const Mat &src, Mat &dst, double thresh, double maxval, int type) {  // THRESH_BINARY / THRESH_BINARY_INV
+    // cv::threshold(I, I, ...) works in place: views of the same buffer (computeMouseBox's I_side_view / I_bottom_view) must
+    // see the result, so an output that already has the source's size and type is written through
+    const bool inplace = dst.data && dst.rows == src.rows && dst.cols == src.cols && dst.type() == src.type();
     Mat out(src.rows, src.cols, src.type());  // same depth as the source: 8-bit or 32-bit float
     const bool inv = type == THRESH_BINARY_INV;
     for (int r = 0; r < src.rows; ++r)
@@ -306,7 +319,12 @@ inline double threshold(const Mat &src, Mat &dst, double thresh, double maxval, 
             if (src.type() == CV_32F) out.ptr<float>(r)[c] = ((src.ptr<float>(r)[c] > (float)thresh) != inv) ? (float)maxval : 0.f;
             else out.ptr<uchar>(r)[c] = (((double)src.ptr<uchar>(r)[c] > thresh) != inv) ? (uchar)maxval : 0;
         }
-    dst = out;
+    if (inplace) {
+        for (int r = 0; r < src.rows; ++r)
+            std::memcpy(dst.ptr<uchar>(r), out.ptr<uchar>(r), (size_t)src.cols * src.elemSize());
+    } else {
+        dst = out;
+    }
     return thresh;
 }
 // ---- additions for the tail code (detectLineCandidates / selectLargestRegion, LocoMouse_class.cpp:2558-2767) -----------
@@ -370,7 +388,9 @@ inline int connectedComponentsWithStats(const Mat &img, Mat &labels, Mat &stats,
     std::vector<unsigned short> lab(flat.size());
     std::vector<int> areas(65536);
     const int n = shim_cc_callback()(flat.data(), img.rows, img.cols, connectivity, lab.data(), areas.data(), (int)areas.size());
-    Mat L(img.rows, img.cols, CV_16U), S(n > 0 ? n : 1, 5, CV_32S);
+    // one spare zero row: largestBWAreaObject reads stats row 1 before it knows that there is a foreground label
+    // (LocoMouse_class.cpp:932); in the real OpenCV that read is out of bounds and its value is never used
+    Mat L(img.rows, img.cols, CV_16U), S((n > 0 ? n : 1) + 1, 5, CV_32S);
     for (int r = 0; r < img.rows; ++r)
         for (int c = 0; c < img.cols; ++c) L.ptr<unsigned short>(r)[c] = lab[(size_t)r * img.cols + c];
     for (int i = 0; i < n; ++i) S.ptr<int>(i)[CC_STAT_AREA] = areas[i];
@@ -386,6 +406,18 @@ inline void filter2D(const Mat &src, Mat &dst, int /*CV_32F*/, const Mat &k, Poi
     for (int r = 0; r < src.rows; ++r)
         for (int c = 0; c < src.cols; ++c) out.ptr<float>(r)[c] = flat[(size_t)r * src.cols + c];
     dst = out;
+}
+
+// cv::medianBlur is an ALGORITHM: it runs in the REAL OpenCV through a callback (cv2.medianBlur), in place like the reference's call
+typedef void (*shim_median_fn)(const uchar *src, uchar *dst, int rows, int cols, int ksize);
+inline shim_median_fn &shim_median_callback() { static shim_median_fn f = nullptr; return f; }
+inline void medianBlur(const Mat &src, Mat &dst, int ksize) {
+    if (!shim_median_callback()) throw std::runtime_error("medianBlur: no callback installed");
+    std::vector<uchar> in((size_t)src.rows * src.cols), out(in.size());
+    for (int r = 0; r < src.rows; ++r) std::memcpy(&in[(size_t)r * src.cols], src.ptr<uchar>(r), (size_t)src.cols);
+    shim_median_callback()(in.data(), out.data(), src.rows, src.cols, ksize);
+    if (!(dst.data && dst.rows == src.rows && dst.cols == src.cols)) dst = Mat(src.rows, src.cols, CV_8U);
+    for (int r = 0; r < src.rows; ++r) std::memcpy(dst.ptr<uchar>(r), &out[(size_t)r * src.cols], (size_t)src.cols);
 }
 
 // ---- additions for readFrame / correctImage (LocoMouse_class.cpp:1273-1406) --------------------------------------------

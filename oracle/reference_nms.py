@@ -282,3 +282,51 @@ def mouse_box_de(side_view, threshold=255 * 0.05, min_count=10, margin=1.1):
     if rc != 0:
         raise RuntimeError("the reference's computeMouseBox_DE threw")
     return float(bbx.value)
+
+
+_MEDIAN_FN = C.CFUNCTYPE(None, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int)
+
+
+def compute_mouse_box(images, side, bottom, median_size=11, min_pixel_visible=1, conn=8):
+    """The reference's LocoMouse::computeMouseBox + largestBWAreaObject (LocoMouse_class.cpp:921-997) for a sequence of
+    calibrated images (what the base readFrame writes into I_center), set up as computeBoundingBox does (579-631): one
+    zero-padded I_median kept across frames.  cv::medianBlur and cv::connectedComponentsWithStats run in the REAL OpenCV
+    (cv2) through callbacks.  side / bottom = (x, y, w, h).  Returns box float64[n, 6]."""
+    import cv2
+
+    L = lib()
+    imgs = np.ascontiguousarray(images, np.uint8)
+    n, rows, cols = imgs.shape
+
+    def med(src, dst, r, c, k):
+        a = np.ctypeslib.as_array(src, shape=(r, c))
+        np.ctypeslib.as_array(dst, shape=(r, c))[:] = cv2.medianBlur(np.ascontiguousarray(a), k)
+
+    def cc(img, r, c, connectivity, labels, areas, cap):
+        a = np.ctypeslib.as_array(img, shape=(r, c))
+        k, lab, stats, _ = cv2.connectedComponentsWithStats(a, connectivity=connectivity, ltype=cv2.CV_16U)
+        assert k <= cap
+        np.ctypeslib.as_array(labels, shape=(r, c))[:] = lab
+        np.ctypeslib.as_array(areas, shape=(cap,))[:k] = stats[:, cv2.CC_STAT_AREA]
+        return int(k)
+
+    m_cb, c_cb = _MEDIAN_FN(med), _CC_FN(cc)
+    box = np.zeros((n, 6), np.float64)
+    sv = (C.c_int * 4)(*[int(v) for v in side])
+    bv = (C.c_int * 4)(*[int(v) for v in bottom])
+    L.ref_compute_mouse_box.restype = C.c_int
+    rc = L.ref_compute_mouse_box(C.c_void_p(imgs.ctypes.data), n, rows, cols, sv, bv, int(median_size), int(min_pixel_visible), int(conn),
+                                 m_cb, c_cb, C.c_void_p(box.ctypes.data))
+    if rc != 0:
+        raise RuntimeError("the reference's computeMouseBox threw")
+    return box
+
+
+def mouse_box_size(w, hb, hs):
+    """The reference's computeMouseBoxSize + medianvec + stdvec (LocoMouse_class.cpp:1481-1556) -> (width, bottom h, side h)."""
+    L = lib()
+    a, b, c = (np.array(v, np.float64, copy=True) for v in (w, hb, hs))
+    size = np.zeros(3, np.int32)
+    L.ref_mouse_box_size.restype = C.c_int
+    L.ref_mouse_box_size(C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data), C.c_void_p(c.ctypes.data), int(a.size), C.c_void_p(size.ctypes.data))
+    return tuple(int(v) for v in size)

@@ -29,7 +29,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     L = api.load_library()
     for name in _declared_functions():
         assert hasattr(L, name), name
-    assert L.lm_abi_version() == 3
+    assert L.lm_abi_version() == 4
 
 
 def test_struct_layouts_match_the_header():
@@ -42,6 +42,7 @@ def test_struct_layouts_match_the_header():
     assert types.CAND_DTYPE.itemsize == 16
     assert ctypes.sizeof(types.lm_location_prior) == 56 and ctypes.sizeof(types.lm_pairwise_params) == 56
     assert ctypes.sizeof(types.lm_bb_de_params) == 56
+    assert ctypes.sizeof(types.lm_bb_base_params) == 48
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -318,3 +318,59 @@ def test_results_in_lm_host_alloc_memory():
     finally:
         assert L.lm_host_free(p) == 0
     assert L.lm_host_free(None) == 0
+
+
+# ---- API robustness (round-1 advisor findings) -------------------------------------------------------------------------
+def test_large_candidate_capacity_runs_the_pairing_kernel(oracle):
+    """cand_cap = 512 makes k_pair's per-warp arrays exceed the default 48 kB of dynamic shared memory: the launcher opts in."""
+    spec = synth.SynthSpec(cand_cap=512, match_cap=2048)
+    got, ref, det, _ = _both(oracle, spec, 3, seed=1000)
+    assert diff_results(got, ref) == []
+    assert int(ref.match_n.sum()) > 0
+
+
+def test_reconfigure_keeps_model_and_rederives_geometry(oracle):
+    """lm_configure with a new box size after lm_set_model: pads / canvas (lm_get_geometry) and the ROI check follow the new
+    configuration, and detection with the re-sent static inputs equals the oracle."""
+    import ctypes as C
+
+    spec_a, spec_b = synth.SynthSpec(method="TM"), synth.SynthSpec(method="TM_DE")
+    cfg_a, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(spec_a, 3, seed=1000)
+    cfg_b, model_b, bkg_b, calib_b, frames_b, bx_b, bs_b, bb_b = synth.make_problem(spec_b, 3, seed=1000)
+    det = _detector(cfg_a, model, bkg, calib)
+    canvas = (C.c_int32 * 4)()
+    pads = (C.c_int32 * 8)()
+    assert det._L.lm_get_geometry(det._ctx, pads, canvas) == 0
+    assert canvas[1] == max(cfg_a.bb_h_side, 15)
+    c = cfg_b.to_c()
+    det._check(det._L.lm_configure(det._ctx, C.byref(c)))          # model kept, geometry re-derived
+    assert det._L.lm_get_geometry(det._ctx, pads, canvas) == 0
+    assert canvas[1] == max(cfg_b.bb_h_side, 15) and cfg_a.bb_h_side != cfg_b.bb_h_side
+    det.cfg = cfg_b
+    det.set_model(model_b)
+    det.set_background(bkg_b)
+    det.set_calibration(calib_b)
+    got = det.detect_batch(frames_b.numpy(), bx_b, bs_b, bb_b)
+    ref = oracle.detect(cfg_b, model_b, bkg_b, calib_b, frames_b.numpy(), bx_b, bs_b, bb_b, n_threads=4)
+    assert diff_results(got, ref) == []
+
+
+def test_null_result_array_is_an_argument_error_and_device_is_restored():
+    import ctypes as C
+
+    import torch
+
+    cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(synth.SynthSpec(), 2, seed=1000)
+    det = _detector(cfg, model, bkg, calib)
+    res = Results(2, cfg.cand_cap, cfg.match_cap, cfg.n_tail_points)
+    r = res.to_c()
+    r.match_s = None
+    fr = np.ascontiguousarray(frames.numpy())
+    bx, bs, bb = (np.ascontiguousarray(a, np.uint32) for a in (bx, bs, bb))
+    rc = det._L.lm_detect_batch(det._ctx, fr.ctypes.data, 0, None, 2, 0, bx.ctypes.data, bs.ctypes.data, bb.ctypes.data, C.byref(r))
+    assert rc == -1 and b"lm_results" in det._L.lm_last_error(det._ctx)
+    if torch.cuda.device_count() > 1:   # the library runs on its own device and leaves the caller's current device alone
+        torch.cuda.set_device(1)
+        det.detect_batch(fr, bx, bs, bb)
+        assert torch.cuda.current_device() == 1
+        torch.cuda.set_device(0)

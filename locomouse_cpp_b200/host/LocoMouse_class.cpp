@@ -13,6 +13,7 @@
 
 #include "cv_yaml.hpp"
 #include "lm_files.hpp"
+#include "lm_media.hpp"
 
 // =====================================================================================================
 // LocoMouse_ParseInputs (LocoMouse_ParseInputs.cpp:56-100)
@@ -96,6 +97,9 @@ LocoMouse_Parameters::LocoMouse_Parameters(const std::string &config_file_name) 
         try {
             if (key == "conn_comp_connectivity") conn_comp_connectivity = std::stoi(val);
             else if (key == "side_bottom_min_overlap") side_bottom_min_overlap = std::stod(val);
+            else if (key == "median_filter_size") median_filter_size = std::stoi(val);
+            else if (key == "min_pixel_visible") min_pixel_visible = std::stoi(val);
+            else if (key == "pass1_integer_sums") pass1_integer_sums = std::stoi(val);
             else if (key == "tail_sub_bounding_box") tail_sub_bounding_box = std::stod(val);
             else if (key == "use_provided_bounding_box") use_provided_bb = std::stoi(val);
             else if (key == "bounding_box_side") BB_USER_SIDE = parse_rect(val, key);
@@ -151,6 +155,8 @@ LocoMouse_Parameters::LocoMouse_Parameters(const std::string &config_file_name) 
         throw std::invalid_argument("side_bottom_min_overlap must belong to [0, 1].");
     if (!(tail_sub_bounding_box >= 0 && tail_sub_bounding_box <= 1))
         throw std::invalid_argument("tail_sub_bounding_box must belong to [0, 1].");
+    if (median_filter_size % 2 == 0) throw std::invalid_argument("median_filter_size must be odd. Was " + std::to_string(median_filter_size) + ".");
+    if (min_pixel_visible < 0) throw std::invalid_argument("min_pixel_visible must be non-negative. Was " + std::to_string(min_pixel_visible) + ".");
     if (bb_width <= 0 || bb_height_side <= 0) throw std::invalid_argument("bb_width and bb_height_side must be positive.");
     if (batch_frames <= 0) throw std::invalid_argument("batch_frames must be positive.");
     if (max_displacement_side < 0) throw std::invalid_argument("max_displacement_side must be non-negative. Was " + std::to_string(max_displacement_side) + ".");
@@ -276,6 +282,14 @@ void LocoMouse::initializePaths(const LocoMouse_ParseInputs &INPUT) {
 }
 
 void LocoMouse::loadVideo() {
+    if (lmmedia::is_avi(VIDEO_FILE)) {  // the reference's input: VideoCapture + extractChannel(0) (class.cpp:367-400, 1282-1293)
+        lmmedia::Video V = lmmedia::read_avi(VIDEO_FILE);
+        N_FRAMES = (unsigned int)V.n;
+        VID_ROWS = V.rows;
+        VID_COLS = V.cols;
+        VIDEO = std::move(V.frames);
+        return;
+    }
     lmfile::Reader r(VIDEO_FILE, "LMV1");
     const int n = r.i32();
     VID_ROWS = r.i32();
@@ -287,6 +301,12 @@ void LocoMouse::loadVideo() {
 }
 
 void LocoMouse::loadBackground() {
+    if (lmmedia::is_png(BKG_FILE)) {  // imread(BKG_FILE, CV_LOAD_IMAGE_GRAYSCALE) (class.cpp:402-417)
+        lmmedia::Image I = lmmedia::read_png_gray(BKG_FILE);
+        if (I.rows != VID_ROWS || I.cols != VID_COLS) throw std::runtime_error("Background image and video frames must have the same size.");
+        BKG = std::move(I.px);
+        return;
+    }
     lmfile::Reader r(BKG_FILE, "LMI1");
     const int rows = r.i32(), cols = r.i32();
     if (rows <= 0 || cols <= 0) throw std::runtime_error("Background image is empty: " + BKG_FILE);
@@ -401,14 +421,62 @@ void LocoMouse::getBoundingBox() {
     }
 }
 
-// Base method: positions and (via bounding_box_side / bounding_box_bottom widths and heights) sizes are
-// pass-1 outputs (LocoMouse_class.cpp:578-653 computes them from the whole video).
+// LocoMouse::computeBoundingBox (LocoMouse_class.cpp:578-653).  Per frame computeMouseBox runs on the device
+// (lm_bounding_box_base: median, threshold, largest component of each view, sums, first / last); computeMouseBoxSize and the
+// three moving averages follow on the host as in the reference.  A pass-1 output file (bounding_box_file) replaces it.
 void LocoMouse::computeBoundingBox() {
-    read_boxes(LM_PARAMS.bounding_box_file, N_FRAMES, BB_X_POS, BB_Y_SIDE_POS, BB_Y_BOTTOM_POS);
-    if (LM_PARAMS.BB_USER_BOTTOM.width <= 0 || LM_PARAMS.BB_USER_SIDE.width <= 0)
-        throw std::invalid_argument("bounding_box_side / bounding_box_bottom must give the box sizes for the default method.");
-    BB_BOTTOM_MOUSE = cv::Rect(0, 0, LM_PARAMS.BB_USER_BOTTOM.width, LM_PARAMS.BB_USER_BOTTOM.height);
-    BB_SIDE_MOUSE = cv::Rect(0, 0, LM_PARAMS.BB_USER_SIDE.width, LM_PARAMS.BB_USER_SIDE.height);
+    if (!LM_PARAMS.bounding_box_file.empty()) {
+        read_boxes(LM_PARAMS.bounding_box_file, N_FRAMES, BB_X_POS, BB_Y_SIDE_POS, BB_Y_BOTTOM_POS);
+        if (LM_PARAMS.BB_USER_BOTTOM.width <= 0 || LM_PARAMS.BB_USER_SIDE.width <= 0)
+            throw std::invalid_argument("bounding_box_side / bounding_box_bottom must give the box sizes when bounding_box_file is used.");
+        BB_BOTTOM_MOUSE = cv::Rect(0, 0, LM_PARAMS.BB_USER_BOTTOM.width, LM_PARAMS.BB_USER_BOTTOM.height);
+        BB_SIDE_MOUSE = cv::Rect(0, 0, LM_PARAMS.BB_USER_SIDE.width, LM_PARAMS.BB_USER_SIDE.height);
+        return;
+    }
+    // lm_configure needs positive box sizes; pass 1 does not use them
+    BB_BOTTOM_MOUSE = cv::Rect(0, 0, 1, 1);
+    BB_SIDE_MOUSE = cv::Rect(0, 0, 1, 1);
+    configureDevice();
+    lm_bb_base_params p{};
+    p.side_x = BB_SIDE_VIEW.x;
+    p.side_y = BB_SIDE_VIEW.y;
+    p.side_w = BB_SIDE_VIEW.width;
+    p.side_h = BB_SIDE_VIEW.height;
+    p.bottom_x = BB_BOTTOM_VIEW.x;
+    p.bottom_y = BB_BOTTOM_VIEW.y;
+    p.bottom_w = BB_BOTTOM_VIEW.width;
+    p.bottom_h = BB_BOTTOM_VIEW.height;
+    p.median_filter_size = LM_PARAMS.median_filter_size;
+    p.min_pixel_visible = LM_PARAMS.min_pixel_visible;
+    p.sums_as_float = LM_PARAMS.pass1_integer_sums ? 0 : 1;
+    std::vector<double> box((size_t)N_FRAMES * 6);
+    check(lm_bounding_box_base(CTX, VIDEO.data(), /*frames_on_device=*/0, N_FRAMES, &p, box.data(), nullptr));
+    std::vector<double> bb_x(N_FRAMES), bb_yb(N_FRAMES), bb_ys(N_FRAMES), w(N_FRAMES), hb(N_FRAMES), hs(N_FRAMES);
+    for (unsigned int f = 0; f < N_FRAMES; ++f) {
+        const double *o = &box[(size_t)f * 6];
+        bb_x[f] = o[0];
+        bb_yb[f] = o[1];
+        bb_ys[f] = o[2];
+        w[f] = o[3];
+        hb[f] = o[4];
+        hs[f] = o[5];
+    }
+    int32_t size[3];
+    if (lm_mouse_box_size(w.data(), hb.data(), hs.data(), N_FRAMES, size) != LM_OK) throw std::runtime_error("computeMouseBoxSize failed.");
+    BB_SIDE_MOUSE = cv::Rect(0, 0, size[0], size[2]);
+    BB_BOTTOM_MOUSE = cv::Rect(0, 0, size[0], size[1]);
+    BB_X_POS.assign(N_FRAMES, 0);
+    BB_Y_BOTTOM_POS.assign(N_FRAMES, 0);
+    BB_Y_SIDE_POS.assign(N_FRAMES, 0);
+    const int win = LM_PARAMS.moving_average_window;
+    if (lm_moving_average(bb_x.data(), N_FRAMES, win, BB_X_POS.data()) != LM_OK || lm_moving_average(bb_yb.data(), N_FRAMES, win, BB_Y_BOTTOM_POS.data()) != LM_OK ||
+        lm_moving_average(bb_ys.data(), N_FRAMES, win, BB_Y_SIDE_POS.data()) != LM_OK)
+        throw std::invalid_argument("moving_average_window is invalid.");
+    if (size[0] <= 0 || size[1] <= 0 || size[2] <= 0)
+        // With the reference's own settings this is what its pass 1 yields: firstLastOverT reads the integer sums as floats
+        // (LocoMouse_class.hpp:417), every limit is -1 and the box collapses; the reference then fails inside OpenCV.
+        throw std::runtime_error("computeBoundingBox(): the mouse box is empty (width " + std::to_string(size[0]) + ", heights " + std::to_string(size[1]) + " / " +
+                                 std::to_string(size[2]) + "); set pass1_integer_sums: 1, use_provided_bounding_box or bounding_box_file.");
 }
 
 LocoMouse_TM::LocoMouse_TM(LocoMouse_ParseInputs INPUTS) : LocoMouse(INPUTS) { METHOD = 1; }

@@ -48,6 +48,9 @@ public:
     int tracker_threads = 0;          // host threads for the independent match2nd problems (0: one per hardware thread)
     std::vector<LocoMouse_LocationPrior> PRIOR_PAW, PRIOR_SNOUT;  // config key location_prior (5 x 7); empty: cost builders are skipped
     int conn_comp_connectivity = 8;
+    int median_filter_size = 11;      // class.hpp:54-55: pass 1 of the base class
+    int min_pixel_visible = 1;
+    int pass1_integer_sums = 0;       // 0: firstLastOverT reads the CV_32S sums as floats, as the reference does; 1: as integers
     double side_bottom_min_overlap = 0.7;
     double tail_sub_bounding_box = 0.6;
     int use_provided_bb = 0;

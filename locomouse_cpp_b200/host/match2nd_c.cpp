@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "cv_yaml.hpp"
+#include "lm_media.hpp"
 #include "match2nd.hpp"
 
 namespace {
@@ -81,6 +82,33 @@ int lmh_yaml_write(const char *path, const char *names, int n, const int32_t *ro
         return w.good() ? 0 : 1;
     } catch (const std::exception &) {
         return 2;
+    }
+}
+// lm_media.hpp readers: dims = {n, rows, cols}; with out == NULL only the dimensions are returned.  0 ok, 1 error (msg filled)
+int lmh_read_avi(const char *path, int32_t *dims, uint8_t *out, char *msg, int msg_cap) {
+    try {
+        const lmmedia::Video V = lmmedia::read_avi(path);
+        dims[0] = V.n;
+        dims[1] = V.rows;
+        dims[2] = V.cols;
+        if (out) std::memcpy(out, V.frames.data(), V.frames.size());
+        return 0;
+    } catch (const std::exception &e) {
+        if (msg && msg_cap > 0) std::snprintf(msg, (size_t)msg_cap, "%s", e.what());
+        return 1;
+    }
+}
+int lmh_read_png(const char *path, int32_t *dims, uint8_t *out, char *msg, int msg_cap) {
+    try {
+        const lmmedia::Image I = lmmedia::read_png_gray(path);
+        dims[0] = 1;
+        dims[1] = I.rows;
+        dims[2] = I.cols;
+        if (out) std::memcpy(out, I.px.data(), I.px.size());
+        return 0;
+    } catch (const std::exception &e) {
+        if (msg && msg_cap > 0) std::snprintf(msg, (size_t)msg_cap, "%s", e.what());
+        return 1;
     }
 }
 // the same job `copies` times on `threads` host threads; returns 1 when every result equals the serial one

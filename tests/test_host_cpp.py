@@ -286,9 +286,11 @@ def test_opencv_yaml_reader_reads_what_opencv_writes(tmp_path):
 
 @pytest.mark.gpu
 def test_main_sequence_with_opencv_yaml_model_calibration_and_config(tmp_path, oracle):
-    """The class mirror driven with the reference's own file formats for the model (six f64 matrices + biases), the calibration
-    (ind_warp_mapping, view_boxes) and the configuration (location_prior as a 5 x 7 matrix node), all written by the real OpenCV:
+    """The class mirror driven with the reference's own file formats: the video as an AVI and the background as a PNG, both
+    written by the real OpenCV (cv2.VideoWriter / cv2.imwrite), the model (six f64 matrices + biases), the calibration
+    (ind_warp_mapping, view_boxes) and the configuration (location_prior as a 5 x 7 matrix node) written by cv2.FileStorage:
     detection results and cost matrices equal the oracle."""
+    cv2 = pytest.importorskip("cv2")
     from locomouse_cpp_b200 import synth
     from locomouse_cpp_b200.types import location_priors
 
@@ -314,7 +316,13 @@ def test_main_sequence_with_opencv_yaml_model_calibration_and_config(tmp_path, o
     _write_opencv_yaml(tmp_path / "prior.yml", [("location_prior", np.array(rows, np.float64))])
     node = (tmp_path / "prior.yml").read_text().split("---\n", 1)[1]
     (tmp_path / "config.yml").write_text((tmp_path / "config.yml").read_text() + node)
-    p = subprocess.run([exe, "1", str(tmp_path / "config.yml"), str(tmp_path / "video.lmv"), str(tmp_path / "bkg.lmi"),
+    vw = cv2.VideoWriter(str(tmp_path / "video.avi"), 0, 30.0, (cfg.vid_cols, cfg.vid_rows), False)  # uncompressed 8-bit grey
+    assert vw.isOpened()
+    for f in frames:
+        vw.write(f)
+    vw.release()
+    assert cv2.imwrite(str(tmp_path / "bkg.png"), bkg)
+    p = subprocess.run([exe, "1", str(tmp_path / "config.yml"), str(tmp_path / "video.avi"), str(tmp_path / "bkg.png"),
                         str(tmp_path / "model.yml"), str(tmp_path / "calibration.yml"), "R", str(tmp_path)], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
     out = read_output(tmp_path / "output_video.lmo")
@@ -325,9 +333,52 @@ def test_main_sequence_with_opencv_yaml_model_calibration_and_config(tmp_path, o
             cb, cs, matches = feats[feat]
             assert cb == ref.candidates_bottom(f, feat) and cs == ref.candidates_side(f, feat)
             assert [m for m in matches] == [w[1] for w in ref.p22d(f, feat)]
+    assert (tmp_path / "output_video.yml").exists()   # tracks: the reference's output file
     # the priors reached the cost builders: first frame's paw unary matrix
     buf = (tmp_path / "costs_video.lmo").read_bytes()
     nr, nc = struct.unpack_from("<ii", buf, 8)
     U = np.frombuffer(buf, np.float64, nr * nc, 16).reshape(nc, nr).T
     want = oracle.unary_cost_box(ref.candidates_bottom(0, 0), cfg.bb_w, cfg.bb_h_bottom, location_priors(rows[:4]))
     assert np.array_equal(np.ascontiguousarray(U).view(np.uint64), want.view(np.uint64))
+
+
+@pytest.mark.gpu
+def test_base_class_pass1_on_device_then_detection(tmp_path, oracle):
+    """Method 0 with no pass-1 file: LocoMouse::computeBoundingBox runs computeMouseBox on the device (lm_bounding_box_base),
+    computeMouseBoxSize and the moving averages on the host; detection then uses those boxes.  With the reference's own
+    reading of the integer sums the box is empty (and the driver says so); with pass1_integer_sums everything equals the
+    oracle's pass 1 + detection."""
+    import copy
+
+    from locomouse_cpp_b200 import synth
+    from locomouse_cpp_b200.types import bb_base_params
+
+    exe = _build_driver()
+    spec = synth.SynthSpec(method="base")
+    n = 9
+    cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(spec, n, seed=1000)
+    frames = frames.numpy()
+    args = lambda d: [exe, "0", str(d / "config.yml"), str(d / "video.lmv"), str(d / "bkg.lmi"), str(d / "model.lmm"), str(d / "calib.lmc"), "R", str(d)]
+    write_problem_files(tmp_path, cfg, model, bkg, calib, frames, bx, bs, bb, spec.side_h, extra_cfg="batch_frames: 4\n", with_boxes=False)
+    p = subprocess.run(args(tmp_path), capture_output=True, text=True)
+    assert p.returncode == 1 and "the mouse box is empty" in p.stdout, p.stdout
+    d2 = tmp_path / "int"
+    d2.mkdir()
+    write_problem_files(d2, cfg, model, bkg, calib, frames, bx, bs, bb, spec.side_h, extra_cfg="batch_frames: 4\npass1_integer_sums: 1\n", with_boxes=False)
+    p = subprocess.run(args(d2), capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    box, _ = oracle.bounding_box_base(cfg, bkg, calib, frames, bb_base_params(cfg, side_h=spec.side_h, sums_as_float=0))
+    w, hb, hs = oracle.mouse_box_size(box[:, 3], box[:, 4], box[:, 5])
+    c2 = copy.copy(cfg)
+    c2.bb_w, c2.bb_h_bottom, c2.bb_h_side = w, hb, hs   # tail_w follows (property)
+    wx, wyb, wys = (oracle.vecmovingaverage(box[:, k], 5) for k in (0, 1, 2))
+    ref = oracle.detect(c2, model, bkg, calib, frames, wx, wys, wyb, n_threads=4)
+    assert ref.rc == 0
+    out = read_output(d2 / "output_video.lmo")
+    assert len(out) == n
+    for f, (tail, feats) in enumerate(out):
+        assert np.array_equal(tail, ref.tail[f])
+        for feat in range(2):
+            cb, cs, matches = feats[feat]
+            assert cb == ref.candidates_bottom(f, feat) and cs == ref.candidates_side(f, feat)
+            assert matches == [m[1] for m in ref.p22d(f, feat)]

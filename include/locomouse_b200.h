@@ -164,7 +164,8 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device,
  *             measured neutral: the pipeline is bound by aggregate SM work, not by kernel ordering).
  * lm_get_info: "screen_active" (2/1/0 after the first lm_detect_batch, -1 before), "subbatch", "ms_screen"
  *             (device ms of the tensor-core kernel alone in the last call; ms[2] of lm_last_timing = screen + exact pass),
- *             "screen_eps_<view><feat>" / "screen_scale_<view><feat>" (error bound / weight quantum). */
+ *             "screen_eps_<view><feat>" / "screen_scale_<view><feat>" (error bound / weight quantum), "screen_macs" (int8
+ *             multiply-accumulates the last CTA-pair screen launch issued: executed work, beside the algorithmic count). */
 int lm_set_option(lm_ctx *ctx, const char *name, int64_t value);
 int lm_get_info(const lm_ctx *ctx, const char *name, double *value);
 

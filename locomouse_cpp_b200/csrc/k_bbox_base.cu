@@ -304,16 +304,20 @@ int lm_launch_bbox_base(const LmBatch &b, const lm_bb_base_params &p, uint32_t *
     int dev_smem = 0, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    // dynamic shared memory each kernel may ask for = the opt-in limit minus its own static shared memory
+    cudaFuncAttributes fa_cc{}, fa_slow{};
+    if (cudaFuncGetAttributes(&fa_cc, k_bbb_cc) != cudaSuccess || cudaFuncGetAttributes(&fa_slow, k_bbb_cc_slow) != cudaSuccess) return -1;
+    const int dyn_cc = dev_smem - (int)fa_cc.sharedSizeBytes, dyn_slow = dev_smem - (int)fa_slow.sharedSizeBytes;
     // the largest run capacity (<= RUNCAP, 16-bit run ids) that fits beside the larger view's bit images
     const int rmax = std::max(p.side_h, p.bottom_h), cmax = std::max(p.side_w, p.bottom_w);
     int runcap = RUNCAP;
-    while (runcap > 0 && bbb_cc_smem(rmax, cmax, runcap) > (size_t)dev_smem) runcap -= 256;
+    while (runcap > 0 && bbb_cc_smem(rmax, cmax, runcap) > (size_t)std::max(dyn_cc, 0)) runcap -= 256;
     if (const char *e = getenv("LM_BBOX_RUNCAP")) runcap = std::max(0, std::min(runcap, atoi(e)));
     P.runcap = std::max(runcap, 0);
     static LmDevOnce once;
     if (once.first()) {
-        cudaFuncSetAttribute(k_bbb_cc, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem);
-        cudaFuncSetAttribute(k_bbb_cc_slow, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem);
+        if (cudaFuncSetAttribute(k_bbb_cc, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_cc) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(k_bbb_cc_slow, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_slow) != cudaSuccess) return -1;
     }
     int gx = (nwords + 32 * 8 - 1) / (32 * 8);
     gx = gx < 1 ? 1 : (gx > 48 ? 48 : gx);
@@ -322,7 +326,7 @@ int lm_launch_bbox_base(const LmBatch &b, const lm_bb_base_params &p, uint32_t *
     gm = gm < 1 ? 1 : (gm > 1024 ? 1024 : gm);
     k_bbb_major<<<dim3(gm, b.B), 128, 0, s>>>(P);
     const size_t smem = bbb_cc_smem(rmax, cmax, P.runcap);
-    if (smem <= (size_t)dev_smem && P.runcap > 0) {
+    if (smem <= (size_t)std::max(dyn_cc, 0) && P.runcap > 0) {
         k_bbb_cc<<<dim3(b.B, 2), TAIL_THREADS, smem, s>>>(P);
     } else {  // views too large for the shared-memory labelling: everything takes the global-memory path
         int *ns = need_slow;
@@ -331,7 +335,7 @@ int lm_launch_bbox_base(const LmBatch &b, const lm_bb_base_params &p, uint32_t *
         if (cudaStreamSynchronize(s) != cudaSuccess) return -1;  // `ones` goes out of scope
     }
     const size_t slow_smem = (size_t)(2 * cmax + rmax) * sizeof(int);
-    if (slow_smem > (size_t)dev_smem) return -1;
+    if (slow_smem > (size_t)std::max(dyn_slow, 0)) return -1;
     k_bbb_cc_slow<<<BB_SLOW_SLOTS, SLOW_THREADS, slow_smem, s>>>(P);
     launches += 4;
     return cudaGetLastError() == cudaSuccess ? launches : -1;

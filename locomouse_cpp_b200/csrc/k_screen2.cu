@@ -25,6 +25,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <atomic>
 #include <climits>
 #include <cmath>
 
@@ -358,6 +359,11 @@ static bool encode_window_map(CUtensorMap *tm, const uint8_t *win, int pitch, in
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// int8 multiply-accumulates the last launch issued to the tensor cores (all instructions: M = 256 x N x K = 32 each), for
+// bench.py's executed-work figure beside the algorithmic one
+static std::atomic<long long> g_last_macs{0};
+long long lm_screen2_last_macs() { return g_last_macs.load(); }
+
 // Launches k_screen2 for the pair-level jobs; the caller has zeroed the task counters.
 int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s) {
     const int n_sm = lm_sm_count();
@@ -365,6 +371,7 @@ int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s) {
     Screen2Params P{};
     size_t smem = 0;
     double work[6], total = 0.0;
+    long long macs = 0;
     auto icost = [](int N) { return std::max(93.0, 42.0 + N / 2.0); };  // cycles per instruction (tools/umma_sw_probe.cu)
     for (int v = 0; v < 2; ++v)
         for (int q = 0; q < 3; ++q) {
@@ -394,6 +401,7 @@ int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s) {
             for (int xt = 0; xt < J.nxt; ++xt) n_narrow += (xt * S2_TILE_X >= sj.narrow_x0);
             work[P.njobs] = (double)J.ntp * sj.KH * sj.ks * ((J.nxt - n_narrow) * icost(2 * sj.nhalf) + n_narrow * icost(2 * sj.nhalf_narrow));
             total += work[P.njobs];
+            macs += (long long)J.ntp * sj.KH * sj.ks * 256LL * 32LL * ((long long)(J.nxt - n_narrow) * 2 * sj.nhalf + (long long)n_narrow * 2 * sj.nhalf_narrow);
             smem = std::max(smem, lm_screen2_smem_bytes(sj.KH, sj.ks, sj.rows, sj.nhalf, sj.stages));
             if (sj.stacked && b.view[v].win_stride != (int64_t)b.view[v].win_pitch * b.view[v].win_h) return -1;
             if (!encode_window_map(&P.tmap[P.njobs], b.win[v], b.view[v].win_pitch, b.view[v].win_h, b.view[v].win_stride, b.B, sj.rows, sj.stacked != 0))
@@ -429,6 +437,7 @@ int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s) {
     if (once.first()) {
         if (cudaFuncSetAttribute(k_screen2, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) return -1;
     }
+    g_last_macs.store(macs);
     const int pairs = P.job[P.njobs - 1].pair_begin + P.job[P.njobs - 1].npair;
     k_screen2<<<2 * pairs, S2_THREADS, smem, s>>>(P);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;

@@ -1065,6 +1065,10 @@ int lm_get_info(const lm_ctx *ctx, const char *name, double *value) {
         *value = (double)ctx->opt_streams;
         return LM_OK;
     }
+    if (!strcmp(name, "screen_macs")) {  // int8 MACs the last k_screen2 launch (one sub-batch) issued to the tensor cores
+        *value = (double)lm_screen2_last_macs();
+        return LM_OK;
+    }
     if (!strcmp(name, "subbatch")) {
         *value = (double)ctx->Bcap;
         return LM_OK;

@@ -181,6 +181,7 @@ size_t lm_screen2_smem_bytes(int KH, int ks, int rows, int nhalf, int stages);
 // thresholds / scale / eps of one template (no image); false for non-finite weights
 bool lm_screen_quantize(const float *w, int kh, int kw, float init, LmScreenHost *out);
 int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s);
+long long lm_screen2_last_macs();  // int8 MACs issued by the last k_screen2 launch (whole sub-batch)
 
 // pick the padded kernel-row width the correlation kernel is instantiated for (>= kw), or -1
 int lm_corr_kwp(int kw);

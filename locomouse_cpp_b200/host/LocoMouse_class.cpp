@@ -229,10 +229,11 @@ LocoMouse_Model::LocoMouse_Model(const std::string &model_file_name) {
 struct LocoMouse::Batch {
     unsigned int first = 0, count = 0;
     int cand_cap = 0, match_cap = 0, n_tail = 0;
-    std::vector<int32_t> n_bottom, n_side, match_n, match_y, tail;
-    std::vector<lm_cand> bottom, side;
-    std::vector<double> match_s;
-    std::vector<uint32_t> flags;
+    // page-locked: lm_detect_batch copies device -> here directly (include/locomouse_b200.h, lm_host_alloc)
+    PinnedArray<int32_t> n_bottom, n_side, match_n, match_y, tail;
+    PinnedArray<lm_cand> bottom, side;
+    PinnedArray<double> match_s;
+    PinnedArray<uint32_t> flags;
     // cost builders (per feature): unary [count][n_priors][cand_cap]; pairwise packed CSC over count + 1 frames (frame 0 =
     // last frame of the previous chunk, so that the first transition of this chunk is present)
     bool has_costs = false;
@@ -287,7 +288,8 @@ void LocoMouse::loadVideo() {
         N_FRAMES = (unsigned int)V.n;
         VID_ROWS = V.rows;
         VID_COLS = V.cols;
-        VIDEO = std::move(V.frames);
+        VIDEO.resize(V.frames.size());
+        std::copy(V.frames.begin(), V.frames.end(), VIDEO.begin());
         return;
     }
     lmfile::Reader r(VIDEO_FILE, "LMV1");
@@ -598,6 +600,7 @@ void LocoMouse::initializeFeatureLoop() {
     PAIRWISE_BOTTOM_SNOUT.clear();
     CURRENT_FRAME = -1;  // the reference rewinds the video here (class.cpp:762)
     BATCH.reset();
+    SPARE.reset();
     LOOP_READY = true;
 }
 
@@ -605,7 +608,9 @@ void LocoMouse::initializeFeatureLoop() {
 // main.cpp:54-82 for those frames.
 void LocoMouse::runChunk(unsigned int first) {
     const unsigned int n = std::min<unsigned int>((unsigned int)LM_PARAMS.batch_frames, N_FRAMES - first);
-    std::unique_ptr<Batch> b(new Batch());
+    std::unique_ptr<Batch> b = std::move(SPARE);
+    if (!b) b.reset(new Batch());
+    b->has_costs = false;
     b->first = first;
     b->count = n;
     b->cand_cap = LM_PARAMS.cand_cap;
@@ -679,6 +684,7 @@ void LocoMouse::runChunk(unsigned int first) {
         }
         b->has_costs = true;
     }
+    SPARE = std::move(BATCH);
     BATCH = std::move(b);
 }
 

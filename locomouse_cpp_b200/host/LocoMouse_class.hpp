@@ -12,6 +12,7 @@
 #pragma once
 #include <cstdint>
 #include <memory>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -31,6 +32,42 @@ public:
     LocoMouse_LocationPrior(double x, double y, double md, double minx, double maxx, double miny, double maxy);
     double max_distance() const { return MAX_DISTANCE; }
     lm_location_prior to_c() const { return lm_location_prior{X, Y, MAX_DISTANCE, MIN_X, MIN_Y, MAX_X - MIN_X, MAX_Y - MIN_Y}; }
+};
+
+// Page-locked host array (lm_host_alloc): frames upload at the full PCIe rate and result arrays receive their device ->
+// host copies directly.  Falls back to nothing: lm_host_alloc failing is an error (std::runtime_error).
+template <typename T>
+class PinnedArray {
+    T *p_ = nullptr;
+    size_t n_ = 0, cap_ = 0;  // shrinking keeps the allocation (page-locking memory is slow)
+
+public:
+    PinnedArray() = default;
+    PinnedArray(const PinnedArray &) = delete;
+    PinnedArray &operator=(const PinnedArray &) = delete;
+    ~PinnedArray() { lm_host_free(p_); }
+    void resize(size_t n) {
+        if (n <= cap_) {
+            n_ = n;
+            return;
+        }
+        lm_host_free(p_);
+        p_ = nullptr;
+        n_ = cap_ = 0;
+        void *q = nullptr;
+        if (lm_host_alloc(&q, n * sizeof(T)) != LM_OK) throw std::runtime_error("lm_host_alloc failed (page-locked host memory)");
+        p_ = static_cast<T *>(q);
+        n_ = cap_ = n;
+    }
+    T *data() { return p_; }
+    const T *data() const { return p_; }
+    size_t size() const { return n_; }
+    T &operator[](size_t i) { return p_[i]; }
+    const T &operator[](size_t i) const { return p_[i]; }
+    T *begin() { return p_; }
+    T *end() { return p_ + n_; }
+    const T *begin() const { return p_; }
+    const T *end() const { return p_ + n_; }
 };
 
 class LocoMouse_Parameters {
@@ -109,7 +146,7 @@ protected:
     std::string LM_CALL, CONFIG_FILE, VIDEO_FILE, BKG_FILE, MODEL_FILE, CALIBRATION_FILE, FLIP_CHAR, OUTPUT_PATH;
     std::string output_file;
 
-    std::vector<uint8_t> VIDEO;       // raw 8-bit frames (channel 0), N_FRAMES x vid_rows x vid_cols
+    PinnedArray<uint8_t> VIDEO;       // raw 8-bit frames (channel 0), N_FRAMES x vid_rows x vid_cols, page-locked
     int VID_ROWS = 0, VID_COLS = 0;
     std::vector<uint8_t> BKG;
     std::vector<int32_t> CALIBRATION;  // ind_warp_mapping, N_ROWS x N_COLS
@@ -143,7 +180,7 @@ protected:
     // ---- device side ------------------------------------------------------------------------------
     lm_ctx *CTX = nullptr;
     struct Batch;                      // result buffers of the chunk that contains CURRENT_FRAME
-    std::unique_ptr<Batch> BATCH;
+    std::unique_ptr<Batch> BATCH, SPARE;   // SPARE: the chunk before BATCH, whose page-locked arrays the next chunk reuses
     bool LOOP_READY = false;
 
     void initializePaths(const LocoMouse_ParseInputs &INPUT);

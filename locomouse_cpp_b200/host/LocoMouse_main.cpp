@@ -11,11 +11,15 @@
 int main(int argc, char *argv[]) {
     const auto t0 = std::chrono::steady_clock::now();
     int return_val = EXIT_SUCCESS;
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     try {
         LocoMouse_ParseInputs inputs = LocoMouse_ParseInputs(argc, argv);
         std::unique_ptr<LocoMouse> L = LocoMouse_Initialize(inputs);
+        const auto t1 = clk::now();
         L->getBoundingBox();
         L->initializeFeatureLoop();
+        const auto t2 = clk::now();
         for (unsigned int i_frames = 0; i_frames < L->N_frames(); ++i_frames) {
             L->readFrame();
             L->cropBoundingBox();
@@ -27,9 +31,15 @@ int main(int argc, char *argv[]) {
             L->matchBottomSideCandidates();
             L->storePreviousImage();
         }
+        const auto t3 = clk::now();
         L->computeBottomTracks();
         L->computeSideTracks();
+        const auto t4 = clk::now();
         L->exportResults();
+        const auto t5 = clk::now();
+        // phases of the reference's main(): construction (file loading), pass 1, the per-frame loop, the tracker, export
+        std::cout << "LM_TIMING frames=" << L->N_frames() << " load_s=" << secs(t0, t1) << " pass1_s=" << secs(t1, t2) << " loop_s=" << secs(t2, t3)
+                  << " tracks_s=" << secs(t3, t4) << " export_s=" << secs(t4, t5) << std::endl;
     } catch (const std::invalid_argument &e) {
         std::cout << "Invalid inputs: " << e.what() << std::endl;
         return_val = EXIT_FAILURE;

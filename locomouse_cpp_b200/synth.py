@@ -310,7 +310,7 @@ def calibrate_rho(spec: SynthSpec, model: Model, bkg, calib, frames: np.ndarray,
     return Model(w=model.w, rho=rho)
 
 
-def make_problem(spec: SynthSpec, n_frames: int, seed: int = 1000, device="cpu", calib_frames: int = 3):
+def make_problem(spec: SynthSpec, n_frames: int, seed: int = 1000, device="cpu", calib_frames: int = 3, target_frac=None):
     """Everything one detect call needs: (cfg, model, bkg, calib, frames, bb_x, bb_y_side, bb_y_bottom).
     rho is calibrated on the first `calib_frames` CPU-rendered frames of video `seed` evenly spread over
     the sequence, so it is identical for host- and device-rendered videos."""
@@ -326,6 +326,7 @@ def make_problem(spec: SynthSpec, n_frames: int, seed: int = 1000, device="cpu",
         cbx.append(bx[0])
         cbs.append(bs[0])
         cbb.append(bb[0])
-    model = calibrate_rho(spec, make_model(spec), bkg, calib, np.stack(cf), cbx, cbs, cbb)
+    model = (calibrate_rho(spec, make_model(spec), bkg, calib, np.stack(cf), cbx, cbs, cbb) if target_frac is None else
+             calibrate_rho(spec, make_model(spec), bkg, calib, np.stack(cf), cbx, cbs, cbb, target_frac=tuple(target_frac)))
     frames, bb_x, bb_y_side, bb_y_bottom = make_video(spec, n_frames, seed, device, bkg, total=total)
     return cfg, model, bkg, calib, frames, bb_x, bb_y_side, bb_y_bottom

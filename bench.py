@@ -13,10 +13,13 @@ video per rank -> weak scaling, no data-path collective); candidate lists are ga
   value  : whole-job frames/s with the frames already resident in HBM (results still return to host).
   e2e    : the same through the public API with HOST (pinned) frame buffers: H2D of every frame and D2H
            of every result inside the timed region; for N>1 the gather of the candidate lists to rank 0 too.
-  roofline : the dominant kernel, k_corr (FP32 FMA bound by ~90x over HBM): algorithmic FLOPs
-           per launch / its CUDA-event duration, against the FP32 FMA peak.
-  cpu_baseline : the CPU oracle (a port of the reference path), 1 thread like the reference, on a bounded
-           sample of the same frames.
+  roofline : the dominant kernel, k_screen2 (int8 tcgen05 screen that decides the six correlations):
+           algorithmic FLOPs per launch / its CUDA-event duration against the measured bf16 tensor peak, plus the int8
+           work it actually executes against the int8 pipe; the exact dense FP32 kernel (k_corr) beside it.
+  cpu_baseline : the CPU oracle (a port of the reference path), 1 thread like the reference, on the first 1000 frames
+           (BASELINE configs[0]: one 1000-frame video, CPU vs 1 GPU).
+  other_configs : configs[0] (1000-frame video, host frames), configs[4] (2x frames, 60x60 templates) and a
+           throughput-vs-detection-density sweep; bounded samples, never part of `value`.
 """
 from __future__ import annotations
 
@@ -147,7 +150,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_STEP, help="frames per step per GPU (default: the 10k config)")
-    ap.add_argument("--cpu-sample", type=int, default=640, help="frames of the workload timed on the CPU oracle (1 thread)")
+    ap.add_argument("--cpu-sample", type=int, default=1000, help="frames of the workload timed on the CPU oracle (1 thread); 1000 = configs[0]'s video")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[0] / configs[4] / density side measurements")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="library option for the measured arm (lm_set_option), e.g. streams=3")
     args = ap.parse_args()
@@ -279,6 +283,41 @@ def main():
         except Exception:
             return None
 
+    def executed_int8(det, ms_per_launch, flop_alg, sm_mhz, rank, local):
+        """The int8 multiply-accumulates k_screen2 issues per launch (counted by the launcher from its job table) against
+        the int8 tensor pipe: nominal 8192 MAC/clk/SM and the best rate tools/umma_rate_probe reaches on this GPU."""
+        try:
+            macs = float(det.info("screen_macs"))
+        except Exception:
+            return None
+        if macs <= 0:
+            return None
+        tops = 2.0 * macs / (ms_per_launch * 1e-3) / 1e12
+        nominal = 148 * 8192 * 2 * sm_mhz * 1e6 / 1e12
+        out = {"int8_mac_per_launch": macs, "int8_tops": tops, "int8_nominal_peak_tops": nominal, "frac_of_int8_nominal": tops / nominal,
+               "executed_over_algorithmic": 2.0 * macs / flop_alg,
+               "note": "executed/algorithmic = two int8 weight digits x 64/30 Toeplitz K padding x tile padding"}
+        try:
+            if rank == 0:
+                o = subprocess.run([os.path.join(ROOT, "tools", "umma_rate_probe")], capture_output=True, text=True, timeout=120,
+                                   env=dict(os.environ, CUDA_VISIBLE_DEVICES=str(local))).stdout
+                best = 0.0
+                for ln in o.splitlines():
+                    try:
+                        j = json.loads(ln)
+                    except Exception:
+                        continue
+                    if j.get("kind") == "i8" and j.get("status") == 0 and j.get("grid", 0) >= 148:
+                        best = max(best, float(j.get("mac_per_cycle_per_sm", 0.0)))
+                if best > 0:
+                    probe = 148 * best * 2 * sm_mhz * 1e6 / 1e12
+                    out["int8_probe_peak_tops"] = probe
+                    out["frac_of_int8_probe_peak"] = tops / probe
+                    out["probe"] = "tools/umma_rate_probe: best kind::i8 SS-form rate on all SMs (mac/clk/SM) x 148 x SM clock"
+        except Exception as ex:  # pragma: no cover
+            out["probe_error"] = repr(ex)
+        return out
+
     corr_ms_per_launch = stage["corr"] / (launches_per_step * args.steps)
     corr_tflops = flop_per_launch / (corr_ms_per_launch * 1e-3) / 1e12
     if screen_on:
@@ -293,7 +332,8 @@ def main():
                     "share_of_step": ms_screen / max(stage["total"], 1e-9),
                     "launch_ms_in_timed_region_overlapped": ms_screen_overlapped / (launches_per_step * args.steps),
                     "note": "algorithmic FLOPs = the exact correlation the screen decides (SURVEY 8d), not the int8 MMA work executed "
-                            "(2 weight digits x 64/30 Toeplitz padding = 4.3x more MACs, run at the bf16-equivalent rate)",
+                            "(see `executed`)",
+                    "executed": executed_int8(det, scr_ms_per_launch, flop_per_launch, sm_max, rank, local),
                     "correlation_stage": {"kernels": ("k_screen2" if screen_mode == 2 else "k_screen") + " + k_corr_sparse", "launch_ms": corr_ms_per_launch,
                                           "achieved_tflops": corr_tflops, "vs_fp32_fma_nominal_peak": corr_tflops / fp32_nominal,
                                           "fp32_fma_nominal_peak": fp32_nominal,
@@ -326,6 +366,7 @@ def main():
         try:
             m = min(n, 4 * subb)
             det.set_option("screen", 0)
+            det.set_option("streams", 1)   # stage events of a strictly serial run: no cross-stream waiting inside "corr"
             det.detect_batch(frames[:m], bx[:m], bs[:m], bb[:m])
             det.detect_batch(frames[:m], bx[:m], bs[:m], bb[:m])
             tm0, _ = det.last_timing()
@@ -334,6 +375,7 @@ def main():
                                               "frac": dense_tflops / fp32_nominal, "frames": m, "corr_ms": tm0["corr"],
                                               "frac_of_measured_ffma": (dense_tflops / ffma_measured["ffma_reg_tflops"]) if ffma_measured else None}
             det.set_option("screen", screen_mode)
+            det.set_option("streams", n_streams)
             det.detect_batch(frames[:m], bx[:m], bs[:m], bb[:m])  # re-prepare scratch before the e2e leg
         except Exception as ex:  # pragma: no cover
             roofline["dense_exact_kernel"] = {"error": repr(ex)}
@@ -450,6 +492,127 @@ def main():
                "stage_seconds": dict(zip(("preprocess", "correlation", "tail", "nms", "pairing", "total"), map(float, st))),
                "gpu_results_bit_exact_on_sample": bool(same)}
 
+    # ---- other BASELINE configs and the density sweep (rank 0, N=1 only; bounded samples, never part of `value`) -------------
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = {}
+        src = host if host is not None else frames   # pinned host frames after the e2e leg, else the device tensor
+
+        def timed(fn, reps):
+            fn()
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t) / reps
+
+        # configs[0]: one 1000-frame video, reference CPU path vs 1 GPU.  GPU side: (a) the ctypes call with host frames,
+        # (b) the C++ class mirror's main() sequence on files (the drop-in path a reference user runs): its own LM_TIMING line.
+        try:
+            m0 = min(1000, n)
+            h0 = src[:m0] if host is not None else src[:m0].cpu().pin_memory()
+            r0 = Results(m0, cfg.cand_cap, cfg.match_cap, cfg.n_tail_points, pinned=True)
+            dt0 = timed(lambda: det.detect_batch(h0, bx[:m0], bs[:m0], bb[:m0], results=r0), 5)
+            c0 = {"frames": m0, "gpu_host_frames_per_s": m0 / dt0, "gpu_ms_per_video": dt0 * 1e3,
+                  "cpu_frames_per_s_1_thread": cpu["value"] if cpu else None, "cpu_s_per_video": (m0 / cpu["value"]) if cpu else None,
+                  "note": "lm_detect_batch on one 1000-frame video in pinned host memory (H2D + D2H inside); cpu_baseline is the same 1000 frames on 1 thread"}
+            try:
+                import pathlib
+                import tempfile
+
+                from locomouse_cpp_b200.lmfiles import write_problem_files
+
+                exe = os.path.join(ROOT, "locomouse_cpp_b200", "host", "locomouse_b200")
+                with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
+                    d = pathlib.Path(td)
+                    write_problem_files(d, cfg, model, bkg, calib, h0.numpy(), bx[:m0], bs[:m0], bb[:m0], spec.side_h)
+                    best = None
+                    for _ in range(2):
+                        t = time.perf_counter()
+                        pr = subprocess.run([exe, "1", str(d / "config.yml"), str(d / "video.lmv"), str(d / "bkg.lmi"), str(d / "model.lmm"),
+                                             str(d / "calib.lmc"), "R", str(d)], capture_output=True, text=True, timeout=300)
+                        wall0 = time.perf_counter() - t
+                        tl = [ln for ln in pr.stdout.splitlines() if ln.startswith("LM_TIMING")]
+                        if pr.returncode != 0 or not tl:
+                            raise RuntimeError((pr.stdout + pr.stderr)[-300:])
+                        kv = dict(x.split("=") for x in tl[-1].split()[1:])
+                        cur = {k: float(v) for k, v in kv.items()}
+                        cur["process_wall_s"] = wall0
+                        if best is None or cur["loop_s"] < best["loop_s"]:
+                            best = cur
+                    c0["cpp_driver"] = dict(best, loop_frames_per_s=m0 / best["loop_s"],
+                                            whole_program_frames_per_s=m0 / best["process_wall_s"],
+                                            note="host/locomouse_b200 (main.cpp's call sequence through the C++ class mirror) on files in /dev/shm: "
+                                                 "load_s = reading the 680 MB video into page-locked memory + CUDA context, loop_s = the per-frame "
+                                                 "loop (batched lm_detect_batch behind readFrame ... matchBottomSideCandidates), export_s = output file")
+            except Exception as ex:  # pragma: no cover
+                c0["cpp_driver"] = {"error": repr(ex)[:300]}
+            extra["config0"] = c0
+        except Exception as ex:  # pragma: no cover
+            extra["config0"] = {"error": repr(ex)[:300]}
+
+        # throughput vs detection density: rho re-calibrated so that x0.25 / x1 / x4 of the default fraction of pixels score > 0
+        try:
+            md = min(n, 4 * subb)
+            dens = []
+            for mult in (0.25, 1.0, 4.0):
+                tf = (0.012 * mult, 0.012 * mult, 0.02 * mult)
+                _c, model_d, _b, _k, _f, _x, _s, _y = synth.make_problem(spec, 8, seed=1000, target_frac=tf)
+                det.set_model(model_d)
+                if src.is_cuda:
+                    fd = src[:md]
+                else:
+                    fd = src[:md].to(dev)
+                rd = det.detect_batch(fd, bx[:md], bs[:md], bb[:md], allow_overflow=True)
+                dtd = timed(lambda: det.detect_batch(fd, bx[:md], bs[:md], bb[:md], allow_overflow=True), 3)
+                dens.append({"target_fraction_x": mult, "frames_per_s": md / dtd, "positives_per_frame": float(det.info("positives")) / subb,
+                             "sparse_patches_per_frame": float(det.info("sparse_tasks")) / subb,
+                             "candidates_per_frame": float(rd.n_bottom.sum() + rd.n_side.sum()) / md,
+                             "overflow_frames": int((rd.flags != 0).sum())})
+                del fd
+            det.set_model(model)
+            extra["density_sweep"] = {"frames": md, "points": dens,
+                                      "note": "resident frames; the screen's exact pass and the NMS lists grow with the fraction of positive pixels "
+                                              "(x1 = the benchmarked calibration: 1.2 % paw / snout, 2 % tail)"}
+        except Exception as ex:  # pragma: no cover
+            extra["density_sweep"] = {"error": repr(ex)[:300]}
+
+        # configs[4]: 2x-upsampled frames (800 x 3400), six 60 x 60 templates
+        try:
+            det.close()
+            det = None
+            frames = None
+            host5 = None
+            torch.cuda.empty_cache()
+            spec5 = synth.SynthSpec(scale=2, cand_cap=128, match_cap=512)
+            cfg5, model5, bkg5, calib5, _, _, _, _ = synth.make_problem(spec5, 8, seed=1000)
+            m5 = 1024
+            fr5, bx5, bs5, bb5 = synth.make_video(spec5, m5, 1000, dev, bkg5)
+            det5 = Detector(cfg5, model5, bkg5, calib5, device=local)
+            det5.detect_batch(fr5, bx5, bs5, bb5, allow_overflow=True)
+            dt5 = timed(lambda: det5.detect_batch(fr5, bx5, bs5, bb5, allow_overflow=True), 3)
+            fma5 = algorithmic_fma_per_frame(cfg5, model5)
+            det5.set_option("streams", 1)
+            det5.detect_batch(fr5, bx5, bs5, bb5, allow_overflow=True)
+            det5.detect_batch(fr5, bx5, bs5, bb5, allow_overflow=True)
+            tm5, _ = det5.last_timing()
+            ms5 = det5.info("ms_screen")
+            tp = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+            extra["config4_2x_60x60"] = {
+                "frames": m5, "frame": [cfg5.vid_rows, cfg5.vid_cols], "templates": "6 x 60x60 f32", "frames_per_s": m5 / dt5,
+                "screen_active": int(det5.info("screen_active")), "algorithmic_gflop_per_frame": 2.0 * fma5 / 1e9,
+                "whole_path_algorithmic_tflops": 2.0 * fma5 * m5 / dt5 / 1e12,
+                "screen_kernel_ms_serial": ms5, "screen_kernel_algorithmic_tflops": 2.0 * fma5 * m5 / (ms5 * 1e-3) / 1e12 if ms5 > 0 else None,
+                "screen_kernel_frac_of_bf16_peak": (2.0 * fma5 * m5 / (ms5 * 1e-3) / 1e12 / tp) if ms5 > 0 else None,
+                "corr_stage_ms_serial": tm5["corr"], "fp32_fma_bound_frames_per_s": fp32_nominal * 1e12 / (2.0 * fma5),
+                "note": "contraction-bound stress: 16x the FMAs of config 1 per frame; the exact FP32 path is bounded by fp32_fma_bound_frames_per_s, "
+                        "the tensor-core screen decides the same outputs (bit-exact parity: tests/test_gpu_screen.py::test_screen_config5_upsampled_60x60)"}
+            det5.close()
+            del fr5
+        except Exception as ex:  # pragma: no cover
+            extra["config4_2x_60x60"] = {"error": repr(ex)[:300]}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -467,7 +630,7 @@ def main():
                            "streams": n_streams, "note": "value/wall/device_event: overlapped multi-stream pipeline; stage_ms_per_step_serial and the roofline "
                                    "launch times: the same steps with the library option streams=1 (kernels strictly serial)"},
                 "clocks": sampler.summary(), "gpu_launches": int(launches), "overflow_frames": overflow,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "pass1_tm_de": pass1, "cost_builders": costs}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "pass1_tm_de": pass1, "cost_builders": costs, "other_configs": extra}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -22,22 +22,24 @@
 
 namespace {
 
-constexpr int NMS_THREADS = 512;
+// 16 bytes of shared memory per list entry: the 64-bit sort key, whose storage is reused after the sort for the score
+// (low word) and the slot / root scratch (high word); link; packed position.  The small size class (<= NMS_SMALL_P entries,
+// NMS_SMALL_T threads) keeps a CTA below 10 kB so that several fit beside a resident k_screen2 CTA.
+constexpr int NMS_SMALL_T = 256, NMS_BIG_T = 512;
 
 struct NmsSmem {
-    unsigned long long *key;  // [P]
-    short *x, *y;             // [P]
-    float *s;                 // [P]
+    unsigned long long *key;  // [P]  sort keys; afterwards {score, slot} pairs
+    uint32_t *xy;             // [P]  x | y << 16 (one load per overlap test)
     int *link;                // [P]  parent / root / cluster id
+    __device__ __forceinline__ float &s(int i) const { return reinterpret_cast<float *>(key)[2 * i]; }
+    __device__ __forceinline__ int &slot(int i) const { return reinterpret_cast<int *>(key)[2 * i + 1]; }
 };
 
 __device__ __forceinline__ NmsSmem carve(unsigned char *base, int P) {
     NmsSmem m;
     m.key = reinterpret_cast<unsigned long long *>(base);
-    m.s = reinterpret_cast<float *>(m.key + P);
-    m.link = reinterpret_cast<int *>(m.s + P);
-    m.x = reinterpret_cast<short *>(m.link + P);
-    m.y = m.x + P;
+    m.link = reinterpret_cast<int *>(m.key + P);
+    m.xy = reinterpret_cast<uint32_t *>(m.link + P);
     return m;
 }
 
@@ -48,6 +50,7 @@ __device__ __forceinline__ int next_pow2(int v) {
 }
 
 // Loads, filters, sorts.  Returns the number of detections n (<= det_cap); sets *overflow.
+template <int NMS_THREADS>
 __device__ int load_and_sort(const LmBatch &b, int f, int feat, int view, NmsSmem &m, int P, int *s_n,
                              bool *overflow) {
     const int tid = threadIdx.x;
@@ -73,17 +76,15 @@ __device__ int load_and_sort(const LmBatch &b, int f, int feat, int view, NmsSme
     __syncthreads();
     const int n = *s_n;
     const int Q = next_pow2(n < 2 ? 2 : n);
+    // bitonic network, one thread per compare-exchange PAIR (i, i | j): every thread of a pass is active
     for (int k = 2; k <= Q; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < Q; i += NMS_THREADS) {
-                int l = i ^ j;
-                if (l > i) {
-                    unsigned long long a = m.key[i], c = m.key[l];
-                    bool up = (i & k) == 0;
-                    if ((a > c) == up) {
-                        m.key[i] = c;
-                        m.key[l] = a;
-                    }
+            for (int t = tid; t < (Q >> 1); t += NMS_THREADS) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                const unsigned long long a = m.key[i], c = m.key[l];
+                if ((a > c) == ((i & k) == 0)) {
+                    m.key[i] = c;
+                    m.key[l] = a;
                 }
             }
             __syncthreads();
@@ -92,9 +93,8 @@ __device__ int load_and_sort(const LmBatch &b, int f, int feat, int view, NmsSme
         unsigned long long k = m.key[i];
         unsigned idx = (unsigned)(k & 0xffffffffu);
         int y = idx / bw;
-        m.y[i] = (short)y;
-        m.x[i] = (short)(idx - y * bw);
-        m.s[i] = __uint_as_float(~(unsigned)(k >> 32));
+        m.xy[i] = (uint32_t)(idx - y * bw) | ((uint32_t)y << 16);
+        m.s(i) = __uint_as_float(~(unsigned)(k >> 32));  // overwrites this entry's own key
     }
     __syncthreads();
     return n;
@@ -109,13 +109,12 @@ __device__ __forceinline__ bool overlaps(int dx, int dy, int w, int h, int wh2) 
 // One WARP per cluster slot: the lanes scan the rank-ordered detections 32 at a time (ballot of the slot's members),
 // lane 0 accumulates the members of each ballot in rank order in double, as the reference's loops do (1731-1739,
 // 1865-1869; double addition is not associative, so the order is part of the result).  On entry link[i] holds the
-// root of detection i; it is first replaced by the root's candidate slot.
-template <bool HALF_EVEN>
-__device__ void write_candidates(const NmsSmem &m, int n, const int *slot_of_root, int ncand, int cap,
-                                 lm_cand *out, const int *root_rank) {
+// root of detection i and slot(r) the candidate slot of root r; link is first replaced by the root's candidate slot.
+template <bool HALF_EVEN, int NMS_THREADS>
+__device__ void write_candidates(const NmsSmem &m, int n, int ncand, int cap, lm_cand *out, const int *root_rank) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NWARPS = NMS_THREADS / 32;
-    for (int i = tid; i < n; i += NMS_THREADS) m.link[i] = slot_of_root[m.link[i]];
+    for (int i = tid; i < n; i += NMS_THREADS) m.link[i] = m.slot(m.link[i]);
     __syncthreads();
     for (int k = warp; k < cap; k += NWARPS) {
         lm_cand c;
@@ -131,9 +130,10 @@ __device__ void write_candidates(const NmsSmem &m, int n, const int *slot_of_roo
                     while (mask) {
                         const int q = base + __ffs(mask) - 1;
                         mask &= mask - 1;
-                        const double s = (double)m.s[q];
-                        wx = __dadd_rn(wx, __dmul_rn((double)m.x[q], s));
-                        wy = __dadd_rn(wy, __dmul_rn((double)m.y[q], s));
+                        const double s = (double)m.s(q);
+                        const uint32_t pq = m.xy[q];
+                        wx = __dadd_rn(wx, __dmul_rn((double)(int)(pq & 0xffffu), s));
+                        wy = __dadd_rn(wy, __dmul_rn((double)(int)(pq >> 16), s));
                         ss = __dadd_rn(ss, s);
                     }
             }
@@ -146,7 +146,7 @@ __device__ void write_candidates(const NmsSmem &m, int n, const int *slot_of_roo
                     c.x = (int)round(qx);
                     c.y = (int)round(qy);
                 }
-                c.s = (double)m.s[root_rank[k]];
+                c.s = (double)m.s(root_rank[k]);
             }
         }
         if (lane == 0) out[k] = c;
@@ -154,11 +154,11 @@ __device__ void write_candidates(const NmsSmem &m, int n, const int *slot_of_roo
 }
 
 // ---- nmsMax ------------------------------------------------------------------------------------------
+template <int NMS_THREADS>
 __global__ void __launch_bounds__(NMS_THREADS) k_nms_bottom(const __grid_constant__ LmBatch b, int P, int lo, int hi) {
     extern __shared__ __align__(16) unsigned char raw[];
     NmsSmem m = carve(raw, P);
-    int *slot = reinterpret_cast<int *>(m.y + P);      // [P] slot of a root rank
-    int *root_rank = slot + P;                          // [cand_cap]
+    int *root_rank = reinterpret_cast<int *>(m.xy + P);  // [cand_cap]
     __shared__ int s_n, s_nc;
     const int f = blockIdx.x >> 1, feat = blockIdx.x & 1, tid = threadIdx.x;
     {   // size class of this list (the two launches partition the lists by raw count)
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_bottom(const __grid_constan
         if (c <= lo || c > hi) return;
     }
     bool overflow;
-    const int n = load_and_sort(b, f, feat, LM_BOTTOM, m, P, &s_n, &overflow);
+    const int n = load_and_sort<NMS_THREADS>(b, f, feat, LM_BOTTOM, m, P, &s_n, &overflow);
     const LmTemplateDev &T = b.tmpl[LM_BOTTOM][feat];
     const int w = T.kw, h = T.kh, wh2 = 2 * w * h;
     if (tid == 0) s_nc = 0;
@@ -176,11 +176,13 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_bottom(const __grid_constan
     {
         const int lane = tid & 31, warp = tid >> 5;
         for (int j = warp; j < n; j += NMS_THREADS / 32) {
-            const int xj = m.x[j], yj = m.y[j];
+            const uint32_t pj = m.xy[j];
+            const int xj = (int)(pj & 0xffffu), yj = (int)(pj >> 16);
             int par = j;
             for (int base = 0; base < j; base += 32) {
                 const int i = base + lane;
-                const bool hit = i < j && overlaps(m.x[i] - xj, m.y[i] - yj, w, h, wh2);
+                const uint32_t pi = m.xy[i < j ? i : j];
+                const bool hit = i < j && overlaps((int)(pi & 0xffffu) - xj, (int)(pi >> 16) - yj, w, h, wh2);
                 const unsigned bal = __ballot_sync(0xffffffffu, hit);
                 if (bal) {
                     par = base + __ffs(bal) - 1;
@@ -195,10 +197,10 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_bottom(const __grid_constan
     for (int j = tid; j < n; j += NMS_THREADS) {
         int r = j;
         while (m.link[r] != r) r = m.link[r];
-        slot[j] = r;  // temp: root of j
+        m.slot(j) = r;  // temp: root of j
     }
     __syncthreads();
-    for (int j = tid; j < n; j += NMS_THREADS) m.link[j] = slot[j];
+    for (int j = tid; j < n; j += NMS_THREADS) m.link[j] = m.slot(j);
     __syncthreads();
     // candidate slots = roots in rank order (serial prefix by one warp is enough: n is small)
     if (tid < 32) {
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_bottom(const __grid_constan
             unsigned bal = __ballot_sync(0xffffffffu, is_root);
             if (is_root) {
                 int k = base + __popc(bal & ((1u << tid) - 1));
-                slot[j] = k;
+                m.slot(j) = k;
                 if (k < b.cand_cap) root_rank[k] = j;
             }
             base += __popc(bal);
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_bottom(const __grid_constan
     __syncthreads();
     const int nc = s_nc;
     const int ncw = nc < b.cand_cap ? nc : b.cand_cap;
-    write_candidates<true>(m, n, slot, ncw, b.cand_cap, b.bottom + (int64_t)(f * 2 + feat) * b.cand_cap, root_rank);
+    write_candidates<true, NMS_THREADS>(m, n, ncw, b.cand_cap, b.bottom + (int64_t)(f * 2 + feat) * b.cand_cap, root_rank);
     if (tid == 0) {
         b.n_bottom[f * 2 + feat] = ncw;
         unsigned fl = 0;
@@ -230,11 +232,11 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_bottom(const __grid_constan
 }
 
 // ---- peakClustering ----------------------------------------------------------------------------------
+template <int NMS_THREADS>
 __global__ void __launch_bounds__(NMS_THREADS) k_nms_side(const __grid_constant__ LmBatch b, int P, int lo, int hi) {
     extern __shared__ __align__(16) unsigned char raw[];
     NmsSmem m = carve(raw, P);
-    int *slot = reinterpret_cast<int *>(m.y + P);
-    int *root_rank = slot + P;
+    int *root_rank = reinterpret_cast<int *>(m.xy + P);
     __shared__ int s_n, s_next;
     const int f = blockIdx.x >> 1, feat = blockIdx.x & 1, tid = threadIdx.x;
     lm_cand *out = b.side + (int64_t)(f * 2 + feat) * b.cand_cap;
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_side(const __grid_constant_
         return;
     }
     bool overflow;
-    const int n = load_and_sort(b, f, feat, LM_SIDE, m, P, &s_n, &overflow);
+    const int n = load_and_sort<NMS_THREADS>(b, f, feat, LM_SIDE, m, P, &s_n, &overflow);
     const LmTemplateDev &T = b.tmpl[LM_SIDE][feat];
     const int w = T.kw, h = T.kh, wh2 = 2 * w * h;
     for (int j = tid; j < n; j += NMS_THREADS) m.link[j] = -1;  // -1 = free
@@ -278,20 +280,23 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_side(const __grid_constant_
         }
         if (found == INF) break;
         c = found;
-        const int xc = m.x[c], yc = m.y[c];
+        const int xc = (int)(m.xy[c] & 0xffffu), yc = (int)(m.xy[c] >> 16);
         if (tid == 0) {
             s_next = INF;
             m.link[c] = c;
-            slot[c] = nc;
+            m.slot(c) = nc;
             if (nc < b.cand_cap) root_rank[nc] = c;
         }
         for (int j = c + 1 + tid; j < n; j += NMS_THREADS)
-            if (m.link[j] < 0 && overlaps(m.x[j] - xc, m.y[j] - yc, w, h, wh2)) m.link[j] = c;
+            if (m.link[j] < 0) {
+                const uint32_t pq = m.xy[j];
+                if (overlaps((int)(pq & 0xffffu) - xc, (int)(pq >> 16) - yc, w, h, wh2)) m.link[j] = c;
+            }
         ++nc;
         __syncthreads();
     }
     const int ncw = nc < b.cand_cap ? nc : b.cand_cap;
-    write_candidates<false>(m, n, slot, ncw, b.cand_cap, out, root_rank);
+    write_candidates<false, NMS_THREADS>(m, n, ncw, b.cand_cap, out, root_rank);
     if (tid == 0) {
         b.n_side[f * 2 + feat] = ncw;
         unsigned fl = 0;
@@ -302,8 +307,8 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_side(const __grid_constant_
 }
 
 size_t nms_smem(int P, int cand_cap) {
-    // key 8 + s 4 + link 4 + x 2 + y 2 + slot 4 = 24 bytes per entry
-    return (size_t)P * 24 + (size_t)cand_cap * 4 + 16;
+    // key 8 (later score + slot) + link 4 + xy 4 = 16 bytes per entry
+    return (size_t)P * 16 + (size_t)cand_cap * 4 + 16;
 }
 
 }  // namespace
@@ -318,8 +323,8 @@ int lm_launch_nms(const LmBatch &b, cudaStream_t s) {
     if (const char *e = getenv("LM_NMS_SMALL")) SMALL = std::max(2, atoi(e));
     static LmDevOnce once;
     if (once.first()) {
-        cudaFuncSetAttribute(k_nms_bottom, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(k_nms_side, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_nms_bottom<NMS_BIG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_nms_side<NMS_BIG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     }
     int launches = 0;
     int cls[4], ncls = 0;
@@ -328,10 +333,19 @@ int lm_launch_nms(const LmBatch &b, cudaStream_t s) {
     for (int view = 0; view < 2; ++view) {
         int lo = -1;
         for (int q = 0; q < ncls; ++q) {
-            if (view == 0)
-                k_nms_bottom<<<b.B * 2, NMS_THREADS, nms_smem(cls[q], b.cand_cap), s>>>(b, cls[q], lo, cls[q]);
-            else
-                k_nms_side<<<b.B * 2, NMS_THREADS, nms_smem(cls[q], b.cand_cap), s>>>(b, cls[q], lo, cls[q]);
+            const size_t smem = nms_smem(cls[q], b.cand_cap);
+            const bool small = q == 0 && cls[q] <= 1024;   // few entries: half the threads, so that more CTAs are resident
+            if (view == 0) {
+                if (small)
+                    k_nms_bottom<NMS_SMALL_T><<<b.B * 2, NMS_SMALL_T, smem, s>>>(b, cls[q], lo, cls[q]);
+                else
+                    k_nms_bottom<NMS_BIG_T><<<b.B * 2, NMS_BIG_T, smem, s>>>(b, cls[q], lo, cls[q]);
+            } else {
+                if (small)
+                    k_nms_side<NMS_SMALL_T><<<b.B * 2, NMS_SMALL_T, smem, s>>>(b, cls[q], lo, cls[q]);
+                else
+                    k_nms_side<NMS_BIG_T><<<b.B * 2, NMS_BIG_T, smem, s>>>(b, cls[q], lo, cls[q]);
+            }
             ++launches;
             lo = cls[q];
         }

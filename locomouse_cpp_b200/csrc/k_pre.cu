@@ -23,25 +23,19 @@ __device__ __forceinline__ const uint8_t *frame_ptr(const LmBatch &b, int i) {  
 }
 
 // ---- k_minmax ------------------------------------------------------------------------------------
-// minmax[slot] = (255 - min, max) so that both reduce with atomicMax from a zero-initialised buffer.
-// The only pass over whole raw frames, hence HBM-bound.  A CTA owns an 8 kB pixel range (two 16-byte vectors per thread)
-// and walks MM_GROUP consecutive frames with the background vectors of that range held in registers, so the L2-resident
-// background costs 1/MM_GROUP of the frame traffic instead of doubling it; two frames' loads are in flight per thread
-// (streaming loads: a frame is read once).  Per-frame partials go warp -> shared memory, one barrier per CTA at the end.
+// minmax[slot] = (255 - min, max) of d = max(F - BKG, 0), so that both reduce with atomicMax from a zero-initialised
+// buffer.  The only pass over whole raw frames, hence HBM-bound.  Because max(., 0) is monotone, min d = max(min(F - BKG), 0)
+// and max d = max(max(F - BKG), 0): the kernel tracks the SIGNED difference and clamps once per frame.
+// A CTA owns a 16 kB pixel range (MM_VEC 16-byte vectors per thread, lanes on consecutive vectors) and walks MM_GROUP
+// consecutive frames with the negated background of that range held in registers as s16x2 lanes (even / odd bytes), so the
+// L2-resident background costs 1/MM_GROUP of the frame traffic; all MM_VEC loads of a frame are in flight together
+// (streaming loads: a frame is read once).  Per four pixels: two widening ops (LOP3 + PRMT) and four fused add-min / add-max
+// (VIADDMNMX.S16x2; the byte-SIMD intrinsics __vsubus4 / __vminu4 are emulated with dozens of instructions on this
+// architecture and had made the pass ALU-bound).  Per-frame partials go warp (REDUX) -> shared memory, one barrier per CTA.
 constexpr int MM_GROUP = 8;
-constexpr int MM_VEC = 2;
+constexpr int MM_VEC = 4;
+constexpr int MM_THREADS = 256;
 
-// One 32-bit word = four pixels.  Bytes are widened to s16x2 lanes (even / odd bytes) and go through the DPX
-// instructions: d = max(f + (-k), 0) is one VIADDMNMX.S16x2.RELU, the running min / max one VIMNMX3.S16x2 each -- six
-// instructions per four pixels (the byte-SIMD intrinsics __vsubus4 / __vminu4 are emulated with dozens of instructions
-// on this architecture and made the pass ALU-bound at 40 % of the HBM rate).  nke / nko: the background's even / odd
-// bytes negated per 16-bit lane, prepared once per CTA.
-__device__ __forceinline__ void mm_word(uint32_t &mn, uint32_t &mx, uint32_t f, uint32_t nke, uint32_t nko) {
-    const uint32_t fe = f & 0x00ff00ffu, fo = (f >> 8) & 0x00ff00ffu;
-    const uint32_t de = __viaddmax_s16x2_relu(fe, nke, 0u), dd = __viaddmax_s16x2_relu(fo, nko, 0u);
-    mn = __vimin3_s16x2(mn, de, dd);
-    mx = __vimax3_s16x2(mx, de, dd);
-}
 struct NegBkg {
     uint32_t e[4], o[4];
 };
@@ -51,9 +45,17 @@ __device__ __forceinline__ NegBkg mm_neg(const uint4 &k) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         r.e[q] = __vneg2(w[q] & 0x00ff00ffu);
-        r.o[q] = __vneg2((w[q] >> 8) & 0x00ff00ffu);
+        r.o[q] = __vneg2(__byte_perm(w[q], 0u, 0x4341));
     }
     return r;
+}
+// one 32-bit word = four pixels: mn = min(mn, f - k), mx = max(mx, f - k) per s16 lane
+__device__ __forceinline__ void mm_word(uint32_t &mn, uint32_t &mx, uint32_t f, uint32_t nke, uint32_t nko) {
+    const uint32_t fe = f & 0x00ff00ffu, fo = __byte_perm(f, 0u, 0x4341);  // bytes 0,2 / bytes 1,3 as 16-bit lanes
+    mn = __viaddmin_s16x2(fe, nke, mn);
+    mx = __viaddmax_s16x2(fe, nke, mx);
+    mn = __viaddmin_s16x2(fo, nko, mn);
+    mx = __viaddmax_s16x2(fo, nko, mx);
 }
 __device__ __forceinline__ void mm_acc(uint32_t &mn, uint32_t &mx, const uint4 &f, const NegBkg &k) {
     mm_word(mn, mx, f.x, k.e[0], k.o[0]);
@@ -61,73 +63,89 @@ __device__ __forceinline__ void mm_acc(uint32_t &mn, uint32_t &mx, const uint4 &
     mm_word(mn, mx, f.z, k.e[2], k.o[2]);
     mm_word(mn, mx, f.w, k.e[3], k.o[3]);
 }
+// clamp the signed lane extrema at 0 and reduce over the warp
+__device__ __forceinline__ void mm_warp_reduce(uint32_t mn, uint32_t mx, int &lo, int &hi) {
+    lo = min((int)(short)(mn & 0xffffu), (int)(short)(mn >> 16));
+    hi = max((int)(short)(mx & 0xffffu), (int)(short)(mx >> 16));
+    lo = __reduce_min_sync(0xffffffffu, max(lo, 0));  // REDUX: one instruction per warp reduction
+    hi = __reduce_max_sync(0xffffffffu, max(hi, 0));
+}
 
-__global__ void __launch_bounds__(256, 6) k_minmax(const __grid_constant__ LmBatch b, int slot0, int nslots) {
-    __shared__ uint32_t slo[MM_GROUP][8], shi[MM_GROUP][8];
+// ALIGNED: background, first frame and frame_bytes are all multiples of 16 (every frame of the batch is then 16-byte
+// aligned and has no tail): vector path without per-frame checks.  Otherwise: the same ranges byte by byte.
+template <bool ALIGNED>
+__global__ void __launch_bounds__(MM_THREADS, 3) k_minmax(const __grid_constant__ LmBatch b, int slot0, int nslots) {
+    __shared__ int slo[MM_GROUP][MM_THREADS / 32], shi[MM_GROUP][MM_THREADS / 32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t n = b.frame_bytes;
     const uint8_t *K = b.bkg;
     const int g0 = blockIdx.y * MM_GROUP;
     const int ng = min(MM_GROUP, nslots - g0);
-    // all frames of a batch share alignment (contiguous, frame_bytes apart) unless frame_bytes is odd; checked per frame
-    const int64_t v0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * MM_VEC;  // first 16-byte vector of this thread
-    const int64_t nvec = n >> 4;
-    NegBkg k[MM_VEC];
-    const bool kvec = (reinterpret_cast<uintptr_t>(K) & 15) == 0;
+    const int64_t vbase = (int64_t)blockIdx.x * (MM_THREADS * MM_VEC) + threadIdx.x;  // this thread's vectors: vbase + q * MM_THREADS
+    if (ALIGNED) {
+        const int64_t nvec = n >> 4;
+        const uint4 *K4 = reinterpret_cast<const uint4 *>(K);
+        NegBkg k[MM_VEC];
+        bool ok[MM_VEC];
 #pragma unroll
-    for (int q = 0; q < MM_VEC; ++q)
-        k[q] = mm_neg((kvec && v0 + q < nvec) ? __ldg(reinterpret_cast<const uint4 *>(K) + v0 + q) : make_uint4(0, 0, 0, 0));
-    for (int g = 0; g < ng; ++g) {
-        const int slot = slot0 + g0 + g;  // slot 0 = halo frame (-1)
-        const uint8_t *F = frame_ptr(b, slot - 1);
-        uint32_t mn = 0x00ff00ffu, mx = 0u;  // s16x2 lanes
-        if (F) {
-            if (kvec && (reinterpret_cast<uintptr_t>(F) & 15) == 0) {
-                const uint4 *F4 = reinterpret_cast<const uint4 *>(F);
+        for (int q = 0; q < MM_VEC; ++q) {
+            ok[q] = vbase + q * MM_THREADS < nvec;
+            // a vector past the end reads as F = K = 0: difference 0 would disturb the minimum, so it is skipped below
+            k[q] = mm_neg(ok[q] ? __ldg(K4 + vbase + q * MM_THREADS) : make_uint4(0, 0, 0, 0));
+        }
+        for (int g = 0; g < ng; ++g) {
+            const int slot = slot0 + g0 + g;  // slot 0 = halo frame (-1)
+            const uint8_t *F = frame_ptr(b, slot - 1);
+            uint32_t mn = 0x7fff7fffu, mx = 0x80008000u;  // s16x2 lanes
+            if (F) {
+                const uint4 *F4 = reinterpret_cast<const uint4 *>(F) + vbase;
                 uint4 f[MM_VEC];
 #pragma unroll
-                for (int q = 0; q < MM_VEC; ++q) f[q] = (v0 + q < nvec) ? __ldcs(F4 + v0 + q) : make_uint4(0, 0, 0, 0);  // streamed once
+                for (int q = 0; q < MM_VEC; ++q)
+                    if (ok[q]) f[q] = __ldcs(F4 + q * MM_THREADS);  // streamed once
 #pragma unroll
                 for (int q = 0; q < MM_VEC; ++q)
-                    if (v0 + q < nvec) mm_acc(mn, mx, f[q], k[q]);
-                // bytes after the last whole vector: the thread that owns the vector slot right after them
-                if (v0 <= nvec && nvec < v0 + MM_VEC)
-                    for (int64_t t = nvec << 4; t < n; ++t) {
-                        const int d = (int)F[t] - (int)K[t];
-                        const uint32_t u = d < 0 ? 0u : (uint32_t)d;
-                        mn = __vimin3_s16x2(mn, u * 0x00010001u, u * 0x00010001u);
-                        mx = __vimax3_s16x2(mx, u * 0x00010001u, u * 0x00010001u);
-                    }
-            } else {  // unaligned frames (odd frame size or caller pointer): bytewise over this thread's range
-                const int64_t t0 = v0 << 4, t1 = min(n, (v0 + MM_VEC) << 4);
-                for (int64_t t = t0; t < t1; ++t) {
-                    const int d = (int)F[t] - (int)K[t];
-                    const uint32_t u = d < 0 ? 0u : (uint32_t)d;
-                    mn = __vimin3_s16x2(mn, u * 0x00010001u, u * 0x00010001u);
-                    mx = __vimax3_s16x2(mx, u * 0x00010001u, u * 0x00010001u);
-                }
+                    if (ok[q]) mm_acc(mn, mx, f[q], k[q]);
+            }
+            int lo, hi;
+            mm_warp_reduce(mn, mx, lo, hi);
+            if (lane == 0) {
+                slo[g][w] = lo;
+                shi[g][w] = hi;
             }
         }
-        uint32_t lo = min(mn & 0xffffu, mn >> 16);
-        uint32_t hi = max(mx & 0xffffu, mx >> 16);
-        lo = __reduce_min_sync(0xffffffffu, lo);   // REDUX: one instruction per warp reduction
-        hi = __reduce_max_sync(0xffffffffu, hi);
-        if (lane == 0) {
-            slo[g][w] = lo;
-            shi[g][w] = hi;
+    } else {
+        const int64_t t0 = (int64_t)blockIdx.x * (MM_THREADS * MM_VEC * 16);
+        for (int g = 0; g < ng; ++g) {
+            const uint8_t *F = frame_ptr(b, slot0 + g0 + g - 1);
+            int lo = 0x7fff, hi = -0x8000;
+            if (F)
+                for (int64_t t = t0 + threadIdx.x; t < min(n, t0 + MM_THREADS * MM_VEC * 16); t += MM_THREADS) {
+                    const int d = (int)F[t] - (int)K[t];
+                    lo = min(lo, d);
+                    hi = max(hi, d);
+                }
+            lo = __reduce_min_sync(0xffffffffu, max(lo, 0));
+            hi = __reduce_max_sync(0xffffffffu, max(hi, 0));
+            if (lane == 0) {
+                slo[g][w] = lo;
+                shi[g][w] = hi;
+            }
         }
     }
     __syncthreads();
     if (threadIdx.x < ng) {
         const int g = threadIdx.x, slot = slot0 + g0 + g;
         if (frame_ptr(b, slot - 1)) {
-            uint32_t lo = slo[g][0], hi = shi[g][0];
-            for (int q = 1; q < 8; ++q) {
+            int lo = slo[g][0], hi = shi[g][0];
+#pragma unroll
+            for (int q = 1; q < MM_THREADS / 32; ++q) {
                 lo = min(lo, slo[g][q]);
                 hi = max(hi, shi[g][q]);
             }
-            atomicMax(&b.minmax[slot * 2 + 0], (int)(255u - lo));
-            atomicMax(&b.minmax[slot * 2 + 1], (int)hi);
+            // a CTA whose range holds no pixel of the frame contributes (0x7fff -> clamped, -0x8000 -> 0): lo > 255 is skipped
+            if (lo <= 255) atomicMax(&b.minmax[slot * 2 + 0], 255 - lo);
+            atomicMax(&b.minmax[slot * 2 + 1], hi);
         }
     }
 }
@@ -172,13 +190,27 @@ constexpr int PREP_ROWS = 64;
 constexpr int PREP_THREADS = 256;
 
 __global__ void __launch_bounds__(256) k_fold_calib(const int32_t *__restrict__ calib, const uint8_t *__restrict__ bkg, int n_rows, int n_cols,
-                                                    int flip, int32_t *__restrict__ calib_flip, uint8_t *__restrict__ bkg_warp) {
+                                                    int flip, int32_t *__restrict__ calib_flip, uint8_t *__restrict__ bkg_warp,
+                                                    uint8_t *__restrict__ run_mode) {
     const int64_t n = (int64_t)n_rows * n_cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / n_cols), c = (int)(i - (int64_t)r * n_cols);
-        const int32_t src = calib[(int64_t)r * n_cols + (flip ? n_cols - 1 - c : c)];
+        const int32_t *row = calib + (int64_t)r * n_cols;
+        auto at = [&](int cc) { return row[flip ? n_cols - 1 - cc : cc]; };
+        const int32_t src = at(c);
         calib_flip[i] = src;
         bkg_warp[i] = bkg[src];
+        // run_mode[r][c]: the four pixels c .. c+3 of this row come from raw bytes src, src+1, src+2, src+3 (1) or
+        // src, src-1, src-2, src-3 (2: mirrored); 0 otherwise.  Real calibration maps are piecewise such runs.
+        uint8_t m = 0;
+        if (c + 3 < n_cols) {
+            const int32_t a1 = at(c + 1), a2 = at(c + 2), a3 = at(c + 3);
+            if (a1 == src + 1 && a2 == src + 2 && a3 == src + 3)
+                m = 1;
+            else if (a1 == src - 1 && a2 == src - 2 && a3 == src - 3)
+                m = 2;
+        }
+        run_mode[i] = m;
     }
 }
 
@@ -194,6 +226,8 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ L
     const uint8_t *__restrict__ F = b.frames + (int64_t)f * b.frame_bytes;
     const uint8_t *__restrict__ Kw = b.bkg_warp;
     const int32_t *__restrict__ C2 = b.calib_flip;
+    const uint8_t *__restrict__ RM = b.run_mode;
+    const int fbytes = (int)b.frame_bytes;
     const int x0 = (int)b.bb_x[f] - b.bb_w + 1 - V.halo_x;
     const int ypos = (int)(v == LM_BOTTOM ? b.bb_y_bottom[f] : b.bb_y_side[f]);
     const int y0 = ypos - V.box_h + 1 - V.halo_y;
@@ -220,14 +254,26 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ L
                 if (yy >= 0 && yy < n_rows) {
                     const int base = yy * n_cols + xx0;
                     const int32_t *cp = C2 + base;
-                    const int i0 = __ldg(cp), i1 = __ldg(cp + 1), i2 = __ldg(cp + 2), i3 = __ldg(cp + 3);
+                    const int i0 = __ldg(cp);
                     const uint32_t *kp = reinterpret_cast<const uint32_t *>(Kw + (base & ~3));  // bkg_warp is 4-byte aligned and padded
                     const uint32_t kw4 = __funnelshift_r(__ldg(kp), __ldg(kp + 1), (base & 3) * 8);
-                    const int d0 = max((int)__ldg(F + i0) - (int)(kw4 & 0xffu), 0);
-                    const int d1 = max((int)__ldg(F + i1) - (int)((kw4 >> 8) & 0xffu), 0);
-                    const int d2 = max((int)__ldg(F + i2) - (int)((kw4 >> 16) & 0xffu), 0);
-                    const int d3 = max((int)__ldg(F + i3) - (int)(kw4 >> 24), 0);
-                    out = (uint32_t)lut[d0] | ((uint32_t)lut[d1] << 8) | ((uint32_t)lut[d2] << 16) | ((uint32_t)lut[d3] << 24);
+                    const int mode = __ldg(RM + base);
+                    // a run of four raw bytes: two aligned word loads instead of three more map loads and four byte gathers.
+                    // The aligned words must lie inside this frame's bytes (the caller's buffer ends with the last frame).
+                    const int lo_i = mode == 2 ? i0 - 3 : i0;
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(F) + (uintptr_t)(unsigned)lo_i;
+                    uint32_t f4;
+                    if (mode != 0 && lo_i >= 4 && lo_i + 8 <= fbytes) {
+                        const uint32_t *fp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+                        f4 = __funnelshift_r(__ldg(fp), __ldg(fp + 1), ((unsigned)a & 3u) * 8u);
+                        if (mode == 2) f4 = __byte_perm(f4, 0u, 0x0123);
+                    } else {
+                        const int i1 = __ldg(cp + 1), i2 = __ldg(cp + 2), i3 = __ldg(cp + 3);
+                        f4 = (uint32_t)__ldg(F + i0) | ((uint32_t)__ldg(F + i1) << 8) | ((uint32_t)__ldg(F + i2) << 16) | ((uint32_t)__ldg(F + i3) << 24);
+                    }
+                    const uint32_t d4 = __vsubus4(f4, kw4);  // per-byte max(F - BKG, 0)
+                    out = (uint32_t)lut[d4 & 0xffu] | ((uint32_t)lut[(d4 >> 8) & 0xffu] << 8) | ((uint32_t)lut[(d4 >> 16) & 0xffu] << 16) |
+                          ((uint32_t)lut[d4 >> 24] << 24);
                 }
                 *dst = out;
             }
@@ -256,9 +302,16 @@ int lm_launch_minmax(const LmBatch &b, cudaStream_t s) {
     const int slot0 = b.prev ? 0 : 1;
     const int nslots = b.B + 1 - slot0;
     if (nslots <= 0) return 0;
-    const int64_t nvec = (b.frame_bytes >> 4) + 1;  // + 1: the slot that owns the bytes after the last whole vector
-    const int bx = (int)((nvec + 256 * MM_VEC - 1) / (256 * MM_VEC));
-    k_minmax<<<dim3(bx, (nslots + MM_GROUP - 1) / MM_GROUP), 256, 0, s>>>(b, slot0, nslots);
+    const int64_t per_cta = (int64_t)MM_THREADS * MM_VEC * 16;
+    const int bx = (int)((b.frame_bytes + per_cta - 1) / per_cta);
+    const dim3 grid(bx, (nslots + MM_GROUP - 1) / MM_GROUP);
+    // every frame (and the halo frame) 16-byte aligned, no tail bytes: the vector path
+    const bool aligned = (b.frame_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(b.frames) & 15) == 0 && (reinterpret_cast<uintptr_t>(b.bkg) & 15) == 0 &&
+                         (b.prev == nullptr || (reinterpret_cast<uintptr_t>(b.prev) & 15) == 0);
+    if (aligned)
+        k_minmax<true><<<grid, MM_THREADS, 0, s>>>(b, slot0, nslots);
+    else
+        k_minmax<false><<<grid, MM_THREADS, 0, s>>>(b, slot0, nslots);
     k_lut<<<nslots, 256, 0, s>>>(b, slot0);
     return 2;
 }
@@ -272,7 +325,7 @@ int lm_launch_prep(const LmBatch &b, cudaStream_t s) {
 }
 
 int lm_launch_fold_calib(const int32_t *calib, const uint8_t *bkg, int n_rows, int n_cols, int flip, int32_t *calib_flip, uint8_t *bkg_warp,
-                         cudaStream_t s) {
-    k_fold_calib<<<lm_sm_count() * 4, 256, 0, s>>>(calib, bkg, n_rows, n_cols, flip, calib_flip, bkg_warp);
+                         uint8_t *run_mode, cudaStream_t s) {
+    k_fold_calib<<<lm_sm_count() * 4, 256, 0, s>>>(calib, bkg, n_rows, n_cols, flip, calib_flip, bkg_warp, run_mode);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -15,7 +15,7 @@
 //                 rows) stays resident in shared memory for the CTA's lifetime.  A rigorous error bound
 //                 (quantisation + fp32 rounding of the exact path, lm_screen_build) turns into two integer
 //                 thresholds: V <= t_lo proves score <= 0, V > t_hi proves score > 0.
-//  k_corr_sparse  (FP32 FFMA, oracle tap order)  re-evaluates only the 4x8 output patches that contain an
+//  k_corr_sparse  (FP32 FFMA, oracle tap order)  re-evaluates only the 2x4 output patches that contain an
 //                 output the screen could not decide (paw / snout: possibly positive and unmasked; tail:
 //                 sign not proven) and emits exactly what the dense kernel emits for those patches.
 //
@@ -262,12 +262,10 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(const __grid_constant
                     if (__ldg(crow + c) <= 25) need &= ~(1u << c);
                 }
             }
-            // 4x8 patches: lanes 4k..4k+3 hold the four rows of patch row (y >> 2)
-            uint32_t pf = ((need & 0xffu) ? 1u : 0u) | ((need & 0xff00u) ? 2u : 0u) | ((need & 0xff0000u) ? 4u : 0u) |
-                          ((need & 0xff000000u) ? 8u : 0u);
+            // 2x4 patches: lanes 2k, 2k+1 hold the two rows of patch row (y >> 1); bit q of pf = columns 4q .. 4q+3
+            uint32_t pf = lm_nibble_any(need);
             pf |= __shfl_xor_sync(0xffffffffu, pf, 1);
-            pf |= __shfl_xor_sync(0xffffffffu, pf, 2);
-            const int cnt = ((lane & 3) == 0) ? __popc(pf) : 0;
+            const int cnt = ((lane & 1) == 0) ? __popc(pf) : 0;
             const uint32_t any = __ballot_sync(0xffffffffu, cnt > 0);
             if (any) {
                 int incl = cnt;
@@ -282,12 +280,12 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(const __grid_constant
                 base = __shfl_sync(0xffffffffu, base, 31);
                 int o = base + incl - cnt;
                 if (cnt) {
-                    const uint32_t head = ((uint32_t)f << 14) | ((uint32_t)(y >> 2) << 7);
+                    const uint32_t head = ((uint32_t)f << 16) | ((uint32_t)(y >> 1) << 8);
                     uint32_t m = pf;
                     while (m) {
                         const int q = __ffs(m) - 1;
                         m &= m - 1;
-                        if (o < J.j.task_cap) J.j.tasks[o] = head | (uint32_t)((x0 >> 3) + q);
+                        if (o < J.j.task_cap) J.j.tasks[o] = head | (uint32_t)((x0 >> 2) + q);
                         ++o;
                     }
                 }
@@ -304,10 +302,10 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_screen(const __grid_constant
 }
 
 // =================================================================================================================
-// k_corr_sparse: one thread per undecided 4x8 patch, exact fp32 scores in the oracle's tap order.
+// k_corr_sparse: one thread per undecided 2x4 patch, exact fp32 scores in the oracle's tap order.
 // =================================================================================================================
 constexpr int SP_THREADS = 128;
-constexpr int SP_TX = 8, SP_TY = 4;
+constexpr int SP_TX = 4, SP_TY = 2;   // patch = 2 rows x 4 columns (task word: frame << 16 | patch_row << 8 | patch_col)
 
 struct SparseJob {
     int view, feat, is_tail;
@@ -377,7 +375,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_corr_sparse(const __grid_constan
     const int kh = J.kh;
     for (int ti = blockIdx.x * SP_THREADS + tid; ti < ntasks; ti += gridDim.x * SP_THREADS) {
         const uint32_t task = J.tasks[ti];
-        const int f = (int)(task >> 14), y0 = (int)((task >> 7) & 127u) * TY, x0 = (int)(task & 127u) * TX;
+        const int f = (int)(task >> 16), y0 = (int)((task >> 8) & 255u) * TY, x0 = (int)(task & 255u) * TX;
         const uint8_t *wbase = P.win[v] + (int64_t)f * P.win_stride[v];
         const int col0 = x0 + J.dx;
         const int shift = (col0 & 3) * 8;
@@ -670,7 +668,7 @@ int lm_launch_screen(const LmBatch &b, cudaStream_t s) {
         if (hi) {
             if (cudaEventRecord(b.ev_screen_go, s) != cudaSuccess || cudaStreamWaitEvent(b.screen_stream, b.ev_screen_go, 0) != cudaSuccess) return -1;
         }
-        if (lm_launch_screen2_kernel(b, hi ? b.screen_stream : s) < 0) return -1;
+        if (!(lm_whatif_skip() & 4) && lm_launch_screen2_kernel(b, hi ? b.screen_stream : s) < 0) return -1;
         if (hi) {
             if (cudaEventRecord(b.ev_screen_done, b.screen_stream) != cudaSuccess || cudaStreamWaitEvent(s, b.ev_screen_done, 0) != cudaSuccess) return -1;
         }
@@ -685,7 +683,7 @@ int lm_launch_screen(const LmBatch &b, cudaStream_t s) {
     bool done[6] = {};
     const bool fma = b.fma_mode != 0;
     for (int q0 = 0; q0 < Q.njobs; ++q0) {
-        if (done[q0]) continue;
+        if (done[q0] || (lm_whatif_skip() & 8)) continue;
         const int kwp = lm_corr_kwp(Q.job[q0].kw);
         int kh_max = 0;
         for (int q = q0; q < Q.njobs; ++q)

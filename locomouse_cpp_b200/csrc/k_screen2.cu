@@ -15,7 +15,7 @@
 // "stacked": the sub-batch's windows, contiguous in memory at the window pitch, are treated as one tall image and cut
 // into 256-row tile pairs (179-row windows: 84 % useful rows instead of 59 %); a tile may straddle two frames, each
 // accumulator row maps back to (frame, y) and rows in the inter-frame halo are dropped.
-// Everything else (exact int8 arithmetic, thresholds, 4x8 patch tasks for k_corr_sparse) is k_screen.cu's.
+// Everything else (exact int8 arithmetic, thresholds, 2x4 patch tasks for k_corr_sparse) is k_screen.cu's.
 //
 // Pair protocol: window-tile "full" and accumulator "empty" barriers live in the leader CTA (rank 0) and
 // collect arrivals from both CTAs (remote arrive through mapa); tcgen05.commit multicasts "tile free" and
@@ -213,7 +213,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
         for (int u = prank; u < nunits; u += J.npair) {
             const int tp = u / J.nxt, xt = u - tp * J.nxt;
             const int R = (2 * tp + (int)rank) * S2_TILE_M + tid, x0 = xt * S2_TILE_X;
-            const int f = R / VH, y = R - f * VH;   // VH % 4 == 0: the four rows of a patch share f and y >> 2
+            const int f = R / VH, y = R - f * VH;   // VH % 4 == 0: the two rows of a patch share f and y >> 1
             const int nar = x0 >= J.j.narrow_x0 ? 1 : 0;
             const int nt = nar ? J.j.ntmpl_narrow : J.j.ntmpl;
             mbar_wait(d_full(acc), accphase);
@@ -279,11 +279,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
                         if (__ldg(crow + c) <= 25) need &= ~(1u << c);
                     }
                 }
-                uint32_t pf = ((need & 0xffu) ? 1u : 0u) | ((need & 0xff00u) ? 2u : 0u) | ((need & 0xff0000u) ? 4u : 0u) |
-                              ((need & 0xff000000u) ? 8u : 0u);
+                uint32_t pf = lm_nibble_any(need);   // 2x4 patches: bit q = columns 4q .. 4q+3, rows y and y ^ 1 combined below
                 pf |= __shfl_xor_sync(0xffffffffu, pf, 1);
-                pf |= __shfl_xor_sync(0xffffffffu, pf, 2);
-                const int cnt = ((lane & 3) == 0) ? __popc(pf) : 0;
+                const int cnt = ((lane & 1) == 0) ? __popc(pf) : 0;
                 const uint32_t any = __ballot_sync(0xffffffffu, cnt > 0);
                 if (any) {
                     int incl = cnt;
@@ -298,12 +296,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
                     base = __shfl_sync(0xffffffffu, base, 31);
                     int o = base + incl - cnt;
                     if (cnt) {
-                        const uint32_t head = ((uint32_t)f << 14) | ((uint32_t)(y >> 2) << 7);
+                        const uint32_t head = ((uint32_t)f << 16) | ((uint32_t)(y >> 1) << 8);
                         uint32_t m = pf;
                         while (m) {
                             const int q = __ffs(m) - 1;
                             m &= m - 1;
-                            if (o < J.j.task_cap[t]) J.j.tasks[t][o] = head | (uint32_t)((x0 >> 3) + q);
+                            if (o < J.j.task_cap[t]) J.j.tasks[t][o] = head | (uint32_t)((x0 >> 2) + q);
                             ++o;
                         }
                     }

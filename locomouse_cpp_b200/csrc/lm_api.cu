@@ -49,6 +49,7 @@ struct lm_ctx {
     uint8_t *d_bkg = nullptr;
     int32_t *d_calib = nullptr;
     int32_t *d_calib_flip = nullptr;  // calibration with the mirror folded in + the background seen through it (k_fold_calib):
+    uint8_t *d_run_mode = nullptr;
     uint8_t *d_bkg_warp = nullptr;    // scratch of prepare(), rebuilt when the background / calibration change (fold_dirty)
     bool fold_dirty = true;
     float *d_tmpl[2][3] = {};
@@ -188,6 +189,7 @@ void free_scratch(lm_ctx *c) {
     for (int s = 0; s < 2; ++s) c->d_stage[s] = nullptr;
     c->d_calib_flip = nullptr;
     c->d_bkg_warp = nullptr;
+    c->d_run_mode = nullptr;
     c->fold_dirty = true;
     for (int s = 0; s < lm_ctx::NRES; ++s) c->d_bb[s] = nullptr;
     for (int s = 0; s < lm_ctx::NSLOT; ++s) c->d_res[s] = nullptr;
@@ -212,7 +214,7 @@ int prepare_screen(lm_ctx *ctx, LmBatch &b, int want, size_t B) {
     b.scr = LmScreen{};
     const lm_config &k = ctx->cfg;
     const size_t smem_limit = 220 * 1024;
-    if (want <= 0 || k.bb_w > 1024 || std::max(k.bb_h_bottom, k.bb_h_side) > 512 || B > ((size_t)1 << 17)) return LM_OK;
+    if (want <= 0 || k.bb_w > 1024 || std::max(k.bb_h_bottom, k.bb_h_side) > 512 || B > ((size_t)1 << 16)) return LM_OK;  // task word: frame << 16 | patch_row << 8 | patch_col
     const int nfeat = k.tail_w > 0 ? 3 : 2;
     // 1. quantisation + thresholds of every template
     for (int v = 0; v < 2; ++v)
@@ -331,7 +333,7 @@ int prepare_screen(lm_ctx *ctx, LmBatch &b, int want, size_t B) {
             J.t_lo = H.t_lo;
             J.t_hi = H.t_hi;
             const int ow = (f == LM_TAIL) ? k.tail_w : k.bb_w;
-            J.task_cap = (int)std::min<size_t>((size_t)1 << 30, B * (size_t)((b.bb_h[v] + 3) / 4) * (size_t)((ow + 7) / 8));
+            J.task_cap = (int)std::min<size_t>((size_t)1 << 30, B * (size_t)((b.bb_h[v] + 1) / 2) * (size_t)((ow + 3) / 4));  // every 2x4 patch undecided
             if ((rc = dalloc(ctx, &J.tasks, (size_t)J.task_cap))) return rc;
             if (have1) {
                 int8_t *dimg = nullptr;
@@ -459,7 +461,9 @@ int prepare(lm_ctx *ctx) {
     int rc;
     if ((rc = dalloc(ctx, &ctx->d_calib_flip, (size_t)k.n_rows * k.n_cols))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_bkg_warp, (size_t)k.n_rows * k.n_cols + 16))) return rc;  // + padding: word loads past the last pixel
+    if ((rc = dalloc(ctx, &ctx->d_run_mode, (size_t)k.n_rows * k.n_cols))) return rc;
     b.calib_flip = ctx->d_calib_flip;
+    b.run_mode = ctx->d_run_mode;
     b.bkg_warp = ctx->d_bkg_warp;
     ctx->fold_dirty = true;
     if ((rc = dalloc(ctx, &b.minmax, (B + 1) * 2))) return rc;
@@ -806,7 +810,7 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
         return rc;
     }
     if (ctx->fold_dirty) {  // per-video constants of k_prep / k_pair; every stream of the previous call has been drained
-        if (lm_launch_fold_calib(ctx->d_calib, ctx->d_bkg, k.n_rows, k.n_cols, k.flip, ctx->d_calib_flip, ctx->d_bkg_warp, ctx->stream) < 0)
+        if (lm_launch_fold_calib(ctx->d_calib, ctx->d_bkg, k.n_rows, k.n_cols, k.flip, ctx->d_calib_flip, ctx->d_bkg_warp, ctx->d_run_mode, ctx->stream) < 0)
             return fail(ctx, LM_ERR_RUNTIME, "calibration fold launch failed");
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->fold_dirty = false;
@@ -926,10 +930,11 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
         CK(cudaMemsetAsync(b.flags, 0, (size_t)B * 4, stf));
         CK(cudaEventRecord(ev[0], stf));
         int nl;
-        if ((nl = lm_launch_minmax(b, stf)) < 0) return fail(ctx, LM_ERR_RUNTIME, "minmax launch failed");
+        const int skip = lm_whatif_skip();  // timing experiments only (0 in production)
+        if ((nl = (skip & 1) ? 0 : lm_launch_minmax(b, stf)) < 0) return fail(ctx, LM_ERR_RUNTIME, "minmax launch failed");
         ctx->launches += nl;
         CK(cudaEventRecord(ev[1], stf));
-        if ((nl = lm_launch_prep(b, stf)) < 0) return fail(ctx, LM_ERR_RUNTIME, "prep launch failed");
+        if ((nl = (skip & 2) ? 0 : lm_launch_prep(b, stf)) < 0) return fail(ctx, LM_ERR_RUNTIME, "prep launch failed");
         ctx->launches += nl;
         CK(cudaEventRecord(ev[2], stf));
         if (split) CK(cudaStreamWaitEvent(st, ev[2], 0));
@@ -937,13 +942,13 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
         if (nl < 0) return fail(ctx, LM_ERR_RUNTIME, "correlation launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         ctx->launches += nl;
         CK(cudaEventRecord(ev[3], st));
-        if ((nl = lm_launch_tail(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "tail launch failed");
+        if ((nl = (skip & 16) ? 0 : lm_launch_tail(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "tail launch failed");
         ctx->launches += nl;
         CK(cudaEventRecord(ev[4], st));
-        if ((nl = lm_launch_nms(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "nms launch failed");
+        if ((nl = (skip & 32) ? 0 : lm_launch_nms(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "nms launch failed");
         ctx->launches += nl;
         CK(cudaEventRecord(ev[5], st));
-        if ((nl = lm_launch_pair(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "pair launch failed");
+        if ((nl = (skip & 64) ? 0 : lm_launch_pair(b, st)) < 0) return fail(ctx, LM_ERR_RUNTIME, "pair launch failed");
         ctx->launches += nl;
         CK(cudaEventRecord(ev[6], st));
         CK(cudaGetLastError());
@@ -1071,6 +1076,24 @@ int lm_get_info(const lm_ctx *ctx, const char *name, double *value) {
     }
     if (!strcmp(name, "subbatch")) {
         *value = (double)ctx->Bcap;
+        return LM_OK;
+    }
+    // diagnostics of the sub-batch that last ran in scratch set 0 (all streams drained when lm_detect_batch returns):
+    // "sparse_tasks" = 4x8 patches handed to the exact pass, "positives" = entries of the positive-pixel lists
+    if (!strcmp(name, "sparse_tasks") || !strcmp(name, "positives")) {
+        if (!ctx->Bcap) return LM_ERR_INVALID;
+        const LmBatch &b = ctx->bt;
+        double tot = 0.0;
+        if (name[0] == 's') {
+            int32_t nt[8] = {};
+            if (!b.scr.ntasks || cudaMemcpy(nt, b.scr.ntasks, sizeof nt, cudaMemcpyDeviceToHost) != cudaSuccess) return LM_ERR_RUNTIME;
+            for (int i = 0; i < 6; ++i) tot += nt[i];
+        } else {
+            std::vector<int32_t> c((size_t)ctx->Bcap * 4);
+            if (cudaMemcpy(c.data(), b.det_count, c.size() * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return LM_ERR_RUNTIME;
+            for (int32_t x : c) tot += x;
+        }
+        *value = tot;
         return LM_OK;
     }
     return LM_ERR_INVALID;

@@ -10,6 +10,7 @@
 //   det lists       {u32 idx; f32 score} [B][2 feat][2 view][det_cap] + counts i32 [B][4]
 //   results         same struct-of-arrays as lm_results, for B frames
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -54,7 +55,7 @@ struct LmScreenJob {
     int dx, dy;           // window column / row of tap (0,0) for output (0,0): halo - anchor
     int rows;             // window rows staged per 128-row tile: 128 + kh - 1 + dy, rounded up to 8
     long long t_lo, t_hi; // V <= t_lo: score provably <= 0;  V > t_hi: score provably > 0
-    uint32_t *tasks;      // device, [task_cap]: frame << 14 | patch_row << 7 | patch_col
+    uint32_t *tasks;      // device, [task_cap]: frame << 16 | patch_row << 8 | patch_col (2x4 patches)
     int task_cap;
 };
 // CTA-pair variant (k_screen2.cu).  A job decides up to three templates of one view with one resident B operand per
@@ -98,6 +99,7 @@ struct LmBatch {
     const int32_t *calib;
     const int32_t *calib_flip;  // [n_rows][n_cols] calib with the mirror folded in (k_fold_calib); detection path only
     const uint8_t *bkg_warp;    // [n_rows][n_cols] bkg[calib_flip], 4-byte aligned, >= 8 bytes of padding behind it
+    const uint8_t *run_mode;    // [n_rows][n_cols] 1 / 2: pixels c..c+3 come from four consecutive raw bytes (ascending / descending); 0: no run
     const uint32_t *bb_x, *bb_y_side, *bb_y_bottom;  // device, [B]
     // config
     int vid_rows, vid_cols, n_rows, n_cols;
@@ -135,7 +137,7 @@ struct LmBatch {
 // launchers (each returns the number of kernels it launched)
 int lm_launch_minmax(const LmBatch &b, cudaStream_t s);
 int lm_launch_prep(const LmBatch &b, cudaStream_t s);
-int lm_launch_fold_calib(const int32_t *calib, const uint8_t *bkg, int n_rows, int n_cols, int flip, int32_t *calib_flip, uint8_t *bkg_warp,
+int lm_launch_fold_calib(const int32_t *calib, const uint8_t *bkg, int n_rows, int n_cols, int flip, int32_t *calib_flip, uint8_t *bkg_warp, uint8_t *run_mode,
                          cudaStream_t s);
 int lm_launch_corr(const LmBatch &b, cudaStream_t s);
 int lm_launch_tail(const LmBatch &b, cudaStream_t s);
@@ -181,6 +183,12 @@ size_t lm_screen2_smem_bytes(int KH, int ks, int rows, int nhalf, int stages);
 // thresholds / scale / eps of one template (no image); false for non-finite weights
 bool lm_screen_quantize(const float *w, int kh, int kw, float init, LmScreenHost *out);
 int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s);
+// timing experiments only (tools/whatif.py): bit mask from the environment variable LM_WHATIF_SKIP of stages NOT launched
+// (1 minmax, 2 prep, 4 screen kernel, 8 sparse exact pass, 16 tail, 32 nms, 64 pairing); results are then meaningless
+inline int lm_whatif_skip() {
+    const char *e = getenv("LM_WHATIF_SKIP");
+    return e ? atoi(e) : 0;
+}
 long long lm_screen2_last_macs();  // int8 MACs issued by the last k_screen2 launch (whole sub-batch)
 
 // pick the padded kernel-row width the correlation kernel is instantiated for (>= kw), or -1

@@ -104,3 +104,13 @@ __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const void *tmap,
                  "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster)
                  : "memory");
 }
+
+// bit q of the result = any of bits 4q .. 4q+3 of m (q = 0..7): which 4-column groups of a 32-column mask are non-empty
+__device__ __forceinline__ uint32_t lm_nibble_any(uint32_t m) {
+    m |= m >> 1;
+    m |= m >> 2;
+    m &= 0x11111111u;                 // bit 4q = any of nibble q
+    m = (m | (m >> 3)) & 0x03030303u; // two flags per byte
+    m = (m | (m >> 6)) & 0x000f000fu; // four flags per half
+    return (m | (m >> 12)) & 0xffu;
+}

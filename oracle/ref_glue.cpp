@@ -144,6 +144,17 @@ public:
     double SIDE_THRESHOLD = 255 * 0.05;
     void computeMouseBox_DE(cv::Mat &I_SIDE, double &bb_x);
 };
+class LocoMouse_TM : public LocoMouse {  // members computeMouseBox_DD / bwAreaOpen read (LocoMouse_TM.hpp:22-40)
+public:
+    unsigned int BOTTOM_THRESHOLD = 0, SIDE_THRESHOLD = 0, MIN_PIXEL_COUNT = 1;
+    unsigned int ZERO_COL_PRE = 0, ZERO_COL_POST = 0, ZERO_ROW_PRE = 0, ZERO_ROW_POST = 0;
+    cv::Mat DISK_FILTER;
+    cv::Mat I;   // LocoMouse::I, the calibrated frame LocoMouse_TM::readFrame() fills (LocoMouse_class.hpp:170)
+    cv::Mat bwAreaOpen(cv::Mat &Iin);
+    void computeMouseBox_DD(cv::Mat &I_SIDE, double &bb_x);
+    void imfill(const cv::Mat &Iin, cv::Mat &Iout);
+    void readFrame();
+};
 #include "_ref/ref_imadjust_default_body.inc"  // LocoMouse::imadjust_default (LocoMouse_class.cpp:3244-3311)
 #include "_ref/ref_box_de_body.inc"            // LocoMouse_TM_DE::computeMouseBox_DE (LocoMouse_TM_DE.cpp:56-113)
 #include "_ref/ref_read_body.inc"     // readFrame(cv::Mat&), correctImage (LocoMouse_class.cpp:1273-1406)
@@ -154,6 +165,9 @@ public:
 #include "_ref/ref_side_cost_body.inc" // pairwisePotential_SideView (LocoMouse_class.cpp:2073-2150)
 #include "_ref/ref_box_base_body.inc"  // largestBWAreaObject, computeMouseBox (LocoMouse_class.cpp:921-997)
 #include "_ref/ref_box_size_body.inc"  // computeMouseBoxSize, storePreviousImage, medianvec, stdvec (LocoMouse_class.cpp:1481-1556)
+using namespace cv;   // LocoMouse_TM.cpp is written against `using namespace cv` (Locomouse.hpp:12)
+using namespace std;
+#include "_ref/ref_box_tm_body.inc"    // LocoMouse_TM::bwAreaOpen, computeMouseBox_DD, readFrame, imfill (LocoMouse_TM.cpp:158-269)
 
 extern "C" {
 
@@ -321,6 +335,38 @@ int ref_mouse_box_de(unsigned char *side, int side_h, int n_cols, double thresho
         L.computeMouseBox_DE(I, *bb_x);
         return 0;
     } catch (const std::exception &) {
+        return -1;
+    }
+}
+
+// LocoMouse_TM::computeMouseBox_DD on a calibrated side view (u8, side_h x n_cols, modified in place as the reference does):
+// returns bb_x.  zero[4] = ZERO_COL_PRE, ZERO_COL_POST, ZERO_ROW_PRE, ZERO_ROW_POST; disk: the DISK_FILTER matrix (float,
+// dk x dk).  connectedComponentsWithStats, filter2D, floodFill and the scaled 8-bit conversions run in the real OpenCV.
+int ref_mouse_box_dd(unsigned char *side, int side_h, int n_cols, int threshold, int min_pixel_count, int min_pixel_visible, int conn,
+                     const int *zero, const float *disk, int dk, cv::shim_scale_fn scale, cv::shim_cc_fn cc, cv::shim_filter_u8_fn filt,
+                     cv::shim_flood_fn flood, double *bb_x) {
+    try {
+        LocoMouse_TM L;
+        L.N_COLS = (unsigned int)n_cols;
+        L.BB_SIDE_VIEW = cv::Rect(0, 0, n_cols, side_h);
+        L.SIDE_THRESHOLD = (unsigned int)threshold;
+        L.MIN_PIXEL_COUNT = (unsigned int)min_pixel_count;
+        L.LM_PARAMS.min_pixel_visible = min_pixel_visible;
+        L.LM_PARAMS.conn_comp_connectivity = conn;
+        L.ZERO_COL_PRE = zero[0];
+        L.ZERO_COL_POST = zero[1];
+        L.ZERO_ROW_PRE = zero[2];
+        L.ZERO_ROW_POST = zero[3];
+        L.DISK_FILTER = cv::Mat(dk, dk, CV_32F, (void *)disk, (size_t)dk * sizeof(float));
+        cv::shim_scale_callback() = scale;
+        cv::shim_cc_callback() = cc;
+        cv::shim_filter_u8_callback() = filt;
+        cv::shim_flood_callback() = flood;
+        cv::Mat I(side_h, n_cols, CV_8U, (void *)side, (size_t)n_cols);
+        L.computeMouseBox_DD(I, *bb_x);
+        return 0;
+    } catch (const std::exception &e) {
+        fprintf(stderr, "ref_mouse_box_dd: %s\n", e.what());
         return -1;
     }
 }

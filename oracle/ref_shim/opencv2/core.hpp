@@ -127,7 +127,7 @@ inline std::ostream &operator<<(std::ostream &o, const Rect_<T> &r) { return o <
 #define CV_64FC1 6
 #define CV_16U 2
 #define CV_16UC1 2
-enum { NORM_MINMAX = 32, THRESH_BINARY = 0, THRESH_BINARY_INV = 1, CV_REDUCE_SUM = 0, CV_REDUCE_MAX = 2, CMP_EQ = 0, CC_STAT_AREA = 4, BORDER_CONSTANT = 0 };
+enum { NORM_MINMAX = 32, THRESH_BINARY = 0, THRESH_BINARY_INV = 1, CV_REDUCE_SUM = 0, CV_REDUCE_MAX = 2, CMP_EQ = 0, CC_STAT_AREA = 4, BORDER_CONSTANT = 0, BORDER_REPLICATE = 1 };
 
 class Mat;
 // the one lazy expression the path relies on: alpha * A + beta, folded like cv::MatOp_AddEx
@@ -173,6 +173,11 @@ public:
         Mat out;
         convertTo(out, type_);
         dst = out;
+    }
+    Mat clone() const {
+        Mat out;
+        convertTo(out, type_);
+        return out;
     }
     Mat reshape(int /*cn*/, int /*rows*/) const { return *this; }  // the reference discards the result (class.cpp:1352)
     template <typename T>
@@ -398,7 +403,51 @@ inline int connectedComponentsWithStats(const Mat &img, Mat &labels, Mat &stats,
     stats = S;
     return n;
 }
-inline void filter2D(const Mat &src, Mat &dst, int /*CV_32F*/, const Mat &k, Point_<int> /*anchor*/, double /*delta*/, int /*border*/) {
+// 8-bit -> 8-bit filter2D with a float kernel (LocoMouse_TM::computeMouseBox_DD's disk filter, LocoMouse_TM.cpp:216) and
+// cv::floodFill (imfill, LocoMouse_TM.cpp:259) are ALGORITHMS too: both run in the REAL OpenCV through callbacks
+// (cv2.filter2D(src, CV_8U, kernel, anchor (-1,-1), delta 0, BORDER_REPLICATE); cv2.floodFill(img, None, (x, y), value)).
+typedef void (*shim_filter_u8_fn)(const uchar *src, uchar *dst, int rows, int cols, const float *kernel, int krows, int kcols);
+typedef void (*shim_flood_fn)(uchar *img, int rows, int cols, int x, int y, int value);
+inline shim_filter_u8_fn &shim_filter_u8_callback() { static shim_filter_u8_fn f = nullptr; return f; }
+inline shim_flood_fn &shim_flood_callback() { static shim_flood_fn f = nullptr; return f; }
+inline void floodFill(Mat &img, Point_<int> seed, double value) {
+    if (!shim_flood_callback()) throw std::runtime_error("floodFill: no callback installed");
+    std::vector<uchar> flat((size_t)img.rows * img.cols);
+    for (int r = 0; r < img.rows; ++r) std::memcpy(&flat[(size_t)r * img.cols], img.ptr<uchar>(r), (size_t)img.cols);
+    shim_flood_callback()(flat.data(), img.rows, img.cols, seed.x, seed.y, (int)value);
+    for (int r = 0; r < img.rows; ++r) std::memcpy(img.ptr<uchar>(r), &flat[(size_t)r * img.cols], (size_t)img.cols);
+}
+inline void bitwise_not(const Mat &src, Mat &dst) {  // 8-bit
+    Mat out(src.rows, src.cols, CV_8U);
+    for (int r = 0; r < src.rows; ++r)
+        for (int c = 0; c < src.cols; ++c) out.ptr<uchar>(r)[c] = (uchar)~src.ptr<uchar>(r)[c];
+    dst = out;
+}
+inline Mat operator|(const Mat &a, const Mat &b) {  // bitwise or of two 8-bit images
+    Mat out(a.rows, a.cols, CV_8U);
+    for (int r = 0; r < a.rows; ++r)
+        for (int c = 0; c < a.cols; ++c) out.ptr<uchar>(r)[c] = a.ptr<uchar>(r)[c] | b.ptr<uchar>(r)[c];
+    return out;
+}
+inline Mat &operator|=(Mat &a, const Mat &b) {  // in place
+    for (int r = 0; r < a.rows; ++r)
+        for (int c = 0; c < a.cols; ++c) a.ptr<uchar>(r)[c] |= b.ptr<uchar>(r)[c];
+    return a;
+}
+inline void filter2D(const Mat &src, Mat &dst, int ddepth, const Mat &k, Point_<int> /*anchor*/, double /*delta*/, int /*border*/) {
+    if (ddepth == CV_8U && src.type() == CV_8U && !k.empty() && (k.rows > 1 || k.cols > 1)) {
+        if (!shim_filter_u8_callback()) throw std::runtime_error("filter2D (8-bit): no callback installed");
+        std::vector<uchar> in((size_t)src.rows * src.cols), o8(in.size());
+        for (int r = 0; r < src.rows; ++r) std::memcpy(&in[(size_t)r * src.cols], src.ptr<uchar>(r), (size_t)src.cols);
+        std::vector<float> kk((size_t)k.rows * k.cols);
+        for (int r = 0; r < k.rows; ++r)
+            for (int c = 0; c < k.cols; ++c) kk[(size_t)r * k.cols + c] = k.type() == CV_64F ? (float)k.ptr<double>(r)[c] : k.ptr<float>(r)[c];
+        shim_filter_u8_callback()(in.data(), o8.data(), src.rows, src.cols, kk.data(), k.rows, k.cols);
+        Mat out(src.rows, src.cols, CV_8U);
+        for (int r = 0; r < src.rows; ++r) std::memcpy(out.ptr<uchar>(r), &o8[(size_t)r * src.cols], (size_t)src.cols);
+        dst = out;
+        return;
+    }
     if (!shim_filter_callback()) throw std::runtime_error("filter2D: no callback installed");
     Mat out(src.rows, src.cols, CV_32F);
     std::vector<float> flat((size_t)src.rows * src.cols);

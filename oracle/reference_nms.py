@@ -284,6 +284,56 @@ def mouse_box_de(side_view, threshold=255 * 0.05, min_count=10, margin=1.1):
     return float(bbx.value)
 
 
+_FILT8_FN = C.CFUNCTYPE(None, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int)
+_FLOOD_FN = C.CFUNCTYPE(None, C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
+
+
+def mouse_box_dd(side_view, disk, threshold=3, min_pixel_count=10, min_pixel_visible=1, conn=8, zero=(0, None, 0, None)):
+    """The reference's LocoMouse_TM::computeMouseBox_DD + bwAreaOpen + imfill (LocoMouse_TM.cpp:158-269) on a calibrated side
+    view, with LocoMouse::imadjust_default (LocoMouse_class.cpp:3244-3311).  zero = (ZERO_COL_PRE, ZERO_COL_POST,
+    ZERO_ROW_PRE, ZERO_ROW_POST), None = the image size (an empty band).  connectedComponentsWithStats, filter2D (8-bit,
+    BORDER_REPLICATE), floodFill and the scaled 8-bit conversions run in the REAL OpenCV (cv2).  Returns bb_x (double)."""
+    import cv2
+
+    L = lib()
+    img = np.array(side_view, dtype=np.uint8, order="C", copy=True)   # modified in place by the reference
+    rows, cols = img.shape
+    z = [int(zero[0]), cols if zero[1] is None else int(zero[1]), int(zero[2]), rows if zero[3] is None else int(zero[3])]
+    dk = np.ascontiguousarray(disk, np.float32)
+    assert dk.ndim == 2 and dk.shape[0] == dk.shape[1]
+
+    def scale(src, dst, r, c, alpha, beta):
+        a = np.ctypeslib.as_array(src, shape=(r, c))
+        np.ctypeslib.as_array(dst, shape=(r, c))[:] = cv2.convertScaleAbs(a, alpha=alpha, beta=beta)
+
+    def cc(im, r, c, connectivity, labels, areas, cap):
+        a = np.ctypeslib.as_array(im, shape=(r, c))
+        k, lab, stats, _ = cv2.connectedComponentsWithStats(a, connectivity=connectivity, ltype=cv2.CV_16U)
+        assert k <= cap
+        np.ctypeslib.as_array(labels, shape=(r, c))[:] = lab
+        np.ctypeslib.as_array(areas, shape=(cap,))[:k] = stats[:, cv2.CC_STAT_AREA]
+        return int(k)
+
+    def filt(src, dst, r, c, kern, kr, kc):
+        a = np.ascontiguousarray(np.ctypeslib.as_array(src, shape=(r, c)))
+        kk = np.ascontiguousarray(np.ctypeslib.as_array(kern, shape=(kr, kc)))
+        np.ctypeslib.as_array(dst, shape=(r, c))[:] = cv2.filter2D(a, cv2.CV_8U, kk, anchor=(-1, -1), delta=0, borderType=cv2.BORDER_REPLICATE)
+
+    def flood(im, r, c, x, y, value):
+        a = np.ascontiguousarray(np.ctypeslib.as_array(im, shape=(r, c)))
+        cv2.floodFill(a, None, (x, y), value)
+        np.ctypeslib.as_array(im, shape=(r, c))[:] = a
+
+    cbs = (_SCALE_FN(scale), _CC_FN(cc), _FILT8_FN(filt), _FLOOD_FN(flood))
+    bbx = C.c_double(0.0)
+    L.ref_mouse_box_dd.restype = C.c_int
+    rc = L.ref_mouse_box_dd(C.c_void_p(img.ctypes.data), rows, cols, int(threshold), int(min_pixel_count), int(min_pixel_visible), int(conn),
+                            (C.c_int * 4)(*z), C.c_void_p(dk.ctypes.data), dk.shape[0], *cbs, C.byref(bbx))
+    if rc != 0:
+        raise RuntimeError("the reference's computeMouseBox_DD threw")
+    return float(bbx.value)
+
+
 _MEDIAN_FN = C.CFUNCTYPE(None, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int)
 
 

@@ -36,4 +36,5 @@ for _ in range(args.iters):
     r = det.detect_batch(frames, bx, bs, bb, allow_overflow=True)
     print(det.last_timing())
 print("screen_active", det.info("screen_active"), "merged", det.info("screen2_merged"), "stacked", det.info("screen2_stacked"), "ms_screen", det.info("ms_screen"), "checksum", r.checksum())
+print("sparse_tasks(set0)", det.info("sparse_tasks"), "positives(set0)", det.info("positives"), "subbatch", det.info("subbatch"))
 print("flags", int((r.flags != 0).sum()), "n_bottom", r.n_bottom.mean(0), "n_side", r.n_side.mean(0))

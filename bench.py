@@ -554,7 +554,7 @@ def main():
 
         # throughput vs detection density: rho re-calibrated so that x0.25 / x1 / x4 of the default fraction of pixels score > 0
         try:
-            md = min(n, 4 * subb)
+            md = n   # the whole resident video: a short run would measure pipeline fill / drain, not the steady state
             dens = []
             for mult in (0.25, 1.0, 4.0):
                 tf = (0.012 * mult, 0.012 * mult, 0.02 * mult)

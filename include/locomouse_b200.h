@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LM_ABI_VERSION 4  /* 4: lm_bounding_box_base, lm_mouse_box_size; 2: lm_set_option, lm_get_info, lm_debug_nms, lm_bounding_box_tm_de, lm_moving_average; 3: lm_host_alloc / lm_host_free, lm_unary_costs / lm_pairwise_costs, options streams 1..4, screen_layout, screen_priority */
+#define LM_ABI_VERSION 5  /* 5: lm_bounding_box_tm; 4: lm_bounding_box_base, lm_mouse_box_size; 2: lm_set_option, lm_get_info, lm_debug_nms, lm_bounding_box_tm_de, lm_moving_average; 3: lm_host_alloc / lm_host_free, lm_unary_costs / lm_pairwise_costs, options streams 1..4, screen_layout, screen_priority */
 
 /* feature / view indices used in every [2] / [3] array below */
 enum { LM_PAW = 0, LM_SNOUT = 1, LM_TAIL = 2 };
@@ -221,6 +221,39 @@ int lm_bounding_box_base(lm_ctx *ctx, const uint8_t *frames, int frames_on_devic
 /* computeMouseBoxSize (LocoMouse_class.cpp:1481-1506) with medianvec / stdvec (1515-1556): size[3] = final width, bottom
  * height, side height = min(median + 3 std, max) per series.  The three arrays are sorted in place, as the reference's are. */
 int lm_mouse_box_size(double *bb_w, double *bb_hb, double *bb_hs, int64_t n, int32_t size[3]);
+
+/* Pass 1 of LocoMouse_TM: LocoMouse_TM::computeBoundingBox / computeMouseBox_DD / bwAreaOpen / imfill
+ * (LocoMouse_TM.cpp:115-269): per frame, the base-class readFrame; on the side view imadjust_default
+ * (LocoMouse_class.cpp:3244-3311); the four border bands set to zero; threshold(> bw_threshold_side -> 1); bwAreaOpen
+ * (connected components of conn_comp_connectivity with fewer than min_pixel_count pixels removed); filter2D with the
+ * DISK_FILTER matrix (8-bit result, anchor at the centre, BORDER_REPLICATE; float accumulation over the taps in row-major
+ * order, rounded half to even -- OpenCV's direct path, which it uses for kernels of fewer than 130 taps; larger kernels go
+ * through its DFT path, whose rounding at exact .5 ties is build-dependent); imfill (every pixel that a 4-connected flood
+ * fill from pixel (0, 0) does not reach becomes 255); the CV_32S column sums; firstLastOverT with min_pixel_visible;
+ * bb_x = the last qualifying column.  BB_Y_BOTTOM_POS = N_ROWS - 1 and BB_Y_SIDE_POS = 164 are constants of the method
+ * (LocoMouse_TM.cpp:141-142); the moving average over the video is lm_moving_average.
+ * sums_as_float: as for lm_bb_base_params -- 1 is the reference (firstLastOverT reads the integer sums through a float
+ * pointer: with min_pixel_visible >= 1 nothing ever qualifies and bb_x = -1 for every frame; with 0 everything does and
+ * bb_x = side_w - 1), 0 compares the integer sums themselves (the evident intent).
+ * The reference requires BB_SIDE_VIEW to span the image width (colRange(ZERO_COL_POST, N_COLS) on the side view,
+ * LocoMouse_TM.cpp:205): side_w != n_cols, zero_col_pre > zero_col_post-style inverted ranges and bands beyond the view are
+ * rejected with LM_ERR_INVALID where OpenCV would throw. */
+typedef struct {
+    int32_t side_x, side_y, side_w, side_h;   /* BB_SIDE_VIEW                                                        */
+    int32_t side_threshold;                   /* bw_threshold_side (SIDE_THRESHOLD, 0..255)                          */
+    int32_t min_pixel_count;                  /* min_pixel_count (MIN_PIXEL_COUNT >= 1): bwAreaOpen                  */
+    int32_t min_pixel_visible;                /* LM_PARAMS.min_pixel_visible: firstLastOverT threshold               */
+    int32_t zero_col_pre, zero_col_post;      /* columns [0, pre) and [post, n_cols) of the side view are zeroed     */
+    int32_t zero_row_pre, zero_row_post;      /* rows [0, pre) and [post, side_h)                                    */
+    int32_t sums_as_float;                    /* 1: as the reference (see above), 0: integer sums                    */
+    int32_t disk_size;                        /* DISK_FILTER is disk_size x disk_size (diskfilter.yml "H")           */
+    int32_t reserved;
+    const float *disk;                        /* host memory, row-major                                              */
+} lm_bb_tm_params;
+/* bb_x_raw[n]: per-frame, unsmoothed box position; lims (optional, may be NULL): [n][2] first / last qualifying column.
+ * Needs lm_configure (its conn_comp_connectivity is used), lm_set_background and lm_set_calibration. */
+int lm_bounding_box_tm(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, int64_t n, const lm_bb_tm_params *p,
+                       double *bb_x_raw, int32_t *lims);
 
 /* cost builders of the host tracker --------------------------------------------------------------- *
  * LocoMouse::computeUnaryCostsBottom / unaryCostBox (LocoMouse_class.cpp:873-894, 1909-1952) and

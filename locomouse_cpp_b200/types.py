@@ -87,6 +87,30 @@ def bb_base_params(cfg, side_h: int = 165, **kw) -> lm_bb_base_params:
     return lm_bb_base_params(**d)
 
 
+class lm_bb_tm_params(C.Structure):
+    _fields_ = [("side_x", C.c_int32), ("side_y", C.c_int32), ("side_w", C.c_int32), ("side_h", C.c_int32),
+                ("side_threshold", C.c_int32), ("min_pixel_count", C.c_int32), ("min_pixel_visible", C.c_int32),
+                ("zero_col_pre", C.c_int32), ("zero_col_post", C.c_int32), ("zero_row_pre", C.c_int32), ("zero_row_post", C.c_int32),
+                ("sums_as_float", C.c_int32), ("disk_size", C.c_int32), ("reserved", C.c_int32), ("disk", C.POINTER(C.c_float))]
+
+
+def bb_tm_params(cfg, disk, side_h: int = 165, **kw) -> lm_bb_tm_params:
+    """LocoMouse_TM pass-1 parameters (LocoMouse_TM.cpp:44-113 reads them from the configuration file; DISK_FILTER from
+    diskfilter.yml) for a side view that spans the upper `side_h` rows.  `disk` (square float32 matrix) is kept alive on the
+    returned structure.  sums_as_float = 1 is the reference's behaviour (see include/locomouse_b200.h)."""
+    import numpy as np
+
+    dk = np.ascontiguousarray(disk, np.float32)
+    assert dk.ndim == 2 and dk.shape[0] == dk.shape[1]
+    d = dict(side_x=0, side_y=0, side_w=cfg.n_cols, side_h=side_h, side_threshold=3, min_pixel_count=10, min_pixel_visible=1,
+             zero_col_pre=0, zero_col_post=cfg.n_cols, zero_row_pre=0, zero_row_post=side_h, sums_as_float=1, disk_size=dk.shape[0], reserved=0)
+    d.update(kw)
+    p = lm_bb_tm_params(**d)
+    p.disk = dk.ctypes.data_as(C.POINTER(C.c_float))
+    p._keep = dk
+    return p
+
+
 class lm_location_prior(C.Structure):
     _fields_ = [("pos_x", C.c_double), ("pos_y", C.c_double), ("max_distance", C.c_double), ("area_x", C.c_double),
                 ("area_y", C.c_double), ("area_w", C.c_double), ("area_h", C.c_double)]

@@ -937,6 +937,143 @@ void mouse_box_base(const uint8_t *I, int n_rows, int n_cols, int conn, const lm
     if (lims) std::memcpy(lims, fl, sizeof fl);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pass 1 of LocoMouse_TM — computeMouseBox_DD / bwAreaOpen / imfill (LocoMouse_TM.cpp:158-269) on the image the base
+// readFrame produced.  Stage by stage (each stage is compared with what the reference's own compiled lines hand to
+// OpenCV, tests/test_oracle_pass1_tm.py):
+//  * imadjust_default on the side view (a 256-entry table, as for LocoMouse_TM_DE), four bands zeroed (203-206);
+//  * threshold(I, ., SIDE_THRESHOLD, 1, THRESH_BINARY): 1 where the value is > the threshold (210);
+//  * bwAreaOpen (158-187): components (4- / 8-connected) with area >= MIN_PIXEL_COUNT kept (255 / 255 -> 1); all zero when
+//    there is no foreground label;
+//  * filter2D(., CV_8UC1, DISK_FILTER, (-1,-1), 0, BORDER_REPLICATE) (216): anchor = size / 2, clamped coordinates, float
+//    accumulation over the kernel in row-major order, saturate_cast<uchar> = round half to even (OpenCV's direct path);
+//  * imfill (252-269): floodFill(copy, (0,0), 255) with the default zero tolerances and 4-connectivity reaches the pixels
+//    connected to (0,0) through pixels of the same value; out = in | ~filled: a reached pixel keeps its value, every other
+//    pixel becomes 255;
+//  * reduce(SUM over rows, CV_32S) (221), firstLastOverT<int>(Row_side, N_COLS, ., min_pixel_visible) with the float read of
+//    the integer sums (class.hpp:417) when sums_as_float; bb_x = last.
+// ---------------------------------------------------------------------------------------------
+bool tm_params_ok(const lm_bb_tm_params *p, int n_rows, int n_cols) {
+    return p && p->disk && p->disk_size >= 1 && p->disk_size <= 63 && p->side_x >= 0 && p->side_y >= 0 && p->side_h > 0 &&
+           p->side_x == 0 && p->side_w == n_cols &&  // colRange(ZERO_COL_POST, N_COLS) on the side view (TM.cpp:205)
+           p->side_y + p->side_h <= n_rows && p->side_threshold >= 0 && p->side_threshold <= 255 && p->min_pixel_count >= 1 &&
+           p->min_pixel_visible >= 0 && p->zero_col_pre >= 0 && p->zero_col_pre <= p->side_w && p->zero_col_post >= 0 &&
+           p->zero_col_post <= n_cols && p->zero_row_pre >= 0 && p->zero_row_pre <= p->side_h && p->zero_row_post >= 0 &&
+           p->zero_row_post <= p->side_h;
+}
+
+// filter2D(src, dst, CV_8UC1, kernel, (-1,-1), 0, BORDER_REPLICATE) on 8-bit data, OpenCV's direct path
+void filter2d_u8_replicate(const uint8_t *src, int H, int W, const float *kern, int K, uint8_t *dst) {
+    const int an = K / 2;
+    for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c) {
+            float s = 0.f;
+            for (int j = 0; j < K; ++j) {
+                const int rr = std::min(H - 1, std::max(0, r + j - an));
+                for (int i = 0; i < K; ++i) {
+                    const int cc = std::min(W - 1, std::max(0, c + i - an));
+                    s += kern[j * K + i] * (float)src[(size_t)rr * W + cc];   // -ffp-contract=off: multiply, then add
+                }
+            }
+            dst[(size_t)r * W + c] = sat_u8_rint(s);
+        }
+}
+
+struct TmStages {  // optional taps (tests)
+    uint8_t *adjusted = nullptr, *binary = nullptr, *opened = nullptr, *filtered = nullptr;
+    int32_t *row_sums = nullptr;
+};
+
+void mouse_box_tm(const uint8_t *I, int n_cols, int conn, const lm_bb_tm_params &p, double *bb_x, int32_t *lims, const TmStages &T) {
+    const int W = p.side_w, H = p.side_h;
+    const size_t N = (size_t)W * H;
+    std::vector<uint8_t> a(N), b(N), o(N), f(N);
+    uint32_t hist[256] = {0};
+    for (int r = 0; r < H; ++r) {
+        const uint8_t *row = I + (int64_t)(p.side_y + r) * n_cols + p.side_x;
+        for (int x = 0; x < W; ++x) ++hist[row[x]];
+    }
+    uint8_t lut[256];
+    imadjust_default_lut(hist, lut, nullptr);
+    for (int r = 0; r < H; ++r) {
+        const uint8_t *row = I + (int64_t)(p.side_y + r) * n_cols + p.side_x;
+        const bool rz = r < p.zero_row_pre || r >= p.zero_row_post;
+        for (int x = 0; x < W; ++x) {
+            const bool z = rz || x < p.zero_col_pre || x >= p.zero_col_post;
+            a[(size_t)r * W + x] = z ? 0 : lut[row[x]];
+            b[(size_t)r * W + x] = a[(size_t)r * W + x] > p.side_threshold ? 1 : 0;
+        }
+    }
+    // bwAreaOpen
+    {
+        std::vector<int32_t> label(N, -1), stack;
+        std::vector<int64_t> area;
+        for (size_t p0 = 0; p0 < N; ++p0) {
+            if (!b[p0] || label[p0] >= 0) continue;
+            const int32_t lab = (int32_t)area.size();
+            area.push_back(0);
+            stack.assign(1, (int32_t)p0);
+            label[p0] = lab;
+            while (!stack.empty()) {
+                const int32_t q = stack.back();
+                stack.pop_back();
+                ++area[lab];
+                const int r = q / W, c = q % W;
+                for (int dr = -1; dr <= 1; ++dr)
+                    for (int dc = -1; dc <= 1; ++dc) {
+                        if ((!dr && !dc) || (conn != 8 && dr && dc)) continue;
+                        const int rr = r + dr, cc = c + dc;
+                        if (rr < 0 || rr >= H || cc < 0 || cc >= W) continue;
+                        const size_t t = (size_t)rr * W + cc;
+                        if (b[t] && label[t] < 0) {
+                            label[t] = lab;
+                            stack.push_back((int32_t)t);
+                        }
+                    }
+            }
+        }
+        for (size_t q = 0; q < N; ++q) o[q] = (label[q] >= 0 && (uint64_t)area[label[q]] >= (uint64_t)(uint32_t)p.min_pixel_count) ? 1 : 0;
+    }
+    filter2d_u8_replicate(o.data(), H, W, p.disk, p.disk_size, f.data());
+    // imfill + column sums
+    std::vector<int32_t> sums(W, 0);
+    {
+        std::vector<uint8_t> reached(N, 0);
+        std::vector<int32_t> stack(1, 0);
+        const uint8_t seed = f[0];
+        reached[0] = 1;
+        while (!stack.empty()) {
+            const int32_t q = stack.back();
+            stack.pop_back();
+            const int r = q / W, c = q % W;
+            const int nr[4] = {r - 1, r + 1, r, r}, nc[4] = {c, c, c - 1, c + 1};
+            for (int d = 0; d < 4; ++d) {
+                if (nr[d] < 0 || nr[d] >= H || nc[d] < 0 || nc[d] >= W) continue;
+                const size_t t = (size_t)nr[d] * W + nc[d];
+                if (!reached[t] && f[t] == seed) {
+                    reached[t] = 1;
+                    stack.push_back((int32_t)t);
+                }
+            }
+        }
+        for (int r = 0; r < H; ++r)
+            for (int c = 0; c < W; ++c) sums[c] += reached[(size_t)r * W + c] ? (int32_t)seed : 255;
+    }
+    int32_t fl[2];
+    // firstLastOverT(Row_side, N_COLS, ...): N_COLS == side_w (checked)
+    first_last_i32(sums.data(), (uint32_t)W, p.min_pixel_visible, p.sums_as_float != 0, fl);
+    if (lims) {
+        lims[0] = fl[0];
+        lims[1] = fl[1];
+    }
+    *bb_x = (double)fl[1];
+    if (T.adjusted) std::memcpy(T.adjusted, a.data(), N);
+    if (T.binary) std::memcpy(T.binary, b.data(), N);
+    if (T.opened) std::memcpy(T.opened, o.data(), N);
+    if (T.filtered) std::memcpy(T.filtered, f.data(), N);
+    if (T.row_sums) std::memcpy(T.row_sums, sums.data(), (size_t)W * 4);
+}
+
 // medianvec / stdvec / computeMouseBoxSize (class.cpp:1481-1556).  medianvec sorts its argument; for an odd count it
 // returns the element BELOW the middle (v[N/2 - 1]), as written there.  stdvec runs on the sorted data.
 double medianvec(std::vector<double> &v) {
@@ -1020,6 +1157,34 @@ int lmo_bounding_box_base(const lm_config *cfg, const uint8_t *bkg, const int32_
     for (int64_t f = 0; f < n; ++f) {
         preprocess(base, bkg, calib, frames + f * fsz, I.data(), nullptr);
         mouse_box_base(I.data(), cfg->n_rows, cfg->n_cols, cfg->conn, *p, box + f * 6, lims ? lims + f * 8 : nullptr);
+    }
+    return LM_OK;
+}
+void lmo_filter2d_u8(const uint8_t *src, int32_t rows, int32_t cols, const float *kernel, int32_t k, uint8_t *dst) {
+    filter2d_u8_replicate(src, rows, cols, kernel, k, dst);
+}
+int lmo_mouse_box_tm(const uint8_t *I, int32_t n_rows, int32_t n_cols, int32_t conn, const lm_bb_tm_params *p, double *bb_x, int32_t *lims,
+                     uint8_t *adjusted, uint8_t *binary, uint8_t *opened, uint8_t *filtered, int32_t *row_sums) {
+    if (!I || !bb_x || !tm_params_ok(p, n_rows, n_cols) || (conn != 4 && conn != 8)) return LM_ERR_INVALID;
+    TmStages T;
+    T.adjusted = adjusted;
+    T.binary = binary;
+    T.opened = opened;
+    T.filtered = filtered;
+    T.row_sums = row_sums;
+    mouse_box_tm(I, n_cols, conn, *p, bb_x, lims, T);
+    return LM_OK;
+}
+int lmo_bounding_box_tm(const lm_config *cfg, const uint8_t *bkg, const int32_t *calib, const uint8_t *frames, int64_t n,
+                        const lm_bb_tm_params *p, double *bb_x, int32_t *lims) {
+    if (!cfg || !bkg || !calib || !frames || !bb_x || n < 0 || !tm_params_ok(p, cfg->n_rows, cfg->n_cols)) return LM_ERR_INVALID;
+    lm_config base = *cfg;
+    base.imadjust = 0;  // LocoMouse::readFrame(I), LocoMouse_TM.cpp:138
+    std::vector<uint8_t> I((size_t)cfg->n_rows * cfg->n_cols);
+    const int64_t fsz = (int64_t)cfg->vid_rows * cfg->vid_cols;
+    for (int64_t f = 0; f < n; ++f) {
+        preprocess(base, bkg, calib, frames + f * fsz, I.data(), nullptr);
+        mouse_box_tm(I.data(), cfg->n_cols, cfg->conn, *p, bb_x + f, lims ? lims + 2 * f : nullptr, TmStages());
     }
     return LM_OK;
 }

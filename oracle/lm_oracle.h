@@ -89,6 +89,13 @@ int lmo_bounding_box_base(const lm_config *cfg, const uint8_t *bkg, const int32_
 /* the same from an already pre-processed image I [n_rows][n_cols] (what the reference-compiled checker is fed) */
 int lmo_mouse_box_base(const uint8_t *I, int32_t n_rows, int32_t n_cols, int32_t conn, const lm_bb_base_params *p, double *box, int32_t *lims);
 /* computeMouseBoxSize + medianvec + stdvec (LocoMouse_class.cpp:1481-1556); sorts the inputs like the reference */
+/* LocoMouse_TM pass 1 (LocoMouse_TM.cpp:115-269); lmo_mouse_box_tm works on one calibrated image and can hand back every
+ * intermediate image (any of the five output pointers may be NULL) */
+void lmo_filter2d_u8(const uint8_t *src, int32_t rows, int32_t cols, const float *kernel, int32_t k, uint8_t *dst);
+int lmo_mouse_box_tm(const uint8_t *I, int32_t n_rows, int32_t n_cols, int32_t conn, const lm_bb_tm_params *p, double *bb_x, int32_t *lims,
+                     uint8_t *adjusted, uint8_t *binary, uint8_t *opened, uint8_t *filtered, int32_t *row_sums);
+int lmo_bounding_box_tm(const lm_config *cfg, const uint8_t *bkg, const int32_t *calib, const uint8_t *frames, int64_t n,
+                        const lm_bb_tm_params *p, double *bb_x, int32_t *lims);
 void lmo_mouse_box_size(double *w, double *hb, double *hs, int64_t n, int32_t size[3]);
 /* ---- cost builders ----------------------------------------------------------------- */
 /* unaryCostBox (LocoMouse_class.cpp:1909-1952): out = MyMat(n x n_priors), column-major */

@@ -239,6 +239,65 @@ def bounding_box_base(cfg: Config, bkg, calib, frames, params):
     return box, lims
 
 
+def bounding_box_tm(cfg: Config, bkg, calib, frames, params):
+    """Per-frame output of LocoMouse_TM::computeMouseBox_DD after the base readFrame (LocoMouse_TM.cpp:115-269):
+    (raw bb_x float64[n], lims int32[n, 2])."""
+    L = lib()
+    frames = _u8(frames)
+    n = frames.shape[0]
+    c = cfg.to_c()
+    raw = np.zeros(n, np.float64)
+    lims = np.zeros((n, 2), np.int32)
+    L.lmo_bounding_box_tm.restype = C.c_int
+    rc = L.lmo_bounding_box_tm(C.byref(c), _p(_u8(bkg), _u8p), _p(np.ascontiguousarray(calib, np.int32), _i32p), _p(frames, _u8p),
+                               C.c_int64(n), C.byref(params), raw.ctypes.data_as(_f64p), lims.ctypes.data_as(_i32p))
+    if rc != 0:
+        raise ValueError(f"lmo_bounding_box_tm failed ({rc})")
+    return raw, lims
+
+
+def mouse_box_tm(side_view, disk, threshold=3, min_pixel_count=10, min_pixel_visible=1, conn=8, zero=(0, None, 0, None), sums_as_float=1):
+    """computeMouseBox_DD on a calibrated side view (the whole image IS the side view) -> (bb_x, lims int32[2], stages) with
+    stages = adjusted / binary / opened / filtered images and row_sums, as oracle/reference_nms.mouse_box_dd reports them."""
+    from locomouse_cpp_b200.types import lm_bb_tm_params
+
+    L = lib()
+    I = _u8(side_view)
+    rows, cols = I.shape
+    dk = np.ascontiguousarray(disk, np.float32)
+    z = [int(zero[0]), cols if zero[1] is None else int(zero[1]), int(zero[2]), rows if zero[3] is None else int(zero[3])]
+    p = lm_bb_tm_params(side_x=0, side_y=0, side_w=cols, side_h=rows, side_threshold=int(threshold), min_pixel_count=int(min_pixel_count),
+                        min_pixel_visible=int(min_pixel_visible), zero_col_pre=z[0], zero_col_post=z[1], zero_row_pre=z[2], zero_row_post=z[3],
+                        sums_as_float=int(sums_as_float), disk_size=dk.shape[0], reserved=0)
+    p.disk = dk.ctypes.data_as(C.POINTER(C.c_float))
+    st = {k: np.zeros((rows, cols), np.uint8) for k in ("adjusted", "binary", "opened", "filtered")}
+    st["row_sums"] = np.zeros(cols, np.int32)
+    bbx = C.c_double(0.0)
+    lims = np.zeros(2, np.int32)
+    L.lmo_mouse_box_tm.restype = C.c_int
+    rc = L.lmo_mouse_box_tm(_p(I, _u8p), rows, cols, int(conn), C.byref(p), C.byref(bbx), lims.ctypes.data_as(_i32p),
+                            _p(st["adjusted"], _u8p), _p(st["binary"], _u8p), _p(st["opened"], _u8p), _p(st["filtered"], _u8p),
+                            st["row_sums"].ctypes.data_as(_i32p))
+    if rc != 0:
+        raise ValueError(f"lmo_mouse_box_tm failed ({rc})")
+    return float(bbx.value), lims, st
+
+
+def filter2d_u8(image, kernel):
+    """8-bit -> 8-bit filter2D, BORDER_REPLICATE, as the oracle's TM pass 1 evaluates it (the "filtered" stage with every other
+    stage made transparent: threshold 0 on a 0 / 1 image, min_pixel_count 1 keeps everything)."""
+    img = _u8(image)
+    assert img.max() <= 1
+    # imadjust_default would rescale the image: run the stages from "opened" on by feeding a binary image whose histogram maps
+    # to itself is not possible in general, so the filter is evaluated through the dedicated entry point
+    L = lib()
+    dk = np.ascontiguousarray(kernel, np.float32)
+    out = np.zeros_like(img)
+    L.lmo_filter2d_u8.restype = None
+    L.lmo_filter2d_u8(_p(img, _u8p), img.shape[0], img.shape[1], dk.ctypes.data_as(C.POINTER(C.c_float)), dk.shape[0], _p(out, _u8p))
+    return out
+
+
 def mouse_box_base(image, conn, params):
     """computeMouseBox on an already pre-processed calibrated image -> (box float64[6], lims int32[4, 2])."""
     L = lib()

@@ -340,11 +340,11 @@ int ref_mouse_box_de(unsigned char *side, int side_h, int n_cols, double thresho
 }
 
 // LocoMouse_TM::computeMouseBox_DD on a calibrated side view (u8, side_h x n_cols, modified in place as the reference does):
-// returns bb_x.  zero[4] = ZERO_COL_PRE, ZERO_COL_POST, ZERO_ROW_PRE, ZERO_ROW_POST; disk: the DISK_FILTER matrix (float,
+// returns bb_x and (optional) row_sums[n_cols].  zero[4] = ZERO_COL_PRE, ZERO_COL_POST, ZERO_ROW_PRE, ZERO_ROW_POST; disk: the DISK_FILTER matrix (float,
 // dk x dk).  connectedComponentsWithStats, filter2D, floodFill and the scaled 8-bit conversions run in the real OpenCV.
 int ref_mouse_box_dd(unsigned char *side, int side_h, int n_cols, int threshold, int min_pixel_count, int min_pixel_visible, int conn,
                      const int *zero, const float *disk, int dk, cv::shim_scale_fn scale, cv::shim_cc_fn cc, cv::shim_filter_u8_fn filt,
-                     cv::shim_flood_fn flood, double *bb_x) {
+                     cv::shim_flood_fn flood, double *bb_x, int *row_sums) {
     try {
         LocoMouse_TM L;
         L.N_COLS = (unsigned int)n_cols;
@@ -364,6 +364,10 @@ int ref_mouse_box_dd(unsigned char *side, int side_h, int n_cols, int threshold,
         cv::shim_flood_callback() = flood;
         cv::Mat I(side_h, n_cols, CV_8U, (void *)side, (size_t)n_cols);
         L.computeMouseBox_DD(I, *bb_x);
+        if (row_sums) {  // Row_side, the CV_32S column sums firstLastOverT was handed (LocoMouse_TM.cpp:223)
+            const cv::Mat &R = cv::shim_last_reduce_i32();
+            for (int c = 0; c < n_cols && c < R.cols; ++c) row_sums[c] = R.ptr<int>(0)[c];
+        }
         return 0;
     } catch (const std::exception &e) {
         fprintf(stderr, "ref_mouse_box_dd: %s\n", e.what());

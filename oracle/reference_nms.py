@@ -292,7 +292,10 @@ def mouse_box_dd(side_view, disk, threshold=3, min_pixel_count=10, min_pixel_vis
     """The reference's LocoMouse_TM::computeMouseBox_DD + bwAreaOpen + imfill (LocoMouse_TM.cpp:158-269) on a calibrated side
     view, with LocoMouse::imadjust_default (LocoMouse_class.cpp:3244-3311).  zero = (ZERO_COL_PRE, ZERO_COL_POST,
     ZERO_ROW_PRE, ZERO_ROW_POST), None = the image size (an empty band).  connectedComponentsWithStats, filter2D (8-bit,
-    BORDER_REPLICATE), floodFill and the scaled 8-bit conversions run in the REAL OpenCV (cv2).  Returns bb_x (double)."""
+    BORDER_REPLICATE), floodFill and the scaled 8-bit conversions run in the REAL OpenCV (cv2).  Returns (bb_x, stages):
+    stages holds what the reference's code handed to OpenCV on the way -- "adjusted" (I_SIDE after imadjust_default and the
+    zeroed bands), "binary" (the labelling's input), "opened" (the filter's input, after bwAreaOpen), "filtered" (the flood
+    fill's input) -- and "row_sums" (the CV_32S column sums firstLastOverT reads)."""
     import cv2
 
     L = lib()
@@ -306,8 +309,11 @@ def mouse_box_dd(side_view, disk, threshold=3, min_pixel_count=10, min_pixel_vis
         a = np.ctypeslib.as_array(src, shape=(r, c))
         np.ctypeslib.as_array(dst, shape=(r, c))[:] = cv2.convertScaleAbs(a, alpha=alpha, beta=beta)
 
+    stages = {}
+
     def cc(im, r, c, connectivity, labels, areas, cap):
         a = np.ctypeslib.as_array(im, shape=(r, c))
+        stages["binary"] = np.array(a, copy=True)
         k, lab, stats, _ = cv2.connectedComponentsWithStats(a, connectivity=connectivity, ltype=cv2.CV_16U)
         assert k <= cap
         np.ctypeslib.as_array(labels, shape=(r, c))[:] = lab
@@ -316,22 +322,27 @@ def mouse_box_dd(side_view, disk, threshold=3, min_pixel_count=10, min_pixel_vis
 
     def filt(src, dst, r, c, kern, kr, kc):
         a = np.ascontiguousarray(np.ctypeslib.as_array(src, shape=(r, c)))
+        stages["opened"] = np.array(a, copy=True)
         kk = np.ascontiguousarray(np.ctypeslib.as_array(kern, shape=(kr, kc)))
         np.ctypeslib.as_array(dst, shape=(r, c))[:] = cv2.filter2D(a, cv2.CV_8U, kk, anchor=(-1, -1), delta=0, borderType=cv2.BORDER_REPLICATE)
 
     def flood(im, r, c, x, y, value):
         a = np.ascontiguousarray(np.ctypeslib.as_array(im, shape=(r, c)))
+        stages["filtered"] = np.array(a, copy=True)
         cv2.floodFill(a, None, (x, y), value)
         np.ctypeslib.as_array(im, shape=(r, c))[:] = a
 
     cbs = (_SCALE_FN(scale), _CC_FN(cc), _FILT8_FN(filt), _FLOOD_FN(flood))
     bbx = C.c_double(0.0)
+    sums = np.zeros(cols, np.int32)
     L.ref_mouse_box_dd.restype = C.c_int
     rc = L.ref_mouse_box_dd(C.c_void_p(img.ctypes.data), rows, cols, int(threshold), int(min_pixel_count), int(min_pixel_visible), int(conn),
-                            (C.c_int * 4)(*z), C.c_void_p(dk.ctypes.data), dk.shape[0], *cbs, C.byref(bbx))
+                            (C.c_int * 4)(*z), C.c_void_p(dk.ctypes.data), dk.shape[0], *cbs, C.byref(bbx), C.c_void_p(sums.ctypes.data))
     if rc != 0:
         raise RuntimeError("the reference's computeMouseBox_DD threw")
-    return float(bbx.value)
+    stages["adjusted"] = img
+    stages["row_sums"] = sums
+    return float(bbx.value), stages
 
 
 _MEDIAN_FN = C.CFUNCTYPE(None, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int)

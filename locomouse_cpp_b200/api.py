@@ -26,7 +26,7 @@ _lib = None
 EXPORTS = ("lm_abi_version", "lm_create", "lm_destroy", "lm_last_error", "lm_configure", "lm_set_model",
            "lm_set_background", "lm_set_calibration", "lm_get_geometry", "lm_detect_batch", "lm_last_timing",
            "lm_debug_fetch", "lm_set_option", "lm_get_info", "lm_debug_nms", "lm_bounding_box_tm_de", "lm_moving_average",
-           "lm_host_alloc", "lm_host_free", "lm_unary_costs", "lm_pairwise_costs", "lm_bounding_box_base", "lm_mouse_box_size")
+           "lm_host_alloc", "lm_host_free", "lm_unary_costs", "lm_pairwise_costs", "lm_bounding_box_base", "lm_mouse_box_size", "lm_bounding_box_tm")
 
 
 def _pinned_zeros(shape, dtype):
@@ -92,6 +92,8 @@ def load_library():
     L.lm_pairwise_costs.argtypes = [vp, C.POINTER(lm_results), i64, i32, vp, vp, vp, vp, vp, i64, vp]
     L.lm_bounding_box_base.restype = C.c_int
     L.lm_bounding_box_base.argtypes = [vp, vp, i32, i64, vp, vp, vp]
+    L.lm_bounding_box_tm.restype = C.c_int
+    L.lm_bounding_box_tm.argtypes = [vp, vp, i32, i64, vp, vp, vp]
     L.lm_mouse_box_size.restype = C.c_int
     L.lm_mouse_box_size.argtypes = [vp, vp, vp, i64, vp]
     L.lm_host_alloc.restype = C.c_int
@@ -224,6 +226,15 @@ class Detector:
         lims = np.zeros((n, 4, 2), np.int32)
         self._check(self._L.lm_bounding_box_base(self._ctx, ptr, int(on_dev), n, C.addressof(p), box.ctypes.data, lims.ctypes.data))
         return box, lims
+
+    def bounding_box_tm(self, frames, params):
+        """Pass 1 of LocoMouse_TM, per frame (LocoMouse_TM::computeMouseBox_DD after the base readFrame, LocoMouse_TM.cpp:115-269):
+        (raw bb_x float64[n], lims int32[n, 2]).  params: types.bb_tm_params(cfg, disk, ...)."""
+        ptr, n, on_dev, keep = _frames_ptr(frames, self.cfg, self.device)
+        raw = np.zeros(n, np.float64)
+        lims = np.zeros((n, 2), np.int32)
+        self._check(self._L.lm_bounding_box_tm(self._ctx, ptr, int(on_dev), n, C.addressof(params), raw.ctypes.data, lims.ctypes.data))
+        return raw, lims
 
     def mouse_box_size(self, w, hb, hs):
         """computeMouseBoxSize (LocoMouse_class.cpp:1481-1506) -> (width, bottom height, side height)."""

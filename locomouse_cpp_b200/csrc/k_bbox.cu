@@ -181,15 +181,7 @@ __global__ void __launch_bounds__(256) k_bb_cols(const __grid_constant__ BBoxDev
 
 }  // namespace
 
-// b: frames / bkg / calib / minmax / lut / n_cols / flip / B filled in by the caller (imadjust must be 0)
-int lm_launch_bbox_tm_de(const LmBatch &b, const lm_bb_de_params &p, uint32_t *hist, uint8_t *pred, double *bb_x, int32_t *lims,
-                         cudaStream_t s) {
-    int launches = 0;
-    if (cudaMemsetAsync(b.minmax, 0, (size_t)(b.B + 1) * 2 * sizeof(int32_t), s) != cudaSuccess) return -1;
-    if (cudaMemsetAsync(hist, 0, (size_t)b.B * 256 * sizeof(uint32_t), s) != cudaSuccess) return -1;
-    int nl = lm_launch_minmax(b, s);
-    if (nl < 0) return -1;
-    launches += nl;
+static BBoxDev bbox_dev(const LmBatch &b, const lm_bb_de_params &p, uint32_t *hist, uint8_t *pred, double *bb_x, int32_t *lims) {
     BBoxDev P{};
     P.frames = b.frames;
     P.frame_bytes = b.frame_bytes;
@@ -204,12 +196,35 @@ int lm_launch_bbox_tm_de(const LmBatch &b, const lm_bb_de_params &p, uint32_t *h
     P.pred = pred;
     P.bb_x = bb_x;
     P.lims = lims;
+    return P;
+}
+
+// The front end LocoMouse_TM_DE and LocoMouse_TM share: per-frame normalisation LUT, side-view histogram, imadjust_default
+// and the threshold, folded into pred[f][d] (d = raw difference).  p: the side view rectangle and the threshold are used.
+int lm_launch_bbox_pred(const LmBatch &b, const lm_bb_de_params &p, uint32_t *hist, uint8_t *pred, cudaStream_t s) {
+    int launches = 0;
+    if (cudaMemsetAsync(b.minmax, 0, (size_t)(b.B + 1) * 2 * sizeof(int32_t), s) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(hist, 0, (size_t)b.B * 256 * sizeof(uint32_t), s) != cudaSuccess) return -1;
+    int nl = lm_launch_minmax(b, s);
+    if (nl < 0) return -1;
+    launches += nl;
+    const BBoxDev P = bbox_dev(b, p, hist, pred, nullptr, nullptr);
     const int npx = p.side_w * p.side_h;
     int gx = (npx + 256 * 16 - 1) / (256 * 16);
     gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
     k_bb_hist<<<dim3(gx, b.B), 256, 0, s>>>(P);
     k_bb_pred<<<b.B, 256, 0, s>>>(P);
+    launches += 2;
+    return cudaGetLastError() == cudaSuccess ? launches : -1;
+}
+
+// b: frames / bkg / calib / minmax / lut / n_cols / flip / B filled in by the caller (imadjust must be 0)
+int lm_launch_bbox_tm_de(const LmBatch &b, const lm_bb_de_params &p, uint32_t *hist, uint8_t *pred, double *bb_x, int32_t *lims,
+                         cudaStream_t s) {
+    int launches = lm_launch_bbox_pred(b, p, hist, pred, s);
+    if (launches < 0) return -1;
+    const BBoxDev P = bbox_dev(b, p, hist, pred, bb_x, lims);
     k_bb_cols<<<b.B, 256, 0, s>>>(P);
-    launches += 3;
+    launches += 1;
     return cudaGetLastError() == cudaSuccess ? launches : -1;
 }

@@ -1270,6 +1270,88 @@ int lm_bounding_box_base(lm_ctx *ctx, const uint8_t *frames, int frames_on_devic
     return LM_OK;
 }
 
+// Pass 1 of LocoMouse_TM, per frame (LocoMouse_TM.cpp:115-269); see include/locomouse_b200.h.
+int lm_bounding_box_tm(lm_ctx *ctx, const uint8_t *frames, int frames_on_device, int64_t n, const lm_bb_tm_params *p, double *bb_x_raw,
+                       int32_t *lims) {
+    if (!ctx) return LM_ERR_INVALID;
+    if (!ctx->configured || !ctx->bkg_set || !ctx->calib_set)
+        return fail(ctx, LM_ERR_STATE, "lm_bounding_box_tm needs lm_configure, lm_set_background and lm_set_calibration first");
+    if (n < 0) return fail(ctx, LM_ERR_INVALID, "negative frame count");
+    if (n == 0) return LM_OK;
+    if (!frames || !p || !bb_x_raw || !p->disk) return fail(ctx, LM_ERR_INVALID, "null argument");
+    const lm_config &k = ctx->cfg;
+    // what the reference's own checks and OpenCV's range assertions would reject (LocoMouse_TM.cpp:20-36, 203-206)
+    if (p->side_x != 0 || p->side_w != k.n_cols || p->side_y < 0 || p->side_h <= 0 || p->side_y + p->side_h > k.n_rows)
+        return fail(ctx, LM_ERR_INVALID, "the side view must span the image width and lie inside the calibrated image");
+    if (p->side_threshold < 0 || p->side_threshold > 255) return fail(ctx, LM_ERR_INVALID, "bw_threshold_side must belong to [0, 255].");
+    if (p->min_pixel_count < 1) return fail(ctx, LM_ERR_INVALID, "Min pixel count must be at least 1.");
+    if (p->min_pixel_visible < 0) return fail(ctx, LM_ERR_INVALID, "min_pixel_visible must be non-negative. Was %d.", p->min_pixel_visible);
+    if (p->zero_col_pre < 0 || p->zero_col_post < 0 || p->zero_row_pre < 0 || p->zero_row_post < 0 || p->zero_col_pre > p->side_w ||
+        p->zero_col_post > k.n_cols || p->zero_row_pre > p->side_h || p->zero_row_post > p->side_h)
+        return fail(ctx, LM_ERR_INVALID, "zero_*_* parameters range from 0 to the relevant size of the image.");
+    if (p->disk_size < 1 || p->disk_size > 63) return fail(ctx, LM_ERR_INVALID, "disk_size must be in [1, 63]. Was %d.", p->disk_size);
+    if (p->side_w > 65535 || p->side_h > 65535) return fail(ctx, LM_ERR_INVALID, "side view too large for 16-bit run coordinates");
+    {
+        // the device keeps the filtered image as bits: its values must be 0 or 1, i.e. no sum of taps may round above 1
+        double pos = 0.0;
+        for (int i = 0; i < p->disk_size * p->disk_size; ++i) {
+            if (!std::isfinite(p->disk[i])) return fail(ctx, LM_ERR_INVALID, "DISK_FILTER has a non-finite entry");
+            if (p->disk[i] > 0.f) pos += (double)p->disk[i];
+        }
+        if (pos >= 1.499) return fail(ctx, LM_ERR_INVALID, "DISK_FILTER must be a normalised smoothing kernel (its positive taps sum to %.4f, limit 1.499)", pos);
+    }
+    DeviceGuard guard(ctx->device);
+    const int64_t fsz = (int64_t)k.vid_rows * k.vid_cols;
+    const int cap = 256;
+    cudaStream_t st = ctx->stream;
+    DevBuf d_minmax(st), d_lut(st), d_hist(st), d_pred(st), d_a(st), d_b(st), d_slow(st), d_runs(st), d_disk(st), d_bbx(st), d_lims(st), d_stage(st);
+    CK(d_minmax.alloc((size_t)(cap + 1) * 2 * sizeof(int32_t)));
+    CK(d_lut.alloc((size_t)(cap + 1) * 256));
+    CK(d_hist.alloc((size_t)cap * 256 * sizeof(uint32_t)));
+    CK(d_pred.alloc((size_t)cap * 256));
+    CK(d_a.alloc(lm_bbox_tm_bits_bytes(*p, cap)));
+    CK(d_b.alloc(lm_bbox_tm_bits_bytes(*p, cap)));
+    CK(d_slow.alloc((size_t)cap * 2 * sizeof(int)));
+    CK(d_runs.alloc((size_t)lm_bbox_tm_slow_slots() * lm_bbox_tm_slow_runs(*p) * 14 + 64));
+    CK(d_disk.alloc((size_t)p->disk_size * p->disk_size * sizeof(float)));
+    CK(d_bbx.alloc((size_t)n * sizeof(double)));
+    CK(d_lims.alloc((size_t)n * 2 * sizeof(int32_t)));
+    if (!frames_on_device) CK(d_stage.alloc((size_t)cap * fsz));
+    CK(cudaMemcpyAsync(d_disk.p, p->disk, (size_t)p->disk_size * p->disk_size * sizeof(float), cudaMemcpyHostToDevice, st));
+    for (int64_t s0 = 0; s0 < n; s0 += cap) {
+        const int B = (int)std::min<int64_t>(cap, n - s0);
+        LmBatch b{};
+        b.B = B;
+        b.frame_bytes = fsz;
+        b.prev = nullptr;
+        b.bkg = ctx->d_bkg;
+        b.calib = ctx->d_calib;
+        b.n_rows = k.n_rows;
+        b.n_cols = k.n_cols;
+        b.vid_rows = k.vid_rows;
+        b.vid_cols = k.vid_cols;
+        b.flip = k.flip;
+        b.conn = k.conn;
+        b.imadjust = 0;  // LocoMouse::readFrame(I), LocoMouse_TM.cpp:138
+        b.minmax = (int32_t *)d_minmax.p;
+        b.lut = (uint8_t *)d_lut.p;
+        if (frames_on_device) {
+            b.frames = frames + s0 * fsz;
+        } else {
+            CK(cudaMemcpyAsync(d_stage.p, frames + s0 * fsz, (size_t)B * fsz, cudaMemcpyHostToDevice, st));
+            b.frames = (const uint8_t *)d_stage.p;
+        }
+        const int rc = lm_launch_bbox_tm(b, *p, (const float *)d_disk.p, (uint32_t *)d_hist.p, (uint8_t *)d_pred.p, (uint32_t *)d_a.p, (uint32_t *)d_b.p,
+                                         (int *)d_slow.p, (unsigned char *)d_runs.p, (double *)d_bbx.p + s0, (int32_t *)d_lims.p + s0 * 2, st);
+        if (rc == -2) return fail(ctx, LM_ERR_INVALID, "side view of %d x %d pixels does not fit the shared-memory bit image", p->side_w, p->side_h);
+        if (rc < 0) return fail(ctx, LM_ERR_RUNTIME, "bounding-box launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    CK(cudaMemcpyAsync(bb_x_raw, d_bbx.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (lims) CK(cudaMemcpyAsync(lims, d_lims.p, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LM_OK;
+}
+
 // computeMouseBoxSize (LocoMouse_class.cpp:1481-1506): per series min(median + 3 std, max).  medianvec sorts the series
 // and, for an odd count, returns the element below the middle; stdvec is the sample standard deviation (1515-1556).
 int lm_mouse_box_size(double *bb_w, double *bb_hb, double *bb_hs, int64_t n, int32_t size[3]) {

@@ -107,6 +107,14 @@ LocoMouse_Parameters::LocoMouse_Parameters(const std::string &config_file_name) 
             else if (key == "bb_width") bb_width = std::stoi(val);
             else if (key == "bb_height_side") bb_height_side = std::stoi(val);
             else if (key == "moving_average_window") moving_average_window = std::stoi(val);
+            else if (key == "bw_threshold_bottom") bw_threshold_bottom = std::stoi(val);
+            else if (key == "bw_threshold_side") bw_threshold_side = std::stoi(val);
+            else if (key == "min_pixel_count") min_pixel_count = std::stoi(val);
+            else if (key == "zero_col_pre") zero_col_pre = std::stoi(val);
+            else if (key == "zero_col_post") zero_col_post = std::stoi(val);
+            else if (key == "zero_row_pre") zero_row_pre = std::stoi(val);
+            else if (key == "zero_row_post") zero_row_post = std::stoi(val);
+            else if (key == "disk_filter_file") disk_filter_file = val;
             else if (key == "bounding_box_file") bounding_box_file = val;
             else if (key == "device") device = std::stoi(val);
             else if (key == "batch_frames") batch_frames = std::stoi(val);
@@ -481,12 +489,66 @@ void LocoMouse::computeBoundingBox() {
                                  std::to_string(size[2]) + "); set pass1_integer_sums: 1, use_provided_bounding_box or bounding_box_file.");
 }
 
-LocoMouse_TM::LocoMouse_TM(LocoMouse_ParseInputs INPUTS) : LocoMouse(INPUTS) { METHOD = 1; }
+LocoMouse_TM::LocoMouse_TM(LocoMouse_ParseInputs INPUTS) : LocoMouse(INPUTS) {
+    METHOD = 1;
+    REF_PATH = INPUTS.REF_PATH;
+}
 
-// LocoMouse_TM.cpp:115-157: x from pass 1, bottom anchor = last image row, side anchor = row 164.
+// LocoMouse_TM::computeBoundingBox (LocoMouse_TM.cpp:115-157): x from computeMouseBox_DD per frame (on the device:
+// lm_bounding_box_tm) smoothed by the moving average, bottom anchor = last image row, side anchor = row 164.  A pass-1 output
+// file (bounding_box_file) replaces the per-frame part.  The reference reads its parameters and diskfilter.yml in the
+// constructor (LocoMouse_TM.cpp:3-42) and fails there when they are missing; here they are only required when pass 1 runs.
 void LocoMouse_TM::computeBoundingBox() {
-    std::vector<unsigned int> ys, yb;
-    read_boxes(LM_PARAMS.bounding_box_file, N_FRAMES, BB_X_POS, ys, yb);
+    if (!LM_PARAMS.bounding_box_file.empty()) {
+        std::vector<unsigned int> ys, yb;
+        read_boxes(LM_PARAMS.bounding_box_file, N_FRAMES, BB_X_POS, ys, yb);
+    } else {
+        const std::string dfile = LM_PARAMS.disk_filter_file.empty() ? REF_PATH + "diskfilter.yml" : LM_PARAMS.disk_filter_file;
+        cvyaml::File y(dfile);
+        if (!y.isOpened() || !y.has("H")) throw std::invalid_argument("Failed to read config file: diskfilter.yml");  // LocoMouse_TM.cpp:9
+        const cvyaml::Matrix &Hm = y.mat("H");
+        if (Hm.empty() || Hm.rows != Hm.cols) throw std::invalid_argument("diskfilter.yml: H must be a square matrix.");
+        DISK_SIZE = Hm.rows;
+        DISK_FILTER.assign(Hm.data.begin(), Hm.data.end());
+        // LocoMouse_TM_Parameters' range checks (LocoMouse_TM.cpp:58-111), same messages
+        const std::string em = "Invalid configuration parameter: ";
+        if (LM_PARAMS.bw_threshold_bottom < 0 || LM_PARAMS.bw_threshold_bottom > 255) throw std::invalid_argument(em + "bw_threshold_bottom must belong to [0, 1].");
+        if (LM_PARAMS.bw_threshold_side < 0 || LM_PARAMS.bw_threshold_side > 255) throw std::invalid_argument(em + "bw_threshold_side must belong to [0, 255].");
+        if (LM_PARAMS.min_pixel_count < 1) throw std::invalid_argument(em + "Min pixel count must be at least 1.");
+        if (LM_PARAMS.zero_col_post < 0 || LM_PARAMS.zero_col_pre < 0 || LM_PARAMS.zero_row_post < 0 || LM_PARAMS.zero_row_pre < 0)
+            throw std::invalid_argument(em + "zero_*_* parameters range from 0 to the relevant size of the image.");
+        if (LM_PARAMS.bb_width < 1) throw std::invalid_argument(em + "bb_width must be at least 1 pixel.");
+        if (LM_PARAMS.bb_height_side < 1) throw std::invalid_argument(em + "bb_height_side must be at least 1 pixel.");
+        // LocoMouse_TM.cpp:20-36
+        if (BB_SIDE_VIEW.width < LM_PARAMS.zero_col_pre || BB_SIDE_VIEW.width < LM_PARAMS.zero_col_post)
+            throw std::invalid_argument("Side View image size is not compatible with the zero_col parameters for the bounding box computations. See the definition of the LocoMouse_TM class.");
+        if (BB_SIDE_VIEW.height < LM_PARAMS.zero_row_pre || BB_SIDE_VIEW.height < LM_PARAMS.zero_row_post)
+            throw std::invalid_argument("Side View image size is not compatible with the zero_row parameters for the bounding box computations. See the definition of the LocoMouse_TM class.");
+        // lm_configure needs positive box sizes; pass 1 does not use them
+        BB_SIDE_MOUSE = cv::Rect(0, 0, LM_PARAMS.bb_width, LM_PARAMS.bb_height_side);
+        BB_BOTTOM_MOUSE = cv::Rect(0, 0, LM_PARAMS.bb_width, BB_BOTTOM_VIEW.height);
+        configureDevice();
+        lm_bb_tm_params p{};
+        p.side_x = BB_SIDE_VIEW.x;
+        p.side_y = BB_SIDE_VIEW.y;
+        p.side_w = BB_SIDE_VIEW.width;
+        p.side_h = BB_SIDE_VIEW.height;
+        p.side_threshold = LM_PARAMS.bw_threshold_side;
+        p.min_pixel_count = LM_PARAMS.min_pixel_count;
+        p.min_pixel_visible = LM_PARAMS.min_pixel_visible;
+        p.zero_col_pre = LM_PARAMS.zero_col_pre;
+        p.zero_col_post = LM_PARAMS.zero_col_post;
+        p.zero_row_pre = LM_PARAMS.zero_row_pre;
+        p.zero_row_post = LM_PARAMS.zero_row_post;
+        p.sums_as_float = LM_PARAMS.pass1_integer_sums ? 0 : 1;
+        p.disk_size = DISK_SIZE;
+        p.disk = DISK_FILTER.data();
+        std::vector<double> bb_x(N_FRAMES);
+        check(lm_bounding_box_tm(CTX, VIDEO.data(), /*frames_on_device=*/0, N_FRAMES, &p, bb_x.data(), nullptr));
+        BB_X_POS.assign(N_FRAMES, 0);
+        if (lm_moving_average(bb_x.data(), N_FRAMES, LM_PARAMS.moving_average_window, BB_X_POS.data()) != LM_OK)
+            throw std::invalid_argument("moving_average_window is invalid.");
+    }
     std::fill(BB_Y_BOTTOM_POS.begin(), BB_Y_BOTTOM_POS.end(), N_ROWS - 1);
     std::fill(BB_Y_SIDE_POS.begin(), BB_Y_SIDE_POS.end(), 165u - 1u);
     BB_SIDE_MOUSE = cv::Rect(0, 0, LM_PARAMS.bb_width, LM_PARAMS.bb_height_side);

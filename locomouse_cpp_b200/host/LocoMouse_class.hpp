@@ -95,6 +95,10 @@ public:
     static constexpr unsigned int N_paws = 4, N_snout = 1, N_tail_points = 15;
     // TM / TM_DE (LocoMouse_TM.cpp:57-112)
     int bb_width = 400, bb_height_side = 150;
+    // LocoMouse_TM_Parameters (LocoMouse_TM.cpp:44-113); -1: key absent from the configuration file
+    int bw_threshold_bottom = -1, bw_threshold_side = -1, min_pixel_count = -1;
+    int zero_col_pre = -1, zero_col_post = -1, zero_row_pre = -1, zero_row_post = -1;
+    std::string disk_filter_file;   // default: diskfilter.yml beside the executable (LocoMouse_TM.cpp:6)
     int moving_average_window = 5;
     // B200 path
     std::string bounding_box_file;  // pass-1 output (BB_X_POS, BB_Y_SIDE_POS, BB_Y_BOTTOM_POS), see lm_files.hpp
@@ -257,6 +261,11 @@ protected:
 public:
     explicit LocoMouse_TM(LocoMouse_ParseInputs INPUTS);
     void computeBoundingBox() override;
+
+protected:
+    std::vector<float> DISK_FILTER;   // diskfilter.yml "H" (LocoMouse_TM.cpp:4-14), row-major, DISK_SIZE x DISK_SIZE
+    int DISK_SIZE = 0;
+    std::string REF_PATH;
 };
 
 // LocoMouse_TM_DE (LocoMouse_TM_DE.hpp:39-43): same readFrame; 400-wide boxes over the full view heights

@@ -29,7 +29,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     L = api.load_library()
     for name in _declared_functions():
         assert hasattr(L, name), name
-    assert L.lm_abi_version() == 4
+    assert L.lm_abi_version() == 5
 
 
 def test_struct_layouts_match_the_header():

@@ -349,3 +349,60 @@ def test_base_class_pass1_on_device_then_detection(tmp_path, oracle):
             cb, cs, matches = feats[feat]
             assert cb == ref.candidates_bottom(f, feat) and cs == ref.candidates_side(f, feat)
             assert matches == [m[1] for m in ref.p22d(f, feat)]
+
+
+@pytest.mark.gpu
+def test_tm_pass1_on_device_then_detection(tmp_path, oracle):
+    """Method 1 with no pass-1 file: LocoMouse_TM::computeBoundingBox runs computeMouseBox_DD on the device
+    (lm_bounding_box_tm: imadjust_default, bands, threshold, bwAreaOpen, disk filter from a diskfilter.yml written by the real
+    OpenCV, imfill, column sums) + the host moving average; detection then uses those boxes.  With the reference's own reading
+    of the integer sums every bb_x is -1 and the crop fails, as it does in the reference; with pass1_integer_sums everything
+    equals the oracle's pass 1 + detection."""
+    cv2 = pytest.importorskip("cv2")
+    from locomouse_cpp_b200 import synth
+    from locomouse_cpp_b200.types import bb_tm_params
+
+    exe = _build_driver()
+    spec = synth.SynthSpec(method="TM")
+    n = 9
+    cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(spec, n, seed=1000)
+    frames = frames.numpy()
+    y, x = np.mgrid[-5:6, -5:6]
+    disk = ((x * x + y * y) <= 5.5 ** 2).astype(np.float64)
+    disk = (disk / disk.sum()).astype(np.float32)
+    fs = cv2.FileStorage(str(tmp_path / "diskfilter.yml"), cv2.FILE_STORAGE_WRITE)
+    fs.write("H", disk)
+    fs.release()
+    tm_cfg = (f"bw_threshold_bottom: 3\nbw_threshold_side: 3\nmin_pixel_count: 25\nzero_col_pre: 0\nzero_col_post: {cfg.n_cols}\n"
+              f"zero_row_pre: 0\nzero_row_post: {spec.side_h}\ndisk_filter_file: {tmp_path / 'diskfilter.yml'}\n")
+    args = lambda d: [exe, "1", str(d / "config.yml"), str(d / "video.lmv"), str(d / "bkg.lmi"), str(d / "model.lmm"), str(d / "calib.lmc"), "R", str(d)]
+    d1 = tmp_path / "ref"
+    d1.mkdir()
+    write_problem_files(d1, cfg, model, bkg, calib, frames, bx, bs, bb, spec.side_h, extra_cfg="batch_frames: 4\n" + tm_cfg, with_boxes=False)
+    p = subprocess.run(args(d1), capture_output=True, text=True)
+    assert p.returncode == 1, p.stdout + p.stderr   # bb_x = -1 for every frame: the crop leaves the image (ROI exception in the reference)
+    d2 = tmp_path / "int"
+    d2.mkdir()
+    write_problem_files(d2, cfg, model, bkg, calib, frames, bx, bs, bb, spec.side_h, extra_cfg="batch_frames: 4\npass1_integer_sums: 1\n" + tm_cfg,
+                        with_boxes=False)
+    p = subprocess.run(args(d2), capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    P = bb_tm_params(cfg, disk, side_h=spec.side_h, side_threshold=3, min_pixel_count=25, sums_as_float=0)
+    raw, _ = oracle.bounding_box_tm(cfg, bkg, calib, frames, P)
+    want_bx = oracle.vecmovingaverage(raw, 5)
+    assert (raw > 0).all()
+    ys = np.full(n, 164, np.uint32)
+    yb = np.full(n, cfg.n_rows - 1, np.uint32)
+    ref = oracle.detect(cfg, model, bkg, calib, frames, want_bx, ys, yb, n_threads=4)
+    assert ref.rc == 0
+    out = read_output(d2 / "output_video.lmo")
+    assert len(out) == n
+    total = 0
+    for f, (tail, feats) in enumerate(out):
+        assert np.array_equal(tail, ref.tail[f])
+        for feat in range(2):
+            cb, cs, matches = feats[feat]
+            assert cb == ref.candidates_bottom(f, feat) and cs == ref.candidates_side(f, feat)
+            assert matches == [m[1] for m in ref.p22d(f, feat)]
+            total += len(cb)
+    assert total > 0

@@ -114,7 +114,6 @@ __device__ bool largest_region_runs(TailSmem &S, int rows, int cols, int wpr, in
         S.sum[c] = 0;
         if (want_colany) S.colany[c] = 0;
     }
-    for (int i = tid; i < nwords; i += TAIL_THREADS) S.obits[i] = 0u;
     if (S.rowcnt)
         for (int r = tid; r < rows; r += TAIL_THREADS) S.rowcnt[r] = 0;
     if (tid == 0) *s_best = 0ull;
@@ -152,6 +151,8 @@ __device__ bool largest_region_runs(TailSmem &S, int rows, int cols, int wpr, in
         }
     }
     __syncthreads();
+    // the input bits are not read again: S.obits may be the same memory as S.bits (k_tail does that to halve its footprint)
+    for (int i = tid; i < nwords; i += TAIL_THREADS) S.obits[i] = 0u;
     // rows without runs: rowfirst[r] = rowfirst of the next row that has one (suffix min)
     if (tid == 0) {
         int nxt = total;

@@ -181,12 +181,15 @@ __global__ void __launch_bounds__(256) k_lut(const __grid_constant__ LmBatch b, 
 
 // ---- k_prep --------------------------------------------------------------------------------------
 // Per video, once (k_fold_calib): the calibration map with the optional mirror folded in, calib_flip[r][c] =
-// calib[r][flip ? n_cols - 1 - c : c], and the background seen through it, bkg_warp[r][c] = bkg[calib_flip[r][c]].  A window
-// pixel is then lut[max(F[calib_flip] - bkg_warp, 0)]: one gather (the frame) instead of three.
-// k_prep: one CTA = PREP_ROWS window rows of one (frame, view).  A thread owns one 4-pixel word column and walks the rows
-// (32-bit incremental indexing); words that lie wholly inside the image -- all but the box border -- take a path without
-// per-pixel predicates: four map loads, four frame bytes, the background word by two aligned loads + funnel shift.
-constexpr int PREP_ROWS = 64;
+// calib[r][flip ? n_cols - 1 - c : c]; the background seen through it, bkg_warp[r][c] = bkg[calib_flip[r][c]]; and run flags:
+// real calibration maps are piecewise runs of consecutive raw bytes, run_mode[r][c] says whether the 4 / 16 pixels that start
+// at column c come from 4 / 16 consecutive raw bytes (ascending, or descending for a mirrored map).
+// k_prep: one CTA = PREP_ROWS window rows of one (frame, view); a thread produces 16 window pixels (one 16-byte store).
+//   tier 1  the 16 pixels are one run: one map load, five aligned frame words + funnel shifts, per-byte saturating
+//           subtract of the background words, 16 table look-ups;
+//   tier 2  per 4-pixel word: a run of 4 (two aligned frame words) or four separate gathers;
+//   tier 3  words that cross the image border: per-pixel predicates.
+constexpr int PREP_ROWS = 32;
 constexpr int PREP_THREADS = 256;
 
 __global__ void __launch_bounds__(256) k_fold_calib(const int32_t *__restrict__ calib, const uint8_t *__restrict__ bkg, int n_rows, int n_cols,
@@ -200,18 +203,26 @@ __global__ void __launch_bounds__(256) k_fold_calib(const int32_t *__restrict__ 
         const int32_t src = at(c);
         calib_flip[i] = src;
         bkg_warp[i] = bkg[src];
-        // run_mode[r][c]: the four pixels c .. c+3 of this row come from raw bytes src, src+1, src+2, src+3 (1) or
-        // src, src-1, src-2, src-3 (2: mirrored); 0 otherwise.  Real calibration maps are piecewise such runs.
-        uint8_t m = 0;
-        if (c + 3 < n_cols) {
-            const int32_t a1 = at(c + 1), a2 = at(c + 2), a3 = at(c + 3);
-            if (a1 == src + 1 && a2 == src + 2 && a3 == src + 3)
-                m = 1;
-            else if (a1 == src - 1 && a2 == src - 2 && a3 == src - 3)
-                m = 2;
+        // bit 0 / 1: pixels c .. c+3 come from raw bytes src, src+1, .. / src, src-1, ..; bit 2 / 3: the same for c .. c+15
+        int up = 0, down = 0;
+        for (int q = 1; q < 16 && c + q < n_cols; ++q) {
+            const int32_t a = at(c + q);
+            if (a == src + q && up == q - 1) up = q;
+            if (a == src - q && down == q - 1) down = q;
+            if (up < q && down < q) break;
         }
-        run_mode[i] = m;
+        run_mode[i] = (uint8_t)((up >= 3 ? 1 : 0) | (down >= 3 ? 2 : 0) | (up >= 15 ? 4 : 0) | (down >= 15 ? 8 : 0));
     }
+}
+
+// four bytes at an arbitrary address through two aligned words (the caller guarantees both words lie inside the buffer)
+__device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t *p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), ((unsigned)a & 3u) * 8u);
+}
+__device__ __forceinline__ uint32_t prep_lut4(const uint8_t *lut, uint32_t d4) {
+    return (uint32_t)lut[d4 & 0xffu] | ((uint32_t)lut[(d4 >> 8) & 0xffu] << 8) | ((uint32_t)lut[(d4 >> 16) & 0xffu] << 16) | ((uint32_t)lut[d4 >> 24] << 24);
 }
 
 __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ LmBatch b) {
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ L
     __syncthreads();
     const int r1 = min(V.win_h, r0 + PREP_ROWS);
     const uint8_t *__restrict__ F = b.frames + (int64_t)f * b.frame_bytes;
-    const uint8_t *__restrict__ Kw = b.bkg_warp;
+    const uint8_t *__restrict__ Kw = b.bkg_warp;   // 4-byte aligned, padded by >= 24 bytes
     const int32_t *__restrict__ C2 = b.calib_flip;
     const uint8_t *__restrict__ RM = b.run_mode;
     const int fbytes = (int)b.frame_bytes;
@@ -232,66 +243,85 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep(const __grid_constant__ L
     const int ypos = (int)(v == LM_BOTTOM ? b.bb_y_bottom[f] : b.bb_y_side[f]);
     const int y0 = ypos - V.box_h + 1 - V.halo_y;
     uint8_t *W = b.win[v] + (int64_t)f * V.win_stride;
-    const int wpr = V.win_pitch >> 2, n_cols = b.n_cols, n_rows = b.n_rows;
-    // thread -> (row slot, word column); when a row has more words than the CTA has threads the words are looped over
-    const int nslot = wpr <= PREP_THREADS ? PREP_THREADS / wpr : 1;
-    const int slot = wpr <= PREP_THREADS ? (int)threadIdx.x / wpr : 0;
-    if (slot >= nslot) return;
-    for (int w = wpr <= PREP_THREADS ? (int)threadIdx.x - slot * wpr : (int)threadIdx.x; w < wpr; w += PREP_THREADS) {
-        const int c4 = w << 2, xx0 = x0 + c4;
-        // bit q: pixel q of the word is a window pixel that lies inside the image
-        unsigned vm = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (c4 + q < V.win_w && xx0 + q >= 0 && xx0 + q < n_cols) vm |= 1u << q;
-        uint32_t *dst = reinterpret_cast<uint32_t *>(W + (int64_t)(r0 + slot) * V.win_pitch) + w;
-        const int dst_step = nslot * wpr;  // words
-        int yy = y0 + r0 + slot;
-        if (vm == 0xFu) {
-#pragma unroll 2
-            for (int r = r0 + slot; r < r1; r += nslot, yy += nslot, dst += dst_step) {
-                uint32_t out = 0;
-                if (yy >= 0 && yy < n_rows) {
-                    const int base = yy * n_cols + xx0;
-                    const int32_t *cp = C2 + base;
-                    const int i0 = __ldg(cp);
-                    const uint32_t *kp = reinterpret_cast<const uint32_t *>(Kw + (base & ~3));  // bkg_warp is 4-byte aligned and padded
-                    const uint32_t kw4 = __funnelshift_r(__ldg(kp), __ldg(kp + 1), (base & 3) * 8);
-                    const int mode = __ldg(RM + base);
-                    // a run of four raw bytes: two aligned word loads instead of three more map loads and four byte gathers.
-                    // The aligned words must lie inside this frame's bytes (the caller's buffer ends with the last frame).
-                    const int lo_i = mode == 2 ? i0 - 3 : i0;
-                    const uintptr_t a = reinterpret_cast<uintptr_t>(F) + (uintptr_t)(unsigned)lo_i;
-                    uint32_t f4;
-                    if (mode != 0 && lo_i >= 4 && lo_i + 8 <= fbytes) {
+    const int nseg = V.win_pitch >> 4, n_cols = b.n_cols, n_rows = b.n_rows;
+    const int items = (r1 - r0) * nseg;
+    for (int it = threadIdx.x; it < items; it += PREP_THREADS) {
+        const int rr = it / nseg, sg = it - rr * nseg;
+        const int r = r0 + rr, c16 = sg << 4, xx0 = x0 + c16, yy = y0 + r;
+        uint32_t o[4] = {0u, 0u, 0u, 0u};
+        if (yy >= 0 && yy < n_rows && c16 < V.win_w && xx0 + 16 > 0 && xx0 < n_cols) {
+            const int base = yy * n_cols + xx0;
+            bool done = false;
+            if (xx0 >= 0 && xx0 + 16 <= n_cols) {
+                const int mode = __ldg(RM + base);
+                if (mode & 12) {   // tier 1: one run of 16 raw bytes
+                    const int i0 = __ldg(C2 + base);
+                    const int lo_i = (mode & 4) ? i0 : i0 - 15;
+                    if (lo_i >= 4 && lo_i + 24 <= fbytes) {   // the aligned words read lie inside this frame's bytes
+                        const uintptr_t a = reinterpret_cast<uintptr_t>(F) + (uintptr_t)(unsigned)lo_i;
                         const uint32_t *fp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-                        f4 = __funnelshift_r(__ldg(fp), __ldg(fp + 1), ((unsigned)a & 3u) * 8u);
-                        if (mode == 2) f4 = __byte_perm(f4, 0u, 0x0123);
-                    } else {
-                        const int i1 = __ldg(cp + 1), i2 = __ldg(cp + 2), i3 = __ldg(cp + 3);
-                        f4 = (uint32_t)__ldg(F + i0) | ((uint32_t)__ldg(F + i1) << 8) | ((uint32_t)__ldg(F + i2) << 16) | ((uint32_t)__ldg(F + i3) << 24);
-                    }
-                    const uint32_t d4 = __vsubus4(f4, kw4);  // per-byte max(F - BKG, 0)
-                    out = (uint32_t)lut[d4 & 0xffu] | ((uint32_t)lut[(d4 >> 8) & 0xffu] << 8) | ((uint32_t)lut[(d4 >> 16) & 0xffu] << 16) |
-                          ((uint32_t)lut[d4 >> 24] << 24);
-                }
-                *dst = out;
-            }
-        } else {
-            for (int r = r0 + slot; r < r1; r += nslot, yy += nslot, dst += dst_step) {
-                uint32_t out = 0;
-                if (vm && yy >= 0 && yy < n_rows) {
-                    const int base = yy * n_cols + xx0;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (vm & (1u << q)) {
-                            const int d = max((int)__ldg(F + __ldg(C2 + base + q)) - (int)__ldg(Kw + base + q), 0);
-                            out |= (uint32_t)lut[d] << (8 * q);
+                        const unsigned sh = ((unsigned)a & 3u) * 8u;
+                        const uint32_t f0 = __ldg(fp), f1 = __ldg(fp + 1), f2 = __ldg(fp + 2), f3 = __ldg(fp + 3), f4 = __ldg(fp + 4);
+                        uint32_t fw[4] = {__funnelshift_r(f0, f1, sh), __funnelshift_r(f1, f2, sh), __funnelshift_r(f2, f3, sh), __funnelshift_r(f3, f4, sh)};
+                        if (!(mode & 4)) {   // descending run: pixel q is raw byte lo_i + 15 - q
+                            const uint32_t t0 = __byte_perm(fw[3], 0u, 0x0123), t1 = __byte_perm(fw[2], 0u, 0x0123);
+                            const uint32_t t2 = __byte_perm(fw[1], 0u, 0x0123), t3 = __byte_perm(fw[0], 0u, 0x0123);
+                            fw[0] = t0; fw[1] = t1; fw[2] = t2; fw[3] = t3;
                         }
+                        const uint32_t *kp = reinterpret_cast<const uint32_t *>(Kw + (base & ~3));
+                        const unsigned ks = (unsigned)(base & 3) * 8u;
+                        const uint32_t k0 = __ldg(kp), k1 = __ldg(kp + 1), k2 = __ldg(kp + 2), k3 = __ldg(kp + 3), k4 = __ldg(kp + 4);
+                        o[0] = prep_lut4(lut, __vsubus4(fw[0], __funnelshift_r(k0, k1, ks)));   // per-byte max(F - BKG, 0)
+                        o[1] = prep_lut4(lut, __vsubus4(fw[1], __funnelshift_r(k1, k2, ks)));
+                        o[2] = prep_lut4(lut, __vsubus4(fw[2], __funnelshift_r(k2, k3, ks)));
+                        o[3] = prep_lut4(lut, __vsubus4(fw[3], __funnelshift_r(k3, k4, ks)));
+                        done = true;
+                    }
                 }
-                *dst = out;
+            }
+            if (!done) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int c4 = c16 + 4 * w, xw = xx0 + 4 * w, bw = base + 4 * w;
+                    if (c4 >= V.win_w) break;
+                    if (xw >= 0 && xw + 4 <= n_cols) {   // tier 2: the word lies inside the image
+                        const int32_t *cp = C2 + bw;
+                        const int i0 = __ldg(cp);
+                        const int mode = __ldg(RM + bw) & 3;
+                        const int lo_i = mode == 2 ? i0 - 3 : i0;
+                        uint32_t f4;
+                        if (mode != 0 && lo_i >= 4 && lo_i + 8 <= fbytes) {
+                            f4 = ldg_u32_unaligned(F + lo_i);
+                            if (mode == 2) f4 = __byte_perm(f4, 0u, 0x0123);
+                        } else {
+                            const int i1 = __ldg(cp + 1), i2 = __ldg(cp + 2), i3 = __ldg(cp + 3);
+                            f4 = (uint32_t)__ldg(F + i0) | ((uint32_t)__ldg(F + i1) << 8) | ((uint32_t)__ldg(F + i2) << 16) | ((uint32_t)__ldg(F + i3) << 24);
+                        }
+                        o[w] = prep_lut4(lut, __vsubus4(f4, ldg_u32_unaligned(Kw + bw)));
+                    } else {   // tier 3: image border
+                        uint32_t out = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (xw + q >= 0 && xw + q < n_cols) {
+                                const int d = max((int)__ldg(F + __ldg(C2 + bw + q)) - (int)__ldg(Kw + bw + q), 0);
+                                out |= (uint32_t)lut[d] << (8 * q);
+                            }
+                        o[w] = out;
+                    }
+                }
+            }
+            // pixels right of the window (the pitch rounds the row up to 16 bytes) stay zero
+            const int valid = V.win_w - c16;
+            if (valid < 16) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int vb = valid - 4 * w;
+                    if (vb <= 0) o[w] = 0u;
+                    else if (vb < 4) o[w] &= (1u << (8 * vb)) - 1u;
+                }
             }
         }
+        *reinterpret_cast<uint4 *>(W + (int64_t)r * V.win_pitch + c16) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ L
     TailSmem S;
     unsigned char *p = raw;
     S.bits = reinterpret_cast<uint32_t *>(p); p += (size_t)hmax * wpr * 4;
-    S.obits = reinterpret_cast<uint32_t *>(p); p += (size_t)hmax * wpr * 4;
+    S.obits = S.bits;   // the winner mask replaces the input bits once the runs are extracted (cc_runs.cuh)
     S.rowfirst = reinterpret_cast<int *>(p); p += (size_t)(hmax + 1) * 4;
     const size_t rcap = (size_t)((runcap > 1 ? runcap : 1) + 63) & ~(size_t)63;  // run arrays are sized for the launch's threshold
     S.parent = reinterpret_cast<int *>(p); p += rcap * 4;
@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const __grid_constant__ L
             atomicMin(&s_first, c);
             atomicMax(&s_last, c);
         }
+    __syncthreads();   // the winner mask (same memory as the bit image) has been written out by every thread
     load_bits(bin_s, hs, cols, pitch, wpr, S.colany, S.bits);
     __syncthreads();
     S.cnt = cnt_s;
@@ -196,7 +197,7 @@ size_t tail_smem(const LmBatch &b, int runcap) {
     const size_t rcap = (size_t)((runcap > 1 ? runcap : 1) + 63) & ~(size_t)63;
     const int hmax = b.bb_h[0] > b.bb_h[1] ? b.bb_h[0] : b.bb_h[1];
     const int wpr = (b.tail_w + 31) >> 5;
-    size_t s = (size_t)hmax * wpr * 4 * 2 + (size_t)(hmax + 1) * 4 + rcap * 4 * 3 + (size_t)b.tail_w * 4 * 5 +
+    size_t s = (size_t)hmax * wpr * 4 + (size_t)(hmax + 1) * 4 + rcap * 4 * 3 + (size_t)b.tail_w * 4 * 5 +
                rcap * 2 * 3;
     return (s + 15) & ~(size_t)15;
 }

@@ -460,7 +460,7 @@ int prepare(lm_ctx *ctx) {
     const size_t B = (size_t)Bcap;
     int rc;
     if ((rc = dalloc(ctx, &ctx->d_calib_flip, (size_t)k.n_rows * k.n_cols))) return rc;
-    if ((rc = dalloc(ctx, &ctx->d_bkg_warp, (size_t)k.n_rows * k.n_cols + 16))) return rc;  // + padding: word loads past the last pixel
+    if ((rc = dalloc(ctx, &ctx->d_bkg_warp, (size_t)k.n_rows * k.n_cols + 32))) return rc;  // + padding: word loads past the last pixel
     if ((rc = dalloc(ctx, &ctx->d_run_mode, (size_t)k.n_rows * k.n_cols))) return rc;
     b.calib_flip = ctx->d_calib_flip;
     b.run_mode = ctx->d_run_mode;

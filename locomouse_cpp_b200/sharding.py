@@ -118,6 +118,9 @@ def concat(parts) -> Results:
     return out
 
 
+_GATHER_CACHE = {}
+
+
 def gather_to_rank0(res: Results, device=None):
     """Gather every rank's Results on rank 0 (list in rank order; None elsewhere).
 
@@ -134,13 +137,35 @@ def gather_to_rank0(res: Results, device=None):
     dist.all_gather(metas, meta)
     metas = [tuple(int(v) for v in m.tolist()) for m in metas]
     if all(m == metas[0] for m in metas):
-        send = torch.from_numpy(res.raw).to(dev, non_blocking=True)
-        recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+        n, cap, mcap, ntp = metas[0]
+        if dev.type != "cuda":
+            send = torch.from_numpy(res.raw)
+            recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+            dist.gather(send, recv, dst=0)
+            if rank != 0:
+                return None
+            return [Results(n, cap, mcap, ntp, buffer=r.numpy()) for r in recv]
+        # GPU ranks: the receive buffers on the device and the page-locked host buffers they are copied into are allocated
+        # once and reused (a fresh pageable .cpu() copy of world x 11 kB/frame per call had made rank 0 the bottleneck of
+        # every step); the returned Results alias those host buffers and stay valid until the next call.
+        nbytes = int(res.raw.nbytes)
+        key = (world, rank, nbytes, str(dev))
+        bufs = _GATHER_CACHE.get(key)
+        if bufs is None:
+            _GATHER_CACHE.clear()
+            send = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            recv = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+            host = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(world)] if rank == 0 else None
+            bufs = _GATHER_CACHE[key] = (send, recv, host)
+        send, recv, host = bufs
+        send.copy_(torch.from_numpy(res.raw), non_blocking=True)
         dist.gather(send, recv, dst=0)
         if rank != 0:
             return None
-        n, cap, mcap, ntp = metas[0]
-        return [Results(n, cap, mcap, ntp, buffer=r.cpu().numpy()) for r in recv]
+        for h, r in zip(host, recv):
+            h.copy_(r, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return [Results(n, cap, mcap, ntp, buffer=h.numpy()) for h in host]
     payload = torch.from_numpy(pack(res).copy())
     size = torch.tensor([payload.numel()], dtype=torch.int64, device=dev)
     sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]

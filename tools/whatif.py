@@ -11,7 +11,7 @@ from locomouse_cpp_b200 import synth  # noqa: E402
 from locomouse_cpp_b200.api import Detector  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 5120
-spec = synth.SynthSpec()
+spec = synth.SynthSpec(det_cap=int(os.environ.get("LM_WHATIF_DETCAP", "8192")))
 cfg, model, bkg, calib, _, _, _, _ = synth.make_problem(spec, 8, seed=1000)
 frames, bx, bs, bb = synth.make_video(spec, n, 1000, "cuda", bkg)
 det = Detector(cfg, model, bkg, calib)

@@ -10,12 +10,13 @@
 //   k_minmax + k_lut (k_pre.cu), k_bb_hist + k_bb_pred (k_bbox.cu)   pred[d] = imadjust_default(normalise(d)) > threshold
 //   k_bbtm_bin    bit image of the side view through the calibration map, bands zeroed (a warp = one 32-pixel word)
 //   k_bbtm_open   per frame: run-based component labelling in shared memory, runs of components below the area limit cleared
-//   k_bbtm_disk   a thread = one output word; words whose whole neighbourhood is empty are skipped, the others add the
-//                 kernel's taps in row-major order in float exactly as OpenCV's direct filter does
+//   k_bbtm_disk   a thread = one output word; words whose whole neighbourhood is empty are skipped; otherwise taps over set
+//                 pixels are counted per distinct kernel weight (popcounts) and only sums within the rounding margin of 0.5
+//                 replay OpenCV's float adds in row-major tap order
 //   k_bbtm_fill   per frame: 4-connected labelling of the seed-valued pixels, the component of pixel (0, 0) = the flood
 //                 fill; column sums via a difference array; first / last; bb_x
 // Frames whose run count exceeds the shared-memory capacity set a flag and are redone by the same code with its run arrays
-// in global memory (k_bbtm_open / k_bbtm_fill instantiated with GLOBAL = true, a few CTAs looping over the flagged frames).
+// in global memory (k_bbtm_open / k_bbtm_fill instantiated with GLOBAL = true, one CTA per flagged frame).
 #include <algorithm>
 #include <cstdlib>
 
@@ -24,7 +25,7 @@
 
 namespace {
 
-constexpr int TM_SLOW_SLOTS = 16;
+constexpr int TM_DISK_LEVELS = 8;   // distinct kernel weights the counting path of k_bbtm_disk handles
 
 struct BBTmDev {
     const uint8_t *frames;
@@ -41,7 +42,7 @@ struct BBTmDev {
     uint32_t *bits_a, *bits_b;  // [B][H][wpr]
     int *need_slow;          // [B][2]: open, fill
     int runcap;              // run capacity of the shared-memory path
-    // global run arrays for the slow path: TM_SLOW_SLOTS x worst-case runs
+    // global run arrays for the slow path: one slot of worst-case size per frame of the chunk
     int *g_parent, *g_area;
     unsigned short *g_rrow, *g_rx0, *g_rx1;
     int64_t g_stride;        // runs per slot
@@ -153,8 +154,14 @@ __device__ int label_runs(const uint32_t *bits, int rows, int cols, int wpr, int
         const int r = R.rrow[id];
         if (r == 0) continue;
         const int lo = (int)R.rx0[id] - ext, hi = (int)R.rx1[id] + ext;
-        for (int q = rowfirst[r - 1]; q < rowfirst[r]; ++q) {
-            if ((int)R.rx1[q] < lo) continue;
+        // the previous row's runs are x-sorted: binary search for the first one that ends at or after lo
+        int a = rowfirst[r - 1], e = rowfirst[r];
+        while (a < e) {
+            const int mid = (a + e) >> 1;
+            if ((int)R.rx1[mid] < lo) a = mid + 1;
+            else e = mid;
+        }
+        for (int q = a; q < rowfirst[r]; ++q) {
             if ((int)R.rx0[q] > hi) break;
             uf_union_s(R.parent, id, q);
         }
@@ -213,7 +220,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_bbtm_open(const __grid_constan
     const RunArrays R = GLOBAL ? global_runs(P, blockIdx.x) : carve_runs(raw + fixed, P.runcap);
     const int cap = GLOBAL ? (int)P.g_stride : P.runcap;
     const int nwords = P.H * P.wpr, tid = threadIdx.x;
-    for (int f = blockIdx.x; f < P.B; f += gridDim.x) {
+    for (int f = blockIdx.x; f < P.B; f += gridDim.x) {   // grid = B: one frame per CTA
         if (GLOBAL && !P.need_slow[f * 2 + 0]) continue;
         const uint32_t *in = P.bits_a + (int64_t)f * nwords;
         uint32_t *out = P.bits_b + (int64_t)f * nwords;
@@ -239,21 +246,36 @@ __device__ __forceinline__ uint32_t bit_clamped(const uint32_t *row, int x, int 
     return (__ldg(row + (x >> 5)) >> (x & 31)) & 1u;
 }
 
-// filter2D(., CV_8UC1, DISK_FILTER, (-1,-1), 0, BORDER_REPLICATE) on the 0 / 1 image bits_b -> bits_a = [ result != 0 ]
-// plus, per frame, whether any result differs from 0 / 1 is impossible to represent: results are kept as bits of
-// "value == seedless 1"; see the note in lm_launch_bbox_tm (kernels whose taps sum above 1.5 are rejected by the host).
-__global__ void __launch_bounds__(128) k_bbtm_disk(const __grid_constant__ BBTmDev P) {
-    extern __shared__ float kern[];
+// filter2D(., CV_8UC1, DISK_FILTER, (-1,-1), 0, BORDER_REPLICATE) on the 0 / 1 image bits_b -> bits_a = [ result >= 1 ]
+// (the host guarantees that no sum of taps rounds above 1).  A thread = one output word.  Words whose neighbourhood is empty
+// are 0.  Otherwise each of the K window rows is fetched once as a 64-bit strip (columns 32c - an .. 32c - an + 63, edge
+// pixels replicated) into shared memory; per pixel the taps over set pixels are COUNTED per distinct kernel weight
+// (popcounts against per-row masks) and the sum formed in double: when it is farther from 0.5 than the worst-case rounding
+// error of OpenCV's float accumulation, the result is certain; the few pixels inside that margin -- and kernels with more
+// than TM_DISK_LEVELS distinct weights or more than 32 columns -- replay OpenCV's float adds in row-major tap order.
+struct DiskLevels {
+    int L;                      // 0: always the exact replay
+    double val[TM_DISK_LEVELS];
+    double margin;
+};
+constexpr int DISK_THREADS = 128;
+
+__global__ void __launch_bounds__(DISK_THREADS) k_bbtm_disk(const __grid_constant__ BBTmDev P, const __grid_constant__ DiskLevels D,
+                                                             const uint32_t *__restrict__ level_mask /* [L][K] */) {
+    extern __shared__ __align__(16) unsigned char dsm[];
     const int K = P.K, an = K >> 1;
-    for (int i = threadIdx.x; i < K * K; i += blockDim.x) kern[i] = P.disk[i];
+    float *kern = reinterpret_cast<float *>(dsm);                                         // [K][K]
+    uint32_t *lmask = reinterpret_cast<uint32_t *>(kern + K * K);                         // [L][K]
+    unsigned long long *wins = reinterpret_cast<unsigned long long *>(dsm + (((size_t)(K * K + TM_DISK_LEVELS * K) * 4 + 15) & ~(size_t)15));  // [K][DISK_THREADS]
+    for (int i = threadIdx.x; i < K * K; i += DISK_THREADS) kern[i] = P.disk[i];
+    for (int i = threadIdx.x; i < D.L * K; i += DISK_THREADS) lmask[i] = level_mask[i];
     __syncthreads();
+    const bool counting = D.L > 0 && K <= 32;
     const int f = blockIdx.y, nwords = P.H * P.wpr;
     const uint32_t *in = P.bits_b + (int64_t)f * nwords;
     uint32_t *out = P.bits_a + (int64_t)f * nwords;
-    for (int wi = blockIdx.x * blockDim.x + threadIdx.x; wi < nwords; wi += gridDim.x * blockDim.x) {
+    for (int wi = blockIdx.x * DISK_THREADS + threadIdx.x; wi < nwords; wi += gridDim.x * DISK_THREADS) {
         const int r = wi / P.wpr, c = wi - r * P.wpr;
-        // empty neighbourhood -> every sum is 0.  Rows r - an .. r + K - 1 - an (clamped), words covering columns
-        // 32c - an .. 32c + 31 + K - 1 - an (clamped columns replicate the edge pixels, which lie in the edge words)
         const int ra = max(0, r - an), rb = min(P.H - 1, r + K - 1 - an);
         const int ca = max(0, (c * 32 - an) >> 5), cb = min(P.wpr - 1, (c * 32 + 31 + K - 1 - an) >> 5);
         uint32_t any = 0;
@@ -262,19 +284,53 @@ __global__ void __launch_bounds__(128) k_bbtm_disk(const __grid_constant__ BBTmD
         uint32_t word = 0;
         if (any) {
             const int valid = min(32, P.W - c * 32);
-            for (int q = 0; q < valid; ++q) {
-                const int x = c * 32 + q;
-                float s = 0.f;
+            const int x_lo = c * 32 - an;   // column of strip bit 0
+            if (counting) {
+                const bool interior = x_lo >= 0 && x_lo + 63 < P.W;
                 for (int j = 0; j < K; ++j) {
                     int rr = r + j - an;
                     rr = rr < 0 ? 0 : (rr >= P.H ? P.H - 1 : rr);
                     const uint32_t *row = in + rr * P.wpr;
-                    for (int i = 0; i < K; ++i)
-                        if (bit_clamped(row, x + i - an, P.W)) s = __fadd_rn(s, kern[j * K + i]);  // + k * 1; a 0 pixel adds k * 0 = 0
+                    unsigned long long w;
+                    if (interior) {
+                        const int w0 = x_lo >> 5, sh = x_lo & 31;
+                        const uint32_t a0 = __ldg(row + w0), a1 = __ldg(row + w0 + 1), a2 = (w0 + 2 < P.wpr) ? __ldg(row + w0 + 2) : 0u;
+                        w = (unsigned long long)__funnelshift_r(a0, a1, sh) | ((unsigned long long)__funnelshift_r(a1, a2, sh) << 32);
+                    } else {
+                        w = 0ull;
+                        for (int t = 0; t < 32 + K - 1; ++t) w |= (unsigned long long)bit_clamped(row, x_lo + t, P.W) << t;
+                    }
+                    wins[j * DISK_THREADS + threadIdx.x] = w;
                 }
-                // saturate_cast<uchar>(float): round half to even, clipped; the host guarantees the result is 0 or 1
-                const int v = __float2int_rn(s);
-                word |= (uint32_t)(v >= 1) << q;
+            }
+            for (int q = 0; q < valid; ++q) {
+                bool decided = false;
+                int v = 0;
+                if (counting) {
+                    double sd = 0.0;
+                    for (int l = 0; l < D.L; ++l) {
+                        int cnt = 0;
+                        for (int j = 0; j < K; ++j) cnt += __popc((uint32_t)(wins[j * DISK_THREADS + threadIdx.x] >> q) & lmask[l * K + j]);
+                        sd += D.val[l] * (double)cnt;
+                    }
+                    if (fabs(sd - 0.5) > D.margin) {
+                        v = sd > 0.5 ? 1 : 0;
+                        decided = true;
+                    }
+                }
+                if (!decided) {   // OpenCV's float accumulation, tap by tap in row-major order
+                    const int x = c * 32 + q;
+                    float s = 0.f;
+                    for (int j = 0; j < K; ++j) {
+                        int rr = r + j - an;
+                        rr = rr < 0 ? 0 : (rr >= P.H ? P.H - 1 : rr);
+                        const uint32_t *row = in + rr * P.wpr;
+                        for (int i = 0; i < K; ++i)
+                            if (bit_clamped(row, x + i - an, P.W)) s = __fadd_rn(s, kern[j * K + i]);  // + k * 1; a 0 pixel adds k * 0 = 0
+                    }
+                    v = __float2int_rn(s) >= 1 ? 1 : 0;   // saturate_cast<uchar>(float): round half to even
+                }
+                word |= (uint32_t)v << q;
             }
         }
         out[wi] = word;
@@ -363,15 +419,14 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_bbtm_fill(const __grid_constan
 }  // namespace
 
 size_t lm_bbox_tm_bits_bytes(const lm_bb_tm_params &p, int B) { return (size_t)B * p.side_h * ((p.side_w + 31) / 32) * sizeof(uint32_t); }
-int lm_bbox_tm_slow_slots() { return TM_SLOW_SLOTS; }
 // worst-case number of runs of one side view (every other pixel set)
 size_t lm_bbox_tm_slow_runs(const lm_bb_tm_params &p) { return (size_t)p.side_h * ((size_t)p.side_w / 2 + 1); }
 
 // b: frames / bkg / calib / minmax / lut / n_cols / flip / conn / B filled in by the caller (imadjust must be 0).
-// hist / pred: [B][256]; bits_a / bits_b: lm_bbox_tm_bits_bytes each; need_slow: [B][2]; g_runs: TM_SLOW_SLOTS x
-// lm_bbox_tm_slow_runs x 14 bytes; disk: the kernel on the device.
+// hist / pred: [B][256]; bits_a / bits_b: lm_bbox_tm_bits_bytes each; need_slow: [B][2]; g_runs: chunk capacity x
+// lm_bbox_tm_slow_runs x 14 bytes (slots: the frames of a chunk); disk: the kernel on the device.
 int lm_launch_bbox_tm(const LmBatch &b, const lm_bb_tm_params &p, const float *d_disk, uint32_t *hist, uint8_t *pred, uint32_t *bits_a,
-                      uint32_t *bits_b, int *need_slow, unsigned char *g_runs, double *bb_x, int32_t *lims, cudaStream_t s) {
+                      uint32_t *bits_b, int *need_slow, unsigned char *g_runs, int g_slots, uint32_t *level_mask, double *bb_x, int32_t *lims, cudaStream_t s) {
     // 1. pred[d]: the front end shared with LocoMouse_TM_DE (normalisation LUT, histogram, imadjust_default, threshold)
     lm_bb_de_params q{};
     q.side_x = p.side_x;
@@ -414,7 +469,8 @@ int lm_launch_bbox_tm(const LmBatch &b, const lm_bb_tm_params &p, const float *d
     P.g_stride = (int64_t)runs;
     {
         unsigned char *g = g_runs;
-        const size_t n = (size_t)TM_SLOW_SLOTS * runs;
+        if (g_slots < b.B) return -1;
+        const size_t n = (size_t)g_slots * runs;
         P.g_parent = reinterpret_cast<int *>(g); g += n * 4;
         P.g_area = reinterpret_cast<int *>(g); g += n * 4;
         P.g_rrow = reinterpret_cast<unsigned short *>(g); g += n * 2;
@@ -443,7 +499,7 @@ int lm_launch_bbox_tm(const LmBatch &b, const lm_bb_tm_params &p, const float *d
             cudaFuncSetAttribute(k_bbtm_open<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget) != cudaSuccess ||
             cudaFuncSetAttribute(k_bbtm_fill<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget) != cudaSuccess ||
             cudaFuncSetAttribute(k_bbtm_fill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget) != cudaSuccess ||
-            cudaFuncSetAttribute(k_bbtm_disk, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
+            cudaFuncSetAttribute(k_bbtm_disk, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
             return -1;
     }
     if (cudaMemsetAsync(need_slow, 0, (size_t)b.B * 2 * sizeof(int), s) != cudaSuccess) return -1;
@@ -456,12 +512,43 @@ int lm_launch_bbox_tm(const LmBatch &b, const lm_bb_tm_params &p, const float *d
         k_bbtm_open<false><<<b.B, TAIL_THREADS, smem_fast, s>>>(P);
     else if (cudaMemsetAsync(need_slow, 1, (size_t)b.B * 2 * sizeof(int), s) != cudaSuccess)  // any non-zero value flags the frame
         return -1;
-    k_bbtm_open<true><<<TM_SLOW_SLOTS, TAIL_THREADS, smem_slow, s>>>(P);
-    int gd = (nwords + 127) / 128;
+    k_bbtm_open<true><<<b.B, TAIL_THREADS, smem_slow, s>>>(P);
+    // distinct non-zero kernel weights -> per-row tap masks for the counting path of k_bbtm_disk
+    DiskLevels D{};
+    uint32_t h_mask[TM_DISK_LEVELS * 64] = {0};
+    {
+        const int K = P.K;
+        float vals[TM_DISK_LEVELS];
+        int L = 0;
+        double sum_abs = 0.0;
+        bool ok = K <= 32;
+        for (int i = 0; i < K * K && ok; ++i) {
+            const float w = p.disk[i];
+            sum_abs += fabs((double)w);
+            if (w == 0.f) continue;
+            int l = 0;
+            while (l < L && vals[l] != w) ++l;
+            if (l == L) {
+                if (L == TM_DISK_LEVELS) {
+                    ok = false;
+                    break;
+                }
+                vals[L++] = w;
+            }
+            h_mask[l * K + i / K] |= 1u << (i % K);
+        }
+        D.L = ok ? L : 0;
+        for (int l = 0; l < D.L; ++l) D.val[l] = (double)vals[l];
+        // each of OpenCV's float adds rounds by at most 2^-24 of a partial sum bounded by sum|w|
+        D.margin = 4.0 * (double)K * K * 5.9604644775390625e-8 * (sum_abs > 1.0 ? sum_abs : 1.0) + 1e-9;
+    }
+    if (cudaMemcpyAsync(level_mask, h_mask, (size_t)TM_DISK_LEVELS * 64 * sizeof(uint32_t), cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+    int gd = (nwords + DISK_THREADS - 1) / DISK_THREADS;
     gd = gd < 1 ? 1 : (gd > 256 ? 256 : gd);
-    k_bbtm_disk<<<dim3(gd, b.B), 128, (size_t)P.K * P.K * sizeof(float), s>>>(P);
+    const size_t disk_smem = (((size_t)(P.K * P.K + TM_DISK_LEVELS * P.K) * 4 + 15) & ~(size_t)15) + (size_t)P.K * DISK_THREADS * 8;
+    k_bbtm_disk<<<dim3(gd, b.B), DISK_THREADS, disk_smem, s>>>(P, D, level_mask);
     if (P.runcap > 0) k_bbtm_fill<false><<<b.B, TAIL_THREADS, smem_fast, s>>>(P);
-    k_bbtm_fill<true><<<TM_SLOW_SLOTS, TAIL_THREADS, smem_slow, s>>>(P);
+    k_bbtm_fill<true><<<b.B, TAIL_THREADS, smem_slow, s>>>(P);
     launches += 6;
     return cudaGetLastError() == cudaSuccess ? launches : -1;
 }

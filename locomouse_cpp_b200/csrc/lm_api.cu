@@ -1312,7 +1312,10 @@ int lm_bounding_box_tm(lm_ctx *ctx, const uint8_t *frames, int frames_on_device,
     CK(d_a.alloc(lm_bbox_tm_bits_bytes(*p, cap)));
     CK(d_b.alloc(lm_bbox_tm_bits_bytes(*p, cap)));
     CK(d_slow.alloc((size_t)cap * 2 * sizeof(int)));
-    CK(d_runs.alloc((size_t)lm_bbox_tm_slow_slots() * lm_bbox_tm_slow_runs(*p) * 14 + 64));
+    const int cap_tm = (int)std::min<int64_t>(cap, n);   // run-array slots of the global-memory labelling: one per frame of a chunk
+    CK(d_runs.alloc((size_t)cap_tm * lm_bbox_tm_slow_runs(*p) * 14 + 64));
+    DevBuf d_lmask(st);
+    CK(d_lmask.alloc(512 * sizeof(uint32_t)));
     CK(d_disk.alloc((size_t)p->disk_size * p->disk_size * sizeof(float)));
     CK(d_bbx.alloc((size_t)n * sizeof(double)));
     CK(d_lims.alloc((size_t)n * 2 * sizeof(int32_t)));
@@ -1342,7 +1345,7 @@ int lm_bounding_box_tm(lm_ctx *ctx, const uint8_t *frames, int frames_on_device,
             b.frames = (const uint8_t *)d_stage.p;
         }
         const int rc = lm_launch_bbox_tm(b, *p, (const float *)d_disk.p, (uint32_t *)d_hist.p, (uint8_t *)d_pred.p, (uint32_t *)d_a.p, (uint32_t *)d_b.p,
-                                         (int *)d_slow.p, (unsigned char *)d_runs.p, (double *)d_bbx.p + s0, (int32_t *)d_lims.p + s0 * 2, st);
+                                         (int *)d_slow.p, (unsigned char *)d_runs.p, cap_tm, (uint32_t *)d_lmask.p, (double *)d_bbx.p + s0, (int32_t *)d_lims.p + s0 * 2, st);
         if (rc == -2) return fail(ctx, LM_ERR_INVALID, "side view of %d x %d pixels does not fit the shared-memory bit image", p->side_w, p->side_h);
         if (rc < 0) return fail(ctx, LM_ERR_RUNTIME, "bounding-box launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }

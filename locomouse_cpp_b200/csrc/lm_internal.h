@@ -151,10 +151,10 @@ int lm_launch_bbox_pred(const LmBatch &b, const lm_bb_de_params &p, uint32_t *hi
 // pass 1 of LocoMouse_TM (k_bbox_tm.cu); returns the number of launches, -1 on a launch error, -2 when the side view's bit
 // image does not fit into shared memory
 size_t lm_bbox_tm_bits_bytes(const lm_bb_tm_params &p, int B);
-int lm_bbox_tm_slow_slots();
 size_t lm_bbox_tm_slow_runs(const lm_bb_tm_params &p);
 int lm_launch_bbox_tm(const LmBatch &b, const lm_bb_tm_params &p, const float *d_disk, uint32_t *hist, uint8_t *pred, uint32_t *bits_a,
-                      uint32_t *bits_b, int *need_slow, unsigned char *g_runs, double *bb_x, int32_t *lims, cudaStream_t s);
+                      uint32_t *bits_b, int *need_slow, unsigned char *g_runs, int g_slots, uint32_t *level_mask /* 512 words */, double *bb_x, int32_t *lims,
+                      cudaStream_t s);
 size_t lm_bbox_base_bits_bytes(int n_rows, int n_cols, int B);
 size_t lm_bbox_base_slow_ints(const lm_bb_base_params &p);
 constexpr int LM_BBOX_SLOW_SLOTS = 8;

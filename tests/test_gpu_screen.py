@@ -153,7 +153,7 @@ def test_screen2_job_layouts_are_equivalent(oracle, kw, n, sub):
     assert (0.0, 0.0) in seen and len(seen) >= 3   # the layouts were really different
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("seed", list(range(1, 25)))
 def test_screen2_random_geometries_equal_oracle(oracle, seed):
     """Random geometries for the CTA-pair screen's tiling: image / box sizes (boxes lower than one 128-row tile so that stacked
     tiles span several frames, and taller than 256 rows so that a frame needs two tile pairs), tail boxes whose width is
@@ -169,9 +169,14 @@ def test_screen2_random_geometries_equal_oracle(oracle, seed):
     tsh = lambda: (int(rng.integers(8, 31)), int(rng.integers(8, 31)))
     shapes = tuple(tuple(tsh() for _ in range(3)) for _ in range(2))
     method = str(rng.choice(["TM", "TM_DE"]))
+    # seeds above 6 (the memory-safety fuzz that used to live in tools/fuzz_geometries.py only) also draw a warped calibration
+    # (the gather tiers of k_prep), the connectivity, the stream count and the base method
+    extra = dict(warp=bool(rng.integers(0, 2)), conn=int(rng.choice([4, 8]))) if seed > 6 else {}
+    if seed > 6 and rng.integers(0, 3) == 0:
+        method = "base"
     spec = synth.SynthSpec(method=method, n_rows=side_h + bottom_h, n_cols=n_cols, side_h=side_h, bb_w=bb_w,
                            bb_h_side_tm=max(40, side_h - 15), tshapes=shapes, mouse_scale=min(1.0, bb_w / 400, bottom_h / 235, side_h / 165),
-                           flip=bool(rng.integers(0, 2)), cand_cap=128, match_cap=1024)
+                           flip=bool(rng.integers(0, 2)), cand_cap=128, match_cap=1024, **extra)
     n = int(rng.integers(5, 12))
     cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(spec, n, seed=1000 + seed)
     frames = frames.numpy()
@@ -180,6 +185,8 @@ def test_screen2_random_geometries_equal_oracle(oracle, seed):
         det = Detector(cfg, model, bkg, calib, device=0)
         det.set_option("screen_layout", layout)
         det.set_option("subbatch", int(rng.integers(2, 8)))
+        if seed > 6:
+            det.set_option("streams", int(rng.integers(1, 5)))
         got = det.detect_batch(frames, bx, bs, bb, allow_overflow=True)
         active = det.info("screen_active")
         det.close()

@@ -373,7 +373,7 @@ def test_tm_pass1_on_device_then_detection(tmp_path, oracle):
     fs = cv2.FileStorage(str(tmp_path / "diskfilter.yml"), cv2.FILE_STORAGE_WRITE)
     fs.write("H", disk)
     fs.release()
-    tm_cfg = (f"bw_threshold_bottom: 3\nbw_threshold_side: 3\nmin_pixel_count: 25\nzero_col_pre: 0\nzero_col_post: {cfg.n_cols}\n"
+    tm_cfg = (f"bw_threshold_bottom: 40\nbw_threshold_side: 40\nmin_pixel_count: 25\nzero_col_pre: 0\nzero_col_post: {cfg.n_cols}\n"
               f"zero_row_pre: 0\nzero_row_post: {spec.side_h}\ndisk_filter_file: {tmp_path / 'diskfilter.yml'}\n")
     args = lambda d: [exe, "1", str(d / "config.yml"), str(d / "video.lmv"), str(d / "bkg.lmi"), str(d / "model.lmm"), str(d / "calib.lmc"), "R", str(d)]
     d1 = tmp_path / "ref"
@@ -387,7 +387,7 @@ def test_tm_pass1_on_device_then_detection(tmp_path, oracle):
                         with_boxes=False)
     p = subprocess.run(args(d2), capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
-    P = bb_tm_params(cfg, disk, side_h=spec.side_h, side_threshold=3, min_pixel_count=25, sums_as_float=0)
+    P = bb_tm_params(cfg, disk, side_h=spec.side_h, side_threshold=40, min_pixel_count=25, sums_as_float=0)
     raw, _ = oracle.bounding_box_tm(cfg, bkg, calib, frames, P)
     want_bx = oracle.vecmovingaverage(raw, 5)
     assert (raw > 0).all()

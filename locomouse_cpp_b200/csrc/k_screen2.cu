@@ -28,14 +28,20 @@
 #include <atomic>
 #include <climits>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "lm_internal.h"
 #include "umma_common.cuh"
 
 namespace {
 
-constexpr int S2_THREADS = 192;   // warps 0-3 epilogue, 4 TMA producer, 5 MMA issuer / TMEM owner
-constexpr int S2_WARP_TMA = 4, S2_WARP_MMA = 5;
+// warps 0-7 epilogue (two groups of four: group g = warp >> 2 drains accumulator g, i.e. every other unit; warp & 3 = its TMEM
+// lane quadrant), 8 TMA producer, 9 MMA issuer / TMEM owner.  In isolation the pair instruction runs at the tensor pipe's rate
+// (tools/umma_pair_probe.cu: N = 192 -> 96 cycles); what it needs from the rest of the kernel is an epilogue that drains an
+// accumulator within one unit's MMA time (60 x 64 .. 96 cycles), hence two groups and no dependent global-memory chains below.
+constexpr int S2_THREADS = 320;
+constexpr int S2_WARP_TMA = 8, S2_WARP_MMA = 9;
 constexpr int S2_TILE_M = 128;
 constexpr int S2_TILE_X = 32;
 constexpr int S2_STAGES = 4;      // maximum ring depth; a job uses J.j.stages of them
@@ -69,13 +75,19 @@ struct Screen2Params {
     uint8_t *tailbin[2];
     int tail_pitch;
     int64_t tailbin_stride[2];
+    int whatif;   // timing experiments only (LM_WHATIF_S2): 1 = no TMA loads after the ring's first fill, 2 = epilogue stops after draining TMEM,
+                  // 4 = epilogue emits no tasks,
+                  // 8 = accumulators released unread, 16 = the MMA warp does not wait for window tiles; results of such runs are meaningless
 };
+
+__device__ long long g_s2_dbg[3 * 80];   // LM_WHATIF_S2 & 128: per pair {cycles before the MMA loop, cycles in it, units}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_screen2(const __grid_constant__ Screen2Params P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[2 * S2_STAGES + 4];
     __shared__ uint32_t tmem_base_s;
 
+    const long long dbg_t0 = clock64();
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1;
     int ji = 0;
@@ -114,7 +126,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
         }
         for (int a = 0; a < 2; ++a) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(d_full(a)), "r"(1));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(d_empty(a)), "r"(256));  // 128 epilogue threads x 2 CTAs
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(d_empty(a)), "r"(8));    // one arrival per epilogue warp of the group that drains it, x 2 CTAs
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -129,7 +141,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
 
-    if (warp == S2_WARP_TMA) {
+    const bool bare = (P.whatif & 32) != 0;   // 32: only the MMA issue loop runs (no barriers, no producer, no epilogue)
+    if (bare && warp != S2_WARP_MMA) {
+    } else if (warp == S2_WARP_TMA) {
         // ================= TMA producer (both CTAs): this CTA's y tile of the unit ================================
         const CUtensorMap *tm = &P.tmap[ji];
         const bool stacked = J.j.stacked != 0;
@@ -141,9 +155,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
             mbar_wait(a_empty(stage), phase ^ 1u);
             if (elect_one()) {
                 const uint32_t full = mapa_u32(a_full(stage), 0);  // the leader's barrier counts both CTAs' bytes
-                mbar_arrive_expect_tx_cluster(full, stage_bytes);
+                const bool skip_load = (P.whatif & 1) && u >= prank + nst * J.npair;
+                mbar_arrive_expect_tx_cluster(full, skip_load ? 0u : stage_bytes);
                 const uint32_t dst = smem_u32(sA) + (uint32_t)stage * stage_bytes;
-                if (stacked) {
+                if (skip_load) {
+                } else if (stacked) {
                     for (int p = 0; p < npanel; ++p) tma_load_2d_pair(dst + (uint32_t)p * panel_a, tm, full, x0 + 16 * p, R0);
                 } else {
                     const int f0 = R0 / VH, yf0 = R0 - f0 * VH;
@@ -168,33 +184,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
             const uint32_t b_row = ((uint32_t)npanel * chunk_b) >> 4;
             int stage = 0, acc = 0;
             uint32_t phase = 0, accphase = 0;
+            const long long dbg_t1 = clock64();
+            int dbg_units = 0;
             for (int u = prank; u < nunits; u += J.npair) {
+                ++dbg_units;
                 const int xt = u % J.nxt;
-                const uint32_t idesc = (xt * S2_TILE_X >= J.j.narrow_x0) ? idesc_narrow : idesc_wide;
-                mbar_wait(d_empty(acc), accphase ^ 1u);
-                mbar_wait(a_full(stage), phase);
+                uint32_t idesc = (xt * S2_TILE_X >= J.j.narrow_x0) ? idesc_narrow : idesc_wide;
+                if (P.whatif & 256) idesc = idesc_wide;
+                if (P.whatif & 512) idesc = idesc_narrow;
+                if (!bare) mbar_wait(d_empty(acc), accphase ^ 1u);
+                if (!bare && (!(P.whatif & 16) || u < prank + nst * J.npair)) mbar_wait(a_full(stage), phase);   // 16: window tiles not waited for
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint32_t d = tmem + (uint32_t)acc * (uint32_t)S2_ACC_STRIDE;
-                    uint64_t adesc = umma_desc(smem_u32(sA) + (uint32_t)stage * stage_bytes, panel_a);
-                    uint64_t bdesc = bdesc0;
-                    uint32_t accum = 0;
-                    for (int j = 0; j < KH; ++j) {
-                        uint64_t ad = adesc, bd = bdesc;
-                        for (int k = 0; k < ks; ++k) {
-                            umma_i8_2cta(d, ad, bd, idesc, accum);
-                            accum = 1;
-                            ad += a_step;
-                            bd += b_step;
+                    const uint64_t adesc = umma_desc(smem_u32(sA) + (uint32_t)stage * stage_bytes, panel_a);
+                    const uint32_t alo = (uint32_t)adesc, ahi = (uint32_t)(adesc >> 32), blo = (uint32_t)bdesc0, bhi = (uint32_t)(bdesc0 >> 32);
+                    if (ks == 2 && KH % 6 == 0) {
+                        umma_issue_tile_ks2<6>(d, alo, ahi, blo, bhi, a_step, b_step, b_row, idesc, KH);
+                    } else if (ks == 2 && KH % 5 == 0) {
+                        umma_issue_tile_ks2<5>(d, alo, ahi, blo, bhi, a_step, b_step, b_row, idesc, KH);
+                    } else if (ks == 2 && KH % 4 == 0) {
+                        umma_issue_tile_ks2<4>(d, alo, ahi, blo, bhi, a_step, b_step, b_row, idesc, KH);
+                    } else {
+                        uint32_t a_j = alo, b_j = blo, accum = 0;
+                        for (int j = 0; j < KH; ++j) {
+                            uint32_t a = a_j, b = b_j;
+                            for (int k = 0; k < ks; ++k) {
+                                umma_i8_2cta_lohi(d, a, ahi, b, bhi, idesc, accum);
+                                accum = 1;
+                                a += a_step;
+                                b += b_step;
+                            }
+                            a_j += 1;  // next kernel row: 16 bytes further down the same tile (in both CTAs)
+                            b_j += b_row;
                         }
-                        adesc += 1;  // next kernel row: 16 bytes further down the same tile (in both CTAs)
-                        bdesc += b_row;
                     }
-                    umma_commit_2cta(a_empty(stage));
-                    umma_commit_2cta(d_full(acc));
+                    if (!bare) {
+                        umma_commit_2cta(a_empty(stage));
+                        umma_commit_2cta(d_full(acc));
+                    }
                 }
                 __syncwarp();
-                if (++stage == nst) {
+                if (++stage == nst || (P.whatif & 1024)) {
                     stage = 0;
                     phase ^= 1u;
                 }
@@ -203,25 +234,59 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
                     accphase ^= 1u;
                 }
             }
+            if (bare) {
+                if (elect_one()) umma_commit_2cta(d_full(0));
+                __syncwarp();
+                mbar_wait(d_full(0), 0);
+            }
+            if ((P.whatif & 128) && lane == 0) {
+                g_s2_dbg[3 * pair] = dbg_t1 - dbg_t0;
+                g_s2_dbg[3 * pair + 1] = clock64() - dbg_t1;
+                g_s2_dbg[3 * pair + 2] = dbg_units;
+            }
         }
     } else {
         // ================= epilogue (both CTAs): this CTA's 128 rows x N columns ===================================
         const int v = J.j.view;
         const int pitch = P.win_pitch[v];
-        int acc = 0;
-        uint32_t accphase = 0;
-        for (int u = prank; u < nunits; u += J.npair) {
+        const int grp = warp >> 2, quad = warp & 3;
+        const int row_in_tile = quad * 32 + lane;
+        bool any_point = false;   // paw / snout slots consult the centre pixel
+        for (int t = 0; t < J.j.ntmpl; ++t) any_point |= J.j.feat[t] != LM_TAIL;
+        int it = 0;
+        for (int u = prank; u < nunits; u += J.npair, ++it) {
+            if ((it & 1) != grp) continue;
+            const int acc = grp;
+            const uint32_t accphase = (uint32_t)(it >> 1) & 1u;
             const int tp = u / J.nxt, xt = u - tp * J.nxt;
-            const int R = (2 * tp + (int)rank) * S2_TILE_M + tid, x0 = xt * S2_TILE_X;
+            const int R = (2 * tp + (int)rank) * S2_TILE_M + row_in_tile, x0 = xt * S2_TILE_X;
             const int f = R / VH, y = R - f * VH;   // VH % 4 == 0: the two rows of a patch share f and y >> 1
             const int nar = x0 >= J.j.narrow_x0 ? 1 : 0;
             const int nt = nar ? J.j.ntmpl_narrow : J.j.ntmpl;
+            const bool rowok = f < P.B && y < J.out_h;
+            // centre pixels of this row's 32 outputs (class.cpp:849, 864: candidates need a centre pixel > 25), fetched before
+            // the wait so that their latency is hidden: nine aligned words, bit c of cmask = pixel c > 25
+            uint32_t cw[9];
+            uint32_t csh = 0;
+            if (any_point) {
+                const uint8_t *crow = P.win[v] + (int64_t)f * P.win_stride[v] + (int64_t)(y + J.halo_y) * pitch + x0 + J.halo_x;
+                const uint32_t *cbase = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(crow) & ~(uintptr_t)3);
+                csh = (uint32_t)(reinterpret_cast<uintptr_t>(crow) & 3u) * 8u;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) cw[q] = rowok ? __ldg(cbase + q) : 0u;
+            }
             mbar_wait(d_full(acc), accphase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)acc * (uint32_t)S2_ACC_STRIDE;
-            const bool rowok = f < P.B && y < J.out_h;
+            if (P.whatif & 8) {   // accumulator released unread
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(d_empty(acc), 0);
+                continue;
+            }
+            const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * (uint32_t)S2_ACC_STRIDE;
             uint32_t need_t[3] = {0u, 0u, 0u}, sign_t[3] = {0u, 0u, 0u};
-            for (int t = 0; t < nt; ++t) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                if (t >= nt) break;
                 uint32_t hi[32], lo[32];
                 tmem_ld32(ta + (uint32_t)J.j.col_hi[nar][t], hi);
                 tmem_ld32(ta + (uint32_t)J.j.col_lo[nar][t], lo);
@@ -247,13 +312,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
                 need_t[t] = rowok ? (need & colmask) : 0u;
                 sign_t[t] = sign;
             }
+            // every lane's tcgen05.ld has completed (wait::ld above); one arrival per warp: 128 remote arrivals per unit on the
+            // leader's barrier cost more than the unit's MMAs (the accumulator came back ~6 k cycles after its commit)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive_cluster(d_empty(acc), 0);  // the leader's barrier counts both CTAs' epilogues
-            if (++acc == 2) {
-                acc = 0;
-                accphase ^= 1u;
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(d_empty(acc), 0);  // the leader's barrier counts both CTAs' epilogues
+            if (P.whatif & 2) continue;
+            uint32_t cmask = 0;
+            if (any_point) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t x = __funnelshift_r(cw[q], cw[q + 1], csh);
+                    const uint32_t gt = (((x & 0x7f7f7f7fu) + 0x66666666u) | x) & 0x80808080u;  // bit 7 of each byte: byte >= 26
+                    cmask |= ((gt * 0x00204081u) >> 28) << (4 * q);
+                }
             }
-            for (int t = 0; t < nt; ++t) {
+            // pass 1: final "undecided" masks, tail sign rows, per-lane task counts and their warp prefix sums
+            uint32_t pf_t[3] = {0u, 0u, 0u};
+            int cnt_t[3] = {0, 0, 0}, incl_t[3] = {0, 0, 0}, total_t[3] = {0, 0, 0};
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                if (t >= nt) break;
                 uint32_t need = need_t[t];
                 if (J.j.feat[t] == LM_TAIL) {
                     if (x0 >= J.out_w[t]) continue;  // warp-uniform: no tail columns in this x tile
@@ -270,40 +349,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
                         reinterpret_cast<uint4 *>(tb)[1] = make_uint4(w[4], w[5], w[6], w[7]);
                     }
                     need &= ~sign_t[t];
-                } else if (need) {
-                    const uint8_t *crow = P.win[v] + (int64_t)f * P.win_stride[v] + (int64_t)(y + J.halo_y) * pitch + x0 + J.halo_x;
-                    uint32_t m = need;
-                    while (m) {
-                        const int c = __ffs(m) - 1;
-                        m &= m - 1;
-                        if (__ldg(crow + c) <= 25) need &= ~(1u << c);
-                    }
+                } else {
+                    need &= cmask;
                 }
                 uint32_t pf = lm_nibble_any(need);   // 2x4 patches: bit q = columns 4q .. 4q+3, rows y and y ^ 1 combined below
                 pf |= __shfl_xor_sync(0xffffffffu, pf, 1);
                 const int cnt = ((lane & 1) == 0) ? __popc(pf) : 0;
-                const uint32_t any = __ballot_sync(0xffffffffu, cnt > 0);
-                if (any) {
-                    int incl = cnt;
+                int incl = cnt;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int w2 = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += w2;
-                    }
-                    const int total = __shfl_sync(0xffffffffu, incl, 31);
-                    int base = 0;
-                    if (lane == 31) base = atomicAdd(J.j.ntasks[t], total);
-                    base = __shfl_sync(0xffffffffu, base, 31);
-                    int o = base + incl - cnt;
-                    if (cnt) {
-                        const uint32_t head = ((uint32_t)f << 16) | ((uint32_t)(y >> 1) << 8);
-                        uint32_t m = pf;
-                        while (m) {
-                            const int q = __ffs(m) - 1;
-                            m &= m - 1;
-                            if (o < J.j.task_cap[t]) J.j.tasks[t][o] = head | (uint32_t)((x0 >> 2) + q);
-                            ++o;
-                        }
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int w2 = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += w2;
+                }
+                pf_t[t] = pf;
+                cnt_t[t] = cnt;
+                incl_t[t] = incl;
+                total_t[t] = __shfl_sync(0xffffffffu, incl, 31);
+            }
+            // pass 2: one reservation per non-empty list, issued together (independent round trips to L2)
+            int base_t[3] = {0, 0, 0};
+            if (P.whatif & 4) continue;
+            if (lane == 31) {
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+                    if (t < nt && total_t[t]) base_t[t] = atomicAdd(J.j.ntasks[t], total_t[t]);
+            }
+            // pass 3: the task words
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                if (t >= nt) break;
+                if (!total_t[t]) continue;   // warp-uniform
+                const int base = __shfl_sync(0xffffffffu, base_t[t], 31);
+                if (cnt_t[t]) {
+                    int o = base + incl_t[t] - cnt_t[t];
+                    const uint32_t head = ((uint32_t)f << 16) | ((uint32_t)(y >> 1) << 8);
+                    uint32_t m = pf_t[t];
+                    while (m) {
+                        const int q = __ffs(m) - 1;
+                        m &= m - 1;
+                        if (o < J.j.task_cap[t]) J.j.tasks[t][o] = head | (uint32_t)((x0 >> 2) + q);
+                        ++o;
                     }
                 }
             }
@@ -370,7 +455,7 @@ int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s) {
     size_t smem = 0;
     double work[6], total = 0.0;
     long long macs = 0;
-    auto icost = [](int N) { return std::max(93.0, 42.0 + N / 2.0); };  // cycles per instruction (tools/umma_sw_probe.cu)
+    auto icost = [](int N) { return std::max(43.0, N / 2.0); };  // cycles per pair instruction (tools/umma_pair_probe.cu: the tensor pipe's rate down to N = 64)
     for (int v = 0; v < 2; ++v)
         for (int q = 0; q < 3; ++q) {
             const LmScreen2Job &sj = b.scr.job2[v][q];
@@ -430,13 +515,32 @@ int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s) {
         P.tailbin_stride[v] = (int64_t)b.bb_h[v] * b.tail_pitch;
     }
     P.tail_pitch = b.tail_pitch;
+    {
+        static const int whatif = getenv("LM_WHATIF_S2") ? atoi(getenv("LM_WHATIF_S2")) : 0;
+        P.whatif = whatif;
+    }
     static_assert(sizeof(Screen2Params) <= 4000, "kernel parameter space");
     static LmDevOnce once;
     if (once.first()) {
         if (cudaFuncSetAttribute(k_screen2, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) return -1;
     }
+    if (P.whatif & 64) {
+        for (int q = 0; q < P.njobs; ++q) {
+            const Screen2JobDev &J = P.job[q];
+            fprintf(stderr, "k_screen2 job %d: view %d ntmpl %d KH %d ks %d rows %d nhalf %d nhalf_narrow %d narrow_x0 %d nxt %d ntp %d VH %d npair %d stages %d stacked %d smem %zu\n", q,
+                    J.j.view, J.j.ntmpl, J.j.KH, J.j.ks, J.j.rows, J.j.nhalf, J.j.nhalf_narrow, J.j.narrow_x0, J.nxt, J.ntp, J.VH, J.npair, J.j.stages, J.j.stacked, smem);
+        }
+    }
     g_last_macs.store(macs);
     const int pairs = P.job[P.njobs - 1].pair_begin + P.job[P.njobs - 1].npair;
     k_screen2<<<2 * pairs, S2_THREADS, smem, s>>>(P);
+    if (P.whatif & 128) {
+        long long h[3 * 80];
+        cudaStreamSynchronize(s);
+        cudaMemcpyFromSymbol(h, g_s2_dbg, sizeof(h));
+        for (int q = 0; q < pairs; q += 6)
+            fprintf(stderr, "k_screen2 pair %d: setup %lld cycles, MMA loop %lld cycles for %lld units = %.1f per MMA\n", q, h[3 * q], h[3 * q + 1], h[3 * q + 2],
+                    (double)h[3 * q + 1] / (60.0 * (double)h[3 * q + 2]));
+    }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

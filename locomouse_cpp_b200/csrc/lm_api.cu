@@ -254,8 +254,8 @@ int prepare_screen(lm_ctx *ctx, LmBatch &b, int want, size_t B) {
             if (lm_screen2_smem_bytes(S.KH, S.ks, S.rows, 32 * S.nplanes, S.stages) <= smem_limit) return true;
         return false;
     };
-    // issue cost of one tile in units of MMA cycles: KH * ks instructions of ~max(93, 42 + N/2) cycles (tools/umma_sw_probe.cu)
-    auto icost = [](int N) { return std::max(93.0, 42.0 + N / 2.0); };
+    // cost of one tile in tensor-pipe cycles: KH * ks instructions of N/2 cycles each
+    auto icost = [](int N) { return std::max(43.0, N / 2.0); };   // cycles per pair instruction (tools/umma_pair_probe.cu)
     const int nxt_box = (k.bb_w + 31) / 32, nxt_tail = (k.tail_w + 31) / 32;
     for (int v = 0; v < 2 && have2; ++v) {
         Spec ps = SPEC_PS, pst = SPEC_PST, tl = single(LM_TAIL);

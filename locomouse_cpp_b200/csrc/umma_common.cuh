@@ -81,6 +81,37 @@ __device__ __forceinline__ void umma_i8_2cta(uint32_t tmem_d, uint64_t adesc, ui
                  : "memory");
 }
 
+// The same instruction with each descriptor given as its two 32-bit halves: only the low word (start address >> 4 in bits 0-13,
+// which never carries out of its field for shared-memory addresses) moves between the instructions of a tile, so an issue loop
+// needs one 32-bit add per operand and instruction.
+__device__ __forceinline__ void umma_i8_2cta_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{.reg .pred p; .reg .b64 da, db; setp.ne.b32 p, %6, 0; mov.b64 da, {%1, %2}; mov.b64 db, {%3, %4};"
+        " tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %5, p;}" ::"r"(tmem_d),
+        "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// All MMAs of one window tile for ks = 2 K steps per kernel row, U kernel rows per loop iteration (KH % U == 0): 2 U instructions
+// whose descriptors are independent sums off the iteration's base, so that no instruction waits for the registers of the one
+// before it (a serial add -> R2UR -> UTCIMMA chain over four re-used uniform registers cost ~22 cycles per instruction).
+template <int U>
+__device__ __forceinline__ void umma_issue_tile_ks2(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t a_step, uint32_t b_step,
+                                                    uint32_t b_row, uint32_t idesc, int KH) {
+    uint32_t accum = 0;
+    for (int j = 0; j < KH; j += U) {
+#pragma unroll
+        for (int jj = 0; jj < U; ++jj) {
+            const uint32_t a = alo + (uint32_t)jj, b = blo + (uint32_t)jj * b_row;
+            umma_i8_2cta_lohi(d, a, ahi, b, bhi, idesc, accum);
+            accum = 1;
+            umma_i8_2cta_lohi(d, a + a_step, ahi, b + b_step, bhi, idesc, 1u);
+        }
+        alo += (uint32_t)U;
+        blo += (uint32_t)U * b_row;
+    }
+}
+
 // ---- TMA (cp.async.bulk.tensor) into a CTA pair's window ring ------------------------------------------------
 // shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `cta` of the cluster
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {

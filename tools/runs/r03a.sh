@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r03a_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r03a_pytest.log
+python tools/whatif.py 10000 0,4,123 4 > gpurun_out/r03a_whatif.txt 2>&1
+timeout 900 python bench.py --steps 8 --warmup 3 > gpurun_out/r03a_bench.json 2> gpurun_out/r03a_bench.err; echo "rc=$?" >> gpurun_out/r03a_bench.err

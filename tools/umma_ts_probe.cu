@@ -20,7 +20,13 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     return false;
 }
 
-// mode 0 = SS (A and B from shared memory), 1 = TS (A from tensor memory, B from shared memory)
+// mode 0 = SS (A and B from shared memory), 1 = TS (A from tensor memory, B from shared memory),
+// mode 2 = "CP+TS": the k_screen2 orientation (A = shifted window rows) with every instruction's A tile first copied
+//          shared -> tensor memory by tcgen05.cp.128x256b into a rotating set of four 8-column buffers (tcgen05.cp and
+//          tcgen05.mma execute in issue order), then consumed in TS form: does the copy engine's shared-memory read overlap
+//          the tensor pipe where the SS form's A read does not?
+// mode 3 = numerical check of mode 2's operand layout: D(SS) in columns 0.., D(CP+TS) in columns 256.. on pseudo-random
+//          operands; status 2 if any accumulator differs.
 __global__ void __launch_bounds__(128) rate(int mode, int N, int chain, long long *cycles, int *status) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -28,7 +34,8 @@ __global__ void __launch_bounds__(128) rate(int mode, int N, int chain, long lon
     const int tid = threadIdx.x, warp = tid >> 5;
     constexpr int R = 160;
     const uint32_t panel_a = R * 16, panel_b = (uint32_t)(N + 32) * 16;   // B rows shift like the window rows do
-    for (int i = tid; i < (int)((4 * panel_a + 4 * panel_b) / 4); i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x01010101u;
+    for (int i = tid; i < (int)((4 * panel_a + 4 * panel_b) / 4); i += 128)
+        reinterpret_cast<uint32_t *>(smem)[i] = mode == 3 ? ((uint32_t)i * 2654435761u) >> 3 : 0x01010101u;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;");
@@ -51,7 +58,19 @@ __global__ void __launch_bounds__(128) rate(int mode, int N, int chain, long lon
         for (int i = 0; i < chain; ++i) {
             const int j = i & 15, ks = i & 1;
             uint64_t bd = make_desc(b0 + j * 16 + ks * 2 * panel_b, panel_b);
-            if (mode == 0) {
+            if (mode == 2) {
+                uint64_t ad = make_desc(a0 + j * 16 + ks * 2 * panel_a, panel_a);
+                const uint32_t at = tmem + 256u + (uint32_t)((i & 3) * 8);
+                asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(at), "l"(ad) : "memory");
+                asm volatile("{.reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;}" ::"r"(tmem), "r"(at), "l"(bd), "r"(idesc), "r"(1) : "memory");
+            } else if (mode == 3) {
+                uint64_t ad = make_desc(a0 + j * 16 + ks * 2 * panel_a, panel_a);
+                const uint32_t at = tmem + 500u;
+                const int acc = i > 0;
+                asm volatile("{.reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;}" ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+                asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(at), "l"(ad) : "memory");
+                asm volatile("{.reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;}" ::"r"(tmem + 256u), "r"(at), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+            } else if (mode == 0) {
                 uint64_t ad = make_desc(a0 + j * 16 + ks * 2 * panel_a, panel_a);
                 asm volatile("{.reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;}" ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(1) : "memory");
             } else {
@@ -68,6 +87,20 @@ __global__ void __launch_bounds__(128) rate(int mode, int N, int chain, long lon
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
+    if (mode == 3) {
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        int bad = 0;
+        for (int c = 0; c < N; ++c) {
+            uint32_t x, y;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(x) : "r"(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(y) : "r"(tmem + ((uint32_t)(warp * 32) << 16) + 256u + (uint32_t)c));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            bad += (x != y) || (x == 0u);
+        }
+        if (bad) atomicMax(status, 2);
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+    }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
@@ -77,11 +110,13 @@ int main() {
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
     cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    const int chain = 6000;
-    for (int mode = 0; mode < 2; ++mode)
+    const int chain_t = 6000;
+    for (int mode = 0; mode < 4; ++mode)
         for (int N : {64, 128, 192, 256}) {
+            if (mode == 3 && N > 192) continue;   // the check keeps its second accumulator at column 256 and A at 500
             cudaMemset(dC, 0, 8); cudaMemset(dS, 0, 4);
             const size_t smem = 4 * 160 * 16 + 4 * (N + 32) * 16;
+            const int chain = mode == 3 ? 37 : chain_t;
             rate<<<nsm, 128, smem>>>(mode, N, chain, dC, dS);  // warm-up
             rate<<<nsm, 128, smem>>>(mode, N, chain, dC, dS);
             cudaError_t e = cudaDeviceSynchronize();
@@ -89,7 +124,7 @@ int main() {
             cudaMemcpy(&c, dC, 8, cudaMemcpyDeviceToHost); cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost);
             const double per = (double)c / chain;
             printf("{\"grid\": %d, \"operands\": \"%s\", \"N\": %d, \"cuda\": \"%s\", \"status\": %d, \"cycles_per_mma\": %.1f, \"mac_per_cycle_per_sm\": %.0f}\n",
-                   nsm, mode == 0 ? "SS" : "TS", N, cudaGetErrorString(e), st, per, 128.0 * N * 32.0 / per);
+                   nsm, mode == 0 ? "SS" : mode == 1 ? "TS" : mode == 2 ? "CP+TS" : "CP+TS check vs SS", N, cudaGetErrorString(e), st, per, 128.0 * N * 32.0 / per);
             if (e != cudaSuccess) return 1;
         }
     return 0;

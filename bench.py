@@ -285,7 +285,8 @@ def main():
 
     def executed_int8(det, ms_per_launch, flop_alg, sm_mhz, rank, local):
         """The int8 multiply-accumulates k_screen2 issues per launch (counted by the launcher from its job table) against
-        the int8 tensor pipe: nominal 8192 MAC/clk/SM and the best rate tools/umma_rate_probe reaches on this GPU."""
+        the int8 tensor pipe: nominal 8192 MAC/clk/SM and the rate tools/umma_pair_probe measures on this GPU for the kernel's own
+        instruction (tcgen05.mma.cta_group::2.kind::i8, M = 256, N = 192, same descriptors, no producer / epilogue)."""
         try:
             macs = float(det.info("screen_macs"))
         except Exception:
@@ -299,7 +300,7 @@ def main():
                "note": "executed/algorithmic = two int8 weight digits x 64/30 Toeplitz K padding x tile padding"}
         try:
             if rank == 0:
-                o = subprocess.run([os.path.join(ROOT, "tools", "umma_rate_probe")], capture_output=True, text=True, timeout=120,
+                o = subprocess.run([os.path.join(ROOT, "tools", "umma_pair_probe")], capture_output=True, text=True, timeout=120,
                                    env=dict(os.environ, CUDA_VISIBLE_DEVICES=str(local))).stdout
                 best = 0.0
                 for ln in o.splitlines():
@@ -307,13 +308,13 @@ def main():
                         j = json.loads(ln)
                     except Exception:
                         continue
-                    if j.get("kind") == "i8" and j.get("status") == 0 and j.get("grid", 0) >= 148:
+                    if j.get("cg") == 2 and j.get("N") == 192 and j.get("cuda") == "no error" and j.get("grid", 0) >= 148 and not j.get("mix"):
                         best = max(best, float(j.get("mac_per_cycle_per_sm", 0.0)))
                 if best > 0:
                     probe = 148 * best * 2 * sm_mhz * 1e6 / 1e12
                     out["int8_probe_peak_tops"] = probe
                     out["frac_of_int8_probe_peak"] = tops / probe
-                    out["probe"] = "tools/umma_rate_probe: best kind::i8 SS-form rate on all SMs (mac/clk/SM) x 148 x SM clock"
+                    out["probe"] = "tools/umma_pair_probe: the kernel's own pair instruction (M 256, N 192, K 32, kind::i8) on all SMs (mac/clk/SM) x 148 x SM clock"
         except Exception as ex:  # pragma: no cover
             out["probe_error"] = repr(ex)
         return out

@@ -35,6 +35,9 @@ struct NmsSmem {
     __device__ __forceinline__ int &slot(int i) const { return reinterpret_cast<int *>(key)[2 * i + 1]; }
 };
 
+// shared memory in front of the list arrays: root_rank[cand_cap], rounded to the alignment of the 64-bit keys
+__host__ __device__ __forceinline__ size_t nms_cand_bytes(int cand_cap) { return ((size_t)cand_cap * 4 + 15) & ~(size_t)15; }
+
 __device__ __forceinline__ NmsSmem carve(unsigned char *base, int P) {
     NmsSmem m;
     m.key = reinterpret_cast<unsigned long long *>(base);
@@ -155,10 +158,12 @@ __device__ void write_candidates(const NmsSmem &m, int n, int ncand, int cap, lm
 
 // ---- nmsMax ------------------------------------------------------------------------------------------
 template <int NMS_THREADS>
-__global__ void __launch_bounds__(NMS_THREADS) k_nms_bottom(const __grid_constant__ LmBatch b, int P, int lo, int hi) {
+__global__ void __launch_bounds__(NMS_THREADS) k_nms_bottom(const __grid_constant__ LmBatch b, int P, int lo, int hi, unsigned char *scratch) {
     extern __shared__ __align__(16) unsigned char raw[];
-    NmsSmem m = carve(raw, P);
-    int *root_rank = reinterpret_cast<int *>(m.xy + P);  // [cand_cap]
+    // lists of the small class live in shared memory; the rare longer ones in this CTA's slice of a global scratch array
+    // (16 P bytes per list), so that no launch of the stage asks for more shared memory than fits beside a k_screen2 CTA
+    NmsSmem m = carve(scratch ? scratch + (size_t)blockIdx.x * (size_t)P * 16 : raw + nms_cand_bytes(b.cand_cap), P);
+    int *root_rank = reinterpret_cast<int *>(raw);  // [cand_cap]
     __shared__ int s_n, s_nc;
     const int f = blockIdx.x >> 1, feat = blockIdx.x & 1, tid = threadIdx.x;
     {   // size class of this list (the two launches partition the lists by raw count)
@@ -233,10 +238,12 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_bottom(const __grid_constan
 
 // ---- peakClustering ----------------------------------------------------------------------------------
 template <int NMS_THREADS>
-__global__ void __launch_bounds__(NMS_THREADS) k_nms_side(const __grid_constant__ LmBatch b, int P, int lo, int hi) {
+__global__ void __launch_bounds__(NMS_THREADS) k_nms_side(const __grid_constant__ LmBatch b, int P, int lo, int hi, unsigned char *scratch) {
     extern __shared__ __align__(16) unsigned char raw[];
-    NmsSmem m = carve(raw, P);
-    int *root_rank = reinterpret_cast<int *>(m.xy + P);
+    // lists of the small class live in shared memory; the rare longer ones in this CTA's slice of a global scratch array
+    // (16 P bytes per list), so that no launch of the stage asks for more shared memory than fits beside a k_screen2 CTA
+    NmsSmem m = carve(scratch ? scratch + (size_t)blockIdx.x * (size_t)P * 16 : raw + nms_cand_bytes(b.cand_cap), P);
+    int *root_rank = reinterpret_cast<int *>(raw);
     __shared__ int s_n, s_next;
     const int f = blockIdx.x >> 1, feat = blockIdx.x & 1, tid = threadIdx.x;
     lm_cand *out = b.side + (int64_t)(f * 2 + feat) * b.cand_cap;
@@ -306,45 +313,47 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_side(const __grid_constant_
     }
 }
 
-size_t nms_smem(int P, int cand_cap) {
-    // key 8 (later score + slot) + link 4 + xy 4 = 16 bytes per entry
-    return (size_t)P * 16 + (size_t)cand_cap * 4 + 16;
-}
 
 }  // namespace
 
 int lm_launch_nms(const LmBatch &b, cudaStream_t s) {
     int P = 2;
     while (P < b.det_cap) P <<= 1;
-    // Size classes: lists of up to SMALL (then MID) positives run with a small shared-memory footprint (several CTAs per
-    // SM, and room next to a resident k_screen2 CTA of the neighbouring sub-batch); the rare longer lists run in a launch
-    // sized for det_cap (the other CTAs of each launch exit at once).
-    int SMALL = 1024, MID = 2048;
+    // Size classes: lists of up to SMALL positives are sorted and clustered in shared memory (16 B per entry: a CTA fits
+    // beside a resident k_screen2 CTA of a neighbouring sub-batch); the rare longer lists use the same code on a slice of
+    // a global scratch array (the other CTAs of that launch exit at once), so that no launch waits for screen-free SMs.
+    int SMALL = 1024;
     if (const char *e = getenv("LM_NMS_SMALL")) SMALL = std::max(2, atoi(e));
     static LmDevOnce once;
     if (once.first()) {
         cudaFuncSetAttribute(k_nms_bottom<NMS_BIG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_nms_side<NMS_BIG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        lm_prefer_max_shared(k_nms_bottom<NMS_BIG_T>);
+        lm_prefer_max_shared(k_nms_side<NMS_BIG_T>);
+        lm_prefer_max_shared(k_nms_bottom<NMS_SMALL_T>);
+        lm_prefer_max_shared(k_nms_side<NMS_SMALL_T>);
     }
     int launches = 0;
     int cls[4], ncls = 0;
-    for (int c : {SMALL, MID, P})
+    for (int c : {SMALL, P})
         if (ncls == 0 || (c > cls[ncls - 1] && cls[ncls - 1] < P)) cls[ncls++] = std::min(c, P);
     for (int view = 0; view < 2; ++view) {
         int lo = -1;
         for (int q = 0; q < ncls; ++q) {
-            const size_t smem = nms_smem(cls[q], b.cand_cap);
             const bool small = q == 0 && cls[q] <= 1024;   // few entries: half the threads, so that more CTAs are resident
+            unsigned char *scratch = q == 0 ? nullptr : b.nms_scratch;   // the views' launches follow each other in the stream
+            const size_t smem = nms_cand_bytes(b.cand_cap) + (q == 0 ? (size_t)cls[q] * 16 : 0);
+            if (q > 0 && !scratch) return -1;
             if (view == 0) {
                 if (small)
-                    k_nms_bottom<NMS_SMALL_T><<<b.B * 2, NMS_SMALL_T, smem, s>>>(b, cls[q], lo, cls[q]);
+                    k_nms_bottom<NMS_SMALL_T><<<b.B * 2, NMS_SMALL_T, smem, s>>>(b, cls[q], lo, cls[q], scratch);
                 else
-                    k_nms_bottom<NMS_BIG_T><<<b.B * 2, NMS_BIG_T, smem, s>>>(b, cls[q], lo, cls[q]);
+                    k_nms_bottom<NMS_BIG_T><<<b.B * 2, NMS_BIG_T, smem, s>>>(b, cls[q], lo, cls[q], scratch);
             } else {
                 if (small)
-                    k_nms_side<NMS_SMALL_T><<<b.B * 2, NMS_SMALL_T, smem, s>>>(b, cls[q], lo, cls[q]);
+                    k_nms_side<NMS_SMALL_T><<<b.B * 2, NMS_SMALL_T, smem, s>>>(b, cls[q], lo, cls[q], scratch);
                 else
-                    k_nms_side<NMS_BIG_T><<<b.B * 2, NMS_BIG_T, smem, s>>>(b, cls[q], lo, cls[q]);
+                    k_nms_side<NMS_BIG_T><<<b.B * 2, NMS_BIG_T, smem, s>>>(b, cls[q], lo, cls[q], scratch);
             }
             ++launches;
             lo = cls[q];

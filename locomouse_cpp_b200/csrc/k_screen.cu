@@ -466,6 +466,11 @@ __global__ void __launch_bounds__(SP_THREADS) k_corr_sparse(const __grid_constan
 
 template <int KW>
 cudaError_t launch_sparse_kw(const SparseParams &P, dim3 grid, size_t smem, bool fma, cudaStream_t s) {
+    static LmDevOnce once;
+    if (once.first()) {
+        lm_prefer_max_shared(k_corr_sparse<KW, true>);
+        lm_prefer_max_shared(k_corr_sparse<KW, false>);
+    }
     if (fma)
         k_corr_sparse<KW, true><<<grid, SP_THREADS, smem, s>>>(P, KW);
     else
@@ -656,7 +661,7 @@ int lm_launch_screen(const LmBatch &b, cudaStream_t s) {
     Q.det = b.det;
     Q.det_count = b.det_count;
 
-    if (cudaMemsetAsync(b.scr.ntasks, 0, 6 * sizeof(int), s) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(b.scr.ntasks, 0, 16 * sizeof(int), s) != cudaSuccess) return -1;
     static LmDevOnce once;
     if (once.first()) {
         if (cudaFuncSetAttribute(k_screen, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) return -1;
@@ -668,6 +673,7 @@ int lm_launch_screen(const LmBatch &b, cudaStream_t s) {
         if (hi) {
             if (cudaEventRecord(b.ev_screen_go, s) != cudaSuccess || cudaStreamWaitEvent(b.screen_stream, b.ev_screen_go, 0) != cudaSuccess) return -1;
         }
+        if (b.ev_screen_start) cudaEventRecord(b.ev_screen_start, hi ? b.screen_stream : s);
         if (!(lm_whatif_skip() & 4) && lm_launch_screen2_kernel(b, hi ? b.screen_stream : s) < 0) return -1;
         if (hi) {
             if (cudaEventRecord(b.ev_screen_done, b.screen_stream) != cudaSuccess || cudaStreamWaitEvent(s, b.ev_screen_done, 0) != cudaSuccess) return -1;

@@ -47,6 +47,7 @@ constexpr int S2_TILE_X = 32;
 constexpr int S2_STAGES = 4;      // maximum ring depth; a job uses J.j.stages of them
 constexpr int S2_TMEM_COLS = 512; // two accumulators of up to 256 columns
 constexpr int S2_ACC_STRIDE = 256;
+constexpr int S2_RING = 16;       // published unit indices in flight (the scheduler runs at most stages + 4 units ahead of the slowest reader)
 
 struct Screen2JobDev {
     LmScreen2Job j;
@@ -55,6 +56,7 @@ struct Screen2JobDev {
     int ntp;                  // 256-row tile pairs over the whole sub-batch
     int VH;                   // rows between consecutive frames in tile-row space (window height when stacked)
     int pair_begin, npair;
+    int *next_unit;           // device counter (zeroed with the task counters): units beyond each pair's first are claimed here
     int halo_x, halo_y;
     // 32-bit form of the thresholds on H = hi + (lo >> 8) (V = 256 H + (lo & 255)):  V > t_lo  =>  H >= q_need;
     // H > q_sign  =>  V > t_hi.  Conservative by less than one hi-digit unit (256 of ~2e5 units between t_lo and t_hi).
@@ -77,15 +79,18 @@ struct Screen2Params {
     int64_t tailbin_stride[2];
     int whatif;   // timing experiments only (LM_WHATIF_S2): 1 = no TMA loads after the ring's first fill, 2 = epilogue stops after draining TMEM,
                   // 4 = epilogue emits no tasks,
-                  // 8 = accumulators released unread, 16 = the MMA warp does not wait for window tiles; results of such runs are meaningless
+                  // 8 = accumulators released unread, 16 = the MMA warp does not wait for window tiles, 64 = print the jobs,
+                  // 128 = print per-pair MMA-loop cycles; results of runs with bits 1-16 are meaningless
 };
 
 __device__ long long g_s2_dbg[3 * 80];   // LM_WHATIF_S2 & 128: per pair {cycles before the MMA loop, cycles in it, units}
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_screen2(const __grid_constant__ Screen2Params P) {
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(96) k_screen2(const __grid_constant__ Screen2Params P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[2 * S2_STAGES + 4];
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t sbar[S2_RING];   // "unit of iteration it published", one per ring slot, in each CTA
+    __shared__ int unit_ring[S2_RING];
 
     const long long dbg_t0 = clock64();
     const uint32_t rank = cluster_ctarank();
@@ -128,6 +133,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(d_full(a)), "r"(1));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(d_empty(a)), "r"(8));    // one arrival per epilogue warp of the group that drains it, x 2 CTAs
         }
+        for (int q = 0; q < S2_RING; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&sbar[q])), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == S2_WARP_MMA) {
@@ -141,21 +147,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
 
-    const bool bare = (P.whatif & 32) != 0;   // 32: only the MMA issue loop runs (no barriers, no producer, no epilogue)
-    if (bare && warp != S2_WARP_MMA) {
-    } else if (warp == S2_WARP_TMA) {
+    // Units (256-row tile pair x 32-column x tile) are dealt dynamically: a pair's first unit is its rank in the job, the others are
+    // claimed from the job's counter by the leader CTA's producer warp, which publishes the index of iteration `it` in slot
+    // it % S2_RING of both CTAs' rings (-1: no more work).  A pair whose SMs were still busy with another kernel when the launch
+    // began simply claims fewer units; every role reads the ring after waiting for the slot's barrier.
+    auto unit_of = [&](int it) -> int {
+        mbar_wait_cluster(smem_u32(&sbar[it & (S2_RING - 1)]), (uint32_t)(it / S2_RING) & 1u);
+        return *reinterpret_cast<volatile int *>(&unit_ring[it & (S2_RING - 1)]);
+    };
+    if (warp == S2_WARP_TMA) {
         // ================= TMA producer (both CTAs): this CTA's y tile of the unit ================================
         const CUtensorMap *tm = &P.tmap[ji];
         const bool stacked = J.j.stacked != 0;
         int stage = 0;
         uint32_t phase = 0;
-        for (int u = prank; u < nunits; u += J.npair) {
+        int u_claim = prank;   // leader: the unit of the coming iteration (lane 0 holds the claimed value)
+        for (int it = 0;; ++it) {
+            int u;
+            if (rank == 0) {
+                u = __shfl_sync(0xffffffffu, u_claim, 0);
+                if (u >= nunits) u = -1;
+                if (lane == 0) {
+                    const uint32_t slot = (uint32_t)it & (S2_RING - 1);
+                    unit_ring[slot] = u;
+                    st_shared_cluster_u32(mapa_u32(smem_u32(&unit_ring[slot]), 1), (uint32_t)u);
+                    mbar_arrive_cluster(smem_u32(&sbar[slot]), 0);
+                    mbar_arrive_cluster(smem_u32(&sbar[slot]), 1);
+                    if (u >= 0) u_claim = J.npair + atomicAdd(J.next_unit, 1);   // in flight while the ring stage is awaited below
+                }
+            } else {
+                u = unit_of(it);
+            }
+            if (u < 0) break;
             const int tp = u / J.nxt, xt = u - tp * J.nxt;
             const int R0 = (2 * tp + (int)rank) * S2_TILE_M, x0 = xt * S2_TILE_X;  // first tile row in tile-row space
             mbar_wait(a_empty(stage), phase ^ 1u);
             if (elect_one()) {
                 const uint32_t full = mapa_u32(a_full(stage), 0);  // the leader's barrier counts both CTAs' bytes
-                const bool skip_load = (P.whatif & 1) && u >= prank + nst * J.npair;
+                const bool skip_load = (P.whatif & 1) && it >= nst;
                 mbar_arrive_expect_tx_cluster(full, skip_load ? 0u : stage_bytes);
                 const uint32_t dst = smem_u32(sA) + (uint32_t)stage * stage_bytes;
                 if (skip_load) {
@@ -186,14 +215,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
             uint32_t phase = 0, accphase = 0;
             const long long dbg_t1 = clock64();
             int dbg_units = 0;
-            for (int u = prank; u < nunits; u += J.npair) {
+            for (int it = 0;; ++it) {
+                const int u = unit_of(it);
+                if (u < 0) break;
                 ++dbg_units;
                 const int xt = u % J.nxt;
-                uint32_t idesc = (xt * S2_TILE_X >= J.j.narrow_x0) ? idesc_narrow : idesc_wide;
-                if (P.whatif & 256) idesc = idesc_wide;
-                if (P.whatif & 512) idesc = idesc_narrow;
-                if (!bare) mbar_wait(d_empty(acc), accphase ^ 1u);
-                if (!bare && (!(P.whatif & 16) || u < prank + nst * J.npair)) mbar_wait(a_full(stage), phase);   // 16: window tiles not waited for
+                const uint32_t idesc = (xt * S2_TILE_X >= J.j.narrow_x0) ? idesc_narrow : idesc_wide;
+                mbar_wait(d_empty(acc), accphase ^ 1u);
+                if (!(P.whatif & 16) || it < nst) mbar_wait(a_full(stage), phase);   // 16: window tiles not waited for
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint32_t d = tmem + (uint32_t)acc * (uint32_t)S2_ACC_STRIDE;
@@ -219,13 +248,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
                             b_j += b_row;
                         }
                     }
-                    if (!bare) {
-                        umma_commit_2cta(a_empty(stage));
-                        umma_commit_2cta(d_full(acc));
-                    }
+                    umma_commit_2cta(a_empty(stage));
+                    umma_commit_2cta(d_full(acc));
                 }
                 __syncwarp();
-                if (++stage == nst || (P.whatif & 1024)) {
+                if (++stage == nst) {
                     stage = 0;
                     phase ^= 1u;
                 }
@@ -233,11 +260,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
                     acc = 0;
                     accphase ^= 1u;
                 }
-            }
-            if (bare) {
-                if (elect_one()) umma_commit_2cta(d_full(0));
-                __syncwarp();
-                mbar_wait(d_full(0), 0);
             }
             if ((P.whatif & 128) && lane == 0) {
                 g_s2_dbg[3 * pair] = dbg_t1 - dbg_t0;
@@ -253,8 +275,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
         const int row_in_tile = quad * 32 + lane;
         bool any_point = false;   // paw / snout slots consult the centre pixel
         for (int t = 0; t < J.j.ntmpl; ++t) any_point |= J.j.feat[t] != LM_TAIL;
-        int it = 0;
-        for (int u = prank; u < nunits; u += J.npair, ++it) {
+        for (int it = 0;; ++it) {
+            const int u = unit_of(it);
+            if (u < 0) break;
             if ((it & 1) != grp) continue;
             const int acc = grp;
             const uint32_t accphase = (uint32_t)(it >> 1) & 1u;
@@ -287,24 +310,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1) k_scr
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
                 if (t >= nt) break;
-                uint32_t hi[32], lo[32];
-                tmem_ld32(ta + (uint32_t)J.j.col_hi[nar][t], hi);
-                tmem_ld32(ta + (uint32_t)J.j.col_lo[nar][t], lo);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // two halves of 16 columns: 32 live accumulator registers instead of 64, so that the CTA leaves room in the
+                // register file for the other kernels' CTAs on this SM
                 const int q_need = J.q_need[t], q_sign = J.q_sign[t];
+                const bool is_tail = J.j.feat[t] == LM_TAIL;   // warp-uniform: only the tail consumes the "provably positive" map
                 uint32_t need = 0, sign = 0;
-                if (J.j.feat[t] == LM_TAIL) {  // warp-uniform: only the tail consumes the "provably positive" map
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int H = (int)hi[c] + ((int)lo[c] >> 8);
-                        if (H >= q_need) need |= 1u << c;
-                        if (H > q_sign) sign |= 1u << c;
-                    }
-                } else {
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t hi[16], lo[16];
+                    tmem_ld16(ta + (uint32_t)(J.j.col_hi[nar][t] + 16 * h), hi);
+                    tmem_ld16(ta + (uint32_t)(J.j.col_lo[nar][t] + 16 * h), lo);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (is_tail) {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int H = (int)hi[c] + ((int)lo[c] >> 8);
-                        if (H >= q_need) need |= 1u << c;
+                        for (int c = 0; c < 16; ++c) {
+                            const int H = (int)hi[c] + ((int)lo[c] >> 8);
+                            if (H >= q_need) need |= 1u << (16 * h + c);
+                            if (H > q_sign) sign |= 1u << (16 * h + c);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const int H = (int)hi[c] + ((int)lo[c] >> 8);
+                            if (H >= q_need) need |= 1u << (16 * h + c);
+                        }
                     }
                 }
                 const int wvalid = J.out_w[t] - x0;
@@ -468,6 +497,7 @@ int lm_launch_screen2_kernel(const LmBatch &b, cudaStream_t s) {
                 ow = std::max(ow, J.out_w[t]);
             }
             J.out_h = b.view[v].box_h;
+            J.next_unit = b.scr.ntasks + 8 + P.njobs;
             J.nxt = (ow + S2_TILE_X - 1) / S2_TILE_X;
             const int nytp = ((J.out_h + S2_TILE_M - 1) / S2_TILE_M + 1) / 2;
             J.VH = sj.stacked ? b.view[v].win_h : 2 * S2_TILE_M * nytp;

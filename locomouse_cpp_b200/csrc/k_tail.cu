@@ -209,6 +209,8 @@ int lm_launch_tail(const LmBatch &b, cudaStream_t s) {
     static LmDevOnce once;
     if (once.first()) {
         cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        lm_prefer_max_shared(k_tail);
+        lm_prefer_max_shared(k_tail_slow);
     }
     int *need_slow = b.cc_flag;
     // Run capacity of the shared-memory path; frames with more runs take k_tail_slow.  The default keeps the footprint

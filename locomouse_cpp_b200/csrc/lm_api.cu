@@ -85,6 +85,7 @@ struct lm_ctx {
     cudaEvent_t ev_call[2] = {};      // first kernel / last D2H of a whole lm_detect_batch call
     cudaEvent_t ev_mid[NRES] = {};    // between k_screen and k_corr_sparse
     cudaEvent_t ev_go[NRES] = {};     // before k_screen (hand-over to the high-priority stream)
+    cudaEvent_t ev_sstart[NRES] = {}; // on the screen's stream right before k_screen2 (device timeline only)
     float ms_screen = 0.f;            // k_screen alone, summed over the sub-batches of the last call
     float ms[7] = {};
     std::vector<float> timeline;     // [sub-batch][9]: ms from the start of the last call to its stage events 0..7 and to the end of the screen kernel
@@ -320,7 +321,7 @@ int prepare_screen(lm_ctx *ctx, LmBatch &b, int want, size_t B) {
     if (!have1 && !have2) return LM_OK;
     // 3. task lists + what k_corr_sparse needs, for both modes
     int rc;
-    if ((rc = dalloc(ctx, &b.scr.ntasks, 8))) return rc;
+    if ((rc = dalloc(ctx, &b.scr.ntasks, 16))) return rc;
     for (int v = 0; v < 2; ++v)
         for (int f = 0; f < nfeat; ++f) {
             const LmScreenHost &H = ctx->scr_info[v][f];
@@ -479,6 +480,11 @@ int prepare(lm_ctx *ctx) {
     if ((rc = dalloc(ctx, &b.cc_flag, B))) return rc;
     if ((rc = dalloc(ctx, &b.det, B * 4 * (size_t)k.det_cap))) return rc;
     if ((rc = dalloc(ctx, &b.det_count, B * 4))) return rc;
+    {
+        size_t P = 2;
+        while (P < (size_t)k.det_cap) P <<= 1;
+        if ((rc = dalloc(ctx, &b.nms_scratch, B * 2 * P * 16))) return rc;
+    }
     for (int s = 0; s < lm_ctx::NRES; ++s)
         if ((rc = dalloc(ctx, &ctx->d_bb[s], 3 * B))) return rc;
     // results: one device block + two pinned host blocks, same sub-array order
@@ -534,9 +540,14 @@ int prepare(lm_ctx *ctx) {
         if ((rc = dalloc(ctx, &c.cc_flag, B))) return rc;
         if ((rc = dalloc(ctx, &c.det, B * 4 * (size_t)k.det_cap))) return rc;
         if ((rc = dalloc(ctx, &c.det_count, B * 4))) return rc;
+        {
+            size_t P = 2;
+            while (P < (size_t)k.det_cap) P <<= 1;
+            if ((rc = dalloc(ctx, &c.nms_scratch, B * 2 * P * 16))) return rc;
+        }
         if ((rc = bind_results(c, set))) return rc;
         if (b.scr.enabled) {
-            if ((rc = dalloc(ctx, &c.scr.ntasks, 8))) return rc;
+            if ((rc = dalloc(ctx, &c.scr.ntasks, 16))) return rc;
             for (int v = 0; v < 2; ++v)
                 for (int f = 0; f < 3; ++f)
                     if (b.scr.job[v][f].tasks && (rc = dalloc(ctx, &c.scr.job[v][f].tasks, (size_t)b.scr.job[v][f].task_cap))) return rc;
@@ -621,6 +632,7 @@ int lm_create(lm_ctx **out, int device) {
         for (int q = 0; q < 8; ++q) cudaEventCreate(&ctx->ev_stage[s][q]);
         cudaEventCreate(&ctx->ev_mid[s]);
         cudaEventCreateWithFlags(&ctx->ev_go[s], cudaEventDisableTiming);
+        cudaEventCreate(&ctx->ev_sstart[s]);
     }
     *out = ctx;
     return LM_OK;
@@ -642,6 +654,7 @@ int lm_destroy(lm_ctx *ctx) {
         for (int q = 0; q < 8; ++q) cudaEventDestroy(ctx->ev_stage[s][q]);
         cudaEventDestroy(ctx->ev_mid[s]);
         cudaEventDestroy(ctx->ev_go[s]);
+        cudaEventDestroy(ctx->ev_sstart[s]);
     }
     cudaStreamDestroy(ctx->stream);
     for (int s = 0; s < lm_ctx::NSLOT - 1; ++s) cudaStreamDestroy(ctx->stream_more[s]);
@@ -823,7 +836,7 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
     for (int q = 0; q < 7; ++q) ctx->ms[q] = 0.f;
     ctx->ms_screen = 0.f;
     ctx->launches = 0;
-    ctx->timeline.assign((size_t)nsub * 9, -1.f);
+    ctx->timeline.assign((size_t)nsub * 10, -1.f);
     const lm_ctx::ResOff &o = ctx->ro;
     const int nslot = ctx->nsets;  // scratch sets in rotation; with option streams = 1 they share one stream (strictly serial kernels)
     cudaStream_t streams[lm_ctx::NSLOT];
@@ -887,10 +900,10 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
         for (int q = 0; q < 6; ++q)
             if (cudaEventElapsedTime(&t, ctx->ev_stage[slot][q], ctx->ev_stage[slot][q + 1]) == cudaSuccess) ctx->ms[q] += t;
         if (ctx->bt.scr.enabled && cudaEventElapsedTime(&t, ctx->ev_stage[slot][2], ctx->ev_mid[slot]) == cudaSuccess) ctx->ms_screen += t;
-        for (int q = 0; q < 9; ++q) {
+        for (int q = 0; q < 10; ++q) {
             t = -1.f;
-            if (cudaEventElapsedTime(&t, ctx->ev_call[0], q < 8 ? ctx->ev_stage[slot][q] : ctx->ev_mid[slot]) != cudaSuccess) t = -1.f;
-            ctx->timeline[(size_t)sub * 9 + q] = t;
+            if (cudaEventElapsedTime(&t, ctx->ev_call[0], q < 8 ? ctx->ev_stage[slot][q] : (q == 8 ? ctx->ev_mid[slot] : ctx->ev_sstart[slot])) != cudaSuccess) t = -1.f;
+            ctx->timeline[(size_t)sub * 10 + q] = t;
         }
         cudaGetLastError();
         return LM_OK;
@@ -921,6 +934,7 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
         b.ev_screen_done = ctx->ev_mid[ring];
         b.screen_stream = (ctx->opt_streams > 1 && ctx->opt_screen_priority) ? ctx->stream_hi : nullptr;
         b.ev_screen_go = ctx->ev_go[ring];
+        b.ev_screen_start = ctx->ev_sstart[ring];
         cudaEvent_t *ev = ctx->ev_stage[ring];
         CK(cudaStreamWaitEvent(stf, ctx->ev_h2d[ring], 0));
         // with the back phase on its own stream the slot's scratch is no longer protected by stream order alone
@@ -1056,10 +1070,10 @@ int lm_get_info(const lm_ctx *ctx, const char *name, double *value) {
         *value = (double)m;
         return LM_OK;
     }
-    if (!strncmp(name, "tl_", 3)) {  // tl_<sub>_<k>: device timeline of the last call (ms since its start), k = 0..7 stage events, 8 = screen end
+    if (!strncmp(name, "tl_", 3)) {  // tl_<sub>_<k>: device timeline of the last call (ms since its start), k = 0..7 stage events, 8 = screen end, 9 = screen start
         int sub = -1, q = -1;
-        if (sscanf(name + 3, "%d_%d", &sub, &q) != 2 || sub < 0 || q < 0 || q > 8 || (size_t)sub * 9 + q >= ctx->timeline.size()) return LM_ERR_INVALID;
-        *value = (double)ctx->timeline[(size_t)sub * 9 + q];
+        if (sscanf(name + 3, "%d_%d", &sub, &q) != 2 || sub < 0 || q < 0 || q > 9 || (size_t)sub * 10 + q >= ctx->timeline.size()) return LM_ERR_INVALID;
+        *value = (double)ctx->timeline[(size_t)sub * 10 + q];
         return LM_OK;
     }
     if (!strcmp(name, "ms_screen")) {  // device time of k_screen alone in the last lm_detect_batch call

@@ -106,6 +106,7 @@ struct LmBatch {
     int bb_w, bb_h[2], tail_w, tail_pitch;
     int flip, imadjust, conn, n_tail_points, fma_mode;
     int cand_cap, det_cap, match_cap;
+    unsigned char *nms_scratch;  // device, [2 B lists][16 * pow2(det_cap)] bytes: lists too long for the shared-memory NMS class
     int ovlp[2];                // (int)(w_bottom * (1 - T)) per feature (class.cpp:1047), host computed
     LmView view[2];
     LmTemplateDev tmpl[2][3];
@@ -122,6 +123,7 @@ struct LmBatch {
     LmScreen scr;
     cudaEvent_t ev_screen_done; // recorded by lm_launch_screen between k_screen and k_corr_sparse (may be null)
     cudaStream_t screen_stream; // when set (with ev_screen_go and ev_screen_done): the screen kernel runs on this (high-priority) stream
+    cudaEvent_t ev_screen_start;  // recorded on the screen's stream right before the kernel (device timeline)
     cudaEvent_t ev_screen_go;
     LmDet *det;                 // [B][2][2][det_cap]   index: ((f*2+feat)*2+view)
     int32_t *det_count;         // [B][2][2]
@@ -214,6 +216,15 @@ struct LmDevOnce {
         return !done[dev].exchange(true);
     }
 };
+// The SM's L1 / shared-memory split is a per-SM setting that can only change while the SM is idle.  k_screen2 needs the largest
+// shared-memory carve-out; a kernel that prefers another split cannot join an SM the screen runs on (measured: every other
+// kernel of the pipeline then costs its full stand-alone time on top of the screen's).  The pipeline's kernels therefore all
+// ask for the same split.  LM_CARVEOUT=0 (what-if runs) leaves the driver's default.
+template <class F>
+inline void lm_prefer_max_shared(F *kernel) {
+    static const bool on = !(getenv("LM_CARVEOUT") && atoi(getenv("LM_CARVEOUT")) == 0);
+    if (on) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
 inline int lm_sm_count() {
     int dev = 0, n = 0;
     cudaGetDevice(&dev);

@@ -137,6 +137,23 @@ __device__ __forceinline__ void body(const Cfg c, long long *cycles, int *status
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(160, 1) probe2(const Cfg c, long long *cycles, int *status) { body<2>(c, cycles, status); }
 __global__ void __launch_bounds__(160, 1) probe1(const Cfg c, long long *cycles, int *status) { body<1>(c, cycles, status); }
 
+// a memory-streaming kernel to run beside the MMA chain (k_minmax-like: 256 threads, reads `n16` 16-byte words once)
+__global__ void __launch_bounds__(256) stream_beside(const uint4 *src, long long n16, int *sink) {
+    uint32_t acc = 0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n16; i += (long long)gridDim.x * 256) {
+        const uint4 v = __ldg(src + i);
+        acc += v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x12345678u) *sink = 2;
+}
+// an ALU-only kernel beside the chain (no memory traffic): 256 threads spinning for `spin` cycles
+__global__ void __launch_bounds__(256) alu_beside(long long spin, int *sink) {
+    const long long t0 = clock64();
+    int acc = 0;
+    while (clock64() - t0 < spin) ++acc;
+    if (acc == 123456789) *sink = acc;
+}
+
 int main(int argc, char **argv) {
     long long *dC;
     int *dS;
@@ -172,6 +189,63 @@ int main(int argc, char **argv) {
         fflush(stdout);
         if (e != cudaSuccess) exit(1);
     };
+    if (argc > 1 && !strcmp(argv[1], "beside")) {
+        // Does another kernel make progress on the SMs while the pair instruction streams its operands from shared memory at
+        // ~106 B/clk, and what does it cost the MMA chain?  A = the N = 192 chain (1200 units, ~3.5 ms) on a high-priority stream,
+        // B = a streaming read of 348 MB (k_minmax's traffic per 512 frames) or an ALU spin, started ~100 us later on another stream.
+        cudaStream_t sa, sb;
+        int lo, hi;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamCreateWithPriority(&sa, cudaStreamNonBlocking, hi);
+        cudaStreamCreateWithPriority(&sb, cudaStreamNonBlocking, lo);
+        cudaEvent_t a0, a1, b0, b1;
+        cudaEventCreate(&a0); cudaEventCreate(&a1); cudaEventCreate(&b0); cudaEventCreate(&b1);
+        uint4 *big;
+        const long long nbytes = 348LL << 20;
+        cudaMalloc(&big, nbytes);
+        cudaMemset(big, 1, nbytes);
+        Cfg c{2, 192, 30, 1200, 1, 1, 1, rows, 0, 2, 0};
+        const size_t smem = (size_t)30 * 4 * 96 * 16 + 4 * rows * 16;
+        for (int kind = 0; kind < 3; ++kind) {
+            auto launch_b = [&]() {
+                if (kind == 0) stream_beside<<<592, 256, 0, sb>>>(big, nbytes / 16, dS);
+                if (kind == 1) stream_beside<<<2688, 256, 0, sb>>>(big, nbytes / 16, dS);
+                if (kind == 2) alu_beside<<<592, 256, 0, sb>>>(200000, dS);
+            };
+            launch_b();                                     // warm (module load) and time alone
+            cudaDeviceSynchronize();
+            cudaEventRecord(b0, sb);
+            launch_b();
+            cudaEventRecord(b1, sb);
+            cudaDeviceSynchronize();
+            float alone = 0;
+            cudaEventElapsedTime(&alone, b0, b1);
+            probe2<<<nsm, 160, smem>>>(c, dC, dS);       // warm
+            cudaDeviceSynchronize();
+            cudaMemset(dC, 0, 8 * 160);
+            cudaEventRecord(a0, sa);
+            probe2<<<nsm, 160, smem, sa>>>(c, dC, dS);
+            cudaEventRecord(a1, sa);
+            alu_beside<<<1, 256, 0, sb>>>(200000, dS);      // ~100 us delay
+            cudaEventRecord(b0, sb);
+            launch_b();
+            cudaEventRecord(b1, sb);
+            cudaError_t e = cudaDeviceSynchronize();
+            float ta = 0, tb0 = 0, tb1 = 0;
+            cudaEventElapsedTime(&ta, a0, a1);
+            cudaEventElapsedTime(&tb0, a0, b0);
+            cudaEventElapsedTime(&tb1, a0, b1);
+            long long cyc2[160];
+            cudaMemcpy(cyc2, dC, 8 * 160, cudaMemcpyDeviceToHost);
+            long long cyc = 0;
+            for (int b = 0; b < nsm; b += 2) cyc = cyc2[2 + b] > cyc ? cyc2[2 + b] : cyc;
+            printf("{\"beside\": \"%s\", \"cuda\": \"%s\", \"mma_chain_ms\": %.3f, \"cycles_per_mma_with_B\": %.1f, \"B_alone_ms\": %.3f, \"B_start_ms\": %.3f, \"B_end_ms\": %.3f, "
+                   "\"B_ms_beside\": %.3f}\n",
+                   kind == 0 ? "stream 348 MB, 592 CTAs" : kind == 1 ? "stream 348 MB, 2688 CTAs" : "ALU spin 100 us, 592 CTAs", cudaGetErrorString(e), ta,
+                   (double)cyc / (1200.0 * 60.0), alone, tb0, tb1, tb1 - tb0);
+        }
+        return 0;
+    }
     // k_screen2's own shapes first
     run(2, 192, 30, 1, 1, 1, nsm, "k_screen2 wide instruction (paw+snout+tail), real-like data");
     run(2, 128, 30, 1, 1, 1, nsm, "k_screen2 narrow instruction");

@@ -480,6 +480,28 @@ def main():
                     sharding.gather_to_rank0(r, device=dev)
                 return r
 
+            # what the host can deliver at this N: every rank copies its own page-locked frames to its GPU at the same time
+            # (bare cudaMemcpyAsync, no kernels); the slowest rank bounds a weak-scaling step, as it does for the real path
+            ceiling = None
+            try:
+                devbuf = torch.empty((min(n, 2048),) + tuple(host.shape[1:]), dtype=torch.uint8, device=dev)
+                nb = devbuf.shape[0]
+                devbuf.copy_(host[:nb], non_blocking=True)
+                torch.cuda.synchronize()
+                barrier()
+                t0 = time.perf_counter()
+                reps = max(1, n // nb)
+                for q in range(reps):
+                    devbuf.copy_(host[q * nb:(q + 1) * nb], non_blocking=True)
+                torch.cuda.synchronize()
+                mine = reps * nb * cfg.vid_rows * cfg.vid_cols / (time.perf_counter() - t0) / 1e9
+                slowest = -max_over_ranks(-mine)
+                barrier()
+                ceiling = {"per_gpu_gbs_slowest": slowest, "aggregate_gbs_by_slowest": slowest * world, "this_rank_gbs": mine}
+                del devbuf
+                torch.cuda.empty_cache()
+            except Exception as ex:  # pragma: no cover
+                ceiling = {"error": repr(ex)}
             for _ in range(max(1, min(args.warmup, 2))):
                 e2e_step()
             barrier()
@@ -493,8 +515,14 @@ def main():
             e2e = {"value": world * n * args.steps / ew, "unit": UNIT,
                    "h2d_bytes_per_step": int(n * cfg.vid_rows * cfg.vid_cols + 3 * 4 * n), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": ew / args.steps * 1e3, "numa_bound": bool(numa_bound),
+                   "h2d_gbs_achieved": world * n * cfg.vid_rows * cfg.vid_cols * args.steps / ew / 1e9,
+                   "h2d_ceiling_gbs": (ceiling or {}).get("aggregate_gbs_by_slowest"),
+                   "frac_of_ceiling": (world * n * cfg.vid_rows * cfg.vid_cols * args.steps / ew / 1e9 / ceiling["aggregate_gbs_by_slowest"])
+                   if ceiling and ceiling.get("aggregate_gbs_by_slowest") else None,
+                   "h2d_ceiling": ceiling,
                    "note": f"frames in pinned host memory, copied H2D inside the call (overlapped with compute per {subb}-frame "
-                           "sub-batch); results copied D2H" + ("; candidate lists gathered to rank 0 over NCCL" if world > 1 else "")}
+                           "sub-batch); results copied D2H" + ("; candidate lists gathered to rank 0 over NCCL" if world > 1 else "") +
+                           "; h2d_ceiling = bare concurrent cudaMemcpyAsync of the same page-locked frames on every rank, N x the slowest rank's rate"}
         except Exception as ex:  # pragma: no cover
             e2e = {"value": None, "unit": UNIT, "error": repr(ex)}
 

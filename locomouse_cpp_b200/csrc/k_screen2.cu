@@ -229,11 +229,21 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(96) k_screen2(const __grid
                     const uint64_t adesc = umma_desc(smem_u32(sA) + (uint32_t)stage * stage_bytes, panel_a);
                     const uint32_t alo = (uint32_t)adesc, ahi = (uint32_t)(adesc >> 32), blo = (uint32_t)bdesc0, bhi = (uint32_t)(bdesc0 >> 32);
                     if (ks == 2 && KH % 6 == 0) {
-                        umma_issue_tile_ks2<6>(d, alo, ahi, blo, bhi, a_step, b_step, b_row, idesc, KH);
+                        umma_issue_tile<2, 6>(d, alo, ahi, blo, bhi, a_step, b_step, b_row, idesc, KH);
                     } else if (ks == 2 && KH % 5 == 0) {
-                        umma_issue_tile_ks2<5>(d, alo, ahi, blo, bhi, a_step, b_step, b_row, idesc, KH);
+                        umma_issue_tile<2, 5>(d, alo, ahi, blo, bhi, a_step, b_step, b_row, idesc, KH);
                     } else if (ks == 2 && KH % 4 == 0) {
-                        umma_issue_tile_ks2<4>(d, alo, ahi, blo, bhi, a_step, b_step, b_row, idesc, KH);
+                        umma_issue_tile<2, 4>(d, alo, ahi, blo, bhi, a_step, b_step, b_row, idesc, KH);
+                    } else if (ks == 3 && KH % 4 == 0) {
+                        umma_issue_tile<3, 4>(d, alo, ahi, blo, bhi, a_step, b_step, b_row, idesc, KH);
+                    } else if (ks == 3 && KH % 3 == 0) {
+                        umma_issue_tile<3, 3>(d, alo, ahi, blo, bhi, a_step, b_step, b_row, idesc, KH);
+                    } else if (ks == 1 && KH % 8 == 0) {
+                        umma_issue_tile<1, 8>(d, alo, ahi, blo, bhi, a_step, b_step, b_row, idesc, KH);
+                    } else if (ks == 2) {
+                        umma_issue_tile<2, 1>(d, alo, ahi, blo, bhi, a_step, b_step, b_row, idesc, KH);
+                    } else if (ks == 3) {
+                        umma_issue_tile<3, 1>(d, alo, ahi, blo, bhi, a_step, b_step, b_row, idesc, KH);
                     } else {
                         uint32_t a_j = alo, b_j = blo, accum = 0;
                         for (int j = 0; j < KH; ++j) {

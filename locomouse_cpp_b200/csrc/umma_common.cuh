@@ -116,20 +116,21 @@ __device__ __forceinline__ void umma_i8_2cta_lohi(uint32_t tmem_d, uint32_t alo,
         "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// All MMAs of one window tile for ks = 2 K steps per kernel row, U kernel rows per loop iteration (KH % U == 0): 2 U instructions
+// All MMAs of one window tile for KS K steps per kernel row, U kernel rows per loop iteration (KH % U == 0): KS * U instructions
 // whose descriptors are independent sums off the iteration's base, so that no instruction waits for the registers of the one
 // before it (a serial add -> R2UR -> UTCIMMA chain over four re-used uniform registers cost ~22 cycles per instruction).
-template <int U>
-__device__ __forceinline__ void umma_issue_tile_ks2(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t a_step, uint32_t b_step,
-                                                    uint32_t b_row, uint32_t idesc, int KH) {
+template <int KS, int U>
+__device__ __forceinline__ void umma_issue_tile(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t a_step, uint32_t b_step,
+                                                uint32_t b_row, uint32_t idesc, int KH) {
     uint32_t accum = 0;
     for (int j = 0; j < KH; j += U) {
 #pragma unroll
         for (int jj = 0; jj < U; ++jj) {
-            const uint32_t a = alo + (uint32_t)jj, b = blo + (uint32_t)jj * b_row;
-            umma_i8_2cta_lohi(d, a, ahi, b, bhi, idesc, accum);
-            accum = 1;
-            umma_i8_2cta_lohi(d, a + a_step, ahi, b + b_step, bhi, idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                umma_i8_2cta_lohi(d, alo + (uint32_t)jj + (uint32_t)k * a_step, ahi, blo + (uint32_t)jj * b_row + (uint32_t)k * b_step, bhi, idesc, accum);
+                accum = 1;
+            }
         }
         alo += (uint32_t)U;
         blo += (uint32_t)U * b_row;

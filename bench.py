@@ -153,6 +153,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1000, help="frames of the workload timed on the CPU oracle (1 thread); 1000 = configs[0]'s video")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[0] / configs[4] / density side measurements")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--shard-weights", default="", help="N > 1: comma-separated per-rank weights for the end-to-end job's shards instead of the measured host rates")
+    ap.add_argument("--even-shards", action="store_true", help="N > 1: keep the end-to-end job evenly split even when the ranks' measured host rates differ")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="library option for the measured arm (lm_set_option), e.g. streams=3")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -474,12 +476,6 @@ def main():
             frames = None
             torch.cuda.empty_cache()
 
-            def e2e_step():
-                r = det.detect_batch(host, bx, bs, bb, results=res)
-                if world > 1:
-                    sharding.gather_to_rank0(r, device=dev)
-                return r
-
             # what the host can deliver at this N: every rank copies its own page-locked frames to its GPU at the same time
             # (bare cudaMemcpyAsync, no kernels); the slowest rank bounds a weak-scaling step, as it does for the real path
             ceiling = None
@@ -502,6 +498,45 @@ def main():
                 torch.cuda.empty_cache()
             except Exception as ex:  # pragma: no cover
                 ceiling = {"error": repr(ex)}
+            # Shards by measured host rate: on a box whose GPUs sit behind unequal host paths an even split is bound by the
+            # slowest rank.  8-GPU pool box (profiles/r02_bench_n8.json, profiles/r02_bench_n8_even.json): four GPUs copy at
+            # 23 GB/s and four at 35 GB/s when all copy at once; even shards 331 ms per step (242 k frames/s, 164 GB/s in
+            # total), shards in proportion to those rates 295 ms (271 k frames/s, 185 GB/s).  The job's world x n frames are dealt
+            # by sharding.weighted_counts; rates within 5 % of each other keep the even split (--even-shards forces it,
+            # --shard-weights overrides the measured rates).
+            counts = [n] * world
+            if world > 1 and ceiling and "this_rank_gbs" in ceiling and not args.even_shards:
+                rt = torch.tensor([ceiling["this_rank_gbs"]], dtype=torch.float64, device=dev)
+                rates = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+                dist.all_gather(rates, rt)
+                rates = [float(x.item()) for x in rates]
+                ceiling["per_rank_gbs"] = list(rates)
+                if args.shard_weights:
+                    rates = [float(x) for x in args.shard_weights.split(",")]
+                    if len(rates) != world:
+                        raise ValueError("--shard-weights needs one weight per rank")
+                if max(rates) > 1.05 * min(rates):
+                    counts = sharding.weighted_counts(world * n, rates)
+                    if not args.shard_weights:
+                        ceiling["aggregate_gbs_sum_of_rates"] = float(sum(rates))
+            n_e = counts[rank]
+            e_bx, e_bs, e_bb, e_res = bx, bs, bb, res
+            if n_e != n:
+                if n_e > n:   # this rank takes more than one video's worth: the synthetic video repeats
+                    bigger = torch.empty((n_e,) + tuple(host.shape[1:]), dtype=torch.uint8, pin_memory=True)
+                    bigger[:n].copy_(host)
+                    bigger[n:].copy_(host[:n_e - n])
+                    host = bigger
+                e_bx, e_bs, e_bb = (np.resize(a, n_e) for a in (bx, bs, bb))
+                e_res = Results(n_e, cfg.cand_cap, cfg.match_cap, cfg.n_tail_points, pinned=True)
+            e_host = host[:n_e]
+
+            def e2e_step():
+                r = det.detect_batch(e_host, e_bx, e_bs, e_bb, results=e_res)
+                if world > 1:
+                    sharding.gather_to_rank0(r, device=dev)
+                return r
+
             for _ in range(max(1, min(args.warmup, 2))):
                 e2e_step()
             barrier()
@@ -517,9 +552,10 @@ def main():
                    "ms_per_step": ew / args.steps * 1e3, "numa_bound": bool(numa_bound),
                    "h2d_gbs_achieved": world * n * cfg.vid_rows * cfg.vid_cols * args.steps / ew / 1e9,
                    "h2d_ceiling_gbs": (ceiling or {}).get("aggregate_gbs_by_slowest"),
-                   "frac_of_ceiling": (world * n * cfg.vid_rows * cfg.vid_cols * args.steps / ew / 1e9 / ceiling["aggregate_gbs_by_slowest"])
+                   "frac_of_ceiling": (world * n * cfg.vid_rows * cfg.vid_cols * args.steps / ew / 1e9 /
+                                       ceiling["aggregate_gbs_by_slowest"])
                    if ceiling and ceiling.get("aggregate_gbs_by_slowest") else None,
-                   "h2d_ceiling": ceiling,
+                   "h2d_ceiling": ceiling, "frames_per_rank": counts,
                    "note": f"frames in pinned host memory, copied H2D inside the call (overlapped with compute per {subb}-frame "
                            "sub-batch); results copied D2H" + ("; candidate lists gathered to rank 0 over NCCL" if world > 1 else "") +
                            "; h2d_ceiling = bare concurrent cudaMemcpyAsync of the same page-locked frames on every rank, N x the slowest rank's rate"}

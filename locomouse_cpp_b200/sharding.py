@@ -24,6 +24,39 @@ def frame_range(n_frames: int, world: int, rank: int):
     return f0, f0 + q + (1 if rank < r else 0)
 
 
+def weighted_counts(total: int, weights, quantum: int = 1):
+    """Frame counts per rank in proportion to `weights` (e.g. each rank's measured host-to-device rate: on a box whose GPUs sit
+    behind unequal PCIe / memory paths the slowest rank bounds an evenly split job), summing to `total`.  Counts are multiples
+    of `quantum` (the sub-batch size) except that the remainder goes to the heaviest rank; every rank gets at least one
+    quantum when total allows."""
+    w = np.asarray(list(weights), dtype=np.float64)
+    if w.ndim != 1 or w.size == 0 or not np.all(np.isfinite(w)) or np.any(w <= 0):
+        raise ValueError("weights must be positive and finite")
+    total, quantum = int(total), max(1, int(quantum))
+    if total < 0:
+        raise ValueError("negative total")
+    ideal = total * w / w.sum()
+    counts = np.floor(ideal / quantum).astype(np.int64) * quantum
+    if total >= quantum * w.size:
+        counts = np.maximum(counts, quantum)
+    # hand the remaining quanta to the ranks furthest below their ideal share, the last odd frames to the heaviest rank
+    while counts.sum() + quantum <= total:
+        counts[int(np.argmax(ideal - counts))] += quantum
+    while counts.sum() > total:
+        counts[int(np.argmax(counts - ideal))] -= min(quantum, int(counts.sum() - total))
+    counts[int(np.argmax(w))] += total - int(counts.sum())
+    return [int(c) for c in counts]
+
+
+def weighted_ranges(total: int, weights, quantum: int = 1):
+    """Contiguous [f0, f1) per rank with weighted_counts' sizes (rank r's range follows rank r - 1's)."""
+    out, f0 = [], 0
+    for c in weighted_counts(total, weights, quantum):
+        out.append((f0, f0 + c))
+        f0 += c
+    return out
+
+
 @dataclass(frozen=True)
 class Shard:
     video: int
@@ -166,6 +199,33 @@ def gather_to_rank0(res: Results, device=None):
             h.copy_(r, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         return [Results(n, cap, mcap, ntp, buffer=h.numpy()) for h in host]
+    if dev.type == "cuda" and all(m[1:] == metas[0][1:] for m in metas):
+        # unequal frame counts (weighted shards) with equal capacities: each rank's contiguous buffer moves as it is, point to
+        # point, into reused device / page-locked buffers of the right sizes on rank 0 -- no per-entry host work either
+        sizes = [Results.raw_nbytes(m[0], m[1], m[2], m[3]) for m in metas]
+        key = ("ragged", world, rank, tuple(sizes), str(dev))
+        bufs = _GATHER_CACHE.get(key)
+        if bufs is None:
+            _GATHER_CACHE.clear()
+            send = torch.empty(sizes[rank], dtype=torch.uint8, device=dev)
+            recv = [torch.empty(sz, dtype=torch.uint8, device=dev) for sz in sizes] if rank == 0 else None
+            host = [torch.empty(sz, dtype=torch.uint8, pin_memory=True) for sz in sizes] if rank == 0 else None
+            bufs = _GATHER_CACHE[key] = (send, recv, host)
+        send, recv, host = bufs
+        send.copy_(torch.from_numpy(res.raw), non_blocking=True)
+        if rank == 0:
+            ops = [dist.P2POp(dist.irecv, recv[r], r) for r in range(1, world)]
+            recv[0].copy_(send, non_blocking=True)
+        else:
+            ops = [dist.P2POp(dist.isend, send, 0)]
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
+        if rank != 0:
+            return None
+        for h, r in zip(host, recv):
+            h.copy_(r, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return [Results(m[0], m[1], m[2], m[3], buffer=h.numpy()) for m, h in zip(metas, host)]
     payload = torch.from_numpy(pack(res).copy())
     size = torch.tensor([payload.numel()], dtype=torch.int64, device=dev)
     sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]

@@ -54,7 +54,24 @@ def test_pack_unpack_roundtrip(oracle):
     assert empty.n == 0
 
 
-def _worker(rank, world, port, n, out_path):
+def test_weighted_counts_follow_the_weights():
+    for total in (0, 5, 1000, 80000):
+        for w in ([1.0], [1, 1], [23.3] * 4 + [35.6] * 4, [3, 1, 2]):
+            c = sharding.weighted_counts(total, w)
+            assert sum(c) == total and all(x >= 0 for x in c)
+            if total >= 100 * len(w):
+                ideal = [total * x / sum(w) for x in w]
+                assert all(abs(a - b) <= 1 for a, b in zip(c, ideal))
+    assert sharding.weighted_counts(20000, [55.5, 55.5]) == [10000, 10000]
+    c = sharding.weighted_counts(80000, [23.3] * 4 + [35.6] * 4, quantum=512)
+    assert sum(c) == 80000 and all(x % 512 == 0 for x in c[:4]) and min(c) >= 512
+    r = sharding.weighted_ranges(10, [1, 1], 4)
+    assert r[0][0] == 0 and r[-1][1] == 10 and r[0][1] == r[1][0]
+    with pytest.raises(ValueError):
+        sharding.weighted_counts(10, [1, 0])
+
+
+def _worker(rank, world, port, n, out_path, weights=None):
     import torch.distributed as dist
 
     from oracle import oracle
@@ -64,9 +81,12 @@ def _worker(rank, world, port, n, out_path):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     cfg, model, bkg, calib, frames, bx, bs, bb = _small_problem(n)
     frames = frames.numpy()
-    (shard,) = sharding.plan(1, n, world)[rank]
-    f0, f1 = shard.f0, shard.f1
-    prev = frames[f0 - 1] if shard.needs_halo else None
+    if weights is None:
+        (shard,) = sharding.plan(1, n, world)[rank]
+        f0, f1 = shard.f0, shard.f1
+    else:   # shards sized by per-rank weights (measured host-to-device rates on the GPU box): unequal counts, ragged gather
+        f0, f1 = sharding.weighted_ranges(n, weights)[rank]
+    prev = frames[f0 - 1] if f0 > 0 else None
     local = oracle.detect(cfg, model, bkg, calib, frames[f0:f1], bx[f0:f1], bs[f0:f1], bb[f0:f1], prev_frame=prev,
                           first_frame_index=f0)
     parts = sharding.gather_to_rank0(local)
@@ -77,7 +97,8 @@ def _worker(rank, world, port, n, out_path):
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_frame_sharding_equals_single_process(oracle, tmp_path):
+@pytest.mark.parametrize("weights", [None, (2.0, 1.0)])
+def test_two_rank_gloo_frame_sharding_equals_single_process(oracle, tmp_path, weights):
     import torch.multiprocessing as mp
 
     n = 9
@@ -86,7 +107,7 @@ def test_two_rank_gloo_frame_sharding_equals_single_process(oracle, tmp_path):
     port = s.getsockname()[1]
     s.close()
     out = str(tmp_path / "gathered.npy")
-    mp.spawn(_worker, args=(2, port, n, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, n, out, weights), nprocs=2, join=True)
     cfg, model, bkg, calib, frames, bx, bs, bb = _small_problem(n)
     ref = oracle.detect(cfg, model, bkg, calib, frames.numpy(), bx, bs, bb)
     got = np.load(out)

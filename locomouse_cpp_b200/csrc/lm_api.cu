@@ -68,6 +68,11 @@ struct lm_ctx {
     LmBatch bt_more[NSLOT - 1] = {};  // the same with scratch sets 1..: consecutive sub-batches overlap on their own streams
     int nsets = 0;                    // scratch sets allocated by prepare()
     std::vector<void *> dev_allocs;   // everything cudaMalloc'ed for the scratch
+    // Guard mode (environment variable LM_GUARD=1 when the context is created; compute-sanitizer is not available on the pool):
+    // every scratch allocation sits between two 4 kB regions filled with a pattern, lm_get_info("guard_violations") counts the
+    // bytes of those regions that no longer hold it, i.e. out-of-bounds WRITES of any kernel since the allocation.
+    bool guard = false;
+    std::vector<std::pair<uint8_t *, size_t>> guard_regions;
     uint8_t *d_stage[2] = {};         // staged raw frames (Bcap + 1 each) when frames come from the host
     uint32_t *d_bb[10] = {};           // [3][Bcap] per ring set
     // result staging
@@ -183,6 +188,7 @@ void free_scratch(lm_ctx *c) {
     c->bbs = lm_ctx::BBScratch{};
     for (void *p : c->dev_allocs) cudaFree(p);
     c->dev_allocs.clear();
+    c->guard_regions.clear();
     for (int s = 0; s < lm_ctx::NRES; ++s) {
         if (c->h_res[s]) cudaFreeHost(c->h_res[s]);
         c->h_res[s] = nullptr;
@@ -198,13 +204,35 @@ void free_scratch(lm_ctx *c) {
     c->Bcap = 0;
 }
 
+constexpr size_t LM_GUARD_BYTES = 4096;
+constexpr int LM_GUARD_PATTERN = 0xA5;
+
 template <typename T>
 int dalloc(lm_ctx *ctx, T **p, size_t count) {
     void *q = nullptr;
-    CK(cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 256)));
+    const size_t bytes = std::max<size_t>(count * sizeof(T), 256);
+    if (ctx->guard) {
+        CK(cudaMalloc(&q, bytes + 2 * LM_GUARD_BYTES));
+        ctx->dev_allocs.push_back(q);
+        uint8_t *base = static_cast<uint8_t *>(q);
+        CK(cudaMemset(base, LM_GUARD_PATTERN, LM_GUARD_BYTES));
+        CK(cudaMemset(base + LM_GUARD_BYTES, 0, bytes));
+        CK(cudaMemset(base + LM_GUARD_BYTES + bytes, LM_GUARD_PATTERN, LM_GUARD_BYTES));
+        ctx->guard_regions.emplace_back(base, LM_GUARD_BYTES);
+        ctx->guard_regions.emplace_back(base + LM_GUARD_BYTES + bytes, LM_GUARD_BYTES);
+        *p = reinterpret_cast<T *>(base + LM_GUARD_BYTES);
+        return LM_OK;
+    }
+    CK(cudaMalloc(&q, bytes));
     ctx->dev_allocs.push_back(q);
     *p = reinterpret_cast<T *>(q);
     return LM_OK;
+}
+
+__global__ void k_guard_check(const uint8_t *p, size_t n, unsigned long long *bad) {
+    unsigned int c = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) c += p[i] != (uint8_t)LM_GUARD_PATTERN;
+    if (c) atomicAdd(bad, (unsigned long long)c);
 }
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -609,6 +637,7 @@ int lm_create(lm_ctx **out, int device) {
                     prop.major, prop.minor);
     ctx = new lm_ctx();
     ctx->device = device;
+    if (const char *g = getenv("LM_GUARD")) ctx->guard = atoi(g) != 0;
     bool streams_ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
                       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int s = 0; s < lm_ctx::NSLOT - 1; ++s)
@@ -1090,6 +1119,29 @@ int lm_get_info(const lm_ctx *ctx, const char *name, double *value) {
     }
     if (!strcmp(name, "subbatch")) {
         *value = (double)ctx->Bcap;
+        return LM_OK;
+    }
+    if (!strcmp(name, "guard_regions")) {
+        *value = (double)ctx->guard_regions.size();
+        return LM_OK;
+    }
+    const bool selftest = !strcmp(name, "guard_selftest");   // positive control: three guard bytes are overwritten, counted, restored
+    if (!strcmp(name, "guard_violations") || selftest) {   // bytes of the guard regions overwritten so far (-1: guard mode is off)
+        if (!ctx->guard || (selftest && ctx->guard_regions.empty())) {
+            *value = -1.0;
+            return LM_OK;
+        }
+        DeviceGuard dg(ctx->device);
+        unsigned long long *bad = nullptr, h = 0;
+        if (cudaDeviceSynchronize() != cudaSuccess || cudaMalloc(&bad, sizeof *bad) != cudaSuccess) return LM_ERR_RUNTIME;
+        cudaMemset(bad, 0, sizeof *bad);
+        if (selftest) cudaMemset(ctx->guard_regions.back().first + 7, 0, 3);
+        for (const auto &r : ctx->guard_regions) k_guard_check<<<4, 256>>>(r.first, r.second, bad);
+        const cudaError_t e = cudaMemcpy(&h, bad, sizeof h, cudaMemcpyDeviceToHost);
+        if (selftest) cudaMemset(ctx->guard_regions.back().first + 7, LM_GUARD_PATTERN, 3);
+        cudaFree(bad);
+        if (e != cudaSuccess) return LM_ERR_RUNTIME;
+        *value = (double)h;
         return LM_OK;
     }
     // diagnostics of the sub-batch that last ran in scratch set 0 (all streams drained when lm_detect_batch returns):

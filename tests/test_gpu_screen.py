@@ -153,14 +153,17 @@ def test_screen2_job_layouts_are_equivalent(oracle, kw, n, sub):
     assert (0.0, 0.0) in seen and len(seen) >= 3   # the layouts were really different
 
 
-@pytest.mark.parametrize("seed", list(range(1, 25)))
-def test_screen2_random_geometries_equal_oracle(oracle, seed):
+@pytest.mark.parametrize("seed", list(range(1, 37)))
+def test_screen2_random_geometries_equal_oracle(oracle, seed, monkeypatch):
     """Random geometries for the CTA-pair screen's tiling: image / box sizes (boxes lower than one 128-row tile so that stacked
     tiles span several frames, and taller than 256 rows so that a frame needs two tile pairs), tail boxes whose width is
     not a multiple of the 32-column tile, template shapes that differ per feature and view, odd sub-batch sizes.  Every
-    result byte equals the oracle for the default layout and with merging / stacking off."""
+    result byte equals the oracle for the default layout and with merging / stacking off.  The contexts run in guard mode
+    (LM_GUARD: every scratch allocation between two pattern-filled 4 kB regions; compute-sanitizer is closed on the pool), and
+    no kernel may have written outside its allocations."""
     from locomouse_cpp_b200.api import Detector
 
+    monkeypatch.setenv("LM_GUARD", "1")
     rng = np.random.Generator(np.random.PCG64(9000 + seed))
     side_h = int(rng.choice([60, 96, 140, 165, 300]))
     bottom_h = int(rng.choice([70, 120, 235, 280]))
@@ -189,6 +192,34 @@ def test_screen2_random_geometries_equal_oracle(oracle, seed):
             det.set_option("streams", int(rng.integers(1, 5)))
         got = det.detect_batch(frames, bx, bs, bb, allow_overflow=True)
         active = det.info("screen_active")
+        regions, violated = det.info("guard_regions"), det.info("guard_violations")
         det.close()
+        assert regions > 20 and violated == 0.0, f"seed {seed}, layout {layout}: {violated} guard bytes overwritten"
         assert active >= 1.0, "the screen should handle templates up to 30 x 30"
         assert diff_results(got, ref) == [], f"seed {seed}, layout {layout}: side_h {side_h}, bottom_h {bottom_h}, bb_w {bb_w}, shapes {shapes}"
+
+
+@pytest.mark.gpu
+def test_guard_regions_stay_intact_on_the_benchmark_geometry(oracle, monkeypatch):
+    """Config 1's geometry, several sub-batches on four streams, the dense fallback and the single-CTA screen as well: no kernel
+    of the detection path writes outside its scratch allocations (guard mode, see lm_api.cu), and a deliberate overwrite of a
+    guard region is noticed."""
+    from locomouse_cpp_b200.api import Detector
+
+    monkeypatch.setenv("LM_GUARD", "1")
+    spec = synth.SynthSpec()
+    cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(spec, 70, seed=1234)
+    frames = frames.numpy()
+    ref = oracle.detect(cfg, model, bkg, calib, frames, bx, bs, bb, n_threads=8)
+    for screen in (2, 1, 0):
+        det = Detector(cfg, model, bkg, calib, device=0)
+        det.set_option("screen", screen)
+        det.set_option("subbatch", 16)
+        got = det.detect_batch(frames, bx, bs, bb)
+        violated = det.info("guard_violations")
+        control = det.info("guard_selftest")          # three guard bytes overwritten on purpose, counted, restored
+        again = det.info("guard_violations")
+        det.close()
+        assert violated == 0.0, f"screen={screen}: {violated} guard bytes overwritten"
+        assert control == 3.0 and again == 0.0
+        assert diff_results(got, ref) == []

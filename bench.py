@@ -252,6 +252,7 @@ def main():
     for k in stage:
         stage[k] *= args.steps / isteps   # normalised to the number of timed steps, as the fields below assume
     ms_screen *= args.steps / isteps
+    subb = int(det.info("subbatch"))   # sub-batch size of the resident passes above
     det.set_option("streams", n_streams)
     det.detect_batch(frames[: min(n, 512)], bx[: min(n, 512)], bs[: min(n, 512)], bb[: min(n, 512)])
 
@@ -259,7 +260,6 @@ def main():
     # Screen on (default): k_screen, the int8 tcgen05 implicit GEMM, is the dominant kernel -> "tensor" bound; its
     # algorithmic work is the correlation it decides (720.7 MFLOP per frame), not the MMA work it executes.
     # Screen off: k_corr, the dense exact FP32 kernel -> FP32 FMA pipe.
-    subb = int(det.info("subbatch"))
     nsub = (n + subb - 1) // subb
     launches_per_step = nsub
     flop_per_launch = 2.0 * fma_frame * (n / nsub)

@@ -151,7 +151,7 @@ int lm_detect_batch(lm_ctx *ctx, const uint8_t *frames, int frames_on_device,
  *             cta_group::2, 1 = one CTA per tile) followed by an exact FP32 re-evaluation of the undecided
  *             outputs; 0: dense exact FP32 kernel only.  All three produce bit-identical results (the screen
  *             only discards outputs proven <= 0).
- *  "subbatch" frames per internal sub-batch (default 512).
+ *  "subbatch" frames per internal sub-batch (default 1024; frames in host memory use half of it, and a video shorter than two sub-batches is cut in two).
  *  "streams"  n = 2 .. 8 (default 4): n consecutive sub-batches are in flight on n streams with separate scratch (about
  *             1 GB each at the default sub-batch), so the latency-bound kernels of some overlap the tensor-core kernel of
  *             another; 1: all kernels strictly serial (used when timing a single kernel with events).

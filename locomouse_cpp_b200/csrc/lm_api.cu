@@ -55,7 +55,7 @@ struct lm_ctx {
     float *d_tmpl[2][3] = {};
     std::vector<float> h_tmpl[2][3];  // host copies (the screen's quantisation is derived from them)
     int opt_screen = 2;               // 0: dense exact kernel only, 1: tensor-core screen, one CTA per tile, 2: CTA pairs
-    int opt_subbatch = 512;
+    int opt_subbatch = 1024;
     int opt_screen_layout = 3;        // k_screen2 job layout: bit 0 = tail shares the paw + snout job (N = 192), bit 1 = stacked y tiles
     int opt_streams = 4;              // n > 1: n consecutive sub-batches in flight on n streams, 1: strictly serial kernels
     LmScreenHost scr_info[2][3] = {};
@@ -67,6 +67,7 @@ struct lm_ctx {
     LmBatch bt{};                     // config-derived fields + scratch pointers (scratch set 0)
     LmBatch bt_more[NSLOT - 1] = {};  // the same with scratch sets 1..: consecutive sub-batches overlap on their own streams
     int nsets = 0;                    // scratch sets allocated by prepare()
+    int last_Bsub = 0;                // sub-batch size of the last lm_detect_batch call
     std::vector<void *> dev_allocs;   // everything cudaMalloc'ed for the scratch
     // Guard mode (environment variable LM_GUARD=1 when the context is created; compute-sanitizer is not available on the pool):
     // every scratch allocation sits between two 4 kB regions filled with a pattern, lm_get_info("guard_violations") counts the
@@ -420,8 +421,21 @@ int prepare_screen(lm_ctx *ctx, LmBatch &b, int want, size_t B) {
 }
 
 // derive window geometry + allocate scratch for sub-batches of Bcap frames
-int prepare(lm_ctx *ctx) {
-    if (ctx->Bcap) return LM_OK;
+// Scratch for sub-batches of up to `want_B` frames in `want_sets` rotating sets (0: the configured sub-batch size / stream
+// count).  Grows on demand and never shrinks: a short first video does not pay for (or wait for the allocation of) the
+// ~2.5 GB per set that a long one uses.
+int prepare(lm_ctx *ctx, int want_B = 0, int want_sets = 0) {
+    int cap_B = ctx->opt_subbatch;
+    if (const char *e = getenv("LM_SUBBATCH")) cap_B = std::max(1, atoi(e));
+    const int cap_sets = std::max(2, std::min(ctx->opt_streams, (int)lm_ctx::NSLOT));
+    want_B = want_B <= 0 ? cap_B : std::min(want_B, cap_B);
+    want_sets = want_sets <= 0 ? cap_sets : std::max(2, std::min(want_sets, cap_sets));
+    if (ctx->Bcap >= want_B && ctx->nsets >= want_sets) return LM_OK;
+    if (ctx->Bcap) {   // too small for this call: every stream was drained when the previous call returned
+        want_B = std::max(want_B, ctx->Bcap);
+        want_sets = std::max(want_sets, ctx->nsets);
+        free_scratch(ctx);
+    }
     const lm_config &k = ctx->cfg;
     LmBatch &b = ctx->bt;
     b = LmBatch{};
@@ -484,8 +498,7 @@ int prepare(lm_ctx *ctx) {
                             k.bb_w, ctx->t_rows[v][f], ctx->t_cols[v][f], need);
         }
 
-    int Bcap = ctx->opt_subbatch;
-    if (const char *e = getenv("LM_SUBBATCH")) Bcap = std::max(1, atoi(e));
+    const int Bcap = want_B;
     const size_t B = (size_t)Bcap;
     int rc;
     if ((rc = dalloc(ctx, &ctx->d_calib_flip, (size_t)k.n_rows * k.n_cols))) return rc;
@@ -552,7 +565,7 @@ int prepare(lm_ctx *ctx) {
         if ((rc = prepare_screen(ctx, b, want_screen, B))) return rc;
     }
     // ---- scratch sets 1..: same geometry and operands, their own mutable buffers ---------------------------------
-    ctx->nsets = std::max(2, std::min(ctx->opt_streams, (int)lm_ctx::NSLOT));
+    ctx->nsets = want_sets;
     for (int set = 1; set < ctx->nsets; ++set) {
         LmBatch &c = ctx->bt_more[set - 1];
         c = b;
@@ -845,7 +858,20 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
             return fail(ctx, LM_ERR_ROI, "frame %lld: bounding box (x=%u, y_side=%u, y_bottom=%u) leaves the padded image",
                         (long long)(first_frame_index + f), bb_x[f], bb_y_side[f], bb_y_bottom[f]);
     CK(cudaSetDevice(ctx->device));
-    int rc = prepare(ctx);
+    // Sub-batch size of this call.  Frames in HOST memory: the path is bound by the PCIe link, so half the configured size
+    // (the first kernels start after half as many bytes, the last ones finish sooner).  A short video is cut in (at least) two
+    // so that sub-batches overlap on the streams (and the second half's copy runs under the first half's kernels).
+    int Bsub;
+    {
+        int cap = ctx->opt_subbatch;
+        if (const char *e = getenv("LM_SUBBATCH")) cap = std::max(1, atoi(e));
+        Bsub = cap;
+        if (!frames_on_device && cap >= 128) Bsub = (cap / 2 + 63) / 64 * 64;
+        if (n < 2 * (int64_t)Bsub) Bsub = (int)std::min<int64_t>(Bsub, std::max<int64_t>(64, ((n + 1) / 2 + 63) / 64 * 64));
+        Bsub = std::min(Bsub, cap);
+    }
+    ctx->last_Bsub = Bsub;
+    int rc = prepare(ctx, Bsub, (int)std::min<int64_t>(lm_ctx::NSLOT, (n + Bsub - 1) / Bsub));
     if (rc == LM_OK && !frames_on_device) rc = ensure_stage(ctx);
     if (rc) {  // a half-built scratch set (device or pinned memory ran out) is released, not leaked
         free_scratch(ctx);
@@ -860,7 +886,7 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
 
     const int Bcap = ctx->Bcap;
     const int64_t fsz = ctx->bt.frame_bytes;
-    const int64_t nsub = (n + Bcap - 1) / Bcap;
+    const int64_t nsub = (n + Bsub - 1) / Bsub;
     const bool has_prev0 = first_frame_index > 0;
     for (int q = 0; q < 7; ++q) ctx->ms[q] = 0.f;
     ctx->ms_screen = 0.f;
@@ -874,8 +900,8 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
 
     auto issue_h2d = [&](int64_t sub) -> int {
         const int slot = (int)(sub & 1);   // frame staging slot
-        const int64_t s0 = sub * Bcap;
-        const int B = (int)std::min<int64_t>(Bcap, n - s0);
+        const int64_t s0 = sub * Bsub;
+        const int B = (int)std::min<int64_t>(Bsub, n - s0);
         uint32_t *bb = ctx->d_bb[sub % lm_ctx::NRES];   // its last user (sub - NRES) has been drained
         CK(cudaMemcpyAsync(bb, bb_x + s0, (size_t)B * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaMemcpyAsync(bb + Bcap, bb_y_side + s0, (size_t)B * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -908,8 +934,8 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
     int overflow = 0;
     auto drain = [&](int64_t sub) -> int {  // wait for sub-batch `sub` and copy its results to the caller
         const int slot = (int)(sub % lm_ctx::NRES);
-        const int64_t s0 = sub * Bcap;
-        const int B = (int)std::min<int64_t>(Bcap, n - s0);
+        const int64_t s0 = sub * Bsub;
+        const int B = (int)std::min<int64_t>(Bsub, n - s0);
         CK(cudaEventSynchronize(ctx->ev_done[slot]));
         const uint8_t *h = ctx->h_res[slot];
         if (!direct) {
@@ -942,8 +968,8 @@ static int detect_batch_impl(lm_ctx *ctx, const uint8_t *frames, int frames_on_d
     auto issue_chain = [&](int64_t sub) -> int {  // every kernel of sub-batch `sub` + the D2H of its results
         int rc = LM_OK;
         const int slot = (int)(sub % nslot), ring = (int)(sub % lm_ctx::NRES), stg = (int)(sub & 1);
-        const int64_t s0 = sub * Bcap;
-        const int B = (int)std::min<int64_t>(Bcap, n - s0);
+        const int64_t s0 = sub * Bsub;
+        const int B = (int)std::min<int64_t>(Bsub, n - s0);
         cudaStream_t stf = streams[slot];   // front: min/max, LUT, crop
         const bool split = ctx->opt_streams > 1 && ctx->opt_back_priority;
         cudaStream_t st = split ? ctx->stream_back[slot] : stf;   // back: screen hand-over, sparse pass, tail, NMS, pairing, D2H
@@ -1117,7 +1143,11 @@ int lm_get_info(const lm_ctx *ctx, const char *name, double *value) {
         *value = (double)lm_screen2_last_macs();
         return LM_OK;
     }
-    if (!strcmp(name, "subbatch")) {
+    if (!strcmp(name, "subbatch")) {   // frames per sub-batch of the last lm_detect_batch call (before the first: the configured size)
+        *value = (double)(ctx->last_Bsub > 0 ? ctx->last_Bsub : ctx->opt_subbatch);
+        return LM_OK;
+    }
+    if (!strcmp(name, "scratch_subbatch")) {   // capacity the scratch sets are allocated for (grows on demand)
         *value = (double)ctx->Bcap;
         return LM_OK;
     }

@@ -1,16 +1,14 @@
 // k_screen2.cu — the tensor-core screen of k_screen.cu on CTA PAIRS (tcgen05 cta_group::2).
 //
-// Why: an SS-operand tcgen05.mma with M = 128 is bound by operand streaming from shared memory (A is 4 kB per
-// instruction whatever N is), and a single CTA can only keep ONE template's Toeplitz operand
-// resident (120 kB), i.e. N = 64.  A CTA pair executes one M = 256 instruction: each CTA streams its own 128
-// window rows (its own y tile of the same frame / x tile) and only HALF of B, so N doubles at the same
-// per-SM operand traffic:
+// Why: a single CTA can only keep ONE template's Toeplitz operand resident (120 kB), i.e. N = 64 per instruction, which the
+// tensor pipe executes in 32 cycles but which cannot be issued faster than every ~43-50 (tools/umma_pair_probe.cu).  A CTA pair
+// executes one M = 256 instruction: each CTA streams its own 128 window rows (its own y tile of the same frame / x tile) and
+// holds only HALF of B, so three templates fit and N = 192 runs at the tensor pipe's rate (96 cycles, 8187 MAC/clk/SM):
 //   paw + snout + tail job : N = 192 = 32 columns x [paw hi | paw lo | tail hi || snout hi | snout lo | tail lo]; the first
 //                            three planes live in CTA 0's shared memory, the others in CTA 1's.  x tiles right of the tail
-//                            box issue the same operands with N = 128 (each CTA's first two planes).
+//                            box issue the same operands with N = 128 (each CTA's first two planes, 64 cycles).
 //   paw + snout job        : N = 128 (templates whose sizes differ too much to share kernel-row steps with the tail)
 //   one-template job       : N = 64  = [hi || lo]; hi digits in CTA 0, lo digits in CTA 1.
-// An instruction costs ~max(93, 42 + N/2) cycles whatever it computes (operand streaming), so wide N is what pays.
 // y tiles: either whole 256-row tile pairs per frame, or -- when that wastes more (side view: 150 of 256 rows) --
 // "stacked": the sub-batch's windows, contiguous in memory at the window pitch, are treated as one tall image and cut
 // into 256-row tile pairs (179-row windows: 84 % useful rows instead of 59 %); a tile may straddle two frames, each

@@ -100,7 +100,11 @@ struct lm_ctx {
     struct BBScratch {
         int cap = 0;
         int32_t *minmax = nullptr;
-        uint8_t *lut = nullptr, *pred = nullptr, *stage = nullptr;
+        uint8_t *lut = nullptr, *pred = nullptr, *stage = nullptr, *diff = nullptr;
+        size_t diff_bytes = 0;
+        int32_t *calib_flip = nullptr;   // k_fold_calib's arrays for pass 1 (folded at every call: the background may have changed)
+        uint8_t *bkg_warp = nullptr, *run_mode = nullptr;
+        size_t fold_px = 0;
         uint32_t *hist = nullptr;
         double *bbx = nullptr;
         int32_t *lims = nullptr;
@@ -183,6 +187,10 @@ void free_scratch(lm_ctx *c) {
     cudaFree(c->bbs.lut);
     cudaFree(c->bbs.pred);
     cudaFree(c->bbs.stage);
+    cudaFree(c->bbs.diff);
+    cudaFree(c->bbs.calib_flip);
+    cudaFree(c->bbs.bkg_warp);
+    cudaFree(c->bbs.run_mode);
     cudaFree(c->bbs.hist);
     cudaFree(c->bbs.bbx);
     cudaFree(c->bbs.lims);
@@ -1239,7 +1247,35 @@ int lm_bounding_box_tm_de(lm_ctx *ctx, const uint8_t *frames, int frames_on_devi
         S.cap = cap;
     }
     if (!frames_on_device && !S.stage) CK(cudaMalloc((void **)&S.stage, (size_t)cap * fsz));
+    {   // the side view's raw differences of one chunk (one gather instead of two; see k_bb_hist)
+        const size_t need = (size_t)cap * p->side_w * p->side_h;
+        if (S.diff_bytes < need) {
+            cudaFree(S.diff);
+            S.diff = nullptr;
+            S.diff_bytes = 0;
+            CK(cudaMalloc((void **)&S.diff, need));
+            S.diff_bytes = need;
+        }
+    }
     cudaStream_t st = ctx->stream;
+    {   // calibration map with the mirror folded in, background seen through it, run flags (k_prep's vector tier, used by k_bb_hist16)
+        const size_t px = (size_t)k.n_rows * k.n_cols;
+        if (S.fold_px < px) {
+            cudaFree(S.calib_flip);
+            cudaFree(S.bkg_warp);
+            cudaFree(S.run_mode);
+            S.calib_flip = nullptr;
+            S.bkg_warp = S.run_mode = nullptr;
+            S.fold_px = 0;
+            CK(cudaMalloc((void **)&S.calib_flip, px * sizeof(int32_t)));
+            CK(cudaMalloc((void **)&S.bkg_warp, px + 32));
+            CK(cudaMalloc((void **)&S.run_mode, px));
+            CK(cudaMemsetAsync(S.bkg_warp, 0, px + 32, st));
+            S.fold_px = px;
+        }
+        if (lm_launch_fold_calib(ctx->d_calib, ctx->d_bkg, k.n_rows, k.n_cols, k.flip, S.calib_flip, S.bkg_warp, S.run_mode, st) < 0)
+            return fail(ctx, LM_ERR_RUNTIME, "calibration fold launch failed");
+    }
     // results for the whole call stay on the device until the end: chunks run back to back without a host sync
     double *d_bbx = nullptr;
     int32_t *d_lims = nullptr;
@@ -1265,6 +1301,9 @@ int lm_bounding_box_tm_de(lm_ctx *ctx, const uint8_t *frames, int frames_on_devi
         b.imadjust = 0;  // LocoMouse::readFrame(I), not LocoMouse_TM::readFrame (LocoMouse_TM_DE.cpp:36)
         b.minmax = S.minmax;
         b.lut = S.lut;
+        b.calib_flip = S.calib_flip;
+        b.bkg_warp = S.bkg_warp;
+        b.run_mode = S.run_mode;
         if (frames_on_device) {
             b.frames = frames + s0 * fsz;
         } else {
@@ -1273,7 +1312,7 @@ int lm_bounding_box_tm_de(lm_ctx *ctx, const uint8_t *frames, int frames_on_devi
                 rc = fail(ctx, LM_ERR_RUNTIME, "H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
             b.frames = S.stage;
         }
-        if (rc == LM_OK && lm_launch_bbox_tm_de(b, *p, S.hist, S.pred, d_bbx + s0, d_lims + s0 * 2, st) < 0)
+        if (rc == LM_OK && lm_launch_bbox_tm_de(b, *p, S.hist, S.pred, d_bbx + s0, d_lims + s0 * 2, st, S.diff) < 0)
             rc = fail(ctx, LM_ERR_RUNTIME, "bounding-box launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (rc == LM_OK && cudaMemcpyAsync(bb_x_raw, d_bbx, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess)

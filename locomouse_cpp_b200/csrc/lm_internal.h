@@ -146,10 +146,10 @@ int lm_launch_tail(const LmBatch &b, cudaStream_t s);
 int lm_launch_nms(const LmBatch &b, cudaStream_t s);
 int lm_launch_pair(const LmBatch &b, cudaStream_t s);
 int lm_launch_bbox_tm_de(const LmBatch &b, const lm_bb_de_params &p, uint32_t *hist, uint8_t *pred, double *bb_x, int32_t *lims,
-                         cudaStream_t s);
+                         cudaStream_t s, uint8_t *diff = nullptr);
 
 // pass 1 of the base class (k_bbox_base.cu)
-int lm_launch_bbox_pred(const LmBatch &b, const lm_bb_de_params &p, uint32_t *hist, uint8_t *pred, cudaStream_t s);
+int lm_launch_bbox_pred(const LmBatch &b, const lm_bb_de_params &p, uint32_t *hist, uint8_t *pred, cudaStream_t s, uint8_t *diff = nullptr);
 // pass 1 of LocoMouse_TM (k_bbox_tm.cu); returns the number of launches, -1 on a launch error, -2 when the side view's bit
 // image does not fit into shared memory
 size_t lm_bbox_tm_bits_bytes(const lm_bb_tm_params &p, int B);

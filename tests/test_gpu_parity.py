@@ -133,6 +133,36 @@ def test_subbatch_split_and_device_frames_invariance(oracle, monkeypatch):
     assert small.checksum() == small_dev.checksum() == big.checksum() == pinned.checksum() == ref.checksum()
 
 
+def test_scratch_grows_on_demand_and_short_host_videos_are_cut_in_two(oracle):
+    """A short video in host memory runs as two sub-batches (second half's copy under the first half's kernels) in two small
+    scratch sets; a later, longer resident call re-allocates the scratch once (all sets, bigger sub-batches) and a short call
+    after that reuses it.  Results never change."""
+    import torch
+
+    spec = synth.SynthSpec()
+    cfg, model, bkg, calib, frames, bx, bs, bb = synth.make_problem(spec, 150, seed=1011)
+    fnp = frames.numpy()
+    ref = oracle.detect(cfg, model, bkg, calib, fnp, bx, bs, bb, n_threads=8)
+    det = _detector(cfg, model, bkg, calib)
+    det.set_option("subbatch", 256)
+    a = det.detect_batch(fnp[:70], bx[:70], bs[:70], bb[:70])
+    assert det.info("subbatch") == 64.0 and det.info("scratch_subbatch") == 64.0
+    for name in Results.ARRAYS:
+        assert np.array_equal(getattr(a, name)[:70], getattr(ref, name)[:70]), name
+    b = det.detect_batch(frames.cuda(), bx, bs, bb)                       # 150 resident frames: sub-batches of 128, capacity grows
+    assert det.info("subbatch") == 128.0 and det.info("scratch_subbatch") == 128.0
+    assert diff_results(b, ref) == []
+    c = det.detect_batch(fnp[:70], bx[:70], bs[:70], bb[:70])             # the small call again, in the big scratch
+    assert det.info("subbatch") == 64.0 and det.info("scratch_subbatch") == 128.0
+    for name in Results.ARRAYS:
+        assert np.array_equal(getattr(c, name)[:70], getattr(a, name)[:70]), name
+    d = det.detect_batch(fnp, bx, bs, bb)                                 # host frames: half the configured sub-batch
+    assert det.info("subbatch") == 128.0
+    assert diff_results(d, ref) == []
+    det.close()
+    torch.cuda.synchronize()
+
+
 def test_tail_slow_path_equals_fast_path(oracle, monkeypatch):
     """k_tail labels runs in shared memory; frames with more runs than its capacity take the pixel-based
     global-memory kernel.  Force that path (capacity 4) and compare with the oracle and the fast path."""

@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[0] / configs[4] / density side measurements")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--shard-weights", default="", help="N > 1: comma-separated per-rank weights for the end-to-end job's shards instead of the measured host rates")
+    ap.add_argument("--nccl-gather", action="store_true", help="N > 1: move the result records to rank 0 with an NCCL gather instead of shared host memory")
     ap.add_argument("--even-shards", action="store_true", help="N > 1: keep the end-to-end job evenly split even when the ranks' measured host rates differ")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="library option for the measured arm (lm_set_option), e.g. streams=3")
     args = ap.parse_args()
@@ -530,6 +531,18 @@ def main():
                 e_bx, e_bs, e_bb = (np.resize(a, n_e) for a in (bx, bs, bb))
                 e_res = Results(n_e, cfg.cand_cap, cfg.match_cap, cfg.n_tail_points, pinned=True)
             e_host = host[:n_e]
+            gather_mode = "none"
+            if world > 1:
+                gather_mode = "nccl"
+                if not args.nccl_gather:
+                    # one box: every rank's result buffers live in named, page-locked shared memory and rank 0 reads them in
+                    # place; the 11 kB per frame of fixed-capacity records do not cross PCIe again on their way to rank 0's host
+                    try:
+                        e_res = sharding.shared_results(n_e, cfg.cand_cap, cfg.match_cap, cfg.n_tail_points, rank,
+                                                        tag=os.environ.get("MASTER_PORT", "0"))
+                        gather_mode = "shared-memory" if getattr(e_res, "_shm_pinned", False) else "shared-memory (not page-locked)"
+                    except Exception as ex:  # pragma: no cover
+                        sys.stderr.write(f"shared result buffers unavailable ({ex!r}); gathering over NCCL\n")
 
             def e2e_step():
                 r = det.detect_batch(e_host, e_bx, e_bs, e_bb, results=e_res)
@@ -555,9 +568,9 @@ def main():
                    "frac_of_ceiling": (world * n * cfg.vid_rows * cfg.vid_cols * args.steps / ew / 1e9 /
                                        ceiling["aggregate_gbs_by_slowest"])
                    if ceiling and ceiling.get("aggregate_gbs_by_slowest") else None,
-                   "h2d_ceiling": ceiling, "frames_per_rank": counts,
+                   "h2d_ceiling": ceiling, "frames_per_rank": counts, "gather": gather_mode,
                    "note": f"frames in pinned host memory, copied H2D inside the call (overlapped with compute per {subb}-frame "
-                           "sub-batch); results copied D2H" + ("; candidate lists gathered to rank 0 over NCCL" if world > 1 else "") +
+                           "sub-batch); results copied D2H" + ("; rank 0 reads every rank's records (see `gather`)" if world > 1 else "") +
                            "; h2d_ceiling = bare concurrent cudaMemcpyAsync of the same page-locked frames on every rank, N x the slowest rank's rate"}
         except Exception as ex:  # pragma: no cover
             e2e = {"value": None, "unit": UNIT, "error": repr(ex)}

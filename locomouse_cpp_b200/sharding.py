@@ -152,14 +152,86 @@ def concat(parts) -> Results:
 
 
 _GATHER_CACHE = {}
+_SHM_OWN = {}      # path -> (np.memmap, pinned pointer or None): segments this process created
+_SHM_PEER = {}     # path -> np.memmap: other ranks' segments rank 0 has mapped
+
+
+def _shm_path(tag: str, rank: int) -> str:
+    import os
+    import tempfile
+
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    return os.path.join(d, f"lmres-{tag}-{rank}")
+
+
+def shared_results(n: int, cand_cap: int, match_cap: int, n_tail_points: int, rank: int, tag: str, pin: bool = True) -> Results:
+    """Result buffers for `n` frames in a named shared-memory file (page-locked when a CUDA device is present and `pin`):
+    lm_detect_batch writes into them like into any page-locked arrays, and on a single box rank 0 reads every rank's records in
+    place (gather_to_rank0 recognises such Results) -- the fixed-capacity records (11 kB per frame) then never cross PCIe a
+    second and third time on their way to the host tracker.  `tag` must be the same on every rank of the job and unique per
+    job (e.g. the rendezvous port)."""
+    import atexit
+    import os
+
+    nbytes = Results.raw_nbytes(n, cand_cap, match_cap, n_tail_points)
+    path = _shm_path(tag, rank)
+    old = _SHM_OWN.pop(path, None)
+    if old is not None:
+        _release_own(path, old)
+    if os.path.exists(path):   # left over from a run that died
+        os.unlink(path)
+    buf = np.memmap(path, dtype=np.uint8, mode="w+", shape=(nbytes,))
+    buf[:] = 0
+    pinned = None
+    if pin:
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                if int(torch.cuda.cudart().cudaHostRegister(buf.ctypes.data, nbytes, 0)) == 0:
+                    pinned = buf.ctypes.data
+        except Exception:
+            pinned = None
+    if not _SHM_OWN:
+        atexit.register(_release_all)
+    _SHM_OWN[path] = (buf, pinned)
+    res = Results(n, cand_cap, match_cap, n_tail_points, buffer=buf)
+    res._shm_tag = tag
+    res._shm_pinned = pinned is not None
+    return res
+
+
+def _release_own(path, entry):
+    import os
+
+    _buf, pinned = entry
+    try:
+        if pinned is not None:
+            import torch
+
+            torch.cuda.cudart().cudaHostUnregister(pinned)
+    except Exception:
+        pass
+    try:
+        os.unlink(path)
+    except OSError:
+        pass
+
+
+def _release_all():
+    _SHM_PEER.clear()
+    for path, entry in list(_SHM_OWN.items()):
+        _release_own(path, entry)
+    _SHM_OWN.clear()
 
 
 def gather_to_rank0(res: Results, device=None):
     """Gather every rank's Results on rank 0 (list in rank order; None elsewhere).
 
-    Equal frame counts on all ranks (the usual case): every rank's contiguous result buffer (Results.raw, fixed size)
-    moves with ONE collective and rank 0 adopts the received buffers as Results views -- no per-entry host work.
-    Ragged counts: compact payloads (pack / unpack), sizes exchanged first."""
+    Results created by shared_results (named shared memory, ranks of one box): rank 0 maps the peers' buffers, nothing moves.
+    Otherwise, equal frame counts on all ranks: every rank's contiguous result buffer (Results.raw, fixed size) moves with ONE
+    collective and rank 0 adopts the received buffers as Results views -- no per-entry host work.  Unequal counts on GPU ranks:
+    the same buffers point to point.  Unequal counts on CPU ranks: compact payloads (pack / unpack), sizes exchanged first."""
     import torch
     import torch.distributed as dist
 
@@ -169,6 +241,30 @@ def gather_to_rank0(res: Results, device=None):
     metas = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(metas, meta)
     metas = [tuple(int(v) for v in m.tolist()) for m in metas]
+    tag = getattr(res, "_shm_tag", None)
+    if tag is not None:
+        # Results in named shared memory (shared_results): the all_gather above ordered every rank's writes before this point;
+        # one more collective tells rank 0 whether all ranks use the shared path, then it maps the peers' segments.
+        flag = torch.tensor([1], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            if rank != 0:
+                return None
+            out = []
+            for r, m in enumerate(metas):
+                if r == 0:
+                    out.append(res)
+                    continue
+                path = _shm_path(tag, r)
+                nbytes = Results.raw_nbytes(m[0], m[1], m[2], m[3])
+                # mapped anew at every call (microseconds): a rank may have re-created its file since the last one
+                mm = _SHM_PEER[path] = np.memmap(path, dtype=np.uint8, mode="r+", shape=(nbytes,))
+                out.append(Results(m[0], m[1], m[2], m[3], buffer=mm))
+            return out
+    if tag is None:
+        # keep the collective sequence identical on ranks that do and do not use shared results (mixed use falls back below)
+        flag = torch.tensor([0], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if all(m == metas[0] for m in metas):
         n, cap, mcap, ntp = metas[0]
         if dev.type != "cuda":

@@ -71,7 +71,7 @@ def test_weighted_counts_follow_the_weights():
         sharding.weighted_counts(10, [1, 0])
 
 
-def _worker(rank, world, port, n, out_path, weights=None):
+def _worker(rank, world, port, n, out_path, weights=None, shared=False):
     import torch.distributed as dist
 
     from oracle import oracle
@@ -89,6 +89,10 @@ def _worker(rank, world, port, n, out_path, weights=None):
     prev = frames[f0 - 1] if f0 > 0 else None
     local = oracle.detect(cfg, model, bkg, calib, frames[f0:f1], bx[f0:f1], bs[f0:f1], bb[f0:f1], prev_frame=prev,
                           first_frame_index=f0)
+    if shared:   # result buffers in named shared memory: rank 0 reads the peers' records in place
+        sh = sharding.shared_results(local.n, local.cand_cap, local.match_cap, local.n_tail_points, rank, tag=str(port), pin=False)
+        sh.raw[:] = local.raw
+        local = sh
     parts = sharding.gather_to_rank0(local)
     if rank == 0:
         whole = sharding.concat(parts)
@@ -97,8 +101,8 @@ def _worker(rank, world, port, n, out_path, weights=None):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("weights", [None, (2.0, 1.0)])
-def test_two_rank_gloo_frame_sharding_equals_single_process(oracle, tmp_path, weights):
+@pytest.mark.parametrize("weights,shared", [(None, False), ((2.0, 1.0), False), (None, True), ((1.0, 2.0), True)])
+def test_two_rank_gloo_frame_sharding_equals_single_process(oracle, tmp_path, weights, shared):
     import torch.multiprocessing as mp
 
     n = 9
@@ -107,7 +111,7 @@ def test_two_rank_gloo_frame_sharding_equals_single_process(oracle, tmp_path, we
     port = s.getsockname()[1]
     s.close()
     out = str(tmp_path / "gathered.npy")
-    mp.spawn(_worker, args=(2, port, n, out, weights), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, n, out, weights, shared), nprocs=2, join=True)
     cfg, model, bkg, calib, frames, bx, bs, bb = _small_problem(n)
     ref = oracle.detect(cfg, model, bkg, calib, frames.numpy(), bx, bs, bb)
     got = np.load(out)

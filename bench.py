@@ -254,6 +254,12 @@ def main():
         stage[k] *= args.steps / isteps   # normalised to the number of timed steps, as the fields below assume
     ms_screen *= args.steps / isteps
     subb = int(det.info("subbatch"))   # sub-batch size of the resident passes above
+    # int8 MACs of the LAST launch of those passes (n - (nsub - 1) * subb frames), scaled to the average launch the roofline uses
+    try:
+        _last = n - ((n + subb - 1) // subb - 1) * subb
+        macs_per_avg_launch = float(det.info("screen_macs")) / _last * (n / ((n + subb - 1) // subb))
+    except Exception:
+        macs_per_avg_launch = 0.0
     det.set_option("streams", n_streams)
     det.detect_batch(frames[: min(n, 512)], bx[: min(n, 512)], bs[: min(n, 512)], bb[: min(n, 512)])
 
@@ -290,10 +296,7 @@ def main():
         """The int8 multiply-accumulates k_screen2 issues per launch (counted by the launcher from its job table) against
         the int8 tensor pipe: nominal 8192 MAC/clk/SM and the rate tools/umma_pair_probe measures on this GPU for the kernel's own
         instruction (tcgen05.mma.cta_group::2.kind::i8, M = 256, N = 192, same descriptors, no producer / epilogue)."""
-        try:
-            macs = float(det.info("screen_macs"))
-        except Exception:
-            return None
+        macs = macs_per_avg_launch
         if macs <= 0:
             return None
         tops = 2.0 * macs / (ms_per_launch * 1e-3) / 1e12

@@ -287,8 +287,14 @@ def main():
         ffma_measured = None
 
     def traffic_of(kernel):
+        """DRAM bytes of one launch from the round's ncu capture, scaled from the capture's frames per launch to this run's."""
         try:
-            return json.load(open(os.path.join(ROOT, "profiles", f"{kernel}_traffic.json"))).get("dram_bytes_per_launch")
+            j = json.load(open(os.path.join(ROOT, "profiles", f"{kernel}_traffic.json")))
+            per = j.get("dram_bytes_per_launch")
+            fpl = j.get("frames_per_launch")
+            if per is None:
+                return None
+            return int(per * (n / nsub) / fpl) if fpl else per
         except Exception:
             return None
 

@@ -216,13 +216,14 @@ struct LmDevOnce {
         return !done[dev].exchange(true);
     }
 };
-// The SM's L1 / shared-memory split is a per-SM setting that can only change while the SM is idle.  k_screen2 needs the largest
-// shared-memory carve-out; a kernel that prefers another split cannot join an SM the screen runs on (measured: every other
-// kernel of the pipeline then costs its full stand-alone time on top of the screen's).  The pipeline's kernels therefore all
-// ask for the same split.  LM_CARVEOUT=0 (what-if runs) leaves the driver's default.
+// The SM's L1 / shared-memory split is a per-SM setting.  Hypothesis tested in round 2: a kernel that prefers another split than
+// k_screen2's (the largest shared-memory carve-out) cannot join an SM the screen runs on.  Measured: it can (tools/
+// coresidency_probe.cu; what decides is registers per SM sub-partition and the shared memory left), and asking every kernel of the
+// pipeline for the screen's split changed nothing (0.900 vs 0.904 ms per sub-batch) while taking L1 away from k_prep's gathers.
+// The preference is therefore OFF by default; LM_CARVEOUT=1 turns it on for what-if runs.
 template <class F>
 inline void lm_prefer_max_shared(F *kernel) {
-    static const bool on = !(getenv("LM_CARVEOUT") && atoi(getenv("LM_CARVEOUT")) == 0);
+    static const bool on = getenv("LM_CARVEOUT") && atoi(getenv("LM_CARVEOUT")) != 0;
     if (on) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 }
 inline int lm_sm_count() {

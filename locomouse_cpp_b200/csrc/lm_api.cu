@@ -1608,7 +1608,7 @@ int lm_debug_nms(lm_ctx *ctx, int view, int feat, const float *scores, lm_cand *
     if (!ctx->configured || !ctx->model_set) return fail(ctx, LM_ERR_STATE, "lm_debug_nms needs lm_configure and lm_set_model first");
     if (view < 0 || view > 1 || feat < 0 || feat > 1 || !scores || !out) return fail(ctx, LM_ERR_INVALID, "lm_debug_nms: bad argument");
     DeviceGuard guard(ctx->device);
-    int rc = prepare(ctx);
+    int rc = prepare(ctx, 64, 2);   // one frame's lists: the smallest scratch set will do (grows later if a detection call needs more)
     if (rc) {
         free_scratch(ctx);
         return rc;
